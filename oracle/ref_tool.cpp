@@ -1,0 +1,768 @@
+// TEST INFRASTRUCTURE ONLY (oracle/_ref build).
+//
+// Command-line driver around the reference's OWN hot-path code, compiled unmodified from
+// $(REF)/tangerine and $(REF)/third_party (see oracle/Makefile).  It exists to
+//   * turn the reference's Lua models into portable tree files (.tgm) for the tests,
+//   * produce golden vectors (raw SDF samples, gradients, material colours, octree programs,
+//     exported PLY / STL / VOX files) from the reference implementation itself,
+//   * time the reference CPU export path (bench.py --impl reference, cpu_baseline kind "reference").
+//
+// The first include pulls in the reference's sdf_evaluator.cpp *textually, unmodified, from where it
+// lies*: the node classes (BrushNode, SetNode, FlateNode, StencilMaskNode) are private to that
+// translation unit, and the tree dumper / loader below needs to see them.  Nothing from the
+// reference is copied into this repository.
+
+#include REF_SDF_EVALUATOR_CPP
+
+#include <cstdio>
+#include <cstring>
+#include <cstdint>
+#include <chrono>
+#include <map>
+#include <thread>
+#include <atomic>
+#include <fstream>
+#include <surface_nets.h>
+
+#include "lua_env.h"
+#include "export.h"
+#include "magica.h"
+
+extern SDFNodeShared g_CapturedTree;
+extern std::atomic_bool ExportActive;
+extern std::atomic_int ExportState;
+extern std::atomic_int GenerationProgress;
+extern std::atomic_int RefinementProgress;
+extern std::atomic_int SecondaryProgress;
+extern std::atomic_int WriteProgress;
+void ExportCommon(SDFNodeShared Evaluator, float GridSize, int RefineIterations, const char* Path, ExportFormat Format, float Scale);
+void MeshExportThread(SDFNodeShared Evaluator, vec3 ModelMin, vec3 ModelMax, vec3 Step, int RefineIterations, std::string Path, ExportFormat Format, float Scale);
+void PointCloudExportThread(SDFNodeShared Evaluator, vec3 ModelMin, vec3 ModelMax, vec3 Step, int RefineIterations, std::string Path, ExportFormat Format, float Scale);
+
+using Clock = std::chrono::steady_clock;
+static double Seconds(Clock::time_point A, Clock::time_point B)
+{
+	return std::chrono::duration<double>(B - A).count();
+}
+
+// ------------------------------------------------------------------------------------------------
+// .tgm tree files (format documented in tangerine_b200/host/tgm.h)
+// ------------------------------------------------------------------------------------------------
+
+static const uint32_t TGM_NONE = 0xFFFFFFFFu;
+static const uint32_t TGM_STENCIL_POS = 100; // StencilMaskNode<false>
+static const uint32_t TGM_STENCIL_NEG = 101; // StencilMaskNode<true>
+
+struct TgmNode
+{
+	uint32_t Kind;
+	uint32_t A;
+	uint32_t B;
+	uint32_t Material;
+	float Params[4];
+	float Quat[4]; // w x y z
+	float Trans[3];
+	float Scale;
+	float BoundsMin[3];
+	float BoundsMax[3];
+};
+static_assert(sizeof(TgmNode) == 88);
+
+struct TgmWriter
+{
+	std::vector<TgmNode> Nodes;
+	std::vector<vec3> MaterialColors;
+	std::map<MaterialInterface*, uint32_t> MaterialIds;
+
+	uint32_t MaterialId(MaterialShared& Material)
+	{
+		if (!Material)
+		{
+			return TGM_NONE;
+		}
+		auto Found = MaterialIds.find(Material.get());
+		if (Found != MaterialIds.end())
+		{
+			return Found->second;
+		}
+		// The export path only ever looks at SampleColor(GuessColor()) (export.cpp:303-311).
+		vec3 Color = SampleColor(Material->GuessColor());
+		uint32_t Id = uint32_t(MaterialColors.size());
+		MaterialColors.push_back(Color);
+		MaterialIds[Material.get()] = Id;
+		return Id;
+	}
+
+	template<typename BrushT>
+	bool TryBrush(SDFNode* Node, uint32_t& OutIndex)
+	{
+		BrushT* Brush = dynamic_cast<BrushT*>(Node);
+		if (!Brush)
+		{
+			return false;
+		}
+		TgmNode Rec = {};
+		Rec.Kind = uint32_t(Brush->Opcode);
+		Rec.A = TGM_NONE;
+		Rec.B = TGM_NONE;
+		Rec.Material = MaterialId(Brush->Material);
+		for (size_t i = 0; i < Brush->NodeParams.size(); ++i)
+		{
+			Rec.Params[i] = Brush->NodeParams[i];
+		}
+		Rec.Quat[0] = Brush->LocalToWorld.Rotation.w;
+		Rec.Quat[1] = Brush->LocalToWorld.Rotation.x;
+		Rec.Quat[2] = Brush->LocalToWorld.Rotation.y;
+		Rec.Quat[3] = Brush->LocalToWorld.Rotation.z;
+		for (int i = 0; i < 3; ++i)
+		{
+			Rec.Trans[i] = Brush->LocalToWorld.Translation[i];
+			Rec.BoundsMin[i] = Brush->BrushAABB.Min[i];
+			Rec.BoundsMax[i] = Brush->BrushAABB.Max[i];
+		}
+		Rec.Scale = Brush->LocalToWorld.Scalation;
+		OutIndex = uint32_t(Nodes.size());
+		Nodes.push_back(Rec);
+		return true;
+	}
+
+	template<SetFamily Family, bool Blend>
+	bool TrySet(SDFNode* Node, uint32_t& OutIndex)
+	{
+		auto* Set = dynamic_cast<SetNode<Family, Blend>*>(Node);
+		if (!Set)
+		{
+			return false;
+		}
+		TgmNode Rec = {};
+		Rec.Kind = uint32_t(Set->Opcode);
+		Rec.A = Visit(Set->LHS.get());
+		Rec.B = Visit(Set->RHS.get());
+		Rec.Material = TGM_NONE;
+		Rec.Params[0] = Set->Threshold;
+		Rec.Quat[0] = 1.0f;
+		Rec.Scale = 1.0f;
+		OutIndex = uint32_t(Nodes.size());
+		Nodes.push_back(Rec);
+		return true;
+	}
+
+	template<bool ApplyToNegative>
+	bool TryStencil(SDFNode* Node, uint32_t& OutIndex)
+	{
+		auto* Stencil = dynamic_cast<StencilMaskNode<ApplyToNegative>*>(Node);
+		if (!Stencil)
+		{
+			return false;
+		}
+		TgmNode Rec = {};
+		Rec.Kind = ApplyToNegative ? TGM_STENCIL_NEG : TGM_STENCIL_POS;
+		Rec.A = Visit(Stencil->Child.get());
+		Rec.B = Visit(Stencil->StencilMask.get());
+		Rec.Material = MaterialId(Stencil->Material);
+		Rec.Quat[0] = 1.0f;
+		Rec.Scale = 1.0f;
+		OutIndex = uint32_t(Nodes.size());
+		Nodes.push_back(Rec);
+		return true;
+	}
+
+	uint32_t Visit(SDFNode* Node)
+	{
+		uint32_t Index = TGM_NONE;
+		if (TryBrush<BrushNode<std::array<float, 1>>>(Node, Index)) return Index;
+		if (TryBrush<BrushNode<std::array<float, 2>>>(Node, Index)) return Index;
+		if (TryBrush<BrushNode<std::array<float, 3>>>(Node, Index)) return Index;
+		if (TrySet<SetFamily::Union, false>(Node, Index)) return Index;
+		if (TrySet<SetFamily::Union, true>(Node, Index)) return Index;
+		if (TrySet<SetFamily::Inter, false>(Node, Index)) return Index;
+		if (TrySet<SetFamily::Inter, true>(Node, Index)) return Index;
+		if (TrySet<SetFamily::Diff, false>(Node, Index)) return Index;
+		if (TrySet<SetFamily::Diff, true>(Node, Index)) return Index;
+		if (FlateNode* Flate = dynamic_cast<FlateNode*>(Node))
+		{
+			TgmNode Rec = {};
+			Rec.Kind = uint32_t(OpcodeT::Flate);
+			Rec.A = Visit(Flate->Child.get());
+			Rec.B = TGM_NONE;
+			Rec.Material = TGM_NONE;
+			Rec.Params[0] = Flate->Radius;
+			Rec.Quat[0] = 1.0f;
+			Rec.Scale = 1.0f;
+			Index = uint32_t(Nodes.size());
+			Nodes.push_back(Rec);
+			return Index;
+		}
+		if (TryStencil<false>(Node, Index)) return Index;
+		if (TryStencil<true>(Node, Index)) return Index;
+		std::fprintf(stderr, "tgm: unknown node class\n");
+		std::exit(2);
+	}
+
+	bool Write(SDFNodeShared& Tree, const char* Path)
+	{
+		uint32_t Root = Visit(Tree.get());
+		FILE* File = std::fopen(Path, "wb");
+		if (!File)
+		{
+			return false;
+		}
+		uint32_t Header[4] = { 0x314D4754u /* "TGM1" */, uint32_t(Nodes.size()), uint32_t(MaterialColors.size()), Root };
+		std::fwrite(Header, 4, 4, File);
+		for (vec3& Color : MaterialColors)
+		{
+			std::fwrite(&Color, 4, 3, File);
+		}
+		std::fwrite(Nodes.data(), sizeof(TgmNode), Nodes.size(), File);
+		std::fclose(File);
+		return true;
+	}
+};
+
+
+// A material whose only property is the colour recorded in a .tgm file.
+static std::vector<MaterialShared> g_TgmMaterials;
+
+static SDFNodeShared TgmBuild(const std::vector<TgmNode>& Nodes, uint32_t Index)
+{
+	const TgmNode& Rec = Nodes[Index];
+	MaterialShared Material = (Rec.Material == TGM_NONE) ? nullptr : g_TgmMaterials[Rec.Material];
+	auto SetXform = [&](auto* Brush)
+	{
+		Brush->LocalToWorld.Rotation = quat(Rec.Quat[0], Rec.Quat[1], Rec.Quat[2], Rec.Quat[3]);
+		Brush->LocalToWorld.Translation = vec3(Rec.Trans[0], Rec.Trans[1], Rec.Trans[2]);
+		Brush->LocalToWorld.Scalation = Rec.Scale;
+		Brush->BrushAABB.Min = vec3(Rec.BoundsMin[0], Rec.BoundsMin[1], Rec.BoundsMin[2]);
+		Brush->BrushAABB.Max = vec3(Rec.BoundsMax[0], Rec.BoundsMax[1], Rec.BoundsMax[2]);
+		Brush->Material = Material;
+	};
+	const float* P = Rec.Params;
+	SDFNodeShared Node;
+	switch (Rec.Kind)
+	{
+	case uint32_t(OpcodeT::Sphere): Node = SDF::Sphere(P[0]); break;
+	case uint32_t(OpcodeT::Ellipsoid): Node = SDF::Ellipsoid(P[0], P[1], P[2]); break;
+	case uint32_t(OpcodeT::Box): Node = SDF::Box(P[0], P[1], P[2]); break;
+	case uint32_t(OpcodeT::Torus): Node = SDF::Torus(P[0], P[1]); break;
+	case uint32_t(OpcodeT::Cylinder): Node = SDF::Cylinder(P[0], P[1]); break;
+	case uint32_t(OpcodeT::Cone):
+	{
+		// Params are (Tangent, Height); build the node directly so they are not re-derived.
+		std::array<float, 2> Params = { P[0], P[1] };
+		BrushMixin Eval = std::bind(SDFMath::Cone, _1, P[0], P[1]);
+		AABB Bounds = {};
+		Node = SDFNodeShared(new BrushNode(OpcodeT::Cone, Params, Eval, Bounds));
+		break;
+	}
+	case uint32_t(OpcodeT::Coninder):
+	{
+		std::array<float, 3> Params = { P[0], P[1], P[2] };
+		BrushMixin Eval = std::bind(SDFMath::Coninder, _1, P[0], P[1], P[2]);
+		AABB Bounds = {};
+		Node = SDFNodeShared(new BrushNode(OpcodeT::Coninder, Params, Eval, Bounds));
+		break;
+	}
+	case uint32_t(OpcodeT::Plane):
+	{
+		std::array<float, 3> Params = { P[0], P[1], P[2] };
+		using PlanePtr = float(*)(vec3, vec3);
+		BrushMixin Eval = std::bind((PlanePtr)SDFMath::Plane, _1, vec3(P[0], P[1], P[2]));
+		AABB Bounds = {};
+		Node = SDFNodeShared(new BrushNode(OpcodeT::Plane, Params, Eval, Bounds));
+		break;
+	}
+	case uint32_t(OpcodeT::Union):
+	case uint32_t(OpcodeT::Inter):
+	case uint32_t(OpcodeT::Diff):
+	case uint32_t(OpcodeT::BlendUnion):
+	case uint32_t(OpcodeT::BlendInter):
+	case uint32_t(OpcodeT::BlendDiff):
+	{
+		SDFNodeShared LHS = TgmBuild(Nodes, Rec.A);
+		SDFNodeShared RHS = TgmBuild(Nodes, Rec.B);
+		switch (Rec.Kind)
+		{
+		case uint32_t(OpcodeT::Union): return SDF::Union(LHS, RHS);
+		case uint32_t(OpcodeT::Inter): return SDF::Inter(LHS, RHS);
+		case uint32_t(OpcodeT::Diff): return SDF::Diff(LHS, RHS);
+		case uint32_t(OpcodeT::BlendUnion): return SDF::BlendUnion(P[0], LHS, RHS);
+		case uint32_t(OpcodeT::BlendInter): return SDF::BlendInter(P[0], LHS, RHS);
+		default: return SDF::BlendDiff(P[0], LHS, RHS);
+		}
+	}
+	case uint32_t(OpcodeT::Flate):
+	{
+		SDFNodeShared Child = TgmBuild(Nodes, Rec.A);
+		return SDF::Flate(Child, P[0]);
+	}
+	case TGM_STENCIL_POS:
+	case TGM_STENCIL_NEG:
+	{
+		SDFNodeShared Child = TgmBuild(Nodes, Rec.A);
+		SDFNodeShared Mask = TgmBuild(Nodes, Rec.B);
+		return SDF::Stencil(Child, Mask, Material, Rec.Kind == TGM_STENCIL_NEG);
+	}
+	default:
+		std::fprintf(stderr, "tgm: bad node kind %u\n", Rec.Kind);
+		std::exit(2);
+	}
+	// Brush fall-through: install transform, bounds and paint exactly as recorded.
+	if (auto* B1 = dynamic_cast<BrushNode<std::array<float, 1>>*>(Node.get())) SetXform(B1);
+	else if (auto* B2 = dynamic_cast<BrushNode<std::array<float, 2>>*>(Node.get())) SetXform(B2);
+	else if (auto* B3 = dynamic_cast<BrushNode<std::array<float, 3>>*>(Node.get())) SetXform(B3);
+	return Node;
+}
+
+static SDFNodeShared TgmLoad(const char* Path)
+{
+	FILE* File = std::fopen(Path, "rb");
+	if (!File)
+	{
+		return nullptr;
+	}
+	uint32_t Header[4];
+	if (std::fread(Header, 4, 4, File) != 4 || Header[0] != 0x314D4754u)
+	{
+		std::fclose(File);
+		return nullptr;
+	}
+	g_TgmMaterials.clear();
+	for (uint32_t i = 0; i < Header[2]; ++i)
+	{
+		vec3 Color;
+		if (std::fread(&Color, 4, 3, File) != 3) return nullptr;
+		g_TgmMaterials.push_back(MaterialShared(new MaterialPBRBR(ColorPoint(Color))));
+	}
+	std::vector<TgmNode> Nodes(Header[1]);
+	if (std::fread(Nodes.data(), sizeof(TgmNode), Nodes.size(), File) != Nodes.size()) return nullptr;
+	std::fclose(File);
+	return TgmBuild(Nodes, Header[3]);
+}
+
+
+static bool EndsWith(const std::string& Text, const char* Suffix)
+{
+	size_t Len = std::strlen(Suffix);
+	return Text.size() >= Len && Text.compare(Text.size() - Len, Len, Suffix) == 0;
+}
+
+
+static SDFNodeShared LoadModel(const std::string& Path)
+{
+	if (EndsWith(Path, ".tgm"))
+	{
+		return TgmLoad(Path.c_str());
+	}
+	LuaEnvironment* Env = new LuaEnvironment();
+	Env->LoadFromPath(Path);
+	// Env is leaked on purpose: the tree holds references into the Lua-owned material table.
+	return g_CapturedTree;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Octree dump / checksum
+// ------------------------------------------------------------------------------------------------
+
+static uint64_t Fnv(uint64_t Hash, const void* Data, size_t Bytes)
+{
+	const uint8_t* Cursor = static_cast<const uint8_t*>(Data);
+	for (size_t i = 0; i < Bytes; ++i)
+	{
+		Hash ^= Cursor[i];
+		Hash *= 0x100000001B3ull;
+	}
+	return Hash;
+}
+
+struct OctreeStats
+{
+	uint64_t Nodes = 0;
+	uint64_t Leaves = 0;
+	uint64_t Words = 0;
+	uint64_t LeafWords = 0;
+	uint64_t MaxWords = 0;
+	uint64_t MaxStack = 0;
+	uint64_t Hash = 0xCBF29CE484222325ull;
+	FILE* Dump = nullptr;
+};
+
+// Pre-order walk; per node hashes (pivot, terminus, child mask, program words).  With Dump set,
+// writes the same fields as: f32 pivot[3], u32 terminus, u32 childmask, u32 nwords, u32 words[].
+static void WalkOctree(SDFOctree* Node, OctreeStats& Stats)
+{
+	uint32_t ChildMask = 0;
+	for (int i = 0; i < 8; ++i)
+	{
+		if (Node->Children[i]) ChildMask |= (1u << i);
+	}
+	uint32_t Terminus = Node->Terminus ? 1 : 0;
+	const std::vector<ProgramBuffer::Word>& Words = Node->Interpreter->Program.Words;
+	uint32_t WordCount = uint32_t(Words.size());
+	Stats.Nodes++;
+	Stats.Words += WordCount;
+	if (Terminus)
+	{
+		Stats.Leaves++;
+		Stats.LeafWords += WordCount;
+	}
+	Stats.MaxWords = std::max<uint64_t>(Stats.MaxWords, WordCount);
+	Stats.MaxStack = std::max<uint64_t>(Stats.MaxStack, Node->Interpreter->StackSize);
+	Stats.Hash = Fnv(Stats.Hash, &Node->Pivot, 12);
+	Stats.Hash = Fnv(Stats.Hash, &Terminus, 4);
+	Stats.Hash = Fnv(Stats.Hash, &ChildMask, 4);
+	Stats.Hash = Fnv(Stats.Hash, Words.data(), WordCount * 4);
+	if (Stats.Dump)
+	{
+		std::fwrite(&Node->Pivot, 4, 3, Stats.Dump);
+		std::fwrite(&Terminus, 4, 1, Stats.Dump);
+		std::fwrite(&ChildMask, 4, 1, Stats.Dump);
+		std::fwrite(&WordCount, 4, 1, Stats.Dump);
+		std::fwrite(Words.data(), 4, WordCount, Stats.Dump);
+	}
+	for (int i = 0; i < 8; ++i)
+	{
+		if (Node->Children[i]) WalkOctree(Node->Children[i], Stats);
+	}
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Commands
+// ------------------------------------------------------------------------------------------------
+
+static int Usage()
+{
+	std::fprintf(stderr,
+		"usage: tangerine_ref <command> ...\n"
+		"  dump-tgm  <model.lua|.tgm> <out.tgm>\n"
+		"  info      <model>                                  bounds / tree / octree statistics + hash (JSON)\n"
+		"  octree    <model> <out.bin>                        dump every octree node's pruned program\n"
+		"  eval      <model> <mode> <points.f32> <out.bin>    mode: octree | tree | interp | gradient | color | clipnull\n"
+		"  export    <model> <cells_per_unit> <refine> <out.ply|.stl>   reference ExportCommon (as shipped)\n"
+		"  export-grid <model> <minx miny minz maxx maxy maxz> <step> <refine> <pointcloud 0|1> <out.ply|.stl>\n"
+		"  vox       <model> <grid_size> <color_index> <out.vox>\n"
+		"  bench     <model> <minx..maxz> <step> <threads> <slice_stride> reference thunks on std::threads (JSON)\n");
+	return 1;
+}
+
+
+static int CmdInfo(SDFNodeShared Tree)
+{
+	AABB Bounds = Tree->Bounds();
+	SDFInterpreter Root(Tree);
+	auto T0 = Clock::now();
+	SDFOctreeShared Octree = SDFOctree::Create(Tree, 0.25);
+	auto T1 = Clock::now();
+	OctreeStats Stats;
+	if (Octree)
+	{
+		WalkOctree(Octree.get(), Stats);
+	}
+	std::printf("{\"bounds_min\": [%.9g, %.9g, %.9g], \"bounds_max\": [%.9g, %.9g, %.9g], \"leaf_count\": %d, "
+		"\"stack_size\": %zu, \"root_words\": %zu, \"has_paint\": %s, \"octree_nodes\": %llu, \"octree_leaves\": %llu, "
+		"\"octree_words\": %llu, \"octree_leaf_words\": %llu, \"octree_max_words\": %llu, \"octree_max_stack\": %llu, "
+		"\"octree_hash\": \"%016llx\", \"octree_build_s\": %.6f}\n",
+		Bounds.Min.x, Bounds.Min.y, Bounds.Min.z, Bounds.Max.x, Bounds.Max.y, Bounds.Max.z, Tree->LeafCount(),
+		Tree->StackSize, Root.Program.Size(), Tree->HasPaint() ? "true" : "false",
+		(unsigned long long)Stats.Nodes, (unsigned long long)Stats.Leaves, (unsigned long long)Stats.Words,
+		(unsigned long long)Stats.LeafWords, (unsigned long long)Stats.MaxWords, (unsigned long long)Stats.MaxStack,
+		(unsigned long long)Stats.Hash, Seconds(T0, T1));
+	return 0;
+}
+
+
+static std::vector<float> ReadFloats(const char* Path)
+{
+	std::vector<float> Data;
+	FILE* File = std::fopen(Path, "rb");
+	if (!File) return Data;
+	std::fseek(File, 0, SEEK_END);
+	long Bytes = std::ftell(File);
+	std::fseek(File, 0, SEEK_SET);
+	Data.resize(Bytes / 4);
+	if (std::fread(Data.data(), 4, Data.size(), File) != Data.size()) Data.clear();
+	std::fclose(File);
+	return Data;
+}
+
+
+static int CmdEval(SDFNodeShared Tree, const std::string& Mode, const char* PointsPath, const char* OutPath)
+{
+	std::vector<float> Points = ReadFloats(PointsPath);
+	size_t Count = Points.size() / 3;
+	FILE* Out = std::fopen(OutPath, "wb");
+	if (!Out) return 2;
+	SDFOctreeShared Octree = SDFOctree::Create(Tree, 0.25);
+	SDFInterpreter Root(Tree);
+	const bool ExportColor = Tree->HasPaint();
+	for (size_t i = 0; i < Count; ++i)
+	{
+		vec3 Point(Points[i * 3 + 0], Points[i * 3 + 1], Points[i * 3 + 2]);
+		if (Mode == "octree")
+		{
+			// What the mesher samples (export.cpp:339-342).
+			float Dist = Octree->Eval(Point);
+			std::fwrite(&Dist, 4, 1, Out);
+		}
+		else if (Mode == "tree")
+		{
+			// What VoxExport samples (magica.cpp:61).
+			float Dist = Tree->Eval(Point);
+			std::fwrite(&Dist, 4, 1, Out);
+		}
+		else if (Mode == "interp")
+		{
+			float Dist = Root.Eval(Point);
+			std::fwrite(&Dist, 4, 1, Out);
+		}
+		else if (Mode == "gradient")
+		{
+			// What WritePLY stores as the normal (export.cpp:300).
+			vec3 Normal = Octree->Gradient(Point);
+			std::fwrite(&Normal, 4, 3, Out);
+		}
+		else if (Mode == "color")
+		{
+			// export.cpp:303-311, including the truncating float -> u8 conversion.
+			vec3 Color = vec3(1.0f);
+			if (ExportColor)
+			{
+				MaterialShared Material = Octree->GetMaterial(Point);
+				if (Material)
+				{
+					Color = SampleColor(Material->GuessColor());
+				}
+			}
+			uint8_t Bytes[3];
+			Bytes[0] = 0xFF * Color.r;
+			Bytes[1] = 0xFF * Color.g;
+			Bytes[2] = 0xFF * Color.b;
+			std::fwrite(Bytes, 1, 3, Out);
+		}
+		else
+		{
+			return Usage();
+		}
+	}
+	std::fclose(Out);
+	return 0;
+}
+
+
+static ExportFormat FormatFromPath(const std::string& Path)
+{
+	if (EndsWith(Path, ".stl")) return ExportFormat::STL;
+	return ExportFormat::PLY;
+}
+
+
+static void ResetExportAtomics()
+{
+	ExportActive.store(true);
+	ExportState.store(0);
+	GenerationProgress.store(0);
+	RefinementProgress.store(0);
+	SecondaryProgress.store(0);
+	WriteProgress.store(0);
+	ExportState.store(1);
+}
+
+
+struct GridArgs
+{
+	vec3 Min;
+	vec3 Max;
+	vec3 Step;
+};
+
+static GridArgs ParseGrid(char** Argv)
+{
+	GridArgs Grid;
+	Grid.Min = vec3(std::atof(Argv[0]), std::atof(Argv[1]), std::atof(Argv[2]));
+	Grid.Max = vec3(std::atof(Argv[3]), std::atof(Argv[4]), std::atof(Argv[5]));
+	Grid.Step = vec3(float(std::atof(Argv[6])));
+	return Grid;
+}
+
+
+// Reference surface-nets thunks driven by plain std::threads, the way sodapop.cpp:685-713 drives them.
+// slice_stride > 1 times only every Nth z-slice of loop 1 (stratified sample for very large grids).
+static int CmdBench(SDFNodeShared Tree, GridArgs Args, int ThreadCount, int SliceStride)
+{
+	auto T0 = Clock::now();
+	SDFOctreeShared Octree = SDFOctree::Create(Tree, 0.25);
+	auto T1 = Clock::now();
+
+	vec3 ModelMin = Args.Min - Args.Step * vec3(2.0);
+	ivec3 Extent = ivec3(ceil((Args.Max - ModelMin) / Args.Step));
+
+	isosurface::AsyncParallelSurfaceNets Task;
+	Task.Grid.x = ModelMin.x;
+	Task.Grid.y = ModelMin.y;
+	Task.Grid.z = ModelMin.z;
+	Task.Grid.dx = Args.Step.x;
+	Task.Grid.dy = Args.Step.y;
+	Task.Grid.dz = Args.Step.z;
+	Task.Grid.sx = Extent.x;
+	Task.Grid.sy = Extent.y;
+	Task.Grid.sz = Extent.z;
+	Task.ImplicitFunction = [&](float X, float Y, float Z) -> float
+	{
+		return Octree->Eval(vec3(X, Y, Z));
+	};
+	Task.Setup();
+
+	// Loop 1 over z slices (all config grids have z as a non-strictly-shorter axis or are cubic; the
+	// reference's axis swap quirk is avoided by iterating cells explicitly).
+	std::vector<size_t> Slices;
+	for (size_t k = 0; k < Task.Grid.sz; k += SliceStride)
+	{
+		Slices.push_back(k);
+	}
+	std::atomic<size_t> NextSlice(0);
+	auto T2 = Clock::now();
+	{
+		std::vector<std::thread> Threads;
+		for (int t = 0; t < ThreadCount; ++t)
+		{
+			Threads.emplace_back([&]()
+			{
+				while (true)
+				{
+					size_t Index = NextSlice.fetch_add(1);
+					if (Index >= Slices.size()) break;
+					size_t k = Slices[Index];
+					for (size_t j = 0; j < Task.Grid.sy; ++j)
+					{
+						for (size_t i = 0; i < Task.Grid.sx; ++i)
+						{
+							Task.FirstLoopInnerThunk(Task, { i, j, k });
+						}
+					}
+				}
+			});
+		}
+		for (auto& Thread : Threads) Thread.join();
+	}
+	auto T3 = Clock::now();
+
+	// Loop 2 only makes sense when every slice was visited.
+	double Loop2 = 0.0;
+	if (SliceStride == 1)
+	{
+		std::vector<std::pair<size_t, uint64_t>> Domain(Task.SecondLoopDomain.begin(), Task.SecondLoopDomain.end());
+		std::atomic<size_t> NextCell(0);
+		auto T4 = Clock::now();
+		std::vector<std::thread> Threads;
+		for (int t = 0; t < ThreadCount; ++t)
+		{
+			Threads.emplace_back([&]()
+			{
+				while (true)
+				{
+					size_t Begin = NextCell.fetch_add(256);
+					if (Begin >= Domain.size()) break;
+					size_t End = std::min(Begin + 256, Domain.size());
+					for (size_t c = Begin; c < End; ++c)
+					{
+						Task.SecondLoopThunk(Task, Domain[c]);
+					}
+				}
+			});
+		}
+		for (auto& Thread : Threads) Thread.join();
+		Loop2 = Seconds(T4, Clock::now());
+	}
+
+	double Loop1 = Seconds(T2, T3);
+	double CellsTimed = double(Slices.size()) * double(Task.Grid.sx) * double(Task.Grid.sy);
+	double CellsTotal = double(Task.Grid.sx) * double(Task.Grid.sy) * double(Task.Grid.sz);
+	std::printf("{\"grid\": [%zu, %zu, %zu], \"threads\": %d, \"slice_stride\": %d, \"slices_timed\": %zu, "
+		"\"octree_build_s\": %.6f, \"loop1_s\": %.6f, \"loop2_s\": %.6f, \"cells_timed\": %.0f, \"cells_total\": %.0f, "
+		"\"vertices\": %zu, \"faces\": %zu, \"mvoxels_per_s_loop1\": %.6f}\n",
+		Task.Grid.sx, Task.Grid.sy, Task.Grid.sz, ThreadCount, SliceStride, Slices.size(),
+		Seconds(T0, T1), Loop1, Loop2, CellsTimed, CellsTotal,
+		Task.OutputMesh.vertex_count(), Task.OutputMesh.face_count(), CellsTimed / Loop1 * 1e-6);
+	return 0;
+}
+
+
+int main(int Argc, char** Argv)
+{
+	if (Argc < 3)
+	{
+		return Usage();
+	}
+	std::string Command = Argv[1];
+	SDFNodeShared Tree = LoadModel(Argv[2]);
+	if (!Tree)
+	{
+		std::fprintf(stderr, "failed to load model %s\n", Argv[2]);
+		return 2;
+	}
+
+	if (Command == "dump-tgm" && Argc == 4)
+	{
+		TgmWriter Writer;
+		return Writer.Write(Tree, Argv[3]) ? 0 : 2;
+	}
+	else if (Command == "info")
+	{
+		return CmdInfo(Tree);
+	}
+	else if (Command == "octree" && Argc == 4)
+	{
+		SDFOctreeShared Octree = SDFOctree::Create(Tree, 0.25);
+		OctreeStats Stats;
+		Stats.Dump = std::fopen(Argv[3], "wb");
+		if (!Stats.Dump || !Octree) return 2;
+		WalkOctree(Octree.get(), Stats);
+		std::fclose(Stats.Dump);
+		return 0;
+	}
+	else if (Command == "eval" && Argc == 6)
+	{
+		return CmdEval(Tree, Argv[3], Argv[4], Argv[5]);
+	}
+	else if (Command == "export" && Argc == 6)
+	{
+		auto T0 = Clock::now();
+		ExportCommon(Tree, float(std::atof(Argv[3])), std::atoi(Argv[4]), Argv[5], FormatFromPath(Argv[5]), 1.0f);
+		std::printf("{\"export_s\": %.6f}\n", Seconds(T0, Clock::now()));
+		return 0;
+	}
+	else if (Command == "export-grid" && Argc == 13)
+	{
+		GridArgs Grid = ParseGrid(Argv + 3);
+		int Refine = std::atoi(Argv[10]);
+		bool PointCloud = std::atoi(Argv[11]) != 0;
+		std::string Path = Argv[12];
+		ResetExportAtomics();
+		auto T0 = Clock::now();
+		if (PointCloud)
+		{
+			PointCloudExportThread(Tree, Grid.Min, Grid.Max, Grid.Step, Refine, Path, FormatFromPath(Path), 1.0f);
+		}
+		else
+		{
+			MeshExportThread(Tree, Grid.Min, Grid.Max, Grid.Step, Refine, Path, FormatFromPath(Path), 1.0f);
+		}
+		std::printf("{\"export_s\": %.6f}\n", Seconds(T0, Clock::now()));
+		return 0;
+	}
+	else if (Command == "vox" && Argc == 6)
+	{
+		std::string Path = Argv[5];
+		auto T0 = Clock::now();
+		VoxExport(Tree, Path, float(std::atof(Argv[3])), std::atoi(Argv[4]));
+		std::printf("{\"vox_s\": %.6f}\n", Seconds(T0, Clock::now()));
+		return 0;
+	}
+	else if (Command == "bench" && Argc == 12)
+	{
+		GridArgs Grid = ParseGrid(Argv + 3);
+		return CmdBench(Tree, Grid, std::atoi(Argv[10]), std::atoi(Argv[11]));
+	}
+	return Usage();
+}
