@@ -1,0 +1,282 @@
+/*
+ * tangerine_b200 -- C ABI of the B200 (sm_100a) SDF meshing path.
+ *
+ * This is the drop-in boundary for the reference's export hot path (Aeva/tangerine).  Host code stays
+ * C++ and reaches CUDA only through these entry points: plain pointers and sizes, `int` status per call
+ * (0 = TG_OK) plus a thread-local error string; nothing here ever aborts the host process (the
+ * reference's own convention is print + abort(), tangerine/errors.cpp:23-32).
+ *
+ * Each group cites the reference interface it replaces.  The precedent for a C ABI over this path is
+ * the reference's own legacy FFI: tangerine/c_sdf.cpp:27-180 (tree building, EvalTree),
+ * tangerine/export.cpp:611-622 (ExportSTL / ExportPLY) and tangerine/magica.cpp:77-84
+ * (ExportMagicaVoxel), bound from Racket in package/tangerine/export.rkt:26-28 and eval.rkt:37-62.
+ *
+ * Threading: a tg_context is used by one thread at a time (the reference runs an export on one
+ * detached std::thread, export.cpp:576-578); tg_progress and tg_cancel may be called concurrently
+ * from another thread, like GetExportProgress / CancelExport are from the UI thread.  Trees are plain
+ * values with no hidden sharing.
+ */
+#ifndef TANGERINE_B200_H
+#define TANGERINE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define TG_API __declspec(dllexport)
+#else
+#define TG_API __attribute__((visibility("default")))
+#endif
+
+enum
+{
+	TG_OK = 0,
+	TG_ERR_INVALID = 1,   /* bad argument / malformed input */
+	TG_ERR_NO_DEVICE = 2, /* CUDA device or kernel image unavailable: there is no CPU fallback */
+	TG_ERR_CUDA = 3,      /* a CUDA call failed; see tg_last_error() */
+	TG_ERR_MEMORY = 4,
+	TG_ERR_IO = 5,
+	TG_ERR_CANCELLED = 6,
+	TG_ERR_UNSUPPORTED = 7 /* e.g. CSG nesting deeper than the device operand stack */
+};
+
+/* Thread-local description of the most recent failure on this thread. */
+TG_API const char* tg_last_error(void);
+TG_API const char* tg_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * CSG trees.  Replaces: SDF:: constructors (tangerine/sdf_evaluator.h:223-264, .cpp:1206-1371) and the
+ * legacy C ABI Make*Brush / Make*Op / MoveTree / RotateTree / ... (tangerine/c_sdf.cpp:27-180).
+ * Arguments have the reference's meaning (radii / half extents, not the Lua layer's diameters).
+ * Operators copy their operands (the Lua layer deep-copies on every modifier too, lua_sdf.cpp:56-62);
+ * the caller keeps ownership of everything it was handed and frees each tree with tg_tree_free.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tg_tree tg_tree;
+
+TG_API tg_tree* tg_make_sphere(float radius);
+TG_API tg_tree* tg_make_ellipsoid(float radipode_x, float radipode_y, float radipode_z);
+TG_API tg_tree* tg_make_box(float extent_x, float extent_y, float extent_z);
+TG_API tg_tree* tg_make_torus(float major_radius, float minor_radius);
+TG_API tg_tree* tg_make_cylinder(float radius, float extent);
+TG_API tg_tree* tg_make_plane(float normal_x, float normal_y, float normal_z);
+TG_API tg_tree* tg_make_cone(float radius, float height);
+TG_API tg_tree* tg_make_coninder(float radius_l, float radius_h, float height);
+
+TG_API tg_tree* tg_make_union(const tg_tree* lhs, const tg_tree* rhs);
+TG_API tg_tree* tg_make_diff(const tg_tree* lhs, const tg_tree* rhs);
+TG_API tg_tree* tg_make_inter(const tg_tree* lhs, const tg_tree* rhs);
+TG_API tg_tree* tg_make_blend_union(float threshold, const tg_tree* lhs, const tg_tree* rhs);
+TG_API tg_tree* tg_make_blend_diff(float threshold, const tg_tree* lhs, const tg_tree* rhs);
+TG_API tg_tree* tg_make_blend_inter(float threshold, const tg_tree* lhs, const tg_tree* rhs);
+TG_API tg_tree* tg_make_flate(const tg_tree* child, float radius);
+/* SDF::Stencil (sdf_evaluator.cpp:1361-1371): `material` overrides the child's paint where the mask is
+ * negative (apply_to_negative != 0, Lua `stencil`) or non-negative (apply_to_negative == 0, Lua `mask`). */
+TG_API tg_tree* tg_make_stencil(const tg_tree* child, const tg_tree* mask, uint32_t material, int apply_to_negative);
+
+TG_API tg_tree* tg_tree_copy(const tg_tree* tree);
+TG_API void tg_tree_free(tg_tree* tree);
+
+/* In-place modifiers: SDFNode::Move / Rotate / Scale / ApplyMaterial, SDF::Align, SDF::RotateX/Y/Z. */
+TG_API int tg_tree_move(tg_tree* tree, float x, float y, float z);
+TG_API int tg_tree_rotate(tg_tree* tree, float quat_x, float quat_y, float quat_z, float quat_w);
+TG_API int tg_tree_rotate_x(tg_tree* tree, float degrees);
+TG_API int tg_tree_rotate_y(tg_tree* tree, float degrees);
+TG_API int tg_tree_rotate_z(tg_tree* tree, float degrees);
+TG_API int tg_tree_scale(tg_tree* tree, float scale);
+TG_API int tg_tree_align(tg_tree* tree, float anchor_x, float anchor_y, float anchor_z);
+TG_API int tg_tree_paint(tg_tree* tree, uint32_t material, int force);
+
+/* A material is what the export path reads from one: its sampled sRGB base colour,
+ * SampleColor(Material->GuessColor()) (tangerine/export.cpp:303-307).  Returns a process-wide id. */
+TG_API uint32_t tg_material_create(float red, float green, float blue);
+
+/* Queries: SDFNode::Eval (legacy EvalTree), Bounds, HasPaint, HasFiniteBounds, LeafCount. */
+TG_API float tg_tree_eval(const tg_tree* tree, float x, float y, float z);
+TG_API int tg_tree_bounds(const tg_tree* tree, float out_min[3], float out_max[3]);
+TG_API int tg_tree_has_paint(const tg_tree* tree);
+TG_API int tg_tree_has_finite_bounds(const tg_tree* tree);
+TG_API int tg_tree_leaf_count(const tg_tree* tree);
+
+/* Portable tree files (.tgm, layout in tangerine_b200/csrc/tg_tree.h). */
+TG_API tg_tree* tg_tree_load(const char* path);
+TG_API int tg_tree_save(const tg_tree* tree, const char* path);
+
+/* The synthetic benchmark tree of SURVEY.md section 8(d), config C4: `primitives` random brushes folded
+ * left to right with smooth unions / differences, clipped to a 10-unit cube. */
+TG_API tg_tree* tg_make_synthetic(uint32_t primitives, uint32_t seed);
+
+/* ------------------------------------------------------------------------------------------------
+ * Contexts and models.  A context owns one CUDA device, its streams and scratch memory.
+ * tg_model_create replaces SDFOctree::Create(Evaluator, 0.25) (tangerine/sdf_evaluator.cpp:1609-1783,
+ * called from export.cpp:322): it builds the pruning octree on host threads, flattens every node's
+ * pruned subtree into device instruction streams and uploads them.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tg_context tg_context;
+typedef struct tg_model tg_model;
+
+TG_API tg_context* tg_context_create(int cuda_device);
+TG_API void tg_context_destroy(tg_context* context);
+TG_API int tg_context_device(const tg_context* context);
+
+typedef struct tg_model_stats
+{
+	uint64_t octree_nodes;
+	uint64_t octree_leaves;
+	uint64_t reference_words;      /* total program size in the reference's word encoding */
+	uint64_t reference_leaf_words;
+	uint64_t reference_max_words;
+	uint64_t max_stack;            /* largest SDFNode::StackSize */
+	uint64_t octree_hash;          /* FNV-1a over (pivot, terminus, child mask, reference words), pre-order */
+	uint64_t device_bytes;         /* size of the uploaded tables */
+	double build_seconds;          /* host octree build + flatten */
+	double upload_seconds;
+	float bounds_min[3];
+	float bounds_max[3];
+	int32_t has_paint;
+	int32_t leaf_count;
+} tg_model_stats;
+
+TG_API tg_model* tg_model_create(tg_context* context, const tg_tree* tree, float octree_target_size, int host_threads);
+/* Host half of tg_model_create only (octree build + flattening, no device needed): fills the octree_*,
+ * reference_*, max_stack, bounds, has_paint, leaf_count and build_seconds fields. */
+TG_API int tg_tree_octree_stats(const tg_tree* tree, float octree_target_size, int host_threads, tg_model_stats* out);
+TG_API void tg_model_destroy(tg_model* model);
+TG_API int tg_model_get_stats(const tg_model* model, tg_model_stats* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Point queries (parity dumps and the Lua-side eval / gradient calls).
+ *   TG_EVAL_OCTREE    SDFOctree::Eval       (sdf_evaluator.cpp:1969-1989)  what the mesher samples
+ *   TG_EVAL_INTERP    SDFInterpreter::Eval on the unpruned model (sdf_evaluator.cpp:1386-1605)
+ *   TG_EVAL_TREE      SDFNode::Eval on the unpruned model        (magica.cpp:61 samples this)
+ *   TG_EVAL_GRADIENT  SDFOctree::Gradient   (sdf_evaluator.h:327-331)      3 floats per point
+ *   TG_EVAL_COLOR     export colour bytes   (export.cpp:297-312)           3 bytes per point
+ * `points` and `out` are host pointers; count points of 3 floats.
+ * ---------------------------------------------------------------------------------------------- */
+enum { TG_EVAL_OCTREE = 0, TG_EVAL_INTERP = 1, TG_EVAL_TREE = 2, TG_EVAL_GRADIENT = 3, TG_EVAL_COLOR = 4 };
+TG_API int tg_eval_points(tg_model* model, int mode, const float* points, uint64_t count, void* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Mesh export.  Replaces the span export.cpp:324-365 (grid set-up, isosurface::par_surface_nets with
+ * the octree as implicit function, mesh conversion) plus the per-vertex attribute loops
+ * export.cpp:297-314 (PLY) / 130-140 (STL), and the refinement loop export.cpp:433-469 applied to the
+ * mesh vertices when refine_iterations > 0.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tg_grid
+{
+	float x, y, z;       /* origin:      isosurface::regular_grid_t (regular_grid.h:29-37) */
+	float dx, dy, dz;    /* cell size */
+	uint64_t sx, sy, sz; /* cells per axis */
+} tg_grid;
+
+/* MeshExportThread's grid: ModelMin -= 2 * Step; Extent = ceil((ModelMax - ModelMin) / Step) (export.cpp:324-337). */
+TG_API int tg_export_grid(const float model_min[3], const float model_max[3], const float step[3], tg_grid* out);
+
+enum
+{
+	TG_MESH_NORMALS = 1u << 0,      /* per-vertex SDFOctree::Gradient */
+	TG_MESH_COLORS = 1u << 1,       /* per-vertex export colour; ignored (white) when the model has no paint */
+	TG_MESH_NO_CULL = 1u << 2,      /* evaluate every brick, as the reference does (dense sweep) */
+	TG_MESH_DEVICE_ONLY = 1u << 3,  /* leave results in HBM: out->positions etc. are NULL, counts are valid */
+	TG_MESH_FACE_NORMALS = 1u << 4  /* per-triangle gradient at the centroid (WriteSTL, export.cpp:130-140) */
+};
+
+typedef struct tg_mesh_options
+{
+	uint32_t flags;
+	int32_t refine_iterations; /* 0 = positions exactly as surface nets produced them */
+	float scale;               /* positions are multiplied by this last (export.cpp:313); 0 means 1 */
+	/* z-slab for multi-GPU runs: this call owns cell layers [slab_begin, slab_end) of the grid.
+	 * Both zero = the whole grid.  See tg_mesh.halo_vertices. */
+	uint64_t slab_begin, slab_end;
+} tg_mesh_options;
+
+typedef struct tg_mesh_timings
+{
+	/* device milliseconds measured with CUDA events on the context's stream */
+	float cull_ms, evaluate_ms, compact_ms, faces_ms, attributes_ms, total_device_ms;
+	float download_ms; /* device -> host copies (0 with TG_MESH_DEVICE_ONLY) */
+	uint64_t bricks_total, bricks_evaluated;
+	uint64_t samples_evaluated;      /* lattice samples actually run through the interpreter */
+	uint64_t algorithmic_flops;      /* sum over evaluated samples of their program's FLOP count */
+	uint64_t kernel_launches;
+} tg_mesh_timings;
+
+typedef struct tg_mesh
+{
+	/* Library-owned host arrays (pinned); release with tg_mesh_free.  Vertices are ordered by cell,
+	 * lexicographically in (k, j, i) -- the order the reference's serial loop produces
+	 * (surface_nets.cpp:976-999).  Triangles are ordered by owning cell, then edge 0..2. */
+	float* positions;      /* 3 per vertex */
+	float* normals;        /* 3 per vertex, or NULL */
+	uint8_t* colors;       /* 3 per vertex, or NULL */
+	uint32_t* triangles;   /* 3 per triangle */
+	float* face_normals;   /* 3 per triangle, or NULL */
+	uint64_t vertex_count;
+	uint64_t triangle_count;
+	/* Slab runs: the first halo_vertices entries of the *local* numbering belong to the cell layer below
+	 * the slab (owned by the previous rank) and are not part of positions[]; triangle indices are local
+	 * numbers minus halo_vertices, so adding the previous ranks' vertex total makes them global. */
+	uint64_t halo_vertices;
+	tg_mesh_timings timings;
+	void* opaque;
+} tg_mesh;
+
+TG_API int tg_export_mesh(tg_model* model, const tg_grid* grid, const tg_mesh_options* options, tg_mesh* out);
+TG_API void tg_mesh_free(tg_mesh* mesh);
+
+/* Raw lattice samples of the grid through SDFOctree::Eval: (sx+1)*(sy+1)*(sz+1) floats, x fastest.
+ * `out` may be NULL to time the evaluator alone; elapsed device milliseconds are returned in *out_ms. */
+TG_API int tg_eval_lattice(tg_model* model, const tg_grid* grid, float* out, float* out_ms);
+
+/* ------------------------------------------------------------------------------------------------
+ * Point-cloud export.  Replaces PointCloudExportThread's two Pool() passes (export.cpp:393-469).
+ * ---------------------------------------------------------------------------------------------- */
+TG_API int tg_export_points(tg_model* model, const float model_min[3], const float model_max[3], const float step[3],
+	int refine_iterations, uint32_t flags, tg_mesh* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Voxel occupancy.  Replaces the Pool() loop of VoxExport (tangerine/magica.cpp:27-69).
+ * out_xyz receives library-owned int32 triples in flat-index order; free with tg_free.
+ * ---------------------------------------------------------------------------------------------- */
+TG_API int tg_export_voxels(tg_model* model, float grid_size, int32_t out_size[3], float* out_radius,
+	int32_t** out_xyz, uint64_t* out_count);
+TG_API void tg_free(void* pointer);
+
+/* ------------------------------------------------------------------------------------------------
+ * Progress / cancel.  Replaces GetExportProgress / CancelExport (tangerine/export.h:27-39,
+ * export.cpp:483-492, 582-592).  stage: 0 idle, 1 generate, 2 refine, 3 attributes + write.
+ * ---------------------------------------------------------------------------------------------- */
+TG_API int tg_progress(const tg_context* context, float out_ratios[4], int* out_stage);
+TG_API int tg_cancel(tg_context* context, int halt);
+
+/* ------------------------------------------------------------------------------------------------
+ * File-level entry points with the signatures of the reference's legacy FFI:
+ *   ExportPLY / ExportSTL(tree, GridSize, RefineIterations, Path)   export.cpp:611-622
+ *   ExportMagicaVoxel(tree, GridSize, ColorIndex, Path)             magica.cpp:77-84
+ * They run ExportCommon's sequence (export.cpp:595-607) on CUDA device `cuda_device`.
+ * ---------------------------------------------------------------------------------------------- */
+TG_API int tg_export_ply(const tg_tree* tree, float grid_size, int refine_iterations, const char* path, int cuda_device);
+TG_API int tg_export_stl(const tg_tree* tree, float grid_size, int refine_iterations, const char* path, int cuda_device);
+TG_API int tg_export_magica_voxel(const tg_tree* tree, float grid_size, int color_index, const char* path, int cuda_device);
+
+/* Writers on already-extracted data (WritePLY / WriteSTL byte layouts, export.cpp:60-108, 198-280). */
+TG_API int tg_write_ply(const char* path, const tg_mesh* mesh);
+TG_API int tg_write_stl(const char* path, const tg_mesh* mesh);
+
+/* ------------------------------------------------------------------------------------------------
+ * Measurement helpers for bench.py: device-side timing on the context's own stream, and an FP32
+ * FMA-chain peak measurement (the roofline denominator for the evaluator; MEASURED_PEAKS.json has none).
+ * ---------------------------------------------------------------------------------------------- */
+TG_API int tg_timer_begin(tg_context* context);
+TG_API int tg_timer_end(tg_context* context, float* out_ms);
+TG_API int tg_measure_fp32_peak(tg_context* context, double* out_tflops);
+TG_API int tg_flush_l2(tg_context* context);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

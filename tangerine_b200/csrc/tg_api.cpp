@@ -1,0 +1,646 @@
+// extern "C" surface of libtangerine_b200.so (declared in include/tangerine_b200.h).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <random>
+#include <string>
+
+#include "../../include/tangerine_b200.h"
+#include "tg_engine.h"
+#include "tg_tree.h"
+#include "tg_writers.h"
+
+using namespace tg;
+
+struct tg_tree
+{
+	Tree tree;
+};
+
+struct tg_context
+{
+	std::unique_ptr<Context> impl;
+};
+
+struct tg_model
+{
+	std::unique_ptr<Model> impl;
+	tg_context* context;
+};
+
+namespace
+{
+thread_local std::string g_last_error;
+
+int Fail(int code, const std::string& message)
+{
+	g_last_error = message;
+	return code;
+}
+
+tg_tree* Wrap(Tree&& t)
+{
+	tg_tree* h = new tg_tree();
+	h->tree = std::move(t);
+	return h;
+}
+
+tg_tree* MakeSet(uint32_t kind, const tg_tree* lhs, const tg_tree* rhs, float threshold)
+{
+	if (!lhs || !rhs || !lhs->tree.Valid() || !rhs->tree.Valid())
+	{
+		Fail(TG_ERR_INVALID, "set operator needs two valid trees");
+		return nullptr;
+	}
+	return Wrap(Tree::Combine(kind, lhs->tree, rhs->tree, threshold));
+}
+} // namespace
+
+extern "C"
+{
+
+const char* tg_last_error(void)
+{
+	return g_last_error.c_str();
+}
+
+const char* tg_version(void)
+{
+	return "tangerine_b200 0.1 (sm_100a)";
+}
+
+// ---- trees ---------------------------------------------------------------------------------------
+
+tg_tree* tg_make_sphere(float radius) { return Wrap(Tree::Sphere(radius)); }
+tg_tree* tg_make_ellipsoid(float x, float y, float z) { return Wrap(Tree::Ellipsoid(x, y, z)); }
+tg_tree* tg_make_box(float x, float y, float z) { return Wrap(Tree::Box(x, y, z)); }
+tg_tree* tg_make_torus(float major_radius, float minor_radius) { return Wrap(Tree::Torus(major_radius, minor_radius)); }
+tg_tree* tg_make_cylinder(float radius, float extent) { return Wrap(Tree::Cylinder(radius, extent)); }
+tg_tree* tg_make_plane(float x, float y, float z) { return Wrap(Tree::Plane(x, y, z)); }
+tg_tree* tg_make_cone(float radius, float height) { return Wrap(Tree::Cone(radius, height)); }
+tg_tree* tg_make_coninder(float radius_l, float radius_h, float height) { return Wrap(Tree::Coninder(radius_l, radius_h, height)); }
+
+tg_tree* tg_make_union(const tg_tree* l, const tg_tree* r) { return MakeSet(kKindUnion, l, r, 0.0f); }
+tg_tree* tg_make_diff(const tg_tree* l, const tg_tree* r) { return MakeSet(kKindDiff, l, r, 0.0f); }
+tg_tree* tg_make_inter(const tg_tree* l, const tg_tree* r) { return MakeSet(kKindInter, l, r, 0.0f); }
+tg_tree* tg_make_blend_union(float t, const tg_tree* l, const tg_tree* r) { return MakeSet(kKindBlendUnion, l, r, t); }
+tg_tree* tg_make_blend_diff(float t, const tg_tree* l, const tg_tree* r) { return MakeSet(kKindBlendDiff, l, r, t); }
+tg_tree* tg_make_blend_inter(float t, const tg_tree* l, const tg_tree* r) { return MakeSet(kKindBlendInter, l, r, t); }
+
+tg_tree* tg_make_flate(const tg_tree* child, float radius)
+{
+	if (!child || !child->tree.Valid())
+	{
+		Fail(TG_ERR_INVALID, "flate needs a valid tree");
+		return nullptr;
+	}
+	return Wrap(Tree::Flate(child->tree, radius));
+}
+
+tg_tree* tg_make_stencil(const tg_tree* child, const tg_tree* mask, uint32_t material, int apply_to_negative)
+{
+	if (!child || !mask || !child->tree.Valid() || !mask->tree.Valid())
+	{
+		Fail(TG_ERR_INVALID, "stencil needs two valid trees");
+		return nullptr;
+	}
+	return Wrap(Tree::Stencil(child->tree, mask->tree, material, apply_to_negative != 0));
+}
+
+tg_tree* tg_tree_copy(const tg_tree* tree)
+{
+	if (!tree)
+	{
+		Fail(TG_ERR_INVALID, "null tree");
+		return nullptr;
+	}
+	tg_tree* h = new tg_tree();
+	h->tree = tree->tree;
+	return h;
+}
+
+void tg_tree_free(tg_tree* tree)
+{
+	delete tree;
+}
+
+#define TG_REQUIRE_TREE(t) \
+	if (!(t) || !(t)->tree.Valid()) return Fail(TG_ERR_INVALID, "null or empty tree")
+
+int tg_tree_move(tg_tree* t, float x, float y, float z)
+{
+	TG_REQUIRE_TREE(t);
+	t->tree.Move(Vec3(x, y, z));
+	return TG_OK;
+}
+
+int tg_tree_rotate(tg_tree* t, float qx, float qy, float qz, float qw)
+{
+	TG_REQUIRE_TREE(t);
+	Quat q;
+	q.w = qw;
+	q.x = qx;
+	q.y = qy;
+	q.z = qz;
+	t->tree.Rotate(q);
+	return TG_OK;
+}
+
+int tg_tree_rotate_x(tg_tree* t, float degrees)
+{
+	TG_REQUIRE_TREE(t);
+	t->tree.RotateX(degrees);
+	return TG_OK;
+}
+
+int tg_tree_rotate_y(tg_tree* t, float degrees)
+{
+	TG_REQUIRE_TREE(t);
+	t->tree.RotateY(degrees);
+	return TG_OK;
+}
+
+int tg_tree_rotate_z(tg_tree* t, float degrees)
+{
+	TG_REQUIRE_TREE(t);
+	t->tree.RotateZ(degrees);
+	return TG_OK;
+}
+
+int tg_tree_scale(tg_tree* t, float scale)
+{
+	TG_REQUIRE_TREE(t);
+	t->tree.Scale(scale);
+	return TG_OK;
+}
+
+int tg_tree_align(tg_tree* t, float x, float y, float z)
+{
+	TG_REQUIRE_TREE(t);
+	t->tree.Align(Vec3(x, y, z));
+	return TG_OK;
+}
+
+int tg_tree_paint(tg_tree* t, uint32_t material, int force)
+{
+	TG_REQUIRE_TREE(t);
+	if (material >= MaterialCount()) return Fail(TG_ERR_INVALID, "unknown material id");
+	t->tree.Paint(material, force != 0);
+	return TG_OK;
+}
+
+uint32_t tg_material_create(float r, float g, float b)
+{
+	return RegisterMaterial(r, g, b);
+}
+
+float tg_tree_eval(const tg_tree* t, float x, float y, float z)
+{
+	if (!t || !t->tree.Valid())
+	{
+		Fail(TG_ERR_INVALID, "null or empty tree");
+		return NAN;
+	}
+	return t->tree.Eval(Vec3(x, y, z));
+}
+
+int tg_tree_bounds(const tg_tree* t, float out_min[3], float out_max[3])
+{
+	TG_REQUIRE_TREE(t);
+	Box3 b = t->tree.Bounds();
+	for (int i = 0; i < 3; ++i)
+	{
+		out_min[i] = b.min[i];
+		out_max[i] = b.max[i];
+	}
+	return TG_OK;
+}
+
+int tg_tree_has_paint(const tg_tree* t) { return t && t->tree.Valid() && t->tree.HasPaint() ? 1 : 0; }
+int tg_tree_has_finite_bounds(const tg_tree* t) { return t && t->tree.Valid() && t->tree.HasFiniteBounds() ? 1 : 0; }
+int tg_tree_leaf_count(const tg_tree* t) { return t && t->tree.Valid() ? t->tree.LeafCount() : 0; }
+
+tg_tree* tg_tree_load(const char* path)
+{
+	if (!path)
+	{
+		Fail(TG_ERR_INVALID, "null path");
+		return nullptr;
+	}
+	Tree t;
+	std::string error;
+	if (!Tree::LoadTgm(path, t, error))
+	{
+		Fail(TG_ERR_IO, error);
+		return nullptr;
+	}
+	return Wrap(std::move(t));
+}
+
+int tg_tree_save(const tg_tree* t, const char* path)
+{
+	TG_REQUIRE_TREE(t);
+	std::string error;
+	if (!path || !t->tree.SaveTgm(path, error)) return Fail(TG_ERR_IO, path ? error : "null path");
+	return TG_OK;
+}
+
+// SURVEY.md section 8(d), config C4.  Uniforms are (rng() >> 8) * 2^-24 from std::mt19937(seed).
+tg_tree* tg_make_synthetic(uint32_t primitives, uint32_t seed)
+{
+	if (primitives == 0)
+	{
+		Fail(TG_ERR_INVALID, "need at least one primitive");
+		return nullptr;
+	}
+	std::mt19937 rng(seed);
+	auto u = [&rng]() { return float(double(rng() >> 8) * (1.0 / 16777216.0)); };
+	Tree model;
+	for (uint32_t n = 0; n < primitives; ++n)
+	{
+		const int type = std::min(5, int(u() * 6.0f));
+		const float s0 = 0.1f + 0.3f * u(), s1 = 0.1f + 0.3f * u(), s2 = 0.1f + 0.3f * u();
+		Tree brush;
+		switch (type)
+		{
+		case 0: brush = Tree::Sphere(s0); break;
+		case 1: brush = Tree::Box(s0, s1, s2); break;
+		case 2: brush = Tree::Cylinder(s0, s1); break;
+		case 3: brush = Tree::Torus(s0, 0.35f * s1); break;
+		case 4: brush = Tree::Coninder(s0, 0.5f * s1, s2); break;
+		default: brush = Tree::Cone(s0, 2.0f * s1); break;
+		}
+		// uniform random unit quaternion (Shoemake)
+		const float u1 = u(), u2 = u(), u3 = u();
+		const float two_pi = 6.28318530717958647692f;
+		Quat q;
+		q.x = std::sqrt(1.0f - u1) * std::sin(two_pi * u2);
+		q.y = std::sqrt(1.0f - u1) * std::cos(two_pi * u2);
+		q.z = std::sqrt(u1) * std::sin(two_pi * u3);
+		q.w = std::sqrt(u1) * std::cos(two_pi * u3);
+		brush.Rotate(q);
+		const float cx = -4.5f + 9.0f * u(), cy = -4.5f + 9.0f * u(), cz = -4.5f + 9.0f * u();
+		brush.Move(Vec3(cx, cy, cz));
+		const float pick = u();
+		const float threshold = 0.02f + 0.08f * u();
+		if (n == 0)
+		{
+			model = std::move(brush);
+		}
+		else
+		{
+			const uint32_t kind = pick < 0.7f ? kKindBlendUnion : pick < 0.9f ? kKindBlendDiff : kKindUnion;
+			model.Fold(kind, brush, threshold);
+		}
+	}
+	model.Fold(kKindInter, Tree::Box(5.0f, 5.0f, 5.0f), 0.0f);
+	return Wrap(std::move(model));
+}
+
+// ---- contexts and models -------------------------------------------------------------------------
+
+tg_context* tg_context_create(int cuda_device)
+{
+	std::string error;
+	Context* c = Context::Create(cuda_device, error);
+	if (!c)
+	{
+		Fail(TG_ERR_NO_DEVICE, error);
+		return nullptr;
+	}
+	tg_context* h = new tg_context();
+	h->impl.reset(c);
+	return h;
+}
+
+void tg_context_destroy(tg_context* context)
+{
+	delete context;
+}
+
+int tg_context_device(const tg_context* context)
+{
+	return context ? context->impl->device : -1;
+}
+
+tg_model* tg_model_create(tg_context* context, const tg_tree* tree, float target_size, int host_threads)
+{
+	if (!context || !tree || !tree->tree.Valid())
+	{
+		Fail(TG_ERR_INVALID, "tg_model_create needs a context and a valid tree");
+		return nullptr;
+	}
+	if (!(target_size > 0.0f)) target_size = 0.25f; // the export path's constant (export.cpp:322)
+	std::string error;
+	Model* m = Model::Create(context->impl.get(), tree->tree, target_size, host_threads, error);
+	if (!m)
+	{
+		Fail(error.find("deeper") != std::string::npos ? TG_ERR_UNSUPPORTED : TG_ERR_INVALID, error);
+		return nullptr;
+	}
+	tg_model* h = new tg_model();
+	h->impl.reset(m);
+	h->context = context;
+	return h;
+}
+
+void tg_model_destroy(tg_model* model)
+{
+	delete model;
+}
+
+static void FillStats(const FlatModel& f, tg_model_stats* out)
+{
+	std::memset(out, 0, sizeof(*out));
+	out->octree_nodes = f.stats.nodes;
+	out->octree_leaves = f.stats.leaves;
+	out->reference_words = f.stats.ref_words;
+	out->reference_leaf_words = f.stats.ref_leaf_words;
+	out->reference_max_words = f.stats.ref_max_words;
+	out->max_stack = f.stats.max_stack;
+	out->octree_hash = f.stats.hash;
+	out->build_seconds = f.stats.build_seconds;
+	for (int i = 0; i < 3; ++i)
+	{
+		out->bounds_min[i] = f.bounds.min[i];
+		out->bounds_max[i] = f.bounds.max[i];
+	}
+	out->has_paint = f.has_paint ? 1 : 0;
+}
+
+int tg_tree_octree_stats(const tg_tree* tree, float target_size, int host_threads, tg_model_stats* out)
+{
+	TG_REQUIRE_TREE(tree);
+	if (!out) return Fail(TG_ERR_INVALID, "null argument");
+	if (!(target_size > 0.0f)) target_size = 0.25f;
+	FlatModel flat;
+	std::string error;
+	if (!BuildFlatModel(tree->tree, target_size, host_threads, flat, error))
+	{
+		return Fail(error.find("deeper") != std::string::npos ? TG_ERR_UNSUPPORTED : TG_ERR_INVALID, error);
+	}
+	FillStats(flat, out);
+	out->leaf_count = tree->tree.LeafCount();
+	return TG_OK;
+}
+
+int tg_model_get_stats(const tg_model* model, tg_model_stats* out)
+{
+	if (!model || !out) return Fail(TG_ERR_INVALID, "null argument");
+	FillStats(model->impl->flat, out);
+	out->device_bytes = model->impl->device_bytes;
+	out->upload_seconds = model->impl->upload_seconds;
+	out->leaf_count = model->impl->leaf_count;
+	return TG_OK;
+}
+
+// ---- queries and exports -------------------------------------------------------------------------
+
+int tg_eval_points(tg_model* model, int mode, const float* points, uint64_t count, void* out)
+{
+	if (!model || (count && (!points || !out))) return Fail(TG_ERR_INVALID, "null argument");
+	std::string error;
+	int rc = EngineEvalPoints(model->impl.get(), mode, points, count, out, error);
+	return rc == TG_OK ? rc : Fail(rc, error);
+}
+
+int tg_export_grid(const float mn[3], const float mx[3], const float step[3], tg_grid* out)
+{
+	if (!mn || !mx || !step || !out) return Fail(TG_ERR_INVALID, "null argument");
+	// export.cpp:324-337
+	float lo[3];
+	uint64_t size[3];
+	for (int i = 0; i < 3; ++i)
+	{
+		if (!(step[i] > 0.0f)) return Fail(TG_ERR_INVALID, "step must be positive");
+		lo[i] = mn[i] - step[i] * 2.0f;
+		const int32_t extent = int32_t(std::ceil((mx[i] - lo[i]) / step[i]));
+		if (extent <= 0) return Fail(TG_ERR_INVALID, "empty export grid");
+		size[i] = uint64_t(extent);
+	}
+	out->x = lo[0]; out->y = lo[1]; out->z = lo[2];
+	out->dx = step[0]; out->dy = step[1]; out->dz = step[2];
+	out->sx = size[0]; out->sy = size[1]; out->sz = size[2];
+	return TG_OK;
+}
+
+int tg_export_mesh(tg_model* model, const tg_grid* grid, const tg_mesh_options* options, tg_mesh* out)
+{
+	if (!model || !grid || !out) return Fail(TG_ERR_INVALID, "null argument");
+	tg_mesh_options defaults;
+	std::memset(&defaults, 0, sizeof(defaults));
+	defaults.flags = TG_MESH_NORMALS | TG_MESH_COLORS;
+	defaults.scale = 1.0f;
+	std::string error;
+	model->context->impl->active.store(true); // MeshExport re-arms ExportActive on every call (export.cpp:568)
+	int rc = EngineExportMesh(model->impl.get(), *grid, options ? *options : defaults, out, error);
+	if (rc != TG_OK)
+	{
+		EngineFreeMesh(out);
+		model->context->impl->stage.store(0);
+		return Fail(rc, error);
+	}
+	return TG_OK;
+}
+
+void tg_mesh_free(tg_mesh* mesh)
+{
+	EngineFreeMesh(mesh);
+}
+
+int tg_eval_lattice(tg_model* model, const tg_grid* grid, float* out, float* out_ms)
+{
+	if (!model || !grid) return Fail(TG_ERR_INVALID, "null argument");
+	std::string error;
+	int rc = EngineEvalLattice(model->impl.get(), *grid, out, out_ms, error);
+	return rc == TG_OK ? rc : Fail(rc, error);
+}
+
+int tg_export_points(tg_model* model, const float mn[3], const float mx[3], const float step[3], int refine, uint32_t flags, tg_mesh* out)
+{
+	if (!model || !mn || !mx || !step || !out) return Fail(TG_ERR_INVALID, "null argument");
+	std::string error;
+	model->context->impl->active.store(true);
+	int rc = EngineExportPoints(model->impl.get(), mn, mx, step, refine, flags, out, error);
+	if (rc != TG_OK)
+	{
+		EngineFreeMesh(out);
+		model->context->impl->stage.store(0);
+		return Fail(rc, error);
+	}
+	return TG_OK;
+}
+
+int tg_export_voxels(tg_model* model, float grid_size, int32_t out_size[3], float* out_radius, int32_t** out_xyz, uint64_t* out_count)
+{
+	if (!model || !out_size || !out_radius || !out_xyz || !out_count) return Fail(TG_ERR_INVALID, "null argument");
+	std::string error;
+	int rc = EngineExportVoxels(model->impl.get(), grid_size, out_size, out_radius, out_xyz, out_count, error);
+	return rc == TG_OK ? rc : Fail(rc, error);
+}
+
+void tg_free(void* pointer)
+{
+	std::free(pointer);
+}
+
+int tg_progress(const tg_context* context, float out_ratios[4], int* out_stage)
+{
+	if (!context) return Fail(TG_ERR_INVALID, "null context");
+	const Context* c = context->impl.get();
+	if (out_stage) *out_stage = c->stage.load();
+	if (out_ratios)
+	{
+		for (int i = 0; i < 4; ++i)
+		{
+			const uint64_t total = c->progress_total[i].load();
+			out_ratios[i] = total ? float(double(c->progress_done[i].load()) / double(total)) : 0.0f;
+		}
+	}
+	return TG_OK;
+}
+
+int tg_cancel(tg_context* context, int halt)
+{
+	if (!context) return Fail(TG_ERR_INVALID, "null context");
+	// CancelExport (export.cpp:582-592): Halt stops the export; otherwise the current stage is skipped.
+	// Stages here are whole kernels, so both requests stop at the next stage boundary.
+	(void)halt;
+	context->impl->active.store(false);
+	return TG_OK;
+}
+
+// ---- file-level entry points ---------------------------------------------------------------------
+
+static int ExportFile(const tg_tree* tree, float grid_size, int refine, const char* path, int device, bool stl)
+{
+	TG_REQUIRE_TREE(tree);
+	if (!path || !(grid_size > 0.0f)) return Fail(TG_ERR_INVALID, "bad path or grid size");
+	tg_context* context = tg_context_create(device);
+	if (!context) return TG_ERR_NO_DEVICE;
+	int rc = TG_OK;
+	tg_model* model = tg_model_create(context, tree, 0.25f, 0);
+	if (!model)
+	{
+		rc = TG_ERR_INVALID;
+	}
+	else
+	{
+		// ExportCommon (export.cpp:595-607): bounds of the evaluator, Step = 1 / GridSize
+		tg_model_stats stats;
+		tg_model_get_stats(model, &stats);
+		const float step = float(1.0 / grid_size);
+		const float steps[3] = { step, step, step };
+		tg_grid grid;
+		rc = tg_export_grid(stats.bounds_min, stats.bounds_max, steps, &grid);
+		if (rc == TG_OK)
+		{
+			tg_mesh_options options;
+			std::memset(&options, 0, sizeof(options));
+			options.flags = stl ? TG_MESH_FACE_NORMALS : (TG_MESH_NORMALS | TG_MESH_COLORS);
+			options.refine_iterations = refine;
+			options.scale = 1.0f;
+			tg_mesh mesh;
+			rc = tg_export_mesh(model, &grid, &options, &mesh);
+			if (rc == TG_OK)
+			{
+				rc = stl ? tg_write_stl(path, &mesh) : tg_write_ply(path, &mesh);
+				tg_mesh_free(&mesh);
+			}
+		}
+		tg_model_destroy(model);
+	}
+	tg_context_destroy(context);
+	return rc;
+}
+
+int tg_export_ply(const tg_tree* tree, float grid_size, int refine_iterations, const char* path, int cuda_device)
+{
+	return ExportFile(tree, grid_size, refine_iterations, path, cuda_device, false);
+}
+
+int tg_export_stl(const tg_tree* tree, float grid_size, int refine_iterations, const char* path, int cuda_device)
+{
+	return ExportFile(tree, grid_size, refine_iterations, path, cuda_device, true);
+}
+
+int tg_export_magica_voxel(const tg_tree* tree, float grid_size, int color_index, const char* path, int cuda_device)
+{
+	TG_REQUIRE_TREE(tree);
+	if (!path) return Fail(TG_ERR_INVALID, "null path");
+	tg_context* context = tg_context_create(cuda_device);
+	if (!context) return TG_ERR_NO_DEVICE;
+	int rc = TG_ERR_INVALID;
+	tg_model* model = tg_model_create(context, tree, 0.25f, 0);
+	if (model)
+	{
+		int32_t size[3];
+		float radius = 0.0f;
+		int32_t* xyz = nullptr;
+		uint64_t count = 0;
+		rc = tg_export_voxels(model, grid_size, size, &radius, &xyz, &count);
+		if (rc == TG_OK)
+		{
+			std::string error;
+			if (!WriteVox(path, size, xyz, count, color_index, error)) rc = Fail(TG_ERR_IO, error);
+			tg_free(xyz);
+		}
+		tg_model_destroy(model);
+	}
+	tg_context_destroy(context);
+	return rc;
+}
+
+int tg_write_ply(const char* path, const tg_mesh* mesh)
+{
+	if (!path || !mesh) return Fail(TG_ERR_INVALID, "null argument");
+	std::string error;
+	if (!WritePly(path, mesh->positions, mesh->normals, mesh->colors, mesh->vertex_count, mesh->triangles, mesh->triangle_count, error)) return Fail(TG_ERR_IO, error);
+	return TG_OK;
+}
+
+int tg_write_stl(const char* path, const tg_mesh* mesh)
+{
+	if (!path || !mesh) return Fail(TG_ERR_INVALID, "null argument");
+	std::string error;
+	if (!WriteStl(path, mesh->positions, mesh->normals, mesh->face_normals, mesh->vertex_count, mesh->triangles, mesh->triangle_count, error)) return Fail(TG_ERR_IO, error);
+	return TG_OK;
+}
+
+// ---- measurement helpers -------------------------------------------------------------------------
+
+int tg_timer_begin(tg_context* context)
+{
+	if (!context) return Fail(TG_ERR_INVALID, "null context");
+	std::string error;
+	int rc = EngineTimerBegin(context->impl.get(), error);
+	return rc == TG_OK ? rc : Fail(rc, error);
+}
+
+int tg_timer_end(tg_context* context, float* out_ms)
+{
+	if (!context || !out_ms) return Fail(TG_ERR_INVALID, "null argument");
+	std::string error;
+	int rc = EngineTimerEnd(context->impl.get(), out_ms, error);
+	return rc == TG_OK ? rc : Fail(rc, error);
+}
+
+int tg_measure_fp32_peak(tg_context* context, double* out_tflops)
+{
+	if (!context || !out_tflops) return Fail(TG_ERR_INVALID, "null argument");
+	std::string error;
+	int rc = EngineMeasureFp32Peak(context->impl.get(), out_tflops, error);
+	return rc == TG_OK ? rc : Fail(rc, error);
+}
+
+int tg_flush_l2(tg_context* context)
+{
+	if (!context) return Fail(TG_ERR_INVALID, "null context");
+	std::string error;
+	int rc = EngineFlushL2(context->impl.get(), error);
+	return rc == TG_OK ? rc : Fail(rc, error);
+}
+
+} // extern "C"

@@ -1,0 +1,399 @@
+// Device-side SDF interpreter and octree descent (sm_100a).
+//
+// RunProgram executes one flat program (tg_program.h) for S sample points at once per thread: the
+// operand "stack" is an accumulator register per sample plus statically numbered spill slots that only
+// right-nested operands touch, so the common left-leaning CSG chain runs entirely in registers with one
+// header decode per primitive, amortised over S samples of instruction-level parallelism.  When every
+// lane of a warp was handed the same program (the brick kernels arrange that) the header and parameter
+// loads are warp-uniform broadcasts and the opcode switch does not diverge.
+//
+// Arithmetic contract: this file is compiled with -fmad=false and IEEE sqrt/div so that every distance is
+// bit-identical to the reference's CPU evaluation (see tg_sdf.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tg_program.h"
+#include "tg_sdf.h"
+
+namespace tg
+{
+
+struct DeviceModel
+{
+	const FlatNode* nodes;
+	const uint32_t* interp;
+	const uint32_t* tree;
+	const float* material_rgb; // 3 floats per id
+	uint32_t material_count;   // index of the trailing default-white entry
+	uint32_t root_interp_offset;
+	uint32_t root_tree_offset;
+	uint32_t node_count;
+	int has_paint;
+};
+
+struct DeviceGrid
+{
+	float x, y, z, dx, dy, dz;
+	uint32_t sx, sy, sz; // cells
+};
+
+// get_voxel_corner_world_positions (surface_nets.cpp:648-687): origin + float(index) * step, no FMA
+__device__ __forceinline__ float LatticeCoord(float origin, float step, uint32_t index)
+{
+	return __fadd_rn(origin, __fmul_rn(float(index), step));
+}
+
+// SDFOctree::Descend(Point, Exact = true) (sdf_evaluator.cpp:1801-1835), iteratively from `start`.
+__device__ __forceinline__ uint32_t Descend(const FlatNode* __restrict__ nodes, uint32_t start, float px, float py, float pz)
+{
+	uint32_t n = start;
+	for (;;)
+	{
+		const float4 head = __ldg(reinterpret_cast<const float4*>(&nodes[n])); // pivot.xyz, terminus bits
+		if (__float_as_uint(head.w) != 0u)
+		{
+			return n;
+		}
+		const int octant = (px > head.x ? 1 : 0) | (py > head.y ? 2 : 0) | (pz > head.z ? 4 : 0);
+		const int32_t child = __ldg(&nodes[n].children[octant]);
+		if (child < 0)
+		{
+			return n; // empty octant: the reference evaluates this (larger) node's program
+		}
+		n = uint32_t(child);
+	}
+}
+
+template <int S>
+struct MaterialRegs
+{
+	uint32_t v[S];
+};
+
+// Executes `program` for S points.  MATERIAL selects the GetMaterial walk (tree stream only).
+template <int S, bool MATERIAL>
+__device__ __forceinline__ void RunProgram(const uint32_t* __restrict__ program, const float (&px)[S], const float (&py)[S], const float (&pz)[S],
+	float (&result)[S], uint32_t (&result_material)[S])
+{
+	float acc[S];
+	uint32_t accm[S];
+	float stack[kMaxStackSlots][S];
+	uint32_t stackm[MATERIAL ? kMaxStackSlots : 1][S];
+#pragma unroll
+	for (int s = 0; s < S; ++s)
+	{
+		acc[s] = 0.0f;
+		accm[s] = kNoMaterial;
+	}
+	const uint32_t* pc = program;
+	for (;;)
+	{
+		const uint32_t header = __ldg(pc);
+		const uint32_t brush = header & kHdrBrushMask;
+		const uint32_t op = (header >> kHdrOpShift) & 0xFu;
+		const uint32_t slot = (header >> kHdrSlotShift) & 0xFFu;
+		const float* __restrict__ arg = reinterpret_cast<const float*>(pc + 1);
+		pc += header >> kHdrLenShift;
+
+		if (brush != kBrushNone)
+		{
+			float lx[S], ly[S], lz[S];
+			const uint32_t xform = (header >> kHdrXformShift) & 3u;
+			if (xform == kXformMatrix)
+			{
+				// glm mat4 * vec4(p, 1): (m0*x + m1*y) + (m2*z + m3*1)  (type_mat4x4.inl:561-572)
+				const float m00 = __ldg(arg + 0), m01 = __ldg(arg + 1), m02 = __ldg(arg + 2);
+				const float m10 = __ldg(arg + 3), m11 = __ldg(arg + 4), m12 = __ldg(arg + 5);
+				const float m20 = __ldg(arg + 6), m21 = __ldg(arg + 7), m22 = __ldg(arg + 8);
+				const float m30 = __ldg(arg + 9), m31 = __ldg(arg + 10), m32 = __ldg(arg + 11);
+				arg += 12;
+#pragma unroll
+				for (int s = 0; s < S; ++s)
+				{
+					lx[s] = (m00 * px[s] + m10 * py[s]) + (m20 * pz[s] + m30);
+					ly[s] = (m01 * px[s] + m11 * py[s]) + (m21 * pz[s] + m31);
+					lz[s] = (m02 * px[s] + m12 * py[s]) + (m22 * pz[s] + m32);
+				}
+			}
+			else if (xform == kXformOffset)
+			{
+				const float ox = __ldg(arg + 0), oy = __ldg(arg + 1), oz = __ldg(arg + 2);
+				arg += 3;
+#pragma unroll
+				for (int s = 0; s < S; ++s)
+				{
+					lx[s] = px[s] + ox;
+					ly[s] = py[s] + oy;
+					lz[s] = pz[s] + oz;
+				}
+			}
+			else if (xform == kXformQuat)
+			{
+				// Transform::ApplyInv (transform.cpp:64-67): rotate(inverse(q), p - t) / s, glm quat * vec3 (type_quat.inl:343-350)
+				const float qw = __ldg(arg + 0), qx = __ldg(arg + 1), qy = __ldg(arg + 2), qz = __ldg(arg + 3);
+				const float tx = __ldg(arg + 4), ty = __ldg(arg + 5), tz = __ldg(arg + 6), sc = __ldg(arg + 7);
+				arg += 8;
+#pragma unroll
+				for (int s = 0; s < S; ++s)
+				{
+					const float vx = px[s] - tx, vy = py[s] - ty, vz = pz[s] - tz;
+					const float uvx = qy * vz - vy * qz, uvy = qz * vx - vz * qx, uvz = qx * vy - vx * qy;
+					const float uuvx = qy * uvz - uvy * qz, uuvy = qz * uvx - uvz * qx, uuvz = qx * uvy - uvx * qy;
+					lx[s] = (vx + ((uvx * qw) + uuvx) * 2.0f) / sc;
+					ly[s] = (vy + ((uvy * qw) + uuvy) * 2.0f) / sc;
+					lz[s] = (vz + ((uvz * qw) + uuvz) * 2.0f) / sc;
+				}
+			}
+			else
+			{
+#pragma unroll
+				for (int s = 0; s < S; ++s)
+				{
+					lx[s] = px[s];
+					ly[s] = py[s];
+					lz[s] = pz[s];
+				}
+			}
+
+			float d[S];
+			switch (brush)
+			{
+			case kBrushSphere:
+			{
+				const float r = __ldg(arg);
+				arg += 1;
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Sphere(lx[s], ly[s], lz[s], r);
+				break;
+			}
+			case kBrushEllipsoid:
+			{
+				const float a = __ldg(arg), b = __ldg(arg + 1), c = __ldg(arg + 2);
+				arg += 3;
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Ellipsoid(lx[s], ly[s], lz[s], a, b, c);
+				break;
+			}
+			case kBrushBox:
+			{
+				const float a = __ldg(arg), b = __ldg(arg + 1), c = __ldg(arg + 2);
+				arg += 3;
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Box(lx[s], ly[s], lz[s], a, b, c);
+				break;
+			}
+			case kBrushTorus:
+			{
+				const float a = __ldg(arg), b = __ldg(arg + 1);
+				arg += 2;
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Torus(lx[s], ly[s], lz[s], a, b);
+				break;
+			}
+			case kBrushCylinder:
+			{
+				const float a = __ldg(arg), b = __ldg(arg + 1);
+				arg += 2;
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Cylinder(lx[s], ly[s], lz[s], a, b);
+				break;
+			}
+			case kBrushCone:
+			{
+				const float a = __ldg(arg), b = __ldg(arg + 1);
+				arg += 2;
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Cone(lx[s], ly[s], lz[s], a, b);
+				break;
+			}
+			case kBrushConinder:
+			{
+				const float a = __ldg(arg), b = __ldg(arg + 1), c = __ldg(arg + 2);
+				arg += 3;
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Coninder(lx[s], ly[s], lz[s], a, b, c);
+				break;
+			}
+			default:
+			{
+				const float a = __ldg(arg), b = __ldg(arg + 1), c = __ldg(arg + 2);
+				arg += 3;
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Plane(lx[s], ly[s], lz[s], a, b, c);
+				break;
+			}
+			}
+			if (header & kHdrScaleBit)
+			{
+				const float sc = __ldg(arg);
+				arg += 1;
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = d[s] * sc; // ScaleField (:1587-1591) / BrushNode::Eval `* Scalation` (:465)
+			}
+			uint32_t material = kNoMaterial;
+			if (header & kHdrMaterialBit)
+			{
+				material = __ldg(reinterpret_cast<const uint32_t*>(arg));
+				arg += 1;
+			}
+
+			if (op == kOpPush)
+			{
+				if (slot != kNoSlot)
+				{
+#pragma unroll
+					for (int s = 0; s < S; ++s)
+					{
+						stack[slot][s] = acc[s];
+						if (MATERIAL) stackm[slot][s] = accm[s];
+					}
+				}
+#pragma unroll
+				for (int s = 0; s < S; ++s)
+				{
+					acc[s] = d[s];
+					accm[s] = material;
+				}
+			}
+			else
+			{
+				const float threshold = (op >= kOpBlendUnion) ? __ldg(arg) : 0.0f;
+#pragma unroll
+				for (int s = 0; s < S; ++s)
+				{
+					const float l = acc[s];
+					const float r = d[s];
+					const float dist = sdf::SetOp(op, l, r, threshold);
+					if (MATERIAL)
+					{
+						// SetNode::GetMaterial (:957-1012)
+						const bool take_left = (op >= kOpBlendUnion) ? (fabsf(l - dist) <= fabsf(r - dist)) : (dist == l);
+						const uint32_t family = (op - 1u) % 3u; // 0 union, 1 inter, 2 diff
+						uint32_t m;
+						if (family == 2u) m = accm[s];
+						else if (family == 0u) m = take_left ? accm[s] : material;
+						else
+						{
+							const bool lv = (header & kHdrLhsPaintBit) != 0, rv = (header & kHdrRhsPaintBit) != 0;
+							m = (lv && rv) ? (take_left ? accm[s] : material) : (lv ? accm[s] : material);
+						}
+						accm[s] = m;
+					}
+					acc[s] = dist;
+				}
+			}
+		}
+		else if (op == kOpStop)
+		{
+#pragma unroll
+			for (int s = 0; s < S; ++s)
+			{
+				result[s] = acc[s];
+				result_material[s] = accm[s];
+			}
+			return;
+		}
+		else if (op == kOpFlate)
+		{
+			const float radius = __ldg(arg);
+#pragma unroll
+			for (int s = 0; s < S; ++s) acc[s] = acc[s] - radius; // :1567-1571
+		}
+		else if (op == kOpStencil)
+		{
+			// StencilMaskNode::GetMaterial (:666-679): accumulator holds the mask distance, the child is on the stack
+			const uint32_t material = __ldg(reinterpret_cast<const uint32_t*>(arg));
+			const bool apply_to_negative = (header & kHdrStencilNegBit) != 0;
+#pragma unroll
+			for (int s = 0; s < S; ++s)
+			{
+				const bool interior = acc[s] < 0.0f;
+				acc[s] = stack[slot][s];
+				if (MATERIAL) accm[s] = (interior == apply_to_negative) ? material : stackm[slot][s];
+			}
+		}
+		else
+		{
+			// stack-form set operator: lhs was spilled, rhs is the accumulator
+			const float threshold = (op >= kOpBlendUnion) ? __ldg(arg) : 0.0f;
+#pragma unroll
+			for (int s = 0; s < S; ++s)
+			{
+				const float l = stack[slot][s];
+				const float r = acc[s];
+				const float dist = sdf::SetOp(op, l, r, threshold);
+				if (MATERIAL)
+				{
+					const uint32_t ml = stackm[slot][s], mr = accm[s];
+					const bool take_left = (op >= kOpBlendUnion) ? (fabsf(l - dist) <= fabsf(r - dist)) : (dist == l);
+					const uint32_t family = (op - 1u) % 3u;
+					uint32_t m;
+					if (family == 2u) m = ml;
+					else if (family == 0u) m = take_left ? ml : mr;
+					else
+					{
+						const bool lv = (header & kHdrLhsPaintBit) != 0, rv = (header & kHdrRhsPaintBit) != 0;
+						m = (lv && rv) ? (take_left ? ml : mr) : (lv ? ml : mr);
+					}
+					accm[s] = m;
+				}
+				acc[s] = dist;
+			}
+		}
+	}
+}
+
+// Convenience wrappers -------------------------------------------------------------------------------
+
+template <int S>
+__device__ __forceinline__ void EvalDistance(const uint32_t* __restrict__ program, const float (&px)[S], const float (&py)[S], const float (&pz)[S], float (&out)[S])
+{
+	uint32_t unused[S];
+	RunProgram<S, false>(program, px, py, pz, out, unused);
+}
+
+__device__ __forceinline__ float EvalDistance1(const uint32_t* __restrict__ program, float x, float y, float z)
+{
+	float px[1] = { x }, py[1] = { y }, pz[1] = { z }, out[1];
+	uint32_t unused[1];
+	RunProgram<1, false>(program, px, py, pz, out, unused);
+	return out[0];
+}
+
+// SDFNode::Gradient (sdf_evaluator.cpp:298-333) on a tree-stream program: the four tetrahedral taps are
+// the four samples of one RunProgram<4> call.
+__device__ __forceinline__ void EvalGradient(const uint32_t* __restrict__ tree_program, float x, float y, float z, float& gx, float& gy, float& gz)
+{
+	const float ox = 1.0f * 0.0001f;
+	const float oy = -1.0f * 0.0001f;
+	// taps: xyy, yyx, yxy, xxx
+	const float px[4] = { x + ox, x + oy, x + oy, x + ox };
+	const float py[4] = { y + oy, y + oy, y + ox, y + ox };
+	const float pz[4] = { z + oy, z + ox, z + oy, z + ox };
+	float d[4];
+	EvalDistance<4>(tree_program, px, py, pz, d);
+	// Offset.xyy * d0 + Offset.yyx * d1 + Offset.yxy * d2 + Offset.xxx * d3, summed left to right
+	float sx = ((ox * d[0] + oy * d[1]) + oy * d[2]) + ox * d[3];
+	float sy = ((oy * d[0] + oy * d[1]) + ox * d[2]) + ox * d[3];
+	float sz = ((oy * d[0] + ox * d[1]) + oy * d[2]) + ox * d[3];
+	const float len_sq = sx * sx + sy * sy + sz * sz;
+	if (len_sq == 0.0f)
+	{
+		// zero gradient: forward differences (:320-328); taps xyy, yxy, yyx are d[0], d[2], d[1]
+		const float dist = EvalDistance1(tree_program, x, y, z);
+		const float fx = d[0] - dist, fy = d[2] - dist, fz = d[1] - dist;
+		const float inv = 1.0f / sqrtf(fx * fx + fy * fy + fz * fz); // glm::normalize = v * inversesqrt(dot(v, v))
+		gx = fx * inv;
+		gy = fy * inv;
+		gz = fz * inv;
+		return;
+	}
+	const float len = sqrtf(len_sq);
+	gx = sx / len;
+	gy = sy / len;
+	gz = sz / len;
+}
+
+} // namespace tg

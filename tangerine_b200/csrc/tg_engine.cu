@@ -1,0 +1,1950 @@
+// CUDA engine for the SDF meshing hot path (sm_100a).  See DESIGN.md for the pipeline and data layout.
+//
+//   K0  CullLevelKernel        hierarchical Lipschitz culling of empty space: 64^3 -> 8^3 cell bricks
+//   K1  MeshBricksKernel       per active 8^3 brick: octree descent per lattice sample, node-coherent
+//       (+K2 fused)            re-binning, postfix interpreter (4 samples / lane), 9^3 tile in shared memory,
+//                              sign classification, surface-nets vertex, ballot-compacted writes
+//   --  BitmapCount/Scan/Prefix  device-wide exclusive scan over the active-cell bitmap (vertex numbering)
+//   K3  ScatterVerticesKernel  final (k, j, i)-lexicographic vertex order + per-cell quad mask
+//       EmitTrianglesKernel    quads from the three lower neighbours (reference's active-only rule)
+//   K4  AttributesKernel       fused gradient-descent refinement + normal + colour per vertex
+//   K5  VoxelKernel / PointCloudKernel   dense centre sampling (MagicaVoxel / point-cloud export)
+//
+// There is no CPU fallback: every entry point fails with TG_ERR_NO_DEVICE / TG_ERR_CUDA when the device or
+// the sm_100a kernel image is unavailable.
+#include "tg_engine.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include <cuda_runtime.h>
+
+#include "tg_device.cuh"
+
+namespace tg
+{
+
+#define TG_CUDA(call)                                                                                           \
+	do                                                                                                          \
+	{                                                                                                           \
+		cudaError_t tg_err_ = (call);                                                                           \
+		if (tg_err_ != cudaSuccess)                                                                             \
+		{                                                                                                       \
+			error = std::string(#call) + ": " + cudaGetErrorString(tg_err_);                                   \
+			return (tg_err_ == cudaErrorNoDevice || tg_err_ == cudaErrorInsufficientDriver ||                  \
+					   tg_err_ == cudaErrorNoKernelImageForDevice || tg_err_ == cudaErrorInvalidDevice)        \
+				? TG_ERR_NO_DEVICE                                                                              \
+				: (tg_err_ == cudaErrorMemoryAllocation ? TG_ERR_MEMORY : TG_ERR_CUDA);                         \
+		}                                                                                                       \
+	} while (0)
+
+constexpr int kBrick = 8;                 // cells per brick edge
+constexpr int kTile = kBrick + 1;         // lattice samples per brick edge
+constexpr int kTileSamples = kTile * kTile * kTile; // 729
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kLaneSamples = 4;           // samples interpreted per lane per dispatch
+constexpr int kChunk = 32 * kLaneSamples; // samples per warp work item
+constexpr int kMaxGroups = 16;            // distinct octree nodes per brick handled by the coherent path
+constexpr int kMaxChunks = 32;
+constexpr uint32_t kEmptyGroup = 0xFFFFFFFFu;
+constexpr uint32_t kHaloFlag = 1u << 30;
+constexpr int kTopLevel = 3;              // 8 << 3 = 64-cell bricks at the top of the cull hierarchy
+
+enum Counter
+{
+	kCntTmpVertices = 0,
+	kCntSamples = 1,
+	kCntFlops = 2,
+	kCntListA = 3,
+	kCntListB = 4,
+	kCntTotalVertices = 5,
+	kCntTotalQuads = 6,
+	kCntHalo = 7,
+	kCntCount = 8
+};
+
+struct MeshParams
+{
+	DeviceModel model;
+	DeviceGrid grid;
+	const uint32_t* bricks;
+	uint32_t brick_count;
+	unsigned long long* bitmap; // one bit per cell, rows padded to 64 cells; layer 0 = cell layer k_base
+	uint32_t row_words;
+	uint32_t k_base;
+	uint32_t k_own_begin, k_own_end;
+	float4* tmp_pos;            // xyz + orientation bits
+	unsigned long long* tmp_key; // bit index in the bitmap
+	uint32_t tmp_capacity;
+	unsigned long long* counters;
+};
+
+// ------------------------------------------------------------------------------------------------
+// K1 + K2: evaluate one brick's 9^3 lattice tile and extract its surface-nets vertices
+// ------------------------------------------------------------------------------------------------
+
+struct BrickShared
+{
+	float tile[kTileSamples];
+	uint32_t node[kTileSamples];
+	uint16_t order[kTileSamples + 7];
+	uint32_t group_node[kMaxGroups];
+	uint32_t group_count[kMaxGroups];
+	uint32_t group_start[kMaxGroups];
+	uint16_t chunk_group[kMaxChunks];
+	uint16_t chunk_begin[kMaxChunks];
+	uint16_t chunk_count[kMaxChunks];
+	int chunk_total;
+	int overflow;
+	uint32_t emit_count;
+	uint32_t emit_base;
+};
+
+// Evaluates the lattice samples (li < ni, lj < nj, kmin <= lk < nk) of a tile whose corner sample has lattice
+// index (i0, j0, k0) into sh.tile.  Samples are first mapped to their octree node (SDFOctree::Descend), then
+// re-binned so that every warp work item holds up to 128 samples of ONE node, and interpreted 4 per lane.
+__device__ __forceinline__ void EvaluateTile(BrickShared& sh, const DeviceModel& model, const DeviceGrid& grid,
+	uint32_t i0, uint32_t j0, uint32_t k0, int ni, int nj, int nk, int kmin, unsigned long long* counters)
+{
+	const int tid = threadIdx.x;
+	const int lane = tid & 31;
+	const int warp = tid >> 5;
+
+	if (tid < kMaxGroups)
+	{
+		sh.group_node[tid] = kEmptyGroup;
+		sh.group_count[tid] = 0;
+	}
+	if (tid == 0)
+	{
+		sh.overflow = 0;
+		sh.chunk_total = 0;
+	}
+
+	// Brick-level descent: follow the octree while the whole tile lies in one octant.
+	uint32_t start = 0;
+	{
+		const float lox = LatticeCoord(grid.x, grid.dx, i0), loy = LatticeCoord(grid.y, grid.dy, j0), loz = LatticeCoord(grid.z, grid.dz, k0 + kmin);
+		const float hix = LatticeCoord(grid.x, grid.dx, i0 + ni - 1), hiy = LatticeCoord(grid.y, grid.dy, j0 + nj - 1), hiz = LatticeCoord(grid.z, grid.dz, k0 + nk - 1);
+		for (;;)
+		{
+			const float4 head = __ldg(reinterpret_cast<const float4*>(&model.nodes[start]));
+			if (__float_as_uint(head.w) != 0u) break;
+			const int olo = (lox > head.x ? 1 : 0) | (loy > head.y ? 2 : 0) | (loz > head.z ? 4 : 0);
+			const int ohi = (hix > head.x ? 1 : 0) | (hiy > head.y ? 2 : 0) | (hiz > head.z ? 4 : 0);
+			if (olo != ohi) break;
+			const int32_t child = __ldg(&model.nodes[start].children[olo]);
+			if (child < 0) break;
+			start = uint32_t(child);
+		}
+	}
+	__syncthreads();
+
+	// Per-sample descent + warp-aggregated insertion into the brick's node table.
+	uint32_t my_group[3];
+	uint32_t my_rank[3];
+#pragma unroll
+	for (int it = 0; it < 3; ++it)
+	{
+		const int s = tid + it * kThreads;
+		my_group[it] = kEmptyGroup;
+		my_rank[it] = 0;
+		uint32_t node = kEmptyGroup;
+		if (s < kTileSamples)
+		{
+			const int li = s % kTile, lj = (s / kTile) % kTile, lk = s / (kTile * kTile);
+			if (li < ni && lj < nj && lk < nk && lk >= kmin)
+			{
+				node = Descend(model.nodes, start, LatticeCoord(grid.x, grid.dx, i0 + li), LatticeCoord(grid.y, grid.dy, j0 + lj), LatticeCoord(grid.z, grid.dz, k0 + lk));
+			}
+			sh.node[s] = node;
+		}
+		const unsigned peers = __match_any_sync(0xFFFFFFFFu, node);
+		if (node != kEmptyGroup)
+		{
+			const int leader = __ffs(peers) - 1;
+			uint32_t group = kEmptyGroup, base = 0;
+			if (lane == leader)
+			{
+				for (int g = 0; g < kMaxGroups; ++g)
+				{
+					uint32_t seen = sh.group_node[g];
+					if (seen == kEmptyGroup)
+					{
+						seen = atomicCAS(&sh.group_node[g], kEmptyGroup, node);
+						if (seen == kEmptyGroup) seen = node;
+					}
+					if (seen == node)
+					{
+						group = uint32_t(g);
+						base = atomicAdd(&sh.group_count[g], uint32_t(__popc(peers)));
+						break;
+					}
+				}
+				if (group == kEmptyGroup) sh.overflow = 1;
+			}
+			group = __shfl_sync(peers, group, leader);
+			base = __shfl_sync(peers, base, leader);
+			my_group[it] = group;
+			my_rank[it] = base + uint32_t(__popc(peers & ((1u << lane) - 1u)));
+		}
+	}
+	__syncthreads();
+
+	const bool overflow = sh.overflow != 0;
+	if (!overflow)
+	{
+		if (warp == 0)
+		{
+			// Lane g owns group g: exclusive scans give each group its slice of `order` and of the chunk list.
+			const uint32_t count = lane < kMaxGroups ? sh.group_count[lane] : 0u;
+			const uint32_t chunks = (count + kChunk - 1) / kChunk;
+			uint32_t count_incl = count, chunk_incl = chunks;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, count_incl, o);
+				const uint32_t b = __shfl_up_sync(0xFFFFFFFFu, chunk_incl, o);
+				if (lane >= o)
+				{
+					count_incl += a;
+					chunk_incl += b;
+				}
+			}
+			const uint32_t start = count_incl - count;
+			if (lane < kMaxGroups) sh.group_start[lane] = start;
+			for (uint32_t b = 0; b < chunks; ++b)
+			{
+				const uint32_t c = chunk_incl - chunks + b;
+				sh.chunk_group[c] = uint16_t(lane);
+				sh.chunk_begin[c] = uint16_t(start + b * kChunk);
+				sh.chunk_count[c] = uint16_t(min(uint32_t(kChunk), count - b * kChunk));
+			}
+			const uint32_t flops = count ? count * __ldg(&model.nodes[sh.group_node[lane]].flops) : 0u;
+			const uint32_t flops_total = __reduce_add_sync(0xFFFFFFFFu, flops);
+			if (lane == 31)
+			{
+				sh.chunk_total = int(chunk_incl);
+				atomicAdd(&counters[kCntSamples], (unsigned long long)count_incl);
+				atomicAdd(&counters[kCntFlops], (unsigned long long)flops_total);
+			}
+		}
+		__syncthreads();
+#pragma unroll
+		for (int it = 0; it < 3; ++it)
+		{
+			if (my_group[it] != kEmptyGroup)
+			{
+				sh.order[sh.group_start[my_group[it]] + my_rank[it]] = uint16_t(tid + it * kThreads);
+			}
+		}
+		__syncthreads();
+
+		const int chunk_total = sh.chunk_total;
+		for (int c = warp; c < chunk_total; c += kWarps)
+		{
+			const int begin = sh.chunk_begin[c];
+			const int count = sh.chunk_count[c];
+			const uint32_t node = sh.group_node[sh.chunk_group[c]];
+			const uint32_t* program = model.interp + __ldg(&model.nodes[node].interp_offset);
+			float px[kLaneSamples], py[kLaneSamples], pz[kLaneSamples], d[kLaneSamples];
+			int sample[kLaneSamples];
+#pragma unroll
+			for (int q = 0; q < kLaneSamples; ++q)
+			{
+				const int idx = lane + 32 * q;
+				const int s = sh.order[begin + (idx < count ? idx : 0)];
+				sample[q] = idx < count ? s : -1;
+				const int li = s % kTile, lj = (s / kTile) % kTile, lk = s / (kTile * kTile);
+				px[q] = LatticeCoord(grid.x, grid.dx, i0 + li);
+				py[q] = LatticeCoord(grid.y, grid.dy, j0 + lj);
+				pz[q] = LatticeCoord(grid.z, grid.dz, k0 + lk);
+			}
+			EvalDistance<kLaneSamples>(program, px, py, pz, d);
+#pragma unroll
+			for (int q = 0; q < kLaneSamples; ++q)
+			{
+				if (sample[q] >= 0) sh.tile[sample[q]] = d[q];
+			}
+		}
+	}
+	else
+	{
+		// More distinct nodes than the table holds (tiny leaves vs. a coarse grid): per-lane programs.
+		unsigned long long flops = 0, samples = 0;
+		for (int s = tid; s < kTileSamples; s += kThreads)
+		{
+			const uint32_t node = sh.node[s];
+			if (node == kEmptyGroup) continue;
+			const int li = s % kTile, lj = (s / kTile) % kTile, lk = s / (kTile * kTile);
+			sh.tile[s] = EvalDistance1(model.interp + model.nodes[node].interp_offset,
+				LatticeCoord(grid.x, grid.dx, i0 + li), LatticeCoord(grid.y, grid.dy, j0 + lj), LatticeCoord(grid.z, grid.dz, k0 + lk));
+			flops += model.nodes[node].flops;
+			samples++;
+		}
+		atomicAdd(&counters[kCntSamples], samples);
+		atomicAdd(&counters[kCntFlops], flops);
+	}
+	__syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads) MeshBricksKernel(const MeshParams p)
+{
+	__shared__ BrickShared sh;
+	const DeviceGrid& grid = p.grid;
+	const int tid = threadIdx.x;
+	const int lane = tid & 31;
+
+	const uint32_t brick = p.bricks[blockIdx.x];
+	const uint32_t bx = brick & 1023u, by = (brick >> 10) & 1023u, bz = (brick >> 20) & 1023u;
+	const bool halo = (brick & kHaloFlag) != 0;
+	const uint32_t i0 = bx * kBrick, j0 = by * kBrick, k0 = bz * kBrick;
+	const int ni = int(min(uint32_t(kTile), grid.sx + 1 - i0));
+	const int nj = int(min(uint32_t(kTile), grid.sy + 1 - j0));
+	const int nk = int(min(uint32_t(kTile), grid.sz + 1 - k0));
+	const int kmin = halo ? kBrick - 1 : 0; // halo bricks only need their top cell layer
+
+	if (tid == 0) sh.emit_count = 0;
+	EvaluateTile(sh, p.model, grid, i0, j0, k0, ni, nj, nk, kmin, p.counters);
+
+	// Classification + vertex extraction: FirstLoopInnerThunk (surface_nets.cpp:864-974)
+	const float bbminx = grid.x, bbminy = grid.y, bbminz = grid.z;
+	const float bbmaxx = __fadd_rn(grid.x, __fmul_rn(float(grid.sx), grid.dx));
+	const float bbmaxy = __fadd_rn(grid.y, __fmul_rn(float(grid.sy), grid.dy));
+	const float bbmaxz = __fadd_rn(grid.z, __fmul_rn(float(grid.sz), grid.dz));
+	unsigned char* bitmap_bytes = reinterpret_cast<unsigned char*>(p.bitmap);
+
+	float4 rec_pos[2];
+	unsigned long long rec_key[2];
+	uint32_t rec_slot[2];
+#pragma unroll
+	for (int it = 0; it < 2; ++it)
+	{
+		const int c = tid + it * kThreads;
+		const int ci = c & 7, cj = (c >> 3) & 7, ck = c >> 6;
+		const uint32_t gi = i0 + ci, gj = j0 + cj, gk = k0 + ck;
+		const bool in_grid = gi < grid.sx && gj < grid.sy && gk < grid.sz && ck >= kmin;
+		bool active = false;
+		float v[8];
+		if (in_grid)
+		{
+			const float* t = sh.tile + (ck * kTile + cj) * kTile + ci;
+			// corner numbering of get_voxel_corner_grid_positions (surface_nets.cpp:632-646)
+			v[0] = t[0];
+			v[1] = t[1];
+			v[2] = t[kTile + 1];
+			v[3] = t[kTile];
+			v[4] = t[kTile * kTile];
+			v[5] = t[kTile * kTile + 1];
+			v[6] = t[kTile * kTile + kTile + 1];
+			v[7] = t[kTile * kTile + kTile];
+			// is_scalar_positive is `scalar >= isovalue` (:733-735): -0.0 is positive, NaN is negative
+			unsigned signs = 0;
+#pragma unroll
+			for (int k = 0; k < 8; ++k) signs |= (v[k] >= 0.0f ? 1u : 0u) << k;
+			active = signs != 0u && signs != 0xFFu;
+		}
+		const unsigned ballot = __ballot_sync(0xFFFFFFFFu, active);
+		// Each warp covers 4 rows of 8 cells: lanes 0, 8, 16, 24 publish their row's byte.
+		if ((lane & 7) == 0)
+		{
+			const unsigned byte = (ballot >> lane) & 0xFFu;
+			const bool layer_ok = gk >= p.k_base && gk < p.k_own_end && gj < grid.sy && ck >= kmin;
+			if (byte != 0u && layer_ok)
+			{
+				bitmap_bytes[(size_t(gk - p.k_base) * grid.sy + gj) * (size_t(p.row_words) * 8u) + bx] = (unsigned char)byte;
+			}
+		}
+		rec_slot[it] = 0xFFFFFFFFu;
+		const bool emit = active && !halo && gk >= p.k_own_begin && gk < p.k_own_end;
+		if (emit)
+		{
+			const float fi = float(gi), fj = float(gj), fk = float(gk);
+			const float gx[8] = { fi, fi + 1.f, fi + 1.f, fi, fi, fi + 1.f, fi + 1.f, fi };
+			const float gy[8] = { fj, fj, fj + 1.f, fj + 1.f, fj, fj, fj + 1.f, fj + 1.f };
+			const float gz[8] = { fk, fk, fk, fk, fk + 1.f, fk + 1.f, fk + 1.f, fk + 1.f };
+			const int e0[12] = { 0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3 }; // edge table :889-901
+			const int e1[12] = { 1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7 };
+			float sx = 0.f, sy = 0.f, sz = 0.f;
+			int n = 0;
+#pragma unroll
+			for (int e = 0; e < 12; ++e)
+			{
+				const float s1 = v[e0[e]], s2 = v[e1[e]];
+				if ((s1 >= 0.0f) != (s2 >= 0.0f))
+				{
+					const float t = (0.0f - s1) / (s2 - s1); // :937
+					sx = sx + (gx[e0[e]] + t * (gx[e1[e]] - gx[e0[e]]));
+					sy = sy + (gy[e0[e]] + t * (gy[e1[e]] - gy[e0[e]]));
+					sz = sz + (gz[e0[e]] + t * (gz[e1[e]] - gz[e0[e]]));
+					n++;
+				}
+			}
+			const float count = float(n);
+			const float cx = sx / count, cy = sy / count, cz = sz / count;
+			// :952-965  min + (max - min) * (centre - 0) / (size - 0)
+			const float px = bbminx + (bbmaxx - bbminx) * (cx - 0.f) / (float(grid.sx) - 0.f);
+			const float py = bbminy + (bbmaxy - bbminy) * (cy - 0.f) / (float(grid.sy) - 0.f);
+			const float pz = bbminz + (bbmaxz - bbminz) * (cz - 0.f) / (float(grid.sz) - 0.f);
+			// winding bits for SecondLoopThunk (:1041-1067, :1103-1105): edge (0,4), (3,0), (0,1)
+			const uint32_t orient = (v[4] > v[0] ? 1u : 0u) | (v[0] > v[3] ? 2u : 0u) | (v[1] > v[0] ? 4u : 0u);
+			rec_pos[it] = make_float4(px, py, pz, __uint_as_float(orient));
+			rec_key[it] = ((unsigned long long)(gk - p.k_base) * grid.sy + gj) * ((unsigned long long)p.row_words * 64ull) + gi;
+		}
+		const unsigned emit_ballot = __ballot_sync(0xFFFFFFFFu, emit);
+		uint32_t warp_base = 0;
+		if (lane == 0 && emit_ballot) warp_base = atomicAdd(&sh.emit_count, uint32_t(__popc(emit_ballot)));
+		warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 0);
+		if (emit) rec_slot[it] = warp_base + uint32_t(__popc(emit_ballot & ((1u << lane) - 1u)));
+	}
+	__syncthreads();
+	if (tid == 0)
+	{
+		sh.emit_base = sh.emit_count ? uint32_t(atomicAdd(&p.counters[kCntTmpVertices], (unsigned long long)sh.emit_count)) : 0u;
+	}
+	__syncthreads();
+	const uint32_t base = sh.emit_base;
+#pragma unroll
+	for (int it = 0; it < 2; ++it)
+	{
+		if (rec_slot[it] != 0xFFFFFFFFu)
+		{
+			const uint32_t dst = base + rec_slot[it];
+			if (dst < p.tmp_capacity)
+			{
+				p.tmp_pos[dst] = rec_pos[it];
+				p.tmp_key[dst] = rec_key[it];
+			}
+		}
+	}
+}
+
+// Dense lattice dump: one 8^3 tile of samples per block, written to a (sz+1, sy+1, sx+1) array.
+__global__ void __launch_bounds__(kThreads) LatticeKernel(const DeviceModel model, const DeviceGrid grid, float* __restrict__ out,
+	uint32_t tiles_x, uint32_t tiles_y, unsigned long long* counters)
+{
+	__shared__ BrickShared sh;
+	const uint32_t tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y, tz = blockIdx.x / (tiles_x * tiles_y);
+	const uint32_t i0 = tx * kBrick, j0 = ty * kBrick, k0 = tz * kBrick;
+	const uint32_t nx = grid.sx + 1, ny = grid.sy + 1, nz = grid.sz + 1;
+	const int ni = int(min(uint32_t(kBrick), nx - i0)), nj = int(min(uint32_t(kBrick), ny - j0)), nk = int(min(uint32_t(kBrick), nz - k0));
+	EvaluateTile(sh, model, grid, i0, j0, k0, ni, nj, nk, 0, counters);
+	if (out == nullptr) return;
+	for (int s = threadIdx.x; s < kBrick * kBrick * kBrick; s += kThreads)
+	{
+		const int li = s & 7, lj = (s >> 3) & 7, lk = s >> 6;
+		if (li < ni && lj < nj && lk < nk)
+		{
+			out[(size_t(k0 + lk) * ny + (j0 + lj)) * nx + (i0 + li)] = sh.tile[(lk * kTile + lj) * kTile + li];
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: hierarchical empty-space culling
+// ------------------------------------------------------------------------------------------------
+
+struct CullParams
+{
+	DeviceModel model;
+	DeviceGrid grid;
+	const uint32_t* in_list;
+	uint32_t in_count;
+	uint32_t* out_list;
+	unsigned long long* out_counter;
+	uint32_t out_capacity;
+	int level;          // input bricks are (8 << level) cells wide
+	uint32_t k_begin, k_end; // cell layers that may produce output bricks
+	int halo;           // input is the halo brick layer: restrict the test to its top cell layer, flag the output
+	int no_cull;
+};
+
+// A brick is skipped only when every octree node that any of its lattice samples can descend to has a
+// cullable (1-Lipschitz) program whose value at the brick centre exceeds the brick's half diagonal, all
+// with the same sign: then no cell of the brick has a bipolar edge, whichever program each sample uses.
+__device__ bool BrickIsEmpty(const DeviceModel& model, float lox, float loy, float loz, float hix, float hiy, float hiz)
+{
+	const float cx = 0.5f * (lox + hix), cy = 0.5f * (loy + hiy), cz = 0.5f * (loz + hiz);
+	const float ex = hix - lox, ey = hiy - loy, ez = hiz - loz;
+	const float radius = 0.5f * sqrtf(ex * ex + ey * ey + ez * ez);
+	const float threshold = radius * 1.001f + 1.0e-4f;
+	uint32_t stack[64];
+	int sp = 0;
+	stack[sp++] = 0;
+	int sign = 0;
+	int visited = 0;
+	while (sp > 0)
+	{
+		const uint32_t n = stack[--sp];
+		if (++visited > 96) return false;
+		const float4 head = __ldg(reinterpret_cast<const float4*>(&model.nodes[n]));
+		bool need_self = __float_as_uint(head.w) != 0u;
+		if (!need_self)
+		{
+			const bool hi1[3] = { hix > head.x, hiy > head.y, hiz > head.z };   // some sample takes the upper octant
+			const bool lo0[3] = { !(lox > head.x), !(loy > head.y), !(loz > head.z) }; // some sample takes the lower octant
+			for (int o = 0; o < 8; ++o)
+			{
+				const bool reach = ((o & 1) ? hi1[0] : lo0[0]) && ((o & 2) ? hi1[1] : lo0[1]) && ((o & 4) ? hi1[2] : lo0[2]);
+				if (!reach) continue;
+				const int32_t child = __ldg(&model.nodes[n].children[o]);
+				if (child < 0) need_self = true;
+				else
+				{
+					if (sp >= 64) return false;
+					stack[sp++] = uint32_t(child);
+				}
+			}
+		}
+		if (need_self)
+		{
+			if ((__ldg(&model.nodes[n].flags) & kNodeCullable) == 0u) return false;
+			const float d = EvalDistance1(model.interp + __ldg(&model.nodes[n].interp_offset), cx, cy, cz);
+			if (!(fabsf(d) > threshold)) return false;
+			const int s = d > 0.0f ? 1 : -1;
+			if (sign == 0) sign = s;
+			else if (sign != s) return false;
+		}
+	}
+	return true;
+}
+
+__global__ void __launch_bounds__(128) CullLevelKernel(const CullParams p)
+{
+	const uint32_t index = blockIdx.x * blockDim.x + threadIdx.x;
+	if (index >= p.in_count) return;
+	const uint32_t brick = p.in_list[index];
+	const uint32_t bx = brick & 1023u, by = (brick >> 10) & 1023u, bz = (brick >> 20) & 1023u;
+	const uint32_t width = uint32_t(kBrick) << p.level;
+	const DeviceGrid& g = p.grid;
+	const uint32_t i0 = bx * width, j0 = by * width, k0 = bz * width;
+	const uint32_t i1 = min(i0 + width, g.sx), j1 = min(j0 + width, g.sy);
+	uint32_t klo = max(k0, p.k_begin), k1 = min(min(k0 + width, g.sz), p.k_end);
+	if (p.halo)
+	{
+		klo = k0 + width - 1; // only the top cell layer of a halo brick matters
+		k1 = k0 + width;
+	}
+	bool empty = false;
+	if (!p.no_cull)
+	{
+		empty = BrickIsEmpty(p.model, LatticeCoord(g.x, g.dx, i0), LatticeCoord(g.y, g.dy, j0), LatticeCoord(g.z, g.dz, klo),
+			LatticeCoord(g.x, g.dx, i1), LatticeCoord(g.y, g.dy, j1), LatticeCoord(g.z, g.dz, k1));
+	}
+	if (empty) return;
+	if (p.level == 0)
+	{
+		const unsigned long long slot = atomicAdd(p.out_counter, 1ull);
+		if (slot < p.out_capacity) p.out_list[slot] = brick | (p.halo ? kHaloFlag : 0u);
+		return;
+	}
+	const uint32_t half = width >> 1;
+	for (int o = 0; o < 8; ++o)
+	{
+		const uint32_t cx = bx * 2 + (o & 1), cy = by * 2 + ((o >> 1) & 1), cz = bz * 2 + ((o >> 2) & 1);
+		const uint32_t ci = cx * half, cj = cy * half, ck = cz * half;
+		if (ci >= g.sx || cj >= g.sy || ck >= g.sz) continue;
+		if (ck + half <= p.k_begin || ck >= p.k_end) continue;
+		const unsigned long long slot = atomicAdd(p.out_counter, 1ull);
+		if (slot < p.out_capacity) p.out_list[slot] = cx | (cy << 10) | (cz << 20);
+	}
+}
+
+__global__ void InitBrickListKernel(uint32_t* list, uint32_t nbx, uint32_t nby, uint32_t bz_begin, uint32_t nbz)
+{
+	const uint32_t index = blockIdx.x * blockDim.x + threadIdx.x;
+	if (index >= nbx * nby * nbz) return;
+	const uint32_t x = index % nbx, y = (index / nbx) % nby, z = index / (nbx * nby) + bz_begin;
+	list[index] = x | (y << 10) | (z << 20);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device-wide exclusive scan (block sums -> scan of sums -> per-element prefix)
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kScanBlock = 256;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanBlock * kScanItems;
+
+struct LoadPopcount
+{
+	const unsigned long long* words;
+	__device__ uint32_t operator()(size_t i) const { return uint32_t(__popcll(words[i])); }
+};
+struct LoadU32
+{
+	const uint32_t* values;
+	__device__ uint32_t operator()(size_t i) const { return values[i]; }
+};
+
+__device__ __forceinline__ uint32_t BlockExclusiveScan(uint32_t value, uint32_t* warp_sums, uint32_t& block_total)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t inclusive = value;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inclusive, o);
+		if (lane >= o) inclusive += n;
+	}
+	if (lane == 31) warp_sums[warp] = inclusive;
+	__syncthreads();
+	if (warp == 0)
+	{
+		uint32_t w = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0u;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, w, o);
+			if (lane >= o) w += n;
+		}
+		warp_sums[lane] = w; // inclusive over warps
+	}
+	__syncthreads();
+	block_total = warp_sums[(blockDim.x >> 5) - 1];
+	const uint32_t warp_base = warp ? warp_sums[warp - 1] : 0u;
+	__syncthreads();
+	return warp_base + inclusive - value;
+}
+
+template <typename Load>
+__global__ void __launch_bounds__(kScanBlock) ScanBlockSumsKernel(Load load, size_t count, uint32_t* block_sums)
+{
+	__shared__ uint32_t warp_sums[32];
+	const size_t base = size_t(blockIdx.x) * kScanTile + size_t(threadIdx.x) * kScanItems;
+	uint32_t sum = 0;
+#pragma unroll
+	for (int i = 0; i < kScanItems; ++i)
+	{
+		if (base + i < count) sum += load(base + i);
+	}
+	uint32_t total;
+	BlockExclusiveScan(sum, warp_sums, total);
+	if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// Single block: exclusive scan of block_sums in place, grand total to *total_out.
+__global__ void __launch_bounds__(1024) ScanSumsKernel(uint32_t* block_sums, uint32_t count, unsigned long long* total_out)
+{
+	__shared__ uint32_t warp_sums[32];
+	__shared__ uint32_t carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (uint32_t base = 0; base < count; base += blockDim.x)
+	{
+		const uint32_t i = base + threadIdx.x;
+		const uint32_t v = i < count ? block_sums[i] : 0u;
+		uint32_t total;
+		const uint32_t ex = BlockExclusiveScan(v, warp_sums, total);
+		const uint32_t c = carry;
+		if (i < count) block_sums[i] = c + ex;
+		__syncthreads();
+		if (threadIdx.x == 0) carry = c + total;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) *total_out = carry;
+}
+
+template <typename Load>
+__global__ void __launch_bounds__(kScanBlock) ScanWriteKernel(Load load, size_t count, const uint32_t* block_sums, uint32_t* out)
+{
+	__shared__ uint32_t warp_sums[32];
+	const size_t base = size_t(blockIdx.x) * kScanTile + size_t(threadIdx.x) * kScanItems;
+	uint32_t v[kScanItems];
+	uint32_t sum = 0;
+#pragma unroll
+	for (int i = 0; i < kScanItems; ++i)
+	{
+		v[i] = base + i < count ? load(base + i) : 0u;
+		sum += v[i];
+	}
+	uint32_t total;
+	uint32_t running = BlockExclusiveScan(sum, warp_sums, total) + block_sums[blockIdx.x];
+#pragma unroll
+	for (int i = 0; i < kScanItems; ++i)
+	{
+		if (base + i < count) out[base + i] = running;
+		running += v[i];
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: vertex ordering and quad emission
+// ------------------------------------------------------------------------------------------------
+
+struct FaceParams
+{
+	const unsigned long long* bitmap;
+	const uint32_t* prefix; // exclusive popcount prefix per bitmap word
+	uint32_t row_words;
+	uint32_t sy;
+	uint32_t k_base;
+	uint32_t halo_vertices;
+	const float4* tmp_pos;
+	const unsigned long long* tmp_key;
+	uint32_t tmp_count;
+	float* positions;             // 3 per owned vertex
+	unsigned long long* vertex_info; // bitmap bit index | quad mask << 56 | orientation << 60
+	uint32_t* quad_count;
+	const uint32_t* quad_offset;
+	uint32_t* triangles;
+	uint32_t vertex_count;
+};
+
+__device__ __forceinline__ bool CellActive(const FaceParams& p, uint32_t i, uint32_t j, uint32_t layer)
+{
+	const unsigned long long bit = ((unsigned long long)layer * p.sy + j) * ((unsigned long long)p.row_words * 64ull) + i;
+	return (p.bitmap[bit >> 6] >> (bit & 63ull)) & 1ull;
+}
+
+__device__ __forceinline__ uint32_t CellVertex(const FaceParams& p, uint32_t i, uint32_t j, uint32_t layer)
+{
+	const unsigned long long bit = ((unsigned long long)layer * p.sy + j) * ((unsigned long long)p.row_words * 64ull) + i;
+	const unsigned long long word = p.bitmap[bit >> 6];
+	return p.prefix[bit >> 6] + uint32_t(__popcll(word & ((1ull << (bit & 63ull)) - 1ull)));
+}
+
+__global__ void __launch_bounds__(256) ScatterVerticesKernel(const FaceParams p)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= p.tmp_count) return;
+	const unsigned long long key = p.tmp_key[t];
+	const float4 pos = p.tmp_pos[t];
+	const unsigned long long row_bits = (unsigned long long)p.row_words * 64ull;
+	const uint32_t i = uint32_t(key % row_bits);
+	const unsigned long long row = key / row_bits;
+	const uint32_t j = uint32_t(row % p.sy), layer = uint32_t(row / p.sy);
+	const unsigned long long word = p.bitmap[key >> 6];
+	const uint32_t id = p.prefix[key >> 6] + uint32_t(__popcll(word & ((1ull << (key & 63ull)) - 1ull))) - p.halo_vertices;
+	p.positions[size_t(id) * 3 + 0] = pos.x;
+	p.positions[size_t(id) * 3 + 1] = pos.y;
+	p.positions[size_t(id) * 3 + 2] = pos.z;
+	// SecondLoopThunk (surface_nets.cpp:1016-1030, 1069, 1093-1096): lower-boundary cells emit nothing; a quad needs
+	// its three neighbour cells to be active (the shared edge is NOT tested for bipolarity).
+	uint32_t quads = 0;
+	const uint32_t k_abs = layer + p.k_base;
+	if (i != 0 && j != 0 && k_abs != 0)
+	{
+		const bool n0 = CellActive(p, i - 1, j, layer), n1 = CellActive(p, i - 1, j - 1, layer), n2 = CellActive(p, i, j - 1, layer);
+		const bool n3 = CellActive(p, i, j - 1, layer - 1), n4 = CellActive(p, i, j, layer - 1), n5 = CellActive(p, i - 1, j, layer - 1);
+		quads = (n0 && n1 && n2 ? 1u : 0u) | (n0 && n5 && n4 ? 2u : 0u) | (n2 && n3 && n4 ? 4u : 0u);
+	}
+	p.vertex_info[id] = key | ((unsigned long long)quads << 56) | ((unsigned long long)(__float_as_uint(pos.w) & 7u) << 60);
+	p.quad_count[id] = uint32_t(__popc(quads));
+}
+
+__global__ void __launch_bounds__(256) EmitTrianglesKernel(const FaceParams p)
+{
+	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= p.vertex_count) return;
+	const unsigned long long info = p.vertex_info[v];
+	const uint32_t quads = uint32_t(info >> 56) & 7u;
+	if (quads == 0u) return;
+	const uint32_t orient = uint32_t(info >> 60) & 7u;
+	const unsigned long long key = info & ((1ull << 56) - 1ull);
+	const unsigned long long row_bits = (unsigned long long)p.row_words * 64ull;
+	const uint32_t i = uint32_t(key % row_bits);
+	const unsigned long long row = key / row_bits;
+	const uint32_t j = uint32_t(row % p.sy), layer = uint32_t(row / p.sy);
+	uint32_t out = p.quad_offset[v] * 6u;
+	const uint32_t h = p.halo_vertices;
+#pragma unroll
+	for (int e = 0; e < 3; ++e)
+	{
+		if (!(quads & (1u << e))) continue;
+		uint32_t a, b, c;
+		if (e == 0) // edge z: neighbours (i-1,j,k), (i-1,j-1,k), (i,j-1,k)
+		{
+			a = CellVertex(p, i - 1, j, layer);
+			b = CellVertex(p, i - 1, j - 1, layer);
+			c = CellVertex(p, i, j - 1, layer);
+		}
+		else if (e == 1) // edge y: (i-1,j,k), (i-1,j,k-1), (i,j,k-1)
+		{
+			a = CellVertex(p, i - 1, j, layer);
+			b = CellVertex(p, i - 1, j, layer - 1);
+			c = CellVertex(p, i, j, layer - 1);
+		}
+		else // edge x: (i,j-1,k), (i,j-1,k-1), (i,j,k-1)
+		{
+			a = CellVertex(p, i, j - 1, layer);
+			b = CellVertex(p, i, j - 1, layer - 1);
+			c = CellVertex(p, i, j, layer - 1);
+		}
+		const bool forward = (orient >> e) & 1u; // :1103-1105
+		const uint32_t v1 = (forward ? a : c) - h, v2 = b - h, v3 = (forward ? c : a) - h;
+		p.triangles[out + 0] = v;
+		p.triangles[out + 1] = v1;
+		p.triangles[out + 2] = v2;
+		p.triangles[out + 3] = v;
+		p.triangles[out + 4] = v2;
+		p.triangles[out + 5] = v3;
+		out += 6;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: refinement + normal + colour
+// ------------------------------------------------------------------------------------------------
+
+struct AttributeParams
+{
+	DeviceModel model;
+	float* positions;
+	float* normals;      // may be null
+	unsigned char* colors; // may be null
+	uint32_t count;
+	int refine_iterations;
+	float half_x, half_y, half_z;
+	float scale;
+};
+
+__device__ __forceinline__ void ExportColor(const DeviceModel& model, uint32_t node, float x, float y, float z, unsigned char* out)
+{
+	// export.cpp:303-311: white unless the model is painted; `0xFF * c` truncated to a byte
+	float r = 1.0f, g = 1.0f, b = 1.0f;
+	if (model.has_paint)
+	{
+		float px[1] = { x }, py[1] = { y }, pz[1] = { z }, d[1];
+		uint32_t m[1];
+		RunProgram<1, true>(model.tree + __ldg(&model.nodes[node].tree_offset), px, py, pz, d, m);
+		const uint32_t id = m[0] == kNoMaterial || m[0] >= model.material_count ? model.material_count : m[0];
+		r = __ldg(&model.material_rgb[id * 3 + 0]);
+		g = __ldg(&model.material_rgb[id * 3 + 1]);
+		b = __ldg(&model.material_rgb[id * 3 + 2]);
+	}
+	out[0] = (unsigned char)(255.0f * r);
+	out[1] = (unsigned char)(255.0f * g);
+	out[2] = (unsigned char)(255.0f * b);
+}
+
+__global__ void __launch_bounds__(128) AttributesKernel(const AttributeParams p)
+{
+	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= p.count) return;
+	float x = p.positions[size_t(v) * 3 + 0], y = p.positions[size_t(v) * 3 + 1], z = p.positions[size_t(v) * 3 + 2];
+	const DeviceModel& model = p.model;
+	if (p.refine_iterations > 0)
+	{
+		// export.cpp:442-461 applied to a mesh vertex
+		const float vx = x, vy = y, vz = z;
+		const float diagonal = sqrtf(p.half_x * p.half_x + p.half_y * p.half_y + p.half_z * p.half_z);
+		for (int r = 0; r < p.refine_iterations; ++r)
+		{
+			const uint32_t node = Descend(model.nodes, 0, x, y, z);
+			float gx, gy, gz;
+			EvalGradient(model.tree + __ldg(&model.nodes[node].tree_offset), x, y, z, gx, gy, gz);
+			const float dist = -EvalDistance1(model.interp + __ldg(&model.nodes[node].interp_offset), x, y, z);
+			x = x + gx * dist;
+			y = y + gy * dist;
+			z = z + gz * dist;
+		}
+		x = sdf::gmin(sdf::gmax(x, vx - p.half_x), vx + p.half_x);
+		y = sdf::gmin(sdf::gmax(y, vy - p.half_y), vy + p.half_y);
+		z = sdf::gmin(sdf::gmax(z, vz - p.half_z), vz + p.half_z);
+		const float mx = vx - x, my = vy - y, mz = vz - z;
+		if (!(sqrtf(mx * mx + my * my + mz * mz) <= diagonal))
+		{
+			x = vx;
+			y = vy;
+			z = vz;
+		}
+	}
+	const uint32_t node = Descend(model.nodes, 0, x, y, z);
+	if (p.normals)
+	{
+		float gx, gy, gz;
+		EvalGradient(model.tree + __ldg(&model.nodes[node].tree_offset), x, y, z, gx, gy, gz);
+		p.normals[size_t(v) * 3 + 0] = gx;
+		p.normals[size_t(v) * 3 + 1] = gy;
+		p.normals[size_t(v) * 3 + 2] = gz;
+	}
+	if (p.colors)
+	{
+		ExportColor(model, node, x, y, z, p.colors + size_t(v) * 3);
+	}
+	p.positions[size_t(v) * 3 + 0] = x * p.scale;
+	p.positions[size_t(v) * 3 + 1] = y * p.scale;
+	p.positions[size_t(v) * 3 + 2] = z * p.scale;
+}
+
+// WriteSTL (export.cpp:130-140): gradient at the triangle centroid, before the vertices are scaled.
+__global__ void __launch_bounds__(128) FaceNormalsKernel(const DeviceModel model, const float* positions, const uint32_t* triangles,
+	uint32_t triangle_count, float inv_scale_unused, float* out)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= triangle_count) return;
+	const uint32_t a = triangles[size_t(t) * 3 + 0], b = triangles[size_t(t) * 3 + 1], c = triangles[size_t(t) * 3 + 2];
+	const float cx = ((positions[size_t(a) * 3 + 0] + positions[size_t(b) * 3 + 0]) + positions[size_t(c) * 3 + 0]) / 3.0f;
+	const float cy = ((positions[size_t(a) * 3 + 1] + positions[size_t(b) * 3 + 1]) + positions[size_t(c) * 3 + 1]) / 3.0f;
+	const float cz = ((positions[size_t(a) * 3 + 2] + positions[size_t(b) * 3 + 2]) + positions[size_t(c) * 3 + 2]) / 3.0f;
+	const uint32_t node = Descend(model.nodes, 0, cx, cy, cz);
+	float gx, gy, gz;
+	EvalGradient(model.tree + __ldg(&model.nodes[node].tree_offset), cx, cy, cz, gx, gy, gz);
+	out[size_t(t) * 3 + 0] = gx;
+	out[size_t(t) * 3 + 1] = gy;
+	out[size_t(t) * 3 + 2] = gz;
+}
+
+__global__ void ScalePositionsKernel(float* positions, size_t count, float scale)
+{
+	const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i < count) positions[i] = positions[i] * scale;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Point queries
+// ------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128) EvalPointsKernel(const DeviceModel model, int mode, const float* __restrict__ points, uint32_t count, void* out)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count) return;
+	const float x = points[size_t(i) * 3 + 0], y = points[size_t(i) * 3 + 1], z = points[size_t(i) * 3 + 2];
+	if (mode == TG_EVAL_OCTREE)
+	{
+		const uint32_t node = Descend(model.nodes, 0, x, y, z);
+		static_cast<float*>(out)[i] = EvalDistance1(model.interp + __ldg(&model.nodes[node].interp_offset), x, y, z);
+	}
+	else if (mode == TG_EVAL_INTERP)
+	{
+		static_cast<float*>(out)[i] = EvalDistance1(model.interp + model.root_interp_offset, x, y, z);
+	}
+	else if (mode == TG_EVAL_TREE)
+	{
+		static_cast<float*>(out)[i] = EvalDistance1(model.tree + model.root_tree_offset, x, y, z);
+	}
+	else if (mode == TG_EVAL_GRADIENT)
+	{
+		const uint32_t node = Descend(model.nodes, 0, x, y, z);
+		float gx, gy, gz;
+		EvalGradient(model.tree + __ldg(&model.nodes[node].tree_offset), x, y, z, gx, gy, gz);
+		float* o = static_cast<float*>(out) + size_t(i) * 3;
+		o[0] = gx;
+		o[1] = gy;
+		o[2] = gz;
+	}
+	else
+	{
+		const uint32_t node = Descend(model.nodes, 0, x, y, z);
+		ExportColor(model, node, x, y, z, static_cast<unsigned char*>(out) + size_t(i) * 3);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: dense centre sampling for MagicaVoxel and point-cloud export
+// ------------------------------------------------------------------------------------------------
+
+// VoxExport (magica.cpp:46-69): every lane runs the same (unpruned, tree-walk) program on 4 cells.
+__global__ void __launch_bounds__(128) VoxelKernel(const DeviceModel model, float minx, float miny, float minz, float maxx, float maxy, float maxz,
+	int sx, int sy, int sz, float radius, uint32_t* __restrict__ hit_words, unsigned long long total)
+{
+	const unsigned long long first = (unsigned long long)(blockIdx.x * blockDim.x + threadIdx.x) * 4ull;
+	float px[4], py[4], pz[4], d[4];
+	const int slice = sx * sy;
+#pragma unroll
+	for (int q = 0; q < 4; ++q)
+	{
+		const unsigned long long idx = first + q < total ? first + q : 0ull;
+		const int i = int(idx);
+		const int z = i / slice, y = (i % slice) / sx, x = i % sx;
+		// Alpha = vec3(x + .5, y + .5, z + .5) / vec3(Size); Point = mix(Min, Max, Alpha) = Min * (1 - a) + Max * a
+		const float ax = float(x + .5) / float(sx), ay = float(y + .5) / float(sy), az = float(z + .5) / float(sz);
+		px[q] = minx * (1.0f - ax) + maxx * ax;
+		py[q] = miny * (1.0f - ay) + maxy * ay;
+		pz[q] = minz * (1.0f - az) + maxz * az;
+	}
+	EvalDistance<4>(model.tree + model.root_tree_offset, px, py, pz, d);
+	unsigned bits = 0;
+#pragma unroll
+	for (int q = 0; q < 4; ++q)
+	{
+		if (first + q < total && fabsf(d[q]) <= radius) bits |= 1u << q;
+	}
+	// 8 lanes x 4 cells = one 32-bit word
+	const int lane = threadIdx.x & 31;
+	unsigned word = bits << ((lane & 7) * 4);
+	word |= __shfl_xor_sync(0xFFFFFFFFu, word, 1);
+	word |= __shfl_xor_sync(0xFFFFFFFFu, word, 2);
+	word |= __shfl_xor_sync(0xFFFFFFFFu, word, 4);
+	if ((lane & 7) == 0 && first < total) hit_words[first >> 5] = word;
+}
+
+// PointCloudExportThread generation pass (export.cpp:401-427): one cell centre per thread through the octree.
+__global__ void __launch_bounds__(128) PointCloudKernel(const DeviceModel model, float startx, float starty, float startz, float stepx, float stepy, float stepz,
+	int nx, int ny, int nz, float diagonal, uint32_t* __restrict__ hit_words, unsigned long long total)
+{
+	const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	bool hit = false;
+	if (idx < total)
+	{
+		const int i = int(idx);
+		const int slice = nx * ny;
+		const float z = float(i / slice) * stepz + startz;
+		const float y = float((i % slice) / nx) * stepy + starty;
+		const float x = float(i % nx) * stepx + startx;
+		const float cx = x + stepx / 2.0f, cy = y + stepy / 2.0f, cz = z + stepz / 2.0f;
+		const uint32_t node = Descend(model.nodes, 0, cx, cy, cz);
+		const float d = EvalDistance1(model.interp + __ldg(&model.nodes[node].interp_offset), cx, cy, cz);
+		hit = fabsf(d) < diagonal;
+	}
+	const unsigned ballot = __ballot_sync(0xFFFFFFFFu, hit);
+	if ((threadIdx.x & 31) == 0 && idx < total) hit_words[idx >> 5] = ballot;
+}
+
+__global__ void __launch_bounds__(256) GatherCloudKernel(const uint32_t* __restrict__ hit_words, const uint32_t* __restrict__ prefix, unsigned long long total,
+	float startx, float starty, float startz, float stepx, float stepy, float stepz, int nx, int ny, float* positions)
+{
+	const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= total) return;
+	const uint32_t word = hit_words[idx >> 5];
+	const uint32_t bit = uint32_t(idx & 31ull);
+	if (!((word >> bit) & 1u)) return;
+	const uint32_t id = prefix[idx >> 5] + uint32_t(__popc(word & ((1u << bit) - 1u)));
+	const int i = int(idx);
+	const int slice = nx * ny;
+	const float z = float(i / slice) * stepz + startz;
+	const float y = float((i % slice) / nx) * stepy + starty;
+	const float x = float(i % nx) * stepx + startx;
+	positions[size_t(id) * 3 + 0] = x + stepx / 2.0f;
+	positions[size_t(id) * 3 + 1] = y + stepy / 2.0f;
+	positions[size_t(id) * 3 + 2] = z + stepz / 2.0f;
+}
+
+struct LoadPopcount32
+{
+	const uint32_t* words;
+	__device__ uint32_t operator()(size_t i) const { return uint32_t(__popc(words[i])); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// FP32 peak measurement and L2 flush (bench support)
+// ------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) FmaChainKernel(float* out, int iterations)
+{
+	float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+	const float m = 0.999f, c = 1e-4f;
+	for (int i = 0; i < iterations; ++i)
+	{
+#pragma unroll
+		for (int u = 0; u < 8; ++u)
+		{
+			a0 = __fmaf_rn(a0, m, c); a1 = __fmaf_rn(a1, m, c); a2 = __fmaf_rn(a2, m, c); a3 = __fmaf_rn(a3, m, c);
+			a4 = __fmaf_rn(a4, m, c); a5 = __fmaf_rn(a5, m, c); a6 = __fmaf_rn(a6, m, c); a7 = __fmaf_rn(a7, m, c);
+		}
+	}
+	out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+__global__ void FillKernel(uint32_t* data, size_t count, uint32_t value)
+{
+	const size_t stride = size_t(gridDim.x) * blockDim.x;
+	for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) data[i] = value;
+}
+
+// ================================================================================================
+// Host side
+// ================================================================================================
+
+static inline cudaStream_t StreamOf(Context* c) { return static_cast<cudaStream_t>(c->stream); }
+
+Context* Context::Create(int device, std::string& error)
+{
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0)
+	{
+		error = std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") + "); tangerine_b200 has no CPU fallback";
+		return nullptr;
+	}
+	if (device < 0 || device >= count)
+	{
+		error = "CUDA device index out of range";
+		return nullptr;
+	}
+	if ((e = cudaSetDevice(device)) != cudaSuccess)
+	{
+		error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+		return nullptr;
+	}
+	// Fail loudly when the sm_100a image cannot run here.
+	cudaFuncAttributes attr;
+	if ((e = cudaFuncGetAttributes(&attr, MeshBricksKernel)) != cudaSuccess)
+	{
+		error = std::string("the sm_100a kernel image is not loadable on this device: ") + cudaGetErrorString(e);
+		return nullptr;
+	}
+	Context* c = new Context();
+	c->device = device;
+	cudaStream_t stream;
+	if ((e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)) != cudaSuccess)
+	{
+		error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+		delete c;
+		return nullptr;
+	}
+	c->stream = stream;
+	cudaEvent_t ev0, ev1;
+	cudaEventCreate(&ev0);
+	cudaEventCreate(&ev1);
+	c->timer_events[0] = ev0;
+	c->timer_events[1] = ev1;
+	cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+	// Keep freed scratch in the pool so steady-state exports do not hit the allocator.
+	cudaMemPool_t pool;
+	if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+	{
+		uint64_t threshold = UINT64_MAX;
+		cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+	}
+	for (int i = 0; i < 4; ++i)
+	{
+		c->progress_done[i] = 0;
+		c->progress_total[i] = 0;
+	}
+	return c;
+}
+
+Context::~Context()
+{
+	cudaSetDevice(device);
+	if (stream) cudaStreamSynchronize(StreamOf(this));
+	for (PinnedBlock& b : pinned)
+	{
+		if (b.ptr) cudaFreeHost(b.ptr);
+	}
+	for (void* ev : timer_events)
+	{
+		if (ev) cudaEventDestroy(static_cast<cudaEvent_t>(ev));
+	}
+	if (stream) cudaStreamDestroy(StreamOf(this));
+}
+
+void* Context::AcquirePinned(size_t bytes, std::string& error)
+{
+	if (bytes == 0) bytes = 16;
+	// best fit among free blocks
+	int best = -1;
+	for (size_t i = 0; i < pinned.size(); ++i)
+	{
+		if (!pinned[i].in_use && pinned[i].bytes >= bytes && (best < 0 || pinned[i].bytes < pinned[size_t(best)].bytes)) best = int(i);
+	}
+	if (best >= 0)
+	{
+		pinned[size_t(best)].in_use = true;
+		return pinned[size_t(best)].ptr;
+	}
+	PinnedBlock b;
+	const size_t rounded = (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+	cudaError_t e = cudaMallocHost(&b.ptr, rounded);
+	if (e != cudaSuccess)
+	{
+		error = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
+		return nullptr;
+	}
+	b.bytes = rounded;
+	b.in_use = true;
+	pinned.push_back(b);
+	return b.ptr;
+}
+
+void Context::ReleasePinned(void* ptr)
+{
+	for (PinnedBlock& b : pinned)
+	{
+		if (b.ptr == ptr) b.in_use = false;
+	}
+}
+
+template <typename T>
+static int UploadVector(Context* c, const std::vector<T>& v, void** out, uint64_t& bytes_total, std::string& error)
+{
+	const size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+	TG_CUDA(cudaMalloc(out, bytes));
+	TG_CUDA(cudaMemcpyAsync(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, StreamOf(c)));
+	bytes_total += bytes;
+	return TG_OK;
+}
+
+static int UploadModel(Model* m, std::string& error)
+{
+	Context* c = m->context;
+	TG_CUDA(cudaSetDevice(c->device));
+	int rc;
+	if ((rc = UploadVector(c, m->flat.nodes, &m->d_nodes, m->device_bytes, error)) != TG_OK) return rc;
+	if ((rc = UploadVector(c, m->flat.interp, &m->d_interp, m->device_bytes, error)) != TG_OK) return rc;
+	if ((rc = UploadVector(c, m->flat.tree, &m->d_tree, m->device_bytes, error)) != TG_OK) return rc;
+	if ((rc = UploadVector(c, m->flat.material_rgb, &m->d_materials, m->device_bytes, error)) != TG_OK) return rc;
+	TG_CUDA(cudaStreamSynchronize(StreamOf(c)));
+	return TG_OK;
+}
+
+Model* Model::Create(Context* context, const Tree& tree, float target_size, int threads, std::string& error)
+{
+	Model* m = new Model();
+	m->context = context;
+	if (!BuildFlatModel(tree, target_size, threads, m->flat, error))
+	{
+		delete m;
+		return nullptr;
+	}
+	m->leaf_count = tree.LeafCount();
+	const auto t0 = std::chrono::steady_clock::now();
+	if (UploadModel(m, error) != TG_OK)
+	{
+		delete m;
+		return nullptr;
+	}
+	m->upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	return m;
+}
+
+Model::~Model()
+{
+	if (context) cudaSetDevice(context->device);
+	cudaFree(d_nodes);
+	cudaFree(d_interp);
+	cudaFree(d_tree);
+	cudaFree(d_materials);
+}
+
+static DeviceModel MakeDeviceModel(const Model* m)
+{
+	DeviceModel d;
+	d.nodes = static_cast<const FlatNode*>(m->d_nodes);
+	d.interp = static_cast<const uint32_t*>(m->d_interp);
+	d.tree = static_cast<const uint32_t*>(m->d_tree);
+	d.material_rgb = static_cast<const float*>(m->d_materials);
+	d.material_count = uint32_t(m->flat.material_rgb.size() / 3 - 1);
+	d.root_interp_offset = m->flat.root_interp_offset;
+	d.root_tree_offset = m->flat.root_tree_offset;
+	d.node_count = uint32_t(m->flat.nodes.size());
+	d.has_paint = m->flat.has_paint ? 1 : 0;
+	return d;
+}
+
+static bool MakeDeviceGrid(const tg_grid& g, DeviceGrid& out, std::string& error)
+{
+	if (g.sx == 0 || g.sy == 0 || g.sz == 0 || g.sx > 8184 || g.sy > 8184 || g.sz > 8184)
+	{
+		error = "grid size must be 1..8184 cells per axis";
+		return false;
+	}
+	if (!(g.dx > 0.0f) || !(g.dy > 0.0f) || !(g.dz > 0.0f))
+	{
+		error = "grid step must be positive";
+		return false;
+	}
+	out.x = g.x; out.y = g.y; out.z = g.z;
+	out.dx = g.dx; out.dy = g.dy; out.dz = g.dz;
+	out.sx = uint32_t(g.sx); out.sy = uint32_t(g.sy); out.sz = uint32_t(g.sz);
+	return true;
+}
+
+// RAII for stream-ordered scratch.
+struct Scratch
+{
+	cudaStream_t stream;
+	std::vector<void*> blocks;
+	explicit Scratch(cudaStream_t s) : stream(s) {}
+	~Scratch()
+	{
+		for (void* b : blocks) cudaFreeAsync(b, stream);
+	}
+	template <typename T>
+	cudaError_t Alloc(T** out, size_t count)
+	{
+		void* p = nullptr;
+		cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(count * sizeof(T), 256), stream);
+		if (e == cudaSuccess) blocks.push_back(p);
+		*out = static_cast<T*>(p);
+		return e;
+	}
+	void Keep(void* p) // hand ownership to the caller
+	{
+		blocks.erase(std::remove(blocks.begin(), blocks.end(), p), blocks.end());
+	}
+};
+
+struct MeshResultDevice
+{
+	Context* context = nullptr;
+	float* d_positions = nullptr;
+	float* d_normals = nullptr;
+	unsigned char* d_colors = nullptr;
+	uint32_t* d_triangles = nullptr;
+	float* d_face_normals = nullptr;
+	std::vector<void*> pinned;
+};
+
+void EngineFreeMesh(tg_mesh* mesh)
+{
+	if (!mesh) return;
+	MeshResultDevice* r = static_cast<MeshResultDevice*>(mesh->opaque);
+	if (r)
+	{
+		cudaSetDevice(r->context->device);
+		cudaStream_t s = StreamOf(r->context);
+		if (r->d_positions) cudaFreeAsync(r->d_positions, s);
+		if (r->d_normals) cudaFreeAsync(r->d_normals, s);
+		if (r->d_colors) cudaFreeAsync(r->d_colors, s);
+		if (r->d_triangles) cudaFreeAsync(r->d_triangles, s);
+		if (r->d_face_normals) cudaFreeAsync(r->d_face_normals, s);
+		for (void* p : r->pinned) r->context->ReleasePinned(p);
+		delete r;
+	}
+	std::memset(mesh, 0, sizeof(*mesh));
+}
+
+template <typename Load>
+static int DeviceExclusiveScan(cudaStream_t stream, Scratch& scratch, Load load, size_t count, uint32_t* out, unsigned long long* total_out,
+	uint64_t& launches, std::string& error)
+{
+	const uint32_t blocks = uint32_t((count + kScanTile - 1) / kScanTile);
+	uint32_t* sums = nullptr;
+	TG_CUDA(scratch.Alloc(&sums, std::max<uint32_t>(blocks, 1)));
+	if (blocks == 0)
+	{
+		TG_CUDA(cudaMemsetAsync(total_out, 0, 8, stream));
+		return TG_OK;
+	}
+	ScanBlockSumsKernel<Load><<<blocks, kScanBlock, 0, stream>>>(load, count, sums);
+	ScanSumsKernel<<<1, 1024, 0, stream>>>(sums, blocks, total_out);
+	ScanWriteKernel<Load><<<blocks, kScanBlock, 0, stream>>>(load, count, sums, out);
+	launches += 3;
+	TG_CUDA(cudaGetLastError());
+	return TG_OK;
+}
+
+struct StageTimer
+{
+	cudaStream_t stream;
+	std::vector<cudaEvent_t> events;
+	explicit StageTimer(cudaStream_t s) : stream(s) {}
+	~StageTimer()
+	{
+		for (cudaEvent_t e : events) cudaEventDestroy(e);
+	}
+	int Mark()
+	{
+		cudaEvent_t e;
+		cudaEventCreate(&e);
+		cudaEventRecord(e, stream);
+		events.push_back(e);
+		return int(events.size() - 1);
+	}
+	float Ms(int a, int b)
+	{
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, events[size_t(a)], events[size_t(b)]);
+		return ms;
+	}
+};
+
+// Shared tail of mesh and point-cloud export: refinement / normals / colours, download.
+static int FinishAttributes(Model* model, Scratch& scratch, MeshResultDevice* result, uint32_t vertex_count, const tg_mesh_options& options,
+	const float half[3], uint64_t& launches, std::string& error)
+{
+	Context* ctx = model->context;
+	cudaStream_t stream = StreamOf(ctx);
+	const bool want_normals = (options.flags & TG_MESH_NORMALS) != 0;
+	const bool want_colors = (options.flags & TG_MESH_COLORS) != 0 && model->flat.has_paint;
+	const float scale = options.scale == 0.0f ? 1.0f : options.scale;
+	if (vertex_count == 0) return TG_OK;
+	if (want_normals) TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_normals), size_t(vertex_count) * 12, stream));
+	if (want_colors) TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_colors), size_t(vertex_count) * 3, stream));
+	const bool face_normals = (options.flags & TG_MESH_FACE_NORMALS) != 0;
+	if (want_normals || want_colors || options.refine_iterations > 0 || (scale != 1.0f && !face_normals))
+	{
+		AttributeParams ap;
+		ap.model = MakeDeviceModel(model);
+		ap.positions = result->d_positions;
+		ap.normals = result->d_normals;
+		ap.colors = result->d_colors;
+		ap.count = vertex_count;
+		ap.refine_iterations = options.refine_iterations;
+		ap.half_x = half[0];
+		ap.half_y = half[1];
+		ap.half_z = half[2];
+		ap.scale = face_normals ? 1.0f : scale; // STL scales after the centroid normals (export.cpp:142-145)
+		AttributesKernel<<<(vertex_count + 127) / 128, 128, 0, stream>>>(ap);
+		launches++;
+		TG_CUDA(cudaGetLastError());
+	}
+	(void)scratch;
+	return TG_OK;
+}
+
+int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options& options, tg_mesh* out, std::string& error)
+{
+	std::memset(out, 0, sizeof(*out));
+	Context* ctx = model->context;
+	TG_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t stream = StreamOf(ctx);
+	DeviceGrid grid;
+	if (!MakeDeviceGrid(grid_in, grid, error)) return TG_ERR_INVALID;
+
+	uint32_t k_begin = 0, k_end = grid.sz;
+	if (options.slab_begin != 0 || options.slab_end != 0)
+	{
+		k_begin = uint32_t(options.slab_begin);
+		k_end = uint32_t(std::min<uint64_t>(options.slab_end, grid.sz));
+		if (k_begin >= k_end || (k_begin % kBrick) != 0 || (k_end % kBrick != 0 && k_end != grid.sz))
+		{
+			error = "slab bounds must be multiples of 8 cell layers (or end at the grid top) and non-empty";
+			return TG_ERR_INVALID;
+		}
+	}
+	const bool has_halo = k_begin > 0;
+	const uint32_t k_base = has_halo ? k_begin - 1 : k_begin;
+	const uint32_t layers = k_end - k_base;
+	const uint32_t row_words = (grid.sx + 63) / 64;
+	const size_t bitmap_words = size_t(layers) * grid.sy * row_words;
+	const uint32_t nbx = (grid.sx + kBrick - 1) / kBrick, nby = (grid.sy + kBrick - 1) / kBrick;
+	const uint32_t bz_begin = k_begin / kBrick, bz_end = (k_end + kBrick - 1) / kBrick;
+	const size_t own_bricks = size_t(nbx) * nby * (bz_end - bz_begin);
+	const size_t halo_bricks = has_halo ? size_t(nbx) * nby : 0;
+	const size_t list_capacity = own_bricks + halo_bricks + 8;
+
+	ctx->stage.store(1);
+	ctx->progress_done[0] = 0;
+	ctx->progress_total[0] = own_bricks;
+	if (ctx->Cancelled()) return TG_ERR_CANCELLED;
+
+	Scratch scratch(stream);
+	StageTimer timer(stream);
+	uint64_t launches = 0;
+	tg_mesh_timings& tm = out->timings;
+	tm.bricks_total = own_bricks;
+
+	unsigned long long* counters = nullptr;
+	uint32_t *list_a = nullptr, *list_b = nullptr, *active_list = nullptr;
+	unsigned long long* bitmap = nullptr;
+	uint32_t* prefix = nullptr;
+	TG_CUDA(scratch.Alloc(&counters, kCntCount));
+	TG_CUDA(scratch.Alloc(&list_a, list_capacity));
+	TG_CUDA(scratch.Alloc(&list_b, list_capacity));
+	TG_CUDA(scratch.Alloc(&active_list, list_capacity));
+	TG_CUDA(scratch.Alloc(&bitmap, bitmap_words));
+	TG_CUDA(scratch.Alloc(&prefix, bitmap_words));
+	TG_CUDA(cudaMemsetAsync(counters, 0, kCntCount * 8, stream));
+	TG_CUDA(cudaMemsetAsync(bitmap, 0, bitmap_words * 8, stream));
+	const int t_start = timer.Mark();
+
+	// ---- K0: active brick list -------------------------------------------------------------------
+	const bool no_cull = (options.flags & TG_MESH_NO_CULL) != 0;
+	unsigned long long host_counts[kCntCount];
+	CullParams cp;
+	cp.model = MakeDeviceModel(model);
+	cp.grid = grid;
+	cp.k_begin = k_begin;
+	cp.k_end = k_end;
+	cp.no_cull = no_cull ? 1 : 0;
+	cp.out_capacity = uint32_t(list_capacity);
+	uint64_t active_count = 0;
+	{
+		// owned bricks: refine from 64-cell bricks down to 8-cell bricks
+		int level = no_cull ? 0 : kTopLevel;
+		const uint32_t width = uint32_t(kBrick) << level;
+		const uint32_t tx = (grid.sx + width - 1) / width, ty = (grid.sy + width - 1) / width;
+		const uint32_t tz0 = k_begin / width, tz1 = (k_end + width - 1) / width;
+		uint32_t count = tx * ty * (tz1 - tz0);
+		InitBrickListKernel<<<(count + 255) / 256, 256, 0, stream>>>(list_a, tx, ty, tz0, tz1 - tz0);
+		launches++;
+		uint32_t* in = list_a;
+		uint32_t* outl = list_b;
+		for (; level >= 0; --level)
+		{
+			cp.in_list = in;
+			cp.in_count = count;
+			cp.level = level;
+			cp.halo = 0;
+			cp.out_list = level == 0 ? active_list : outl;
+			cp.out_counter = counters + (level == 0 ? kCntListA : kCntListB);
+			if (level != 0) TG_CUDA(cudaMemsetAsync(counters + kCntListB, 0, 8, stream));
+			if (count) CullLevelKernel<<<(count + 127) / 128, 128, 0, stream>>>(cp);
+			launches++;
+			if (level != 0)
+			{
+				TG_CUDA(cudaMemcpyAsync(host_counts, counters + kCntListB, 8, cudaMemcpyDeviceToHost, stream));
+				TG_CUDA(cudaStreamSynchronize(stream));
+				count = uint32_t(std::min<unsigned long long>(host_counts[0], list_capacity));
+				std::swap(in, outl);
+			}
+		}
+		if (has_halo)
+		{
+			// the brick layer below the slab: only its top cell layer is classified (vertex ids for our bottom quads)
+			const uint32_t hcount = nbx * nby;
+			InitBrickListKernel<<<(hcount + 255) / 256, 256, 0, stream>>>(list_a, nbx, nby, bz_begin - 1, 1);
+			cp.in_list = list_a;
+			cp.in_count = hcount;
+			cp.level = 0;
+			cp.halo = 1;
+			cp.k_begin = k_begin - 1;
+			cp.k_end = k_begin;
+			cp.out_list = active_list;
+			cp.out_counter = counters + kCntListA;
+			CullLevelKernel<<<(hcount + 127) / 128, 128, 0, stream>>>(cp);
+			launches += 2;
+		}
+		TG_CUDA(cudaMemcpyAsync(host_counts, counters + kCntListA, 8, cudaMemcpyDeviceToHost, stream));
+		TG_CUDA(cudaStreamSynchronize(stream));
+		active_count = std::min<unsigned long long>(host_counts[0], list_capacity);
+	}
+	TG_CUDA(cudaGetLastError());
+	const int t_cull = timer.Mark();
+	tm.bricks_evaluated = active_count;
+	ctx->progress_done[0] = own_bricks / 2;
+	if (ctx->Cancelled()) return TG_ERR_CANCELLED;
+
+	// ---- K1 + K2: evaluate bricks, classify, extract vertices ------------------------------------
+	MeshParams mp;
+	mp.model = cp.model;
+	mp.grid = grid;
+	mp.bricks = active_list;
+	mp.brick_count = uint32_t(active_count);
+	mp.bitmap = bitmap;
+	mp.row_words = row_words;
+	mp.k_base = k_base;
+	mp.k_own_begin = k_begin;
+	mp.k_own_end = k_end;
+	mp.counters = counters;
+	uint64_t tmp_capacity = std::max<uint64_t>(active_count * 96, 1 << 16);
+	uint64_t tmp_count = 0;
+	float4* tmp_pos = nullptr;
+	unsigned long long* tmp_key = nullptr;
+	for (int attempt = 0; attempt < 2 && active_count > 0; ++attempt)
+	{
+		TG_CUDA(scratch.Alloc(&tmp_pos, tmp_capacity));
+		TG_CUDA(scratch.Alloc(&tmp_key, tmp_capacity));
+		mp.tmp_pos = tmp_pos;
+		mp.tmp_key = tmp_key;
+		mp.tmp_capacity = uint32_t(tmp_capacity);
+		TG_CUDA(cudaMemsetAsync(counters + kCntTmpVertices, 0, 3 * 8, stream));
+		MeshBricksKernel<<<uint32_t(active_count), kThreads, 0, stream>>>(mp);
+		launches++;
+		TG_CUDA(cudaGetLastError());
+		TG_CUDA(cudaMemcpyAsync(host_counts, counters, kCntCount * 8, cudaMemcpyDeviceToHost, stream));
+		TG_CUDA(cudaStreamSynchronize(stream));
+		tmp_count = host_counts[kCntTmpVertices];
+		if (tmp_count <= tmp_capacity) break;
+		tmp_capacity = tmp_count; // exact size is known now; the bitmap writes are idempotent
+	}
+	if (tmp_count > 0xFFFFFFF0ull)
+	{
+		error = "mesh exceeds 2^32 vertices";
+		return TG_ERR_UNSUPPORTED;
+	}
+	tm.samples_evaluated = active_count ? host_counts[kCntSamples] : 0;
+	tm.algorithmic_flops = active_count ? host_counts[kCntFlops] : 0;
+	const int t_eval = timer.Mark();
+	ctx->progress_done[0] = own_bricks;
+	if (ctx->Cancelled()) return TG_ERR_CANCELLED;
+
+	// ---- vertex numbering: exclusive scan over the bitmap ---------------------------------------
+	int rc = DeviceExclusiveScan(stream, scratch, LoadPopcount{ bitmap }, bitmap_words, prefix, counters + kCntTotalVertices, launches, error);
+	if (rc != TG_OK) return rc;
+	uint32_t halo_vertices = 0;
+	if (has_halo)
+	{
+		// vertices of the halo layer come first in the local numbering
+		TG_CUDA(cudaMemcpyAsync(host_counts, prefix + size_t(grid.sy) * row_words, 4, cudaMemcpyDeviceToHost, stream));
+		TG_CUDA(cudaStreamSynchronize(stream));
+		halo_vertices = uint32_t(host_counts[0] & 0xFFFFFFFFull);
+	}
+	const uint32_t vertex_count = uint32_t(tmp_count);
+
+	MeshResultDevice* result = new MeshResultDevice();
+	result->context = ctx;
+	out->opaque = result;
+	out->vertex_count = vertex_count;
+	out->halo_vertices = halo_vertices;
+
+	unsigned long long* vertex_info = nullptr;
+	uint32_t *quad_count = nullptr, *quad_offset = nullptr;
+	uint64_t quad_total = 0;
+	if (vertex_count > 0)
+	{
+		TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_positions), size_t(vertex_count) * 12, stream));
+		TG_CUDA(scratch.Alloc(&vertex_info, vertex_count));
+		TG_CUDA(scratch.Alloc(&quad_count, vertex_count));
+		TG_CUDA(scratch.Alloc(&quad_offset, vertex_count));
+		FaceParams fp;
+		fp.bitmap = bitmap;
+		fp.prefix = prefix;
+		fp.row_words = row_words;
+		fp.sy = grid.sy;
+		fp.k_base = k_base;
+		fp.halo_vertices = halo_vertices;
+		fp.tmp_pos = tmp_pos;
+		fp.tmp_key = tmp_key;
+		fp.tmp_count = vertex_count;
+		fp.positions = result->d_positions;
+		fp.vertex_info = vertex_info;
+		fp.quad_count = quad_count;
+		fp.quad_offset = quad_offset;
+		fp.triangles = nullptr;
+		fp.vertex_count = vertex_count;
+		ScatterVerticesKernel<<<(vertex_count + 255) / 256, 256, 0, stream>>>(fp);
+		launches++;
+		const int t_compact = timer.Mark();
+		rc = DeviceExclusiveScan(stream, scratch, LoadU32{ quad_count }, vertex_count, quad_offset, counters + kCntTotalQuads, launches, error);
+		if (rc != TG_OK) return rc;
+		TG_CUDA(cudaMemcpyAsync(host_counts, counters + kCntTotalQuads, 8, cudaMemcpyDeviceToHost, stream));
+		TG_CUDA(cudaStreamSynchronize(stream));
+		quad_total = host_counts[0];
+		if (quad_total * 2 > 0xFFFFFFF0ull)
+		{
+			error = "mesh exceeds 2^32 triangles";
+			return TG_ERR_UNSUPPORTED;
+		}
+		if (quad_total > 0)
+		{
+			TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_triangles), size_t(quad_total) * 24, stream));
+			fp.triangles = result->d_triangles;
+			EmitTrianglesKernel<<<(vertex_count + 255) / 256, 256, 0, stream>>>(fp);
+			launches++;
+		}
+		TG_CUDA(cudaGetLastError());
+		const int t_faces = timer.Mark();
+		tm.compact_ms = -1.0f; // filled below from events
+		out->triangle_count = quad_total * 2;
+
+		// ---- K4: attributes ----------------------------------------------------------------------
+		ctx->stage.store(options.refine_iterations > 0 ? 2 : 3);
+		const float half[3] = { grid.dx / 2.0f, grid.dy / 2.0f, grid.dz / 2.0f };
+		rc = FinishAttributes(model, scratch, result, vertex_count, options, half, launches, error);
+		if (rc != TG_OK) return rc;
+		if ((options.flags & TG_MESH_FACE_NORMALS) && quad_total > 0)
+		{
+			TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_face_normals), size_t(quad_total) * 24, stream));
+			if (halo_vertices != 0)
+			{
+				error = "face normals are not available for slab exports";
+				return TG_ERR_UNSUPPORTED;
+			}
+			const uint32_t tris = uint32_t(quad_total * 2);
+			FaceNormalsKernel<<<(tris + 127) / 128, 128, 0, stream>>>(cp.model, result->d_positions, result->d_triangles, tris, 1.0f, result->d_face_normals);
+			launches++;
+			const float scale = options.scale == 0.0f ? 1.0f : options.scale;
+			if (scale != 1.0f)
+			{
+				ScalePositionsKernel<<<uint32_t((size_t(vertex_count) * 3 + 255) / 256), 256, 0, stream>>>(result->d_positions, size_t(vertex_count) * 3, scale);
+				launches++;
+			}
+		}
+		TG_CUDA(cudaGetLastError());
+		const int t_attr = timer.Mark();
+		TG_CUDA(cudaStreamSynchronize(stream));
+		tm.cull_ms = timer.Ms(t_start, t_cull);
+		tm.evaluate_ms = timer.Ms(t_cull, t_eval);
+		tm.compact_ms = timer.Ms(t_eval, t_compact);
+		tm.faces_ms = timer.Ms(t_compact, t_faces);
+		tm.attributes_ms = timer.Ms(t_faces, t_attr);
+		tm.total_device_ms = timer.Ms(t_start, t_attr);
+	}
+	else
+	{
+		const int t_end = timer.Mark();
+		TG_CUDA(cudaStreamSynchronize(stream));
+		tm.cull_ms = timer.Ms(t_start, t_cull);
+		tm.evaluate_ms = timer.Ms(t_cull, t_eval);
+		tm.total_device_ms = timer.Ms(t_start, t_end);
+	}
+	tm.kernel_launches = launches;
+	ctx->stage.store(3);
+
+	// ---- download --------------------------------------------------------------------------------
+	if (!(options.flags & TG_MESH_DEVICE_ONLY) && vertex_count > 0)
+	{
+		const auto h0 = std::chrono::steady_clock::now();
+		auto fetch = [&](void* device, size_t bytes, void** host) -> int
+		{
+			if (!device || bytes == 0) return TG_OK;
+			void* p = ctx->AcquirePinned(bytes, error);
+			if (!p) return TG_ERR_MEMORY;
+			result->pinned.push_back(p);
+			TG_CUDA(cudaMemcpyAsync(p, device, bytes, cudaMemcpyDeviceToHost, stream));
+			*host = p;
+			return TG_OK;
+		};
+		if ((rc = fetch(result->d_positions, size_t(vertex_count) * 12, reinterpret_cast<void**>(&out->positions))) != TG_OK) return rc;
+		if ((rc = fetch(result->d_normals, size_t(vertex_count) * 12, reinterpret_cast<void**>(&out->normals))) != TG_OK) return rc;
+		if ((rc = fetch(result->d_colors, size_t(vertex_count) * 3, reinterpret_cast<void**>(&out->colors))) != TG_OK) return rc;
+		if ((rc = fetch(result->d_triangles, size_t(quad_total) * 24, reinterpret_cast<void**>(&out->triangles))) != TG_OK) return rc;
+		if ((rc = fetch(result->d_face_normals, size_t(quad_total) * 24, reinterpret_cast<void**>(&out->face_normals))) != TG_OK) return rc;
+		TG_CUDA(cudaStreamSynchronize(stream));
+		tm.download_ms = float(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
+	}
+	ctx->stage.store(0);
+	return TG_OK;
+}
+
+int EngineEvalLattice(Model* model, const tg_grid& grid_in, float* out, float* out_ms, std::string& error)
+{
+	Context* ctx = model->context;
+	TG_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t stream = StreamOf(ctx);
+	DeviceGrid grid;
+	if (!MakeDeviceGrid(grid_in, grid, error)) return TG_ERR_INVALID;
+	const uint32_t nx = grid.sx + 1, ny = grid.sy + 1, nz = grid.sz + 1;
+	const uint32_t tx = (nx + kBrick - 1) / kBrick, ty = (ny + kBrick - 1) / kBrick, tz = (nz + kBrick - 1) / kBrick;
+	const size_t total = size_t(nx) * ny * nz;
+	Scratch scratch(stream);
+	float* d_out = nullptr;
+	unsigned long long* counters = nullptr;
+	TG_CUDA(scratch.Alloc(&counters, kCntCount));
+	TG_CUDA(cudaMemsetAsync(counters, 0, kCntCount * 8, stream));
+	if (out) TG_CUDA(scratch.Alloc(&d_out, total));
+	StageTimer timer(stream);
+	const int t0 = timer.Mark();
+	LatticeKernel<<<tx * ty * tz, kThreads, 0, stream>>>(MakeDeviceModel(model), grid, d_out, tx, ty, counters);
+	const int t1 = timer.Mark();
+	TG_CUDA(cudaGetLastError());
+	if (out) TG_CUDA(cudaMemcpyAsync(out, d_out, total * 4, cudaMemcpyDeviceToHost, stream));
+	TG_CUDA(cudaStreamSynchronize(stream));
+	if (out_ms) *out_ms = timer.Ms(t0, t1);
+	return TG_OK;
+}
+
+int EngineEvalPoints(Model* model, int mode, const float* points, uint64_t count, void* out, std::string& error)
+{
+	if (mode < TG_EVAL_OCTREE || mode > TG_EVAL_COLOR)
+	{
+		error = "unknown evaluation mode";
+		return TG_ERR_INVALID;
+	}
+	if (count == 0) return TG_OK;
+	if (count > 0xFFFFFFF0ull)
+	{
+		error = "too many points for one call";
+		return TG_ERR_INVALID;
+	}
+	Context* ctx = model->context;
+	TG_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t stream = StreamOf(ctx);
+	Scratch scratch(stream);
+	float* d_points = nullptr;
+	unsigned char* d_out = nullptr;
+	const size_t out_bytes = size_t(count) * (mode == TG_EVAL_GRADIENT ? 12 : mode == TG_EVAL_COLOR ? 3 : 4);
+	TG_CUDA(scratch.Alloc(&d_points, size_t(count) * 3));
+	TG_CUDA(scratch.Alloc(&d_out, out_bytes));
+	TG_CUDA(cudaMemcpyAsync(d_points, points, size_t(count) * 12, cudaMemcpyHostToDevice, stream));
+	EvalPointsKernel<<<uint32_t((count + 127) / 128), 128, 0, stream>>>(MakeDeviceModel(model), mode, d_points, uint32_t(count), d_out);
+	TG_CUDA(cudaGetLastError());
+	TG_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, stream));
+	TG_CUDA(cudaStreamSynchronize(stream));
+	return TG_OK;
+}
+
+int EngineExportVoxels(Model* model, float grid_size, int32_t out_size[3], float* out_radius, int32_t** out_xyz, uint64_t* out_count, std::string& error)
+{
+	Context* ctx = model->context;
+	TG_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t stream = StreamOf(ctx);
+	// magica.cpp:29-36
+	const Box3 b = model->flat.bounds;
+	const Vec3 ext = b.max - b.min;
+	const int sx = int(std::ceil(ext.x) * grid_size), sy = int(std::ceil(ext.y) * grid_size), sz = int(std::ceil(ext.z) * grid_size);
+	if (sx <= 0 || sy <= 0 || sz <= 0 || double(sx) * sy * sz >= 2147483647.0)
+	{
+		error = "voxel grid is empty or exceeds the reference's int cell index (magica.cpp:38-39)";
+		return TG_ERR_INVALID;
+	}
+	const Vec3 alpha = Vec3(.5f, .5f, .5f) / Vec3(float(sx), float(sy), float(sz));
+	const float radius = Length(Mix(b.min, b.max, alpha) - b.min);
+	const unsigned long long total = (unsigned long long)sx * sy * sz;
+	const size_t words = size_t((total + 31) / 32);
+	Scratch scratch(stream);
+	uint32_t* d_hits = nullptr;
+	TG_CUDA(scratch.Alloc(&d_hits, words));
+	TG_CUDA(cudaMemsetAsync(d_hits, 0, words * 4, stream));
+	const unsigned long long threads = (total + 3) / 4;
+	VoxelKernel<<<uint32_t((threads + 127) / 128), 128, 0, stream>>>(MakeDeviceModel(model), b.min.x, b.min.y, b.min.z, b.max.x, b.max.y, b.max.z,
+		sx, sy, sz, radius, d_hits, total);
+	TG_CUDA(cudaGetLastError());
+	std::vector<uint32_t> hits(words);
+	TG_CUDA(cudaMemcpyAsync(hits.data(), d_hits, words * 4, cudaMemcpyDeviceToHost, stream));
+	TG_CUDA(cudaStreamSynchronize(stream));
+	uint64_t count = 0;
+	for (uint32_t w : hits) count += uint64_t(__builtin_popcount(w));
+	int32_t* xyz = static_cast<int32_t*>(std::malloc((count + 1) * 12));
+	if (!xyz)
+	{
+		error = "out of host memory";
+		return TG_ERR_MEMORY;
+	}
+	uint64_t n = 0;
+	const int slice = sx * sy;
+	for (size_t w = 0; w < words; ++w)
+	{
+		uint32_t bits = hits[w];
+		while (bits)
+		{
+			const int bit = __builtin_ctz(bits);
+			bits &= bits - 1;
+			const int i = int(w * 32 + size_t(bit));
+			xyz[n * 3 + 0] = i % sx;
+			xyz[n * 3 + 1] = (i % slice) / sx;
+			xyz[n * 3 + 2] = i / slice;
+			n++;
+		}
+	}
+	out_size[0] = sx;
+	out_size[1] = sy;
+	out_size[2] = sz;
+	*out_radius = radius;
+	*out_xyz = xyz;
+	*out_count = count;
+	return TG_OK;
+}
+
+int EngineExportPoints(Model* model, const float mn[3], const float mx[3], const float step[3], int refine, uint32_t flags, tg_mesh* out, std::string& error)
+{
+	std::memset(out, 0, sizeof(*out));
+	Context* ctx = model->context;
+	TG_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t stream = StreamOf(ctx);
+	// export.cpp:394-399
+	int n[3];
+	for (int c = 0; c < 3; ++c)
+	{
+		if (!(step[c] > 0.0f))
+		{
+			error = "step must be positive";
+			return TG_ERR_INVALID;
+		}
+		n[c] = int(std::ceil((mx[c] - mn[c]) / step[c]));
+	}
+	if (n[0] <= 0 || n[1] <= 0 || n[2] <= 0 || double(n[0]) * n[1] * n[2] >= 2147483647.0)
+	{
+		error = "point-cloud grid is empty or exceeds the reference's int cell index (export.cpp:396-399)";
+		return TG_ERR_INVALID;
+	}
+	const unsigned long long total = (unsigned long long)n[0] * n[1] * n[2];
+	const size_t words = size_t((total + 31) / 32);
+	const Vec3 half(step[0] / 2.0f, step[1] / 2.0f, step[2] / 2.0f);
+	const float diagonal = Length(half);
+	Scratch scratch(stream);
+	uint64_t launches = 0;
+	uint32_t *d_hits = nullptr, *d_prefix = nullptr;
+	unsigned long long* counters = nullptr;
+	TG_CUDA(scratch.Alloc(&d_hits, words));
+	TG_CUDA(scratch.Alloc(&d_prefix, words));
+	TG_CUDA(scratch.Alloc(&counters, kCntCount));
+	TG_CUDA(cudaMemsetAsync(d_hits, 0, words * 4, stream));
+	ctx->stage.store(1);
+	StageTimer timer(stream);
+	const int t0 = timer.Mark();
+	PointCloudKernel<<<uint32_t((total + 127) / 128), 128, 0, stream>>>(MakeDeviceModel(model), mn[0], mn[1], mn[2], step[0], step[1], step[2],
+		n[0], n[1], n[2], diagonal, d_hits, total);
+	launches++;
+	int rc = DeviceExclusiveScan(stream, scratch, LoadPopcount32{ d_hits }, words, d_prefix, counters + kCntTotalVertices, launches, error);
+	if (rc != TG_OK) return rc;
+	unsigned long long host_total = 0;
+	TG_CUDA(cudaMemcpyAsync(&host_total, counters + kCntTotalVertices, 8, cudaMemcpyDeviceToHost, stream));
+	TG_CUDA(cudaStreamSynchronize(stream));
+	const uint32_t count = uint32_t(host_total);
+	MeshResultDevice* result = new MeshResultDevice();
+	result->context = ctx;
+	out->opaque = result;
+	out->vertex_count = count;
+	if (count > 0)
+	{
+		TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_positions), size_t(count) * 12, stream));
+		GatherCloudKernel<<<uint32_t((total + 255) / 256), 256, 0, stream>>>(d_hits, d_prefix, total, mn[0], mn[1], mn[2], step[0], step[1], step[2], n[0], n[1], result->d_positions);
+		launches++;
+		ctx->stage.store(refine > 0 ? 2 : 3);
+		tg_mesh_options options;
+		std::memset(&options, 0, sizeof(options));
+		options.flags = flags;
+		options.refine_iterations = refine;
+		options.scale = 1.0f;
+		const float halfv[3] = { half.x, half.y, half.z };
+		rc = FinishAttributes(model, scratch, result, count, options, halfv, launches, error);
+		if (rc != TG_OK) return rc;
+		const int t1 = timer.Mark();
+		TG_CUDA(cudaStreamSynchronize(stream));
+		out->timings.total_device_ms = timer.Ms(t0, t1);
+		auto fetch = [&](void* device, size_t bytes, void** host) -> int
+		{
+			if (!device || bytes == 0) return TG_OK;
+			void* p = ctx->AcquirePinned(bytes, error);
+			if (!p) return TG_ERR_MEMORY;
+			result->pinned.push_back(p);
+			TG_CUDA(cudaMemcpyAsync(p, device, bytes, cudaMemcpyDeviceToHost, stream));
+			*host = p;
+			return TG_OK;
+		};
+		if ((rc = fetch(result->d_positions, size_t(count) * 12, reinterpret_cast<void**>(&out->positions))) != TG_OK) return rc;
+		if ((rc = fetch(result->d_normals, size_t(count) * 12, reinterpret_cast<void**>(&out->normals))) != TG_OK) return rc;
+		if ((rc = fetch(result->d_colors, size_t(count) * 3, reinterpret_cast<void**>(&out->colors))) != TG_OK) return rc;
+		TG_CUDA(cudaStreamSynchronize(stream));
+	}
+	out->timings.kernel_launches = launches;
+	ctx->stage.store(0);
+	return TG_OK;
+}
+
+int EngineTimerBegin(Context* ctx, std::string& error)
+{
+	TG_CUDA(cudaSetDevice(ctx->device));
+	TG_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ctx->timer_events[0]), StreamOf(ctx)));
+	return TG_OK;
+}
+
+int EngineTimerEnd(Context* ctx, float* out_ms, std::string& error)
+{
+	TG_CUDA(cudaSetDevice(ctx->device));
+	cudaEvent_t e1 = static_cast<cudaEvent_t>(ctx->timer_events[1]);
+	TG_CUDA(cudaEventRecord(e1, StreamOf(ctx)));
+	TG_CUDA(cudaEventSynchronize(e1));
+	TG_CUDA(cudaEventElapsedTime(out_ms, static_cast<cudaEvent_t>(ctx->timer_events[0]), e1));
+	return TG_OK;
+}
+
+int EngineMeasureFp32Peak(Context* ctx, double* out_tflops, std::string& error)
+{
+	TG_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t stream = StreamOf(ctx);
+	Scratch scratch(stream);
+	const int blocks = ctx->sm_count * 8, threads = 256, iterations = 4096;
+	float* d_out = nullptr;
+	TG_CUDA(scratch.Alloc(&d_out, size_t(blocks) * threads));
+	StageTimer timer(stream);
+	double best = 0.0;
+	for (int rep = 0; rep < 5; ++rep)
+	{
+		const int t0 = timer.Mark();
+		FmaChainKernel<<<blocks, threads, 0, stream>>>(d_out, iterations);
+		const int t1 = timer.Mark();
+		TG_CUDA(cudaStreamSynchronize(stream));
+		TG_CUDA(cudaGetLastError());
+		const double flops = double(blocks) * threads * double(iterations) * 64.0 * 2.0;
+		const double tf = flops / (double(timer.Ms(t0, t1)) * 1e-3) * 1e-12;
+		if (rep > 0 && tf > best) best = tf;
+	}
+	*out_tflops = best;
+	return TG_OK;
+}
+
+int EngineFlushL2(Context* ctx, std::string& error)
+{
+	TG_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t stream = StreamOf(ctx);
+	Scratch scratch(stream);
+	const size_t count = size_t(256) << 18; // 256 MiB of u32 > 126 MB L2
+	uint32_t* d = nullptr;
+	TG_CUDA(scratch.Alloc(&d, count));
+	FillKernel<<<ctx->sm_count * 8, 256, 0, stream>>>(d, count, 0u);
+	TG_CUDA(cudaGetLastError());
+	return TG_OK;
+}
+
+} // namespace tg

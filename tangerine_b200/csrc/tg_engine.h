@@ -1,0 +1,76 @@
+// Host-visible interface of the CUDA engine (implemented in tg_engine.cu).  The C ABI in tg_api.cpp is a
+// thin layer over these classes; nothing here is exported from the shared library directly.
+#pragma once
+
+#include <atomic>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/tangerine_b200.h"
+#include "tg_octree.h"
+
+namespace tg
+{
+
+struct PinnedBlock
+{
+	void* ptr = nullptr;
+	size_t bytes = 0;
+	bool in_use = false;
+};
+
+class Context
+{
+public:
+	int device = 0;
+	void* stream = nullptr;      // cudaStream_t
+	void* timer_events[2] = { nullptr, nullptr };
+	std::vector<PinnedBlock> pinned; // grow-only pool of page-locked host buffers for results
+	int sm_count = 0;
+
+	// Export progress mirrors the reference's atomics (export.cpp:48-57).
+	std::atomic<int> stage{ 0 };
+	std::atomic<bool> active{ true };
+	std::atomic<uint64_t> progress_done[4];
+	std::atomic<uint64_t> progress_total[4];
+
+	static Context* Create(int device, std::string& error);
+	~Context();
+
+	void* AcquirePinned(size_t bytes, std::string& error);
+	void ReleasePinned(void* ptr);
+	bool Cancelled() const { return !active.load(); }
+};
+
+class Model
+{
+public:
+	Context* context = nullptr;
+	FlatModel flat;          // host copy of the tables (kept for stats and debugging)
+	void* d_nodes = nullptr;
+	void* d_interp = nullptr;
+	void* d_tree = nullptr;
+	void* d_materials = nullptr;
+	uint64_t device_bytes = 0;
+	double upload_seconds = 0.0;
+	int leaf_count = 0;
+
+	static Model* Create(Context* context, const Tree& tree, float target_size, int threads, std::string& error);
+	~Model();
+};
+
+struct MeshResultDevice; // opaque device-side result kept alive by tg_mesh.opaque
+
+int EngineEvalPoints(Model* model, int mode, const float* points, uint64_t count, void* out, std::string& error);
+int EngineEvalLattice(Model* model, const tg_grid& grid, float* out, float* out_ms, std::string& error);
+int EngineExportMesh(Model* model, const tg_grid& grid, const tg_mesh_options& options, tg_mesh* out, std::string& error);
+int EngineExportPoints(Model* model, const float mn[3], const float mx[3], const float step[3], int refine, uint32_t flags, tg_mesh* out, std::string& error);
+int EngineExportVoxels(Model* model, float grid_size, int32_t out_size[3], float* out_radius, int32_t** out_xyz, uint64_t* out_count, std::string& error);
+void EngineFreeMesh(tg_mesh* mesh);
+int EngineTimerBegin(Context* context, std::string& error);
+int EngineTimerEnd(Context* context, float* out_ms, std::string& error);
+int EngineMeasureFp32Peak(Context* context, double* out_tflops, std::string& error);
+int EngineFlushL2(Context* context, std::string& error);
+
+} // namespace tg

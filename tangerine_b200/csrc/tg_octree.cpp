@@ -1,0 +1,504 @@
+// See tg_octree.h.  Line references are to the reference's tangerine/sdf_evaluator.cpp.
+#include "tg_octree.h"
+
+#include <chrono>
+#include <future>
+#include <memory>
+#include <thread>
+
+namespace tg
+{
+
+namespace
+{
+
+struct Subtree;
+
+struct BuildNode
+{
+	Box3 bounds;
+	Vec3 pivot;
+	bool terminus = false;
+	uint32_t evaluator = kNoNode; // index into the owning Subtree's pool
+	int32_t evaluator_leaves = 0;
+	// >= 0: index into Subtree::nodes; -1: empty octant; <= -2: root of Subtree::spawned[-2 - value]
+	int32_t children[8] = { -1, -1, -1, -1, -1, -1, -1, -1 };
+};
+
+struct Subtree
+{
+	NodePool pool;
+	std::vector<BuildNode> nodes;
+	std::vector<std::unique_ptr<Subtree>> spawned;
+	int32_t root = -1;
+};
+
+struct Builder
+{
+	float target_size;
+	int parallel_depth; // nodes at depth <= parallel_depth build their octants on worker threads
+
+	// SDFOctree::SDFOctree :1641-1700 with Coalesce = true, MaxDepth = -1 (what MeshExportThread asks for)
+	int32_t Construct(Subtree& st, uint32_t in_evaluator, Box3 bounds, int depth)
+	{
+		const int32_t self = int32_t(st.nodes.size());
+		st.nodes.emplace_back();
+		Vec3 extent = bounds.max - bounds.min;
+		float span = std::fmax(std::fmax(extent.x, extent.y), extent.z);
+		Vec3 pivot = Vec3(float(span * 0.5)) + bounds.min;
+		float radius = float(Length(Vec3(span)) * 0.5);
+		uint32_t evaluator = st.pool.Clip(in_evaluator, pivot, radius);
+		{
+			BuildNode& n = st.nodes[self];
+			n.bounds = bounds;
+			n.pivot = pivot;
+			n.evaluator = evaluator;
+			n.evaluator_leaves = evaluator != kNoNode ? st.pool.nodes[evaluator].leaf_count : 0;
+			n.terminus = span <= target_size || evaluator == kNoNode;
+		}
+		if (!st.nodes[self].terminus)
+		{
+			Populate(st, self, depth);
+		}
+		return self;
+	}
+
+	static Box3 Octant(const Box3& bounds, Vec3 pivot, int i) // :1714-1738
+	{
+		Box3 cb = bounds;
+		if (i & 1) cb.min.x = pivot.x; else cb.max.x = pivot.x;
+		if (i & 2) cb.min.y = pivot.y; else cb.max.y = pivot.y;
+		if (i & 4) cb.min.z = pivot.z; else cb.max.z = pivot.z;
+		return cb;
+	}
+
+	// SDFOctree::Populate :1703-1783
+	void Populate(Subtree& st, int32_t self, int depth)
+	{
+		const Box3 bounds = st.nodes[self].bounds;
+		const Vec3 pivot = st.nodes[self].pivot;
+		const uint32_t evaluator = st.nodes[self].evaluator;
+		bool uniform = true;
+		bool penultimate = true;
+		int live = 0;
+
+		if (depth <= parallel_depth)
+		{
+			// Each octant prunes against a private copy of the pool, so the eight can run concurrently.
+			std::future<std::unique_ptr<Subtree>> jobs[8];
+			for (int i = 0; i < 8; ++i)
+			{
+				Box3 cb = Octant(bounds, pivot, i);
+				jobs[i] = std::async(std::launch::async, [this, &st, evaluator, cb, depth]()
+				{
+					std::unique_ptr<Subtree> child(new Subtree);
+					child->pool = st.pool;
+					child->root = Construct(*child, evaluator, cb, depth + 1);
+					return child;
+				});
+			}
+			for (int i = 0; i < 8; ++i)
+			{
+				std::unique_ptr<Subtree> child = jobs[i].get();
+				const BuildNode& cn = child->nodes[child->root];
+				if (cn.evaluator != kNoNode)
+				{
+					// The child's pool is a superset of this pool, so `evaluator` means the same node there.
+					uniform &= child->pool.Equal(evaluator, cn.evaluator);
+					penultimate &= cn.terminus;
+					live++;
+					st.nodes[self].children[i] = -2 - int32_t(st.spawned.size());
+					st.spawned.push_back(std::move(child));
+				}
+			}
+		}
+		else
+		{
+			for (int i = 0; i < 8; ++i)
+			{
+				int32_t child = Construct(st, evaluator, Octant(bounds, pivot, i), depth + 1);
+				const BuildNode& cn = st.nodes[child];
+				if (cn.evaluator != kNoNode)
+				{
+					uniform &= st.pool.Equal(evaluator, cn.evaluator);
+					penultimate &= cn.terminus;
+					live++;
+					st.nodes[self].children[i] = child;
+				}
+			}
+		}
+
+		BuildNode& n = st.nodes[self];
+		if (live == 0)
+		{
+			n.evaluator = kNoNode; // :1753-1759
+			n.terminus = true;
+		}
+		else if ((penultimate && uniform) || n.evaluator_leaves <= (depth > 3 ? depth : 3)) // :1769
+		{
+			for (int i = 0; i < 8; ++i)
+			{
+				n.children[i] = -1;
+			}
+			n.terminus = true;
+		}
+	}
+};
+
+// ------------------------------------------------------------------------------------------------
+// Device stream generation
+// ------------------------------------------------------------------------------------------------
+
+struct StreamGen
+{
+	const NodePool& pool;
+	std::vector<uint32_t>& out;
+	const bool tree_stream;
+	int depth = 0;      // values currently held (accumulator + spilled)
+	int max_slots = 0;  // deepest spill slot used + 1
+	uint32_t flops = 0;
+	bool cullable = true;
+
+	StreamGen(const NodePool& p, std::vector<uint32_t>& o, bool tree) : pool(p), out(o), tree_stream(tree) {}
+
+	void PushF(float f) { out.push_back(FloatBits(f)); }
+
+	void EmitBrush(const Node& n, uint32_t op, float threshold, uint32_t flags)
+	{
+		const size_t start = out.size();
+		out.push_back(0);
+		uint32_t xform = kXformNone;
+		const bool identity = n.rotation.IsIdentity();
+		const bool unit = n.scalation == 1.0f;
+		const bool moved = !(n.translation == Vec3(0.0f, 0.0f, 0.0f));
+		if (tree_stream)
+		{
+			// Transform::ApplyInv: rotate(inverse(q), p - t) / s.  With q = identity and s = 1 that is p - t exactly.
+			if (!identity || !unit)
+			{
+				xform = kXformQuat;
+				Quat iq = Inverse(n.rotation);
+				PushF(iq.w); PushF(iq.x); PushF(iq.y); PushF(iq.z);
+				PushF(n.translation.x); PushF(n.translation.y); PushF(n.translation.z);
+				PushF(n.scalation);
+			}
+			else if (moved)
+			{
+				xform = kXformOffset;
+				PushF(-n.translation.x); PushF(-n.translation.y); PushF(-n.translation.z);
+			}
+		}
+		else
+		{
+			// EvaluatorTransform::Compile :409-429
+			if (!identity || !unit)
+			{
+				xform = kXformMatrix;
+				Mat4 inv = CompiledInverseMatrix(n);
+				for (int c = 0; c < 4; ++c)
+				{
+					for (int r = 0; r < 3; ++r)
+					{
+						PushF(inv.m[c][r]);
+					}
+				}
+			}
+			else if (moved)
+			{
+				xform = kXformOffset;
+				PushF(-n.translation.x); PushF(-n.translation.y); PushF(-n.translation.z);
+			}
+		}
+		for (int i = 0; i < BrushParamCount(n.kind); ++i)
+		{
+			PushF(n.params[i]);
+		}
+		if (!unit)
+		{
+			flags |= kHdrScaleBit;
+			PushF(n.scalation);
+			flops += 1;
+		}
+		if (tree_stream)
+		{
+			flags |= kHdrMaterialBit;
+			out.push_back(n.material);
+		}
+		uint32_t slot = kNoSlot;
+		if (op == kOpPush)
+		{
+			if (depth >= 1)
+			{
+				slot = uint32_t(depth - 1);
+				if (depth > max_slots) max_slots = depth;
+			}
+			depth++;
+		}
+		else if (op >= kOpBlendUnion && op <= kOpBlendDiff)
+		{
+			PushF(threshold);
+		}
+		flops += uint32_t(XformFlops(xform) + BrushFlops(n.kind) + OpFlops(op));
+		if (n.kind == kKindEllipsoid)
+		{
+			cullable = false;
+		}
+		out[start] = MakeHeader(n.kind, xform, op, slot, flags, uint32_t(out.size() - start));
+	}
+
+	void EmitOp(uint32_t op, float param, uint32_t word, bool has_word, uint32_t flags)
+	{
+		const size_t start = out.size();
+		out.push_back(0);
+		uint32_t slot = kNoSlot;
+		if (op != kOpFlate && op != kOpStop)
+		{
+			slot = uint32_t(depth - 2); // the left operand / stencil child lives one below the accumulator
+			depth--;
+		}
+		if ((op >= kOpBlendUnion && op <= kOpBlendDiff) || op == kOpFlate)
+		{
+			PushF(param);
+		}
+		if (has_word)
+		{
+			out.push_back(word);
+		}
+		flops += uint32_t(OpFlops(op));
+		out[start] = MakeHeader(kBrushNone, kXformNone, op, slot, flags, uint32_t(out.size() - start));
+	}
+
+	void Gen(uint32_t index)
+	{
+		const Node& n = pool.nodes[index];
+		if (IsBrush(n.kind))
+		{
+			EmitBrush(n, kOpPush, 0.0f, 0);
+		}
+		else if (IsSet(n.kind))
+		{
+			Gen(n.a);
+			const Node& r = pool.nodes[n.b];
+			uint32_t flags = (pool.nodes[n.a].has_paint ? kHdrLhsPaintBit : 0) | (r.has_paint ? kHdrRhsPaintBit : 0);
+			const uint32_t op = n.kind - 8;
+			if (IsBrush(r.kind))
+			{
+				EmitBrush(r, op, n.params[0], flags); // fused: accumulator = op(accumulator, brush)
+			}
+			else
+			{
+				Gen(n.b);
+				EmitOp(op, n.params[0], 0, false, flags);
+			}
+		}
+		else if (n.kind == kKindFlate)
+		{
+			Gen(n.a);
+			EmitOp(kOpFlate, n.params[0], 0, false, 0);
+		}
+		else
+		{
+			Gen(n.a);
+			if (tree_stream)
+			{
+				Gen(n.b);
+				EmitOp(kOpStencil, 0.0f, n.material, true, n.kind == kKindStencilNeg ? kHdrStencilNegBit : 0);
+			}
+		}
+	}
+
+	void Finish()
+	{
+		out.push_back(MakeHeader(kBrushNone, kXformNone, kOpStop, kNoSlot, 0, 1));
+	}
+};
+
+inline uint64_t Fnv(uint64_t hash, const void* data, size_t bytes)
+{
+	const uint8_t* c = static_cast<const uint8_t*>(data);
+	for (size_t i = 0; i < bytes; ++i)
+	{
+		hash ^= c[i];
+		hash *= 0x100000001B3ull;
+	}
+	return hash;
+}
+
+struct Flattener
+{
+	FlatModel& model;
+	std::vector<uint32_t> ref_words;
+	int max_slots = 0;
+
+	// Pre-order walk (same order as the octree hash in oracle/ref_tool.cpp) emitting one FlatNode per octree node.
+	uint32_t Walk(const Subtree& st, int32_t index)
+	{
+		const BuildNode& bn = st.nodes[index];
+		const uint32_t self = uint32_t(model.nodes.size());
+		model.nodes.emplace_back();
+		{
+			FlatNode fn;
+			fn.pivot[0] = bn.pivot.x;
+			fn.pivot[1] = bn.pivot.y;
+			fn.pivot[2] = bn.pivot.z;
+			fn.terminus = bn.terminus ? 1u : 0u;
+			for (int i = 0; i < 8; ++i) fn.children[i] = -1;
+			fn.interp_offset = uint32_t(model.interp.size());
+			fn.tree_offset = uint32_t(model.tree.size());
+			StreamGen interp(st.pool, model.interp, false);
+			interp.Gen(bn.evaluator);
+			interp.Finish();
+			StreamGen tree(st.pool, model.tree, true);
+			tree.Gen(bn.evaluator);
+			tree.Finish();
+			fn.flags = interp.cullable ? kNodeCullable : 0u;
+			fn.flops = interp.flops;
+			if (tree.max_slots > max_slots) max_slots = tree.max_slots;
+			model.nodes[self] = fn;
+		}
+		// Reference-format words: statistics + hash only.
+		ref_words.clear();
+		st.pool.CompileReference(bn.evaluator, ref_words);
+		ref_words.push_back(0); // OpcodeT::Stop (:1381)
+		uint32_t child_mask = 0;
+		for (int i = 0; i < 8; ++i)
+		{
+			if (bn.children[i] != -1) child_mask |= 1u << i;
+		}
+		FlatModelStats& s = model.stats;
+		const uint32_t terminus = bn.terminus ? 1u : 0u;
+		const uint64_t words = ref_words.size();
+		s.nodes++;
+		s.ref_words += words;
+		if (terminus)
+		{
+			s.leaves++;
+			s.ref_leaf_words += words;
+		}
+		if (words > s.ref_max_words) s.ref_max_words = words;
+		const uint64_t stack = st.pool.nodes[bn.evaluator].stack_size;
+		if (stack > s.max_stack) s.max_stack = stack;
+		s.hash = Fnv(s.hash, &bn.pivot, 12);
+		s.hash = Fnv(s.hash, &terminus, 4);
+		s.hash = Fnv(s.hash, &child_mask, 4);
+		s.hash = Fnv(s.hash, ref_words.data(), words * 4);
+
+		for (int i = 0; i < 8; ++i)
+		{
+			const int32_t c = bn.children[i];
+			if (c == -1) continue;
+			uint32_t child_index;
+			if (c >= 0)
+			{
+				child_index = Walk(st, c);
+			}
+			else
+			{
+				const Subtree& sub = *st.spawned[size_t(-2 - c)];
+				child_index = Walk(sub, sub.root);
+			}
+			model.nodes[self].children[i] = int32_t(child_index);
+		}
+		return self;
+	}
+};
+
+} // namespace
+
+bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel& out, std::string& error)
+{
+	const auto t0 = std::chrono::steady_clock::now();
+	out = FlatModel();
+	if (!tree.Valid())
+	{
+		error = "empty tree";
+		return false;
+	}
+	// SDFOctree::Create :1609-1638
+	if (!tree.HasFiniteBounds())
+	{
+		error = "Unable to construct SDF octree for infinite area evaluator.";
+		return false;
+	}
+	auto degenerate = [](const Box3& b)
+	{
+		for (int i = 0; i < 3; ++i)
+		{
+			if (std::isinf(b.min[i]) || std::isinf(b.max[i]) || std::isnan(b.min[i]) || std::isnan(b.max[i]) || b.max[i] <= b.min[i]) return true;
+		}
+		return false;
+	};
+	out.bounds = tree.Bounds();
+	if (degenerate(out.bounds))
+	{
+		error = "model bounds are degenerate";
+		return false;
+	}
+	// AABB::BoundingCube (tangerine/aabb.cpp) then operator+(Margin = 0)
+	Vec3 extent = out.bounds.max - out.bounds.min;
+	float longest = std::fmax(std::fmax(extent.x, extent.y), extent.z);
+	Vec3 padding = (Vec3(longest) - extent) * Vec3(0.5f);
+	Box3 cube = { out.bounds.min - padding, out.bounds.max + padding };
+	cube.min = cube.min - Vec3(0.0f);
+	cube.max = cube.max + Vec3(0.0f);
+	if (degenerate(cube))
+	{
+		error = "model bounding cube is degenerate";
+		return false;
+	}
+
+	if (threads <= 0)
+	{
+		threads = int(std::thread::hardware_concurrency());
+	}
+	Builder builder;
+	builder.target_size = target_size;
+	builder.parallel_depth = threads >= 16 ? 2 : threads >= 2 ? 1 : 0;
+
+	Subtree top;
+	top.pool = tree.pool;
+	top.root = builder.Construct(top, tree.root, cube, 1);
+	if (top.nodes[top.root].evaluator == kNoNode)
+	{
+		error = "octree pruned the whole model away";
+		return false;
+	}
+
+	out.stats.hash = 0xCBF29CE484222325ull;
+	Flattener flattener{ out };
+	flattener.Walk(top, top.root);
+	if (flattener.max_slots > kMaxStackSlots)
+	{
+		error = "CSG tree nests deeper than the device operand stack (" + std::to_string(kMaxStackSlots) + " slots)";
+		return false;
+	}
+	out.has_paint = top.pool.nodes[top.nodes[top.root].evaluator].has_paint;
+
+	// Unpruned model programs (VoxExport and whole-tree point queries).
+	{
+		out.root_interp_offset = uint32_t(out.interp.size());
+		StreamGen interp(tree.pool, out.interp, false);
+		interp.Gen(tree.root);
+		interp.Finish();
+		out.root_flops = interp.flops;
+		out.root_tree_offset = uint32_t(out.tree.size());
+		StreamGen tstream(tree.pool, out.tree, true);
+		tstream.Gen(tree.root);
+		tstream.Finish();
+		if (tstream.max_slots > kMaxStackSlots)
+		{
+			error = "CSG tree nests deeper than the device operand stack";
+			return false;
+		}
+	}
+	SnapshotMaterials(out.material_rgb);
+	out.material_rgb.push_back(1.0f); // default material (GetDefaultMaterial :34-38), addressed by kNoMaterial
+	out.material_rgb.push_back(1.0f);
+	out.material_rgb.push_back(1.0f);
+	out.stats.interp_words = out.interp.size();
+	out.stats.tree_words = out.tree.size();
+	out.stats.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	return true;
+}
+
+} // namespace tg

@@ -1,0 +1,53 @@
+// Host octree build + flattening into the device tables.
+//
+// BuildFlatModel reproduces SDFOctree::Create / the SDFOctree constructor / Populate
+// (tangerine/sdf_evaluator.cpp:1609-1783) decision for decision -- same bounding cube, pivots, clip
+// radii, empty-octant pruning and coalescing rule -- so that every sample the GPU evaluates runs the
+// pruned program the reference would have picked for it (SDFOctree::Descend, :1801-1835).  The
+// octants of the first two levels are built on worker threads, each with a private copy of the node
+// pool; results are merged by a pre-order walk that also emits both device instruction streams.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "tg_program.h"
+#include "tg_tree.h"
+
+namespace tg
+{
+
+struct FlatModelStats
+{
+	uint64_t nodes = 0;        // octree nodes
+	uint64_t leaves = 0;       // terminal nodes
+	uint64_t ref_words = 0;    // size of all programs in the reference's word encoding
+	uint64_t ref_leaf_words = 0;
+	uint64_t ref_max_words = 0;
+	uint64_t max_stack = 0;    // largest SDFNode::StackSize of any node program
+	uint64_t hash = 0;         // FNV-1a over (pivot, terminus, child mask, reference words) in pre-order
+	uint64_t interp_words = 0; // device stream sizes
+	uint64_t tree_words = 0;
+	double build_seconds = 0.0;
+};
+
+struct FlatModel
+{
+	std::vector<FlatNode> nodes;      // node 0 is the octree root
+	std::vector<uint32_t> interp;     // kStreamInterp programs, addressed by FlatNode::interp_offset
+	std::vector<uint32_t> tree;       // kStreamTree programs, addressed by FlatNode::tree_offset
+	std::vector<float> material_rgb;  // 3 floats per material id; one extra trailing entry = default white
+	uint32_t root_tree_offset = 0;    // kStreamTree program of the *unpruned* model (VoxExport samples it, magica.cpp:61)
+	uint32_t root_interp_offset = 0;  // kStreamInterp program of the unpruned model
+	uint32_t root_flops = 0;
+	Box3 bounds;                      // Evaluator->Bounds()
+	bool has_paint = false;           // Octree->Evaluator->HasPaint() (export.cpp:285)
+	FlatModelStats stats;
+};
+
+// Returns false (and sets error) when the tree has no finite bounds, prunes away entirely, or nests
+// deeper than the device stack supports.  threads <= 0 picks std::thread::hardware_concurrency().
+bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel& out, std::string& error);
+
+} // namespace tg
