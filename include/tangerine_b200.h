@@ -145,6 +145,9 @@ TG_API tg_model* tg_model_create(tg_context* context, const tg_tree* tree, float
  * reference_*, max_stack, bounds, has_paint, leaf_count and build_seconds fields. */
 TG_API int tg_tree_octree_stats(const tg_tree* tree, float octree_target_size, int host_threads, tg_model_stats* out);
 TG_API void tg_model_destroy(tg_model* model);
+/* Copies the model's tables (octree nodes, both instruction streams, material colours) host -> device again.
+ * tg_model_create already did this once; bench.py calls it inside its end-to-end timed region. */
+TG_API int tg_model_upload(tg_model* model);
 TG_API int tg_model_get_stats(const tg_model* model, tg_model_stats* out);
 
 /* ------------------------------------------------------------------------------------------------
@@ -275,6 +278,12 @@ TG_API int tg_timer_begin(tg_context* context);
 TG_API int tg_timer_end(tg_context* context, float* out_ms);
 TG_API int tg_measure_fp32_peak(tg_context* context, double* out_tflops);
 TG_API int tg_flush_l2(tg_context* context);
+TG_API int tg_context_synchronize(tg_context* context);
+
+/* Multi-GPU partitioning: number of 8^3-cell bricks that survive culling in each brick layer
+ * (layer b = cell layers [8b, 8b+8)); out_layers needs ceil(sz / 8) entries.  Every rank computes the same
+ * profile and cuts the grid into z-slabs of equal work without communicating. */
+TG_API int tg_brick_profile(tg_model* model, const tg_grid* grid, uint32_t* out_layers, uint32_t layer_count);
 
 #ifdef __cplusplus
 }

@@ -620,7 +620,10 @@ static int CmdBench(SDFNodeShared Tree, GridArgs Args, int ThreadCount, int Slic
 	{
 		Slices.push_back(k);
 	}
-	std::atomic<size_t> NextSlice(0);
+	// Work items are (slice, row) pairs so that a bounded sample of a few slices still keeps every host
+	// thread busy (the reference's own PSTL loop hands out whole slices, surface_nets.cpp:1174-1195).
+	std::atomic<size_t> NextRow(0);
+	const size_t RowCount = Slices.size() * size_t(Task.Grid.sy);
 	auto T2 = Clock::now();
 	{
 		std::vector<std::thread> Threads;
@@ -630,15 +633,13 @@ static int CmdBench(SDFNodeShared Tree, GridArgs Args, int ThreadCount, int Slic
 			{
 				while (true)
 				{
-					size_t Index = NextSlice.fetch_add(1);
-					if (Index >= Slices.size()) break;
-					size_t k = Slices[Index];
-					for (size_t j = 0; j < Task.Grid.sy; ++j)
+					size_t Index = NextRow.fetch_add(1);
+					if (Index >= RowCount) break;
+					size_t k = Slices[Index / size_t(Task.Grid.sy)];
+					size_t j = Index % size_t(Task.Grid.sy);
+					for (size_t i = 0; i < Task.Grid.sx; ++i)
 					{
-						for (size_t i = 0; i < Task.Grid.sx; ++i)
-						{
-							Task.FirstLoopInnerThunk(Task, { i, j, k });
-						}
+						Task.FirstLoopInnerThunk(Task, { i, j, k });
 					}
 				}
 			});

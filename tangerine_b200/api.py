@@ -160,6 +160,9 @@ def lib():
         "tg_timer_end": (i32, [vp, fp]),
         "tg_measure_fp32_peak": (i32, [vp, C.POINTER(C.c_double)]),
         "tg_flush_l2": (i32, [vp]),
+        "tg_context_synchronize": (i32, [vp]),
+        "tg_model_upload": (i32, [vp]),
+        "tg_brick_profile": (i32, [vp, C.POINTER(Grid), C.POINTER(C.c_uint32), u32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -374,6 +377,9 @@ class Context:
     def flush_l2(self):
         _check(lib().tg_flush_l2(self.h))
 
+    def synchronize(self):
+        _check(lib().tg_context_synchronize(self.h))
+
     def progress(self):
         ratios = (C.c_float * 4)()
         stage = C.c_int()
@@ -442,6 +448,15 @@ class Model:
         s = ModelStats()
         _check(lib().tg_model_get_stats(self.h, C.byref(s)))
         return s.as_dict()
+
+    def upload(self):
+        _check(lib().tg_model_upload(self.h))
+
+    def brick_profile(self, grid):
+        n = (grid.shape[2] + 7) // 8
+        out = np.zeros(n, np.uint32)
+        _check(lib().tg_brick_profile(self.h, C.byref(grid), out.ctypes.data_as(C.POINTER(C.c_uint32)), n))
+        return out
 
     def eval_points(self, points, mode=EVAL_OCTREE):
         pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)

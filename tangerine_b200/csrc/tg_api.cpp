@@ -643,4 +643,28 @@ int tg_flush_l2(tg_context* context)
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
 
+int tg_context_synchronize(tg_context* context)
+{
+	if (!context) return Fail(TG_ERR_INVALID, "null context");
+	std::string error;
+	int rc = EngineSynchronize(context->impl.get(), error);
+	return rc == TG_OK ? rc : Fail(rc, error);
+}
+
+int tg_model_upload(tg_model* model)
+{
+	if (!model) return Fail(TG_ERR_INVALID, "null model");
+	std::string error;
+	int rc = EngineUploadModel(model->impl.get(), error);
+	return rc == TG_OK ? rc : Fail(rc, error);
+}
+
+int tg_brick_profile(tg_model* model, const tg_grid* grid, uint32_t* out_layers, uint32_t layer_count)
+{
+	if (!model || !grid || !out_layers) return Fail(TG_ERR_INVALID, "null argument");
+	std::string error;
+	int rc = EngineBrickProfile(model->impl.get(), *grid, out_layers, layer_count, error);
+	return rc == TG_OK ? rc : Fail(rc, error);
+}
+
 } // extern "C"

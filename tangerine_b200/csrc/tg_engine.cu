@@ -562,6 +562,12 @@ __global__ void InitBrickListKernel(uint32_t* list, uint32_t nbx, uint32_t nby, 
 	list[index] = x | (y << 10) | (z << 20);
 }
 
+__global__ void BrickLayerHistogramKernel(const uint32_t* __restrict__ list, uint32_t count, uint32_t* __restrict__ layers)
+{
+	const uint32_t index = blockIdx.x * blockDim.x + threadIdx.x;
+	if (index < count) atomicAdd(&layers[(list[index] >> 20) & 1023u], 1u);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Device-wide exclusive scan (block sums -> scan of sums -> per-element prefix)
 // ------------------------------------------------------------------------------------------------
@@ -1171,10 +1177,22 @@ static int UploadVector(Context* c, const std::vector<T>& v, void** out, uint64_
 	return TG_OK;
 }
 
+static void FreeModelTables(Model* m)
+{
+	cudaFree(m->d_nodes);
+	cudaFree(m->d_interp);
+	cudaFree(m->d_tree);
+	cudaFree(m->d_materials);
+	m->d_nodes = m->d_interp = m->d_tree = m->d_materials = nullptr;
+	m->device_bytes = 0;
+}
+
 static int UploadModel(Model* m, std::string& error)
 {
 	Context* c = m->context;
 	TG_CUDA(cudaSetDevice(c->device));
+	TG_CUDA(cudaStreamSynchronize(StreamOf(c)));
+	FreeModelTables(m);
 	int rc;
 	if ((rc = UploadVector(c, m->flat.nodes, &m->d_nodes, m->device_bytes, error)) != TG_OK) return rc;
 	if ((rc = UploadVector(c, m->flat.interp, &m->d_interp, m->device_bytes, error)) != TG_OK) return rc;
@@ -1207,10 +1225,22 @@ Model* Model::Create(Context* context, const Tree& tree, float target_size, int 
 Model::~Model()
 {
 	if (context) cudaSetDevice(context->device);
-	cudaFree(d_nodes);
-	cudaFree(d_interp);
-	cudaFree(d_tree);
-	cudaFree(d_materials);
+	FreeModelTables(this);
+}
+
+int EngineUploadModel(Model* model, std::string& error)
+{
+	const auto t0 = std::chrono::steady_clock::now();
+	const int rc = UploadModel(model, error);
+	model->upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	return rc;
+}
+
+int EngineSynchronize(Context* ctx, std::string& error)
+{
+	TG_CUDA(cudaSetDevice(ctx->device));
+	TG_CUDA(cudaStreamSynchronize(StreamOf(ctx)));
+	return TG_OK;
 }
 
 static DeviceModel MakeDeviceModel(const Model* m)
@@ -1380,64 +1410,20 @@ static int FinishAttributes(Model* model, Scratch& scratch, MeshResultDevice* re
 	return TG_OK;
 }
 
-int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options& options, tg_mesh* out, std::string& error)
+// K0 driver: hierarchical culling from 64-cell bricks down to the list of 8-cell bricks that must be evaluated
+// (plus, for slab runs, the halo bricks of the layer below).  Leaves the list in *out_list, its length in *out_count.
+static int BuildActiveList(Model* model, cudaStream_t stream, Scratch& scratch, const DeviceGrid& grid, uint32_t k_begin, uint32_t k_end,
+	bool has_halo, bool no_cull, unsigned long long* counters, uint32_t** out_list, uint64_t* out_count, uint64_t& launches, std::string& error)
 {
-	std::memset(out, 0, sizeof(*out));
-	Context* ctx = model->context;
-	TG_CUDA(cudaSetDevice(ctx->device));
-	cudaStream_t stream = StreamOf(ctx);
-	DeviceGrid grid;
-	if (!MakeDeviceGrid(grid_in, grid, error)) return TG_ERR_INVALID;
-
-	uint32_t k_begin = 0, k_end = grid.sz;
-	if (options.slab_begin != 0 || options.slab_end != 0)
-	{
-		k_begin = uint32_t(options.slab_begin);
-		k_end = uint32_t(std::min<uint64_t>(options.slab_end, grid.sz));
-		if (k_begin >= k_end || (k_begin % kBrick) != 0 || (k_end % kBrick != 0 && k_end != grid.sz))
-		{
-			error = "slab bounds must be multiples of 8 cell layers (or end at the grid top) and non-empty";
-			return TG_ERR_INVALID;
-		}
-	}
-	const bool has_halo = k_begin > 0;
-	const uint32_t k_base = has_halo ? k_begin - 1 : k_begin;
-	const uint32_t layers = k_end - k_base;
-	const uint32_t row_words = (grid.sx + 63) / 64;
-	const size_t bitmap_words = size_t(layers) * grid.sy * row_words;
 	const uint32_t nbx = (grid.sx + kBrick - 1) / kBrick, nby = (grid.sy + kBrick - 1) / kBrick;
 	const uint32_t bz_begin = k_begin / kBrick, bz_end = (k_end + kBrick - 1) / kBrick;
 	const size_t own_bricks = size_t(nbx) * nby * (bz_end - bz_begin);
 	const size_t halo_bricks = has_halo ? size_t(nbx) * nby : 0;
 	const size_t list_capacity = own_bricks + halo_bricks + 8;
-
-	ctx->stage.store(1);
-	ctx->progress_done[0] = 0;
-	ctx->progress_total[0] = own_bricks;
-	if (ctx->Cancelled()) return TG_ERR_CANCELLED;
-
-	Scratch scratch(stream);
-	StageTimer timer(stream);
-	uint64_t launches = 0;
-	tg_mesh_timings& tm = out->timings;
-	tm.bricks_total = own_bricks;
-
-	unsigned long long* counters = nullptr;
 	uint32_t *list_a = nullptr, *list_b = nullptr, *active_list = nullptr;
-	unsigned long long* bitmap = nullptr;
-	uint32_t* prefix = nullptr;
-	TG_CUDA(scratch.Alloc(&counters, kCntCount));
 	TG_CUDA(scratch.Alloc(&list_a, list_capacity));
 	TG_CUDA(scratch.Alloc(&list_b, list_capacity));
 	TG_CUDA(scratch.Alloc(&active_list, list_capacity));
-	TG_CUDA(scratch.Alloc(&bitmap, bitmap_words));
-	TG_CUDA(scratch.Alloc(&prefix, bitmap_words));
-	TG_CUDA(cudaMemsetAsync(counters, 0, kCntCount * 8, stream));
-	TG_CUDA(cudaMemsetAsync(bitmap, 0, bitmap_words * 8, stream));
-	const int t_start = timer.Mark();
-
-	// ---- K0: active brick list -------------------------------------------------------------------
-	const bool no_cull = (options.flags & TG_MESH_NO_CULL) != 0;
 	unsigned long long host_counts[kCntCount];
 	CullParams cp;
 	cp.model = MakeDeviceModel(model);
@@ -1498,6 +1484,73 @@ int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options
 		active_count = std::min<unsigned long long>(host_counts[0], list_capacity);
 	}
 	TG_CUDA(cudaGetLastError());
+	*out_list = active_list;
+	*out_count = active_count;
+	return TG_OK;
+}
+
+int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options& options, tg_mesh* out, std::string& error)
+{
+	std::memset(out, 0, sizeof(*out));
+	Context* ctx = model->context;
+	TG_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t stream = StreamOf(ctx);
+	DeviceGrid grid;
+	if (!MakeDeviceGrid(grid_in, grid, error)) return TG_ERR_INVALID;
+
+	uint32_t k_begin = 0, k_end = grid.sz;
+	if (options.slab_begin != 0 || options.slab_end != 0)
+	{
+		k_begin = uint32_t(options.slab_begin);
+		k_end = uint32_t(std::min<uint64_t>(options.slab_end, grid.sz));
+		if (k_begin >= k_end || (k_begin % kBrick) != 0 || (k_end % kBrick != 0 && k_end != grid.sz))
+		{
+			error = "slab bounds must be multiples of 8 cell layers (or end at the grid top) and non-empty";
+			return TG_ERR_INVALID;
+		}
+	}
+	const bool has_halo = k_begin > 0;
+	const uint32_t k_base = has_halo ? k_begin - 1 : k_begin;
+	const uint32_t layers = k_end - k_base;
+	const uint32_t row_words = (grid.sx + 63) / 64;
+	const size_t bitmap_words = size_t(layers) * grid.sy * row_words;
+	const uint32_t nbx = (grid.sx + kBrick - 1) / kBrick, nby = (grid.sy + kBrick - 1) / kBrick;
+	const uint32_t bz_begin = k_begin / kBrick, bz_end = (k_end + kBrick - 1) / kBrick;
+	const size_t own_bricks = size_t(nbx) * nby * (bz_end - bz_begin);
+	const size_t halo_bricks = has_halo ? size_t(nbx) * nby : 0;
+	const size_t list_capacity = own_bricks + halo_bricks + 8;
+
+	ctx->stage.store(1);
+	ctx->progress_done[0] = 0;
+	ctx->progress_total[0] = own_bricks;
+	if (ctx->Cancelled()) return TG_ERR_CANCELLED;
+
+	Scratch scratch(stream);
+	StageTimer timer(stream);
+	uint64_t launches = 0;
+	tg_mesh_timings& tm = out->timings;
+	tm.bricks_total = own_bricks;
+
+	unsigned long long* counters = nullptr;
+	uint32_t* active_list = nullptr;
+	unsigned long long* bitmap = nullptr;
+	uint32_t* prefix = nullptr;
+	TG_CUDA(scratch.Alloc(&counters, kCntCount));
+	TG_CUDA(scratch.Alloc(&bitmap, bitmap_words));
+	TG_CUDA(scratch.Alloc(&prefix, bitmap_words));
+	TG_CUDA(cudaMemsetAsync(counters, 0, kCntCount * 8, stream));
+	TG_CUDA(cudaMemsetAsync(bitmap, 0, bitmap_words * 8, stream));
+	const int t_start = timer.Mark();
+
+	// ---- K0: active brick list -------------------------------------------------------------------
+	const bool no_cull = (options.flags & TG_MESH_NO_CULL) != 0;
+	unsigned long long host_counts[kCntCount];
+	uint64_t active_count = 0;
+	{
+		const int rc0 = BuildActiveList(model, stream, scratch, grid, k_begin, k_end, has_halo, no_cull, counters, &active_list, &active_count, launches, error);
+		if (rc0 != TG_OK) return rc0;
+	}
+	TG_CUDA(cudaGetLastError());
 	const int t_cull = timer.Mark();
 	tm.bricks_evaluated = active_count;
 	ctx->progress_done[0] = own_bricks / 2;
@@ -1505,7 +1558,7 @@ int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options
 
 	// ---- K1 + K2: evaluate bricks, classify, extract vertices ------------------------------------
 	MeshParams mp;
-	mp.model = cp.model;
+	mp.model = MakeDeviceModel(model);
 	mp.grid = grid;
 	mp.bricks = active_list;
 	mp.brick_count = uint32_t(active_count);
@@ -1630,7 +1683,7 @@ int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options
 				return TG_ERR_UNSUPPORTED;
 			}
 			const uint32_t tris = uint32_t(quad_total * 2);
-			FaceNormalsKernel<<<(tris + 127) / 128, 128, 0, stream>>>(cp.model, result->d_positions, result->d_triangles, tris, 1.0f, result->d_face_normals);
+			FaceNormalsKernel<<<(tris + 127) / 128, 128, 0, stream>>>(MakeDeviceModel(model), result->d_positions, result->d_triangles, tris, 1.0f, result->d_face_normals);
 			launches++;
 			const float scale = options.scale == 0.0f ? 1.0f : options.scale;
 			if (scale != 1.0f)
@@ -1683,6 +1736,38 @@ int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options
 		tm.download_ms = float(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
 	}
 	ctx->stage.store(0);
+	return TG_OK;
+}
+
+// Active 8-cell bricks per brick layer after culling: what bench.py / the multi-GPU driver balance z-slabs on.
+int EngineBrickProfile(Model* model, const tg_grid& grid_in, uint32_t* out_layers, uint32_t layer_count, std::string& error)
+{
+	Context* ctx = model->context;
+	TG_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t stream = StreamOf(ctx);
+	DeviceGrid grid;
+	if (!MakeDeviceGrid(grid_in, grid, error)) return TG_ERR_INVALID;
+	const uint32_t nbz = (grid.sz + kBrick - 1) / kBrick;
+	if (layer_count < nbz)
+	{
+		error = "brick profile needs ceil(sz / 8) entries";
+		return TG_ERR_INVALID;
+	}
+	Scratch scratch(stream);
+	unsigned long long* counters = nullptr;
+	uint32_t* layers = nullptr;
+	TG_CUDA(scratch.Alloc(&counters, kCntCount));
+	TG_CUDA(scratch.Alloc(&layers, 1024));
+	TG_CUDA(cudaMemsetAsync(counters, 0, kCntCount * 8, stream));
+	TG_CUDA(cudaMemsetAsync(layers, 0, 1024 * 4, stream));
+	uint32_t* list = nullptr;
+	uint64_t count = 0, launches = 0;
+	const int rc = BuildActiveList(model, stream, scratch, grid, 0, grid.sz, false, false, counters, &list, &count, launches, error);
+	if (rc != TG_OK) return rc;
+	if (count) BrickLayerHistogramKernel<<<uint32_t((count + 255) / 256), 256, 0, stream>>>(list, uint32_t(count), layers);
+	TG_CUDA(cudaGetLastError());
+	TG_CUDA(cudaMemcpyAsync(out_layers, layers, size_t(nbz) * 4, cudaMemcpyDeviceToHost, stream));
+	TG_CUDA(cudaStreamSynchronize(stream));
 	return TG_OK;
 }
 

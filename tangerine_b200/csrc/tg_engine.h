@@ -72,5 +72,8 @@ int EngineTimerBegin(Context* context, std::string& error);
 int EngineTimerEnd(Context* context, float* out_ms, std::string& error);
 int EngineMeasureFp32Peak(Context* context, double* out_tflops, std::string& error);
 int EngineFlushL2(Context* context, std::string& error);
+int EngineSynchronize(Context* context, std::string& error);
+int EngineUploadModel(Model* model, std::string& error);
+int EngineBrickProfile(Model* model, const tg_grid& grid, uint32_t* out_layers, uint32_t layer_count, std::string& error);
 
 } // namespace tg
