@@ -23,7 +23,7 @@ namespace tg
 struct DeviceModel
 {
 	const FlatNode* nodes;
-	const uint32_t* interp;
+	const uint4* interp;       // kStreamInterp, 16-byte quads; FlatNode::interp_offset / 4 indexes it
 	const uint32_t* tree;
 	const float* material_rgb; // 3 floats per id
 	uint32_t material_count;   // index of the trailing default-white entry
@@ -51,19 +51,222 @@ __device__ __forceinline__ uint32_t Descend(const FlatNode* __restrict__ nodes, 
 	uint32_t n = start;
 	for (;;)
 	{
-		const float4 head = __ldg(reinterpret_cast<const float4*>(&nodes[n])); // pivot.xyz, terminus bits
+		// One 64-byte node = pivot + terminus and the eight child indices: three independent 128-bit loads, one
+		// round trip per level instead of two dependent ones.
+		const float4* q = reinterpret_cast<const float4*>(&nodes[n]);
+		const float4 head = __ldg(q); // pivot.xyz, terminus bits
+		const int4 lo = __ldg(reinterpret_cast<const int4*>(q + 1));
+		const int4 hi = __ldg(reinterpret_cast<const int4*>(q + 2));
 		if (__float_as_uint(head.w) != 0u)
 		{
 			return n;
 		}
-		const int octant = (px > head.x ? 1 : 0) | (py > head.y ? 2 : 0) | (pz > head.z ? 4 : 0);
-		const int32_t child = __ldg(&nodes[n].children[octant]);
+		const int4 zsel = pz > head.z ? hi : lo;
+		const int c0 = py > head.y ? zsel.z : zsel.x;
+		const int c1 = py > head.y ? zsel.w : zsel.y;
+		const int32_t child = px > head.x ? c1 : c0;
 		if (child < 0)
 		{
 			return n; // empty octant: the reference evaluates this (larger) node's program
 		}
 		n = uint32_t(child);
 	}
+}
+
+// kStreamInterp interpreter (tg_program.h): SDFInterpreter::Eval (sdf_evaluator.cpp:1386-1605) for S points per lane.
+// Every fetch is a 128-bit load whose address does not depend on another fetch of the same instruction, and the
+// first quad of the next instruction is requested before this instruction's arithmetic starts.  The operator
+// switch sits outside the per-sample loops, so with a warp-uniform program there is one dispatch per brush.
+template <int S>
+__device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const float (&px)[S], const float (&py)[S], const float (&pz)[S], float (&result)[S])
+{
+	float acc[S];
+	float stack[kMaxStackSlots][S];
+#pragma unroll
+	for (int s = 0; s < S; ++s) acc[s] = 0.0f;
+	uint4 q = __ldg(pc);
+	for (;;)
+	{
+		const uint32_t header = q.x;
+		const uint32_t brush = header & kHdrBrushMask;
+		const uint32_t op = (header >> kHdrOpShift) & 0xFu;
+		const uint32_t slot = (header >> kHdrSlotShift) & 0xFFu;
+		const uint4* next = pc + (header >> kHdrLenShift);
+		if (brush != kBrushNone)
+		{
+			const float p0 = __uint_as_float(q.y), p1 = __uint_as_float(q.z), p2 = __uint_as_float(q.w);
+			const uint32_t xform = (header >> kHdrXformShift) & 3u;
+			float lx[S], ly[S], lz[S];
+			float scale = 1.0f, threshold = 0.0f;
+			if (xform == kXformMatrix)
+			{
+				const float4 a = __ldg(reinterpret_cast<const float4*>(pc + 1));
+				const float4 b = __ldg(reinterpret_cast<const float4*>(pc + 2));
+				const float4 c = __ldg(reinterpret_cast<const float4*>(pc + 3));
+				if (header & kHdrTailBit)
+				{
+					const float4 t = __ldg(reinterpret_cast<const float4*>(pc + 4));
+					scale = t.x;
+					threshold = t.y;
+				}
+				q = __ldg(next);
+				// glm mat4 * vec4(p, 1): (m0*x + m1*y) + (m2*z + m3*1)  (type_mat4x4.inl:561-572)
+				// columns: m0 = (a.x a.y a.z), m1 = (a.w b.x b.y), m2 = (b.z b.w c.x), m3 = (c.y c.z c.w)
+#pragma unroll
+				for (int s = 0; s < S; ++s)
+				{
+					lx[s] = (a.x * px[s] + a.w * py[s]) + (b.z * pz[s] + c.y);
+					ly[s] = (a.y * px[s] + b.x * py[s]) + (b.w * pz[s] + c.z);
+					lz[s] = (a.z * px[s] + b.y * py[s]) + (c.x * pz[s] + c.w);
+				}
+			}
+			else if (xform == kXformOffset)
+			{
+				const float4 o = __ldg(reinterpret_cast<const float4*>(pc + 1));
+				if (header & kHdrTailBit)
+				{
+					const float4 t = __ldg(reinterpret_cast<const float4*>(pc + 2));
+					scale = t.x;
+					threshold = t.y;
+				}
+				q = __ldg(next);
+#pragma unroll
+				for (int s = 0; s < S; ++s)
+				{
+					lx[s] = px[s] + o.x;
+					ly[s] = py[s] + o.y;
+					lz[s] = pz[s] + o.z;
+				}
+			}
+			else
+			{
+				if (header & kHdrTailBit)
+				{
+					const float4 t = __ldg(reinterpret_cast<const float4*>(pc + 1));
+					scale = t.x;
+					threshold = t.y;
+				}
+				q = __ldg(next);
+#pragma unroll
+				for (int s = 0; s < S; ++s)
+				{
+					lx[s] = px[s];
+					ly[s] = py[s];
+					lz[s] = pz[s];
+				}
+			}
+			pc = next;
+
+			float d[S];
+			switch (brush)
+			{
+			case kBrushSphere:
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Sphere(lx[s], ly[s], lz[s], p0);
+				break;
+			case kBrushEllipsoid:
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Ellipsoid(lx[s], ly[s], lz[s], p0, p1, p2);
+				break;
+			case kBrushBox:
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Box(lx[s], ly[s], lz[s], p0, p1, p2);
+				break;
+			case kBrushTorus:
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Torus(lx[s], ly[s], lz[s], p0, p1);
+				break;
+			case kBrushCylinder:
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Cylinder(lx[s], ly[s], lz[s], p0, p1);
+				break;
+			case kBrushCone:
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Cone(lx[s], ly[s], lz[s], p0, p1);
+				break;
+			case kBrushConinder:
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Coninder(lx[s], ly[s], lz[s], p0, p1, p2);
+				break;
+			default:
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Plane(lx[s], ly[s], lz[s], p0, p1, p2);
+				break;
+			}
+			if (header & kHdrScaleBit)
+			{
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = d[s] * scale; // ScaleField (:1587-1591)
+			}
+			switch (op)
+			{
+			case kOpPush:
+				if (slot != kNoSlot)
+				{
+#pragma unroll
+					for (int s = 0; s < S; ++s) stack[slot][s] = acc[s];
+				}
+#pragma unroll
+				for (int s = 0; s < S; ++s) acc[s] = d[s];
+				break;
+			case kOpUnion:
+#pragma unroll
+				for (int s = 0; s < S; ++s) acc[s] = sdf::Union(acc[s], d[s]);
+				break;
+			case kOpInter:
+#pragma unroll
+				for (int s = 0; s < S; ++s) acc[s] = sdf::Inter(acc[s], d[s]);
+				break;
+			case kOpDiff:
+#pragma unroll
+				for (int s = 0; s < S; ++s) acc[s] = sdf::Diff(acc[s], d[s]);
+				break;
+			case kOpBlendUnion:
+#pragma unroll
+				for (int s = 0; s < S; ++s) acc[s] = sdf::BlendUnion(acc[s], d[s], threshold);
+				break;
+			case kOpBlendInter:
+#pragma unroll
+				for (int s = 0; s < S; ++s) acc[s] = sdf::BlendInter(acc[s], d[s], threshold);
+				break;
+			default:
+#pragma unroll
+				for (int s = 0; s < S; ++s) acc[s] = sdf::BlendDiff(acc[s], d[s], threshold);
+				break;
+			}
+		}
+		else if (op == kOpStop)
+		{
+#pragma unroll
+			for (int s = 0; s < S; ++s) result[s] = acc[s];
+			return;
+		}
+		else
+		{
+			const float param = __uint_as_float(q.y);
+			q = __ldg(next);
+			pc = next;
+			if (op == kOpFlate)
+			{
+#pragma unroll
+				for (int s = 0; s < S; ++s) acc[s] = acc[s] - param; // :1567-1571
+			}
+			else
+			{
+				// stack-form set operator: lhs was spilled, rhs is the accumulator
+#pragma unroll
+				for (int s = 0; s < S; ++s) acc[s] = sdf::SetOp(op, stack[slot][s], acc[s], param);
+			}
+		}
+	}
+}
+
+__device__ __forceinline__ float EvalInterp1(const DeviceModel& model, uint32_t word_offset, float x, float y, float z)
+{
+	const float px[1] = { x }, py[1] = { y }, pz[1] = { z };
+	float out[1];
+	EvalInterp<1>(model.interp + (word_offset >> 2), px, py, pz, out);
+	return out[0];
 }
 
 template <int S>

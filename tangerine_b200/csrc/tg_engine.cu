@@ -44,12 +44,14 @@ namespace tg
 constexpr int kBrick = 8;                 // cells per brick edge
 constexpr int kTile = kBrick + 1;         // lattice samples per brick edge
 constexpr int kTileSamples = kTile * kTile * kTile; // 729
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-constexpr int kLaneSamples = 4;           // samples interpreted per lane per dispatch
-constexpr int kChunk = 32 * kLaneSamples; // samples per warp work item
-constexpr int kMaxGroups = 16;            // distinct octree nodes per brick handled by the coherent path
-constexpr int kMaxChunks = 32;
+constexpr int kTilePadded = 736;
+constexpr int kBrickWarps = 4;            // warps per block of the brick kernels; every warp works alone
+constexpr int kBrickThreads = kBrickWarps * 32;
+constexpr int kMaxGroups = 32;            // distinct octree nodes per grouping round (one table slot per lane)
+#ifndef TG_LANE_SAMPLES
+#define TG_LANE_SAMPLES 2
+#endif
+constexpr int kLaneSamples = TG_LANE_SAMPLES; // samples interpreted per lane per dispatch
 constexpr uint32_t kEmptyGroup = 0xFFFFFFFFu;
 constexpr uint32_t kHaloFlag = 1u << 30;
 constexpr int kTopLevel = 3;              // 8 << 3 = 64-cell bricks at the top of the cull hierarchy
@@ -64,7 +66,8 @@ enum Counter
 	kCntTotalVertices = 5,
 	kCntTotalQuads = 6,
 	kCntHalo = 7,
-	kCntCount = 8
+	kCntBrickCursor = 8,
+	kCntCount = 16
 };
 
 struct MeshParams
@@ -84,46 +87,41 @@ struct MeshParams
 };
 
 // ------------------------------------------------------------------------------------------------
-// K1 + K2: evaluate one brick's 9^3 lattice tile and extract its surface-nets vertices
+// K1 + K2: evaluate one brick's 9^3 lattice tile and extract its surface-nets vertices.
+// One WARP owns one brick from start to finish, so the kernel has no block-wide barrier at all: a warp that is
+// waiting on an octree or instruction fetch is covered by the other resident warps, whatever phase they are in.
 // ------------------------------------------------------------------------------------------------
 
-struct BrickShared
+struct WarpTile
 {
-	float tile[kTileSamples];
-	uint32_t node[kTileSamples];
-	uint16_t order[kTileSamples + 7];
+	float tile[kTilePadded];       // sample values; while samples are being grouped: (group << 16) | rank
+	uint16_t order[kTilePadded];   // sample indices sorted by group; later the brick's active cell list
 	uint32_t group_node[kMaxGroups];
 	uint32_t group_count[kMaxGroups];
 	uint32_t group_start[kMaxGroups];
-	uint16_t chunk_group[kMaxChunks];
-	uint16_t chunk_begin[kMaxChunks];
-	uint16_t chunk_count[kMaxChunks];
-	int chunk_total;
-	int overflow;
-	uint32_t emit_count;
-	uint32_t emit_base;
 };
 
+__device__ __forceinline__ void TileCoords(const DeviceGrid& grid, uint32_t i0, uint32_t j0, uint32_t k0, int s, float& x, float& y, float& z)
+{
+	const int lk = s / (kTile * kTile);
+	const int r = s - lk * (kTile * kTile);
+	const int lj = r / kTile, li = r - lj * kTile;
+	x = LatticeCoord(grid.x, grid.dx, i0 + li);
+	y = LatticeCoord(grid.y, grid.dy, j0 + lj);
+	z = LatticeCoord(grid.z, grid.dz, k0 + lk);
+}
+
 // Evaluates the lattice samples (li < ni, lj < nj, kmin <= lk < nk) of a tile whose corner sample has lattice
-// index (i0, j0, k0) into sh.tile.  Samples are first mapped to their octree node (SDFOctree::Descend), then
-// re-binned so that every warp work item holds up to 128 samples of ONE node, and interpreted 4 per lane.
-__device__ __forceinline__ void EvaluateTile(BrickShared& sh, const DeviceModel& model, const DeviceGrid& grid,
+// index (i0, j0, k0) into w.tile.  Samples are first mapped to their octree node (SDFOctree::Descend), then
+// sorted by node so that every dispatch of the interpreter runs ONE program for the whole warp, kLaneSamples
+// samples per lane.  There is exactly one instantiation of the interpreter in the kernel (instruction-cache
+// footprint: every resident warp is in a different phase); a brick that straddles more than kMaxGroups nodes
+// repeats the group / evaluate round on the samples that did not get a table slot.
+__device__ __forceinline__ void EvaluateTile(WarpTile& w, const DeviceModel& model, const DeviceGrid& grid,
 	uint32_t i0, uint32_t j0, uint32_t k0, int ni, int nj, int nk, int kmin, unsigned long long* counters)
 {
-	const int tid = threadIdx.x;
-	const int lane = tid & 31;
-	const int warp = tid >> 5;
-
-	if (tid < kMaxGroups)
-	{
-		sh.group_node[tid] = kEmptyGroup;
-		sh.group_count[tid] = 0;
-	}
-	if (tid == 0)
-	{
-		sh.overflow = 0;
-		sh.chunk_total = 0;
-	}
+	const int lane = threadIdx.x & 31;
+	constexpr int kRounds = (kTileSamples + 31) / 32;
 
 	// Brick-level descent: follow the octree while the whole tile lies in one octant.
 	uint32_t start = 0;
@@ -142,227 +140,242 @@ __device__ __forceinline__ void EvaluateTile(BrickShared& sh, const DeviceModel&
 			start = uint32_t(child);
 		}
 	}
-	__syncthreads();
 
-	// Per-sample descent + warp-aggregated insertion into the brick's node table.
-	uint32_t my_group[3];
-	uint32_t my_rank[3];
-#pragma unroll
-	for (int it = 0; it < 3; ++it)
+	// bit r of `pending`: sample 32 r + lane still has to be evaluated
+	uint32_t pending = 0;
+	for (int r = 0; r < kRounds; ++r)
 	{
-		const int s = tid + it * kThreads;
-		my_group[it] = kEmptyGroup;
-		my_rank[it] = 0;
-		uint32_t node = kEmptyGroup;
+		const int s = r * 32 + lane;
 		if (s < kTileSamples)
 		{
-			const int li = s % kTile, lj = (s / kTile) % kTile, lk = s / (kTile * kTile);
-			if (li < ni && lj < nj && lk < nk && lk >= kmin)
-			{
-				node = Descend(model.nodes, start, LatticeCoord(grid.x, grid.dx, i0 + li), LatticeCoord(grid.y, grid.dy, j0 + lj), LatticeCoord(grid.z, grid.dz, k0 + lk));
-			}
-			sh.node[s] = node;
+			const int lk = s / (kTile * kTile);
+			const int rem = s - lk * (kTile * kTile);
+			const int lj = rem / kTile, li = rem - lj * kTile;
+			if (li < ni && lj < nj && lk < nk && lk >= kmin) pending |= 1u << r;
 		}
-		const unsigned peers = __match_any_sync(0xFFFFFFFFu, node);
-		if (node != kEmptyGroup)
+	}
+
+	while (__any_sync(0xFFFFFFFFu, pending != 0u))
+	{
+		w.group_node[lane] = kEmptyGroup;
+		w.group_count[lane] = 0;
+		__syncwarp();
+
+		// Pass 1: per-sample descent, warp-aggregated insertion into the brick's node table (open addressing).
+		uint32_t assigned = 0;
+		for (int r = 0; r < kRounds; ++r)
 		{
-			const int leader = __ffs(peers) - 1;
-			uint32_t group = kEmptyGroup, base = 0;
-			if (lane == leader)
+			const bool mine = (pending >> r) & 1u;
+			if (!__any_sync(0xFFFFFFFFu, mine)) continue;
+			const int s = r * 32 + lane;
+			uint32_t node = kEmptyGroup;
+			if (mine)
 			{
-				for (int g = 0; g < kMaxGroups; ++g)
+				float x, y, z;
+				TileCoords(grid, i0, j0, k0, s, x, y, z);
+				node = Descend(model.nodes, start, x, y, z);
+			}
+			const unsigned peers = __match_any_sync(0xFFFFFFFFu, node);
+			if (mine)
+			{
+				const int leader = __ffs(peers) - 1;
+				uint32_t group = kEmptyGroup, rank0 = 0;
+				if (lane == leader)
 				{
-					uint32_t seen = sh.group_node[g];
-					if (seen == kEmptyGroup)
+					uint32_t g = (node * 0x9E3779B1u) >> 27;
+					for (int probe = 0; probe < kMaxGroups; ++probe, g = (g + 1) & (kMaxGroups - 1))
 					{
-						seen = atomicCAS(&sh.group_node[g], kEmptyGroup, node);
-						if (seen == kEmptyGroup) seen = node;
-					}
-					if (seen == node)
-					{
-						group = uint32_t(g);
-						base = atomicAdd(&sh.group_count[g], uint32_t(__popc(peers)));
-						break;
+						uint32_t seen = w.group_node[g];
+						if (seen == kEmptyGroup)
+						{
+							seen = atomicCAS(&w.group_node[g], kEmptyGroup, node); // other leaders of this warp race for the slot
+							if (seen == kEmptyGroup) seen = node;
+						}
+						if (seen == node)
+						{
+							group = g;
+							rank0 = atomicAdd(&w.group_count[g], uint32_t(__popc(peers)));
+							break;
+						}
 					}
 				}
-				if (group == kEmptyGroup) sh.overflow = 1;
-			}
-			group = __shfl_sync(peers, group, leader);
-			base = __shfl_sync(peers, base, leader);
-			my_group[it] = group;
-			my_rank[it] = base + uint32_t(__popc(peers & ((1u << lane) - 1u)));
-		}
-	}
-	__syncthreads();
-
-	const bool overflow = sh.overflow != 0;
-	if (!overflow)
-	{
-		if (warp == 0)
-		{
-			// Lane g owns group g: exclusive scans give each group its slice of `order` and of the chunk list.
-			const uint32_t count = lane < kMaxGroups ? sh.group_count[lane] : 0u;
-			const uint32_t chunks = (count + kChunk - 1) / kChunk;
-			uint32_t count_incl = count, chunk_incl = chunks;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1)
-			{
-				const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, count_incl, o);
-				const uint32_t b = __shfl_up_sync(0xFFFFFFFFu, chunk_incl, o);
-				if (lane >= o)
+				group = __shfl_sync(peers, group, leader);
+				rank0 = __shfl_sync(peers, rank0, leader);
+				if (group != kEmptyGroup) // else the table is full: the sample waits for the next round
 				{
-					count_incl += a;
-					chunk_incl += b;
+					w.tile[s] = __uint_as_float((group << 16) | (rank0 + uint32_t(__popc(peers & ((1u << lane) - 1u)))));
+					assigned |= 1u << r;
 				}
 			}
-			const uint32_t start = count_incl - count;
-			if (lane < kMaxGroups) sh.group_start[lane] = start;
-			for (uint32_t b = 0; b < chunks; ++b)
-			{
-				const uint32_t c = chunk_incl - chunks + b;
-				sh.chunk_group[c] = uint16_t(lane);
-				sh.chunk_begin[c] = uint16_t(start + b * kChunk);
-				sh.chunk_count[c] = uint16_t(min(uint32_t(kChunk), count - b * kChunk));
-			}
-			const uint32_t flops = count ? count * __ldg(&model.nodes[sh.group_node[lane]].flops) : 0u;
-			const uint32_t flops_total = __reduce_add_sync(0xFFFFFFFFu, flops);
-			if (lane == 31)
-			{
-				sh.chunk_total = int(chunk_incl);
-				atomicAdd(&counters[kCntSamples], (unsigned long long)count_incl);
-				atomicAdd(&counters[kCntFlops], (unsigned long long)flops_total);
-			}
 		}
-		__syncthreads();
-#pragma unroll
-		for (int it = 0; it < 3; ++it)
-		{
-			if (my_group[it] != kEmptyGroup)
-			{
-				sh.order[sh.group_start[my_group[it]] + my_rank[it]] = uint16_t(tid + it * kThreads);
-			}
-		}
-		__syncthreads();
+		__syncwarp();
 
-		const int chunk_total = sh.chunk_total;
-		for (int c = warp; c < chunk_total; c += kWarps)
+		// Lane g owns group g: an exclusive scan gives each group its slice of `order`.
+		const uint32_t count = w.group_count[lane];
+		uint32_t incl = count;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
 		{
-			const int begin = sh.chunk_begin[c];
-			const int count = sh.chunk_count[c];
-			const uint32_t node = sh.group_node[sh.chunk_group[c]];
-			const uint32_t* program = model.interp + __ldg(&model.nodes[node].interp_offset);
-			float px[kLaneSamples], py[kLaneSamples], pz[kLaneSamples], d[kLaneSamples];
-			int sample[kLaneSamples];
-#pragma unroll
-			for (int q = 0; q < kLaneSamples; ++q)
+			const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+			if (lane >= o) incl += a;
+		}
+		w.group_start[lane] = incl - count;
+		const uint32_t flops = count ? count * __ldg(&model.nodes[w.group_node[lane]].flops) : 0u;
+		const uint32_t flops_total = __reduce_add_sync(0xFFFFFFFFu, flops);
+		if (lane == 31)
+		{
+			atomicAdd(&counters[kCntSamples], (unsigned long long)incl);
+			atomicAdd(&counters[kCntFlops], (unsigned long long)flops_total);
+		}
+		unsigned live = __ballot_sync(0xFFFFFFFFu, count != 0u);
+		__syncwarp();
+
+		// Pass 2: sample indices sorted by group.
+		for (int r = 0; r < kRounds; ++r)
+		{
+			if ((assigned >> r) & 1u)
 			{
-				const int idx = lane + 32 * q;
-				const int s = sh.order[begin + (idx < count ? idx : 0)];
-				sample[q] = idx < count ? s : -1;
-				const int li = s % kTile, lj = (s / kTile) % kTile, lk = s / (kTile * kTile);
-				px[q] = LatticeCoord(grid.x, grid.dx, i0 + li);
-				py[q] = LatticeCoord(grid.y, grid.dy, j0 + lj);
-				pz[q] = LatticeCoord(grid.z, grid.dz, k0 + lk);
-			}
-			EvalDistance<kLaneSamples>(program, px, py, pz, d);
-#pragma unroll
-			for (int q = 0; q < kLaneSamples; ++q)
-			{
-				if (sample[q] >= 0) sh.tile[sample[q]] = d[q];
+				const int s = r * 32 + lane;
+				const uint32_t code = __float_as_uint(w.tile[s]);
+				w.order[w.group_start[code >> 16] + (code & 0xFFFFu)] = uint16_t(s);
 			}
 		}
-	}
-	else
-	{
-		// More distinct nodes than the table holds (tiny leaves vs. a coarse grid): per-lane programs.
-		unsigned long long flops = 0, samples = 0;
-		for (int s = tid; s < kTileSamples; s += kThreads)
+		pending &= ~assigned;
+		__syncwarp();
+
+		// Evaluation: one program at a time, 32 * kLaneSamples samples per dispatch.
+		while (live)
 		{
-			const uint32_t node = sh.node[s];
-			if (node == kEmptyGroup) continue;
-			const int li = s % kTile, lj = (s / kTile) % kTile, lk = s / (kTile * kTile);
-			sh.tile[s] = EvalDistance1(model.interp + model.nodes[node].interp_offset,
-				LatticeCoord(grid.x, grid.dx, i0 + li), LatticeCoord(grid.y, grid.dy, j0 + lj), LatticeCoord(grid.z, grid.dz, k0 + lk));
-			flops += model.nodes[node].flops;
-			samples++;
+			const int g = __ffs(live) - 1;
+			live &= live - 1;
+			const int total = int(w.group_count[g]);
+			const int first = int(w.group_start[g]);
+			const uint4* program = model.interp + (__ldg(&model.nodes[w.group_node[g]].interp_offset) >> 2);
+			for (int done = 0; done < total; done += 32 * kLaneSamples)
+			{
+				const int count_here = min(total - done, 32 * kLaneSamples);
+				float px[kLaneSamples], py[kLaneSamples], pz[kLaneSamples], d[kLaneSamples];
+				int sample[kLaneSamples];
+#pragma unroll
+				for (int q = 0; q < kLaneSamples; ++q)
+				{
+					const int idx = lane + 32 * q;
+					const int s = w.order[first + done + (idx < count_here ? idx : 0)];
+					sample[q] = idx < count_here ? s : -1;
+					TileCoords(grid, i0, j0, k0, s, px[q], py[q], pz[q]);
+				}
+				EvalInterp<kLaneSamples>(program, px, py, pz, d);
+#pragma unroll
+				for (int q = 0; q < kLaneSamples; ++q)
+				{
+					if (sample[q] >= 0) w.tile[sample[q]] = d[q];
+				}
+			}
 		}
-		atomicAdd(&counters[kCntSamples], samples);
-		atomicAdd(&counters[kCntFlops], flops);
+		__syncwarp();
 	}
-	__syncthreads();
 }
 
-__global__ void __launch_bounds__(kThreads) MeshBricksKernel(const MeshParams p)
+// Loads the eight corner samples of cell c (0..511) of the brick in the reference's corner numbering
+// (get_voxel_corner_grid_positions, surface_nets.cpp:632-646) and returns the `>= 0` mask.
+__device__ __forceinline__ unsigned CellCorners(const WarpTile& w, int c, float (&v)[8])
 {
-	__shared__ BrickShared sh;
+	const int ci = c & 7, cj = (c >> 3) & 7, ck = c >> 6;
+	const float* t = w.tile + (ck * kTile + cj) * kTile + ci;
+	v[0] = t[0];
+	v[1] = t[1];
+	v[2] = t[kTile + 1];
+	v[3] = t[kTile];
+	v[4] = t[kTile * kTile];
+	v[5] = t[kTile * kTile + 1];
+	v[6] = t[kTile * kTile + kTile + 1];
+	v[7] = t[kTile * kTile + kTile];
+	// is_scalar_positive is `scalar >= isovalue` (:733-735): -0.0 is positive, NaN is negative
+	unsigned signs = 0;
+#pragma unroll
+	for (int k = 0; k < 8; ++k) signs |= (v[k] >= 0.0f ? 1u : 0u) << k;
+	return signs;
+}
+
+__global__ void __launch_bounds__(kBrickThreads) MeshBricksKernel(const MeshParams p)
+{
+	__shared__ WarpTile tiles[kBrickWarps];
+	WarpTile& w = tiles[threadIdx.x >> 5];
 	const DeviceGrid& grid = p.grid;
-	const int tid = threadIdx.x;
-	const int lane = tid & 31;
+	const int lane = threadIdx.x & 31;
 
-	const uint32_t brick = p.bricks[blockIdx.x];
-	const uint32_t bx = brick & 1023u, by = (brick >> 10) & 1023u, bz = (brick >> 20) & 1023u;
-	const bool halo = (brick & kHaloFlag) != 0;
-	const uint32_t i0 = bx * kBrick, j0 = by * kBrick, k0 = bz * kBrick;
-	const int ni = int(min(uint32_t(kTile), grid.sx + 1 - i0));
-	const int nj = int(min(uint32_t(kTile), grid.sy + 1 - j0));
-	const int nk = int(min(uint32_t(kTile), grid.sz + 1 - k0));
-	const int kmin = halo ? kBrick - 1 : 0; // halo bricks only need their top cell layer
-
-	if (tid == 0) sh.emit_count = 0;
-	EvaluateTile(sh, p.model, grid, i0, j0, k0, ni, nj, nk, kmin, p.counters);
-
-	// Classification + vertex extraction: FirstLoopInnerThunk (surface_nets.cpp:864-974)
 	const float bbminx = grid.x, bbminy = grid.y, bbminz = grid.z;
 	const float bbmaxx = __fadd_rn(grid.x, __fmul_rn(float(grid.sx), grid.dx));
 	const float bbmaxy = __fadd_rn(grid.y, __fmul_rn(float(grid.sy), grid.dy));
 	const float bbmaxz = __fadd_rn(grid.z, __fmul_rn(float(grid.sz), grid.dz));
 	unsigned char* bitmap_bytes = reinterpret_cast<unsigned char*>(p.bitmap);
 
-	float4 rec_pos[2];
-	unsigned long long rec_key[2];
-	uint32_t rec_slot[2];
-#pragma unroll
-	for (int it = 0; it < 2; ++it)
+	for (;;)
 	{
-		const int c = tid + it * kThreads;
-		const int ci = c & 7, cj = (c >> 3) & 7, ck = c >> 6;
-		const uint32_t gi = i0 + ci, gj = j0 + cj, gk = k0 + ck;
-		const bool in_grid = gi < grid.sx && gj < grid.sy && gk < grid.sz && ck >= kmin;
-		bool active = false;
-		float v[8];
-		if (in_grid)
+		// persistent warps pull bricks from one device-wide cursor
+		uint32_t item = 0;
+		if (lane == 0) item = uint32_t(atomicAdd(&p.counters[kCntBrickCursor], 1ull));
+		item = __shfl_sync(0xFFFFFFFFu, item, 0);
+		if (item >= p.brick_count) break;
+
+		const uint32_t brick = __ldg(&p.bricks[item]);
+		const uint32_t bx = brick & 1023u, by = (brick >> 10) & 1023u, bz = (brick >> 20) & 1023u;
+		const bool halo = (brick & kHaloFlag) != 0;
+		const uint32_t i0 = bx * kBrick, j0 = by * kBrick, k0 = bz * kBrick;
+		const int ni = int(min(uint32_t(kTile), grid.sx + 1 - i0));
+		const int nj = int(min(uint32_t(kTile), grid.sy + 1 - j0));
+		const int nk = int(min(uint32_t(kTile), grid.sz + 1 - k0));
+		const int kmin = halo ? kBrick - 1 : 0; // halo bricks only need their top cell layer
+
+		EvaluateTile(w, p.model, grid, i0, j0, k0, ni, nj, nk, kmin, p.counters);
+
+		// Classification: sign bits of FirstLoopInnerThunk (surface_nets.cpp:864-907); active cells go to the
+		// bitmap (one byte per 8-cell row) and, when this slab owns them, to the brick's cell list.
+		int emit_total = 0;
+		for (int base = 0; base < kBrick * kBrick * kBrick; base += 32)
 		{
-			const float* t = sh.tile + (ck * kTile + cj) * kTile + ci;
-			// corner numbering of get_voxel_corner_grid_positions (surface_nets.cpp:632-646)
-			v[0] = t[0];
-			v[1] = t[1];
-			v[2] = t[kTile + 1];
-			v[3] = t[kTile];
-			v[4] = t[kTile * kTile];
-			v[5] = t[kTile * kTile + 1];
-			v[6] = t[kTile * kTile + kTile + 1];
-			v[7] = t[kTile * kTile + kTile];
-			// is_scalar_positive is `scalar >= isovalue` (:733-735): -0.0 is positive, NaN is negative
-			unsigned signs = 0;
-#pragma unroll
-			for (int k = 0; k < 8; ++k) signs |= (v[k] >= 0.0f ? 1u : 0u) << k;
-			active = signs != 0u && signs != 0xFFu;
-		}
-		const unsigned ballot = __ballot_sync(0xFFFFFFFFu, active);
-		// Each warp covers 4 rows of 8 cells: lanes 0, 8, 16, 24 publish their row's byte.
-		if ((lane & 7) == 0)
-		{
-			const unsigned byte = (ballot >> lane) & 0xFFu;
-			const bool layer_ok = gk >= p.k_base && gk < p.k_own_end && gj < grid.sy && ck >= kmin;
-			if (byte != 0u && layer_ok)
+			const int c = base + lane;
+			const int ci = c & 7, cj = (c >> 3) & 7, ck = c >> 6;
+			const uint32_t gi = i0 + ci, gj = j0 + cj, gk = k0 + ck;
+			const bool in_grid = gi < grid.sx && gj < grid.sy && gk < grid.sz && ck >= kmin;
+			bool active = false;
+			if (in_grid)
 			{
-				bitmap_bytes[(size_t(gk - p.k_base) * grid.sy + gj) * (size_t(p.row_words) * 8u) + bx] = (unsigned char)byte;
+				float v[8];
+				const unsigned signs = CellCorners(w, c, v);
+				active = signs != 0u && signs != 0xFFu;
 			}
+			const unsigned ballot = __ballot_sync(0xFFFFFFFFu, active);
+			// a warp pass covers 4 rows of 8 cells: lanes 0, 8, 16, 24 publish their row's byte
+			if ((lane & 7) == 0)
+			{
+				const unsigned byte = (ballot >> lane) & 0xFFu;
+				const bool layer_ok = gk >= p.k_base && gk < p.k_own_end && gj < grid.sy && ck >= kmin;
+				if (byte != 0u && layer_ok)
+				{
+					bitmap_bytes[(size_t(gk - p.k_base) * grid.sy + gj) * (size_t(p.row_words) * 8u) + bx] = (unsigned char)byte;
+				}
+			}
+			const bool emit = active && !halo && gk >= p.k_own_begin && gk < p.k_own_end;
+			const unsigned emit_ballot = __ballot_sync(0xFFFFFFFFu, emit);
+			if (emit) w.order[emit_total + __popc(emit_ballot & ((1u << lane) - 1u))] = uint16_t(c);
+			emit_total += __popc(emit_ballot);
 		}
-		rec_slot[it] = 0xFFFFFFFFu;
-		const bool emit = active && !halo && gk >= p.k_own_begin && gk < p.k_own_end;
-		if (emit)
+		__syncwarp();
+		if (emit_total == 0) continue;
+
+		uint32_t out_base = 0;
+		if (lane == 0) out_base = uint32_t(atomicAdd(&p.counters[kCntTmpVertices], (unsigned long long)emit_total));
+		out_base = __shfl_sync(0xFFFFFFFFu, out_base, 0);
+
+		// Vertices of the active cells, densely packed over the lanes: :920-965
+		for (int e = lane; e < emit_total; e += 32)
 		{
+			const int c = w.order[e];
+			const int ci = c & 7, cj = (c >> 3) & 7, ck = c >> 6;
+			const uint32_t gi = i0 + ci, gj = j0 + cj, gk = k0 + ck;
+			float v[8];
+			CellCorners(w, c, v);
 			const float fi = float(gi), fj = float(gj), fk = float(gk);
 			const float gx[8] = { fi, fi + 1.f, fi + 1.f, fi, fi, fi + 1.f, fi + 1.f, fi };
 			const float gy[8] = { fj, fj, fj + 1.f, fj + 1.f, fj, fj, fj + 1.f, fj + 1.f };
@@ -372,15 +385,15 @@ __global__ void __launch_bounds__(kThreads) MeshBricksKernel(const MeshParams p)
 			float sx = 0.f, sy = 0.f, sz = 0.f;
 			int n = 0;
 #pragma unroll
-			for (int e = 0; e < 12; ++e)
+			for (int ed = 0; ed < 12; ++ed)
 			{
-				const float s1 = v[e0[e]], s2 = v[e1[e]];
+				const float s1 = v[e0[ed]], s2 = v[e1[ed]];
 				if ((s1 >= 0.0f) != (s2 >= 0.0f))
 				{
 					const float t = (0.0f - s1) / (s2 - s1); // :937
-					sx = sx + (gx[e0[e]] + t * (gx[e1[e]] - gx[e0[e]]));
-					sy = sy + (gy[e0[e]] + t * (gy[e1[e]] - gy[e0[e]]));
-					sz = sz + (gz[e0[e]] + t * (gz[e1[e]] - gz[e0[e]]));
+					sx = sx + (gx[e0[ed]] + t * (gx[e1[ed]] - gx[e0[ed]]));
+					sy = sy + (gy[e0[ed]] + t * (gy[e1[ed]] - gy[e0[ed]]));
+					sz = sz + (gz[e0[ed]] + t * (gz[e1[ed]] - gz[e0[ed]]));
 					n++;
 				}
 			}
@@ -392,54 +405,38 @@ __global__ void __launch_bounds__(kThreads) MeshBricksKernel(const MeshParams p)
 			const float pz = bbminz + (bbmaxz - bbminz) * (cz - 0.f) / (float(grid.sz) - 0.f);
 			// winding bits for SecondLoopThunk (:1041-1067, :1103-1105): edge (0,4), (3,0), (0,1)
 			const uint32_t orient = (v[4] > v[0] ? 1u : 0u) | (v[0] > v[3] ? 2u : 0u) | (v[1] > v[0] ? 4u : 0u);
-			rec_pos[it] = make_float4(px, py, pz, __uint_as_float(orient));
-			rec_key[it] = ((unsigned long long)(gk - p.k_base) * grid.sy + gj) * ((unsigned long long)p.row_words * 64ull) + gi;
-		}
-		const unsigned emit_ballot = __ballot_sync(0xFFFFFFFFu, emit);
-		uint32_t warp_base = 0;
-		if (lane == 0 && emit_ballot) warp_base = atomicAdd(&sh.emit_count, uint32_t(__popc(emit_ballot)));
-		warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 0);
-		if (emit) rec_slot[it] = warp_base + uint32_t(__popc(emit_ballot & ((1u << lane) - 1u)));
-	}
-	__syncthreads();
-	if (tid == 0)
-	{
-		sh.emit_base = sh.emit_count ? uint32_t(atomicAdd(&p.counters[kCntTmpVertices], (unsigned long long)sh.emit_count)) : 0u;
-	}
-	__syncthreads();
-	const uint32_t base = sh.emit_base;
-#pragma unroll
-	for (int it = 0; it < 2; ++it)
-	{
-		if (rec_slot[it] != 0xFFFFFFFFu)
-		{
-			const uint32_t dst = base + rec_slot[it];
+			const uint32_t dst = out_base + uint32_t(e);
 			if (dst < p.tmp_capacity)
 			{
-				p.tmp_pos[dst] = rec_pos[it];
-				p.tmp_key[dst] = rec_key[it];
+				p.tmp_pos[dst] = make_float4(px, py, pz, __uint_as_float(orient));
+				p.tmp_key[dst] = ((unsigned long long)(gk - p.k_base) * grid.sy + gj) * ((unsigned long long)p.row_words * 64ull) + gi;
 			}
 		}
+		__syncwarp();
 	}
 }
 
-// Dense lattice dump: one 8^3 tile of samples per block, written to a (sz+1, sy+1, sx+1) array.
-__global__ void __launch_bounds__(kThreads) LatticeKernel(const DeviceModel model, const DeviceGrid grid, float* __restrict__ out,
-	uint32_t tiles_x, uint32_t tiles_y, unsigned long long* counters)
+// Dense lattice dump: one 8^3 tile of samples per warp, written to a (sz+1, sy+1, sx+1) array.
+__global__ void __launch_bounds__(kBrickThreads) LatticeKernel(const DeviceModel model, const DeviceGrid grid, float* __restrict__ out,
+	uint32_t tiles_x, uint32_t tiles_y, uint32_t tile_count, unsigned long long* counters)
 {
-	__shared__ BrickShared sh;
-	const uint32_t tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y, tz = blockIdx.x / (tiles_x * tiles_y);
+	__shared__ WarpTile tiles[kBrickWarps];
+	WarpTile& w = tiles[threadIdx.x >> 5];
+	const int lane = threadIdx.x & 31;
+	const uint32_t tile = blockIdx.x * kBrickWarps + (threadIdx.x >> 5);
+	if (tile >= tile_count) return;
+	const uint32_t tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, tz = tile / (tiles_x * tiles_y);
 	const uint32_t i0 = tx * kBrick, j0 = ty * kBrick, k0 = tz * kBrick;
 	const uint32_t nx = grid.sx + 1, ny = grid.sy + 1, nz = grid.sz + 1;
 	const int ni = int(min(uint32_t(kBrick), nx - i0)), nj = int(min(uint32_t(kBrick), ny - j0)), nk = int(min(uint32_t(kBrick), nz - k0));
-	EvaluateTile(sh, model, grid, i0, j0, k0, ni, nj, nk, 0, counters);
+	EvaluateTile(w, model, grid, i0, j0, k0, ni, nj, nk, 0, counters);
 	if (out == nullptr) return;
-	for (int s = threadIdx.x; s < kBrick * kBrick * kBrick; s += kThreads)
+	for (int s = lane; s < kBrick * kBrick * kBrick; s += 32)
 	{
 		const int li = s & 7, lj = (s >> 3) & 7, lk = s >> 6;
 		if (li < ni && lj < nj && lk < nk)
 		{
-			out[(size_t(k0 + lk) * ny + (j0 + lj)) * nx + (i0 + li)] = sh.tile[(lk * kTile + lj) * kTile + li];
+			out[(size_t(k0 + lk) * ny + (j0 + lj)) * nx + (i0 + li)] = w.tile[(lk * kTile + lj) * kTile + li];
 		}
 	}
 }
@@ -503,7 +500,7 @@ __device__ bool BrickIsEmpty(const DeviceModel& model, float lox, float loy, flo
 		if (need_self)
 		{
 			if ((__ldg(&model.nodes[n].flags) & kNodeCullable) == 0u) return false;
-			const float d = EvalDistance1(model.interp + __ldg(&model.nodes[n].interp_offset), cx, cy, cz);
+			const float d = EvalInterp1(model, __ldg(&model.nodes[n].interp_offset), cx, cy, cz);
 			if (!(fabsf(d) > threshold)) return false;
 			const int s = d > 0.0f ? 1 : -1;
 			if (sign == 0) sign = s;
@@ -844,7 +841,7 @@ __global__ void __launch_bounds__(128) AttributesKernel(const AttributeParams p)
 			const uint32_t node = Descend(model.nodes, 0, x, y, z);
 			float gx, gy, gz;
 			EvalGradient(model.tree + __ldg(&model.nodes[node].tree_offset), x, y, z, gx, gy, gz);
-			const float dist = -EvalDistance1(model.interp + __ldg(&model.nodes[node].interp_offset), x, y, z);
+			const float dist = -EvalInterp1(model, __ldg(&model.nodes[node].interp_offset), x, y, z);
 			x = x + gx * dist;
 			y = y + gy * dist;
 			z = z + gz * dist;
@@ -914,11 +911,11 @@ __global__ void __launch_bounds__(128) EvalPointsKernel(const DeviceModel model,
 	if (mode == TG_EVAL_OCTREE)
 	{
 		const uint32_t node = Descend(model.nodes, 0, x, y, z);
-		static_cast<float*>(out)[i] = EvalDistance1(model.interp + __ldg(&model.nodes[node].interp_offset), x, y, z);
+		static_cast<float*>(out)[i] = EvalInterp1(model, __ldg(&model.nodes[node].interp_offset), x, y, z);
 	}
 	else if (mode == TG_EVAL_INTERP)
 	{
-		static_cast<float*>(out)[i] = EvalDistance1(model.interp + model.root_interp_offset, x, y, z);
+		static_cast<float*>(out)[i] = EvalInterp1(model, model.root_interp_offset, x, y, z);
 	}
 	else if (mode == TG_EVAL_TREE)
 	{
@@ -995,7 +992,7 @@ __global__ void __launch_bounds__(128) PointCloudKernel(const DeviceModel model,
 		const float x = float(i % nx) * stepx + startx;
 		const float cx = x + stepx / 2.0f, cy = y + stepy / 2.0f, cz = z + stepz / 2.0f;
 		const uint32_t node = Descend(model.nodes, 0, cx, cy, cz);
-		const float d = EvalDistance1(model.interp + __ldg(&model.nodes[node].interp_offset), cx, cy, cz);
+		const float d = EvalInterp1(model, __ldg(&model.nodes[node].interp_offset), cx, cy, cz);
 		hit = fabsf(d) < diagonal;
 	}
 	const unsigned ballot = __ballot_sync(0xFFFFFFFFu, hit);
@@ -1101,6 +1098,10 @@ Context* Context::Create(int device, std::string& error)
 	c->timer_events[0] = ev0;
 	c->timer_events[1] = ev1;
 	cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->brick_blocks_per_sm, MeshBricksKernel, kBrickThreads, 0) != cudaSuccess || c->brick_blocks_per_sm < 1)
+	{
+		c->brick_blocks_per_sm = 1;
+	}
 	// Keep freed scratch in the pool so steady-state exports do not hit the allocator.
 	cudaMemPool_t pool;
 	if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
@@ -1247,7 +1248,7 @@ static DeviceModel MakeDeviceModel(const Model* m)
 {
 	DeviceModel d;
 	d.nodes = static_cast<const FlatNode*>(m->d_nodes);
-	d.interp = static_cast<const uint32_t*>(m->d_interp);
+	d.interp = static_cast<const uint4*>(m->d_interp);
 	d.tree = static_cast<const uint32_t*>(m->d_tree);
 	d.material_rgb = static_cast<const float*>(m->d_materials);
 	d.material_count = uint32_t(m->flat.material_rgb.size() / 3 - 1);
@@ -1580,7 +1581,13 @@ int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options
 		mp.tmp_key = tmp_key;
 		mp.tmp_capacity = uint32_t(tmp_capacity);
 		TG_CUDA(cudaMemsetAsync(counters + kCntTmpVertices, 0, 3 * 8, stream));
-		MeshBricksKernel<<<uint32_t(active_count), kThreads, 0, stream>>>(mp);
+		TG_CUDA(cudaMemsetAsync(counters + kCntBrickCursor, 0, 8, stream));
+		{
+			// persistent warps: enough blocks to fill every SM, never more than there are bricks
+			const uint64_t wanted = (active_count + kBrickWarps - 1) / kBrickWarps;
+			const uint32_t blocks = uint32_t(std::min<uint64_t>(wanted, uint64_t(ctx->sm_count) * ctx->brick_blocks_per_sm));
+			MeshBricksKernel<<<blocks, kBrickThreads, 0, stream>>>(mp);
+		}
 		launches++;
 		TG_CUDA(cudaGetLastError());
 		TG_CUDA(cudaMemcpyAsync(host_counts, counters, kCntCount * 8, cudaMemcpyDeviceToHost, stream));
@@ -1789,7 +1796,8 @@ int EngineEvalLattice(Model* model, const tg_grid& grid_in, float* out, float* o
 	if (out) TG_CUDA(scratch.Alloc(&d_out, total));
 	StageTimer timer(stream);
 	const int t0 = timer.Mark();
-	LatticeKernel<<<tx * ty * tz, kThreads, 0, stream>>>(MakeDeviceModel(model), grid, d_out, tx, ty, counters);
+	const uint32_t tile_count = tx * ty * tz;
+	LatticeKernel<<<(tile_count + kBrickWarps - 1) / kBrickWarps, kBrickThreads, 0, stream>>>(MakeDeviceModel(model), grid, d_out, tx, ty, tile_count, counters);
 	const int t1 = timer.Mark();
 	TG_CUDA(cudaGetLastError());
 	if (out) TG_CUDA(cudaMemcpyAsync(out, d_out, total * 4, cudaMemcpyDeviceToHost, stream));

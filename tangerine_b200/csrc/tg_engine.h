@@ -28,6 +28,7 @@ public:
 	void* timer_events[2] = { nullptr, nullptr };
 	std::vector<PinnedBlock> pinned; // grow-only pool of page-locked host buffers for results
 	int sm_count = 0;
+	int brick_blocks_per_sm = 1; // resident MeshBricksKernel blocks per SM (persistent grid size)
 
 	// Export progress mirrors the reference's atomics (export.cpp:48-57).
 	std::atomic<int> stage{ 0 };

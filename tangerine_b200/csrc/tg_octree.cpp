@@ -165,49 +165,30 @@ struct StreamGen
 
 	void EmitBrush(const Node& n, uint32_t op, float threshold, uint32_t flags)
 	{
+		if (!tree_stream)
+		{
+			EmitBrushQuads(n, op, threshold, flags);
+			return;
+		}
 		const size_t start = out.size();
 		out.push_back(0);
 		uint32_t xform = kXformNone;
 		const bool identity = n.rotation.IsIdentity();
 		const bool unit = n.scalation == 1.0f;
 		const bool moved = !(n.translation == Vec3(0.0f, 0.0f, 0.0f));
-		if (tree_stream)
+		// Transform::ApplyInv: rotate(inverse(q), p - t) / s.  With q = identity and s = 1 that is p - t exactly.
+		if (!identity || !unit)
 		{
-			// Transform::ApplyInv: rotate(inverse(q), p - t) / s.  With q = identity and s = 1 that is p - t exactly.
-			if (!identity || !unit)
-			{
-				xform = kXformQuat;
-				Quat iq = Inverse(n.rotation);
-				PushF(iq.w); PushF(iq.x); PushF(iq.y); PushF(iq.z);
-				PushF(n.translation.x); PushF(n.translation.y); PushF(n.translation.z);
-				PushF(n.scalation);
-			}
-			else if (moved)
-			{
-				xform = kXformOffset;
-				PushF(-n.translation.x); PushF(-n.translation.y); PushF(-n.translation.z);
-			}
+			xform = kXformQuat;
+			Quat iq = Inverse(n.rotation);
+			PushF(iq.w); PushF(iq.x); PushF(iq.y); PushF(iq.z);
+			PushF(n.translation.x); PushF(n.translation.y); PushF(n.translation.z);
+			PushF(n.scalation);
 		}
-		else
+		else if (moved)
 		{
-			// EvaluatorTransform::Compile :409-429
-			if (!identity || !unit)
-			{
-				xform = kXformMatrix;
-				Mat4 inv = CompiledInverseMatrix(n);
-				for (int c = 0; c < 4; ++c)
-				{
-					for (int r = 0; r < 3; ++r)
-					{
-						PushF(inv.m[c][r]);
-					}
-				}
-			}
-			else if (moved)
-			{
-				xform = kXformOffset;
-				PushF(-n.translation.x); PushF(-n.translation.y); PushF(-n.translation.z);
-			}
+			xform = kXformOffset;
+			PushF(-n.translation.x); PushF(-n.translation.y); PushF(-n.translation.z);
 		}
 		for (int i = 0; i < BrushParamCount(n.kind); ++i)
 		{
@@ -219,11 +200,8 @@ struct StreamGen
 			PushF(n.scalation);
 			flops += 1;
 		}
-		if (tree_stream)
-		{
-			flags |= kHdrMaterialBit;
-			out.push_back(n.material);
-		}
+		flags |= kHdrMaterialBit;
+		out.push_back(n.material);
 		uint32_t slot = kNoSlot;
 		if (op == kOpPush)
 		{
@@ -246,6 +224,66 @@ struct StreamGen
 		out[start] = MakeHeader(n.kind, xform, op, slot, flags, uint32_t(out.size() - start));
 	}
 
+	// kStreamInterp: 16-byte quads (tg_program.h).  [header p0 p1 p2] [3 quads matrix | 1 quad offset]? [scale threshold 0 0]?
+	void EmitBrushQuads(const Node& n, uint32_t op, float threshold, uint32_t flags)
+	{
+		const size_t start = out.size();
+		out.push_back(0);
+		for (int i = 0; i < 3; ++i)
+		{
+			PushF(i < BrushParamCount(n.kind) ? n.params[i] : 0.0f);
+		}
+		uint32_t xform = kXformNone;
+		const bool identity = n.rotation.IsIdentity();
+		const bool unit = n.scalation == 1.0f;
+		const bool moved = !(n.translation == Vec3(0.0f, 0.0f, 0.0f));
+		// EvaluatorTransform::Compile :409-429
+		if (!identity || !unit)
+		{
+			xform = kXformMatrix;
+			Mat4 inv = CompiledInverseMatrix(n);
+			for (int c = 0; c < 4; ++c)
+			{
+				for (int r = 0; r < 3; ++r)
+				{
+					PushF(inv.m[c][r]);
+				}
+			}
+		}
+		else if (moved)
+		{
+			xform = kXformOffset;
+			PushF(-n.translation.x); PushF(-n.translation.y); PushF(-n.translation.z); PushF(0.0f);
+		}
+		const bool blend = op >= kOpBlendUnion && op <= kOpBlendDiff;
+		if (!unit)
+		{
+			flags |= kHdrScaleBit;
+			flops += 1;
+		}
+		if (!unit || blend)
+		{
+			flags |= kHdrTailBit;
+			PushF(n.scalation); PushF(blend ? threshold : 0.0f); PushF(0.0f); PushF(0.0f);
+		}
+		uint32_t slot = kNoSlot;
+		if (op == kOpPush)
+		{
+			if (depth >= 1)
+			{
+				slot = uint32_t(depth - 1);
+				if (depth > max_slots) max_slots = depth;
+			}
+			depth++;
+		}
+		flops += uint32_t(XformFlops(xform) + BrushFlops(n.kind) + OpFlops(op));
+		if (n.kind == kKindEllipsoid)
+		{
+			cullable = false;
+		}
+		out[start] = MakeHeader(n.kind, xform, op, slot, flags, uint32_t((out.size() - start) / 4));
+	}
+
 	void EmitOp(uint32_t op, float param, uint32_t word, bool has_word, uint32_t flags)
 	{
 		const size_t start = out.size();
@@ -265,6 +303,12 @@ struct StreamGen
 			out.push_back(word);
 		}
 		flops += uint32_t(OpFlops(op));
+		if (!tree_stream)
+		{
+			while ((out.size() - start) % 4 != 0) out.push_back(0); // [header param 0 0]
+			out[start] = MakeHeader(kBrushNone, kXformNone, op, slot, flags, uint32_t((out.size() - start) / 4));
+			return;
+		}
 		out[start] = MakeHeader(kBrushNone, kXformNone, op, slot, flags, uint32_t(out.size() - start));
 	}
 
@@ -310,6 +354,10 @@ struct StreamGen
 	void Finish()
 	{
 		out.push_back(MakeHeader(kBrushNone, kXformNone, kOpStop, kNoSlot, 0, 1));
+		if (!tree_stream)
+		{
+			for (int i = 0; i < 3; ++i) out.push_back(0);
+		}
 	}
 };
 
@@ -491,6 +539,7 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 			return false;
 		}
 	}
+	for (int i = 0; i < 4; ++i) out.interp.push_back(0); // the interpreter prefetches one quad past an instruction
 	SnapshotMaterials(out.material_rgb);
 	out.material_rgb.push_back(1.0f); // default material (GetDefaultMaterial :34-38), addressed by kNoMaterial
 	out.material_rgb.push_back(1.0f);

@@ -15,7 +15,16 @@
 //                    material ids, paint flags and stencil masks so the same stream also evaluates
 //                    GetMaterial (sdf_evaluator.cpp:537-547, 666-679, 957-1012).
 //
-// Word layout of an instruction:  [header] [transform params] [brush params] [scale] [material] [op param]
+// Word layout of a kStreamTree instruction:  [header] [transform params] [brush params] [scale] [material] [op param]
+//
+// kStreamInterp is the hot stream (every lattice sample runs it) and is laid out in 16-byte quads so that the
+// interpreter fetches an instruction with warp-uniform 128-bit loads, all of them independent of each other:
+//   quad 0            [header, p0, p1, p2]            brush parameters (unused ones are 0)
+//   quads 1-3         matrix transform: 12 floats, column-major 3 rows x 4 columns      (kXformMatrix)
+//   quad 1            [ox, oy, oz, 0]                                                   (kXformOffset)
+//   tail quad         [scale, threshold, 0, 0]        only when kHdrTailBit is set (scaled brush or blend operator)
+// Operator-only instructions are one quad [header, param, 0, 0].  The length field counts quads; programs start
+// on quad boundaries (FlatNode::interp_offset is a word offset that is a multiple of 4).
 #pragma once
 
 #include <cstdint>
@@ -68,8 +77,9 @@ constexpr uint32_t kHdrOpShift = 8;              // bits 8-11
 constexpr uint32_t kHdrLhsPaintBit = 1u << 12;   // HasPaint() of the left operand (material walk of Inter)
 constexpr uint32_t kHdrRhsPaintBit = 1u << 13;   // HasPaint() of the right operand
 constexpr uint32_t kHdrStencilNegBit = 1u << 14; // StencilMaskNode<ApplyToNegative = true>
+constexpr uint32_t kHdrTailBit = 1u << 15;       // kStreamInterp: a [scale, threshold, 0, 0] quad closes the instruction
 constexpr uint32_t kHdrSlotShift = 16;           // bits 16-23: stack slot to spill to / pop from, 0xFF = none
-constexpr uint32_t kHdrLenShift = 24;            // bits 24-31: instruction length in words, header included
+constexpr uint32_t kHdrLenShift = 24;            // bits 24-31: instruction length, header included (words; quads in kStreamInterp)
 constexpr uint32_t kNoSlot = 0xFFu;
 
 constexpr uint32_t kNoMaterial = 0xFFFFFFFFu; // the reference's default white material (sdf_evaluator.cpp:34-38)
