@@ -19,7 +19,8 @@ class TangerineError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, "libtangerine_b200.so")
+    # TANGERINE_B200_LIB: load an alternative build of the same library (kernel tuning experiments)
+    return os.environ.get("TANGERINE_B200_LIB") or os.path.join(_HERE, "libtangerine_b200.so")
 
 
 def build_library():
