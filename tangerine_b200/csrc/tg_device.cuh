@@ -25,6 +25,8 @@ struct DeviceModel
 	const FlatNode* nodes;
 	const uint4* interp;       // kStreamInterp, 16-byte quads; FlatNode::interp_offset / 4 indexes it
 	const uint32_t* tree;
+	const FlatRegion* regions;
+	uint32_t region_count;
 	const float* material_rgb; // 3 floats per id
 	uint32_t material_count;   // index of the trailing default-white entry
 	uint32_t root_interp_offset;

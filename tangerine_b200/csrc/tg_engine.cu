@@ -1,6 +1,6 @@
 // CUDA engine for the SDF meshing hot path (sm_100a).  See DESIGN.md for the pipeline and data layout.
 //
-//   K0  CullLevelKernel        hierarchical Lipschitz culling of empty space: 64^3 -> 8^3 cell bricks
+//   K0  CullRegionInit/Level/Resolve  Lipschitz culling of empty space driven by the octree's evaluation regions
 //   K1  MeshBricksKernel       per active 8^3 brick: octree descent per lattice sample, node-coherent
 //       (+K2 fused)            re-binning, postfix interpreter (4 samples / lane), 9^3 tile in shared memory,
 //                              sign classification, surface-nets vertex, ballot-compacted writes
@@ -54,7 +54,10 @@ constexpr int kMaxGroups = 32;            // distinct octree nodes per grouping 
 constexpr int kLaneSamples = TG_LANE_SAMPLES; // samples interpreted per lane per dispatch
 constexpr uint32_t kEmptyGroup = 0xFFFFFFFFu;
 constexpr uint32_t kHaloFlag = 1u << 30;
-constexpr int kTopLevel = 3;              // 8 << 3 = 64-cell bricks at the top of the cull hierarchy
+#ifndef TG_TOP_LEVEL
+#define TG_TOP_LEVEL 3
+#endif
+constexpr int kTopLevel = TG_TOP_LEVEL;  // cull hierarchy starts at (8 << kTopLevel)-cell bricks
 
 enum Counter
 {
@@ -442,121 +445,261 @@ __global__ void __launch_bounds__(kBrickThreads) LatticeKernel(const DeviceModel
 }
 
 // ------------------------------------------------------------------------------------------------
-// K0: hierarchical empty-space culling
+// K0: empty-space culling, driven by the octree's evaluation regions (FlatRegion) instead of the grid.
+//
+// Every lattice sample belongs to exactly one region, and inside a region the reference evaluates ONE program.
+// A work item is (region, brick at some level of the 8 / 16 / ... / 128-cell brick hierarchy): it evaluates the
+// region's program once, at the centre of the part of the brick's sample box that lies in the region.  If the
+// program is 1-Lipschitz (no Ellipsoid) and |d(centre)| exceeds that box's half diagonal, no sample of the region
+// in this brick can change sign: the brick is flagged "empty, sign s" for this region at this level.  Otherwise the
+// item splits into the child bricks the region touches, or, at the 8-cell level, flags the brick "evaluate".
+// A brick is skipped when no region asked for it to be evaluated and all empty flags it inherits agree in sign.
+// Work is proportional to the octree (a few 10^5 small-program evaluations), not to the grid volume, and the
+// large programs of interior nodes are only run for the few coarse bricks of their empty octants.
 // ------------------------------------------------------------------------------------------------
+
+constexpr int kCullLevels = 5; // 8, 16, 32, 64, 128 cells
+constexpr uint32_t kFlagPositive = 1u, kFlagNegative = 2u, kFlagEvaluate = 4u;
+
+struct CullItem
+{
+	uint32_t region;
+	uint32_t cell; // x | y << 10 | z << 20 at the item's level
+};
+
+struct RegionRange
+{
+	uint16_t a[3], b[3]; // inclusive lattice sample index range of the region inside the slab; a > b = empty
+};
 
 struct CullParams
 {
 	DeviceModel model;
 	DeviceGrid grid;
-	const uint32_t* in_list;
-	uint32_t in_count;
-	uint32_t* out_list;
-	unsigned long long* out_counter;
-	uint32_t out_capacity;
-	int level;          // input bricks are (8 << level) cells wide
-	uint32_t k_begin, k_end; // cell layers that may produce output bricks
-	int halo;           // input is the halo brick layer: restrict the test to its top cell layer, flag the output
-	int no_cull;
+	uint32_t sample_k_lo, sample_k_hi; // slab sample range in z (inclusive): owned cell layers + the halo layer below
+	uint32_t cell_k_lo, cell_k_hi;     // slab cell range in z (hi exclusive)
+	RegionRange* ranges;
+	CullItem* lists[kCullLevels];
+	uint32_t capacity[kCullLevels];
+	uint32_t* counts;                  // kCullLevels item counters
+	uint32_t* flags[kCullLevels];
+	uint32_t dims[kCullLevels][3];     // bricks per axis at each level
+	int level;
 };
 
-// A brick is skipped only when every octree node that any of its lattice samples can descend to has a
-// cullable (1-Lipschitz) program whose value at the brick centre exceeds the brick's half diagonal, all
-// with the same sign: then no cell of the brick has a bipolar edge, whichever program each sample uses.
-__device__ bool BrickIsEmpty(const DeviceModel& model, float lox, float loy, float loz, float hix, float hiy, float hiz)
+// First lattice index i in [0, last + 1] with LatticeCoord(origin, step, i) > p (last + 1 when there is none).
+__device__ __forceinline__ uint32_t FirstIndexAbove(float origin, float step, uint32_t last, float p)
 {
-	const float cx = 0.5f * (lox + hix), cy = 0.5f * (loy + hiy), cz = 0.5f * (loz + hiz);
-	const float ex = hix - lox, ey = hiy - loy, ez = hiz - loz;
-	const float radius = 0.5f * sqrtf(ex * ex + ey * ey + ez * ez);
-	const float threshold = radius * 1.001f + 1.0e-4f;
-	uint32_t stack[64];
-	int sp = 0;
-	stack[sp++] = 0;
-	int sign = 0;
-	int visited = 0;
-	while (sp > 0)
+	if (!(p > -INFINITY)) return 0u; // -inf (or NaN: be conservative)
+	float guess = floorf((p - origin) / step) - 2.0f;
+	guess = fminf(fmaxf(guess, 0.0f), float(last));
+	uint32_t i = uint32_t(guess);
+	while (i > 0u && LatticeCoord(origin, step, i) > p) i--; // the estimate can only be off by rounding
+	while (i <= last && !(LatticeCoord(origin, step, i) > p)) i++;
+	return i;
+}
+
+// Reserves n slots per lane in a device list with one atomic per warp; every lane of the warp must call.
+__device__ __forceinline__ uint32_t WarpAppend(uint32_t* counter, uint32_t n, bool& fits, uint32_t capacity)
+{
+	const int lane = threadIdx.x & 31;
+	uint32_t incl = n;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
 	{
-		const uint32_t n = stack[--sp];
-		if (++visited > 96) return false;
-		const float4 head = __ldg(reinterpret_cast<const float4*>(&model.nodes[n]));
-		bool need_self = __float_as_uint(head.w) != 0u;
-		if (!need_self)
-		{
-			const bool hi1[3] = { hix > head.x, hiy > head.y, hiz > head.z };   // some sample takes the upper octant
-			const bool lo0[3] = { !(lox > head.x), !(loy > head.y), !(loz > head.z) }; // some sample takes the lower octant
-			for (int o = 0; o < 8; ++o)
-			{
-				const bool reach = ((o & 1) ? hi1[0] : lo0[0]) && ((o & 2) ? hi1[1] : lo0[1]) && ((o & 4) ? hi1[2] : lo0[2]);
-				if (!reach) continue;
-				const int32_t child = __ldg(&model.nodes[n].children[o]);
-				if (child < 0) need_self = true;
-				else
-				{
-					if (sp >= 64) return false;
-					stack[sp++] = uint32_t(child);
-				}
-			}
-		}
-		if (need_self)
-		{
-			if ((__ldg(&model.nodes[n].flags) & kNodeCullable) == 0u) return false;
-			const float d = EvalInterp1(model, __ldg(&model.nodes[n].interp_offset), cx, cy, cz);
-			if (!(fabsf(d) > threshold)) return false;
-			const int s = d > 0.0f ? 1 : -1;
-			if (sign == 0) sign = s;
-			else if (sign != s) return false;
-		}
+		const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+		if (lane >= o) incl += v;
 	}
-	return true;
+	const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+	uint32_t base = 0;
+	if (lane == 31 && total) base = atomicAdd(counter, total);
+	base = __shfl_sync(0xFFFFFFFFu, base, 31);
+	fits = base + total <= capacity;
+	return base + incl - n;
+}
+
+__global__ void __launch_bounds__(128) CullRegionInitKernel(const CullParams p)
+{
+	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= p.model.region_count) return;
+	const FlatRegion region = p.model.regions[r];
+	const DeviceGrid& g = p.grid;
+	const float origin[3] = { g.x, g.y, g.z }, step[3] = { g.dx, g.dy, g.dz };
+	const uint32_t last[3] = { g.sx, g.sy, g.sz };
+	uint32_t a[3], b[3];
+	bool empty = false;
+#pragma unroll
+	for (int ax = 0; ax < 3; ++ax)
+	{
+		a[ax] = FirstIndexAbove(origin[ax], step[ax], last[ax], region.lo[ax]);                  // first sample with x > lo
+		const uint32_t above = region.hi[ax] < INFINITY ? FirstIndexAbove(origin[ax], step[ax], last[ax], region.hi[ax]) : last[ax] + 1u;
+		if (above == 0u) empty = true;
+		b[ax] = above - 1u;                                                                        // last sample with x <= hi
+	}
+	a[2] = max(a[2], p.sample_k_lo);
+	b[2] = empty ? 0u : min(b[2], p.sample_k_hi);
+	empty = empty || a[0] > b[0] || a[1] > b[1] || a[2] > b[2];
+	RegionRange range;
+#pragma unroll
+	for (int ax = 0; ax < 3; ++ax)
+	{
+		range.a[ax] = uint16_t(empty ? 1u : a[ax]);
+		range.b[ax] = uint16_t(empty ? 0u : b[ax]);
+	}
+	p.ranges[r] = range;
+	if (empty) return;
+	// cells that use these samples: [a - 1, b], clipped to the grid / slab
+	uint32_t clo[3], chi[3];
+#pragma unroll
+	for (int ax = 0; ax < 3; ++ax)
+	{
+		clo[ax] = a[ax] > 0u ? a[ax] - 1u : 0u;
+		chi[ax] = min(b[ax], last[ax] - 1u);
+	}
+	clo[2] = max(clo[2], p.cell_k_lo);
+	chi[2] = min(chi[2], p.cell_k_hi - 1u);
+	if (clo[2] > chi[2]) return;
+	int level = 0;
+	for (; level < kCullLevels - 1; ++level)
+	{
+		const int sh = 3 + level;
+		if ((chi[0] >> sh) - (clo[0] >> sh) < 3u && (chi[1] >> sh) - (clo[1] >> sh) < 3u && (chi[2] >> sh) - (clo[2] >> sh) < 3u) break;
+	}
+	const int sh = 3 + level;
+	const uint32_t x0 = clo[0] >> sh, x1 = chi[0] >> sh, y0 = clo[1] >> sh, y1 = chi[1] >> sh, z0 = clo[2] >> sh, z1 = chi[2] >> sh;
+	const uint32_t n = (x1 - x0 + 1u) * (y1 - y0 + 1u) * (z1 - z0 + 1u);
+	const uint32_t base = atomicAdd(&p.counts[level], n);
+	if (base + n > p.capacity[level])
+	{
+		// cannot queue: ask for every brick under these cells to be evaluated
+		for (uint32_t z = z0; z <= z1; ++z)
+			for (uint32_t y = y0; y <= y1; ++y)
+				for (uint32_t x = x0; x <= x1; ++x)
+					atomicOr(&p.flags[level][(size_t(z) * p.dims[level][1] + y) * p.dims[level][0] + x], kFlagEvaluate);
+		return;
+	}
+	uint32_t o = base;
+	for (uint32_t z = z0; z <= z1; ++z)
+		for (uint32_t y = y0; y <= y1; ++y)
+			for (uint32_t x = x0; x <= x1; ++x)
+			{
+				CullItem item = { r, x | (y << 10) | (z << 20) };
+				p.lists[level][o++] = item;
+			}
 }
 
 __global__ void __launch_bounds__(128) CullLevelKernel(const CullParams p)
 {
 	const uint32_t index = blockIdx.x * blockDim.x + threadIdx.x;
-	if (index >= p.in_count) return;
-	const uint32_t brick = p.in_list[index];
-	const uint32_t bx = brick & 1023u, by = (brick >> 10) & 1023u, bz = (brick >> 20) & 1023u;
-	const uint32_t width = uint32_t(kBrick) << p.level;
+	const int level = p.level;
+	const uint32_t count = min(p.counts[level], p.capacity[level]);
+	if (blockIdx.x * blockDim.x >= count) return; // whole block beyond the list (warps stay intact below)
 	const DeviceGrid& g = p.grid;
-	const uint32_t i0 = bx * width, j0 = by * width, k0 = bz * width;
-	const uint32_t i1 = min(i0 + width, g.sx), j1 = min(j0 + width, g.sy);
-	uint32_t klo = max(k0, p.k_begin), k1 = min(min(k0 + width, g.sz), p.k_end);
-	if (p.halo)
+	const uint32_t width = uint32_t(kBrick) << level;
+	bool live = index < count;
+	CullItem item = { 0u, 0u };
+	uint32_t cx = 0, cy = 0, cz = 0, lo_i = 0, hi_i = 0, lo_j = 0, hi_j = 0, lo_k = 0, hi_k = 0;
+	if (live)
 	{
-		klo = k0 + width - 1; // only the top cell layer of a halo brick matters
-		k1 = k0 + width;
+		item = p.lists[level][index];
+		const RegionRange range = p.ranges[item.region];
+		cx = item.cell & 1023u, cy = (item.cell >> 10) & 1023u, cz = (item.cell >> 20) & 1023u;
+		// sample box of this brick (clipped to grid and slab) intersected with the region's sample box
+		lo_i = max(cx * width, uint32_t(range.a[0])), hi_i = min(min((cx + 1u) * width, g.sx), uint32_t(range.b[0]));
+		lo_j = max(cy * width, uint32_t(range.a[1])), hi_j = min(min((cy + 1u) * width, g.sy), uint32_t(range.b[1]));
+		lo_k = max(cz * width, uint32_t(range.a[2])), hi_k = min(min((cz + 1u) * width, g.sz), uint32_t(range.b[2]));
+		live = lo_i <= hi_i && lo_j <= hi_j && lo_k <= hi_k;
 	}
-	bool empty = false;
-	if (!p.no_cull)
+	uint32_t* flag = &p.flags[level][(size_t(cz) * p.dims[level][1] + cy) * p.dims[level][0] + cx];
+	if (live)
 	{
-		empty = BrickIsEmpty(p.model, LatticeCoord(g.x, g.dx, i0), LatticeCoord(g.y, g.dy, j0), LatticeCoord(g.z, g.dz, klo),
-			LatticeCoord(g.x, g.dx, i1), LatticeCoord(g.y, g.dy, j1), LatticeCoord(g.z, g.dz, k1));
+		const uint32_t node = p.model.regions[item.region].node;
+		if (__ldg(&p.model.nodes[node].flags) & kNodeCullable)
+		{
+			const float lox = LatticeCoord(g.x, g.dx, lo_i), loy = LatticeCoord(g.y, g.dy, lo_j), loz = LatticeCoord(g.z, g.dz, lo_k);
+			const float hix = LatticeCoord(g.x, g.dx, hi_i), hiy = LatticeCoord(g.y, g.dy, hi_j), hiz = LatticeCoord(g.z, g.dz, hi_k);
+			const float ex = hix - lox, ey = hiy - loy, ez = hiz - loz;
+			const float radius = 0.5f * sqrtf(ex * ex + ey * ey + ez * ez);
+			const float threshold = radius * 1.001f + 1.0e-4f;
+			const float d = EvalInterp1(p.model, __ldg(&p.model.nodes[node].interp_offset), 0.5f * (lox + hix), 0.5f * (loy + hiy), 0.5f * (loz + hiz));
+			if (fabsf(d) > threshold)
+			{
+				atomicOr(flag, d > 0.0f ? kFlagPositive : kFlagNegative);
+				live = false; // decided
+			}
+		}
 	}
-	if (empty) return;
-	if (p.level == 0)
+	if (level == 0)
 	{
-		const unsigned long long slot = atomicAdd(p.out_counter, 1ull);
-		if (slot < p.out_capacity) p.out_list[slot] = brick | (p.halo ? kHaloFlag : 0u);
+		if (live) atomicOr(flag, kFlagEvaluate);
 		return;
 	}
+	// split into the child bricks whose sample box still meets the region
 	const uint32_t half = width >> 1;
-	for (int o = 0; o < 8; ++o)
+	uint32_t children[8];
+	uint32_t n = 0;
+	if (live)
 	{
-		const uint32_t cx = bx * 2 + (o & 1), cy = by * 2 + ((o >> 1) & 1), cz = bz * 2 + ((o >> 2) & 1);
-		const uint32_t ci = cx * half, cj = cy * half, ck = cz * half;
-		if (ci >= g.sx || cj >= g.sy || ck >= g.sz) continue;
-		if (ck + half <= p.k_begin || ck >= p.k_end) continue;
-		const unsigned long long slot = atomicAdd(p.out_counter, 1ull);
-		if (slot < p.out_capacity) p.out_list[slot] = cx | (cy << 10) | (cz << 20);
+#pragma unroll
+		for (int o = 0; o < 8; ++o)
+		{
+			const uint32_t x = cx * 2u + (o & 1), y = cy * 2u + ((o >> 1) & 1), z = cz * 2u + ((o >> 2) & 1);
+			const bool hit = max(x * half, lo_i) <= min((x + 1u) * half, hi_i) && max(y * half, lo_j) <= min((y + 1u) * half, hi_j) &&
+				max(z * half, lo_k) <= min((z + 1u) * half, hi_k) && x * half < g.sx && y * half < g.sy && z * half < p.cell_k_hi && (z + 1u) * half > p.cell_k_lo;
+			if (hit) children[n++] = x | (y << 10) | (z << 20);
+		}
+	}
+	bool fits;
+	const uint32_t base = WarpAppend(&p.counts[level - 1], n, fits, p.capacity[level - 1]);
+	if (!live) return;
+	if (!fits)
+	{
+		atomicOr(flag, kFlagEvaluate); // inherited by every brick below this one
+		return;
+	}
+	for (uint32_t c = 0; c < n; ++c)
+	{
+		CullItem child = { item.region, children[c] };
+		p.lists[level - 1][base + c] = child;
 	}
 }
 
-__global__ void InitBrickListKernel(uint32_t* list, uint32_t nbx, uint32_t nby, uint32_t bz_begin, uint32_t nbz)
+// One thread per 8-cell brick of the slab (and of the halo row below it): combine the flags it inherits.
+__global__ void __launch_bounds__(256) CullResolveKernel(const CullParams p, uint32_t bz_begin, uint32_t bz_end, uint32_t halo_row, int no_cull,
+	uint32_t* __restrict__ out_list, unsigned long long* out_counter, uint32_t out_capacity)
 {
+	const uint32_t nbx = p.dims[0][0], nby = p.dims[0][1];
 	const uint32_t index = blockIdx.x * blockDim.x + threadIdx.x;
-	if (index >= nbx * nby * nbz) return;
-	const uint32_t x = index % nbx, y = (index / nbx) % nby, z = index / (nbx * nby) + bz_begin;
-	list[index] = x | (y << 10) | (z << 20);
+	const uint32_t rows = bz_end - bz_begin;
+	bool active = false;
+	uint32_t brick = 0;
+	if (index < nbx * nby * rows)
+	{
+		const uint32_t x = index % nbx, y = (index / nbx) % nby, z = index / (nbx * nby) + bz_begin;
+		uint32_t f = 0;
+		if (no_cull) f = kFlagEvaluate;
+		else
+		{
+#pragma unroll
+			for (int level = 0; level < kCullLevels; ++level)
+			{
+				f |= p.flags[level][(size_t(z >> level) * p.dims[level][1] + (y >> level)) * p.dims[level][0] + (x >> level)];
+			}
+		}
+		active = (f & kFlagEvaluate) != 0u || (f & 3u) == 3u || f == 0u;
+		brick = x | (y << 10) | (z << 20) | (z == halo_row ? kHaloFlag : 0u);
+	}
+	const unsigned ballot = __ballot_sync(0xFFFFFFFFu, active);
+	if (ballot == 0u) return;
+	const int lane = threadIdx.x & 31;
+	unsigned long long base = 0;
+	if (lane == 0) base = atomicAdd(out_counter, (unsigned long long)__popc(ballot));
+	base = __shfl_sync(0xFFFFFFFFu, base, 0);
+	if (active)
+	{
+		const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
+		if (slot < out_capacity) out_list[slot] = brick;
+	}
 }
 
 __global__ void BrickLayerHistogramKernel(const uint32_t* __restrict__ list, uint32_t count, uint32_t* __restrict__ layers)
@@ -1184,6 +1327,8 @@ static void FreeModelTables(Model* m)
 	cudaFree(m->d_interp);
 	cudaFree(m->d_tree);
 	cudaFree(m->d_materials);
+	cudaFree(m->d_regions);
+	m->d_regions = nullptr;
 	m->d_nodes = m->d_interp = m->d_tree = m->d_materials = nullptr;
 	m->device_bytes = 0;
 }
@@ -1199,6 +1344,7 @@ static int UploadModel(Model* m, std::string& error)
 	if ((rc = UploadVector(c, m->flat.interp, &m->d_interp, m->device_bytes, error)) != TG_OK) return rc;
 	if ((rc = UploadVector(c, m->flat.tree, &m->d_tree, m->device_bytes, error)) != TG_OK) return rc;
 	if ((rc = UploadVector(c, m->flat.material_rgb, &m->d_materials, m->device_bytes, error)) != TG_OK) return rc;
+	if ((rc = UploadVector(c, m->flat.regions, &m->d_regions, m->device_bytes, error)) != TG_OK) return rc;
 	TG_CUDA(cudaStreamSynchronize(StreamOf(c)));
 	return TG_OK;
 }
@@ -1251,6 +1397,8 @@ static DeviceModel MakeDeviceModel(const Model* m)
 	d.interp = static_cast<const uint4*>(m->d_interp);
 	d.tree = static_cast<const uint32_t*>(m->d_tree);
 	d.material_rgb = static_cast<const float*>(m->d_materials);
+	d.regions = static_cast<const FlatRegion*>(m->d_regions);
+	d.region_count = uint32_t(m->flat.regions.size());
 	d.material_count = uint32_t(m->flat.material_rgb.size() / 3 - 1);
 	d.root_interp_offset = m->flat.root_interp_offset;
 	d.root_tree_offset = m->flat.root_tree_offset;
@@ -1411,82 +1559,82 @@ static int FinishAttributes(Model* model, Scratch& scratch, MeshResultDevice* re
 	return TG_OK;
 }
 
-// K0 driver: hierarchical culling from 64-cell bricks down to the list of 8-cell bricks that must be evaluated
-// (plus, for slab runs, the halo bricks of the layer below).  Leaves the list in *out_list, its length in *out_count.
+// K0 driver.  Leaves the list of 8-cell bricks that must be evaluated (plus, for slab runs, the halo bricks of
+// the row below, flagged) in *out_list and its length in *out_count.  No host round trip until the final count.
 static int BuildActiveList(Model* model, cudaStream_t stream, Scratch& scratch, const DeviceGrid& grid, uint32_t k_begin, uint32_t k_end,
 	bool has_halo, bool no_cull, unsigned long long* counters, uint32_t** out_list, uint64_t* out_count, uint64_t& launches, std::string& error)
 {
-	const uint32_t nbx = (grid.sx + kBrick - 1) / kBrick, nby = (grid.sy + kBrick - 1) / kBrick;
+	const uint32_t nbx = (grid.sx + kBrick - 1) / kBrick, nby = (grid.sy + kBrick - 1) / kBrick, nbz = (grid.sz + kBrick - 1) / kBrick;
 	const uint32_t bz_begin = k_begin / kBrick, bz_end = (k_end + kBrick - 1) / kBrick;
-	const size_t own_bricks = size_t(nbx) * nby * (bz_end - bz_begin);
-	const size_t halo_bricks = has_halo ? size_t(nbx) * nby : 0;
-	const size_t list_capacity = own_bricks + halo_bricks + 8;
-	uint32_t *list_a = nullptr, *list_b = nullptr, *active_list = nullptr;
-	TG_CUDA(scratch.Alloc(&list_a, list_capacity));
-	TG_CUDA(scratch.Alloc(&list_b, list_capacity));
+	const uint32_t row_begin = has_halo ? bz_begin - 1 : bz_begin;
+	const size_t slab_bricks = size_t(nbx) * nby * (bz_end - row_begin);
+	const size_t list_capacity = slab_bricks + 8;
+	uint32_t* active_list = nullptr;
 	TG_CUDA(scratch.Alloc(&active_list, list_capacity));
-	unsigned long long host_counts[kCntCount];
+
 	CullParams cp;
 	cp.model = MakeDeviceModel(model);
 	cp.grid = grid;
-	cp.k_begin = k_begin;
-	cp.k_end = k_end;
-	cp.no_cull = no_cull ? 1 : 0;
-	cp.out_capacity = uint32_t(list_capacity);
-	uint64_t active_count = 0;
+	cp.cell_k_lo = has_halo ? k_begin - 1 : k_begin;
+	cp.cell_k_hi = k_end;
+	cp.sample_k_lo = cp.cell_k_lo;
+	cp.sample_k_hi = k_end;
+	uint32_t* counts = nullptr;
+	TG_CUDA(scratch.Alloc(&counts, kCullLevels));
+	cp.counts = counts;
+	size_t flag_words = 0;
+	for (int level = 0; level < kCullLevels; ++level)
 	{
-		// owned bricks: refine from 64-cell bricks down to 8-cell bricks
-		int level = no_cull ? 0 : kTopLevel;
-		const uint32_t width = uint32_t(kBrick) << level;
-		const uint32_t tx = (grid.sx + width - 1) / width, ty = (grid.sy + width - 1) / width;
-		const uint32_t tz0 = k_begin / width, tz1 = (k_end + width - 1) / width;
-		uint32_t count = tx * ty * (tz1 - tz0);
-		InitBrickListKernel<<<(count + 255) / 256, 256, 0, stream>>>(list_a, tx, ty, tz0, tz1 - tz0);
-		launches++;
-		uint32_t* in = list_a;
-		uint32_t* outl = list_b;
-		for (; level >= 0; --level)
-		{
-			cp.in_list = in;
-			cp.in_count = count;
-			cp.level = level;
-			cp.halo = 0;
-			cp.out_list = level == 0 ? active_list : outl;
-			cp.out_counter = counters + (level == 0 ? kCntListA : kCntListB);
-			if (level != 0) TG_CUDA(cudaMemsetAsync(counters + kCntListB, 0, 8, stream));
-			if (count) CullLevelKernel<<<(count + 127) / 128, 128, 0, stream>>>(cp);
-			launches++;
-			if (level != 0)
-			{
-				TG_CUDA(cudaMemcpyAsync(host_counts, counters + kCntListB, 8, cudaMemcpyDeviceToHost, stream));
-				TG_CUDA(cudaStreamSynchronize(stream));
-				count = uint32_t(std::min<unsigned long long>(host_counts[0], list_capacity));
-				std::swap(in, outl);
-			}
-		}
-		if (has_halo)
-		{
-			// the brick layer below the slab: only its top cell layer is classified (vertex ids for our bottom quads)
-			const uint32_t hcount = nbx * nby;
-			InitBrickListKernel<<<(hcount + 255) / 256, 256, 0, stream>>>(list_a, nbx, nby, bz_begin - 1, 1);
-			cp.in_list = list_a;
-			cp.in_count = hcount;
-			cp.level = 0;
-			cp.halo = 1;
-			cp.k_begin = k_begin - 1;
-			cp.k_end = k_begin;
-			cp.out_list = active_list;
-			cp.out_counter = counters + kCntListA;
-			CullLevelKernel<<<(hcount + 127) / 128, 128, 0, stream>>>(cp);
-			launches += 2;
-		}
-		TG_CUDA(cudaMemcpyAsync(host_counts, counters + kCntListA, 8, cudaMemcpyDeviceToHost, stream));
-		TG_CUDA(cudaStreamSynchronize(stream));
-		active_count = std::min<unsigned long long>(host_counts[0], list_capacity);
+		cp.dims[level][0] = (nbx + (1u << level) - 1) >> level;
+		cp.dims[level][1] = (nby + (1u << level) - 1) >> level;
+		cp.dims[level][2] = (nbz + (1u << level) - 1) >> level;
+		flag_words += size_t(cp.dims[level][0]) * cp.dims[level][1] * cp.dims[level][2];
 	}
+	if (!no_cull)
+	{
+		uint32_t* flags = nullptr;
+		TG_CUDA(scratch.Alloc(&flags, flag_words));
+		TG_CUDA(cudaMemsetAsync(flags, 0, flag_words * 4, stream));
+		TG_CUDA(cudaMemsetAsync(counts, 0, kCullLevels * 4, stream));
+		TG_CUDA(scratch.Alloc(&cp.ranges, cp.model.region_count));
+		for (int level = 0; level < kCullLevels; ++level)
+		{
+			cp.flags[level] = flags;
+			flags += size_t(cp.dims[level][0]) * cp.dims[level][1] * cp.dims[level][2];
+			// every region can seed up to 27 items at its start level; splits add at most the bricks of the level below
+			const size_t cells = size_t(cp.dims[level][0]) * cp.dims[level][1] * ((bz_end - row_begin + (1u << level) - 1) >> level);
+			cp.capacity[level] = uint32_t(std::min<size_t>(size_t(cp.model.region_count) * 8 + cells * 4 + 65536, 0x7FFFFFFFu));
+			TG_CUDA(scratch.Alloc(&cp.lists[level], cp.capacity[level]));
+		}
+		cp.level = 0;
+		CullRegionInitKernel<<<(cp.model.region_count + 127) / 128, 128, 0, stream>>>(cp);
+		launches++;
+		// Levels run top-down with grids sized for the level's capacity bound by what can actually arrive
+		// (threads beyond the device-side count exit at once), so no count is read back between levels.
+		uint64_t bound = 0;
+		for (int level = kCullLevels - 1; level >= 0; --level)
+		{
+			const uint64_t seeded = std::min<uint64_t>(uint64_t(cp.model.region_count) * 27u, cp.capacity[level]);
+			bound = std::min<uint64_t>(bound * 8u + seeded, cp.capacity[level]);
+			cp.level = level;
+			CullLevelKernel<<<uint32_t((bound + 127) / 128), 128, 0, stream>>>(cp);
+			launches++;
+		}
+	}
+	else
+	{
+		for (int level = 0; level < kCullLevels; ++level) cp.flags[level] = nullptr;
+	}
+	const uint32_t resolve_threads = uint32_t(slab_bricks);
+	CullResolveKernel<<<(resolve_threads + 255) / 256, 256, 0, stream>>>(cp, row_begin, bz_end, has_halo ? bz_begin - 1 : 0xFFFFFFFFu, no_cull ? 1 : 0,
+		active_list, counters + kCntListA, uint32_t(list_capacity));
+	launches++;
 	TG_CUDA(cudaGetLastError());
+	unsigned long long host_count = 0;
+	TG_CUDA(cudaMemcpyAsync(&host_count, counters + kCntListA, 8, cudaMemcpyDeviceToHost, stream));
+	TG_CUDA(cudaStreamSynchronize(stream));
 	*out_list = active_list;
-	*out_count = active_count;
+	*out_count = std::min<unsigned long long>(host_count, list_capacity);
 	return TG_OK;
 }
 

@@ -53,6 +53,7 @@ public:
 	void* d_interp = nullptr;
 	void* d_tree = nullptr;
 	void* d_materials = nullptr;
+	void* d_regions = nullptr;
 	uint64_t device_bytes = 0;
 	double upload_seconds = 0.0;
 	int leaf_count = 0;

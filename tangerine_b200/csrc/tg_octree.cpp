@@ -2,6 +2,7 @@
 #include "tg_octree.h"
 
 #include <chrono>
+#include <cmath>
 #include <future>
 #include <memory>
 #include <thread>
@@ -379,7 +380,7 @@ struct Flattener
 	int max_slots = 0;
 
 	// Pre-order walk (same order as the octree hash in oracle/ref_tool.cpp) emitting one FlatNode per octree node.
-	uint32_t Walk(const Subtree& st, int32_t index)
+	uint32_t Walk(const Subtree& st, int32_t index, const float (&lo)[3], const float (&hi)[3])
 	{
 		const BuildNode& bn = st.nodes[index];
 		const uint32_t self = uint32_t(model.nodes.size());
@@ -431,19 +432,39 @@ struct Flattener
 		s.hash = Fnv(s.hash, &child_mask, 4);
 		s.hash = Fnv(s.hash, ref_words.data(), words * 4);
 
+		if (bn.terminus)
+		{
+			FlatRegion region = { { lo[0], lo[1], lo[2] }, { hi[0], hi[1], hi[2] }, self, 0 };
+			model.regions.push_back(region);
+			return self;
+		}
+		const float pivot[3] = { bn.pivot.x, bn.pivot.y, bn.pivot.z };
 		for (int i = 0; i < 8; ++i)
 		{
+			// octant i of SDFOctree::Descend: bit set <=> coordinate > pivot
+			float clo[3], chi[3];
+			for (int a = 0; a < 3; ++a)
+			{
+				const bool upper = (i >> a) & 1;
+				clo[a] = upper ? std::fmax(lo[a], pivot[a]) : lo[a];
+				chi[a] = upper ? hi[a] : std::fmin(hi[a], pivot[a]);
+			}
 			const int32_t c = bn.children[i];
-			if (c == -1) continue;
+			if (c == -1)
+			{
+				FlatRegion region = { { clo[0], clo[1], clo[2] }, { chi[0], chi[1], chi[2] }, self, 0 };
+				model.regions.push_back(region);
+				continue;
+			}
 			uint32_t child_index;
 			if (c >= 0)
 			{
-				child_index = Walk(st, c);
+				child_index = Walk(st, c, clo, chi);
 			}
 			else
 			{
 				const Subtree& sub = *st.spawned[size_t(-2 - c)];
-				child_index = Walk(sub, sub.root);
+				child_index = Walk(sub, sub.root, clo, chi);
 			}
 			model.nodes[self].children[i] = int32_t(child_index);
 		}
@@ -514,7 +535,10 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 
 	out.stats.hash = 0xCBF29CE484222325ull;
 	Flattener flattener{ out };
-	flattener.Walk(top, top.root);
+	{
+		const float lo[3] = { -INFINITY, -INFINITY, -INFINITY }, hi[3] = { INFINITY, INFINITY, INFINITY };
+		flattener.Walk(top, top.root, lo, hi);
+	}
 	if (flattener.max_slots > kMaxStackSlots)
 	{
 		error = "CSG tree nests deeper than the device operand stack (" + std::to_string(kMaxStackSlots) + " slots)";

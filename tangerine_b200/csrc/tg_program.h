@@ -125,6 +125,20 @@ struct alignas(16) FlatNode
 };
 static_assert(sizeof(FlatNode) == 64, "FlatNode layout");
 
+// One evaluation region of the octree: the box of points whose SDFOctree::Descend ends at `node` -- the whole
+// cell of a terminus node, or one empty octant of an interior node (the reference then evaluates the interior
+// node's larger program there, sdf_evaluator.cpp:1828-1834).  A point belongs to the region when
+// lo < p <= hi on every axis (the strict `>` of the pivot tests, :1806-1817); the octree root is unbounded.
+// The regions partition space; empty-space culling (K0) walks them instead of the grid.
+struct FlatRegion
+{
+	float lo[3];
+	float hi[3];
+	uint32_t node;
+	uint32_t pad;
+};
+static_assert(sizeof(FlatRegion) == 32, "FlatRegion layout");
+
 constexpr uint32_t kNodeCullable = 1u; // every primitive in the program is a true distance bound (no Ellipsoid)
 
 } // namespace tg
