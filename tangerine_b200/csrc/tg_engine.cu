@@ -459,6 +459,10 @@ __global__ void __launch_bounds__(kBrickThreads) LatticeKernel(const DeviceModel
 // ------------------------------------------------------------------------------------------------
 
 constexpr int kCullLevels = 5; // 8, 16, 32, 64, 128 cells
+#ifndef TG_SEED_SPAN
+#define TG_SEED_SPAN 8
+#endif
+constexpr uint32_t kSeedSpan = TG_SEED_SPAN; // a region is seeded at the finest level where it spans fewer bricks than this per axis
 constexpr uint32_t kFlagPositive = 1u, kFlagNegative = 2u, kFlagEvaluate = 4u;
 
 struct CullItem
@@ -518,6 +522,20 @@ __device__ __forceinline__ uint32_t WarpAppend(uint32_t* counter, uint32_t n, bo
 	return base + incl - n;
 }
 
+// True when the sample box [lo, hi] lies within the ball around an empty octant's centre in which the octree build
+// has shown the region's program to be positive (FlatRegion::known_value), with the same slack as the evaluated test.
+__device__ __forceinline__ bool KnownEmpty(const DeviceModel& model, const FlatRegion& region, const DeviceGrid& g,
+	uint32_t lo_i, uint32_t hi_i, uint32_t lo_j, uint32_t hi_j, uint32_t lo_k, uint32_t hi_k)
+{
+	if (!(region.known_value > 0.0f)) return false;
+	if ((__ldg(&model.nodes[region.node].flags) & kNodeCullable) == 0u) return false;
+	const float dx = fmaxf(fabsf(LatticeCoord(g.x, g.dx, lo_i) - region.center[0]), fabsf(LatticeCoord(g.x, g.dx, hi_i) - region.center[0]));
+	const float dy = fmaxf(fabsf(LatticeCoord(g.y, g.dy, lo_j) - region.center[1]), fabsf(LatticeCoord(g.y, g.dy, hi_j) - region.center[1]));
+	const float dz = fmaxf(fabsf(LatticeCoord(g.z, g.dz, lo_k) - region.center[2]), fabsf(LatticeCoord(g.z, g.dz, hi_k) - region.center[2]));
+	const float reach = sqrtf(dx * dx + dy * dy + dz * dz);
+	return region.known_value > reach * 1.001f + 1.0e-4f;
+}
+
 __global__ void __launch_bounds__(128) CullRegionInitKernel(const CullParams p)
 {
 	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -563,11 +581,20 @@ __global__ void __launch_bounds__(128) CullRegionInitKernel(const CullParams p)
 	for (; level < kCullLevels - 1; ++level)
 	{
 		const int sh = 3 + level;
-		if ((chi[0] >> sh) - (clo[0] >> sh) < 3u && (chi[1] >> sh) - (clo[1] >> sh) < 3u && (chi[2] >> sh) - (clo[2] >> sh) < 3u) break;
+		if ((chi[0] >> sh) - (clo[0] >> sh) < kSeedSpan && (chi[1] >> sh) - (clo[1] >> sh) < kSeedSpan && (chi[2] >> sh) - (clo[2] >> sh) < kSeedSpan) break;
 	}
 	const int sh = 3 + level;
 	const uint32_t x0 = clo[0] >> sh, x1 = chi[0] >> sh, y0 = clo[1] >> sh, y1 = chi[1] >> sh, z0 = clo[2] >> sh, z1 = chi[2] >> sh;
 	const uint32_t n = (x1 - x0 + 1u) * (y1 - y0 + 1u) * (z1 - z0 + 1u);
+	if (KnownEmpty(p.model, region, g, a[0], b[0], a[1], b[1], a[2], b[2]))
+	{
+		// the octree build already proved this whole region empty (outside): flag its bricks, queue nothing
+		for (uint32_t z = z0; z <= z1; ++z)
+			for (uint32_t y = y0; y <= y1; ++y)
+				for (uint32_t x = x0; x <= x1; ++x)
+					atomicOr(&p.flags[level][(size_t(z) * p.dims[level][1] + y) * p.dims[level][0] + x], kFlagPositive);
+		return;
+	}
 	const uint32_t base = atomicAdd(&p.counts[level], n);
 	if (base + n > p.capacity[level])
 	{
@@ -611,6 +638,11 @@ __global__ void __launch_bounds__(128) CullLevelKernel(const CullParams p)
 		live = lo_i <= hi_i && lo_j <= hi_j && lo_k <= hi_k;
 	}
 	uint32_t* flag = &p.flags[level][(size_t(cz) * p.dims[level][1] + cy) * p.dims[level][0] + cx];
+	if (live && KnownEmpty(p.model, p.model.regions[item.region], g, lo_i, hi_i, lo_j, hi_j, lo_k, hi_k))
+	{
+		atomicOr(flag, kFlagPositive);
+		live = false; // decided without running the program
+	}
 	if (live)
 	{
 		const uint32_t node = p.model.regions[item.region].node;
@@ -1614,7 +1646,7 @@ static int BuildActiveList(Model* model, cudaStream_t stream, Scratch& scratch, 
 		uint64_t bound = 0;
 		for (int level = kCullLevels - 1; level >= 0; --level)
 		{
-			const uint64_t seeded = std::min<uint64_t>(uint64_t(cp.model.region_count) * 27u, cp.capacity[level]);
+			const uint64_t seeded = std::min<uint64_t>(uint64_t(cp.model.region_count) * kSeedSpan * kSeedSpan * kSeedSpan, cp.capacity[level]);
 			bound = std::min<uint64_t>(bound * 8u + seeded, cp.capacity[level]);
 			cp.level = level;
 			CullLevelKernel<<<uint32_t((bound + 127) / 128), 128, 0, stream>>>(cp);

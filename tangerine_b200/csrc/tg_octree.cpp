@@ -22,6 +22,11 @@ struct BuildNode
 	bool terminus = false;
 	uint32_t evaluator = kNoNode; // index into the owning Subtree's pool
 	int32_t evaluator_leaves = 0;
+	// Empty octants (children[i] == -1) whose subtree the clip removed outright: the parent's program, evaluated at
+	// the octant's centre empty_center[i], was empty_value[i] > the octant's half diagonal.  0 = nothing known.
+	float clip_value = 0.0f;  // value of the parent's program at this node's pivot, when the clip pruned everything
+	Vec3 empty_center[8];
+	float empty_value[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 	// >= 0: index into Subtree::nodes; -1: empty octant; <= -2: root of Subtree::spawned[-2 - value]
 	int32_t children[8] = { -1, -1, -1, -1, -1, -1, -1, -1 };
 };
@@ -48,9 +53,11 @@ struct Builder
 		float span = std::fmax(std::fmax(extent.x, extent.y), extent.z);
 		Vec3 pivot = Vec3(float(span * 0.5)) + bounds.min;
 		float radius = float(Length(Vec3(span)) * 0.5);
-		uint32_t evaluator = st.pool.Clip(in_evaluator, pivot, radius);
+		float clip_value = 0.0f;
+		uint32_t evaluator = st.pool.Clip(in_evaluator, pivot, radius, &clip_value);
 		{
 			BuildNode& n = st.nodes[self];
+			n.clip_value = evaluator == kNoNode && clip_value > radius ? clip_value : 0.0f;
 			n.bounds = bounds;
 			n.pivot = pivot;
 			n.evaluator = evaluator;
@@ -111,6 +118,11 @@ struct Builder
 					st.nodes[self].children[i] = -2 - int32_t(st.spawned.size());
 					st.spawned.push_back(std::move(child));
 				}
+				else
+				{
+					st.nodes[self].empty_center[i] = cn.pivot;
+					st.nodes[self].empty_value[i] = cn.clip_value;
+				}
 			}
 		}
 		else
@@ -125,6 +137,13 @@ struct Builder
 					penultimate &= cn.terminus;
 					live++;
 					st.nodes[self].children[i] = child;
+				}
+				else
+				{
+					const Vec3 child_pivot = cn.pivot;
+					const float child_value = cn.clip_value;
+					st.nodes[self].empty_center[i] = child_pivot;
+					st.nodes[self].empty_value[i] = child_value;
 				}
 			}
 		}
@@ -434,7 +453,7 @@ struct Flattener
 
 		if (bn.terminus)
 		{
-			FlatRegion region = { { lo[0], lo[1], lo[2] }, { hi[0], hi[1], hi[2] }, self, 0 };
+			FlatRegion region = { { lo[0], lo[1], lo[2] }, { hi[0], hi[1], hi[2] }, { 0.0f, 0.0f, 0.0f }, 0.0f, self, 0 };
 			model.regions.push_back(region);
 			return self;
 		}
@@ -452,7 +471,8 @@ struct Flattener
 			const int32_t c = bn.children[i];
 			if (c == -1)
 			{
-				FlatRegion region = { { clo[0], clo[1], clo[2] }, { chi[0], chi[1], chi[2] }, self, 0 };
+				const Vec3 ec = bn.empty_center[i];
+				FlatRegion region = { { clo[0], clo[1], clo[2] }, { chi[0], chi[1], chi[2] }, { ec.x, ec.y, ec.z }, bn.empty_value[i], self, 0 };
 				model.regions.push_back(region);
 				continue;
 			}

@@ -130,14 +130,21 @@ static_assert(sizeof(FlatNode) == 64, "FlatNode layout");
 // node's larger program there, sdf_evaluator.cpp:1828-1834).  A point belongs to the region when
 // lo < p <= hi on every axis (the strict `>` of the pivot tests, :1806-1817); the octree root is unbounded.
 // The regions partition space; empty-space culling (K0) walks them instead of the grid.
+//
+// For an empty octant the octree build has already evaluated the interior node's program at the octant's centre:
+// SDFNode::Clip (sdf_evaluator.cpp:782-850, 468-478) returns null exactly when that value exceeds the octant's half
+// diagonal.  `known_value` keeps it (0 when nothing is known), so culling can dismiss every brick within
+// known_value of `center` without running the (large) program again.
 struct FlatRegion
 {
 	float lo[3];
 	float hi[3];
+	float center[3];
+	float known_value;
 	uint32_t node;
 	uint32_t pad;
 };
-static_assert(sizeof(FlatRegion) == 32, "FlatRegion layout");
+static_assert(sizeof(FlatRegion) == 48, "FlatRegion layout");
 
 constexpr uint32_t kNodeCullable = 1u; // every primitive in the program is a true distance bound (no Ellipsoid)
 

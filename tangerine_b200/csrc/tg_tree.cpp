@@ -176,16 +176,20 @@ float NodePool::Eval(uint32_t index, Vec3 point) const
 
 // Clip: brush :468-478, set :782-850, flate :1064-1075, stencil :603-615.  Brushes are immutable, so
 // the reference's Copy() of a surviving brush is the brush's own index here.
-uint32_t NodePool::Clip(uint32_t index, Vec3 point, float radius)
+uint32_t NodePool::Clip(uint32_t index, Vec3 point, float radius, float* top_value)
 {
 	const uint32_t kind = nodes[index].kind;
 	if (IsBrush(kind))
 	{
-		return Eval(index, point) <= radius ? index : kNoNode;
+		const float value = Eval(index, point);
+		if (top_value) *top_value = value;
+		return value <= radius ? index : kNoNode;
 	}
 	if (IsSet(kind))
 	{
-		if (!(Eval(index, point) <= radius))
+		const float value = Eval(index, point);
+		if (top_value) *top_value = value;
+		if (!(value <= radius))
 		{
 			return kNoNode;
 		}
@@ -225,7 +229,9 @@ uint32_t NodePool::Clip(uint32_t index, Vec3 point, float radius)
 	}
 	if (kind == kKindFlate)
 	{
-		if (!(Eval(index, point) <= radius))
+		const float value = Eval(index, point);
+		if (top_value) *top_value = value;
+		if (!(value <= radius))
 		{
 			return kNoNode;
 		}
@@ -233,6 +239,7 @@ uint32_t NodePool::Clip(uint32_t index, Vec3 point, float radius)
 		uint32_t child = Clip(nodes[index].a, point, radius + flate);
 		return child == kNoNode ? kNoNode : AddFlate(child, flate);
 	}
+	if (top_value) *top_value = Eval(index, point);
 	uint32_t child = Clip(nodes[index].a, point, radius);
 	return child == kNoNode ? kNoNode : AddStencil(kind, child, nodes[index].b, nodes[index].material);
 }

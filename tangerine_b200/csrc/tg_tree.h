@@ -92,7 +92,8 @@ struct NodePool
 	uint32_t AddStencil(uint32_t kind, uint32_t child, uint32_t mask, uint32_t material);
 
 	float Eval(uint32_t index, Vec3 point) const;                 // virtual Eval
-	uint32_t Clip(uint32_t index, Vec3 point, float radius);      // virtual Clip; kNoNode when pruned away
+	// top_value (optional): receives this node's own value at `point`, which the clip computes anyway
+	uint32_t Clip(uint32_t index, Vec3 point, float radius, float* top_value = nullptr);      // virtual Clip; kNoNode when pruned away
 	bool Equal(uint32_t x, uint32_t y) const;                     // operator==
 	Box3 Bounds(uint32_t index) const;                            // Bounds()
 	Box3 InnerBounds(uint32_t index) const;                       // InnerBounds()
