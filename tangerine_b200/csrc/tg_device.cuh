@@ -79,7 +79,7 @@ __device__ __forceinline__ uint32_t Descend(const FlatNode* __restrict__ nodes, 
 // Every fetch is a 128-bit load whose address does not depend on another fetch of the same instruction, and the
 // first quad of the next instruction is requested before this instruction's arithmetic starts.  The operator
 // switch sits outside the per-sample loops, so with a warp-uniform program there is one dispatch per brush.
-template <int S>
+template <int S, bool PREFETCH = false>
 __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const float (&px)[S], const float (&py)[S], const float (&pz)[S], float (&result)[S])
 {
 	float acc[S];
@@ -94,6 +94,7 @@ __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const f
 		const uint32_t op = (header >> kHdrOpShift) & 0xFu;
 		const uint32_t slot = (header >> kHdrSlotShift) & 0xFFu;
 		const uint4* next = pc + (header >> kHdrLenShift);
+		if (PREFETCH) asm volatile("prefetch.global.L1 [%0];" ::"l"(pc + 32)); // 512 B ahead: long programs stream from L2 / HBM
 		if (brush != kBrushNone)
 		{
 			const float p0 = __uint_as_float(q.y), p1 = __uint_as_float(q.z), p2 = __uint_as_float(q.w);
@@ -267,7 +268,7 @@ __device__ __forceinline__ float EvalInterp1(const DeviceModel& model, uint32_t 
 {
 	const float px[1] = { x }, py[1] = { y }, pz[1] = { z };
 	float out[1];
-	EvalInterp<1>(model.interp + (word_offset >> 2), px, py, pz, out);
+	EvalInterp<1, true>(model.interp + (word_offset >> 2), px, py, pz, out);
 	return out[0];
 }
 

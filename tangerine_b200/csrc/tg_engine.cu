@@ -643,7 +643,10 @@ __global__ void __launch_bounds__(128) CullLevelKernel(const CullParams p)
 		atomicOr(flag, kFlagPositive);
 		live = false; // decided without running the program
 	}
-	if (live)
+	// An empty octant runs its parent's large program: once the known ball has failed, do not pay for it at every
+	// level on the way down -- split to the 8-cell bricks and evaluate there, once.
+	const bool defer = level > 0 && p.model.regions[item.region].known_value > 0.0f;
+	if (live && !defer)
 	{
 		const uint32_t node = p.model.regions[item.region].node;
 		if (__ldg(&p.model.nodes[node].flags) & kNodeCullable)
@@ -1343,25 +1346,37 @@ void Context::ReleasePinned(void* ptr)
 	}
 }
 
+// Copies one table host -> device.  The device allocation and a page-locked staging copy of the host vector are
+// made on first use and kept for the model's lifetime, so a repeated upload (tg_model_upload) is a plain async copy.
 template <typename T>
-static int UploadVector(Context* c, const std::vector<T>& v, void** out, uint64_t& bytes_total, std::string& error)
+static int UploadVector(Context* c, const std::vector<T>& v, void** device, void** staging, uint64_t& bytes_total, std::string& error)
 {
-	const size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
-	TG_CUDA(cudaMalloc(out, bytes));
-	TG_CUDA(cudaMemcpyAsync(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, StreamOf(c)));
+	const size_t payload = v.size() * sizeof(T);
+	const size_t bytes = std::max<size_t>(payload, 16);
+	if (!*device)
+	{
+		TG_CUDA(cudaMalloc(device, bytes));
+		TG_CUDA(cudaMallocHost(staging, bytes));
+		std::memcpy(*staging, v.data(), payload);
+	}
+	TG_CUDA(cudaMemcpyAsync(*device, *staging, payload, cudaMemcpyHostToDevice, StreamOf(c)));
 	bytes_total += bytes;
 	return TG_OK;
 }
 
 static void FreeModelTables(Model* m)
 {
-	cudaFree(m->d_nodes);
-	cudaFree(m->d_interp);
-	cudaFree(m->d_tree);
-	cudaFree(m->d_materials);
-	cudaFree(m->d_regions);
-	m->d_regions = nullptr;
-	m->d_nodes = m->d_interp = m->d_tree = m->d_materials = nullptr;
+	void** tables[] = { &m->d_nodes, &m->d_interp, &m->d_tree, &m->d_materials, &m->d_regions };
+	for (void** t : tables)
+	{
+		cudaFree(*t);
+		*t = nullptr;
+	}
+	for (void*& h : m->staging)
+	{
+		cudaFreeHost(h);
+		h = nullptr;
+	}
 	m->device_bytes = 0;
 }
 
@@ -1369,14 +1384,13 @@ static int UploadModel(Model* m, std::string& error)
 {
 	Context* c = m->context;
 	TG_CUDA(cudaSetDevice(c->device));
-	TG_CUDA(cudaStreamSynchronize(StreamOf(c)));
-	FreeModelTables(m);
+	m->device_bytes = 0;
 	int rc;
-	if ((rc = UploadVector(c, m->flat.nodes, &m->d_nodes, m->device_bytes, error)) != TG_OK) return rc;
-	if ((rc = UploadVector(c, m->flat.interp, &m->d_interp, m->device_bytes, error)) != TG_OK) return rc;
-	if ((rc = UploadVector(c, m->flat.tree, &m->d_tree, m->device_bytes, error)) != TG_OK) return rc;
-	if ((rc = UploadVector(c, m->flat.material_rgb, &m->d_materials, m->device_bytes, error)) != TG_OK) return rc;
-	if ((rc = UploadVector(c, m->flat.regions, &m->d_regions, m->device_bytes, error)) != TG_OK) return rc;
+	if ((rc = UploadVector(c, m->flat.nodes, &m->d_nodes, &m->staging[0], m->device_bytes, error)) != TG_OK) return rc;
+	if ((rc = UploadVector(c, m->flat.interp, &m->d_interp, &m->staging[1], m->device_bytes, error)) != TG_OK) return rc;
+	if ((rc = UploadVector(c, m->flat.tree, &m->d_tree, &m->staging[2], m->device_bytes, error)) != TG_OK) return rc;
+	if ((rc = UploadVector(c, m->flat.material_rgb, &m->d_materials, &m->staging[3], m->device_bytes, error)) != TG_OK) return rc;
+	if ((rc = UploadVector(c, m->flat.regions, &m->d_regions, &m->staging[4], m->device_bytes, error)) != TG_OK) return rc;
 	TG_CUDA(cudaStreamSynchronize(StreamOf(c)));
 	return TG_OK;
 }

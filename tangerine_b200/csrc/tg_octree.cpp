@@ -583,7 +583,7 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 			return false;
 		}
 	}
-	for (int i = 0; i < 4; ++i) out.interp.push_back(0); // the interpreter prefetches one quad past an instruction
+	for (int i = 0; i < 4 * 40; ++i) out.interp.push_back(0); // the interpreter fetches one quad and prefetches 512 B past an instruction
 	SnapshotMaterials(out.material_rgb);
 	out.material_rgb.push_back(1.0f); // default material (GetDefaultMaterial :34-38), addressed by kNoMaterial
 	out.material_rgb.push_back(1.0f);

@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""Per-launch times of the n-th export in an `ncu --metrics gpu__time_duration.sum --csv` log:  launch_list.py <csv> [n]"""
+import csv
+import sys
+
+rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 5]
+which = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+hdr = None
+out = []
+for r in rows:
+    if r[0] == 'ID':
+        hdr = r
+        continue
+    if hdr is None:
+        continue
+    d = dict(zip(hdr, r))
+    v = float(d['Metric Value'].replace(',', ''))
+    u = d['Metric Unit']
+    v = v / 1e3 if u == 'ns' else v * 1e3 if u == 'ms' else v
+    out.append((d['Kernel Name'][:56], v, d.get('Grid Size', '')))
+idx = [i for i, o in enumerate(out) if o[0].startswith('CullRegionInit') or o[0].startswith('CullResolve') and (i == 0 or not out[i - 1][0].startswith('Cull'))]
+idx.append(len(out))
+s, e = idx[which], idx[which + 1]
+total = sum(o[1] for o in out[s:e])
+for o in out[s:e]:
+    print("%-58s %9.1f us  %5.1f%%  grid %s" % (o[0], o[1], 100 * o[1] / total, o[2]))
+print("total %.1f us" % total)
