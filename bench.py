@@ -213,12 +213,16 @@ def main():
     stats = model.stats()
     flags = T.MESH_NORMALS | T.MESH_COLORS | (T.MESH_NO_CULL if args.no_cull else 0)
 
-    # z-slab partition: balanced on the active-brick profile of the whole grid (a cull-only pass every rank repeats)
+    # z-slab partition.  First cut: the cull-only work estimate every rank computes identically (tg_brick_profile).
+    # After the first warm-up export the measured per-layer vertex cost (sum of program FLOPs over a layer's vertices) and stage times are all-reduced and the
+    # cut is redone on cost = eval_rate * brick_weight + vertex_rate * vertex_cost (same inputs on every rank, so
+    # no further communication is needed to agree on it).
     if world > 1:
-        profile = model.brick_profile(grid)
+        profile = model.brick_profile(grid).astype(np.float64)
         slabs = balanced_slabs(profile, world, sz)
         slab = slabs[rank]
     else:
+        profile = None
         slabs = [(0, sz)]
         slab = None
 
@@ -251,8 +255,22 @@ def main():
         mesh.close()
         return t
 
-    for _ in range(args.warmup):
-        device_step()
+    for w in range(args.warmup):
+        mesh = model.export_mesh(grid, flags=flags | T.MESH_DEVICE_ONLY, refine=refine, slab=slab)
+        if world > 1 and w == 0:
+            tm = mesh.timings
+            lo_b, hi_b = slab[0] // 8, (slab[1] + 7) // 8
+            mine = np.zeros(len(profile) + 4, np.float64)
+            mine[:len(profile)] = mesh.layer_vertex_cost[:len(profile)]
+            mine[-4:] = [tm["evaluate_ms"] + tm["cull_ms"], profile[lo_b:hi_b].sum(), tm["compact_ms"] + tm["faces_ms"] + tm["attributes_ms"], mesh.layer_vertex_cost.sum()]
+            t = torch.from_numpy(mine).cuda()
+            dist.all_reduce(t)
+            allv = t.cpu().numpy()
+            eval_rate = allv[-4] / max(allv[-3], 1.0)
+            vertex_rate = allv[-2] / max(allv[-1], 1.0)
+            slabs = balanced_slabs(eval_rate * profile + vertex_rate * allv[:len(profile)], world, sz)
+            slab = slabs[rank]
+        mesh.close()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -267,16 +285,17 @@ def main():
 
     # ---- end to end through the C ABI with host buffers (`e2e`) ------------------------------------------
     def e2e_step():
-        model.upload()                                  # host -> device: octree table + instruction streams
-        mesh = model.export_mesh(grid, flags=flags, refine=refine, slab=slab)   # device -> host: pinned result arrays
-        counts = np.array([mesh.vertex_count, mesh.triangle_count], np.int64)
-        if world > 1:
+        model.upload()                                  # host -> device: octree table, regions, both instruction streams
+        if world == 1:
+            mesh = model.export_mesh(grid, flags=flags, refine=refine)      # device -> host: pinned result arrays
+        else:
+            mesh = model.export_mesh(grid, flags=flags | T.MESH_DEVICE_ONLY, refine=refine, slab=slab)
             # the one exchange of the path: per-slab counts -> exclusive prefix -> global vertex ids
+            counts = torch.tensor([mesh.vertex_count, mesh.triangle_count], dtype=torch.int64, device="cuda")
             gathered = torch.zeros((world, 2), dtype=torch.int64, device="cuda")
-            dist.all_gather_into_tensor(gathered, torch.from_numpy(counts).cuda())
+            dist.all_gather_into_tensor(gathered, counts)
             base = int(gathered[:rank, 0].sum().item())
-            if mesh.triangle_count:
-                np.add(mesh.triangles, np.uint32(base), out=mesh.triangles)
+            mesh.download(index_base=base)              # rebase on the device, then device -> host
         d2h = mesh.vertex_count * (12 + 12 + (3 if mesh.colors is not None else 0)) + mesh.triangle_count * 12
         v, f = mesh.vertex_count, mesh.triangle_count
         mesh.close()
@@ -372,7 +391,7 @@ def main():
             "stage_ms_rank0": {k: mean(k) for k in ("cull_ms", "evaluate_ms", "compact_ms", "faces_ms", "attributes_ms", "total_device_ms")},
             "model_build_s": model_seconds, "octree_nodes": stats["octree_nodes"],
             "e2e": {"value": e2e_value, "unit": "Mvoxel/s", "ms_per_step": e2e_wall_ms / args.steps, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
-                    "timed": "host wall clock around tg_model_upload + tg_export_mesh (pinned host results)%s, max over ranks" % (" + count all-gather + index rebase" if world > 1 else ""),
+                    "timed": "host wall clock around tg_model_upload + tg_export_mesh (pinned host results)%s, max over ranks" % (" + NCCL count all-gather + tg_mesh_download (index rebase on device)" if world > 1 else ""),
                     "device_ms_per_step_rank0": e2e_dev_ms / args.steps},
             "gpu_launches": launches,
             "roofline": roofline,

@@ -224,12 +224,21 @@ typedef struct tg_mesh
 	 * the slab (owned by the previous rank) and are not part of positions[]; triangle indices are local
 	 * numbers minus halo_vertices, so adding the previous ranks' vertex total makes them global. */
 	uint64_t halo_vertices;
+	/* Owned vertices per 8-layer brick layer of the grid (absolute layer index, 0 outside the slab): the measured
+	 * profile a multi-GPU driver feeds back into its next slab cut (bench.py).  layer_count = ceil(sz / 8). */
+	uint32_t* layer_vertices;
+	double* layer_vertex_cost; /* same indexing: sum over the layer's vertices of their octree node's program FLOPs */
+	uint64_t layer_count;
 	tg_mesh_timings timings;
 	void* opaque;
 } tg_mesh;
 
 TG_API int tg_export_mesh(tg_model* model, const tg_grid* grid, const tg_mesh_options* options, tg_mesh* out);
 TG_API void tg_mesh_free(tg_mesh* mesh);
+/* Second half of a TG_MESH_DEVICE_ONLY export: adds index_base to every triangle index on the device (multi-GPU:
+ * the vertex total of the lower ranks, known once the per-slab counts were exchanged) and copies the arrays into
+ * library-owned pinned host memory, filling the NULL pointers of *mesh. */
+TG_API int tg_mesh_download(tg_mesh* mesh, uint32_t index_base);
 
 /* Raw lattice samples of the grid through SDFOctree::Eval: (sx+1)*(sy+1)*(sz+1) floats, x fastest.
  * `out` may be NULL to time the evaluator alone; elapsed device milliseconds are returned in *out_ms. */
@@ -280,9 +289,10 @@ TG_API int tg_measure_fp32_peak(tg_context* context, double* out_tflops);
 TG_API int tg_flush_l2(tg_context* context);
 TG_API int tg_context_synchronize(tg_context* context);
 
-/* Multi-GPU partitioning: number of 8^3-cell bricks that survive culling in each brick layer
- * (layer b = cell layers [8b, 8b+8)); out_layers needs ceil(sz / 8) entries.  Every rank computes the same
- * profile and cuts the grid into z-slabs of equal work without communicating. */
+/* Multi-GPU partitioning: estimated work in each brick layer (layer b = cell layers [8b, 8b+8)):
+ * every 8^3-cell brick that survives culling counts 64 + the FLOPs of the program at its centre; out_layers needs
+ * ceil(sz / 8) entries.  Every rank computes the same profile and cuts the grid into z-slabs of equal work
+ * without communicating. */
 TG_API int tg_brick_profile(tg_model* model, const tg_grid* grid, uint32_t* out_layers, uint32_t layer_count);
 
 #ifdef __cplusplus

@@ -65,6 +65,7 @@ class _Mesh(C.Structure):
     _fields_ = [("positions", C.POINTER(C.c_float)), ("normals", C.POINTER(C.c_float)), ("colors", C.POINTER(C.c_uint8)),
                 ("triangles", C.POINTER(C.c_uint32)), ("face_normals", C.POINTER(C.c_float)),
                 ("vertex_count", C.c_uint64), ("triangle_count", C.c_uint64), ("halo_vertices", C.c_uint64),
+                ("layer_vertices", C.POINTER(C.c_uint32)), ("layer_vertex_cost", C.POINTER(C.c_double)), ("layer_count", C.c_uint64),
                 ("timings", MeshTimings), ("opaque", C.c_void_p)]
 
 
@@ -146,6 +147,7 @@ def lib():
         "tg_export_grid": (i32, [fp, fp, fp, C.POINTER(Grid)]),
         "tg_export_mesh": (i32, [vp, C.POINTER(Grid), C.POINTER(MeshOptions), C.POINTER(_Mesh)]),
         "tg_mesh_free": (None, [C.POINTER(_Mesh)]),
+        "tg_mesh_download": (i32, [C.POINTER(_Mesh), u32]),
         "tg_eval_lattice": (i32, [vp, C.POINTER(Grid), fp, fp]),
         "tg_export_points": (i32, [vp, fp, fp, fp, i32, u32, C.POINTER(_Mesh)]),
         "tg_export_voxels": (i32, [vp, C.c_float, C.POINTER(C.c_int32), fp, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(u64)]),
@@ -396,6 +398,19 @@ class Mesh:
 
     def __init__(self, raw):
         self.raw = raw
+        self.layer_vertices = (np.ctypeslib.as_array(raw.layer_vertices, shape=(int(raw.layer_count),)).copy()
+                               if raw.layer_vertices and raw.layer_count else np.zeros(0, np.uint32))
+        self.layer_vertex_cost = (np.ctypeslib.as_array(raw.layer_vertex_cost, shape=(int(raw.layer_count),)).copy()
+                                  if raw.layer_vertex_cost and raw.layer_count else np.zeros(0, np.float64))
+        self._bind()
+
+    def download(self, index_base=0):
+        """Bring a MESH_DEVICE_ONLY result to the host, adding index_base to the triangle indices on the device."""
+        _check(lib().tg_mesh_download(C.byref(self.raw), int(index_base) & 0xFFFFFFFF))
+        self._bind()
+
+    def _bind(self):
+        raw = self.raw
         nv, nt = int(raw.vertex_count), int(raw.triangle_count)
         self.vertex_count, self.triangle_count = nv, nt
         self.halo_vertices = int(raw.halo_vertices)

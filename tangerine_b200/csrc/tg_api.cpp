@@ -643,6 +643,14 @@ int tg_flush_l2(tg_context* context)
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
 
+int tg_mesh_download(tg_mesh* mesh, uint32_t index_base)
+{
+	if (!mesh) return Fail(TG_ERR_INVALID, "null mesh");
+	std::string error;
+	int rc = EngineDownloadMesh(mesh, index_base, error);
+	return rc == TG_OK ? rc : Fail(rc, error);
+}
+
 int tg_context_synchronize(tg_context* context)
 {
 	if (!context) return Fail(TG_ERR_INVALID, "null context");

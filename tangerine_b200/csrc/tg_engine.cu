@@ -18,6 +18,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include <cuda_runtime.h>
@@ -737,10 +738,17 @@ __global__ void __launch_bounds__(256) CullResolveKernel(const CullParams p, uin
 	}
 }
 
-__global__ void BrickLayerHistogramKernel(const uint32_t* __restrict__ list, uint32_t count, uint32_t* __restrict__ layers)
+// Estimated work per brick layer: every active brick weighs in with the FLOPs of the program at its centre (evaluation
+// and per-vertex attributes both scale with it) plus a constant for descent / classification.
+__global__ void BrickLayerHistogramKernel(const DeviceModel model, const DeviceGrid grid, const uint32_t* __restrict__ list, uint32_t count, uint32_t* __restrict__ layers)
 {
 	const uint32_t index = blockIdx.x * blockDim.x + threadIdx.x;
-	if (index < count) atomicAdd(&layers[(list[index] >> 20) & 1023u], 1u);
+	if (index >= count) return;
+	const uint32_t brick = list[index];
+	const uint32_t bx = brick & 1023u, by = (brick >> 10) & 1023u, bz = (brick >> 20) & 1023u;
+	const uint32_t node = Descend(model.nodes, 0, LatticeCoord(grid.x, grid.dx, bx * kBrick + kBrick / 2), LatticeCoord(grid.y, grid.dy, by * kBrick + kBrick / 2),
+		LatticeCoord(grid.z, grid.dz, bz * kBrick + kBrick / 2));
+	atomicAdd(&layers[bz], 64u + __ldg(&model.nodes[node].flops));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -864,7 +872,7 @@ struct FaceParams
 	uint32_t row_words;
 	uint32_t sy;
 	uint32_t k_base;
-	uint32_t halo_vertices;
+	const uint32_t* halo_ptr; // device: number of vertices in the halo layer (first in the local numbering); null = 0
 	const float4* tmp_pos;
 	const unsigned long long* tmp_key;
 	uint32_t tmp_count;
@@ -900,7 +908,7 @@ __global__ void __launch_bounds__(256) ScatterVerticesKernel(const FaceParams p)
 	const unsigned long long row = key / row_bits;
 	const uint32_t j = uint32_t(row % p.sy), layer = uint32_t(row / p.sy);
 	const unsigned long long word = p.bitmap[key >> 6];
-	const uint32_t id = p.prefix[key >> 6] + uint32_t(__popcll(word & ((1ull << (key & 63ull)) - 1ull))) - p.halo_vertices;
+	const uint32_t id = p.prefix[key >> 6] + uint32_t(__popcll(word & ((1ull << (key & 63ull)) - 1ull))) - (p.halo_ptr ? __ldg(p.halo_ptr) : 0u);
 	p.positions[size_t(id) * 3 + 0] = pos.x;
 	p.positions[size_t(id) * 3 + 1] = pos.y;
 	p.positions[size_t(id) * 3 + 2] = pos.z;
@@ -932,7 +940,7 @@ __global__ void __launch_bounds__(256) EmitTrianglesKernel(const FaceParams p)
 	const unsigned long long row = key / row_bits;
 	const uint32_t j = uint32_t(row % p.sy), layer = uint32_t(row / p.sy);
 	uint32_t out = p.quad_offset[v] * 6u;
-	const uint32_t h = p.halo_vertices;
+	const uint32_t h = p.halo_ptr ? __ldg(p.halo_ptr) : 0u;
 #pragma unroll
 	for (int e = 0; e < 3; ++e)
 	{
@@ -982,6 +990,10 @@ struct AttributeParams
 	int refine_iterations;
 	float half_x, half_y, half_z;
 	float scale;
+	// measured work profile for slab balancing: sum of program FLOPs of the vertices of each brick layer
+	unsigned long long* layer_cost; // may be null
+	float grid_z, grid_dz;
+	uint32_t layer_count;
 };
 
 __device__ __forceinline__ void ExportColor(const DeviceModel& model, uint32_t node, float x, float y, float z, unsigned char* out)
@@ -1036,6 +1048,17 @@ __global__ void __launch_bounds__(128) AttributesKernel(const AttributeParams p)
 		}
 	}
 	const uint32_t node = Descend(model.nodes, 0, x, y, z);
+	if (p.layer_cost)
+	{
+		// one atomic per distinct brick layer in the warp (vertices are in (k, j, i) order: usually one)
+		const float cell = (z - p.grid_z) / p.grid_dz;
+		const uint32_t layer = min(uint32_t(fmaxf(cell, 0.0f)) / uint32_t(kBrick), p.layer_count - 1u);
+		const uint32_t flops = __ldg(&model.nodes[node].flops);
+		const unsigned active = __activemask();
+		const unsigned peers = __match_any_sync(active, layer);
+		const uint32_t sum = __reduce_add_sync(peers, flops);
+		if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&p.layer_cost[layer], (unsigned long long)sum);
+	}
 	if (p.normals)
 	{
 		float gx, gy, gz;
@@ -1202,6 +1225,23 @@ struct LoadPopcount32
 	__device__ uint32_t operator()(size_t i) const { return uint32_t(__popc(words[i])); }
 };
 
+// Vertex numbering at the start of every brick layer of the slab (for the per-layer vertex profile).
+__global__ void LayerStartsKernel(const uint32_t* __restrict__ prefix, size_t words_per_layer, uint32_t k_base, uint32_t first_layer, uint32_t layer_count,
+	uint32_t layers_in_bitmap, uint32_t* __restrict__ out)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= layer_count) return;
+	const uint32_t k = (first_layer + i) * kBrick; // first cell layer of brick layer first_layer + i
+	const uint32_t layer = k > k_base ? k - k_base : 0u;
+	out[i] = layer < layers_in_bitmap ? prefix[size_t(layer) * words_per_layer] : 0xFFFFFFFFu;
+}
+
+__global__ void RebaseIndicesKernel(uint32_t* __restrict__ indices, size_t count, uint32_t base)
+{
+	const size_t stride = size_t(gridDim.x) * blockDim.x;
+	for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) indices[i] += base;
+}
+
 // ------------------------------------------------------------------------------------------------
 // FP32 peak measurement and L2 flush (bench support)
 // ------------------------------------------------------------------------------------------------
@@ -1270,6 +1310,17 @@ Context* Context::Create(int device, std::string& error)
 		return nullptr;
 	}
 	c->stream = stream;
+	cudaStream_t copy_stream;
+	if ((e = cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
+	{
+		error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+		delete c;
+		return nullptr;
+	}
+	c->copy_stream = copy_stream;
+	cudaEvent_t ce0;
+	cudaEventCreateWithFlags(&ce0, cudaEventDisableTiming);
+	c->copy_events[0] = ce0;
 	cudaEvent_t ev0, ev1;
 	cudaEventCreate(&ev0);
 	cudaEventCreate(&ev1);
@@ -1307,6 +1358,8 @@ Context::~Context()
 	{
 		if (ev) cudaEventDestroy(static_cast<cudaEvent_t>(ev));
 	}
+	if (copy_events[0]) cudaEventDestroy(static_cast<cudaEvent_t>(copy_events[0]));
+	if (copy_stream) cudaStreamDestroy(static_cast<cudaStream_t>(copy_stream));
 	if (stream) cudaStreamDestroy(StreamOf(this));
 }
 
@@ -1523,6 +1576,8 @@ void EngineFreeMesh(tg_mesh* mesh)
 		for (void* p : r->pinned) r->context->ReleasePinned(p);
 		delete r;
 	}
+	std::free(mesh->layer_vertices);
+	std::free(mesh->layer_vertex_cost);
 	std::memset(mesh, 0, sizeof(*mesh));
 }
 
@@ -1573,7 +1628,7 @@ struct StageTimer
 
 // Shared tail of mesh and point-cloud export: refinement / normals / colours, download.
 static int FinishAttributes(Model* model, Scratch& scratch, MeshResultDevice* result, uint32_t vertex_count, const tg_mesh_options& options,
-	const float half[3], uint64_t& launches, std::string& error)
+	const float half[3], uint64_t& launches, std::string& error, unsigned long long* layer_cost = nullptr, float grid_z = 0.0f, float grid_dz = 1.0f, uint32_t layer_count = 1)
 {
 	Context* ctx = model->context;
 	cudaStream_t stream = StreamOf(ctx);
@@ -1597,6 +1652,10 @@ static int FinishAttributes(Model* model, Scratch& scratch, MeshResultDevice* re
 		ap.half_y = half[1];
 		ap.half_z = half[2];
 		ap.scale = face_normals ? 1.0f : scale; // STL scales after the centroid normals (export.cpp:142-145)
+		ap.layer_cost = layer_cost;
+		ap.grid_z = grid_z;
+		ap.grid_dz = grid_dz;
+		ap.layer_count = layer_count;
 		AttributesKernel<<<(vertex_count + 127) / 128, 128, 0, stream>>>(ap);
 		launches++;
 		TG_CUDA(cudaGetLastError());
@@ -1804,25 +1863,44 @@ int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options
 	// ---- vertex numbering: exclusive scan over the bitmap ---------------------------------------
 	int rc = DeviceExclusiveScan(stream, scratch, LoadPopcount{ bitmap }, bitmap_words, prefix, counters + kCntTotalVertices, launches, error);
 	if (rc != TG_OK) return rc;
-	uint32_t halo_vertices = 0;
-	if (has_halo)
-	{
-		// vertices of the halo layer come first in the local numbering
-		TG_CUDA(cudaMemcpyAsync(host_counts, prefix + size_t(grid.sy) * row_words, 4, cudaMemcpyDeviceToHost, stream));
-		TG_CUDA(cudaStreamSynchronize(stream));
-		halo_vertices = uint32_t(host_counts[0] & 0xFFFFFFFFull);
-	}
 	const uint32_t vertex_count = uint32_t(tmp_count);
+	const uint32_t* halo_ptr = has_halo ? prefix + size_t(grid.sy) * row_words : nullptr; // vertices of the halo layer come first locally
 
 	MeshResultDevice* result = new MeshResultDevice();
 	result->context = ctx;
 	out->opaque = result;
 	out->vertex_count = vertex_count;
-	out->halo_vertices = halo_vertices;
+
+	// per-brick-layer vertex numbering (adaptive slab balancing) + halo count: read back together with the quad total
+	const uint32_t profile_layers = bz_end - bz_begin;
+	uint32_t* layer_starts = nullptr;
+	TG_CUDA(scratch.Alloc(&layer_starts, profile_layers + 2));
+	LayerStartsKernel<<<(profile_layers + 127) / 128, 128, 0, stream>>>(prefix, size_t(grid.sy) * row_words, k_base, bz_begin, profile_layers, layers, layer_starts);
+	launches++;
+	std::vector<uint32_t> host_starts(profile_layers + 2, 0u);
+	uint32_t halo_vertices = 0;
+	const uint32_t nbz_all = (grid.sz + kBrick - 1) / kBrick;
+	unsigned long long* layer_cost = nullptr;
+	TG_CUDA(scratch.Alloc(&layer_cost, nbz_all));
+	TG_CUDA(cudaMemsetAsync(layer_cost, 0, size_t(nbz_all) * 8, stream));
+	std::vector<unsigned long long> host_layer_cost(nbz_all, 0ull);
 
 	unsigned long long* vertex_info = nullptr;
 	uint32_t *quad_count = nullptr, *quad_offset = nullptr;
 	uint64_t quad_total = 0;
+	const bool want_host = !(options.flags & TG_MESH_DEVICE_ONLY);
+	cudaStream_t copy_stream = static_cast<cudaStream_t>(ctx->copy_stream);
+	cudaEvent_t ready = static_cast<cudaEvent_t>(ctx->copy_events[0]);
+	auto fetch = [&](cudaStream_t on, void* device, size_t bytes, void** host) -> int
+	{
+		if (!device || bytes == 0) return TG_OK;
+		void* p = ctx->AcquirePinned(bytes, error);
+		if (!p) return TG_ERR_MEMORY;
+		result->pinned.push_back(p);
+		TG_CUDA(cudaMemcpyAsync(p, device, bytes, cudaMemcpyDeviceToHost, on));
+		*host = p;
+		return TG_OK;
+	};
 	if (vertex_count > 0)
 	{
 		TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_positions), size_t(vertex_count) * 12, stream));
@@ -1835,7 +1913,7 @@ int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options
 		fp.row_words = row_words;
 		fp.sy = grid.sy;
 		fp.k_base = k_base;
-		fp.halo_vertices = halo_vertices;
+		fp.halo_ptr = halo_ptr;
 		fp.tmp_pos = tmp_pos;
 		fp.tmp_key = tmp_key;
 		fp.tmp_count = vertex_count;
@@ -1851,6 +1929,8 @@ int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options
 		rc = DeviceExclusiveScan(stream, scratch, LoadU32{ quad_count }, vertex_count, quad_offset, counters + kCntTotalQuads, launches, error);
 		if (rc != TG_OK) return rc;
 		TG_CUDA(cudaMemcpyAsync(host_counts, counters + kCntTotalQuads, 8, cudaMemcpyDeviceToHost, stream));
+		TG_CUDA(cudaMemcpyAsync(host_starts.data(), layer_starts, size_t(profile_layers) * 4, cudaMemcpyDeviceToHost, stream));
+		if (halo_ptr) TG_CUDA(cudaMemcpyAsync(&halo_vertices, halo_ptr, 4, cudaMemcpyDeviceToHost, stream));
 		TG_CUDA(cudaStreamSynchronize(stream));
 		quad_total = host_counts[0];
 		if (quad_total * 2 > 0xFFFFFFF0ull)
@@ -1864,17 +1944,24 @@ int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options
 			fp.triangles = result->d_triangles;
 			EmitTrianglesKernel<<<(vertex_count + 255) / 256, 256, 0, stream>>>(fp);
 			launches++;
+			if (want_host)
+			{
+				// the index buffer is final: start bringing it home on the copy stream while the attributes are computed
+				TG_CUDA(cudaEventRecord(ready, stream));
+				TG_CUDA(cudaStreamWaitEvent(copy_stream, ready, 0));
+				if ((rc = fetch(copy_stream, result->d_triangles, size_t(quad_total) * 24, reinterpret_cast<void**>(&out->triangles))) != TG_OK) return rc;
+			}
 		}
 		TG_CUDA(cudaGetLastError());
 		const int t_faces = timer.Mark();
-		tm.compact_ms = -1.0f; // filled below from events
 		out->triangle_count = quad_total * 2;
 
 		// ---- K4: attributes ----------------------------------------------------------------------
 		ctx->stage.store(options.refine_iterations > 0 ? 2 : 3);
 		const float half[3] = { grid.dx / 2.0f, grid.dy / 2.0f, grid.dz / 2.0f };
-		rc = FinishAttributes(model, scratch, result, vertex_count, options, half, launches, error);
+		rc = FinishAttributes(model, scratch, result, vertex_count, options, half, launches, error, layer_cost, grid.z, grid.dz, nbz_all);
 		if (rc != TG_OK) return rc;
+		TG_CUDA(cudaMemcpyAsync(host_layer_cost.data(), layer_cost, size_t(nbz_all) * 8, cudaMemcpyDeviceToHost, stream));
 		if ((options.flags & TG_MESH_FACE_NORMALS) && quad_total > 0)
 		{
 			TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_face_normals), size_t(quad_total) * 24, stream));
@@ -1895,7 +1982,17 @@ int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options
 		}
 		TG_CUDA(cudaGetLastError());
 		const int t_attr = timer.Mark();
+		const auto h0 = std::chrono::steady_clock::now();
+		if (want_host)
+		{
+			if ((rc = fetch(stream, result->d_positions, size_t(vertex_count) * 12, reinterpret_cast<void**>(&out->positions))) != TG_OK) return rc;
+			if ((rc = fetch(stream, result->d_normals, size_t(vertex_count) * 12, reinterpret_cast<void**>(&out->normals))) != TG_OK) return rc;
+			if ((rc = fetch(stream, result->d_colors, size_t(vertex_count) * 3, reinterpret_cast<void**>(&out->colors))) != TG_OK) return rc;
+			if ((rc = fetch(stream, result->d_face_normals, size_t(quad_total) * 24, reinterpret_cast<void**>(&out->face_normals))) != TG_OK) return rc;
+			TG_CUDA(cudaStreamSynchronize(copy_stream));
+		}
 		TG_CUDA(cudaStreamSynchronize(stream));
+		tm.download_ms = want_host ? float(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count()) : 0.0f;
 		tm.cull_ms = timer.Ms(t_start, t_cull);
 		tm.evaluate_ms = timer.Ms(t_cull, t_eval);
 		tm.compact_ms = timer.Ms(t_eval, t_compact);
@@ -1911,32 +2008,73 @@ int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options
 		tm.evaluate_ms = timer.Ms(t_cull, t_eval);
 		tm.total_device_ms = timer.Ms(t_start, t_end);
 	}
-	tm.kernel_launches = launches;
-	ctx->stage.store(3);
-
-	// ---- download --------------------------------------------------------------------------------
-	if (!(options.flags & TG_MESH_DEVICE_ONLY) && vertex_count > 0)
+	out->halo_vertices = halo_vertices;
+	// vertices owned per brick layer (absolute layer index); layers outside the slab stay 0
 	{
-		const auto h0 = std::chrono::steady_clock::now();
-		auto fetch = [&](void* device, size_t bytes, void** host) -> int
+		const uint32_t nbz = (grid.sz + kBrick - 1) / kBrick;
+		uint32_t* profile = static_cast<uint32_t*>(std::calloc(nbz, sizeof(uint32_t)));
+		if (profile && vertex_count > 0)
 		{
-			if (!device || bytes == 0) return TG_OK;
-			void* p = ctx->AcquirePinned(bytes, error);
-			if (!p) return TG_ERR_MEMORY;
-			result->pinned.push_back(p);
-			TG_CUDA(cudaMemcpyAsync(p, device, bytes, cudaMemcpyDeviceToHost, stream));
-			*host = p;
-			return TG_OK;
-		};
-		if ((rc = fetch(result->d_positions, size_t(vertex_count) * 12, reinterpret_cast<void**>(&out->positions))) != TG_OK) return rc;
-		if ((rc = fetch(result->d_normals, size_t(vertex_count) * 12, reinterpret_cast<void**>(&out->normals))) != TG_OK) return rc;
-		if ((rc = fetch(result->d_colors, size_t(vertex_count) * 3, reinterpret_cast<void**>(&out->colors))) != TG_OK) return rc;
-		if ((rc = fetch(result->d_triangles, size_t(quad_total) * 24, reinterpret_cast<void**>(&out->triangles))) != TG_OK) return rc;
-		if ((rc = fetch(result->d_face_normals, size_t(quad_total) * 24, reinterpret_cast<void**>(&out->face_normals))) != TG_OK) return rc;
-		TG_CUDA(cudaStreamSynchronize(stream));
-		tm.download_ms = float(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
+			for (uint32_t i = 0; i < profile_layers; ++i)
+			{
+				const uint32_t begin = host_starts[i];
+				const uint32_t end = (i + 1 < profile_layers && host_starts[i + 1] != 0xFFFFFFFFu) ? host_starts[i + 1] : vertex_count + halo_vertices;
+				profile[bz_begin + i] = end >= begin ? end - begin : 0u;
+			}
+		}
+		out->layer_vertices = profile;
+		out->layer_count = nbz;
+		double* cost = static_cast<double*>(std::calloc(nbz, sizeof(double)));
+		if (cost)
+		{
+			for (uint32_t i = 0; i < nbz; ++i) cost[i] = double(host_layer_cost[i]);
+		}
+		out->layer_vertex_cost = cost;
 	}
+	tm.kernel_launches = launches;
 	ctx->stage.store(0);
+	return TG_OK;
+}
+
+// Brings a TG_MESH_DEVICE_ONLY result to the host, adding index_base to every triangle index first (multi-GPU
+// runs: the vertex total of the lower ranks, known only after the counts were exchanged).
+int EngineDownloadMesh(tg_mesh* mesh, uint32_t index_base, std::string& error)
+{
+	MeshResultDevice* result = static_cast<MeshResultDevice*>(mesh->opaque);
+	if (!result)
+	{
+		error = "mesh has no device data";
+		return TG_ERR_INVALID;
+	}
+	Context* ctx = result->context;
+	TG_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t stream = StreamOf(ctx);
+	const size_t index_count = size_t(mesh->triangle_count) * 3;
+	if (index_base != 0u && result->d_triangles && index_count)
+	{
+		RebaseIndicesKernel<<<ctx->sm_count * 8, 256, 0, stream>>>(result->d_triangles, index_count, index_base);
+		TG_CUDA(cudaGetLastError());
+		mesh->timings.kernel_launches++;
+	}
+	const auto h0 = std::chrono::steady_clock::now();
+	auto fetch = [&](void* device, size_t bytes, void** host) -> int
+	{
+		if (!device || bytes == 0 || *host) return TG_OK;
+		void* p = ctx->AcquirePinned(bytes, error);
+		if (!p) return TG_ERR_MEMORY;
+		result->pinned.push_back(p);
+		TG_CUDA(cudaMemcpyAsync(p, device, bytes, cudaMemcpyDeviceToHost, stream));
+		*host = p;
+		return TG_OK;
+	};
+	int rc;
+	if ((rc = fetch(result->d_triangles, index_count * 4, reinterpret_cast<void**>(&mesh->triangles))) != TG_OK) return rc;
+	if ((rc = fetch(result->d_positions, size_t(mesh->vertex_count) * 12, reinterpret_cast<void**>(&mesh->positions))) != TG_OK) return rc;
+	if ((rc = fetch(result->d_normals, size_t(mesh->vertex_count) * 12, reinterpret_cast<void**>(&mesh->normals))) != TG_OK) return rc;
+	if ((rc = fetch(result->d_colors, size_t(mesh->vertex_count) * 3, reinterpret_cast<void**>(&mesh->colors))) != TG_OK) return rc;
+	if ((rc = fetch(result->d_face_normals, index_count * 4, reinterpret_cast<void**>(&mesh->face_normals))) != TG_OK) return rc;
+	TG_CUDA(cudaStreamSynchronize(stream));
+	mesh->timings.download_ms = float(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
 	return TG_OK;
 }
 
@@ -1965,7 +2103,7 @@ int EngineBrickProfile(Model* model, const tg_grid& grid_in, uint32_t* out_layer
 	uint64_t count = 0, launches = 0;
 	const int rc = BuildActiveList(model, stream, scratch, grid, 0, grid.sz, false, false, counters, &list, &count, launches, error);
 	if (rc != TG_OK) return rc;
-	if (count) BrickLayerHistogramKernel<<<uint32_t((count + 255) / 256), 256, 0, stream>>>(list, uint32_t(count), layers);
+	if (count) BrickLayerHistogramKernel<<<uint32_t((count + 255) / 256), 256, 0, stream>>>(MakeDeviceModel(model), grid, list, uint32_t(count), layers);
 	TG_CUDA(cudaGetLastError());
 	TG_CUDA(cudaMemcpyAsync(out_layers, layers, size_t(nbz) * 4, cudaMemcpyDeviceToHost, stream));
 	TG_CUDA(cudaStreamSynchronize(stream));

@@ -25,6 +25,8 @@ class Context
 public:
 	int device = 0;
 	void* stream = nullptr;      // cudaStream_t
+	void* copy_stream = nullptr; // cudaStream_t: device -> host copies that overlap compute
+	void* copy_events[1] = { nullptr };
 	void* timer_events[2] = { nullptr, nullptr };
 	std::vector<PinnedBlock> pinned; // grow-only pool of page-locked host buffers for results
 	int sm_count = 0;
@@ -71,6 +73,7 @@ int EngineExportMesh(Model* model, const tg_grid& grid, const tg_mesh_options& o
 int EngineExportPoints(Model* model, const float mn[3], const float mx[3], const float step[3], int refine, uint32_t flags, tg_mesh* out, std::string& error);
 int EngineExportVoxels(Model* model, float grid_size, int32_t out_size[3], float* out_radius, int32_t** out_xyz, uint64_t* out_count, std::string& error);
 void EngineFreeMesh(tg_mesh* mesh);
+int EngineDownloadMesh(tg_mesh* mesh, uint32_t index_base, std::string& error);
 int EngineTimerBegin(Context* context, std::string& error);
 int EngineTimerEnd(Context* context, float* out_ms, std::string& error);
 int EngineMeasureFp32Peak(Context* context, double* out_tflops, std::string& error);
