@@ -248,39 +248,60 @@ def main():
 
     # ---- device-resident throughput (`value`) -------------------------------------------------------------
     def device_step():
-        ctx.flush_l2()
         mesh = model.export_mesh(grid, flags=flags | T.MESH_DEVICE_ONLY, refine=refine, slab=slab)
         t = dict(mesh.timings)
         t["vertices"], t["triangles"] = mesh.vertex_count, mesh.triangle_count
         mesh.close()
         return t
 
+    cost = None
     for w in range(args.warmup):
         mesh = model.export_mesh(grid, flags=flags | T.MESH_DEVICE_ONLY, refine=refine, slab=slab)
-        if world > 1 and w == 0:
+        if world > 1:
             tm = mesh.timings
             lo_b, hi_b = slab[0] // 8, (slab[1] + 7) // 8
-            mine = np.zeros(len(profile) + 4, np.float64)
-            mine[:len(profile)] = mesh.layer_vertex_cost[:len(profile)]
-            mine[-4:] = [tm["evaluate_ms"] + tm["cull_ms"], profile[lo_b:hi_b].sum(), tm["compact_ms"] + tm["faces_ms"] + tm["attributes_ms"], mesh.layer_vertex_cost.sum()]
+            n = len(profile)
+            mine = np.zeros(n + 4 + world, np.float64)
+            mine[:n] = mesh.layer_vertex_cost[:n]
+            mine[n:n + 4] = [tm["evaluate_ms"] + tm["cull_ms"], profile[lo_b:hi_b].sum(), tm["compact_ms"] + tm["faces_ms"] + tm["attributes_ms"], mesh.layer_vertex_cost.sum()]
+            mine[n + 4 + rank] = tm["total_device_ms"]
             t = torch.from_numpy(mine).cuda()
             dist.all_reduce(t)
             allv = t.cpu().numpy()
-            eval_rate = allv[-4] / max(allv[-3], 1.0)
-            vertex_rate = allv[-2] / max(allv[-1], 1.0)
-            slabs = balanced_slabs(eval_rate * profile + vertex_rate * allv[:len(profile)], world, sz)
+            if cost is None:
+                # first model: two rates fitted to the measured stage times of all ranks
+                eval_rate = allv[n] / max(allv[n + 1], 1.0)
+                vertex_rate = allv[n + 2] / max(allv[n + 3], 1.0)
+                cost = eval_rate * profile + vertex_rate * allv[:n] + 1e-9
+            # feedback: rescale every slab's layers so that the model reproduces the time that slab just took
+            for r, (k0, k1) in enumerate(slabs):
+                b0, b1 = k0 // 8, (k1 + 7) // 8
+                predicted = cost[b0:b1].sum()
+                if predicted > 0 and allv[n + 4 + r] > 0:
+                    cost[b0:b1] *= allv[n + 4 + r] / predicted
+            slabs = balanced_slabs(cost, world, sz)
             slab = slabs[rank]
         mesh.close()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
-    ctx.timer_begin()
-    steps = [device_step() for _ in range(args.steps)]
-    ms_local = ctx.timer_end()
+    steps = []
+    ms_local = 0.0
+    for _ in range(args.steps):
+        ctx.flush_l2()                 # between timed iterations, outside the timed interval
+        ctx.timer_begin()              # CUDA events on the context's own stream, the one every kernel is launched on
+        steps.append(device_step())
+        ms_local += ctx.timer_end()
     barrier()
     ms_total = all_max(ms_local)
     ms_per_step = ms_total / args.steps
+    # per-rank view of the same region: wall (events around the K steps) and the sum of the engine's stage timers
+    per_rank = [[ms_local / args.steps, float(np.mean([s["total_device_ms"] for s in steps]))]]
+    if world > 1:
+        t = torch.zeros((world, 2), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(t, torch.tensor(per_rank[0], dtype=torch.float64, device="cuda"))
+        per_rank = t.cpu().numpy().tolist()
     value = cells_total / (ms_per_step * 1e-3) * 1e-6
 
     # ---- end to end through the C ABI with host buffers (`e2e`) ------------------------------------------
@@ -321,7 +342,7 @@ def main():
     triangles = int(all_sum(float(last["triangles"])))
     samples = all_sum(float(last["samples_evaluated"]))
     flops = all_sum(float(last["algorithmic_flops"]))
-    launches = int(all_sum(float(sum(s["kernel_launches"] + 1 for s in steps))))
+    launches = int(all_sum(float(sum(s["kernel_launches"] for s in steps))))
     bricks_total = all_sum(float(last["bricks_total"]))
     bricks_eval = all_sum(float(last["bricks_evaluated"]))
     # per-vertex evaluations: R x (4-tap gradient + 1) + 4-tap normal + 1 material walk
@@ -384,11 +405,12 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "model": name + ".tgm (CSG tree dumped from the reference's Lua front-end)", "grid": [sx, sy, sz], "refine_iterations": refine,
                        "attributes": "normals+colours", "culling": not args.no_cull, "partition": "z-slabs %s" % (slabs,),
-                       "l2": "flushed before every step (256 MiB fill); per-step scratch (bitmap + prefix) exceeds L2 at this grid"},
+                       "l2": "flushed before every timed step (256 MiB fill, outside the per-step event pair); per-step scratch (bitmap + prefix) also exceeds L2 at this grid"},
             "evals_per_s": evals_per_s, "reference_equivalent_evals_per_s": reference_equivalent_evals / (ms_per_step * 1e-3),
             "mesh": {"vertices": vertices, "triangles": triangles},
             "bricks": {"total": bricks_total, "evaluated": bricks_eval},
             "stage_ms_rank0": {k: mean(k) for k in ("cull_ms", "evaluate_ms", "compact_ms", "faces_ms", "attributes_ms", "total_device_ms")},
+            "per_rank_ms": {"step_wall": [round(r[0], 4) for r in per_rank], "stage_sum": [round(r[1], 4) for r in per_rank]},
             "model_build_s": model_seconds, "octree_nodes": stats["octree_nodes"],
             "e2e": {"value": e2e_value, "unit": "Mvoxel/s", "ms_per_step": e2e_wall_ms / args.steps, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
                     "timed": "host wall clock around tg_model_upload + tg_export_mesh (pinned host results)%s, max over ranks" % (" + NCCL count all-gather + tg_mesh_download (index rebase on device)" if world > 1 else ""),

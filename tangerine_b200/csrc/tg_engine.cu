@@ -79,7 +79,8 @@ struct MeshParams
 	DeviceModel model;
 	DeviceGrid grid;
 	const uint32_t* bricks;
-	uint32_t brick_count;
+	const unsigned long long* brick_count; // device: length of `bricks` (written by CullResolveKernel)
+	uint32_t brick_capacity;
 	unsigned long long* bitmap; // one bit per cell, rows padded to 64 cells; layer 0 = cell layer k_base
 	uint32_t row_words;
 	uint32_t k_base;
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__(kBrickThreads) MeshBricksKernel(const MeshPara
 	const float bbmaxy = __fadd_rn(grid.y, __fmul_rn(float(grid.sy), grid.dy));
 	const float bbmaxz = __fadd_rn(grid.z, __fmul_rn(float(grid.sz), grid.dz));
 	unsigned char* bitmap_bytes = reinterpret_cast<unsigned char*>(p.bitmap);
+	const uint32_t brick_count = uint32_t(min(*p.brick_count, (unsigned long long)p.brick_capacity));
 
 	for (;;)
 	{
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(kBrickThreads) MeshBricksKernel(const MeshPara
 		uint32_t item = 0;
 		if (lane == 0) item = uint32_t(atomicAdd(&p.counters[kCntBrickCursor], 1ull));
 		item = __shfl_sync(0xFFFFFFFFu, item, 0);
-		if (item >= p.brick_count) break;
+		if (item >= brick_count) break;
 
 		const uint32_t brick = __ldg(&p.bricks[item]);
 		const uint32_t bx = brick & 1023u, by = (brick >> 10) & 1023u, bz = (brick >> 20) & 1023u;
@@ -1358,6 +1360,7 @@ Context::~Context()
 	{
 		if (ev) cudaEventDestroy(static_cast<cudaEvent_t>(ev));
 	}
+	if (arena) cudaFree(arena);
 	if (copy_events[0]) cudaEventDestroy(static_cast<cudaEvent_t>(copy_events[0]));
 	if (copy_stream) cudaStreamDestroy(static_cast<cudaStream_t>(copy_stream));
 	if (stream) cudaStreamDestroy(StreamOf(this));
@@ -1525,27 +1528,51 @@ static bool MakeDeviceGrid(const tg_grid& g, DeviceGrid& out, std::string& error
 }
 
 // RAII for stream-ordered scratch.
+// Per-call scratch memory: bump allocation out of one grow-only arena the context keeps between calls (a context
+// serves one call at a time and everything is ordered on its stream), so a steady-state export makes no allocator
+// calls for scratch.  Requests the arena cannot hold fall back to the stream-ordered pool and make the arena grow
+// for the next call.
 struct Scratch
 {
+	Context* ctx;
 	cudaStream_t stream;
 	std::vector<void*> blocks;
-	explicit Scratch(cudaStream_t s) : stream(s) {}
+	size_t used = 0;
+	size_t wanted = 0;
+	explicit Scratch(Context* c) : ctx(c), stream(static_cast<cudaStream_t>(c->stream)) {}
 	~Scratch()
 	{
 		for (void* b : blocks) cudaFreeAsync(b, stream);
+		if (wanted > ctx->arena_bytes)
+		{
+			if (ctx->arena) cudaFreeAsync(ctx->arena, stream);
+			ctx->arena = nullptr;
+			ctx->arena_bytes = 0;
+			const size_t bytes = wanted + wanted / 4 + (size_t(1) << 20);
+			void* p = nullptr;
+			if (cudaMallocAsync(&p, bytes, stream) == cudaSuccess)
+			{
+				ctx->arena = p;
+				ctx->arena_bytes = bytes;
+			}
+		}
 	}
 	template <typename T>
 	cudaError_t Alloc(T** out, size_t count)
 	{
+		const size_t bytes = (std::max<size_t>(count * sizeof(T), 256) + 255) & ~size_t(255);
+		wanted += bytes;
+		if (used + bytes <= ctx->arena_bytes)
+		{
+			*out = reinterpret_cast<T*>(static_cast<char*>(ctx->arena) + used);
+			used += bytes;
+			return cudaSuccess;
+		}
 		void* p = nullptr;
-		cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(count * sizeof(T), 256), stream);
+		cudaError_t e = cudaMallocAsync(&p, bytes, stream);
 		if (e == cudaSuccess) blocks.push_back(p);
 		*out = static_cast<T*>(p);
 		return e;
-	}
-	void Keep(void* p) // hand ownership to the caller
-	{
-		blocks.erase(std::remove(blocks.begin(), blocks.end(), p), blocks.end());
 	}
 };
 
@@ -1665,7 +1692,8 @@ static int FinishAttributes(Model* model, Scratch& scratch, MeshResultDevice* re
 }
 
 // K0 driver.  Leaves the list of 8-cell bricks that must be evaluated (plus, for slab runs, the halo bricks of
-// the row below, flagged) in *out_list and its length in *out_count.  No host round trip until the final count.
+// the row below, flagged) in *out_list, its length on the device in counters[kCntListA] and its capacity in
+// *out_count.  No host round trip at all: the brick kernel reads the length itself.
 static int BuildActiveList(Model* model, cudaStream_t stream, Scratch& scratch, const DeviceGrid& grid, uint32_t k_begin, uint32_t k_end,
 	bool has_halo, bool no_cull, unsigned long long* counters, uint32_t** out_list, uint64_t* out_count, uint64_t& launches, std::string& error)
 {
@@ -1735,11 +1763,8 @@ static int BuildActiveList(Model* model, cudaStream_t stream, Scratch& scratch, 
 		active_list, counters + kCntListA, uint32_t(list_capacity));
 	launches++;
 	TG_CUDA(cudaGetLastError());
-	unsigned long long host_count = 0;
-	TG_CUDA(cudaMemcpyAsync(&host_count, counters + kCntListA, 8, cudaMemcpyDeviceToHost, stream));
-	TG_CUDA(cudaStreamSynchronize(stream));
 	*out_list = active_list;
-	*out_count = std::min<unsigned long long>(host_count, list_capacity);
+	*out_count = list_capacity; // capacity of the list; its length stays on the device in counters[kCntListA]
 	return TG_OK;
 }
 
@@ -1779,7 +1804,7 @@ int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options
 	ctx->progress_total[0] = own_bricks;
 	if (ctx->Cancelled()) return TG_ERR_CANCELLED;
 
-	Scratch scratch(stream);
+	Scratch scratch(ctx);
 	StageTimer timer(stream);
 	uint64_t launches = 0;
 	tg_mesh_timings& tm = out->timings;
@@ -1799,14 +1824,13 @@ int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options
 	// ---- K0: active brick list -------------------------------------------------------------------
 	const bool no_cull = (options.flags & TG_MESH_NO_CULL) != 0;
 	unsigned long long host_counts[kCntCount];
-	uint64_t active_count = 0;
+	uint64_t list_capacity_out = 0;
 	{
-		const int rc0 = BuildActiveList(model, stream, scratch, grid, k_begin, k_end, has_halo, no_cull, counters, &active_list, &active_count, launches, error);
+		const int rc0 = BuildActiveList(model, stream, scratch, grid, k_begin, k_end, has_halo, no_cull, counters, &active_list, &list_capacity_out, launches, error);
 		if (rc0 != TG_OK) return rc0;
 	}
 	TG_CUDA(cudaGetLastError());
 	const int t_cull = timer.Mark();
-	tm.bricks_evaluated = active_count;
 	ctx->progress_done[0] = own_bricks / 2;
 	if (ctx->Cancelled()) return TG_ERR_CANCELLED;
 
@@ -1815,40 +1839,43 @@ int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options
 	mp.model = MakeDeviceModel(model);
 	mp.grid = grid;
 	mp.bricks = active_list;
-	mp.brick_count = uint32_t(active_count);
+	mp.brick_count = counters + kCntListA;
+	mp.brick_capacity = uint32_t(list_capacity_out);
 	mp.bitmap = bitmap;
 	mp.row_words = row_words;
 	mp.k_base = k_base;
 	mp.k_own_begin = k_begin;
 	mp.k_own_end = k_end;
 	mp.counters = counters;
-	uint64_t tmp_capacity = std::max<uint64_t>(active_count * 96, 1 << 16);
+	// The brick count is still on the device, so the staging buffers are sized from the slab: surfaces occupy a few
+	// percent of the cells at most.  If that ever falls short the exact count is known after the first attempt.
+	const uint64_t slab_cells = uint64_t(grid.sx) * grid.sy * (k_end - k_begin);
+	uint64_t tmp_capacity = std::min<uint64_t>(slab_cells, std::max<uint64_t>(slab_cells / 16, 1 << 20));
 	uint64_t tmp_count = 0;
+	uint64_t active_count = 0;
 	float4* tmp_pos = nullptr;
 	unsigned long long* tmp_key = nullptr;
-	for (int attempt = 0; attempt < 2 && active_count > 0; ++attempt)
+	for (int attempt = 0; attempt < 2; ++attempt)
 	{
 		TG_CUDA(scratch.Alloc(&tmp_pos, tmp_capacity));
 		TG_CUDA(scratch.Alloc(&tmp_key, tmp_capacity));
 		mp.tmp_pos = tmp_pos;
 		mp.tmp_key = tmp_key;
-		mp.tmp_capacity = uint32_t(tmp_capacity);
+		mp.tmp_capacity = uint32_t(std::min<uint64_t>(tmp_capacity, 0xFFFFFFFFull));
 		TG_CUDA(cudaMemsetAsync(counters + kCntTmpVertices, 0, 3 * 8, stream));
 		TG_CUDA(cudaMemsetAsync(counters + kCntBrickCursor, 0, 8, stream));
-		{
-			// persistent warps: enough blocks to fill every SM, never more than there are bricks
-			const uint64_t wanted = (active_count + kBrickWarps - 1) / kBrickWarps;
-			const uint32_t blocks = uint32_t(std::min<uint64_t>(wanted, uint64_t(ctx->sm_count) * ctx->brick_blocks_per_sm));
-			MeshBricksKernel<<<blocks, kBrickThreads, 0, stream>>>(mp);
-		}
+		// persistent warps: the grid fills every SM; warps beyond the list length leave at their first fetch
+		MeshBricksKernel<<<uint32_t(ctx->sm_count) * uint32_t(ctx->brick_blocks_per_sm), kBrickThreads, 0, stream>>>(mp);
 		launches++;
 		TG_CUDA(cudaGetLastError());
 		TG_CUDA(cudaMemcpyAsync(host_counts, counters, kCntCount * 8, cudaMemcpyDeviceToHost, stream));
 		TG_CUDA(cudaStreamSynchronize(stream));
 		tmp_count = host_counts[kCntTmpVertices];
+		active_count = std::min<unsigned long long>(host_counts[kCntListA], list_capacity_out);
 		if (tmp_count <= tmp_capacity) break;
 		tmp_capacity = tmp_count; // exact size is known now; the bitmap writes are idempotent
 	}
+	tm.bricks_evaluated = active_count;
 	if (tmp_count > 0xFFFFFFF0ull)
 	{
 		error = "mesh exceeds 2^32 vertices";
@@ -2092,7 +2119,7 @@ int EngineBrickProfile(Model* model, const tg_grid& grid_in, uint32_t* out_layer
 		error = "brick profile needs ceil(sz / 8) entries";
 		return TG_ERR_INVALID;
 	}
-	Scratch scratch(stream);
+	Scratch scratch(ctx);
 	unsigned long long* counters = nullptr;
 	uint32_t* layers = nullptr;
 	TG_CUDA(scratch.Alloc(&counters, kCntCount));
@@ -2101,8 +2128,13 @@ int EngineBrickProfile(Model* model, const tg_grid& grid_in, uint32_t* out_layer
 	TG_CUDA(cudaMemsetAsync(layers, 0, 1024 * 4, stream));
 	uint32_t* list = nullptr;
 	uint64_t count = 0, launches = 0;
-	const int rc = BuildActiveList(model, stream, scratch, grid, 0, grid.sz, false, false, counters, &list, &count, launches, error);
+	uint64_t capacity = 0;
+	const int rc = BuildActiveList(model, stream, scratch, grid, 0, grid.sz, false, false, counters, &list, &capacity, launches, error);
 	if (rc != TG_OK) return rc;
+	unsigned long long host_count = 0;
+	TG_CUDA(cudaMemcpyAsync(&host_count, counters + kCntListA, 8, cudaMemcpyDeviceToHost, stream));
+	TG_CUDA(cudaStreamSynchronize(stream));
+	count = std::min<unsigned long long>(host_count, capacity);
 	if (count) BrickLayerHistogramKernel<<<uint32_t((count + 255) / 256), 256, 0, stream>>>(MakeDeviceModel(model), grid, list, uint32_t(count), layers);
 	TG_CUDA(cudaGetLastError());
 	TG_CUDA(cudaMemcpyAsync(out_layers, layers, size_t(nbz) * 4, cudaMemcpyDeviceToHost, stream));
@@ -2120,7 +2152,7 @@ int EngineEvalLattice(Model* model, const tg_grid& grid_in, float* out, float* o
 	const uint32_t nx = grid.sx + 1, ny = grid.sy + 1, nz = grid.sz + 1;
 	const uint32_t tx = (nx + kBrick - 1) / kBrick, ty = (ny + kBrick - 1) / kBrick, tz = (nz + kBrick - 1) / kBrick;
 	const size_t total = size_t(nx) * ny * nz;
-	Scratch scratch(stream);
+	Scratch scratch(ctx);
 	float* d_out = nullptr;
 	unsigned long long* counters = nullptr;
 	TG_CUDA(scratch.Alloc(&counters, kCntCount));
@@ -2154,7 +2186,7 @@ int EngineEvalPoints(Model* model, int mode, const float* points, uint64_t count
 	Context* ctx = model->context;
 	TG_CUDA(cudaSetDevice(ctx->device));
 	cudaStream_t stream = StreamOf(ctx);
-	Scratch scratch(stream);
+	Scratch scratch(ctx);
 	float* d_points = nullptr;
 	unsigned char* d_out = nullptr;
 	const size_t out_bytes = size_t(count) * (mode == TG_EVAL_GRADIENT ? 12 : mode == TG_EVAL_COLOR ? 3 : 4);
@@ -2186,7 +2218,7 @@ int EngineExportVoxels(Model* model, float grid_size, int32_t out_size[3], float
 	const float radius = Length(Mix(b.min, b.max, alpha) - b.min);
 	const unsigned long long total = (unsigned long long)sx * sy * sz;
 	const size_t words = size_t((total + 31) / 32);
-	Scratch scratch(stream);
+	Scratch scratch(ctx);
 	uint32_t* d_hits = nullptr;
 	TG_CUDA(scratch.Alloc(&d_hits, words));
 	TG_CUDA(cudaMemsetAsync(d_hits, 0, words * 4, stream));
@@ -2256,7 +2288,7 @@ int EngineExportPoints(Model* model, const float mn[3], const float mx[3], const
 	const size_t words = size_t((total + 31) / 32);
 	const Vec3 half(step[0] / 2.0f, step[1] / 2.0f, step[2] / 2.0f);
 	const float diagonal = Length(half);
-	Scratch scratch(stream);
+	Scratch scratch(ctx);
 	uint64_t launches = 0;
 	uint32_t *d_hits = nullptr, *d_prefix = nullptr;
 	unsigned long long* counters = nullptr;
@@ -2338,7 +2370,7 @@ int EngineMeasureFp32Peak(Context* ctx, double* out_tflops, std::string& error)
 {
 	TG_CUDA(cudaSetDevice(ctx->device));
 	cudaStream_t stream = StreamOf(ctx);
-	Scratch scratch(stream);
+	Scratch scratch(ctx);
 	const int blocks = ctx->sm_count * 8, threads = 256, iterations = 4096;
 	float* d_out = nullptr;
 	TG_CUDA(scratch.Alloc(&d_out, size_t(blocks) * threads));
@@ -2363,7 +2395,7 @@ int EngineFlushL2(Context* ctx, std::string& error)
 {
 	TG_CUDA(cudaSetDevice(ctx->device));
 	cudaStream_t stream = StreamOf(ctx);
-	Scratch scratch(stream);
+	Scratch scratch(ctx);
 	const size_t count = size_t(256) << 18; // 256 MiB of u32 > 126 MB L2
 	uint32_t* d = nullptr;
 	TG_CUDA(scratch.Alloc(&d, count));

@@ -29,6 +29,8 @@ public:
 	void* copy_events[1] = { nullptr };
 	void* timer_events[2] = { nullptr, nullptr };
 	std::vector<PinnedBlock> pinned; // grow-only pool of page-locked host buffers for results
+	void* arena = nullptr;       // grow-only device scratch reused by every call on this context
+	size_t arena_bytes = 0;
 	int sm_count = 0;
 	int brick_blocks_per_sm = 1; // resident MeshBricksKernel blocks per SM (persistent grid size)
 
