@@ -466,16 +466,43 @@ __device__ __forceinline__ void RunProgram(const uint32_t* __restrict__ program,
 			else
 			{
 				const float threshold = (op >= kOpBlendUnion) ? __ldg(arg) : 0.0f;
+				float dist[S];
+				switch (op) // one dispatch per instruction, not per sample
+				{
+				case kOpUnion:
+#pragma unroll
+					for (int s = 0; s < S; ++s) dist[s] = sdf::Union(acc[s], d[s]);
+					break;
+				case kOpInter:
+#pragma unroll
+					for (int s = 0; s < S; ++s) dist[s] = sdf::Inter(acc[s], d[s]);
+					break;
+				case kOpDiff:
+#pragma unroll
+					for (int s = 0; s < S; ++s) dist[s] = sdf::Diff(acc[s], d[s]);
+					break;
+				case kOpBlendUnion:
+#pragma unroll
+					for (int s = 0; s < S; ++s) dist[s] = sdf::BlendUnion(acc[s], d[s], threshold);
+					break;
+				case kOpBlendInter:
+#pragma unroll
+					for (int s = 0; s < S; ++s) dist[s] = sdf::BlendInter(acc[s], d[s], threshold);
+					break;
+				default:
+#pragma unroll
+					for (int s = 0; s < S; ++s) dist[s] = sdf::BlendDiff(acc[s], d[s], threshold);
+					break;
+				}
 #pragma unroll
 				for (int s = 0; s < S; ++s)
 				{
 					const float l = acc[s];
 					const float r = d[s];
-					const float dist = sdf::SetOp(op, l, r, threshold);
 					if (MATERIAL)
 					{
 						// SetNode::GetMaterial (:957-1012)
-						const bool take_left = (op >= kOpBlendUnion) ? (fabsf(l - dist) <= fabsf(r - dist)) : (dist == l);
+						const bool take_left = (op >= kOpBlendUnion) ? (fabsf(l - dist[s]) <= fabsf(r - dist[s])) : (dist[s] == l);
 						const uint32_t family = (op - 1u) % 3u; // 0 union, 1 inter, 2 diff
 						uint32_t m;
 						if (family == 2u) m = accm[s];
@@ -487,7 +514,7 @@ __device__ __forceinline__ void RunProgram(const uint32_t* __restrict__ program,
 						}
 						accm[s] = m;
 					}
-					acc[s] = dist;
+					acc[s] = dist[s];
 				}
 			}
 		}
@@ -568,6 +595,18 @@ __device__ __forceinline__ float EvalDistance1(const uint32_t* __restrict__ prog
 	return out[0];
 }
 
+// Value (and, through *material, the GetMaterial result) of a tree-stream program at one point.  Deliberately not
+// inlined: the attribute kernels call it from several places and must carry exactly one copy of the interpreter
+// (their instruction footprint is what limits them).
+__device__ __noinline__ float EvalTreeCentre(const uint32_t* __restrict__ tree_program, float x, float y, float z, uint32_t* material = nullptr)
+{
+	float px[1] = { x }, py[1] = { y }, pz[1] = { z }, d[1];
+	uint32_t m[1];
+	RunProgram<1, true>(tree_program, px, py, pz, d, m);
+	if (material) *material = m[0];
+	return d[0];
+}
+
 // SDFNode::Gradient (sdf_evaluator.cpp:298-333) on a tree-stream program: the four tetrahedral taps are
 // the four samples of one RunProgram<4> call.
 __device__ __forceinline__ void EvalGradient(const uint32_t* __restrict__ tree_program, float x, float y, float z, float& gx, float& gy, float& gz)
@@ -588,7 +627,7 @@ __device__ __forceinline__ void EvalGradient(const uint32_t* __restrict__ tree_p
 	if (len_sq == 0.0f)
 	{
 		// zero gradient: forward differences (:320-328); taps xyy, yxy, yyx are d[0], d[2], d[1]
-		const float dist = EvalDistance1(tree_program, x, y, z);
+		const float dist = EvalTreeCentre(tree_program, x, y, z);
 		const float fx = d[0] - dist, fy = d[2] - dist, fz = d[1] - dist;
 		const float inv = 1.0f / sqrtf(fx * fx + fy * fy + fz * fz); // glm::normalize = v * inversesqrt(dot(v, v))
 		gx = fx * inv;

@@ -996,7 +996,37 @@ struct AttributeParams
 	unsigned long long* layer_cost; // may be null
 	float grid_z, grid_dz;
 	uint32_t layer_count;
+	// node-coherent execution order: thread t works on vertex perm[t], whose octree node is vertex_node[perm[t]]
+	const uint32_t* perm;        // may be null (identity)
+	const uint32_t* vertex_node; // may be null
 };
+
+// Counting sort of the vertices by octree node, so that the lanes of a warp run the same tree program.
+__global__ void __launch_bounds__(256) VertexNodeKernel(const DeviceModel model, const float* __restrict__ positions, uint32_t count,
+	uint32_t* __restrict__ vertex_node, uint32_t* __restrict__ histogram)
+{
+	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= count) return;
+	const uint32_t node = Descend(model.nodes, 0, positions[size_t(v) * 3 + 0], positions[size_t(v) * 3 + 1], positions[size_t(v) * 3 + 2]);
+	vertex_node[v] = node;
+	// neighbouring vertices mostly share their node: one atomic per distinct node in the warp
+	const unsigned peers = __match_any_sync(__activemask(), node);
+	if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&histogram[node], uint32_t(__popc(peers)));
+}
+
+__global__ void __launch_bounds__(256) VertexPermutationKernel(const uint32_t* __restrict__ vertex_node, uint32_t count, const uint32_t* __restrict__ node_offset,
+	uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm)
+{
+	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= count) return;
+	const uint32_t node = vertex_node[v];
+	const unsigned peers = __match_any_sync(__activemask(), node);
+	const int leader = __ffs(peers) - 1;
+	uint32_t base = 0;
+	if ((threadIdx.x & 31) == leader) base = atomicAdd(&cursor[node], uint32_t(__popc(peers)));
+	base = __shfl_sync(peers, base, leader);
+	perm[node_offset[node] + base + uint32_t(__popc(peers & ((1u << (threadIdx.x & 31)) - 1u)))] = v;
+}
 
 __device__ __forceinline__ void ExportColor(const DeviceModel& model, uint32_t node, float x, float y, float z, unsigned char* out)
 {
@@ -1004,9 +1034,8 @@ __device__ __forceinline__ void ExportColor(const DeviceModel& model, uint32_t n
 	float r = 1.0f, g = 1.0f, b = 1.0f;
 	if (model.has_paint)
 	{
-		float px[1] = { x }, py[1] = { y }, pz[1] = { z }, d[1];
 		uint32_t m[1];
-		RunProgram<1, true>(model.tree + __ldg(&model.nodes[node].tree_offset), px, py, pz, d, m);
+		EvalTreeCentre(model.tree + __ldg(&model.nodes[node].tree_offset), x, y, z, &m[0]);
 		const uint32_t id = m[0] == kNoMaterial || m[0] >= model.material_count ? model.material_count : m[0];
 		r = __ldg(&model.material_rgb[id * 3 + 0]);
 		g = __ldg(&model.material_rgb[id * 3 + 1]);
@@ -1019,37 +1048,49 @@ __device__ __forceinline__ void ExportColor(const DeviceModel& model, uint32_t n
 
 __global__ void __launch_bounds__(128) AttributesKernel(const AttributeParams p)
 {
-	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-	if (v >= p.count) return;
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= p.count) return;
+	const uint32_t v = p.perm ? p.perm[t] : t;
 	float x = p.positions[size_t(v) * 3 + 0], y = p.positions[size_t(v) * 3 + 1], z = p.positions[size_t(v) * 3 + 2];
 	const DeviceModel& model = p.model;
-	if (p.refine_iterations > 0)
+	const float vx = x, vy = y, vz = z;
+	const int iterations = p.refine_iterations > 0 ? p.refine_iterations : 0;
+	uint32_t node = 0;
+	// One loop body serves the refinement steps (export.cpp:442-461 applied to a mesh vertex) and the final normal, so
+	// the kernel holds a single copy of the gradient interpreter.
+	for (int r = 0; r <= iterations; ++r)
 	{
-		// export.cpp:442-461 applied to a mesh vertex
-		const float vx = x, vy = y, vz = z;
-		const float diagonal = sqrtf(p.half_x * p.half_x + p.half_y * p.half_y + p.half_z * p.half_z);
-		for (int r = 0; r < p.refine_iterations; ++r)
+		const bool last = r == iterations;
+		if (last && iterations > 0)
 		{
-			const uint32_t node = Descend(model.nodes, 0, x, y, z);
-			float gx, gy, gz;
-			EvalGradient(model.tree + __ldg(&model.nodes[node].tree_offset), x, y, z, gx, gy, gz);
-			const float dist = -EvalInterp1(model, __ldg(&model.nodes[node].interp_offset), x, y, z);
-			x = x + gx * dist;
-			y = y + gy * dist;
-			z = z + gz * dist;
+			const float diagonal = sqrtf(p.half_x * p.half_x + p.half_y * p.half_y + p.half_z * p.half_z);
+			x = sdf::gmin(sdf::gmax(x, vx - p.half_x), vx + p.half_x);
+			y = sdf::gmin(sdf::gmax(y, vy - p.half_y), vy + p.half_y);
+			z = sdf::gmin(sdf::gmax(z, vz - p.half_z), vz + p.half_z);
+			const float mx = vx - x, my = vy - y, mz = vz - z;
+			if (!(sqrtf(mx * mx + my * my + mz * mz) <= diagonal))
+			{
+				x = vx;
+				y = vy;
+				z = vz;
+			}
 		}
-		x = sdf::gmin(sdf::gmax(x, vx - p.half_x), vx + p.half_x);
-		y = sdf::gmin(sdf::gmax(y, vy - p.half_y), vy + p.half_y);
-		z = sdf::gmin(sdf::gmax(z, vz - p.half_z), vz + p.half_z);
-		const float mx = vx - x, my = vy - y, mz = vz - z;
-		if (!(sqrtf(mx * mx + my * my + mz * mz) <= diagonal))
+		node = (r == 0 && p.vertex_node) ? p.vertex_node[v] : Descend(model.nodes, 0, x, y, z);
+		if (last && !p.normals) break;
+		float gx, gy, gz;
+		EvalGradient(model.tree + __ldg(&model.nodes[node].tree_offset), x, y, z, gx, gy, gz);
+		if (last)
 		{
-			x = vx;
-			y = vy;
-			z = vz;
+			p.normals[size_t(v) * 3 + 0] = gx;
+			p.normals[size_t(v) * 3 + 1] = gy;
+			p.normals[size_t(v) * 3 + 2] = gz;
+			break;
 		}
+		const float dist = -EvalInterp1(model, __ldg(&model.nodes[node].interp_offset), x, y, z);
+		x = x + gx * dist;
+		y = y + gy * dist;
+		z = z + gz * dist;
 	}
-	const uint32_t node = Descend(model.nodes, 0, x, y, z);
 	if (p.layer_cost)
 	{
 		// one atomic per distinct brick layer in the warp (vertices are in (k, j, i) order: usually one)
@@ -1060,14 +1101,6 @@ __global__ void __launch_bounds__(128) AttributesKernel(const AttributeParams p)
 		const unsigned peers = __match_any_sync(active, layer);
 		const uint32_t sum = __reduce_add_sync(peers, flops);
 		if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&p.layer_cost[layer], (unsigned long long)sum);
-	}
-	if (p.normals)
-	{
-		float gx, gy, gz;
-		EvalGradient(model.tree + __ldg(&model.nodes[node].tree_offset), x, y, z, gx, gy, gz);
-		p.normals[size_t(v) * 3 + 0] = gx;
-		p.normals[size_t(v) * 3 + 1] = gy;
-		p.normals[size_t(v) * 3 + 2] = gz;
 	}
 	if (p.colors)
 	{
@@ -1683,6 +1716,29 @@ static int FinishAttributes(Model* model, Scratch& scratch, MeshResultDevice* re
 		ap.grid_z = grid_z;
 		ap.grid_dz = grid_dz;
 		ap.layer_count = layer_count;
+		ap.perm = nullptr;
+		ap.vertex_node = nullptr;
+		if (vertex_count >= 16384)
+		{
+			// node-coherent order (counting sort by octree node): worth three small kernels once there is real work
+			const uint32_t node_count = uint32_t(model->flat.nodes.size());
+			uint32_t *vertex_node = nullptr, *histogram = nullptr, *node_offset = nullptr, *perm = nullptr;
+			unsigned long long* total = nullptr;
+			TG_CUDA(scratch.Alloc(&vertex_node, vertex_count));
+			TG_CUDA(scratch.Alloc(&perm, vertex_count));
+			TG_CUDA(scratch.Alloc(&histogram, size_t(node_count) * 2));
+			TG_CUDA(scratch.Alloc(&node_offset, node_count));
+			TG_CUDA(scratch.Alloc(&total, 1));
+			TG_CUDA(cudaMemsetAsync(histogram, 0, size_t(node_count) * 8, stream));
+			VertexNodeKernel<<<(vertex_count + 255) / 256, 256, 0, stream>>>(ap.model, result->d_positions, vertex_count, vertex_node, histogram);
+			launches++;
+			int rc = DeviceExclusiveScan(stream, scratch, LoadU32{ histogram }, node_count, node_offset, total, launches, error);
+			if (rc != TG_OK) return rc;
+			VertexPermutationKernel<<<(vertex_count + 255) / 256, 256, 0, stream>>>(vertex_node, vertex_count, node_offset, histogram + node_count, perm);
+			launches++;
+			ap.perm = perm;
+			ap.vertex_node = vertex_node;
+		}
 		AttributesKernel<<<(vertex_count + 127) / 128, 128, 0, stream>>>(ap);
 		launches++;
 		TG_CUDA(cudaGetLastError());
