@@ -105,8 +105,10 @@ TG_API int tg_tree_leaf_count(const tg_tree* tree);
 TG_API tg_tree* tg_tree_load(const char* path);
 TG_API int tg_tree_save(const tg_tree* tree, const char* path);
 
-/* The synthetic benchmark tree of SURVEY.md section 8(d), config C4: `primitives` random brushes folded
- * left to right with smooth unions / differences, clipped to a 10-unit cube. */
+/* The synthetic benchmark scene, config C4 (BASELINE.json configs[3]): `primitives` random brushes (mt19937(seed)) in
+ * clusters of 8 folded left to right with smooth unions / differences, the clusters joined by a balanced tree of
+ * unions, clipped to a 10-unit cube.  (Not one deep fold: SDFOctree::Create is exponential in blend-chain depth,
+ * sdf_evaluator.cpp:793-816, so the reference could not build that tree.) */
 TG_API tg_tree* tg_make_synthetic(uint32_t primitives, uint32_t seed);
 
 /* ------------------------------------------------------------------------------------------------

@@ -14,7 +14,7 @@ oracle/Makefile) on the .tgm test models and stores, per model:
                   the sorted triangle coordinates, plus a strided sample of the raw vertices
   * ``cloud``     point-cloud export with 5 refinement iterations (export.cpp:384-469): digest + sample
 
-Usage:  python tests/golden/make_golden.py        (needs oracle/_ref/tangerine_ref; a few minutes)
+Usage:  python tests/golden/make_golden.py [model ...]   (needs oracle/_ref/tangerine_ref; a few minutes for all)
 The .tgm models themselves come from ``tangerine_ref dump-tgm`` on the reference's models/*.lua and
 on tests/golden/models_src/*.lua (see tests/golden/README.md).
 """
@@ -41,9 +41,19 @@ CASES = {
     "cones": (6, 2000, None),
     "scale": (8, 2000, None),
     "flower": (4, 2000, None),
+    # config C4 at test size: tangerine_b200.Tree.synthetic(200, 1234).save(...), see tests/golden/README.md
+    "synthetic200": (8, 3000, None),
 }
 # Larger exports whose counts SURVEY.md section 6 recorded from the reference (counts + digests only).
 BIG = {"basic_thing": 16, "gear": 32, "color-cube": 10, "seaside_town": 12.8}
+
+
+VOX_GRID, VOX_COLOR = 6.0, 37
+
+
+def file_digest(path):
+    with open(path, "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()
 
 
 def sort_rows(a):
@@ -76,7 +86,13 @@ def main():
         sys.exit("oracle/_ref/tangerine_ref not built (make -C oracle ref)")
     tmp = tempfile.mkdtemp()
     manifest = {}
+    only = sys.argv[1:]  # optional: regenerate just these models and merge them into the existing manifest
+    if only:
+        with open(os.path.join(HERE, "manifest.json")) as f:
+            manifest = json.load(f)
     for name, (cpu, npts, cloud_step) in CASES.items():
+        if only and name not in only:
+            continue
         path = O.model_path(name)
         info = json.loads(O.ref_run("info", path))
         info.pop("octree_build_s")
@@ -91,6 +107,16 @@ def main():
         O.ref_run("export", path, cpu, 0, ply_path)
         ply = O.read_ply(ply_path)
         entry = {"info": info, "cells_per_unit": cpu, "mesh": mesh_summary(ply)}
+        # whole-file digests of the reference's writers (export.cpp:60-317, magica.cpp:27-72 + VoxWriter): PLY as above,
+        # STL at the same grid, MagicaVoxel at VOX_GRID cells per unit
+        stl_path = os.path.join(tmp, name + ".stl")
+        O.ref_run("export", path, cpu, 0, stl_path)
+        vox_path = os.path.join(tmp, name + ".vox")
+        O.ref_run("vox", path, VOX_GRID, VOX_COLOR, vox_path)
+        entry["files"] = {"ply_sha256": file_digest(ply_path), "ply_bytes": os.path.getsize(ply_path),
+                          "stl_sha256": file_digest(stl_path), "stl_bytes": os.path.getsize(stl_path),
+                          "vox_sha256": file_digest(vox_path), "vox_bytes": os.path.getsize(vox_path),
+                          "vox_grid_size": VOX_GRID, "vox_color_index": VOX_COLOR}
         stride = max(1, len(ply["pos"]) // 256)
         arrays["mesh_pos_sample"] = sort_rows(ply["pos"])[::stride]
         if cloud_step:
@@ -103,6 +129,8 @@ def main():
         manifest[name] = entry
         print(name, entry["mesh"]["vertices"], entry["mesh"]["faces"], flush=True)
     for name, cpu in BIG.items():
+        if only and name not in only:
+            continue
         ply_path = os.path.join(tmp, name + "_big.ply")
         O.ref_run("export", O.model_path(name), cpu, 0, ply_path)
         manifest[name]["mesh_big"] = dict(mesh_summary(O.read_ply(ply_path)), cells_per_unit=cpu)

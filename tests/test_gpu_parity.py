@@ -15,7 +15,7 @@ from golden_util import digest, mesh_summary, same_floats, sort_rows, ulp_diff, 
 
 pytestmark = pytest.mark.gpu
 
-MODELS = ["basic_thing", "gear", "color-cube", "seaside_town", "kitchen_sink", "stencil_test", "cones", "scale", "flower"]
+MODELS = ["basic_thing", "gear", "color-cube", "seaside_town", "kitchen_sink", "stencil_test", "cones", "scale", "flower", "synthetic200"]
 
 
 @pytest.fixture(scope="module")
@@ -283,3 +283,31 @@ def test_deep_right_nested_tree_uses_stack(ctx, tmp_path):
     assert same_floats(model.eval_points(pts, T.EVAL_TREE), om.eval_tree(pts))
     assert same_floats(model.eval_points(pts, T.EVAL_GRADIENT), oc.gradient(pts))
     model.close()
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_exported_files_are_byte_identical_to_the_reference(name, golden, tmp_path):
+    """File-level entry points with the legacy FFI signatures (export.cpp:611-622, magica.cpp:77-84): the PLY, STL
+    and MagicaVoxel files written through the CUDA path hash to what the reference's writers produced
+    (tests/golden/make_golden.py: ExportCommon / VoxExport run by oracle/_ref/tangerine_ref)."""
+    import hashlib
+    import os
+    files = golden[name]["files"]
+    tree = T.Tree.load(O.model_path(name))
+    L = T.lib()
+
+    def sha(path):
+        with open(path, "rb") as f:
+            return hashlib.sha256(f.read()).hexdigest()
+
+    cpu = float(golden[name]["cells_per_unit"])
+    ply, stl, vox = (str(tmp_path / (name + ext)) for ext in (".ply", ".stl", ".vox"))
+    assert L.tg_export_ply(tree.h, cpu, 0, os.fsencode(ply), 0) == 0, L.tg_last_error()
+    assert os.path.getsize(ply) == files["ply_bytes"]
+    assert sha(ply) == files["ply_sha256"]
+    assert L.tg_export_stl(tree.h, cpu, 0, os.fsencode(stl), 0) == 0, L.tg_last_error()
+    assert os.path.getsize(stl) == files["stl_bytes"]
+    assert sha(stl) == files["stl_sha256"]
+    assert L.tg_export_magica_voxel(tree.h, files["vox_grid_size"], files["vox_color_index"], os.fsencode(vox), 0) == 0, L.tg_last_error()
+    assert os.path.getsize(vox) == files["vox_bytes"]
+    assert sha(vox) == files["vox_sha256"]

@@ -11,7 +11,7 @@ import oracle_lib as O
 from conftest import load_npz
 from golden_util import digest, mesh_summary, same_floats, vertex_records
 
-MODELS = ["basic_thing", "gear", "color-cube", "seaside_town", "kitchen_sink", "stencil_test", "cones", "scale", "flower"]
+MODELS = ["basic_thing", "gear", "color-cube", "seaside_town", "kitchen_sink", "stencil_test", "cones", "scale", "flower", "synthetic200"]
 
 
 @pytest.fixture(scope="module")
