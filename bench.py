@@ -101,23 +101,6 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def balanced_slabs(profile, world, sz):
-    """Cut [0, sz) into `world` z-slabs on 8-layer boundaries so that each holds about the same number of
-    active bricks (`profile[b]` = active bricks in brick layer b).  Deterministic: every rank computes the same cut."""
-    nb = len(profile)
-    cost = np.asarray(profile, np.float64) + 1e-3
-    cum = np.concatenate([[0.0], np.cumsum(cost)])
-    cuts = [0]
-    for r in range(1, world):
-        target = cum[-1] * r / world
-        b = int(np.searchsorted(cum, target))
-        b = max(b, cuts[-1] + 1)
-        b = min(b, nb - (world - r))
-        cuts.append(b)
-    cuts.append(nb)
-    return [(cuts[r] * 8, min(cuts[r + 1] * 8, sz)) for r in range(world)]
-
-
 def run_reference_sample(model_file, lo, hi, step, stride, threads):
     """The reference's FirstLoopInnerThunk / SecondLoopThunk on std::threads over every `stride`-th z-slice."""
     args = [REF_TOOL, "bench", model_file] + ["%.9g" % v for v in list(lo) + list(hi)] + ["%.9g" % step, str(threads), str(stride)]
@@ -186,6 +169,7 @@ def main():
     import torch
     import torch.distributed as dist
     import tangerine_b200 as T
+    from tangerine_b200.slabs import balanced_slabs, exchange_counts
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -312,10 +296,7 @@ def main():
         else:
             mesh = model.export_mesh(grid, flags=flags | T.MESH_DEVICE_ONLY, refine=refine, slab=slab)
             # the one exchange of the path: per-slab counts -> exclusive prefix -> global vertex ids
-            counts = torch.tensor([mesh.vertex_count, mesh.triangle_count], dtype=torch.int64, device="cuda")
-            gathered = torch.zeros((world, 2), dtype=torch.int64, device="cuda")
-            dist.all_gather_into_tensor(gathered, counts)
-            base = int(gathered[:rank, 0].sum().item())
+            base, _, _, _ = exchange_counts(mesh.vertex_count, mesh.triangle_count, rank, world, device="cuda")
             mesh.download(index_base=base)              # rebase on the device, then device -> host
         d2h = mesh.vertex_count * (12 + 12 + (3 if mesh.colors is not None else 0)) + mesh.triangle_count * 12
         v, f = mesh.vertex_count, mesh.triangle_count

@@ -20,6 +20,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <cmath>
 
 #include <cuda_runtime.h>
 
@@ -71,6 +73,7 @@ enum Counter
 	kCntTotalQuads = 6,
 	kCntHalo = 7,
 	kCntBrickCursor = 8,
+	kCntAttrCursor = 9,
 	kCntCount = 16
 };
 
@@ -864,117 +867,284 @@ __global__ void __launch_bounds__(kScanBlock) ScanWriteKernel(Load load, size_t 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: vertex ordering and quad emission
+// K3: vertex numbering, quad numbering and emission.
+//
+// The active-cell bitmap alone decides both numberings: a cell's vertex id is the number of active cells before it
+// in (k, j, i) order, and -- because SecondLoopThunk emits a quad whenever the three neighbour cells of an edge are
+// active, without testing the edge itself (surface_nets.cpp:1093-1096) -- the quads a cell owns are a bitwise
+// function of seven bitmap words.  So one pass scans both popcounts per 64-cell word, and one kernel then writes
+// positions and triangles at their final places.  No count travels to the host in between.
 // ------------------------------------------------------------------------------------------------
+
+// A device-side count that must fit its arrays.  When it does not, the export is going to be repeated with exact
+// sizes (the host sees the same counters), and every kernel downstream of the overflow treats the count as zero
+// instead of walking half-filled arrays.
+__device__ __forceinline__ uint32_t BoundedCount(const unsigned long long* count, uint32_t capacity)
+{
+	const unsigned long long n = *count;
+	return n > (unsigned long long)capacity ? 0u : uint32_t(n);
+}
+
+struct QuadWords
+{
+	unsigned long long z, y, x; // bit b set: cell b of the word owns the quad of its z / y / x edge
+};
+
+// Quads owned by the 64 cells of bitmap word `index` (row-major [layer][j][word]).  SecondLoopThunk
+// (surface_nets.cpp:1016-1030, 1069, 1093-1096): cells with i, j or k = 0 emit nothing; edge z needs cells
+// (i-1,j,k), (i-1,j-1,k), (i,j-1,k); edge y needs (i-1,j,k), (i-1,j,k-1), (i,j,k-1); edge x needs (i,j-1,k),
+// (i,j-1,k-1), (i,j,k-1).  Layer 0 of the bitmap is either cell layer 0 or the halo layer owned by the slab below.
+__device__ __forceinline__ QuadWords QuadMasks(const unsigned long long* __restrict__ bitmap, size_t index, unsigned long long self,
+	uint32_t row_words, uint32_t sy)
+{
+	QuadWords q = { 0ull, 0ull, 0ull };
+	if (self == 0ull) return q;
+	const size_t row = index / row_words;
+	const uint32_t wi = uint32_t(index - row * row_words);
+	const uint32_t j = uint32_t(row % sy);
+	const size_t layer = row / sy;
+	if (layer == 0 || j == 0u) return q;
+	const size_t below = index - size_t(sy) * row_words;
+	const unsigned long long b = bitmap[index - row_words], c = bitmap[below], d = bitmap[below - row_words];
+	unsigned long long wp = 0ull, bp = 0ull, cp = 0ull;
+	if (wi != 0u)
+	{
+		wp = bitmap[index - 1];
+		bp = bitmap[index - row_words - 1];
+		cp = bitmap[below - 1];
+	}
+	const unsigned long long n0 = (self << 1) | (wp >> 63); // (i-1, j,   k)
+	const unsigned long long n1 = (b << 1) | (bp >> 63);    // (i-1, j-1, k)
+	const unsigned long long n5 = (c << 1) | (cp >> 63);    // (i-1, j,   k-1)
+	const unsigned long long not_first = wi == 0u ? ~1ull : ~0ull; // i != 0
+	q.z = self & n0 & n1 & b;
+	q.y = self & n0 & n5 & c;
+	q.x = self & b & d & c & not_first;
+	return q;
+}
+
+struct LoadVertexQuadCounts
+{
+	const unsigned long long* bitmap;
+	uint32_t row_words, sy;
+	// low half: active cells of the word, high half: quads they own
+	__device__ unsigned long long operator()(size_t i) const
+	{
+		const unsigned long long w = bitmap[i];
+		if (w == 0ull) return 0ull;
+		const QuadWords q = QuadMasks(bitmap, i, w, row_words, sy);
+		return (unsigned long long)__popcll(w) | ((unsigned long long)(__popcll(q.z) + __popcll(q.y) + __popcll(q.x)) << 32);
+	}
+};
+
+__device__ __forceinline__ unsigned long long BlockExclusiveScan64(unsigned long long value, unsigned long long* warp_sums, unsigned long long& block_total)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned long long inclusive = value;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		const unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, inclusive, o);
+		if (lane >= o) inclusive += n;
+	}
+	if (lane == 31) warp_sums[warp] = inclusive;
+	__syncthreads();
+	if (warp == 0)
+	{
+		unsigned long long w = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0ull;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, w, o);
+			if (lane >= o) w += n;
+		}
+		warp_sums[lane] = w;
+	}
+	__syncthreads();
+	block_total = warp_sums[(blockDim.x >> 5) - 1];
+	const unsigned long long warp_base = warp ? warp_sums[warp - 1] : 0ull;
+	__syncthreads();
+	return warp_base + inclusive - value;
+}
+
+// Dual scan, pass 1: per-tile totals of (vertices, quads), packed low / high.
+__global__ void __launch_bounds__(kScanBlock) PairSumsKernel(LoadVertexQuadCounts load, size_t count, unsigned long long* block_sums)
+{
+	__shared__ unsigned long long warp_sums[32];
+	const size_t base = size_t(blockIdx.x) * kScanTile + size_t(threadIdx.x) * kScanItems;
+	unsigned long long sum = 0;
+#pragma unroll
+	for (int i = 0; i < kScanItems; ++i)
+	{
+		if (base + i < count) sum += load(base + i);
+	}
+	unsigned long long total;
+	BlockExclusiveScan64(sum, warp_sums, total);
+	if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// Pass 2 (one block): exclusive scan of the tile totals in place; grand totals to totals_out[0] (vertices) and [1] (quads).
+__global__ void __launch_bounds__(1024) PairSumsScanKernel(unsigned long long* block_sums, uint32_t count, unsigned long long* totals_out)
+{
+	__shared__ unsigned long long warp_sums[32];
+	__shared__ unsigned long long carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (uint32_t base = 0; base < count; base += blockDim.x)
+	{
+		const uint32_t i = base + threadIdx.x;
+		const unsigned long long v = i < count ? block_sums[i] : 0ull;
+		unsigned long long total;
+		const unsigned long long ex = BlockExclusiveScan64(v, warp_sums, total);
+		const unsigned long long c = carry;
+		if (i < count) block_sums[i] = c + ex;
+		__syncthreads();
+		if (threadIdx.x == 0) carry = c + total;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+	{
+		totals_out[0] = carry & 0xFFFFFFFFull;
+		totals_out[1] = carry >> 32;
+	}
+}
+
+// Pass 3: exclusive (vertex, quad) prefix of every bitmap word.
+__global__ void __launch_bounds__(kScanBlock) PairPrefixKernel(LoadVertexQuadCounts load, size_t count, const unsigned long long* block_sums, uint2* out)
+{
+	__shared__ unsigned long long warp_sums[32];
+	const size_t base = size_t(blockIdx.x) * kScanTile + size_t(threadIdx.x) * kScanItems;
+	unsigned long long v[kScanItems];
+	unsigned long long sum = 0;
+#pragma unroll
+	for (int i = 0; i < kScanItems; ++i)
+	{
+		v[i] = base + i < count ? load(base + i) : 0ull;
+		sum += v[i];
+	}
+	unsigned long long total;
+	unsigned long long running = BlockExclusiveScan64(sum, warp_sums, total) + block_sums[blockIdx.x];
+#pragma unroll
+	for (int i = 0; i < kScanItems; ++i)
+	{
+		if (base + i < count) out[base + i] = make_uint2(uint32_t(running), uint32_t(running >> 32));
+		running += v[i];
+	}
+}
 
 struct FaceParams
 {
+	DeviceModel model;
 	const unsigned long long* bitmap;
-	const uint32_t* prefix; // exclusive popcount prefix per bitmap word
+	const uint2* prefix;      // per bitmap word: exclusive (vertex, quad) counts
 	uint32_t row_words;
 	uint32_t sy;
 	uint32_t k_base;
-	const uint32_t* halo_ptr; // device: number of vertices in the halo layer (first in the local numbering); null = 0
+	uint32_t has_halo;        // layer 0 of the bitmap is the halo layer: its vertices come first locally and are not owned
 	const float4* tmp_pos;
 	const unsigned long long* tmp_key;
-	uint32_t tmp_count;
+	const unsigned long long* counters; // kCntTmpVertices = entries in tmp_*
+	uint32_t vertex_capacity;
+	uint32_t quad_capacity;
+	const unsigned long long* index_base; // device: added to every triangle index (vertices of the slabs below); null = 0
 	float* positions;             // 3 per owned vertex
-	unsigned long long* vertex_info; // bitmap bit index | quad mask << 56 | orientation << 60
-	uint32_t* quad_count;
-	const uint32_t* quad_offset;
-	uint32_t* triangles;
-	uint32_t vertex_count;
+	uint32_t* triangles;          // 6 indices per quad
+	uint32_t* vertex_node;        // octree node of every owned vertex (node-coherent attribute pass); may be null
+	uint32_t* node_histogram;     // vertices per octree node; may be null
+	// vertex numbering at the start of every brick layer of the slab (per-layer vertex profile)
+	uint32_t* layer_starts;
+	uint32_t profile_first_layer, profile_layers, layers_in_bitmap;
 };
-
-__device__ __forceinline__ bool CellActive(const FaceParams& p, uint32_t i, uint32_t j, uint32_t layer)
-{
-	const unsigned long long bit = ((unsigned long long)layer * p.sy + j) * ((unsigned long long)p.row_words * 64ull) + i;
-	return (p.bitmap[bit >> 6] >> (bit & 63ull)) & 1ull;
-}
 
 __device__ __forceinline__ uint32_t CellVertex(const FaceParams& p, uint32_t i, uint32_t j, uint32_t layer)
 {
 	const unsigned long long bit = ((unsigned long long)layer * p.sy + j) * ((unsigned long long)p.row_words * 64ull) + i;
 	const unsigned long long word = p.bitmap[bit >> 6];
-	return p.prefix[bit >> 6] + uint32_t(__popcll(word & ((1ull << (bit & 63ull)) - 1ull)));
+	return p.prefix[bit >> 6].x + uint32_t(__popcll(word & ((1ull << (bit & 63ull)) - 1ull)));
 }
 
-__global__ void __launch_bounds__(256) ScatterVerticesKernel(const FaceParams p)
+// One thread per extracted vertex (grid-stride over the device-side count): final position in (k, j, i) order, the
+// vertex's octree node for the attribute pass, and the triangles of the quads its cell owns, at their final offsets.
+__global__ void __launch_bounds__(256) FinalizeMeshKernel(const FaceParams p)
 {
-	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= p.tmp_count) return;
-	const unsigned long long key = p.tmp_key[t];
-	const float4 pos = p.tmp_pos[t];
-	const unsigned long long row_bits = (unsigned long long)p.row_words * 64ull;
-	const uint32_t i = uint32_t(key % row_bits);
-	const unsigned long long row = key / row_bits;
-	const uint32_t j = uint32_t(row % p.sy), layer = uint32_t(row / p.sy);
-	const unsigned long long word = p.bitmap[key >> 6];
-	const uint32_t id = p.prefix[key >> 6] + uint32_t(__popcll(word & ((1ull << (key & 63ull)) - 1ull))) - (p.halo_ptr ? __ldg(p.halo_ptr) : 0u);
-	p.positions[size_t(id) * 3 + 0] = pos.x;
-	p.positions[size_t(id) * 3 + 1] = pos.y;
-	p.positions[size_t(id) * 3 + 2] = pos.z;
-	// SecondLoopThunk (surface_nets.cpp:1016-1030, 1069, 1093-1096): lower-boundary cells emit nothing; a quad needs
-	// its three neighbour cells to be active (the shared edge is NOT tested for bipolarity).
-	uint32_t quads = 0;
-	const uint32_t k_abs = layer + p.k_base;
-	if (i != 0 && j != 0 && k_abs != 0)
+	const uint32_t stride = gridDim.x * blockDim.x;
+	const uint32_t first = blockIdx.x * blockDim.x + threadIdx.x;
+	if (first < p.profile_layers)
 	{
-		const bool n0 = CellActive(p, i - 1, j, layer), n1 = CellActive(p, i - 1, j - 1, layer), n2 = CellActive(p, i, j - 1, layer);
-		const bool n3 = CellActive(p, i, j - 1, layer - 1), n4 = CellActive(p, i, j, layer - 1), n5 = CellActive(p, i - 1, j, layer - 1);
-		quads = (n0 && n1 && n2 ? 1u : 0u) | (n0 && n5 && n4 ? 2u : 0u) | (n2 && n3 && n4 ? 4u : 0u);
+		const uint32_t k = (p.profile_first_layer + first) * kBrick; // first cell layer of that brick layer
+		const uint32_t layer = k > p.k_base ? k - p.k_base : 0u;
+		p.layer_starts[first] = layer < p.layers_in_bitmap ? p.prefix[size_t(layer) * p.sy * p.row_words].x : 0xFFFFFFFFu;
 	}
-	p.vertex_info[id] = key | ((unsigned long long)quads << 56) | ((unsigned long long)(__float_as_uint(pos.w) & 7u) << 60);
-	p.quad_count[id] = uint32_t(__popc(quads));
-}
-
-__global__ void __launch_bounds__(256) EmitTrianglesKernel(const FaceParams p)
-{
-	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-	if (v >= p.vertex_count) return;
-	const unsigned long long info = p.vertex_info[v];
-	const uint32_t quads = uint32_t(info >> 56) & 7u;
-	if (quads == 0u) return;
-	const uint32_t orient = uint32_t(info >> 60) & 7u;
-	const unsigned long long key = info & ((1ull << 56) - 1ull);
+	const uint32_t count = BoundedCount(p.counters + kCntTmpVertices, p.vertex_capacity);
+	const uint32_t halo = p.has_halo ? p.prefix[size_t(p.sy) * p.row_words].x : 0u;
+	const uint32_t base = p.index_base ? uint32_t(*p.index_base) : 0u;
 	const unsigned long long row_bits = (unsigned long long)p.row_words * 64ull;
-	const uint32_t i = uint32_t(key % row_bits);
-	const unsigned long long row = key / row_bits;
-	const uint32_t j = uint32_t(row % p.sy), layer = uint32_t(row / p.sy);
-	uint32_t out = p.quad_offset[v] * 6u;
-	const uint32_t h = p.halo_ptr ? __ldg(p.halo_ptr) : 0u;
-#pragma unroll
-	for (int e = 0; e < 3; ++e)
+	for (uint32_t t = first; t < count; t += stride)
 	{
-		if (!(quads & (1u << e))) continue;
-		uint32_t a, b, c;
-		if (e == 0) // edge z: neighbours (i-1,j,k), (i-1,j-1,k), (i,j-1,k)
+		const unsigned long long key = p.tmp_key[t];
+		const float4 pos = p.tmp_pos[t];
+		const size_t word_index = size_t(key >> 6);
+		const uint32_t bit = uint32_t(key & 63ull);
+		const unsigned long long lower = (1ull << bit) - 1ull;
+		const unsigned long long word = p.bitmap[word_index];
+		const uint2 pre = p.prefix[word_index];
+		const uint32_t id = pre.x + uint32_t(__popcll(word & lower)) - halo;
+		if (id >= p.vertex_capacity) continue;
+		p.positions[size_t(id) * 3 + 0] = pos.x;
+		p.positions[size_t(id) * 3 + 1] = pos.y;
+		p.positions[size_t(id) * 3 + 2] = pos.z;
+		if (p.vertex_node)
 		{
-			a = CellVertex(p, i - 1, j, layer);
-			b = CellVertex(p, i - 1, j - 1, layer);
-			c = CellVertex(p, i, j - 1, layer);
+			// neighbouring vertices mostly share their node: one atomic per distinct node in the warp
+			const uint32_t node = Descend(p.model.nodes, 0, pos.x, pos.y, pos.z);
+			p.vertex_node[id] = node;
+			const unsigned peers = __match_any_sync(__activemask(), node);
+			if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&p.node_histogram[node], uint32_t(__popc(peers)));
 		}
-		else if (e == 1) // edge y: (i-1,j,k), (i-1,j,k-1), (i,j,k-1)
+		const QuadWords q = QuadMasks(p.bitmap, word_index, word, p.row_words, p.sy);
+		const uint32_t quads = uint32_t((q.z >> bit) & 1ull) | (uint32_t((q.y >> bit) & 1ull) << 1) | (uint32_t((q.x >> bit) & 1ull) << 2);
+		if (quads == 0u) continue;
+		uint32_t quad = pre.y + uint32_t(__popcll(q.z & lower) + __popcll(q.y & lower) + __popcll(q.x & lower));
+		const uint32_t i = uint32_t(key % row_bits);
+		const unsigned long long row = key / row_bits;
+		const uint32_t j = uint32_t(row % p.sy), layer = uint32_t(row / p.sy);
+		const uint32_t orient = __float_as_uint(pos.w) & 7u;
+		const uint32_t shift = base - halo; // local number -> global index
+		const uint32_t v = id + base;
+#pragma unroll
+		for (int e = 0; e < 3; ++e)
 		{
-			a = CellVertex(p, i - 1, j, layer);
-			b = CellVertex(p, i - 1, j, layer - 1);
-			c = CellVertex(p, i, j, layer - 1);
+			if (!(quads & (1u << e))) continue;
+			uint32_t a, b, c;
+			if (e == 0) // edge z: neighbours (i-1,j,k), (i-1,j-1,k), (i,j-1,k)
+			{
+				a = CellVertex(p, i - 1, j, layer);
+				b = CellVertex(p, i - 1, j - 1, layer);
+				c = CellVertex(p, i, j - 1, layer);
+			}
+			else if (e == 1) // edge y: (i-1,j,k), (i-1,j,k-1), (i,j,k-1)
+			{
+				a = CellVertex(p, i - 1, j, layer);
+				b = CellVertex(p, i - 1, j, layer - 1);
+				c = CellVertex(p, i, j, layer - 1);
+			}
+			else // edge x: (i,j-1,k), (i,j-1,k-1), (i,j,k-1)
+			{
+				a = CellVertex(p, i, j - 1, layer);
+				b = CellVertex(p, i, j - 1, layer - 1);
+				c = CellVertex(p, i, j, layer - 1);
+			}
+			if (quad < p.quad_capacity)
+			{
+				const bool forward = (orient >> e) & 1u; // :1103-1105
+				const uint32_t v1 = (forward ? a : c) + shift, v2 = b + shift, v3 = (forward ? c : a) + shift;
+				uint2* out = reinterpret_cast<uint2*>(p.triangles + size_t(quad) * 6u);
+				out[0] = make_uint2(v, v1);
+				out[1] = make_uint2(v2, v);
+				out[2] = make_uint2(v2, v3);
+			}
+			quad++;
 		}
-		else // edge x: (i,j-1,k), (i,j-1,k-1), (i,j,k-1)
-		{
-			a = CellVertex(p, i, j - 1, layer);
-			b = CellVertex(p, i, j - 1, layer - 1);
-			c = CellVertex(p, i, j, layer - 1);
-		}
-		const bool forward = (orient >> e) & 1u; // :1103-1105
-		const uint32_t v1 = (forward ? a : c) - h, v2 = b - h, v3 = (forward ? c : a) - h;
-		p.triangles[out + 0] = v;
-		p.triangles[out + 1] = v1;
-		p.triangles[out + 2] = v2;
-		p.triangles[out + 3] = v;
-		p.triangles[out + 4] = v2;
-		p.triangles[out + 5] = v3;
-		out += 6;
 	}
 }
 
@@ -988,7 +1158,8 @@ struct AttributeParams
 	float* positions;
 	float* normals;      // may be null
 	unsigned char* colors; // may be null
-	uint32_t count;
+	const unsigned long long* count_ptr; // device-side vertex count ...
+	uint32_t capacity;                   // ... clamped to the capacity of the arrays
 	int refine_iterations;
 	float half_x, half_y, half_z;
 	float scale;
@@ -997,35 +1168,63 @@ struct AttributeParams
 	float grid_z, grid_dz;
 	uint32_t layer_count;
 	// node-coherent execution order: thread t works on vertex perm[t], whose octree node is vertex_node[perm[t]]
+	unsigned long long* cursor;  // device work cursor, zero at launch
 	const uint32_t* perm;        // may be null (identity)
 	const uint32_t* vertex_node; // may be null
 };
 
-// Counting sort of the vertices by octree node, so that the lanes of a warp run the same tree program.
-__global__ void __launch_bounds__(256) VertexNodeKernel(const DeviceModel model, const float* __restrict__ positions, uint32_t count,
-	uint32_t* __restrict__ vertex_node, uint32_t* __restrict__ histogram)
+// Counting sort of the vertices by octree node, so that the lanes of a warp run the same tree program.  The
+// histogram is filled by FinalizeMeshKernel (meshes) or VertexNodeKernel (point clouds).
+__global__ void __launch_bounds__(256) VertexNodeKernel(const DeviceModel model, const float* __restrict__ positions, const unsigned long long* __restrict__ count_ptr,
+	uint32_t capacity, uint32_t* __restrict__ vertex_node, uint32_t* __restrict__ histogram)
 {
-	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-	if (v >= count) return;
-	const uint32_t node = Descend(model.nodes, 0, positions[size_t(v) * 3 + 0], positions[size_t(v) * 3 + 1], positions[size_t(v) * 3 + 2]);
-	vertex_node[v] = node;
-	// neighbouring vertices mostly share their node: one atomic per distinct node in the warp
-	const unsigned peers = __match_any_sync(__activemask(), node);
-	if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&histogram[node], uint32_t(__popc(peers)));
+	const uint32_t count = BoundedCount(count_ptr, capacity);
+	const uint32_t stride = gridDim.x * blockDim.x;
+	for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < count; v += stride)
+	{
+		const uint32_t node = Descend(model.nodes, 0, positions[size_t(v) * 3 + 0], positions[size_t(v) * 3 + 1], positions[size_t(v) * 3 + 2]);
+		vertex_node[v] = node;
+		const unsigned peers = __match_any_sync(__activemask(), node);
+		if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&histogram[node], uint32_t(__popc(peers)));
+	}
 }
 
-__global__ void __launch_bounds__(256) VertexPermutationKernel(const uint32_t* __restrict__ vertex_node, uint32_t count, const uint32_t* __restrict__ node_offset,
-	uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm)
+// One block: exclusive scan of the per-node histogram (a few tens of thousands of entries).
+__global__ void __launch_bounds__(1024) NodeOffsetsKernel(const uint32_t* __restrict__ histogram, uint32_t node_count, uint32_t* __restrict__ node_offset)
 {
-	const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-	if (v >= count) return;
-	const uint32_t node = vertex_node[v];
-	const unsigned peers = __match_any_sync(__activemask(), node);
-	const int leader = __ffs(peers) - 1;
-	uint32_t base = 0;
-	if ((threadIdx.x & 31) == leader) base = atomicAdd(&cursor[node], uint32_t(__popc(peers)));
-	base = __shfl_sync(peers, base, leader);
-	perm[node_offset[node] + base + uint32_t(__popc(peers & ((1u << (threadIdx.x & 31)) - 1u)))] = v;
+	__shared__ uint32_t warp_sums[32];
+	__shared__ uint32_t carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (uint32_t base = 0; base < node_count; base += blockDim.x)
+	{
+		const uint32_t i = base + threadIdx.x;
+		const uint32_t v = i < node_count ? histogram[i] : 0u;
+		uint32_t total;
+		const uint32_t ex = BlockExclusiveScan(v, warp_sums, total);
+		const uint32_t c = carry;
+		if (i < node_count) node_offset[i] = c + ex;
+		__syncthreads();
+		if (threadIdx.x == 0) carry = c + total;
+		__syncthreads();
+	}
+}
+
+__global__ void __launch_bounds__(256) VertexPermutationKernel(const uint32_t* __restrict__ vertex_node, const unsigned long long* __restrict__ count_ptr, uint32_t capacity,
+	const uint32_t* __restrict__ node_offset, uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm)
+{
+	const uint32_t count = BoundedCount(count_ptr, capacity);
+	const uint32_t stride = gridDim.x * blockDim.x;
+	for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < count; v += stride)
+	{
+		const uint32_t node = vertex_node[v];
+		const unsigned peers = __match_any_sync(__activemask(), node);
+		const int leader = __ffs(peers) - 1;
+		uint32_t base = 0;
+		if ((threadIdx.x & 31) == leader) base = atomicAdd(&cursor[node], uint32_t(__popc(peers)));
+		base = __shfl_sync(peers, base, leader);
+		perm[node_offset[node] + base + uint32_t(__popc(peers & ((1u << (threadIdx.x & 31)) - 1u)))] = v;
+	}
 }
 
 __device__ __forceinline__ void ExportColor(const DeviceModel& model, uint32_t node, float x, float y, float z, unsigned char* out)
@@ -1046,10 +1245,28 @@ __device__ __forceinline__ void ExportColor(const DeviceModel& model, uint32_t n
 	out[2] = (unsigned char)(255.0f * b);
 }
 
+__device__ __forceinline__ void VertexAttributes(const AttributeParams& p, uint32_t t);
+
+// Persistent warps over the device-side vertex count: a warp takes the next 32 entries of the node-sorted order from
+// a device-wide cursor (so it runs one tree program, and long and short programs balance themselves over the SMs).
 __global__ void __launch_bounds__(128) AttributesKernel(const AttributeParams p)
 {
-	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= p.count) return;
+	const uint32_t count = BoundedCount(p.count_ptr, p.capacity);
+	const int lane = threadIdx.x & 31;
+	for (;;)
+	{
+		unsigned long long first = 0;
+		if (lane == 0) first = atomicAdd(p.cursor, 32ull);
+		first = __shfl_sync(0xFFFFFFFFu, first, 0);
+		if (first >= count) break;
+		const uint32_t t = uint32_t(first) + uint32_t(lane);
+		if (t < count) VertexAttributes(p, t);
+		__syncwarp();
+	}
+}
+
+__device__ __forceinline__ void VertexAttributes(const AttributeParams& p, uint32_t t)
+{
 	const uint32_t v = p.perm ? p.perm[t] : t;
 	float x = p.positions[size_t(v) * 3 + 0], y = p.positions[size_t(v) * 3 + 1], z = p.positions[size_t(v) * 3 + 2];
 	const DeviceModel& model = p.model;
@@ -1112,27 +1329,48 @@ __global__ void __launch_bounds__(128) AttributesKernel(const AttributeParams p)
 }
 
 // WriteSTL (export.cpp:130-140): gradient at the triangle centroid, before the vertices are scaled.
+// *quad_count_ptr quads (two triangles each), clamped to quad_capacity.
 __global__ void __launch_bounds__(128) FaceNormalsKernel(const DeviceModel model, const float* positions, const uint32_t* triangles,
-	uint32_t triangle_count, float inv_scale_unused, float* out)
+	const unsigned long long* quad_count_ptr, uint32_t quad_capacity, float* out)
 {
-	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= triangle_count) return;
-	const uint32_t a = triangles[size_t(t) * 3 + 0], b = triangles[size_t(t) * 3 + 1], c = triangles[size_t(t) * 3 + 2];
-	const float cx = ((positions[size_t(a) * 3 + 0] + positions[size_t(b) * 3 + 0]) + positions[size_t(c) * 3 + 0]) / 3.0f;
-	const float cy = ((positions[size_t(a) * 3 + 1] + positions[size_t(b) * 3 + 1]) + positions[size_t(c) * 3 + 1]) / 3.0f;
-	const float cz = ((positions[size_t(a) * 3 + 2] + positions[size_t(b) * 3 + 2]) + positions[size_t(c) * 3 + 2]) / 3.0f;
-	const uint32_t node = Descend(model.nodes, 0, cx, cy, cz);
-	float gx, gy, gz;
-	EvalGradient(model.tree + __ldg(&model.nodes[node].tree_offset), cx, cy, cz, gx, gy, gz);
-	out[size_t(t) * 3 + 0] = gx;
-	out[size_t(t) * 3 + 1] = gy;
-	out[size_t(t) * 3 + 2] = gz;
+	const uint32_t triangle_count = BoundedCount(quad_count_ptr, quad_capacity) * 2u;
+	const uint32_t stride = gridDim.x * blockDim.x;
+	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < triangle_count; t += stride)
+	{
+		const uint32_t a = triangles[size_t(t) * 3 + 0], b = triangles[size_t(t) * 3 + 1], c = triangles[size_t(t) * 3 + 2];
+		const float cx = ((positions[size_t(a) * 3 + 0] + positions[size_t(b) * 3 + 0]) + positions[size_t(c) * 3 + 0]) / 3.0f;
+		const float cy = ((positions[size_t(a) * 3 + 1] + positions[size_t(b) * 3 + 1]) + positions[size_t(c) * 3 + 1]) / 3.0f;
+		const float cz = ((positions[size_t(a) * 3 + 2] + positions[size_t(b) * 3 + 2]) + positions[size_t(c) * 3 + 2]) / 3.0f;
+		const uint32_t node = Descend(model.nodes, 0, cx, cy, cz);
+		float gx, gy, gz;
+		EvalGradient(model.tree + __ldg(&model.nodes[node].tree_offset), cx, cy, cz, gx, gy, gz);
+		out[size_t(t) * 3 + 0] = gx;
+		out[size_t(t) * 3 + 1] = gy;
+		out[size_t(t) * 3 + 2] = gz;
+	}
 }
 
-__global__ void ScalePositionsKernel(float* positions, size_t count, float scale)
+__global__ void ScalePositionsKernel(float* positions, const unsigned long long* vertex_count_ptr, uint32_t vertex_capacity, float scale)
 {
-	const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-	if (i < count) positions[i] = positions[i] * scale;
+	const size_t count = size_t(BoundedCount(vertex_count_ptr, vertex_capacity)) * 3;
+	const size_t stride = size_t(gridDim.x) * blockDim.x;
+	for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) positions[i] = positions[i] * scale;
+}
+
+// Delivers device-side words straight into page-locked host memory (the mailbox).  A kernel rather than a
+// cudaMemcpyAsync: a copy on the compute stream would queue on the DMA engine behind the large result copies that
+// run on the copy stream, and everything enqueued after it on the compute stream would wait with it.
+__global__ void MailKernel(const uint32_t* __restrict__ a, uint32_t na, uint32_t* __restrict__ host_a, const uint32_t* __restrict__ b, uint32_t nb, uint32_t* __restrict__ host_b)
+{
+	for (uint32_t i = threadIdx.x; i < na; i += blockDim.x) host_a[i] = a[i];
+	for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) host_b[i] = b[i];
+	__threadfence_system();
+}
+
+// Slab pipeline: after a slab's triangles are out, the vertices it owned are added to the running index base.
+__global__ void AdvanceIndexBaseKernel(unsigned long long* index_base, const unsigned long long* counters, uint32_t vertex_capacity)
+{
+	if (threadIdx.x == 0 && blockIdx.x == 0) *index_base += min(counters[kCntTmpVertices], (unsigned long long)vertex_capacity);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1353,6 +1591,14 @@ Context* Context::Create(int device, std::string& error)
 		return nullptr;
 	}
 	c->copy_stream = copy_stream;
+	cudaStream_t stream2;
+	if ((e = cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking)) != cudaSuccess)
+	{
+		error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+		delete c;
+		return nullptr;
+	}
+	c->stream2 = stream2;
 	cudaEvent_t ce0;
 	cudaEventCreateWithFlags(&ce0, cudaEventDisableTiming);
 	c->copy_events[0] = ce0;
@@ -1394,6 +1640,10 @@ Context::~Context()
 		if (ev) cudaEventDestroy(static_cast<cudaEvent_t>(ev));
 	}
 	if (arena) cudaFree(arena);
+	if (arena2) cudaFree(arena2);
+	if (stream2) cudaStreamDestroy(static_cast<cudaStream_t>(stream2));
+	if (index_base) cudaFree(index_base);
+	for (void* m : mailboxes) cudaFreeHost(m);
 	if (copy_events[0]) cudaEventDestroy(static_cast<cudaEvent_t>(copy_events[0]));
 	if (copy_stream) cudaStreamDestroy(static_cast<cudaStream_t>(copy_stream));
 	if (stream) cudaStreamDestroy(StreamOf(this));
@@ -1425,6 +1675,31 @@ void* Context::AcquirePinned(size_t bytes, std::string& error)
 	b.in_use = true;
 	pinned.push_back(b);
 	return b.ptr;
+}
+
+constexpr size_t kMailboxBytes = 16384;
+
+void* Context::AcquireMailbox(std::string& error)
+{
+	if (!mailboxes.empty())
+	{
+		void* p = mailboxes.back();
+		mailboxes.pop_back();
+		return p;
+	}
+	void* p = nullptr;
+	cudaError_t e = cudaMallocHost(&p, kMailboxBytes);
+	if (e != cudaSuccess)
+	{
+		error = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
+		return nullptr;
+	}
+	return p;
+}
+
+void Context::ReleaseMailbox(void* ptr)
+{
+	if (ptr) mailboxes.push_back(ptr);
 }
 
 void Context::ReleasePinned(void* ptr)
@@ -1569,24 +1844,30 @@ struct Scratch
 {
 	Context* ctx;
 	cudaStream_t stream;
+	void*& arena;
+	size_t& arena_bytes;
 	std::vector<void*> blocks;
 	size_t used = 0;
 	size_t wanted = 0;
-	explicit Scratch(Context* c) : ctx(c), stream(static_cast<cudaStream_t>(c->stream)) {}
+	// lane 0: the context's stream and arena; lane 1: the second compute lane of the slab pipeline
+	explicit Scratch(Context* c, int lane = 0)
+		: ctx(c), stream(static_cast<cudaStream_t>(lane ? c->stream2 : c->stream)), arena(lane ? c->arena2 : c->arena), arena_bytes(lane ? c->arena2_bytes : c->arena_bytes)
+	{
+	}
 	~Scratch()
 	{
 		for (void* b : blocks) cudaFreeAsync(b, stream);
-		if (wanted > ctx->arena_bytes)
+		if (wanted > arena_bytes)
 		{
-			if (ctx->arena) cudaFreeAsync(ctx->arena, stream);
-			ctx->arena = nullptr;
-			ctx->arena_bytes = 0;
+			if (arena) cudaFreeAsync(arena, stream);
+			arena = nullptr;
+			arena_bytes = 0;
 			const size_t bytes = wanted + wanted / 4 + (size_t(1) << 20);
 			void* p = nullptr;
 			if (cudaMallocAsync(&p, bytes, stream) == cudaSuccess)
 			{
-				ctx->arena = p;
-				ctx->arena_bytes = bytes;
+				arena = p;
+				arena_bytes = bytes;
 			}
 		}
 	}
@@ -1595,9 +1876,9 @@ struct Scratch
 	{
 		const size_t bytes = (std::max<size_t>(count * sizeof(T), 256) + 255) & ~size_t(255);
 		wanted += bytes;
-		if (used + bytes <= ctx->arena_bytes)
+		if (used + bytes <= arena_bytes)
 		{
-			*out = reinterpret_cast<T*>(static_cast<char*>(ctx->arena) + used);
+			*out = reinterpret_cast<T*>(static_cast<char*>(arena) + used);
 			used += bytes;
 			return cudaSuccess;
 		}
@@ -1686,134 +1967,179 @@ struct StageTimer
 	}
 };
 
-// Shared tail of mesh and point-cloud export: refinement / normals / colours, download.
-static int FinishAttributes(Model* model, Scratch& scratch, MeshResultDevice* result, uint32_t vertex_count, const tg_mesh_options& options,
-	const float half[3], uint64_t& launches, std::string& error, unsigned long long* layer_cost = nullptr, float grid_z = 0.0f, float grid_dz = 1.0f, uint32_t layer_count = 1)
+// Shared tail of mesh and point-cloud export: refinement / normals / colours.  The vertex count stays on the device
+// (*count_ptr, clamped to `capacity`, which also sizes the attribute arrays), so nothing here waits for the host.
+// `histogram_filled`: FinalizeMeshKernel already produced vertex_node[] and the per-node histogram.
+struct AttributeScratch
 {
-	Context* ctx = model->context;
-	cudaStream_t stream = StreamOf(ctx);
-	const bool want_normals = (options.flags & TG_MESH_NORMALS) != 0;
-	const bool want_colors = (options.flags & TG_MESH_COLORS) != 0 && model->flat.has_paint;
-	const float scale = options.scale == 0.0f ? 1.0f : options.scale;
-	if (vertex_count == 0) return TG_OK;
-	if (want_normals) TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_normals), size_t(vertex_count) * 12, stream));
-	if (want_colors) TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_colors), size_t(vertex_count) * 3, stream));
-	const bool face_normals = (options.flags & TG_MESH_FACE_NORMALS) != 0;
-	if (want_normals || want_colors || options.refine_iterations > 0 || (scale != 1.0f && !face_normals))
-	{
-		AttributeParams ap;
-		ap.model = MakeDeviceModel(model);
-		ap.positions = result->d_positions;
-		ap.normals = result->d_normals;
-		ap.colors = result->d_colors;
-		ap.count = vertex_count;
-		ap.refine_iterations = options.refine_iterations;
-		ap.half_x = half[0];
-		ap.half_y = half[1];
-		ap.half_z = half[2];
-		ap.scale = face_normals ? 1.0f : scale; // STL scales after the centroid normals (export.cpp:142-145)
-		ap.layer_cost = layer_cost;
-		ap.grid_z = grid_z;
-		ap.grid_dz = grid_dz;
-		ap.layer_count = layer_count;
-		ap.perm = nullptr;
-		ap.vertex_node = nullptr;
-		if (vertex_count >= 16384)
-		{
-			// node-coherent order (counting sort by octree node): worth three small kernels once there is real work
-			const uint32_t node_count = uint32_t(model->flat.nodes.size());
-			uint32_t *vertex_node = nullptr, *histogram = nullptr, *node_offset = nullptr, *perm = nullptr;
-			unsigned long long* total = nullptr;
-			TG_CUDA(scratch.Alloc(&vertex_node, vertex_count));
-			TG_CUDA(scratch.Alloc(&perm, vertex_count));
-			TG_CUDA(scratch.Alloc(&histogram, size_t(node_count) * 2));
-			TG_CUDA(scratch.Alloc(&node_offset, node_count));
-			TG_CUDA(scratch.Alloc(&total, 1));
-			TG_CUDA(cudaMemsetAsync(histogram, 0, size_t(node_count) * 8, stream));
-			VertexNodeKernel<<<(vertex_count + 255) / 256, 256, 0, stream>>>(ap.model, result->d_positions, vertex_count, vertex_node, histogram);
-			launches++;
-			int rc = DeviceExclusiveScan(stream, scratch, LoadU32{ histogram }, node_count, node_offset, total, launches, error);
-			if (rc != TG_OK) return rc;
-			VertexPermutationKernel<<<(vertex_count + 255) / 256, 256, 0, stream>>>(vertex_node, vertex_count, node_offset, histogram + node_count, perm);
-			launches++;
-			ap.perm = perm;
-			ap.vertex_node = vertex_node;
-		}
-		AttributesKernel<<<(vertex_count + 127) / 128, 128, 0, stream>>>(ap);
-		launches++;
-		TG_CUDA(cudaGetLastError());
-	}
-	(void)scratch;
+	uint32_t* vertex_node = nullptr;
+	uint32_t* histogram = nullptr; // node_count counters + node_count cursors
+};
+
+static int PrepareAttributeScratch(Model* model, cudaStream_t stream, Scratch& scratch, uint32_t capacity, AttributeScratch& as, std::string& error)
+{
+	const uint32_t node_count = uint32_t(model->flat.nodes.size());
+	TG_CUDA(scratch.Alloc(&as.vertex_node, capacity));
+	TG_CUDA(scratch.Alloc(&as.histogram, size_t(node_count) * 2));
+	TG_CUDA(cudaMemsetAsync(as.histogram, 0, size_t(node_count) * 8, stream));
 	return TG_OK;
 }
 
-// K0 driver.  Leaves the list of 8-cell bricks that must be evaluated (plus, for slab runs, the halo bricks of
-// the row below, flagged) in *out_list, its length on the device in counters[kCntListA] and its capacity in
-// *out_count.  No host round trip at all: the brick kernel reads the length itself.
-static int BuildActiveList(Model* model, cudaStream_t stream, Scratch& scratch, const DeviceGrid& grid, uint32_t k_begin, uint32_t k_end,
-	bool has_halo, bool no_cull, unsigned long long* counters, uint32_t** out_list, uint64_t* out_count, uint64_t& launches, std::string& error)
+static bool WantsAttributePass(const Model* model, const tg_mesh_options& options)
+{
+	const bool want_normals = (options.flags & TG_MESH_NORMALS) != 0;
+	const bool want_colors = (options.flags & TG_MESH_COLORS) != 0 && model->flat.has_paint;
+	const bool face_normals = (options.flags & TG_MESH_FACE_NORMALS) != 0;
+	const float scale = options.scale == 0.0f ? 1.0f : options.scale;
+	return want_normals || want_colors || options.refine_iterations > 0 || (scale != 1.0f && !face_normals);
+}
+
+// Resident blocks of `kernel` per SM times the SM count: the grid of a persistent kernel.
+template <typename Kernel>
+static uint32_t PersistentGrid(const Context* ctx, Kernel kernel, int threads)
+{
+	int per_sm = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+	return uint32_t(ctx->sm_count) * uint32_t(per_sm);
+}
+
+static int EnqueueAttributes(Model* model, Scratch& scratch, MeshResultDevice* result, const unsigned long long* count_ptr, unsigned long long* cursor, uint32_t capacity,
+	const tg_mesh_options& options, const float half[3], AttributeScratch& as, bool histogram_filled, uint64_t& launches, std::string& error,
+	unsigned long long* layer_cost = nullptr, float grid_z = 0.0f, float grid_dz = 1.0f, uint32_t layer_count = 1)
+{
+	Context* ctx = model->context;
+	cudaStream_t stream = scratch.stream;
+	const bool want_normals = (options.flags & TG_MESH_NORMALS) != 0;
+	const bool want_colors = (options.flags & TG_MESH_COLORS) != 0 && model->flat.has_paint;
+	const float scale = options.scale == 0.0f ? 1.0f : options.scale;
+	if (capacity == 0) return TG_OK;
+	if (want_normals) TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_normals), size_t(capacity) * 12, stream));
+	if (want_colors) TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_colors), size_t(capacity) * 3, stream));
+	const bool face_normals = (options.flags & TG_MESH_FACE_NORMALS) != 0;
+	if (!WantsAttributePass(model, options)) return TG_OK;
+	AttributeParams ap;
+	ap.model = MakeDeviceModel(model);
+	ap.positions = result->d_positions;
+	ap.normals = result->d_normals;
+	ap.colors = result->d_colors;
+	ap.count_ptr = count_ptr;
+	ap.capacity = capacity;
+	ap.refine_iterations = options.refine_iterations;
+	ap.half_x = half[0];
+	ap.half_y = half[1];
+	ap.half_z = half[2];
+	ap.scale = face_normals ? 1.0f : scale; // STL scales after the centroid normals (export.cpp:142-145)
+	ap.layer_cost = layer_cost;
+	ap.grid_z = grid_z;
+	ap.grid_dz = grid_dz;
+	ap.layer_count = layer_count;
+	// node-coherent order: counting sort of the vertices by octree node
+	const uint32_t node_count = uint32_t(model->flat.nodes.size());
+	static const uint32_t wide_node = PersistentGrid(ctx, VertexNodeKernel, 256), wide_perm = PersistentGrid(ctx, VertexPermutationKernel, 256);
+	static const uint32_t wide_attr = PersistentGrid(ctx, AttributesKernel, 128);
+	uint32_t *node_offset = nullptr, *perm = nullptr;
+	TG_CUDA(scratch.Alloc(&perm, capacity));
+	TG_CUDA(scratch.Alloc(&node_offset, node_count));
+	if (!histogram_filled)
+	{
+		VertexNodeKernel<<<wide_node, 256, 0, stream>>>(ap.model, result->d_positions, count_ptr, capacity, as.vertex_node, as.histogram);
+		launches++;
+	}
+	NodeOffsetsKernel<<<1, 1024, 0, stream>>>(as.histogram, node_count, node_offset);
+	VertexPermutationKernel<<<wide_perm, 256, 0, stream>>>(as.vertex_node, count_ptr, capacity, node_offset, as.histogram + node_count, perm);
+	launches += 2;
+	ap.perm = perm;
+	ap.vertex_node = as.vertex_node;
+	ap.cursor = cursor;
+	AttributesKernel<<<uint32_t(std::min<uint64_t>((uint64_t(capacity) + 127) / 128, wide_attr)), 128, 0, stream>>>(ap);
+	launches++;
+	TG_CUDA(cudaGetLastError());
+	return TG_OK;
+}
+
+// K0 driver, part 1: the cull flags of every level for cell layers [k_begin, k_end) (plus the halo layer below when
+// has_halo).  `flags_storage` (device, FlagWords(grid) words) is zeroed here; the item lists are scratch.
+static size_t FlagWords(const DeviceGrid& grid)
+{
+	const uint32_t nbx = (grid.sx + kBrick - 1) / kBrick, nby = (grid.sy + kBrick - 1) / kBrick, nbz = (grid.sz + kBrick - 1) / kBrick;
+	size_t words = 0;
+	for (int level = 0; level < kCullLevels; ++level)
+	{
+		words += size_t((nbx + (1u << level) - 1) >> level) * ((nby + (1u << level) - 1) >> level) * ((nbz + (1u << level) - 1) >> level);
+	}
+	return words;
+}
+
+static int BuildCullFlags(Model* model, cudaStream_t stream, Scratch& scratch, const DeviceGrid& grid, uint32_t k_begin, uint32_t k_end,
+	bool has_halo, bool no_cull, uint32_t* flags_storage, CullParams& cp, uint64_t& launches, std::string& error)
 {
 	const uint32_t nbx = (grid.sx + kBrick - 1) / kBrick, nby = (grid.sy + kBrick - 1) / kBrick, nbz = (grid.sz + kBrick - 1) / kBrick;
 	const uint32_t bz_begin = k_begin / kBrick, bz_end = (k_end + kBrick - 1) / kBrick;
 	const uint32_t row_begin = has_halo ? bz_begin - 1 : bz_begin;
-	const size_t slab_bricks = size_t(nbx) * nby * (bz_end - row_begin);
-	const size_t list_capacity = slab_bricks + 8;
-	uint32_t* active_list = nullptr;
-	TG_CUDA(scratch.Alloc(&active_list, list_capacity));
-
-	CullParams cp;
 	cp.model = MakeDeviceModel(model);
 	cp.grid = grid;
 	cp.cell_k_lo = has_halo ? k_begin - 1 : k_begin;
 	cp.cell_k_hi = k_end;
 	cp.sample_k_lo = cp.cell_k_lo;
 	cp.sample_k_hi = k_end;
-	uint32_t* counts = nullptr;
-	TG_CUDA(scratch.Alloc(&counts, kCullLevels));
-	cp.counts = counts;
+	cp.ranges = nullptr;
+	cp.counts = nullptr;
+	cp.level = 0;
 	size_t flag_words = 0;
 	for (int level = 0; level < kCullLevels; ++level)
 	{
 		cp.dims[level][0] = (nbx + (1u << level) - 1) >> level;
 		cp.dims[level][1] = (nby + (1u << level) - 1) >> level;
 		cp.dims[level][2] = (nbz + (1u << level) - 1) >> level;
+		cp.flags[level] = no_cull ? nullptr : flags_storage + flag_words;
+		cp.lists[level] = nullptr;
+		cp.capacity[level] = 0;
 		flag_words += size_t(cp.dims[level][0]) * cp.dims[level][1] * cp.dims[level][2];
 	}
-	if (!no_cull)
+	if (no_cull) return TG_OK;
+	uint32_t* counts = nullptr;
+	TG_CUDA(scratch.Alloc(&counts, kCullLevels));
+	cp.counts = counts;
+	TG_CUDA(cudaMemsetAsync(flags_storage, 0, flag_words * 4, stream));
+	TG_CUDA(cudaMemsetAsync(counts, 0, kCullLevels * 4, stream));
+	TG_CUDA(scratch.Alloc(&cp.ranges, cp.model.region_count));
+	for (int level = 0; level < kCullLevels; ++level)
 	{
-		uint32_t* flags = nullptr;
-		TG_CUDA(scratch.Alloc(&flags, flag_words));
-		TG_CUDA(cudaMemsetAsync(flags, 0, flag_words * 4, stream));
-		TG_CUDA(cudaMemsetAsync(counts, 0, kCullLevels * 4, stream));
-		TG_CUDA(scratch.Alloc(&cp.ranges, cp.model.region_count));
-		for (int level = 0; level < kCullLevels; ++level)
-		{
-			cp.flags[level] = flags;
-			flags += size_t(cp.dims[level][0]) * cp.dims[level][1] * cp.dims[level][2];
-			// every region can seed up to 27 items at its start level; splits add at most the bricks of the level below
-			const size_t cells = size_t(cp.dims[level][0]) * cp.dims[level][1] * ((bz_end - row_begin + (1u << level) - 1) >> level);
-			cp.capacity[level] = uint32_t(std::min<size_t>(size_t(cp.model.region_count) * 8 + cells * 4 + 65536, 0x7FFFFFFFu));
-			TG_CUDA(scratch.Alloc(&cp.lists[level], cp.capacity[level]));
-		}
-		cp.level = 0;
-		CullRegionInitKernel<<<(cp.model.region_count + 127) / 128, 128, 0, stream>>>(cp);
+		// every region can seed up to 27 items at its start level; splits add at most the bricks of the level below
+		const size_t cells = size_t(cp.dims[level][0]) * cp.dims[level][1] * ((bz_end - row_begin + (1u << level) - 1) >> level);
+		cp.capacity[level] = uint32_t(std::min<size_t>(size_t(cp.model.region_count) * 8 + cells * 4 + 65536, 0x7FFFFFFFu));
+		TG_CUDA(scratch.Alloc(&cp.lists[level], cp.capacity[level]));
+	}
+	CullRegionInitKernel<<<(cp.model.region_count + 127) / 128, 128, 0, stream>>>(cp);
+	launches++;
+	// Levels run top-down with grids sized for the level's capacity bound by what can actually arrive
+	// (threads beyond the device-side count exit at once), so no count is read back between levels.
+	uint64_t bound = 0;
+	for (int level = kCullLevels - 1; level >= 0; --level)
+	{
+		const uint64_t seeded = std::min<uint64_t>(uint64_t(cp.model.region_count) * kSeedSpan * kSeedSpan * kSeedSpan, cp.capacity[level]);
+		bound = std::min<uint64_t>(bound * 8u + seeded, cp.capacity[level]);
+		cp.level = level;
+		CullLevelKernel<<<uint32_t((bound + 127) / 128), 128, 0, stream>>>(cp);
 		launches++;
-		// Levels run top-down with grids sized for the level's capacity bound by what can actually arrive
-		// (threads beyond the device-side count exit at once), so no count is read back between levels.
-		uint64_t bound = 0;
-		for (int level = kCullLevels - 1; level >= 0; --level)
-		{
-			const uint64_t seeded = std::min<uint64_t>(uint64_t(cp.model.region_count) * kSeedSpan * kSeedSpan * kSeedSpan, cp.capacity[level]);
-			bound = std::min<uint64_t>(bound * 8u + seeded, cp.capacity[level]);
-			cp.level = level;
-			CullLevelKernel<<<uint32_t((bound + 127) / 128), 128, 0, stream>>>(cp);
-			launches++;
-		}
 	}
-	else
-	{
-		for (int level = 0; level < kCullLevels; ++level) cp.flags[level] = nullptr;
-	}
+	TG_CUDA(cudaGetLastError());
+	return TG_OK;
+}
+
+// K0 driver, part 2: the list of 8-cell bricks of cell layers [k_begin, k_end) that must be evaluated (plus, for slab
+// runs, the halo bricks of the row below, flagged) in *out_list, its length on the device in counters[kCntListA] and
+// its capacity in *out_count.  No host round trip at all: the brick kernel reads the length itself.
+static int ResolveActiveList(cudaStream_t stream, Scratch& scratch, const CullParams& cp, const DeviceGrid& grid, uint32_t k_begin, uint32_t k_end,
+	bool has_halo, bool no_cull, unsigned long long* counters, uint32_t** out_list, uint64_t* out_count, uint64_t& launches, std::string& error)
+{
+	const uint32_t nbx = (grid.sx + kBrick - 1) / kBrick, nby = (grid.sy + kBrick - 1) / kBrick;
+	const uint32_t bz_begin = k_begin / kBrick, bz_end = (k_end + kBrick - 1) / kBrick;
+	const uint32_t row_begin = has_halo ? bz_begin - 1 : bz_begin;
+	const size_t slab_bricks = size_t(nbx) * nby * (bz_end - row_begin);
+	const size_t list_capacity = slab_bricks + 8;
+	uint32_t* active_list = nullptr;
+	TG_CUDA(scratch.Alloc(&active_list, list_capacity));
 	const uint32_t resolve_threads = uint32_t(slab_bricks);
 	CullResolveKernel<<<(resolve_threads + 255) / 256, 256, 0, stream>>>(cp, row_begin, bz_end, has_halo ? bz_begin - 1 : 0xFFFFFFFFu, no_cull ? 1 : 0,
 		active_list, counters + kCntListA, uint32_t(list_capacity));
@@ -1824,13 +2150,89 @@ static int BuildActiveList(Model* model, cudaStream_t stream, Scratch& scratch, 
 	return TG_OK;
 }
 
-int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options& options, tg_mesh* out, std::string& error)
+static int BuildActiveList(Model* model, cudaStream_t stream, Scratch& scratch, const DeviceGrid& grid, uint32_t k_begin, uint32_t k_end,
+	bool has_halo, bool no_cull, unsigned long long* counters, uint32_t** out_list, uint64_t* out_count, uint64_t& launches, std::string& error)
 {
-	std::memset(out, 0, sizeof(*out));
-	Context* ctx = model->context;
-	TG_CUDA(cudaSetDevice(ctx->device));
-	cudaStream_t stream = StreamOf(ctx);
+	CullParams cp;
+	uint32_t* flags = nullptr;
+	if (!no_cull) TG_CUDA(scratch.Alloc(&flags, FlagWords(grid)));
+	int rc = BuildCullFlags(model, stream, scratch, grid, k_begin, k_end, has_halo, no_cull, flags, cp, launches, error);
+	if (rc != TG_OK) return rc;
+	return ResolveActiveList(stream, scratch, cp, grid, k_begin, k_end, has_halo, no_cull, counters, out_list, out_count, launches, error);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mesh export.  A MeshJob is one slab's work enqueued on the context's stream with NO host round trip: every
+// count (active bricks, vertices, quads) stays on the device, later kernels read it there, and the arrays are sized
+// by a capacity.  The host learns the counts from a small pinned mailbox filled by two async copies and only then
+// issues the device -> host copies of the exact sizes.  If a capacity was too small the export is repeated once with
+// the exact sizes (the counts are exact even when the arrays overflowed).
+// ------------------------------------------------------------------------------------------------
+
+struct Mailbox
+{
+	unsigned long long counters[kCntCount];
+	uint32_t halo_vertices;
+	uint32_t pad[15];
+	uint32_t layer_starts[1024];
+	unsigned long long layer_cost[1024];
+};
+
+struct MeshJob
+{
+	Model* model = nullptr;
 	DeviceGrid grid;
+	tg_mesh_options options;
+	uint32_t k_begin = 0, k_end = 0, k_base = 0, layers = 0, row_words = 0;
+	uint32_t bz_begin = 0, bz_end = 0, nbz_all = 0, profile_layers = 0;
+	bool has_halo = false;
+	uint64_t own_bricks = 0, list_capacity = 0;
+	uint32_t cap_v = 0, cap_q = 0;
+	unsigned long long* counters = nullptr; // device
+	MeshResultDevice* result = nullptr;
+	Mailbox* mailbox = nullptr;             // pinned host
+	cudaEvent_t marks[6] = {};              // start, cull, eval, scan, faces, attributes
+	cudaEvent_t faces_ready = nullptr, all_ready = nullptr;
+	uint64_t launches = 0;
+	bool enqueued = false;
+	int lane = 0;
+
+	~MeshJob()
+	{
+		for (cudaEvent_t e : marks)
+		{
+			if (e) cudaEventDestroy(e);
+		}
+		if (faces_ready) cudaEventDestroy(faces_ready);
+		if (all_ready) cudaEventDestroy(all_ready);
+		if (mailbox && model) model->context->ReleaseMailbox(mailbox);
+	}
+};
+
+static void DefaultCapacities(uint64_t slab_cells, uint32_t& cap_v, uint32_t& cap_q)
+{
+	// surfaces occupy a few percent of the cells at most; quads come to about one per vertex (three at the very most)
+	const uint64_t v = std::min<uint64_t>(slab_cells, std::max<uint64_t>(slab_cells / 32, 1 << 21));
+	cap_v = uint32_t(std::min<uint64_t>(v, 0xFFFFFFF0ull));
+	cap_q = uint32_t(std::min<uint64_t>(std::min<uint64_t>(v * 3, std::max<uint64_t>(v + v / 2, 1 << 20)), 0x2AAAAAA0ull));
+	if (const char* env = std::getenv("TG_TEST_CAPACITY")) // tests: force the overflow-and-repeat path
+	{
+		const long n = std::atol(env);
+		if (n > 0) cap_v = cap_q = uint32_t(n);
+	}
+}
+
+// Enqueues one slab: culling, brick evaluation, numbering, emission, attributes, mailbox copies.  Does not wait.
+// index_base (device, may be null) is added to every triangle index and then advanced by the slab's vertex count.
+static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const tg_mesh_options& options, uint32_t cap_v, uint32_t cap_q,
+	unsigned long long* index_base, std::string& error, int lane = 0, cudaEvent_t base_ready = nullptr, const CullParams* shared_cull = nullptr)
+{
+	Context* ctx = model->context;
+	cudaStream_t stream = static_cast<cudaStream_t>(lane ? ctx->stream2 : ctx->stream);
+	job.lane = lane;
+	job.model = model;
+	job.options = options;
+	DeviceGrid& grid = job.grid;
 	if (!MakeDeviceGrid(grid_in, grid, error)) return TG_ERR_INVALID;
 
 	uint32_t k_begin = 0, k_end = grid.sz;
@@ -1845,277 +2247,718 @@ int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options
 		}
 	}
 	const bool has_halo = k_begin > 0;
+	const bool face_normals = (options.flags & TG_MESH_FACE_NORMALS) != 0;
+	if (face_normals && has_halo)
+	{
+		error = "face normals are not available for slab exports";
+		return TG_ERR_UNSUPPORTED;
+	}
 	const uint32_t k_base = has_halo ? k_begin - 1 : k_begin;
 	const uint32_t layers = k_end - k_base;
 	const uint32_t row_words = (grid.sx + 63) / 64;
 	const size_t bitmap_words = size_t(layers) * grid.sy * row_words;
 	const uint32_t nbx = (grid.sx + kBrick - 1) / kBrick, nby = (grid.sy + kBrick - 1) / kBrick;
 	const uint32_t bz_begin = k_begin / kBrick, bz_end = (k_end + kBrick - 1) / kBrick;
-	const size_t own_bricks = size_t(nbx) * nby * (bz_end - bz_begin);
-	const size_t halo_bricks = has_halo ? size_t(nbx) * nby : 0;
-	const size_t list_capacity = own_bricks + halo_bricks + 8;
+	const uint32_t nbz_all = (grid.sz + kBrick - 1) / kBrick;
+	if (nbz_all > 1024)
+	{
+		error = "grids deeper than 8192 cell layers are not supported";
+		return TG_ERR_UNSUPPORTED;
+	}
+	job.k_begin = k_begin;
+	job.k_end = k_end;
+	job.k_base = k_base;
+	job.layers = layers;
+	job.row_words = row_words;
+	job.bz_begin = bz_begin;
+	job.bz_end = bz_end;
+	job.nbz_all = nbz_all;
+	job.profile_layers = bz_end - bz_begin;
+	job.has_halo = has_halo;
+	job.own_bricks = uint64_t(nbx) * nby * (bz_end - bz_begin);
+	const uint64_t slab_cells = uint64_t(grid.sx) * grid.sy * (k_end - k_begin);
+	if (cap_v == 0) DefaultCapacities(slab_cells, cap_v, cap_q);
+	job.cap_v = cap_v;
+	job.cap_q = cap_q;
 
-	ctx->stage.store(1);
-	ctx->progress_done[0] = 0;
-	ctx->progress_total[0] = own_bricks;
-	if (ctx->Cancelled()) return TG_ERR_CANCELLED;
+	for (cudaEvent_t& e : job.marks) TG_CUDA(cudaEventCreate(&e));
+	TG_CUDA(cudaEventCreateWithFlags(&job.faces_ready, cudaEventDisableTiming));
+	TG_CUDA(cudaEventCreateWithFlags(&job.all_ready, cudaEventDisableTiming));
+	static_assert(sizeof(Mailbox) <= kMailboxBytes, "mailbox block too small");
+	job.mailbox = static_cast<Mailbox*>(ctx->AcquireMailbox(error));
+	if (!job.mailbox) return TG_ERR_MEMORY;
+	job.result = new MeshResultDevice();
+	job.result->context = ctx;
+	MeshResultDevice* result = job.result;
 
-	Scratch scratch(ctx);
-	StageTimer timer(stream);
-	uint64_t launches = 0;
-	tg_mesh_timings& tm = out->timings;
-	tm.bricks_total = own_bricks;
-
+	Scratch scratch(ctx, lane);
+	uint64_t& launches = job.launches;
 	unsigned long long* counters = nullptr;
 	uint32_t* active_list = nullptr;
 	unsigned long long* bitmap = nullptr;
-	uint32_t* prefix = nullptr;
+	uint2* prefix = nullptr;
 	TG_CUDA(scratch.Alloc(&counters, kCntCount));
 	TG_CUDA(scratch.Alloc(&bitmap, bitmap_words));
 	TG_CUDA(scratch.Alloc(&prefix, bitmap_words));
 	TG_CUDA(cudaMemsetAsync(counters, 0, kCntCount * 8, stream));
 	TG_CUDA(cudaMemsetAsync(bitmap, 0, bitmap_words * 8, stream));
-	const int t_start = timer.Mark();
+	job.counters = counters;
+	TG_CUDA(cudaEventRecord(job.marks[0], stream));
 
 	// ---- K0: active brick list -------------------------------------------------------------------
 	const bool no_cull = (options.flags & TG_MESH_NO_CULL) != 0;
-	unsigned long long host_counts[kCntCount];
-	uint64_t list_capacity_out = 0;
 	{
-		const int rc0 = BuildActiveList(model, stream, scratch, grid, k_begin, k_end, has_halo, no_cull, counters, &active_list, &list_capacity_out, launches, error);
+		// a pipelined export culls the whole grid once and every slab only resolves its rows of the shared flags
+		const int rc0 = shared_cull
+			? ResolveActiveList(stream, scratch, *shared_cull, grid, k_begin, k_end, has_halo, no_cull, counters, &active_list, &job.list_capacity, launches, error)
+			: BuildActiveList(model, stream, scratch, grid, k_begin, k_end, has_halo, no_cull, counters, &active_list, &job.list_capacity, launches, error);
 		if (rc0 != TG_OK) return rc0;
 	}
-	TG_CUDA(cudaGetLastError());
-	const int t_cull = timer.Mark();
-	ctx->progress_done[0] = own_bricks / 2;
-	if (ctx->Cancelled()) return TG_ERR_CANCELLED;
+	TG_CUDA(cudaEventRecord(job.marks[1], stream));
 
 	// ---- K1 + K2: evaluate bricks, classify, extract vertices ------------------------------------
+	float4* tmp_pos = nullptr;
+	unsigned long long* tmp_key = nullptr;
+	TG_CUDA(scratch.Alloc(&tmp_pos, cap_v));
+	TG_CUDA(scratch.Alloc(&tmp_key, cap_v));
 	MeshParams mp;
 	mp.model = MakeDeviceModel(model);
 	mp.grid = grid;
 	mp.bricks = active_list;
 	mp.brick_count = counters + kCntListA;
-	mp.brick_capacity = uint32_t(list_capacity_out);
+	mp.brick_capacity = uint32_t(job.list_capacity);
 	mp.bitmap = bitmap;
 	mp.row_words = row_words;
 	mp.k_base = k_base;
 	mp.k_own_begin = k_begin;
 	mp.k_own_end = k_end;
 	mp.counters = counters;
-	// The brick count is still on the device, so the staging buffers are sized from the slab: surfaces occupy a few
-	// percent of the cells at most.  If that ever falls short the exact count is known after the first attempt.
-	const uint64_t slab_cells = uint64_t(grid.sx) * grid.sy * (k_end - k_begin);
-	uint64_t tmp_capacity = std::min<uint64_t>(slab_cells, std::max<uint64_t>(slab_cells / 16, 1 << 20));
-	uint64_t tmp_count = 0;
-	uint64_t active_count = 0;
-	float4* tmp_pos = nullptr;
-	unsigned long long* tmp_key = nullptr;
+	mp.tmp_pos = tmp_pos;
+	mp.tmp_key = tmp_key;
+	mp.tmp_capacity = cap_v;
+	// persistent warps: the grid fills every SM; warps beyond the list length leave at their first fetch
+	MeshBricksKernel<<<uint32_t(ctx->sm_count) * uint32_t(ctx->brick_blocks_per_sm), kBrickThreads, 0, stream>>>(mp);
+	launches++;
+	TG_CUDA(cudaGetLastError());
+	TG_CUDA(cudaEventRecord(job.marks[2], stream));
+
+	// ---- vertex + quad numbering: one dual scan over the bitmap ----------------------------------
+	{
+		const LoadVertexQuadCounts load{ bitmap, row_words, grid.sy };
+		const uint32_t blocks = uint32_t((bitmap_words + kScanTile - 1) / kScanTile);
+		unsigned long long* sums = nullptr;
+		TG_CUDA(scratch.Alloc(&sums, std::max<uint32_t>(blocks, 1)));
+		PairSumsKernel<<<blocks, kScanBlock, 0, stream>>>(load, bitmap_words, sums);
+		PairSumsScanKernel<<<1, 1024, 0, stream>>>(sums, blocks, counters + kCntTotalVertices);
+		PairPrefixKernel<<<blocks, kScanBlock, 0, stream>>>(load, bitmap_words, sums, prefix);
+		launches += 3;
+		TG_CUDA(cudaGetLastError());
+	}
+	TG_CUDA(cudaEventRecord(job.marks[3], stream));
+
+	// ---- K3: final vertex order, triangles -------------------------------------------------------
+	uint32_t* layer_starts = nullptr;
+	unsigned long long* layer_cost = nullptr;
+	TG_CUDA(scratch.Alloc(&layer_starts, job.profile_layers + 2));
+	TG_CUDA(scratch.Alloc(&layer_cost, nbz_all));
+	TG_CUDA(cudaMemsetAsync(layer_cost, 0, size_t(nbz_all) * 8, stream));
+	TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_positions), size_t(cap_v) * 12, stream));
+	TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_triangles), size_t(cap_q) * 24, stream));
+	const bool attribute_pass = WantsAttributePass(model, options);
+	AttributeScratch as;
+	if (attribute_pass)
+	{
+		const int rc1 = PrepareAttributeScratch(model, stream, scratch, cap_v, as, error);
+		if (rc1 != TG_OK) return rc1;
+	}
+	FaceParams fp;
+	fp.model = mp.model;
+	fp.bitmap = bitmap;
+	fp.prefix = prefix;
+	fp.row_words = row_words;
+	fp.sy = grid.sy;
+	fp.k_base = k_base;
+	fp.has_halo = has_halo ? 1u : 0u;
+	fp.tmp_pos = tmp_pos;
+	fp.tmp_key = tmp_key;
+	fp.counters = counters;
+	fp.vertex_capacity = cap_v;
+	fp.quad_capacity = cap_q;
+	fp.index_base = index_base;
+	fp.positions = result->d_positions;
+	fp.triangles = result->d_triangles;
+	fp.vertex_node = as.vertex_node;
+	fp.node_histogram = as.histogram;
+	fp.layer_starts = layer_starts;
+	fp.profile_first_layer = bz_begin;
+	fp.profile_layers = job.profile_layers;
+	fp.layers_in_bitmap = layers;
+	static const uint32_t wide_finalize = PersistentGrid(ctx, FinalizeMeshKernel, 256);
+	if (base_ready) TG_CUDA(cudaStreamWaitEvent(stream, base_ready, 0)); // the slab below has advanced the index base
+	FinalizeMeshKernel<<<wide_finalize, 256, 0, stream>>>(fp);
+	launches++;
+	if (index_base)
+	{
+		AdvanceIndexBaseKernel<<<1, 32, 0, stream>>>(index_base, counters, cap_v);
+		launches++;
+	}
+	TG_CUDA(cudaGetLastError());
+	TG_CUDA(cudaEventRecord(job.marks[4], stream));
+	// first mailbox delivery: every count, and the halo total (vertices of bitmap layer 0)
+	job.mailbox->halo_vertices = 0;
+	MailKernel<<<1, 128, 0, stream>>>(reinterpret_cast<const uint32_t*>(counters), kCntCount * 2, reinterpret_cast<uint32_t*>(job.mailbox->counters),
+		layer_starts, job.profile_layers, job.mailbox->layer_starts);
+	if (has_halo) MailKernel<<<1, 32, 0, stream>>>(&prefix[size_t(grid.sy) * row_words].x, 1, &job.mailbox->halo_vertices, nullptr, 0, nullptr);
+	TG_CUDA(cudaGetLastError());
+	TG_CUDA(cudaEventRecord(job.faces_ready, stream));
+
+	// ---- K4: attributes ----------------------------------------------------------------------
+	ctx->stage.store(options.refine_iterations > 0 ? 2 : 3);
+	const float half[3] = { grid.dx / 2.0f, grid.dy / 2.0f, grid.dz / 2.0f };
+	int rc = EnqueueAttributes(model, scratch, result, counters + kCntTmpVertices, counters + kCntAttrCursor, cap_v, options, half, as, true, launches, error, layer_cost, grid.z, grid.dz, nbz_all);
+	if (rc != TG_OK) return rc;
+	if (face_normals)
+	{
+		TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_face_normals), size_t(cap_q) * 24, stream));
+		FaceNormalsKernel<<<uint32_t(ctx->sm_count) * 16u, 128, 0, stream>>>(MakeDeviceModel(model), result->d_positions, result->d_triangles, counters + kCntTotalQuads, cap_q, result->d_face_normals);
+		launches++;
+		const float scale = options.scale == 0.0f ? 1.0f : options.scale;
+		if (scale != 1.0f)
+		{
+			ScalePositionsKernel<<<uint32_t(ctx->sm_count) * 8u, 256, 0, stream>>>(result->d_positions, counters + kCntTmpVertices, cap_v, scale);
+			launches++;
+		}
+	}
+	TG_CUDA(cudaGetLastError());
+	TG_CUDA(cudaEventRecord(job.marks[5], stream));
+	MailKernel<<<1, 128, 0, stream>>>(reinterpret_cast<const uint32_t*>(layer_cost), nbz_all * 2, reinterpret_cast<uint32_t*>(job.mailbox->layer_cost), nullptr, 0, nullptr);
+	TG_CUDA(cudaGetLastError());
+	TG_CUDA(cudaEventRecord(job.all_ready, stream));
+	job.enqueued = true;
+	return TG_OK;
+}
+
+// What a finished job reports once its first mailbox delivery arrived.
+struct MeshCounts
+{
+	uint64_t vertices = 0, quads = 0, halo = 0;
+	bool overflow = false;
+};
+
+static int WaitCounts(MeshJob& job, MeshCounts& counts, std::string& error)
+{
+	TG_CUDA(cudaEventSynchronize(job.faces_ready));
+	const Mailbox& mb = *job.mailbox;
+	counts.vertices = mb.counters[kCntTmpVertices];
+	counts.quads = mb.counters[kCntTotalQuads];
+	counts.halo = mb.halo_vertices;
+	counts.overflow = counts.vertices > job.cap_v || counts.quads > job.cap_q;
+	return TG_OK;
+}
+
+// Fills the host-side bookkeeping of *out from a completed job (everything but the arrays).
+static int FinishJob(MeshJob& job, const MeshCounts& counts, tg_mesh* out, std::string& error)
+{
+	TG_CUDA(cudaEventSynchronize(job.all_ready));
+	const Mailbox& mb = *job.mailbox;
+	tg_mesh_timings& tm = out->timings;
+	auto ms = [&](int a, int b) {
+		float v = 0.f;
+		cudaEventElapsedTime(&v, job.marks[a], job.marks[b]);
+		return v;
+	};
+	tm.cull_ms = ms(0, 1);
+	tm.evaluate_ms = ms(1, 2);
+	tm.compact_ms = ms(2, 3);
+	tm.faces_ms = ms(3, 4);
+	tm.attributes_ms = ms(4, 5);
+	tm.total_device_ms = ms(0, 5);
+	tm.bricks_total = job.own_bricks;
+	tm.bricks_evaluated = std::min<unsigned long long>(mb.counters[kCntListA], job.list_capacity);
+	tm.samples_evaluated = tm.bricks_evaluated ? mb.counters[kCntSamples] : 0;
+	tm.algorithmic_flops = tm.bricks_evaluated ? mb.counters[kCntFlops] : 0;
+	tm.kernel_launches = job.launches;
+	out->vertex_count = counts.vertices;
+	out->triangle_count = counts.quads * 2;
+	out->halo_vertices = counts.halo;
+	// vertices owned per brick layer (absolute layer index); layers outside the slab stay 0
+	const uint32_t nbz = job.nbz_all;
+	uint32_t* profile = static_cast<uint32_t*>(std::calloc(nbz, sizeof(uint32_t)));
+	if (profile && counts.vertices > 0)
+	{
+		for (uint32_t i = 0; i < job.profile_layers; ++i)
+		{
+			const uint32_t begin = mb.layer_starts[i];
+			const uint32_t end = (i + 1 < job.profile_layers && mb.layer_starts[i + 1] != 0xFFFFFFFFu) ? mb.layer_starts[i + 1] : uint32_t(counts.vertices + counts.halo);
+			profile[job.bz_begin + i] = end >= begin ? end - begin : 0u;
+		}
+	}
+	out->layer_vertices = profile;
+	out->layer_count = nbz;
+	double* cost = static_cast<double*>(std::calloc(nbz, sizeof(double)));
+	if (cost)
+	{
+		for (uint32_t i = 0; i < nbz; ++i) cost[i] = double(mb.layer_cost[i]);
+	}
+	out->layer_vertex_cost = cost;
+	return TG_OK;
+}
+
+static void FreeResultDevice(MeshResultDevice* r, cudaStream_t s)
+{
+	if (!r) return;
+	if (r->d_positions) cudaFreeAsync(r->d_positions, s);
+	if (r->d_normals) cudaFreeAsync(r->d_normals, s);
+	if (r->d_colors) cudaFreeAsync(r->d_colors, s);
+	if (r->d_triangles) cudaFreeAsync(r->d_triangles, s);
+	if (r->d_face_normals) cudaFreeAsync(r->d_face_normals, s);
+	r->d_positions = r->d_normals = r->d_face_normals = nullptr;
+	r->d_colors = nullptr;
+	r->d_triangles = nullptr;
+}
+
+// One slab (or the whole grid) in one shot.
+static int ExportMeshOnce(Model* model, const tg_grid& grid_in, const tg_mesh_options& options, tg_mesh* out, std::string& error)
+{
+	Context* ctx = model->context;
+	cudaStream_t stream = StreamOf(ctx);
+	cudaStream_t copy_stream = static_cast<cudaStream_t>(ctx->copy_stream);
+	const bool want_host = !(options.flags & TG_MESH_DEVICE_ONLY);
+	uint32_t cap_v = 0, cap_q = 0;
 	for (int attempt = 0; attempt < 2; ++attempt)
 	{
-		TG_CUDA(scratch.Alloc(&tmp_pos, tmp_capacity));
-		TG_CUDA(scratch.Alloc(&tmp_key, tmp_capacity));
-		mp.tmp_pos = tmp_pos;
-		mp.tmp_key = tmp_key;
-		mp.tmp_capacity = uint32_t(std::min<uint64_t>(tmp_capacity, 0xFFFFFFFFull));
-		TG_CUDA(cudaMemsetAsync(counters + kCntTmpVertices, 0, 3 * 8, stream));
-		TG_CUDA(cudaMemsetAsync(counters + kCntBrickCursor, 0, 8, stream));
-		// persistent warps: the grid fills every SM; warps beyond the list length leave at their first fetch
-		MeshBricksKernel<<<uint32_t(ctx->sm_count) * uint32_t(ctx->brick_blocks_per_sm), kBrickThreads, 0, stream>>>(mp);
-		launches++;
-		TG_CUDA(cudaGetLastError());
-		TG_CUDA(cudaMemcpyAsync(host_counts, counters, kCntCount * 8, cudaMemcpyDeviceToHost, stream));
-		TG_CUDA(cudaStreamSynchronize(stream));
-		tmp_count = host_counts[kCntTmpVertices];
-		active_count = std::min<unsigned long long>(host_counts[kCntListA], list_capacity_out);
-		if (tmp_count <= tmp_capacity) break;
-		tmp_capacity = tmp_count; // exact size is known now; the bitmap writes are idempotent
+		MeshJob job;
+		int rc = EnqueueMesh(job, model, grid_in, options, cap_v, cap_q, nullptr, error);
+		MeshCounts counts;
+		if (rc == TG_OK) rc = WaitCounts(job, counts, error);
+		if (rc != TG_OK)
+		{
+			cudaStreamSynchronize(stream);
+			FreeResultDevice(job.result, stream);
+			delete job.result;
+			return rc;
+		}
+		if (counts.vertices > 0xFFFFFFF0ull || counts.quads * 2 > 0xFFFFFFF0ull)
+		{
+			cudaStreamSynchronize(stream);
+			FreeResultDevice(job.result, stream);
+			delete job.result;
+			error = "mesh exceeds 2^32 vertices or triangles";
+			return TG_ERR_UNSUPPORTED;
+		}
+		if (counts.overflow)
+		{
+			// exact sizes are known now; run again with them
+			cudaStreamSynchronize(stream);
+			FreeResultDevice(job.result, stream);
+			delete job.result;
+			if (attempt == 1)
+			{
+				error = "mesh capacities overflowed twice";
+				return TG_ERR_CUDA;
+			}
+			cap_v = uint32_t(std::max<uint64_t>(counts.vertices, 1));
+			cap_q = uint32_t(std::max<uint64_t>(counts.quads, 1));
+			continue;
+		}
+		MeshResultDevice* result = job.result;
+		out->opaque = result;
+		const auto h0 = std::chrono::steady_clock::now();
+		auto fetch = [&](cudaStream_t on, void* device, size_t bytes, void** host) -> int
+		{
+			if (!device || bytes == 0) return TG_OK;
+			void* p = ctx->AcquirePinned(bytes, error);
+			if (!p) return TG_ERR_MEMORY;
+			result->pinned.push_back(p);
+			TG_CUDA(cudaMemcpyAsync(p, device, bytes, cudaMemcpyDeviceToHost, on));
+			*host = p;
+			return TG_OK;
+		};
+		if (want_host && counts.quads > 0)
+		{
+			// the index buffer is final: bring it home on the copy stream while the attributes are computed
+			TG_CUDA(cudaStreamWaitEvent(copy_stream, job.faces_ready, 0));
+			if ((rc = fetch(copy_stream, result->d_triangles, size_t(counts.quads) * 24, reinterpret_cast<void**>(&out->triangles))) != TG_OK) return rc;
+		}
+		if ((rc = FinishJob(job, counts, out, error)) != TG_OK) return rc;
+		if (want_host && counts.vertices > 0)
+		{
+			const size_t v = size_t(counts.vertices);
+			if ((rc = fetch(stream, result->d_positions, v * 12, reinterpret_cast<void**>(&out->positions))) != TG_OK) return rc;
+			if ((rc = fetch(stream, result->d_normals, v * 12, reinterpret_cast<void**>(&out->normals))) != TG_OK) return rc;
+			if ((rc = fetch(stream, result->d_colors, v * 3, reinterpret_cast<void**>(&out->colors))) != TG_OK) return rc;
+			if ((rc = fetch(stream, result->d_face_normals, size_t(counts.quads) * 24, reinterpret_cast<void**>(&out->face_normals))) != TG_OK) return rc;
+		}
+		if (want_host)
+		{
+			TG_CUDA(cudaStreamSynchronize(copy_stream));
+			TG_CUDA(cudaStreamSynchronize(stream));
+			// the arrays are home: the device copies are not needed any more
+			FreeResultDevice(result, stream);
+		}
+		out->timings.download_ms = want_host ? float(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count()) : 0.0f;
+		return TG_OK;
 	}
-	tm.bricks_evaluated = active_count;
-	if (tmp_count > 0xFFFFFFF0ull)
-	{
-		error = "mesh exceeds 2^32 vertices";
-		return TG_ERR_UNSUPPORTED;
-	}
-	tm.samples_evaluated = active_count ? host_counts[kCntSamples] : 0;
-	tm.algorithmic_flops = active_count ? host_counts[kCntFlops] : 0;
-	const int t_eval = timer.Mark();
-	ctx->progress_done[0] = own_bricks;
-	if (ctx->Cancelled()) return TG_ERR_CANCELLED;
+	return TG_ERR_CUDA;
+}
 
-	// ---- vertex numbering: exclusive scan over the bitmap ---------------------------------------
-	int rc = DeviceExclusiveScan(stream, scratch, LoadPopcount{ bitmap }, bitmap_words, prefix, counters + kCntTotalVertices, launches, error);
-	if (rc != TG_OK) return rc;
-	const uint32_t vertex_count = uint32_t(tmp_count);
-	const uint32_t* halo_ptr = has_halo ? prefix + size_t(grid.sy) * row_words : nullptr; // vertices of the halo layer come first locally
+// Host-side destination of a pipelined export: one page-locked array per attribute, filled slab by slab.
+struct HostArrays
+{
+	Context* ctx = nullptr;
+	float* positions = nullptr;
+	float* normals = nullptr;
+	uint8_t* colors = nullptr;
+	uint32_t* triangles = nullptr;
+	uint64_t cap_v = 0, cap_t = 0;
+	bool want_normals = false, want_colors = false;
+
+	void Release()
+	{
+		if (positions) ctx->ReleasePinned(positions);
+		if (normals) ctx->ReleasePinned(normals);
+		if (colors) ctx->ReleasePinned(colors);
+		if (triangles) ctx->ReleasePinned(triangles);
+		positions = normals = nullptr;
+		colors = nullptr;
+		triangles = nullptr;
+		cap_v = cap_t = 0;
+	}
+
+	template <typename T>
+	bool Grow(T*& array, uint64_t old_count, uint64_t new_count, size_t item_bytes, std::string& error)
+	{
+		T* bigger = static_cast<T*>(ctx->AcquirePinned(size_t(new_count) * item_bytes, error));
+		if (!bigger) return false;
+		if (array)
+		{
+			std::memcpy(bigger, array, size_t(old_count) * item_bytes);
+			ctx->ReleasePinned(array);
+		}
+		array = bigger;
+		return true;
+	}
+
+	// Makes room for v vertices and t triangles; `live_v` / `live_t` entries are already in place (copies drained by the caller).
+	bool Reserve(uint64_t v, uint64_t t, uint64_t live_v, uint64_t live_t, std::string& error)
+	{
+		if (v > cap_v)
+		{
+			const uint64_t n = std::max<uint64_t>(v + v / 2, 1024);
+			if (!Grow(positions, live_v, n, 12, error)) return false;
+			if (want_normals && !Grow(normals, live_v, n, 12, error)) return false;
+			if (want_colors && !Grow(colors, live_v, n, 3, error)) return false;
+			cap_v = n;
+		}
+		if (t > cap_t)
+		{
+			const uint64_t n = std::max<uint64_t>(t + t / 2, 1024);
+			if (!Grow(triangles, live_t, n, 12, error)) return false;
+			cap_t = n;
+		}
+		return true;
+	}
+};
+
+constexpr int TG_RETRY_ONE_SHOT = 1000; // internal: the pipelined export gave up (a slab overflowed its capacity)
+
+// Whole-grid export with host results, software-pipelined over z-slabs on ONE device: while slab c is evaluated its
+// predecessor's arrays travel device -> host on the copy stream, straight to their final place in the host arrays
+// (vertex numbering is (k, j, i)-lexicographic, so slabs concatenate; triangle indices are made global on the device
+// by the running index base).  Same kernels and the same halo rule as the multi-GPU partition.
+static int ExportMeshPipelined(Model* model, const tg_grid& grid_in, const tg_mesh_options& options, int chunks, tg_mesh* out, std::string& error)
+{
+	Context* ctx = model->context;
+	cudaStream_t stream = StreamOf(ctx);
+	cudaStream_t copy_stream = static_cast<cudaStream_t>(ctx->copy_stream);
+	DeviceGrid grid;
+	if (!MakeDeviceGrid(grid_in, grid, error)) return TG_ERR_INVALID;
+	const uint32_t nbz = (grid.sz + kBrick - 1) / kBrick;
+	chunks = std::max(1, std::min<int>(chunks, int(nbz)));
+	if (!ctx->index_base) TG_CUDA(cudaMalloc(&ctx->index_base, 8));
+	unsigned long long* index_base = static_cast<unsigned long long*>(ctx->index_base);
+	TG_CUDA(cudaMemsetAsync(index_base, 0, 8, stream));
+	// Optional second compute lane (TG_PIPELINE_LANES=2): even slabs on the context's stream, odd slabs on the second
+	// one, each with its own scratch arena.  The lanes meet only at the running index base (slab c's triangles need
+	// the vertex total of slabs < c).
+	cudaStream_t lane1 = static_cast<cudaStream_t>(ctx->stream2);
+	// K0 once for the whole grid; its flags outlive the slabs, its item lists only this block (they sit in the lane-0
+	// arena, which slab 0 reuses later on the same stream)
+	CullParams shared_cull;
+	uint32_t* shared_flags = nullptr;
+	uint64_t cull_launches = 0;
+	const bool no_cull = (options.flags & TG_MESH_NO_CULL) != 0;
+	cudaEvent_t cull_marks[2] = { nullptr, nullptr };
+	TG_CUDA(cudaEventCreate(&cull_marks[0]));
+	TG_CUDA(cudaEventCreate(&cull_marks[1]));
+	TG_CUDA(cudaEventRecord(cull_marks[0], stream));
+	{
+		if (!no_cull) TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&shared_flags), FlagWords(grid) * 4, stream));
+		Scratch cull_scratch(ctx, 0);
+		const int rc = BuildCullFlags(model, stream, cull_scratch, grid, 0, grid.sz, false, no_cull, shared_flags, shared_cull, cull_launches, error);
+		if (rc != TG_OK)
+		{
+			if (shared_flags) cudaFreeAsync(shared_flags, stream);
+			cudaEventDestroy(cull_marks[0]);
+			cudaEventDestroy(cull_marks[1]);
+			return rc;
+		}
+	}
+	TG_CUDA(cudaEventRecord(cull_marks[1], stream));
+	TG_CUDA(cudaStreamWaitEvent(lane1, cull_marks[1], 0));
+
+	HostArrays host;
+	host.ctx = ctx;
+	host.want_normals = (options.flags & TG_MESH_NORMALS) != 0;
+	host.want_colors = (options.flags & TG_MESH_COLORS) != 0 && model->flat.has_paint;
+	const uint32_t shape_flags = options.flags & (TG_MESH_NORMALS | TG_MESH_COLORS | TG_MESH_NO_CULL);
+	{
+		// exact when this context just exported the same model on the same grid, else surface ~ 6 cells^(2/3)
+		const auto& last = ctx->last_export;
+		const double cells = double(grid.sx) * grid.sy * grid.sz;
+		uint64_t v = uint64_t(6.0 * std::pow(cells, 2.0 / 3.0)) + 65536, t = 2 * v;
+		if (last.model == model && last.sx == grid.sx && last.sy == grid.sy && last.sz == grid.sz && last.flags == shape_flags)
+		{
+			v = last.vertices;
+			t = last.triangles;
+		}
+		host.positions = static_cast<float*>(ctx->AcquirePinned(size_t(std::max<uint64_t>(v, 1)) * 12, error));
+		if (host.want_normals) host.normals = static_cast<float*>(ctx->AcquirePinned(size_t(std::max<uint64_t>(v, 1)) * 12, error));
+		if (host.want_colors) host.colors = static_cast<uint8_t*>(ctx->AcquirePinned(size_t(std::max<uint64_t>(v, 1)) * 3, error));
+		host.triangles = static_cast<uint32_t*>(ctx->AcquirePinned(size_t(std::max<uint64_t>(t, 1)) * 12, error));
+		if (!host.positions || !host.triangles || (host.want_normals && !host.normals) || (host.want_colors && !host.colors))
+		{
+			host.Release();
+			return TG_ERR_MEMORY;
+		}
+		host.cap_v = v;
+		host.cap_t = t;
+	}
+
+	std::vector<std::unique_ptr<MeshJob>> jobs;
+	jobs.reserve(size_t(chunks));
+	uint64_t v_done = 0, t_done = 0;
+	tg_mesh_timings total;
+	std::memset(&total, 0, sizeof(total));
+	std::vector<uint32_t> layer_vertices(nbz, 0u);
+	std::vector<double> layer_cost(nbz, 0.0);
+
+	auto abandon = [&](int rc) {
+		cudaStreamSynchronize(stream);
+		cudaStreamSynchronize(lane1);
+		cudaStreamSynchronize(copy_stream);
+		if (shared_flags) cudaFreeAsync(shared_flags, stream);
+		cudaEventDestroy(cull_marks[0]);
+		cudaEventDestroy(cull_marks[1]);
+		for (auto& j : jobs)
+		{
+			if (j && j->result)
+			{
+				FreeResultDevice(j->result, stream);
+				delete j->result;
+				j->result = nullptr;
+			}
+		}
+		host.Release();
+		return rc;
+	};
+
+	auto collect = [&](int c) -> int {
+		MeshJob& job = *jobs[size_t(c)];
+		MeshCounts counts;
+		int rc = WaitCounts(job, counts, error);
+		if (rc != TG_OK) return rc;
+		if (counts.overflow) return TG_RETRY_ONE_SHOT;
+		const uint64_t v = counts.vertices, t = counts.quads * 2;
+		if (v_done + v > 0xFFFFFFF0ull || t_done + t > 0xFFFFFFF0ull)
+		{
+			error = "mesh exceeds 2^32 vertices or triangles";
+			return TG_ERR_UNSUPPORTED;
+		}
+		if (v_done + v > host.cap_v || t_done + t > host.cap_t)
+		{
+			TG_CUDA(cudaStreamSynchronize(copy_stream)); // earlier slabs must have landed before the arrays move
+			if (!host.Reserve(v_done + v, t_done + t, v_done, t_done, error)) return TG_ERR_MEMORY;
+		}
+		MeshResultDevice* r = job.result;
+		if (t > 0)
+		{
+			TG_CUDA(cudaStreamWaitEvent(copy_stream, job.faces_ready, 0));
+			TG_CUDA(cudaMemcpyAsync(host.triangles + t_done * 3, r->d_triangles, size_t(t) * 12, cudaMemcpyDeviceToHost, copy_stream));
+		}
+		tg_mesh part;
+		std::memset(&part, 0, sizeof(part));
+		if ((rc = FinishJob(job, counts, &part, error)) != TG_OK) return rc;
+		if (v > 0)
+		{
+			TG_CUDA(cudaStreamWaitEvent(copy_stream, job.all_ready, 0));
+			TG_CUDA(cudaMemcpyAsync(host.positions + v_done * 3, r->d_positions, size_t(v) * 12, cudaMemcpyDeviceToHost, copy_stream));
+			if (host.normals && r->d_normals) TG_CUDA(cudaMemcpyAsync(host.normals + v_done * 3, r->d_normals, size_t(v) * 12, cudaMemcpyDeviceToHost, copy_stream));
+			if (host.colors && r->d_colors) TG_CUDA(cudaMemcpyAsync(host.colors + v_done * 3, r->d_colors, size_t(v) * 3, cudaMemcpyDeviceToHost, copy_stream));
+		}
+		const tg_mesh_timings& tm = part.timings;
+		total.cull_ms += tm.cull_ms;
+		total.evaluate_ms += tm.evaluate_ms;
+		total.compact_ms += tm.compact_ms;
+		total.faces_ms += tm.faces_ms;
+		total.attributes_ms += tm.attributes_ms;
+		total.bricks_total += tm.bricks_total;
+		total.bricks_evaluated += tm.bricks_evaluated;
+		total.samples_evaluated += tm.samples_evaluated;
+		total.algorithmic_flops += tm.algorithmic_flops;
+		total.kernel_launches += tm.kernel_launches;
+		for (uint32_t i = 0; i < nbz && i < part.layer_count; ++i)
+		{
+			if (part.layer_vertices) layer_vertices[i] += part.layer_vertices[i];
+			if (part.layer_vertex_cost) layer_cost[i] += part.layer_vertex_cost[i];
+		}
+		std::free(part.layer_vertices);
+		std::free(part.layer_vertex_cost);
+		v_done += v;
+		t_done += t;
+		ctx->progress_done[0] = uint64_t(c + 1);
+		return TG_OK;
+	};
+
+	ctx->progress_total[0] = uint64_t(chunks);
+	// One compute lane by default.  Two lanes (even / odd slabs on two streams with their own scratch arenas, so that a
+	// slab's persistent brick kernel fills the SMs while its predecessor drains) measured no better on seaside 1024^3:
+	// the small numbering / attribute kernels of slab c then queue behind the resident blocks of slab c + 1.
+	int lanes = 1;
+	if (const char* env = std::getenv("TG_PIPELINE_LANES")) lanes = std::atoi(env) >= 2 ? 2 : 1;
+	const auto h0 = std::chrono::steady_clock::now();
+	for (int c = 0; c < chunks; ++c)
+	{
+		if (ctx->Cancelled()) return abandon(TG_ERR_CANCELLED);
+		tg_mesh_options slab = options;
+		slab.flags |= TG_MESH_DEVICE_ONLY;
+		slab.slab_begin = uint64_t(nbz) * uint64_t(c) / uint64_t(chunks) * kBrick;
+		slab.slab_end = c + 1 == chunks ? grid.sz : uint64_t(nbz) * uint64_t(c + 1) / uint64_t(chunks) * kBrick;
+		jobs.emplace_back(new MeshJob());
+		int rc = EnqueueMesh(*jobs.back(), model, grid_in, slab, 0, 0, index_base, error, lanes > 1 ? (c & 1) : 0, c > 0 ? jobs[size_t(c) - 1]->faces_ready : nullptr, &shared_cull);
+		if (rc != TG_OK) return abandon(rc);
+		if (c > 0 && (rc = collect(c - 1)) != TG_OK) return abandon(rc);
+	}
+	{
+		const int rc = collect(chunks - 1);
+		if (rc != TG_OK) return abandon(rc);
+	}
+	TG_CUDA(cudaStreamSynchronize(copy_stream));
+	TG_CUDA(cudaStreamSynchronize(lane1));
+	TG_CUDA(cudaStreamSynchronize(stream));
+	if (std::getenv("TG_TRACE"))
+	{
+		// poor man's timeline: when each stage of each slab ended, in ms after the cull started
+		for (size_t c = 0; c < jobs.size(); ++c)
+		{
+			float t[6];
+			for (int m = 0; m < 6; ++m) cudaEventElapsedTime(&t[m], cull_marks[0], jobs[c]->marks[m]);
+			std::fprintf(stderr, "slab %2zu lane %d: start %.3f  resolve %.3f  eval %.3f  scan %.3f  finalize %.3f  attributes %.3f\n", c, jobs[c]->lane, t[0], t[1], t[2], t[3], t[4], t[5]);
+		}
+	}
+	// the lanes overlap, so the device time of the export is the span from the cull's start to the last slab's end
+	for (auto& j : jobs)
+	{
+		float span = 0.f;
+		if (cudaEventElapsedTime(&span, cull_marks[0], j->marks[5]) == cudaSuccess) total.total_device_ms = std::max(total.total_device_ms, span);
+	}
+	{
+		float cull_ms = 0.f;
+		cudaEventElapsedTime(&cull_ms, cull_marks[0], cull_marks[1]);
+		total.cull_ms += cull_ms;
+		total.kernel_launches += cull_launches;
+	}
+	if (shared_flags) cudaFreeAsync(shared_flags, stream);
+	cudaEventDestroy(cull_marks[0]);
+	cudaEventDestroy(cull_marks[1]);
+	for (auto& j : jobs)
+	{
+		FreeResultDevice(j->result, stream);
+		delete j->result;
+		j->result = nullptr;
+	}
 
 	MeshResultDevice* result = new MeshResultDevice();
 	result->context = ctx;
+	result->pinned.push_back(host.positions);
+	if (host.normals) result->pinned.push_back(host.normals);
+	if (host.colors) result->pinned.push_back(host.colors);
+	result->pinned.push_back(host.triangles);
 	out->opaque = result;
-	out->vertex_count = vertex_count;
-
-	// per-brick-layer vertex numbering (adaptive slab balancing) + halo count: read back together with the quad total
-	const uint32_t profile_layers = bz_end - bz_begin;
-	uint32_t* layer_starts = nullptr;
-	TG_CUDA(scratch.Alloc(&layer_starts, profile_layers + 2));
-	LayerStartsKernel<<<(profile_layers + 127) / 128, 128, 0, stream>>>(prefix, size_t(grid.sy) * row_words, k_base, bz_begin, profile_layers, layers, layer_starts);
-	launches++;
-	std::vector<uint32_t> host_starts(profile_layers + 2, 0u);
-	uint32_t halo_vertices = 0;
-	const uint32_t nbz_all = (grid.sz + kBrick - 1) / kBrick;
-	unsigned long long* layer_cost = nullptr;
-	TG_CUDA(scratch.Alloc(&layer_cost, nbz_all));
-	TG_CUDA(cudaMemsetAsync(layer_cost, 0, size_t(nbz_all) * 8, stream));
-	std::vector<unsigned long long> host_layer_cost(nbz_all, 0ull);
-
-	unsigned long long* vertex_info = nullptr;
-	uint32_t *quad_count = nullptr, *quad_offset = nullptr;
-	uint64_t quad_total = 0;
-	const bool want_host = !(options.flags & TG_MESH_DEVICE_ONLY);
-	cudaStream_t copy_stream = static_cast<cudaStream_t>(ctx->copy_stream);
-	cudaEvent_t ready = static_cast<cudaEvent_t>(ctx->copy_events[0]);
-	auto fetch = [&](cudaStream_t on, void* device, size_t bytes, void** host) -> int
+	out->positions = v_done ? host.positions : nullptr;
+	out->normals = v_done ? host.normals : nullptr;
+	out->colors = v_done ? host.colors : nullptr;
+	out->triangles = t_done ? host.triangles : nullptr;
+	out->vertex_count = v_done;
+	out->triangle_count = t_done;
+	out->halo_vertices = 0;
+	out->timings = total;
+	out->timings.download_ms = float(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
+	out->layer_count = nbz;
+	out->layer_vertices = static_cast<uint32_t*>(std::calloc(nbz, sizeof(uint32_t)));
+	out->layer_vertex_cost = static_cast<double*>(std::calloc(nbz, sizeof(double)));
+	for (uint32_t i = 0; i < nbz; ++i)
 	{
-		if (!device || bytes == 0) return TG_OK;
-		void* p = ctx->AcquirePinned(bytes, error);
-		if (!p) return TG_ERR_MEMORY;
-		result->pinned.push_back(p);
-		TG_CUDA(cudaMemcpyAsync(p, device, bytes, cudaMemcpyDeviceToHost, on));
-		*host = p;
-		return TG_OK;
-	};
-	if (vertex_count > 0)
-	{
-		TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_positions), size_t(vertex_count) * 12, stream));
-		TG_CUDA(scratch.Alloc(&vertex_info, vertex_count));
-		TG_CUDA(scratch.Alloc(&quad_count, vertex_count));
-		TG_CUDA(scratch.Alloc(&quad_offset, vertex_count));
-		FaceParams fp;
-		fp.bitmap = bitmap;
-		fp.prefix = prefix;
-		fp.row_words = row_words;
-		fp.sy = grid.sy;
-		fp.k_base = k_base;
-		fp.halo_ptr = halo_ptr;
-		fp.tmp_pos = tmp_pos;
-		fp.tmp_key = tmp_key;
-		fp.tmp_count = vertex_count;
-		fp.positions = result->d_positions;
-		fp.vertex_info = vertex_info;
-		fp.quad_count = quad_count;
-		fp.quad_offset = quad_offset;
-		fp.triangles = nullptr;
-		fp.vertex_count = vertex_count;
-		ScatterVerticesKernel<<<(vertex_count + 255) / 256, 256, 0, stream>>>(fp);
-		launches++;
-		const int t_compact = timer.Mark();
-		rc = DeviceExclusiveScan(stream, scratch, LoadU32{ quad_count }, vertex_count, quad_offset, counters + kCntTotalQuads, launches, error);
-		if (rc != TG_OK) return rc;
-		TG_CUDA(cudaMemcpyAsync(host_counts, counters + kCntTotalQuads, 8, cudaMemcpyDeviceToHost, stream));
-		TG_CUDA(cudaMemcpyAsync(host_starts.data(), layer_starts, size_t(profile_layers) * 4, cudaMemcpyDeviceToHost, stream));
-		if (halo_ptr) TG_CUDA(cudaMemcpyAsync(&halo_vertices, halo_ptr, 4, cudaMemcpyDeviceToHost, stream));
-		TG_CUDA(cudaStreamSynchronize(stream));
-		quad_total = host_counts[0];
-		if (quad_total * 2 > 0xFFFFFFF0ull)
-		{
-			error = "mesh exceeds 2^32 triangles";
-			return TG_ERR_UNSUPPORTED;
-		}
-		if (quad_total > 0)
-		{
-			TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_triangles), size_t(quad_total) * 24, stream));
-			fp.triangles = result->d_triangles;
-			EmitTrianglesKernel<<<(vertex_count + 255) / 256, 256, 0, stream>>>(fp);
-			launches++;
-			if (want_host)
-			{
-				// the index buffer is final: start bringing it home on the copy stream while the attributes are computed
-				TG_CUDA(cudaEventRecord(ready, stream));
-				TG_CUDA(cudaStreamWaitEvent(copy_stream, ready, 0));
-				if ((rc = fetch(copy_stream, result->d_triangles, size_t(quad_total) * 24, reinterpret_cast<void**>(&out->triangles))) != TG_OK) return rc;
-			}
-		}
-		TG_CUDA(cudaGetLastError());
-		const int t_faces = timer.Mark();
-		out->triangle_count = quad_total * 2;
-
-		// ---- K4: attributes ----------------------------------------------------------------------
-		ctx->stage.store(options.refine_iterations > 0 ? 2 : 3);
-		const float half[3] = { grid.dx / 2.0f, grid.dy / 2.0f, grid.dz / 2.0f };
-		rc = FinishAttributes(model, scratch, result, vertex_count, options, half, launches, error, layer_cost, grid.z, grid.dz, nbz_all);
-		if (rc != TG_OK) return rc;
-		TG_CUDA(cudaMemcpyAsync(host_layer_cost.data(), layer_cost, size_t(nbz_all) * 8, cudaMemcpyDeviceToHost, stream));
-		if ((options.flags & TG_MESH_FACE_NORMALS) && quad_total > 0)
-		{
-			TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_face_normals), size_t(quad_total) * 24, stream));
-			if (halo_vertices != 0)
-			{
-				error = "face normals are not available for slab exports";
-				return TG_ERR_UNSUPPORTED;
-			}
-			const uint32_t tris = uint32_t(quad_total * 2);
-			FaceNormalsKernel<<<(tris + 127) / 128, 128, 0, stream>>>(MakeDeviceModel(model), result->d_positions, result->d_triangles, tris, 1.0f, result->d_face_normals);
-			launches++;
-			const float scale = options.scale == 0.0f ? 1.0f : options.scale;
-			if (scale != 1.0f)
-			{
-				ScalePositionsKernel<<<uint32_t((size_t(vertex_count) * 3 + 255) / 256), 256, 0, stream>>>(result->d_positions, size_t(vertex_count) * 3, scale);
-				launches++;
-			}
-		}
-		TG_CUDA(cudaGetLastError());
-		const int t_attr = timer.Mark();
-		const auto h0 = std::chrono::steady_clock::now();
-		if (want_host)
-		{
-			if ((rc = fetch(stream, result->d_positions, size_t(vertex_count) * 12, reinterpret_cast<void**>(&out->positions))) != TG_OK) return rc;
-			if ((rc = fetch(stream, result->d_normals, size_t(vertex_count) * 12, reinterpret_cast<void**>(&out->normals))) != TG_OK) return rc;
-			if ((rc = fetch(stream, result->d_colors, size_t(vertex_count) * 3, reinterpret_cast<void**>(&out->colors))) != TG_OK) return rc;
-			if ((rc = fetch(stream, result->d_face_normals, size_t(quad_total) * 24, reinterpret_cast<void**>(&out->face_normals))) != TG_OK) return rc;
-			TG_CUDA(cudaStreamSynchronize(copy_stream));
-		}
-		TG_CUDA(cudaStreamSynchronize(stream));
-		tm.download_ms = want_host ? float(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count()) : 0.0f;
-		tm.cull_ms = timer.Ms(t_start, t_cull);
-		tm.evaluate_ms = timer.Ms(t_cull, t_eval);
-		tm.compact_ms = timer.Ms(t_eval, t_compact);
-		tm.faces_ms = timer.Ms(t_compact, t_faces);
-		tm.attributes_ms = timer.Ms(t_faces, t_attr);
-		tm.total_device_ms = timer.Ms(t_start, t_attr);
+		if (out->layer_vertices) out->layer_vertices[i] = layer_vertices[i];
+		if (out->layer_vertex_cost) out->layer_vertex_cost[i] = layer_cost[i];
 	}
-	else
+	auto& last = ctx->last_export;
+	last.model = model;
+	last.sx = grid.sx;
+	last.sy = grid.sy;
+	last.sz = grid.sz;
+	last.flags = shape_flags;
+	last.vertices = v_done;
+	last.triangles = t_done;
+	return TG_OK;
+}
+
+static int PipelineChunks(const tg_grid& g, const tg_mesh_options& options)
+{
+	if (options.flags & (TG_MESH_DEVICE_ONLY | TG_MESH_FACE_NORMALS)) return 1;
+	if (options.slab_begin != 0 || options.slab_end != 0) return 1;
+	if (const char* env = std::getenv("TG_PIPELINE_CHUNKS"))
 	{
-		const int t_end = timer.Mark();
-		TG_CUDA(cudaStreamSynchronize(stream));
-		tm.cull_ms = timer.Ms(t_start, t_cull);
-		tm.evaluate_ms = timer.Ms(t_cull, t_eval);
-		tm.total_device_ms = timer.Ms(t_start, t_end);
+		const int n = std::atoi(env);
+		if (n >= 1) return n;
 	}
-	out->halo_vertices = halo_vertices;
-	// vertices owned per brick layer (absolute layer index); layers outside the slab stay 0
+	// worth it once the result is tens of megabytes: below that the copies are short next to the launch overheads
+	const double cells = double(g.sx) * double(g.sy) * double(g.sz);
+	if (cells < double(1 << 24) || g.sz < 128) return 1;
+	// measured on seaside_town 1024^3 (profiles/): 1 slab 10.3 ms end to end, 2: 9.3, 4: 8.6, 8: 9.2 -- every slab adds
+	// the tail of a persistent kernel and a dozen small launches, so few slabs win
+	return 4;
+}
+
+int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options& options, tg_mesh* out, std::string& error)
+{
+	std::memset(out, 0, sizeof(*out));
+	Context* ctx = model->context;
+	TG_CUDA(cudaSetDevice(ctx->device));
+	ctx->stage.store(1);
+	ctx->progress_done[0] = 0;
+	ctx->progress_total[0] = 1;
+	if (ctx->Cancelled()) return TG_ERR_CANCELLED;
+	int rc = TG_RETRY_ONE_SHOT;
+	const int chunks = PipelineChunks(grid_in, options);
+	if (chunks > 1)
 	{
-		const uint32_t nbz = (grid.sz + kBrick - 1) / kBrick;
-		uint32_t* profile = static_cast<uint32_t*>(std::calloc(nbz, sizeof(uint32_t)));
-		if (profile && vertex_count > 0)
-		{
-			for (uint32_t i = 0; i < profile_layers; ++i)
-			{
-				const uint32_t begin = host_starts[i];
-				const uint32_t end = (i + 1 < profile_layers && host_starts[i + 1] != 0xFFFFFFFFu) ? host_starts[i + 1] : vertex_count + halo_vertices;
-				profile[bz_begin + i] = end >= begin ? end - begin : 0u;
-			}
-		}
-		out->layer_vertices = profile;
-		out->layer_count = nbz;
-		double* cost = static_cast<double*>(std::calloc(nbz, sizeof(double)));
-		if (cost)
-		{
-			for (uint32_t i = 0; i < nbz; ++i) cost[i] = double(host_layer_cost[i]);
-		}
-		out->layer_vertex_cost = cost;
+		rc = ExportMeshPipelined(model, grid_in, options, chunks, out, error);
+		if (rc == TG_RETRY_ONE_SHOT) std::memset(out, 0, sizeof(*out));
 	}
-	tm.kernel_launches = launches;
+	if (rc == TG_RETRY_ONE_SHOT) rc = ExportMeshOnce(model, grid_in, options, out, error);
+	ctx->progress_done[0] = ctx->progress_total[0].load();
 	ctx->stage.store(0);
+	if (rc != TG_OK)
+	{
+		EngineFreeMesh(out);
+		return rc;
+	}
+	if (ctx->Cancelled())
+	{
+		EngineFreeMesh(out);
+		return TG_ERR_CANCELLED;
+	}
 	return TG_OK;
 }
 
@@ -2351,6 +3194,7 @@ int EngineExportPoints(Model* model, const float mn[3], const float mx[3], const
 	TG_CUDA(scratch.Alloc(&d_hits, words));
 	TG_CUDA(scratch.Alloc(&d_prefix, words));
 	TG_CUDA(scratch.Alloc(&counters, kCntCount));
+	TG_CUDA(cudaMemsetAsync(counters, 0, kCntCount * 8, stream));
 	TG_CUDA(cudaMemsetAsync(d_hits, 0, words * 4, stream));
 	ctx->stage.store(1);
 	StageTimer timer(stream);
@@ -2380,7 +3224,13 @@ int EngineExportPoints(Model* model, const float mn[3], const float mx[3], const
 		options.refine_iterations = refine;
 		options.scale = 1.0f;
 		const float halfv[3] = { half.x, half.y, half.z };
-		rc = FinishAttributes(model, scratch, result, count, options, halfv, launches, error);
+		AttributeScratch as;
+		if (WantsAttributePass(model, options))
+		{
+			rc = PrepareAttributeScratch(model, stream, scratch, count, as, error);
+			if (rc != TG_OK) return rc;
+		}
+		rc = EnqueueAttributes(model, scratch, result, counters + kCntTotalVertices, counters + kCntAttrCursor, count, options, halfv, as, false, launches, error);
 		if (rc != TG_OK) return rc;
 		const int t1 = timer.Mark();
 		TG_CUDA(cudaStreamSynchronize(stream));

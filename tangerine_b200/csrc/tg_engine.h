@@ -25,12 +25,19 @@ class Context
 public:
 	int device = 0;
 	void* stream = nullptr;      // cudaStream_t
+	void* stream2 = nullptr;     // cudaStream_t: second compute lane of the slab pipeline (odd slabs)
 	void* copy_stream = nullptr; // cudaStream_t: device -> host copies that overlap compute
 	void* copy_events[1] = { nullptr };
 	void* timer_events[2] = { nullptr, nullptr };
 	std::vector<PinnedBlock> pinned; // grow-only pool of page-locked host buffers for results
+	std::vector<void*> mailboxes;    // free list of small page-locked blocks the device delivers its counts into
+	void* index_base = nullptr;      // device: running vertex total of the slabs already emitted (pipelined export)
+	// last whole-grid export on this context, so that the next identical one can size its host arrays exactly
+	struct { const void* model = nullptr; uint64_t sx = 0, sy = 0, sz = 0; uint32_t flags = 0; uint64_t vertices = 0, triangles = 0; } last_export;
 	void* arena = nullptr;       // grow-only device scratch reused by every call on this context
 	size_t arena_bytes = 0;
+	void* arena2 = nullptr;      // same for the second lane
+	size_t arena2_bytes = 0;
 	int sm_count = 0;
 	int brick_blocks_per_sm = 1; // resident MeshBricksKernel blocks per SM (persistent grid size)
 
@@ -45,6 +52,8 @@ public:
 
 	void* AcquirePinned(size_t bytes, std::string& error);
 	void ReleasePinned(void* ptr);
+	void* AcquireMailbox(std::string& error);
+	void ReleaseMailbox(void* ptr);
 	bool Cancelled() const { return !active.load(); }
 };
 

@@ -29,6 +29,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 import oracle_lib as O  # noqa: E402
+from golden_util import ply_file_digests, stl_file_digests, vox_file_digests  # noqa: E402
 
 # model -> (cells per unit for the mesh export, points, point-cloud step or None)
 CASES = {
@@ -49,11 +50,6 @@ BIG = {"basic_thing": 16, "gear": 32, "color-cube": 10, "seaside_town": 12.8}
 
 
 VOX_GRID, VOX_COLOR = 6.0, 37
-
-
-def file_digest(path):
-    with open(path, "rb") as f:
-        return hashlib.sha256(f.read()).hexdigest()
 
 
 def sort_rows(a):
@@ -107,16 +103,15 @@ def main():
         O.ref_run("export", path, cpu, 0, ply_path)
         ply = O.read_ply(ply_path)
         entry = {"info": info, "cells_per_unit": cpu, "mesh": mesh_summary(ply)}
-        # whole-file digests of the reference's writers (export.cpp:60-317, magica.cpp:27-72 + VoxWriter): PLY as above,
-        # STL at the same grid, MagicaVoxel at VOX_GRID cells per unit
+        # file-level digests of the reference's writers (export.cpp:60-317, magica.cpp:27-72 + VoxWriter): PLY as above,
+        # STL at the same grid, MagicaVoxel at VOX_GRID cells per unit; records whose order the format does not fix
+        # (faces, voxels) are hashed as sorted multisets (tests/golden_util.py)
         stl_path = os.path.join(tmp, name + ".stl")
         O.ref_run("export", path, cpu, 0, stl_path)
         vox_path = os.path.join(tmp, name + ".vox")
         O.ref_run("vox", path, VOX_GRID, VOX_COLOR, vox_path)
-        entry["files"] = {"ply_sha256": file_digest(ply_path), "ply_bytes": os.path.getsize(ply_path),
-                          "stl_sha256": file_digest(stl_path), "stl_bytes": os.path.getsize(stl_path),
-                          "vox_sha256": file_digest(vox_path), "vox_bytes": os.path.getsize(vox_path),
-                          "vox_grid_size": VOX_GRID, "vox_color_index": VOX_COLOR}
+        entry["files"] = dict(ply_file_digests(ply_path), **stl_file_digests(stl_path), **vox_file_digests(vox_path),
+                              vox_grid_size=VOX_GRID, vox_color_index=VOX_COLOR)
         stride = max(1, len(ply["pos"]) // 256)
         arrays["mesh_pos_sample"] = sort_rows(ply["pos"])[::stride]
         if cloud_step:

@@ -47,3 +47,66 @@ def ulp_diff(a, b):
     a = np.where(a < 0, -(a & 0x7FFFFFFF), a)
     b = np.where(b < 0, -(b & 0x7FFFFFFF), b)
     return np.abs(a - b)
+
+
+# ---- order-independent digests of the exported files -------------------------------------------------
+# The reference writes triangles in the iteration order of a std::unordered_map (surface_nets.cpp:1124-1146 walks
+# `active cell -> vertex id`) and MagicaVoxel voxels in the order its Pool() threads won the mutex (magica.cpp:44-66);
+# neither order is part of the format.  Everything else in the files is compared byte for byte: the header and the
+# vertex block of a PLY as one digest, face / triangle / voxel records as sorted multisets.
+
+def _sorted_records(raw, width):
+    rec = np.frombuffer(raw, np.uint8).reshape(-1, width)
+    return sort_rows(rec).tobytes()
+
+
+def ply_file_digests(path):
+    with open(path, "rb") as f:
+        data = f.read()
+    end = data.index(b"end_header\n") + len(b"end_header\n")
+    header = data[:end].decode()
+    nv = nf = 0
+    for line in header.splitlines():
+        if line.startswith("element vertex"):
+            nv = int(line.split()[-1])
+        if line.startswith("element face"):
+            nf = int(line.split()[-1])
+    stride = 24 + (3 if "property uchar red" in header else 0)
+    faces_at = end + nv * stride
+    assert len(data) == faces_at + nf * 13, "unexpected PLY size"
+    return {"ply_bytes": len(data), "ply_header_and_vertices_sha256": hashlib.sha256(data[:faces_at]).hexdigest(),
+            "ply_faces_sorted_sha256": hashlib.sha256(_sorted_records(data[faces_at:], 13)).hexdigest()}
+
+
+def stl_file_digests(path):
+    with open(path, "rb") as f:
+        data = f.read()
+    count = int(np.frombuffer(data[80:84], "<u4")[0])
+    assert len(data) == 84 + 50 * count, "unexpected STL size"
+    return {"stl_bytes": len(data), "stl_header_sha256": hashlib.sha256(data[:84]).hexdigest(),
+            "stl_triangles_sorted_sha256": hashlib.sha256(_sorted_records(data[84:], 50)).hexdigest()}
+
+
+def vox_file_digests(path):
+    """MagicaVoxel: 'VOX ' version, then chunks (id, content bytes, children bytes, content, children).  The voxel
+    list of every XYZI chunk is sorted; all other bytes stay in place."""
+    with open(path, "rb") as f:
+        data = bytearray(f.read())
+    assert data[:4] == b"VOX "
+    voxels = 0
+
+    def walk(pos, end):
+        nonlocal voxels
+        while pos < end:
+            cid = bytes(data[pos:pos + 4])
+            n, m = (int(x) for x in np.frombuffer(bytes(data[pos + 4:pos + 12]), "<u4"))
+            body = pos + 12
+            if cid == b"XYZI":
+                k = int(np.frombuffer(bytes(data[body:body + 4]), "<u4")[0])
+                data[body + 4:body + 4 + 4 * k] = _sorted_records(bytes(data[body + 4:body + 4 + 4 * k]), 4)
+                voxels += k
+            walk(body + n, body + n + m)
+            pos = body + n + m
+
+    walk(8, len(data))
+    return {"vox_bytes": len(data), "vox_voxels": voxels, "vox_canonical_sha256": hashlib.sha256(bytes(data)).hexdigest()}
