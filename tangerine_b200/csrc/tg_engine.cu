@@ -1319,13 +1319,40 @@ __device__ __forceinline__ void VertexAttributes(const AttributeParams& p, uint3
 		const uint32_t sum = __reduce_add_sync(peers, flops);
 		if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&p.layer_cost[layer], (unsigned long long)sum);
 	}
-	if (p.colors)
-	{
-		ExportColor(model, node, x, y, z, p.colors + size_t(v) * 3);
-	}
 	p.positions[size_t(v) * 3 + 0] = x * p.scale;
 	p.positions[size_t(v) * 3 + 1] = y * p.scale;
 	p.positions[size_t(v) * 3 + 2] = z * p.scale;
+}
+
+// Colour pass, separate from the normal pass on purpose: together the two interpreters (4-tap gradient, material walk)
+// exceed the instruction cache and the fused kernel spent most of its time waiting for instructions (ncu: stall
+// no_instruction 7.8 per issue).  Reads the final (refined, unscaled) positions, writes colours and the scaled positions.
+__global__ void __launch_bounds__(128) ColorsKernel(const AttributeParams p)
+{
+	const uint32_t count = BoundedCount(p.count_ptr, p.capacity);
+	const int lane = threadIdx.x & 31;
+	for (;;)
+	{
+		unsigned long long first = 0;
+		if (lane == 0) first = atomicAdd(p.cursor, 32ull);
+		first = __shfl_sync(0xFFFFFFFFu, first, 0);
+		if (first >= count) break;
+		const uint32_t t = uint32_t(first) + uint32_t(lane);
+		if (t < count)
+		{
+			const uint32_t v = p.perm ? p.perm[t] : t;
+			const float x = p.positions[size_t(v) * 3 + 0], y = p.positions[size_t(v) * 3 + 1], z = p.positions[size_t(v) * 3 + 2];
+			const uint32_t node = (p.refine_iterations <= 0 && p.vertex_node) ? p.vertex_node[v] : Descend(p.model.nodes, 0, x, y, z);
+			ExportColor(p.model, node, x, y, z, p.colors + size_t(v) * 3);
+			if (p.scale != 1.0f)
+			{
+				p.positions[size_t(v) * 3 + 0] = x * p.scale;
+				p.positions[size_t(v) * 3 + 1] = y * p.scale;
+				p.positions[size_t(v) * 3 + 2] = z * p.scale;
+			}
+		}
+		__syncwarp();
+	}
 }
 
 // WriteSTL (export.cpp:130-140): gradient at the triangle centroid, before the vertices are scaled.
@@ -2051,8 +2078,25 @@ static int EnqueueAttributes(Model* model, Scratch& scratch, MeshResultDevice* r
 	ap.perm = perm;
 	ap.vertex_node = as.vertex_node;
 	ap.cursor = cursor;
-	AttributesKernel<<<uint32_t(std::min<uint64_t>((uint64_t(capacity) + 127) / 128, wide_attr)), 128, 0, stream>>>(ap);
-	launches++;
+	const bool normal_pass = want_normals || options.refine_iterations > 0 || (!want_colors && ap.scale != 1.0f);
+	if (normal_pass)
+	{
+		AttributeParams np = ap;
+		if (want_colors)
+		{
+			np.colors = nullptr; // the colour pass follows and applies the scale
+			np.scale = 1.0f;
+		}
+		AttributesKernel<<<uint32_t(std::min<uint64_t>((uint64_t(capacity) + 127) / 128, wide_attr)), 128, 0, stream>>>(np);
+		launches++;
+	}
+	if (want_colors)
+	{
+		static const uint32_t wide_colors = PersistentGrid(ctx, ColorsKernel, 128);
+		if (normal_pass) TG_CUDA(cudaMemsetAsync(cursor, 0, 8, stream));
+		ColorsKernel<<<uint32_t(std::min<uint64_t>((uint64_t(capacity) + 127) / 128, wide_colors)), 128, 0, stream>>>(ap);
+		launches++;
+	}
 	TG_CUDA(cudaGetLastError());
 	return TG_OK;
 }
