@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-stride", type=int, default=0, help="z-slice stride of the CPU sample (0 = auto)")
     ap.add_argument("--no-cull", action="store_true", help="evaluate every brick like the reference does")
+    ap.add_argument("--slab-align", type=int, default=2, help="z-slab cuts fall on multiples of this many cell layers (8 = whole brick rows)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -169,7 +170,7 @@ def main():
     import torch
     import torch.distributed as dist
     import tangerine_b200 as T
-    from tangerine_b200.slabs import balanced_slabs, exchange_counts
+    from tangerine_b200.slabs import balanced_slabs, exchange_counts, layer_costs
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,7 +204,7 @@ def main():
     # no further communication is needed to agree on it).
     if world > 1:
         profile = model.brick_profile(grid).astype(np.float64)
-        slabs = balanced_slabs(profile, world, sz)
+        slabs = balanced_slabs(profile, world, sz, args.slab_align)
         slab = slabs[rank]
     else:
         profile = None
@@ -238,16 +239,16 @@ def main():
         mesh.close()
         return t
 
-    cost = None
+    cost = None          # modelled work per CELL layer
     for w in range(args.warmup):
         mesh = model.export_mesh(grid, flags=flags | T.MESH_DEVICE_ONLY, refine=refine, slab=slab)
         if world > 1:
             tm = mesh.timings
-            lo_b, hi_b = slab[0] // 8, (slab[1] + 7) // 8
             n = len(profile)
+            brick_work = layer_costs(profile, sz)
             mine = np.zeros(n + 4 + world, np.float64)
             mine[:n] = mesh.layer_vertex_cost[:n]
-            mine[n:n + 4] = [tm["evaluate_ms"] + tm["cull_ms"], profile[lo_b:hi_b].sum(), tm["compact_ms"] + tm["faces_ms"] + tm["attributes_ms"], mesh.layer_vertex_cost.sum()]
+            mine[n:n + 4] = [tm["evaluate_ms"] + tm["cull_ms"], brick_work[slab[0]:slab[1]].sum(), tm["compact_ms"] + tm["faces_ms"] + tm["attributes_ms"], mesh.layer_vertex_cost.sum()]
             mine[n + 4 + rank] = tm["total_device_ms"]
             t = torch.from_numpy(mine).cuda()
             dist.all_reduce(t)
@@ -256,14 +257,13 @@ def main():
                 # first model: two rates fitted to the measured stage times of all ranks
                 eval_rate = allv[n] / max(allv[n + 1], 1.0)
                 vertex_rate = allv[n + 2] / max(allv[n + 3], 1.0)
-                cost = eval_rate * profile + vertex_rate * allv[:n] + 1e-9
+                cost = eval_rate * brick_work + vertex_rate * layer_costs(allv[:n], sz) + 1e-9
             # feedback: rescale every slab's layers so that the model reproduces the time that slab just took
             for r, (k0, k1) in enumerate(slabs):
-                b0, b1 = k0 // 8, (k1 + 7) // 8
-                predicted = cost[b0:b1].sum()
+                predicted = cost[k0:k1].sum()
                 if predicted > 0 and allv[n + 4 + r] > 0:
-                    cost[b0:b1] *= allv[n + 4 + r] / predicted
-            slabs = balanced_slabs(cost, world, sz)
+                    cost[k0:k1] *= allv[n + 4 + r] / predicted
+            slabs = balanced_slabs(cost, world, sz, args.slab_align)
             slab = slabs[rank]
         mesh.close()
     sampler = ClockSampler(local)
@@ -357,7 +357,7 @@ def main():
         "peak_source": "FP32 FMA-chain kernel measured in this run (MEASURED_PEAKS.json has no CUDA-core figure); theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5",
         "flops_convention": "SURVEY.md 8(d): FMA = 2, sqrt/div/abs/compare = 1, summed over the samples actually evaluated (culled bricks earn nothing)",
         "kernel_ms": eval_ms, "share_of_step": eval_ms / mean("total_device_ms") if mean("total_device_ms") else None,
-        "hbm": {"kernels": "bitmap scan + ScatterVertices + quad scan + EmitTriangles", "bound": "hbm", "achieved": mesh_bytes / (mesh_ms * 1e-3) * 1e-9 if mesh_ms > 0 else None,
+        "hbm": {"kernels": "dual vertex/quad scan over the bitmap (3 launches) + FinalizeMeshKernel", "bound": "hbm", "achieved": mesh_bytes / (mesh_ms * 1e-3) * 1e-9 if mesh_ms > 0 else None,
                 "peak": hbm_peak, "unit": "GB/s", "frac": (mesh_bytes / (mesh_ms * 1e-3) * 1e-9 / hbm_peak) if mesh_ms > 0 else None,
                 "kernel_ms": mesh_ms, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
     }
@@ -385,7 +385,7 @@ def main():
             "metric": "mesh export throughput", "value": value, "unit": "Mvoxel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "model": name + ".tgm (CSG tree dumped from the reference's Lua front-end)", "grid": [sx, sy, sz], "refine_iterations": refine,
-                       "attributes": "normals+colours", "culling": not args.no_cull, "partition": "z-slabs %s" % (slabs,),
+                       "attributes": "normals+colours", "culling": not args.no_cull, "partition": "z-slabs %s (cuts on multiples of %d layers)" % (slabs, args.slab_align),
                        "l2": "flushed before every timed step (256 MiB fill, outside the per-step event pair); per-step scratch (bitmap + prefix) also exceeds L2 at this grid"},
             "evals_per_s": evals_per_s, "reference_equivalent_evals_per_s": reference_equivalent_evals / (ms_per_step * 1e-3),
             "mesh": {"vertices": vertices, "triangles": triangles},

@@ -194,7 +194,8 @@ typedef struct tg_mesh_options
 	uint32_t flags;
 	int32_t refine_iterations; /* 0 = positions exactly as surface nets produced them */
 	float scale;               /* positions are multiplied by this last (export.cpp:313); 0 means 1 */
-	/* z-slab for multi-GPU runs: this call owns cell layers [slab_begin, slab_end) of the grid.
+	/* z-slab for multi-GPU runs: this call owns cell layers [slab_begin, slab_end) of the grid (any layer
+	 * boundary; bricks that straddle a boundary are evaluated by both neighbours, each for its own layers).
 	 * Both zero = the whole grid.  See tg_mesh.halo_vertices. */
 	uint64_t slab_begin, slab_end;
 } tg_mesh_options;

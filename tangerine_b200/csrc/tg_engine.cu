@@ -329,12 +329,13 @@ __global__ void __launch_bounds__(kBrickThreads) MeshBricksKernel(const MeshPara
 
 		const uint32_t brick = __ldg(&p.bricks[item]);
 		const uint32_t bx = brick & 1023u, by = (brick >> 10) & 1023u, bz = (brick >> 20) & 1023u;
-		const bool halo = (brick & kHaloFlag) != 0;
 		const uint32_t i0 = bx * kBrick, j0 = by * kBrick, k0 = bz * kBrick;
 		const int ni = int(min(uint32_t(kTile), grid.sx + 1 - i0));
 		const int nj = int(min(uint32_t(kTile), grid.sy + 1 - j0));
-		const int nk = int(min(uint32_t(kTile), grid.sz + 1 - k0));
-		const int kmin = halo ? kBrick - 1 : 0; // halo bricks only need their top cell layer
+		// The slab owns cell layers [k_own_begin, k_own_end) and also classifies the halo layer k_base below it; a
+		// brick that sticks out of that window only evaluates the sample layers the window needs.
+		const int nk = int(min(uint32_t(kTile), p.k_own_end + 1 - k0));
+		const int kmin = p.k_base > k0 ? int(p.k_base - k0) : 0;
 
 		EvaluateTile(w, p.model, grid, i0, j0, k0, ni, nj, nk, kmin, p.counters);
 
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(kBrickThreads) MeshBricksKernel(const MeshPara
 			const int c = base + lane;
 			const int ci = c & 7, cj = (c >> 3) & 7, ck = c >> 6;
 			const uint32_t gi = i0 + ci, gj = j0 + cj, gk = k0 + ck;
-			const bool in_grid = gi < grid.sx && gj < grid.sy && gk < grid.sz && ck >= kmin;
+			const bool in_grid = gi < grid.sx && gj < grid.sy && gk < p.k_own_end && ck >= kmin;
 			bool active = false;
 			if (in_grid)
 			{
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(kBrickThreads) MeshBricksKernel(const MeshPara
 					bitmap_bytes[(size_t(gk - p.k_base) * grid.sy + gj) * (size_t(p.row_words) * 8u) + bx] = (unsigned char)byte;
 				}
 			}
-			const bool emit = active && !halo && gk >= p.k_own_begin && gk < p.k_own_end;
+			const bool emit = active && gk >= p.k_own_begin; // the halo layer is classified but owned by the slab below
 			const unsigned emit_ballot = __ballot_sync(0xFFFFFFFFu, emit);
 			if (emit) w.order[emit_total + __popc(emit_ballot & ((1u << lane) - 1u))] = uint16_t(c);
 			emit_total += __popc(emit_ballot);
@@ -706,7 +707,7 @@ __global__ void __launch_bounds__(128) CullLevelKernel(const CullParams p)
 }
 
 // One thread per 8-cell brick of the slab (and of the halo row below it): combine the flags it inherits.
-__global__ void __launch_bounds__(256) CullResolveKernel(const CullParams p, uint32_t bz_begin, uint32_t bz_end, uint32_t halo_row, int no_cull,
+__global__ void __launch_bounds__(256) CullResolveKernel(const CullParams p, uint32_t bz_begin, uint32_t bz_end, int no_cull,
 	uint32_t* __restrict__ out_list, unsigned long long* out_counter, uint32_t out_capacity)
 {
 	const uint32_t nbx = p.dims[0][0], nby = p.dims[0][1];
@@ -728,7 +729,7 @@ __global__ void __launch_bounds__(256) CullResolveKernel(const CullParams p, uin
 			}
 		}
 		active = (f & kFlagEvaluate) != 0u || (f & 3u) == 3u || f == 0u;
-		brick = x | (y << 10) | (z << 20) | (z == halo_row ? kHaloFlag : 0u);
+		brick = x | (y << 10) | (z << 20);
 	}
 	const unsigned ballot = __ballot_sync(0xFFFFFFFFu, active);
 	if (ballot == 0u) return;
@@ -2118,8 +2119,8 @@ static int BuildCullFlags(Model* model, cudaStream_t stream, Scratch& scratch, c
 	bool has_halo, bool no_cull, uint32_t* flags_storage, CullParams& cp, uint64_t& launches, std::string& error)
 {
 	const uint32_t nbx = (grid.sx + kBrick - 1) / kBrick, nby = (grid.sy + kBrick - 1) / kBrick, nbz = (grid.sz + kBrick - 1) / kBrick;
-	const uint32_t bz_begin = k_begin / kBrick, bz_end = (k_end + kBrick - 1) / kBrick;
-	const uint32_t row_begin = has_halo ? bz_begin - 1 : bz_begin;
+	const uint32_t bz_end = (k_end + kBrick - 1) / kBrick;
+	const uint32_t row_begin = (has_halo ? k_begin - 1 : k_begin) / kBrick;
 	cp.model = MakeDeviceModel(model);
 	cp.grid = grid;
 	cp.cell_k_lo = has_halo ? k_begin - 1 : k_begin;
@@ -2178,14 +2179,14 @@ static int ResolveActiveList(cudaStream_t stream, Scratch& scratch, const CullPa
 	bool has_halo, bool no_cull, unsigned long long* counters, uint32_t** out_list, uint64_t* out_count, uint64_t& launches, std::string& error)
 {
 	const uint32_t nbx = (grid.sx + kBrick - 1) / kBrick, nby = (grid.sy + kBrick - 1) / kBrick;
-	const uint32_t bz_begin = k_begin / kBrick, bz_end = (k_end + kBrick - 1) / kBrick;
-	const uint32_t row_begin = has_halo ? bz_begin - 1 : bz_begin;
+	const uint32_t bz_end = (k_end + kBrick - 1) / kBrick;
+	const uint32_t row_begin = (has_halo ? k_begin - 1 : k_begin) / kBrick; // the brick row that holds the halo layer
 	const size_t slab_bricks = size_t(nbx) * nby * (bz_end - row_begin);
 	const size_t list_capacity = slab_bricks + 8;
 	uint32_t* active_list = nullptr;
 	TG_CUDA(scratch.Alloc(&active_list, list_capacity));
 	const uint32_t resolve_threads = uint32_t(slab_bricks);
-	CullResolveKernel<<<(resolve_threads + 255) / 256, 256, 0, stream>>>(cp, row_begin, bz_end, has_halo ? bz_begin - 1 : 0xFFFFFFFFu, no_cull ? 1 : 0,
+	CullResolveKernel<<<(resolve_threads + 255) / 256, 256, 0, stream>>>(cp, row_begin, bz_end, no_cull ? 1 : 0,
 		active_list, counters + kCntListA, uint32_t(list_capacity));
 	launches++;
 	TG_CUDA(cudaGetLastError());
@@ -2284,9 +2285,9 @@ static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const
 	{
 		k_begin = uint32_t(options.slab_begin);
 		k_end = uint32_t(std::min<uint64_t>(options.slab_end, grid.sz));
-		if (k_begin >= k_end || (k_begin % kBrick) != 0 || (k_end % kBrick != 0 && k_end != grid.sz))
+		if (k_begin >= k_end)
 		{
-			error = "slab bounds must be multiples of 8 cell layers (or end at the grid top) and non-empty";
+			error = "slab is empty";
 			return TG_ERR_INVALID;
 		}
 	}

@@ -1,6 +1,6 @@
 """Host-side logic of the multi-GPU path: z-slab cuts and the one exchange of the path.
 
-The grid shards into z-slabs on 8-layer (brick) boundaries, one per rank, each with a one-layer halo below it.
+The grid shards into z-slabs, one per rank, each with a one-layer halo below it.
 Every rank numbers its vertices locally in (k, j, i) order; the only collective is an all-gather of two integers
 per rank (owned vertices, triangles), after which `global id = local id + sum of the lower ranks' vertices`
 (tg_mesh.halo_vertices is already subtracted by the engine).  No compute here and no CUDA: the functions take
@@ -8,34 +8,49 @@ whatever process group the caller initialised (NCCL on the GPU box, gloo in the 
 """
 import numpy as np
 
-BRICK = 8  # cell layers per brick layer: slab boundaries are multiples of this (tg_mesh_options.slab_begin/end)
+BRICK = 8  # cell layers per brick layer: the unit of the work profiles (tg_brick_profile, tg_mesh.layer_vertex_cost)
 
 
-def balanced_slabs(profile, world, sz):
-    """Cut [0, sz) into `world` z-slabs on 8-layer boundaries so that each holds about the same share of
-    `profile` (work per brick layer b = cell layers [8b, 8b+8)).  Deterministic, so every rank computes the
-    same cut from the same profile without communicating.  Every slab gets at least one brick layer; needs
-    len(profile) >= world."""
-    nb = len(profile)
-    if nb < world:
-        raise ValueError("grid has %d brick layers, fewer than the %d ranks" % (nb, world))
-    cost = np.asarray(profile, np.float64) + 1e-3
-    cum = np.concatenate([[0.0], np.cumsum(cost)])
+def layer_costs(profile, sz):
+    """Work per CELL layer from a profile given per cell layer (len == sz) or per brick layer (len == ceil(sz / 8),
+    taken as uniform inside the brick layer)."""
+    p = np.asarray(profile, np.float64)
+    if len(p) != sz:
+        if len(p) != (sz + BRICK - 1) // BRICK:
+            raise ValueError("profile has %d entries for %d layers" % (len(p), sz))
+        p = np.repeat(p / BRICK, BRICK)[:sz]
+    return p + 1e-3 / BRICK
+
+
+def balanced_slabs(profile, world, sz, align=BRICK):
+    """Cut [0, sz) into `world` z-slabs so that each holds about the same share of `profile` (work per cell layer, or
+    per brick layer b = cell layers [8b, 8b+8), see layer_costs).  Cuts fall on multiples of `align` cell layers:
+    8 keeps every brick with one rank; smaller values balance finer at the price of evaluating the bricks of a cut
+    row on both sides.  Deterministic, so every rank computes the same cut from the same profile without
+    communicating.  Every slab gets at least `align` layers; needs sz >= world * align."""
+    align = max(1, int(align))
+    steps = (sz + align - 1) // align            # candidate cut positions are align * [0 .. steps]
+    if steps < world:
+        raise ValueError("grid has %d layers, too few for %d ranks at alignment %d" % (sz, world, align))
+    per_layer = layer_costs(profile, sz)
+    cum = np.concatenate([[0.0], np.cumsum(per_layer)])
+    below = cum[np.minimum(np.arange(steps + 1) * align, sz)]   # work of cell layers [0, k) at every candidate cut
     cuts = [0]
     for r in range(1, world):
-        target = cum[-1] * r / world
-        b = int(np.searchsorted(cum, target))
-        b = max(b, cuts[-1] + 1)
-        b = min(b, nb - (world - r))
-        cuts.append(b)
-    cuts.append(nb)
-    return [(cuts[r] * BRICK, min(cuts[r + 1] * BRICK, sz)) for r in range(world)]
+        target = below[-1] * r / world
+        i = int(np.searchsorted(below, target))
+        if i > 0 and abs(below[i - 1] - target) <= abs(below[min(i, steps)] - target):
+            i -= 1
+        i = max(i, cuts[-1] + 1)
+        i = min(i, steps - (world - r))
+        cuts.append(i)
+    cuts.append(steps)
+    return [(cuts[r] * align, min(cuts[r + 1] * align, sz)) for r in range(world)]
 
 
 def uniform_slabs(world, sz):
     """Equal-thickness slabs (the cut used before any work profile exists)."""
-    nb = (sz + BRICK - 1) // BRICK
-    return balanced_slabs(np.ones(nb), world, sz)
+    return balanced_slabs(np.ones(sz), world, sz)
 
 
 def exchange_counts(vertex_count, triangle_count, rank, world, device=None, group=None):

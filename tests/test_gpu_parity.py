@@ -221,6 +221,32 @@ def test_z_slabs_stitch_to_the_whole_mesh(name, parts, golden, models):
     whole.close()
 
 
+@pytest.mark.parametrize("cuts", [(0, 13, 37, 1000), (0, 1, 2, 9, 1000), (0, 31, 32, 33, 1000)])
+def test_z_slabs_on_any_layer_boundary(cuts, golden, models):
+    """Slab boundaries need not fall on brick rows: bricks that straddle a cut are evaluated on both sides, each for
+    its own layers (finer load balance for the multi-GPU partition)."""
+    tree, model = models("kitchen_sink")
+    grid = _grid(tree, golden["kitchen_sink"]["cells_per_unit"] * 2)
+    whole = model.export_mesh(grid)
+    sz = grid.shape[2]
+    pos, nrm, tri = [], [], []
+    base = 0
+    edges = [min(c, sz) for c in cuts]
+    for k0, k1 in zip(edges[:-1], edges[1:]):
+        if k0 >= k1:
+            continue
+        slab = model.export_mesh(grid, slab=(k0, k1))
+        pos.append(slab.positions.copy())
+        nrm.append(slab.normals.copy() if slab.normals is not None else np.zeros((0, 3), np.float32))
+        tri.append((slab.triangles.astype(np.uint32) + np.uint32(base)).astype(np.uint32))
+        base += slab.vertex_count
+        slab.close()
+    assert np.array_equal(np.concatenate(pos), whole.positions)
+    assert same_floats(np.concatenate(nrm), whole.normals)
+    assert np.array_equal(np.concatenate(tri), whole.triangles)
+    whole.close()
+
+
 def test_empty_and_tiny_grids(models):
     tree, model = models("basic_thing")
     far = T.export_grid([10, 10, 10], [10.5, 10.5, 10.5], np.float32(0.125))

@@ -122,6 +122,20 @@ def test_balanced_slabs_properties():
     assert cut[0][1] < 512
     with pytest.raises(ValueError):
         slabs.balanced_slabs(np.ones(2), 4, 16)
+    # finer alignment: cuts on any layer, closer to equal work
+    prof = rng.integers(1, 1000, 128).astype(np.float64)
+    for world in (2, 4, 8):
+        coarse = slabs.balanced_slabs(prof, world, 1024, align=8)
+        fine = slabs.balanced_slabs(prof, world, 1024, align=1)
+        assert fine[0][0] == 0 and fine[-1][1] == 1024 and all(a < b for a, b in fine)
+        assert all(fine[r][0] == fine[r - 1][1] for r in range(1, world))
+        per_layer = np.repeat(prof / 8.0, 8)
+
+        def spread(cut):
+            w = [per_layer[a:b].sum() for a, b in cut]
+            return max(w) / (sum(w) / len(w))
+        assert spread(fine) <= spread(coarse) + 1e-9
+        assert spread(fine) < 1.02
 
 
 def _free_port():
