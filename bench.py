@@ -179,6 +179,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: tangerine_b200 has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     name, step, refine, desc = WORKLOADS[args.workload]
