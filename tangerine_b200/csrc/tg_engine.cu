@@ -57,6 +57,12 @@ constexpr int kMaxGroups = 32;            // distinct octree nodes per grouping 
 constexpr int kLaneSamples = TG_LANE_SAMPLES; // samples interpreted per lane per dispatch
 constexpr uint32_t kEmptyGroup = 0xFFFFFFFFu;
 constexpr uint32_t kHaloFlag = 1u << 30;
+// The brick kernel is instruction-cache bound before it is anything else (ncu: stall_no_instruction): its bookkeeping
+// loops (per-round descent, sort, classification) are kept rolled so that the interpreter stays resident.
+#ifndef TG_UNROLL_BOOKKEEPING
+#define TG_UNROLL_BOOKKEEPING 1
+#endif
+constexpr int kUnrollBookkeeping = TG_UNROLL_BOOKKEEPING;
 #ifndef TG_TOP_LEVEL
 #define TG_TOP_LEVEL 3
 #endif
@@ -171,6 +177,7 @@ __device__ __forceinline__ void EvaluateTile(WarpTile& w, const DeviceModel& mod
 
 		// Pass 1: per-sample descent, warp-aggregated insertion into the brick's node table (open addressing).
 		uint32_t assigned = 0;
+#pragma unroll kUnrollBookkeeping
 		for (int r = 0; r < kRounds; ++r)
 		{
 			const bool mine = (pending >> r) & 1u;
@@ -191,6 +198,7 @@ __device__ __forceinline__ void EvaluateTile(WarpTile& w, const DeviceModel& mod
 				if (lane == leader)
 				{
 					uint32_t g = (node * 0x9E3779B1u) >> 27;
+#pragma unroll 1
 					for (int probe = 0; probe < kMaxGroups; ++probe, g = (g + 1) & (kMaxGroups - 1))
 					{
 						uint32_t seen = w.group_node[g];
@@ -239,6 +247,7 @@ __device__ __forceinline__ void EvaluateTile(WarpTile& w, const DeviceModel& mod
 		__syncwarp();
 
 		// Pass 2: sample indices sorted by group.
+#pragma unroll kUnrollBookkeeping
 		for (int r = 0; r < kRounds; ++r)
 		{
 			if ((assigned >> r) & 1u)
@@ -342,6 +351,7 @@ __global__ void __launch_bounds__(kBrickThreads) MeshBricksKernel(const MeshPara
 		// Classification: sign bits of FirstLoopInnerThunk (surface_nets.cpp:864-907); active cells go to the
 		// bitmap (one byte per 8-cell row) and, when this slab owns them, to the brick's cell list.
 		int emit_total = 0;
+#pragma unroll kUnrollBookkeeping
 		for (int base = 0; base < kBrick * kBrick * kBrick; base += 32)
 		{
 			const int c = base + lane;
