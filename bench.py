@@ -41,7 +41,24 @@ WORKLOADS = {
     "gear512": ("gear", 8.0 / 510.0, 5, "gear.lua 512x512x34 with 5 refinement iterations (BASELINE.json configs[1])"),
     "colorcube512": ("color-cube", 9.6 / 510.0, 0, "color-cube.lua 513^3 with per-vertex colour (BASELINE.json configs[4])"),
     "basic66": ("basic_thing", 1.0 / 16.0, 0, "basic_thing.lua 66^3 (BASELINE.json configs[0])"),
+    # BASELINE.json configs[3]: synthetic random CSG scene, 10k primitives (tg_make_synthetic, seed 1234), dense sweep
+    "synthetic256": ("synthetic:10000", 10.0 / 254.0, 0, "synthetic random CSG scene, 10,000 primitives, 256^3"),
+    "synthetic512": ("synthetic:10000", 10.0 / 510.0, 0, "synthetic random CSG scene, 10,000 primitives, 512^3"),
+    "synthetic1024": ("synthetic:10000", 10.0 / 1022.0, 0, "synthetic random CSG scene, 10,000 primitives, 1024^3"),
+    "synthetic2048": ("synthetic:10000", 10.0 / 2046.0, 0, "synthetic random CSG scene, 10,000 primitives, 2048^3"),
 }
+
+
+def load_workload_tree(T, name):
+    """Returns (tree, path of a .tgm file of it for the reference tool)."""
+    if name.startswith("synthetic:"):
+        import tempfile
+        tree = T.Tree.synthetic(int(name.split(":")[1]), 1234)
+        path = os.path.join(tempfile.gettempdir(), "tg_%s_%d.tgm" % (name.replace(":", "_"), os.getpid()))
+        tree.save(path)
+        return tree, path
+    path = os.path.join(MODELS, name + ".tgm")
+    return T.Tree.load(path), path
 
 
 def log(*a):
@@ -49,20 +66,59 @@ def log(*a):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md).
+
+    NVML in-process (nvidia_ml_py) on a background thread: a query costs tens of microseconds.  Spawning
+    `nvidia-smi -lms` for the same purpose stalled the CUDA driver for about a millisecond per poll and doubled the
+    measured time of sub-millisecond steps (gear.lua 512x512x34: 1.80 ms/step with it, 0.78 without); it is only the
+    fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
+    def __init__(self, device, interval=0.02):
         self.device = device
+        self.interval = interval
+        self.samples = []          # (sm_mhz, sm_max_mhz, power_w, reasons bitmask)
         self.proc = None
-        self.lines = []
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.nvml = None
+        self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(visible.split(",")[device]) if visible and visible.split(",")[device].isdigit() else device
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll_nvml(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                smax = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                # the power read goes out to the board's controller and can hold the driver for milliseconds: once in ten
+                power = n.nvmlDeviceGetPowerUsage(self.handle) * 1e-3 if len(self.samples) % 10 == 0 else (self.samples[-1][2] if self.samples else 0.0)
+                reasons = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((float(sm), float(smax), float(power), int(reasons)))
+            except Exception:
+                pass
+            self.stop_flag.wait(self.interval)
 
     def start(self):
+        self.stop_flag.clear()
+        if self.nvml:
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.lines = []
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
@@ -73,6 +129,19 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        if self.nvml:
+            self.stop_flag.set()
+            if self.thread:
+                self.thread.join(timeout=2)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            n = self.nvml
+            bits = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8), "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            reasons = sorted(name for name in names if any(s[3] & bits[name] for s in self.samples))
+            return {"sm_mhz": float(np.median([s[0] for s in self.samples])), "sm_max_mhz": float(max(s[1] for s in self.samples)),
+                    "power_w_max": float(max(s[2] for s in self.samples)), "samples": len(self.samples), "reasons": reasons, "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -92,13 +161,13 @@ class ClockSampler:
                 power.append(float(f[3]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+            for name, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def run_reference_sample(model_file, lo, hi, step, stride, threads):
@@ -114,12 +183,11 @@ def reference_arm(args, workload):
     if rank != 0:
         return 0
     name, step, refine, desc = WORKLOADS[workload]
-    model_file = os.path.join(MODELS, name + ".tgm")
     if not os.path.exists(REF_TOOL):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/tangerine_ref was not built (run __graft_entry__.build() where /root/reference exists)"}))
         return 0
     import tangerine_b200 as T
-    tree = T.Tree.load(model_file)
+    tree, model_file = load_workload_tree(T, name)
     lo, hi = tree.bounds()
     step32 = float(np.float32(step))
     threads = os.cpu_count() or 1
@@ -186,8 +254,7 @@ def main():
     name, step, refine, desc = WORKLOADS[args.workload]
     if args.refine is not None:
         refine = args.refine
-    model_file = os.path.join(MODELS, name + ".tgm")
-    tree = T.Tree.load(model_file)
+    tree, model_file = load_workload_tree(T, name)
     lo, hi = tree.bounds()
     grid = T.export_grid(lo, hi, np.float32(step))
     sx, sy, sz = grid.shape
@@ -269,7 +336,7 @@ def main():
             slab = slabs[rank]
         mesh.close()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("TG_BENCH_NO_SMI"):
         sampler.start()
     barrier()
     steps = []
@@ -386,7 +453,7 @@ def main():
         line = {
             "metric": "mesh export throughput", "value": value, "unit": "Mvoxel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "model": name + ".tgm (CSG tree dumped from the reference's Lua front-end)", "grid": [sx, sy, sz], "refine_iterations": refine,
+            "config": {"workload": desc, "model": (name + ".tgm (CSG tree dumped from the reference's Lua front-end)") if not name.startswith("synthetic:") else "tg_make_synthetic(%s, 1234)" % name.split(":")[1], "grid": [sx, sy, sz], "refine_iterations": refine,
                        "attributes": "normals+colours", "culling": not args.no_cull, "partition": "z-slabs %s (cuts on multiples of %d layers)" % (slabs, args.slab_align),
                        "l2": "flushed before every timed step (256 MiB fill, outside the per-step event pair); per-step scratch (bitmap + prefix) also exceeds L2 at this grid"},
             "evals_per_s": evals_per_s, "reference_equivalent_evals_per_s": reference_equivalent_evals / (ms_per_step * 1e-3),

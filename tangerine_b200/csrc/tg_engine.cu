@@ -1679,6 +1679,10 @@ Context::~Context()
 	}
 	if (arena) cudaFree(arena);
 	if (arena2) cudaFree(arena2);
+	for (PinnedBlock& b : device_blocks)
+	{
+		if (b.ptr) cudaFree(b.ptr);
+	}
 	if (stream2) cudaStreamDestroy(static_cast<cudaStream_t>(stream2));
 	if (index_base) cudaFree(index_base);
 	for (void* m : mailboxes) cudaFreeHost(m);
@@ -1713,6 +1717,57 @@ void* Context::AcquirePinned(size_t bytes, std::string& error)
 	b.in_use = true;
 	pinned.push_back(b);
 	return b.ptr;
+}
+
+void* Context::AcquireDevice(size_t bytes, std::string& error)
+{
+	if (bytes == 0) bytes = 256;
+	int best = -1;
+	for (size_t i = 0; i < device_blocks.size(); ++i)
+	{
+		const PinnedBlock& b = device_blocks[i];
+		if (!b.in_use && b.bytes >= bytes && (best < 0 || b.bytes < device_blocks[size_t(best)].bytes)) best = int(i);
+	}
+	if (best >= 0)
+	{
+		device_blocks[size_t(best)].in_use = true;
+		return device_blocks[size_t(best)].ptr;
+	}
+	PinnedBlock b;
+	const size_t rounded = (bytes + bytes / 8 + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+	cudaError_t e = cudaMalloc(&b.ptr, rounded);
+	if (e != cudaSuccess)
+	{
+		// out of memory: give the cached blocks nobody uses back and try once more
+		cudaGetLastError();
+		for (size_t i = device_blocks.size(); i-- > 0;)
+		{
+			if (!device_blocks[i].in_use)
+			{
+				cudaFree(device_blocks[i].ptr);
+				device_blocks.erase(device_blocks.begin() + long(i));
+			}
+		}
+		e = cudaMalloc(&b.ptr, rounded);
+	}
+	if (e != cudaSuccess)
+	{
+		error = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+		return nullptr;
+	}
+	b.bytes = rounded;
+	b.in_use = true;
+	device_blocks.push_back(b);
+	return b.ptr;
+}
+
+void Context::ReleaseDevice(void* ptr)
+{
+	if (!ptr) return;
+	for (PinnedBlock& b : device_blocks)
+	{
+		if (b.ptr == ptr) b.in_use = false;
+	}
 }
 
 constexpr size_t kMailboxBytes = 16384;
@@ -1947,11 +2002,12 @@ void EngineFreeMesh(tg_mesh* mesh)
 	{
 		cudaSetDevice(r->context->device);
 		cudaStream_t s = StreamOf(r->context);
-		if (r->d_positions) cudaFreeAsync(r->d_positions, s);
-		if (r->d_normals) cudaFreeAsync(r->d_normals, s);
-		if (r->d_colors) cudaFreeAsync(r->d_colors, s);
-		if (r->d_triangles) cudaFreeAsync(r->d_triangles, s);
-		if (r->d_face_normals) cudaFreeAsync(r->d_face_normals, s);
+		(void)s;
+		r->context->ReleaseDevice(r->d_positions);
+		r->context->ReleaseDevice(r->d_normals);
+		r->context->ReleaseDevice(r->d_colors);
+		r->context->ReleaseDevice(r->d_triangles);
+		r->context->ReleaseDevice(r->d_face_normals);
 		for (void* p : r->pinned) r->context->ReleasePinned(p);
 		delete r;
 	}
@@ -2051,8 +2107,8 @@ static int EnqueueAttributes(Model* model, Scratch& scratch, MeshResultDevice* r
 	const bool want_colors = (options.flags & TG_MESH_COLORS) != 0 && model->flat.has_paint;
 	const float scale = options.scale == 0.0f ? 1.0f : options.scale;
 	if (capacity == 0) return TG_OK;
-	if (want_normals) TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_normals), size_t(capacity) * 12, stream));
-	if (want_colors) TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_colors), size_t(capacity) * 3, stream));
+	if (want_normals) { void* p_ = ctx->AcquireDevice(size_t(capacity) * 12, error); if (!p_) return TG_ERR_MEMORY; result->d_normals = static_cast<decltype(result->d_normals)>(p_); }
+	if (want_colors) { void* p_ = ctx->AcquireDevice(size_t(capacity) * 3, error); if (!p_) return TG_ERR_MEMORY; result->d_colors = static_cast<decltype(result->d_colors)>(p_); }
 	const bool face_normals = (options.flags & TG_MESH_FACE_NORMALS) != 0;
 	if (!WantsAttributePass(model, options)) return TG_OK;
 	AttributeParams ap;
@@ -2267,7 +2323,7 @@ struct MeshJob
 static void DefaultCapacities(uint64_t slab_cells, uint32_t& cap_v, uint32_t& cap_q)
 {
 	// surfaces occupy a few percent of the cells at most; quads come to about one per vertex (three at the very most)
-	const uint64_t v = std::min<uint64_t>(slab_cells, std::max<uint64_t>(slab_cells / 32, 1 << 21));
+	const uint64_t v = std::min<uint64_t>(slab_cells, std::max<uint64_t>(slab_cells / 16, 1 << 22));
 	cap_v = uint32_t(std::min<uint64_t>(v, 0xFFFFFFF0ull));
 	cap_q = uint32_t(std::min<uint64_t>(std::min<uint64_t>(v * 3, std::max<uint64_t>(v + v / 2, 1 << 20)), 0x2AAAAAA0ull));
 	if (const char* env = std::getenv("TG_TEST_CAPACITY")) // tests: force the overflow-and-repeat path
@@ -2285,6 +2341,10 @@ static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const
 	Context* ctx = model->context;
 	cudaStream_t stream = static_cast<cudaStream_t>(lane ? ctx->stream2 : ctx->stream);
 	job.lane = lane;
+	const bool trace = std::getenv("TG_TRACE_HOST") != nullptr;
+	auto host_now = [] { return std::chrono::steady_clock::now(); };
+	const auto h_begin = host_now();
+	auto host_us = [&](const std::chrono::steady_clock::time_point& since) { return std::chrono::duration<double, std::micro>(host_now() - since).count(); };
 	job.model = model;
 	job.options = options;
 	DeviceGrid& grid = job.grid;
@@ -2332,7 +2392,24 @@ static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const
 	job.has_halo = has_halo;
 	job.own_bricks = uint64_t(nbx) * nby * (bz_end - bz_begin);
 	const uint64_t slab_cells = uint64_t(grid.sx) * grid.sy * (k_end - k_begin);
-	if (cap_v == 0) DefaultCapacities(slab_cells, cap_v, cap_q);
+	if (cap_v == 0)
+	{
+		DefaultCapacities(slab_cells, cap_v, cap_q);
+		if (!std::getenv("TG_TEST_CAPACITY"))
+		{
+			for (const Context::ExportHint& h : ctx->hints)
+			{
+				if (h.model == model && h.sx == grid.sx && h.sy == grid.sy && h.sz == grid.sz && h.k_begin == k_begin && h.k_end == k_end &&
+					h.flags == (options.flags & TG_MESH_NO_CULL))
+				{
+					// the same export ran before on this context: its counts (plus a little) are the capacities
+					cap_v = uint32_t(std::min<uint64_t>(h.vertices + h.vertices / 64 + 1024, 0xFFFFFFF0ull));
+					cap_q = uint32_t(std::min<uint64_t>(h.quads + h.quads / 64 + 1024, 0x2AAAAAA0ull));
+					break;
+				}
+			}
+		}
+	}
 	job.cap_v = cap_v;
 	job.cap_q = cap_q;
 
@@ -2359,6 +2436,7 @@ static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const
 	TG_CUDA(cudaMemsetAsync(bitmap, 0, bitmap_words * 8, stream));
 	job.counters = counters;
 	TG_CUDA(cudaEventRecord(job.marks[0], stream));
+	const double h_setup = host_us(h_begin);
 
 	// ---- K0: active brick list -------------------------------------------------------------------
 	const bool no_cull = (options.flags & TG_MESH_NO_CULL) != 0;
@@ -2410,6 +2488,7 @@ static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const
 		TG_CUDA(cudaGetLastError());
 	}
 	TG_CUDA(cudaEventRecord(job.marks[3], stream));
+	const double h_scan = host_us(h_begin);
 
 	// ---- K3: final vertex order, triangles -------------------------------------------------------
 	uint32_t* layer_starts = nullptr;
@@ -2417,8 +2496,9 @@ static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const
 	TG_CUDA(scratch.Alloc(&layer_starts, job.profile_layers + 2));
 	TG_CUDA(scratch.Alloc(&layer_cost, nbz_all));
 	TG_CUDA(cudaMemsetAsync(layer_cost, 0, size_t(nbz_all) * 8, stream));
-	TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_positions), size_t(cap_v) * 12, stream));
-	TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_triangles), size_t(cap_q) * 24, stream));
+	{ void* p_ = ctx->AcquireDevice(size_t(cap_v) * 12, error); if (!p_) return TG_ERR_MEMORY; result->d_positions = static_cast<decltype(result->d_positions)>(p_); }
+	{ void* p_ = ctx->AcquireDevice(size_t(cap_q) * 24, error); if (!p_) return TG_ERR_MEMORY; result->d_triangles = static_cast<decltype(result->d_triangles)>(p_); }
+	const double h_alloc = host_us(h_begin);
 	const bool attribute_pass = WantsAttributePass(model, options);
 	AttributeScratch as;
 	if (attribute_pass)
@@ -2474,7 +2554,7 @@ static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const
 	if (rc != TG_OK) return rc;
 	if (face_normals)
 	{
-		TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_face_normals), size_t(cap_q) * 24, stream));
+		{ void* p_ = ctx->AcquireDevice(size_t(cap_q) * 24, error); if (!p_) return TG_ERR_MEMORY; result->d_face_normals = static_cast<decltype(result->d_face_normals)>(p_); }
 		FaceNormalsKernel<<<uint32_t(ctx->sm_count) * 16u, 128, 0, stream>>>(MakeDeviceModel(model), result->d_positions, result->d_triangles, counters + kCntTotalQuads, cap_q, result->d_face_normals);
 		launches++;
 		const float scale = options.scale == 0.0f ? 1.0f : options.scale;
@@ -2490,6 +2570,7 @@ static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const
 	TG_CUDA(cudaGetLastError());
 	TG_CUDA(cudaEventRecord(job.all_ready, stream));
 	job.enqueued = true;
+	if (trace) std::fprintf(stderr, "host enqueue us: setup %.0f  through scan %.0f  result allocs %.0f  total %.0f\n", h_setup, h_scan, h_alloc, host_us(h_begin));
 	return TG_OK;
 }
 
@@ -2508,6 +2589,20 @@ static int WaitCounts(MeshJob& job, MeshCounts& counts, std::string& error)
 	counts.quads = mb.counters[kCntTotalQuads];
 	counts.halo = mb.halo_vertices;
 	counts.overflow = counts.vertices > job.cap_v || counts.quads > job.cap_q;
+	// remember the counts for the next export of the same slab of the same model (most recent first, a few dozen kept)
+	Context* ctx = job.model->context;
+	Context::ExportHint hint = { job.model, job.grid.sx, job.grid.sy, job.grid.sz, job.k_begin, job.k_end, job.options.flags & TG_MESH_NO_CULL, counts.vertices, counts.quads };
+	for (size_t i = 0; i < ctx->hints.size(); ++i)
+	{
+		const Context::ExportHint& h = ctx->hints[i];
+		if (h.model == hint.model && h.sx == hint.sx && h.sy == hint.sy && h.sz == hint.sz && h.k_begin == hint.k_begin && h.k_end == hint.k_end && h.flags == hint.flags)
+		{
+			ctx->hints.erase(ctx->hints.begin() + long(i));
+			break;
+		}
+	}
+	ctx->hints.insert(ctx->hints.begin(), hint);
+	if (ctx->hints.size() > 48) ctx->hints.pop_back();
 	return TG_OK;
 }
 
@@ -2562,11 +2657,12 @@ static int FinishJob(MeshJob& job, const MeshCounts& counts, tg_mesh* out, std::
 static void FreeResultDevice(MeshResultDevice* r, cudaStream_t s)
 {
 	if (!r) return;
-	if (r->d_positions) cudaFreeAsync(r->d_positions, s);
-	if (r->d_normals) cudaFreeAsync(r->d_normals, s);
-	if (r->d_colors) cudaFreeAsync(r->d_colors, s);
-	if (r->d_triangles) cudaFreeAsync(r->d_triangles, s);
-	if (r->d_face_normals) cudaFreeAsync(r->d_face_normals, s);
+	(void)s; // every caller has synchronised the streams that used these buffers
+	r->context->ReleaseDevice(r->d_positions);
+	r->context->ReleaseDevice(r->d_normals);
+	r->context->ReleaseDevice(r->d_colors);
+	r->context->ReleaseDevice(r->d_triangles);
+	r->context->ReleaseDevice(r->d_face_normals);
 	r->d_positions = r->d_normals = r->d_face_normals = nullptr;
 	r->d_colors = nullptr;
 	r->d_triangles = nullptr;
@@ -2748,12 +2844,12 @@ static int ExportMeshPipelined(Model* model, const tg_grid& grid_in, const tg_me
 	TG_CUDA(cudaEventCreate(&cull_marks[1]));
 	TG_CUDA(cudaEventRecord(cull_marks[0], stream));
 	{
-		if (!no_cull) TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&shared_flags), FlagWords(grid) * 4, stream));
+		if (!no_cull) { void* p_ = ctx->AcquireDevice(FlagWords(grid) * 4, error); if (!p_) return TG_ERR_MEMORY; shared_flags = static_cast<decltype(shared_flags)>(p_); }
 		Scratch cull_scratch(ctx, 0);
 		const int rc = BuildCullFlags(model, stream, cull_scratch, grid, 0, grid.sz, false, no_cull, shared_flags, shared_cull, cull_launches, error);
 		if (rc != TG_OK)
 		{
-			if (shared_flags) cudaFreeAsync(shared_flags, stream);
+			ctx->ReleaseDevice(shared_flags);
 			cudaEventDestroy(cull_marks[0]);
 			cudaEventDestroy(cull_marks[1]);
 			return rc;
@@ -2802,7 +2898,7 @@ static int ExportMeshPipelined(Model* model, const tg_grid& grid_in, const tg_me
 		cudaStreamSynchronize(stream);
 		cudaStreamSynchronize(lane1);
 		cudaStreamSynchronize(copy_stream);
-		if (shared_flags) cudaFreeAsync(shared_flags, stream);
+		ctx->ReleaseDevice(shared_flags);
 		cudaEventDestroy(cull_marks[0]);
 		cudaEventDestroy(cull_marks[1]);
 		for (auto& j : jobs)
@@ -2923,7 +3019,7 @@ static int ExportMeshPipelined(Model* model, const tg_grid& grid_in, const tg_me
 		total.cull_ms += cull_ms;
 		total.kernel_launches += cull_launches;
 	}
-	if (shared_flags) cudaFreeAsync(shared_flags, stream);
+	ctx->ReleaseDevice(shared_flags);
 	cudaEventDestroy(cull_marks[0]);
 	cudaEventDestroy(cull_marks[1]);
 	for (auto& j : jobs)
@@ -3269,7 +3365,7 @@ int EngineExportPoints(Model* model, const float mn[3], const float mx[3], const
 	out->vertex_count = count;
 	if (count > 0)
 	{
-		TG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&result->d_positions), size_t(count) * 12, stream));
+		{ void* p_ = ctx->AcquireDevice(size_t(count) * 12, error); if (!p_) return TG_ERR_MEMORY; result->d_positions = static_cast<decltype(result->d_positions)>(p_); }
 		GatherCloudKernel<<<uint32_t((total + 255) / 256), 256, 0, stream>>>(d_hits, d_prefix, total, mn[0], mn[1], mn[2], step[0], step[1], step[2], n[0], n[1], result->d_positions);
 		launches++;
 		ctx->stage.store(refine > 0 ? 2 : 3);

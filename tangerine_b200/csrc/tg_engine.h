@@ -30,6 +30,7 @@ public:
 	void* copy_events[1] = { nullptr };
 	void* timer_events[2] = { nullptr, nullptr };
 	std::vector<PinnedBlock> pinned; // grow-only pool of page-locked host buffers for results
+	std::vector<PinnedBlock> device_blocks; // grow-only cache of device buffers for results (no allocator call in steady state)
 	std::vector<void*> mailboxes;    // free list of small page-locked blocks the device delivers its counts into
 	void* index_base = nullptr;      // device: running vertex total of the slabs already emitted (pipelined export)
 	// last whole-grid export on this context, so that the next identical one can size its host arrays exactly
@@ -50,8 +51,17 @@ public:
 	static Context* Create(int device, std::string& error);
 	~Context();
 
+	// vertex / quad counts of recent exports, so that a repeated export sizes its arrays exactly
+	struct ExportHint { const void* model; uint64_t sx, sy, sz, k_begin, k_end; uint32_t flags; uint64_t vertices, quads; };
+	std::vector<ExportHint> hints;
+
 	void* AcquirePinned(size_t bytes, std::string& error);
 	void ReleasePinned(void* ptr);
+	// Result buffers.  Released only after every stream that touched them was synchronised, so a released block can
+	// be handed out again at once.  (cudaMallocAsync in the export path queued behind NVML / driver locks and showed
+	// up as milliseconds of idle GPU in short exports.)
+	void* AcquireDevice(size_t bytes, std::string& error);
+	void ReleaseDevice(void* ptr);
 	void* AcquireMailbox(std::string& error);
 	void ReleaseMailbox(void* ptr);
 	bool Cancelled() const { return !active.load(); }
