@@ -229,7 +229,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-stride", type=int, default=0, help="z-slice stride of the CPU sample (0 = auto)")
     ap.add_argument("--no-cull", action="store_true", help="evaluate every brick like the reference does")
-    ap.add_argument("--slab-align", type=int, default=2, help="z-slab cuts fall on multiples of this many cell layers (8 = whole brick rows)")
+    ap.add_argument("--slab-align", type=int, default=1, help="z-slab cuts fall on multiples of this many cell layers (8 = whole brick rows)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -238,7 +238,7 @@ def main():
     import torch
     import torch.distributed as dist
     import tangerine_b200 as T
-    from tangerine_b200.slabs import balanced_slabs, exchange_counts, layer_costs
+    from tangerine_b200.slabs import balanced_slabs, exchange_counts, layer_costs, rebalance
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -332,7 +332,11 @@ def main():
                 predicted = cost[k0:k1].sum()
                 if predicted > 0 and allv[n + 4 + r] > 0:
                     cost[k0:k1] *= allv[n + 4 + r] / predicted
-            slabs = balanced_slabs(cost, world, sz, args.slab_align)
+            if w < 2:
+                slabs = balanced_slabs(cost, world, sz, args.slab_align)
+            else:
+                # the cost model has placed the cuts roughly; from here on they move by the measured times alone
+                slabs = rebalance(slabs, [allv[n + 4 + r] for r in range(world)], sz, args.slab_align)
             slab = slabs[rank]
         mesh.close()
     sampler = ClockSampler(local)
@@ -350,9 +354,10 @@ def main():
     ms_total = all_max(ms_local)
     ms_per_step = ms_total / args.steps
     # per-rank view of the same region: wall (events around the K steps) and the sum of the engine's stage timers
-    per_rank = [[ms_local / args.steps, float(np.mean([s["total_device_ms"] for s in steps]))]]
+    stage_keys = ("cull_ms", "evaluate_ms", "compact_ms", "faces_ms", "attributes_ms")
+    per_rank = [[ms_local / args.steps, float(np.mean([s["total_device_ms"] for s in steps]))] + [float(np.mean([s[k] for s in steps])) for k in stage_keys]]
     if world > 1:
-        t = torch.zeros((world, 2), dtype=torch.float64, device="cuda")
+        t = torch.zeros((world, len(per_rank[0])), dtype=torch.float64, device="cuda")
         dist.all_gather_into_tensor(t, torch.tensor(per_rank[0], dtype=torch.float64, device="cuda"))
         per_rank = t.cpu().numpy().tolist()
     value = cells_total / (ms_per_step * 1e-3) * 1e-6
@@ -460,7 +465,8 @@ def main():
             "mesh": {"vertices": vertices, "triangles": triangles},
             "bricks": {"total": bricks_total, "evaluated": bricks_eval},
             "stage_ms_rank0": {k: mean(k) for k in ("cull_ms", "evaluate_ms", "compact_ms", "faces_ms", "attributes_ms", "total_device_ms")},
-            "per_rank_ms": {"step_wall": [round(r[0], 4) for r in per_rank], "stage_sum": [round(r[1], 4) for r in per_rank]},
+            "per_rank_ms": dict({"step_wall": [round(r[0], 4) for r in per_rank], "stage_sum": [round(r[1], 4) for r in per_rank]},
+                                **{k: [round(r[2 + i], 4) for r in per_rank] for i, k in enumerate(stage_keys)}),
             "model_build_s": model_seconds, "octree_nodes": stats["octree_nodes"],
             "e2e": {"value": e2e_value, "unit": "Mvoxel/s", "ms_per_step": e2e_wall_ms / args.steps, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
                     "timed": "host wall clock around tg_model_upload + tg_export_mesh (pinned host results)%s, max over ranks" % (" + NCCL count all-gather + tg_mesh_download (index rebase on device)" if world > 1 else ""),

@@ -48,6 +48,32 @@ def balanced_slabs(profile, world, sz, align=BRICK):
     return [(cuts[r] * align, min(cuts[r + 1] * align, sz)) for r in range(world)]
 
 
+def rebalance(slabs, times, sz, align=1, relax=0.7):
+    """One step of measured-time balancing: every cut between neighbouring slabs moves towards the slower side by
+    the number of layers that would equalise the two, judged by their mean time per layer, damped by `relax`.
+    Needs only the per-slab times of the last run (every rank holds all of them after one all-reduce), makes no
+    assumption about where inside a slab the work sits, and converges where a global cost model oscillates."""
+    world = len(slabs)
+    if world == 1:
+        return list(slabs)
+    cuts = [s[0] for s in slabs] + [slabs[-1][1]]
+    t = [max(float(x), 1e-9) for x in times]
+    new = list(cuts)
+    for b in range(1, world):
+        left, right = b - 1, b
+        len_l, len_r = cuts[b] - cuts[b - 1], cuts[b + 1] - cuts[b]
+        rho_l, rho_r = t[left] / len_l, t[right] / len_r
+        delta = relax * (t[right] - t[left]) / (rho_l + rho_r)      # > 0: the right slab is slower, the cut moves up
+        delta = max(-0.5 * (len_l - align), min(0.5 * (len_r - align), delta))
+        new[b] = int(round((cuts[b] + delta) / align)) * align
+    for b in range(1, world):                                        # keep every slab at least `align` thick
+        new[b] = max(new[b], new[b - 1] + align)
+    for b in range(world - 1, 0, -1):
+        new[b] = min(new[b], new[b + 1] - align if b + 1 < world else sz - align)
+    new[world] = sz
+    return [(new[r], new[r + 1]) for r in range(world)]
+
+
 def uniform_slabs(world, sz):
     """Equal-thickness slabs (the cut used before any work profile exists)."""
     return balanced_slabs(np.ones(sz), world, sz)
