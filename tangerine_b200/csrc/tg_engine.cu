@@ -481,6 +481,8 @@ constexpr int kCullLevels = 5; // 8, 16, 32, 64, 128 cells
 #endif
 constexpr uint32_t kSeedSpan = TG_SEED_SPAN; // a region is seeded at the finest level where it spans fewer bricks than this per axis
 constexpr uint32_t kFlagPositive = 1u, kFlagNegative = 2u, kFlagEvaluate = 4u;
+constexpr int kCostShift = 3;       // 8-cell level only: bits 3.. of a flag word accumulate the brick's work estimate
+constexpr int kCostClasses = 32;    // half-octave classes of that estimate; the brick list is written longest class first
 
 struct CullItem
 {
@@ -655,6 +657,14 @@ __global__ void __launch_bounds__(128) CullLevelKernel(const CullParams p)
 		live = lo_i <= hi_i && lo_j <= hi_j && lo_k <= hi_k;
 	}
 	uint32_t* flag = &p.flags[level][(size_t(cz) * p.dims[level][1] + cy) * p.dims[level][0] + cx];
+	if (live && level == 0)
+	{
+		// work estimate of the brick, kept above the three flag bits of its word: samples of this region in the brick x
+		// the cost of the region's program.  CullResolveKernel orders the brick list by it (longest first).
+		const uint32_t samples = (hi_i - lo_i + 1u) * (hi_j - lo_j + 1u) * (hi_k - lo_k + 1u);
+		const uint32_t flops = __ldg(&p.model.nodes[p.model.regions[item.region].node].flops);
+		atomicAdd(flag, (((samples * (min(flops, 1u << 20) + 64u)) >> 10) + 1u) << kCostShift);
+	}
 	if (live && KnownEmpty(p.model, p.model.regions[item.region], g, lo_i, hi_i, lo_j, hi_j, lo_k, hi_k))
 	{
 		atomicOr(flag, kFlagPositive);
@@ -662,11 +672,15 @@ __global__ void __launch_bounds__(128) CullLevelKernel(const CullParams p)
 	}
 	// An empty octant runs its parent's large program: once the known ball has failed, do not pay for it at every
 	// level on the way down -- split to the 8-cell bricks and evaluate there, once.
-	const bool defer = level > 0 && p.model.regions[item.region].known_value > 0.0f;
+	// Any long program costs one thread ~a thousand cycles per primitive (dependent fetch + sqrt chain), and a level has
+	// too few such items to hide that: the three finest levels each used to wait ~170 us for one 336-primitive program
+	// of seaside_town.  Long programs are therefore evaluated at every other level only (128, 32 and 8 cells).
+	const uint32_t node = p.model.regions[item.region].node;
+	const uint32_t node_flags = live ? __ldg(&p.model.nodes[node].flags) : 0u;
+	const bool defer = level > 0 && (p.model.regions[item.region].known_value > 0.0f || ((node_flags & kNodeLong) != 0u && (level & 1) != 0));
 	if (live && !defer)
 	{
-		const uint32_t node = p.model.regions[item.region].node;
-		if (__ldg(&p.model.nodes[node].flags) & kNodeCullable)
+		if (node_flags & kNodeCullable)
 		{
 			const float lox = LatticeCoord(g.x, g.dx, lo_i), loy = LatticeCoord(g.y, g.dy, lo_j), loz = LatticeCoord(g.z, g.dz, lo_k);
 			const float hix = LatticeCoord(g.x, g.dx, hi_i), hiy = LatticeCoord(g.y, g.dy, hi_j), hiz = LatticeCoord(g.z, g.dz, hi_k);
@@ -718,13 +732,13 @@ __global__ void __launch_bounds__(128) CullLevelKernel(const CullParams p)
 
 // One thread per 8-cell brick of the slab (and of the halo row below it): combine the flags it inherits.
 __global__ void __launch_bounds__(256) CullResolveKernel(const CullParams p, uint32_t bz_begin, uint32_t bz_end, int no_cull,
-	uint32_t* __restrict__ out_list, unsigned long long* out_counter, uint32_t out_capacity)
+	uint32_t* __restrict__ out_list, unsigned long long* out_counter, uint32_t out_capacity, unsigned char* __restrict__ out_class, uint32_t* __restrict__ class_counts)
 {
 	const uint32_t nbx = p.dims[0][0], nby = p.dims[0][1];
 	const uint32_t index = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t rows = bz_end - bz_begin;
 	bool active = false;
-	uint32_t brick = 0;
+	uint32_t brick = 0, cost = 0;
 	if (index < nbx * nby * rows)
 	{
 		const uint32_t x = index % nbx, y = (index / nbx) % nby, z = index / (nbx * nby) + bz_begin;
@@ -732,8 +746,11 @@ __global__ void __launch_bounds__(256) CullResolveKernel(const CullParams p, uin
 		if (no_cull) f = kFlagEvaluate;
 		else
 		{
+			const uint32_t f0 = p.flags[0][(size_t(z) * p.dims[0][1] + y) * p.dims[0][0] + x];
+			cost = f0 >> kCostShift;
+			f = f0 & ((1u << kCostShift) - 1u);
 #pragma unroll
-			for (int level = 0; level < kCullLevels; ++level)
+			for (int level = 1; level < kCullLevels; ++level)
 			{
 				f |= p.flags[level][(size_t(z >> level) * p.dims[level][1] + (y >> level)) * p.dims[level][0] + (x >> level)];
 			}
@@ -747,11 +764,51 @@ __global__ void __launch_bounds__(256) CullResolveKernel(const CullParams p, uin
 	unsigned long long base = 0;
 	if (lane == 0) base = atomicAdd(out_counter, (unsigned long long)__popc(ballot));
 	base = __shfl_sync(0xFFFFFFFFu, base, 0);
+	// half-octave class of the work estimate: 2 * log2 + the bit below the leading one
+	const uint32_t lg = cost ? 31u - uint32_t(__clz(int(cost))) : 0u;
+	const uint32_t cls = cost ? min(uint32_t(kCostClasses - 1), 2u * lg + (lg ? ((cost >> (lg - 1u)) & 1u) : 0u)) : 0u;
 	if (active)
 	{
 		const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
-		if (slot < out_capacity) out_list[slot] = brick;
+		if (slot < out_capacity)
+		{
+			out_list[slot] = brick;
+			out_class[slot] = (unsigned char)cls;
+		}
 	}
+	const unsigned peers = __match_any_sync(0xFFFFFFFFu, active ? cls : 0xFFFFFFFFu);
+	if (active && lane == __ffs(peers) - 1) atomicAdd(&class_counts[cls], uint32_t(__popc(peers)));
+}
+
+// Second half of the ordering: every list entry moves to its class's segment, the costliest class first, so that the
+// persistent warps of the brick kernel meet the long bricks early and finish on short ones (longest-processing-time
+// list scheduling: a brick keeps one warp busy for ~100 us, a slab of an 8-GPU run is only five bricks deep per warp).
+__global__ void __launch_bounds__(256) BrickOrderKernel(const uint32_t* __restrict__ list, const unsigned char* __restrict__ classes, const unsigned long long* __restrict__ count_ptr,
+	uint32_t capacity, const uint32_t* __restrict__ class_counts, uint32_t* __restrict__ class_cursor, uint32_t* __restrict__ ordered, uint32_t order_limit)
+{
+	__shared__ uint32_t class_base[kCostClasses];
+	const uint32_t count = uint32_t(min(*count_ptr, (unsigned long long)capacity));
+	// A long list (many bricks per persistent warp) has no tail to speak of, and then the spatial order of the list is
+	// worth more -- neighbouring bricks share octree nodes and programs, and the vertex scatter that follows is more
+	// local: everything goes to one class.
+	const bool by_cost = count <= order_limit;
+	if (threadIdx.x < kCostClasses)
+	{
+		uint32_t before = 0;
+		for (int c = kCostClasses - 1; c > int(threadIdx.x); --c) before += class_counts[c];
+		class_base[threadIdx.x] = by_cost ? before : 0u;
+	}
+	__syncthreads();
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool valid = i < count;
+	const uint32_t cls = valid ? (by_cost ? uint32_t(classes[i]) : 0u) : 0xFFFFFFFFu;
+	const unsigned peers = __match_any_sync(0xFFFFFFFFu, cls);
+	if (!valid) return;
+	const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+	uint32_t at = 0;
+	if (lane == leader) at = atomicAdd(&class_cursor[cls], uint32_t(__popc(peers)));
+	at = __shfl_sync(peers, at, leader);
+	ordered[class_base[cls] + at + uint32_t(__popc(peers & ((1u << lane) - 1u)))] = list[i];
 }
 
 // Estimated work per brick layer: every active brick weighs in with the FLOPs of the program at its centre (evaluation
@@ -2244,17 +2301,35 @@ static int BuildCullFlags(Model* model, cudaStream_t stream, Scratch& scratch, c
 static int ResolveActiveList(cudaStream_t stream, Scratch& scratch, const CullParams& cp, const DeviceGrid& grid, uint32_t k_begin, uint32_t k_end,
 	bool has_halo, bool no_cull, unsigned long long* counters, uint32_t** out_list, uint64_t* out_count, uint64_t& launches, std::string& error)
 {
+	const uint32_t order_warps = uint32_t(scratch.ctx->sm_count) * uint32_t(scratch.ctx->brick_blocks_per_sm) * uint32_t(kBrickWarps);
 	const uint32_t nbx = (grid.sx + kBrick - 1) / kBrick, nby = (grid.sy + kBrick - 1) / kBrick;
 	const uint32_t bz_end = (k_end + kBrick - 1) / kBrick;
 	const uint32_t row_begin = (has_halo ? k_begin - 1 : k_begin) / kBrick; // the brick row that holds the halo layer
 	const size_t slab_bricks = size_t(nbx) * nby * (bz_end - row_begin);
 	const size_t list_capacity = slab_bricks + 8;
 	uint32_t* active_list = nullptr;
+	uint32_t* ordered_list = nullptr;
+	unsigned char* classes = nullptr;
+	uint32_t* class_counts = nullptr; // kCostClasses totals, then kCostClasses cursors
 	TG_CUDA(scratch.Alloc(&active_list, list_capacity));
+	TG_CUDA(scratch.Alloc(&ordered_list, list_capacity));
+	TG_CUDA(scratch.Alloc(&classes, list_capacity));
+	TG_CUDA(scratch.Alloc(&class_counts, 2 * kCostClasses));
+	TG_CUDA(cudaMemsetAsync(class_counts, 0, 2 * kCostClasses * sizeof(uint32_t), stream));
 	const uint32_t resolve_threads = uint32_t(slab_bricks);
 	CullResolveKernel<<<(resolve_threads + 255) / 256, 256, 0, stream>>>(cp, row_begin, bz_end, no_cull ? 1 : 0,
-		active_list, counters + kCntListA, uint32_t(list_capacity));
+		active_list, counters + kCntListA, uint32_t(list_capacity), classes, class_counts);
 	launches++;
+	if (!no_cull)
+	{
+		// ordered when a persistent warp of the brick kernel gets fewer than a dozen bricks (TG_BRICK_ORDER=0 / 1: never / always)
+		uint32_t order_limit = order_warps * 12u;
+		if (const char* env = std::getenv("TG_BRICK_ORDER")) order_limit = std::atoi(env) > 0 ? 0xFFFFFFFFu : 0u;
+		BrickOrderKernel<<<uint32_t((list_capacity + 255) / 256), 256, 0, stream>>>(active_list, classes, counters + kCntListA, uint32_t(list_capacity),
+			class_counts, class_counts + kCostClasses, ordered_list, order_limit);
+		launches++;
+		active_list = ordered_list;
+	}
 	TG_CUDA(cudaGetLastError());
 	*out_list = active_list;
 	*out_count = list_capacity; // capacity of the list; its length stays on the device in counters[kCntListA]

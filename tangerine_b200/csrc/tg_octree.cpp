@@ -178,6 +178,7 @@ struct StreamGen
 	int max_slots = 0;  // deepest spill slot used + 1
 	uint32_t flops = 0;
 	bool cullable = true;
+	std::vector<uint32_t> starts; // kStreamInterp: quad offset of every instruction (Stop excluded), relative to the first
 
 	StreamGen(const NodePool& p, std::vector<uint32_t>& o, bool tree) : pool(p), out(o), tree_stream(tree) {}
 
@@ -248,6 +249,7 @@ struct StreamGen
 	void EmitBrushQuads(const Node& n, uint32_t op, float threshold, uint32_t flags)
 	{
 		const size_t start = out.size();
+		starts.push_back(uint32_t(start / 4));
 		out.push_back(0);
 		for (int i = 0; i < 3; ++i)
 		{
@@ -307,6 +309,7 @@ struct StreamGen
 	void EmitOp(uint32_t op, float param, uint32_t word, bool has_word, uint32_t flags)
 	{
 		const size_t start = out.size();
+		if (!tree_stream) starts.push_back(uint32_t(start / 4));
 		out.push_back(0);
 		uint32_t slot = kNoSlot;
 		if (op != kOpFlate && op != kOpStop)
@@ -396,6 +399,7 @@ struct Flattener
 {
 	FlatModel& model;
 	std::vector<uint32_t> ref_words;
+	std::vector<uint32_t> program; // kStreamInterp program of the node being emitted
 	int max_slots = 0;
 
 	// Pre-order walk (same order as the octree hash in oracle/ref_tool.cpp) emitting one FlatNode per octree node.
@@ -411,15 +415,20 @@ struct Flattener
 			fn.pivot[2] = bn.pivot.z;
 			fn.terminus = bn.terminus ? 1u : 0u;
 			for (int i = 0; i < 8; ++i) fn.children[i] = -1;
-			fn.interp_offset = uint32_t(model.interp.size());
 			fn.tree_offset = uint32_t(model.tree.size());
-			StreamGen interp(st.pool, model.interp, false);
+			program.clear();
+			StreamGen interp(st.pool, program, false);
 			interp.Gen(bn.evaluator);
 			interp.Finish();
+			fn.flags = interp.cullable ? kNodeCullable : 0u;
+			const size_t count = interp.starts.size();
+			fn.flags |= uint32_t(std::min<size_t>(count, (1u << 24) - 1u)) << kNodeCountShift;
+			if (count >= kLongProgram) fn.flags |= kNodeLong;
+			fn.interp_offset = uint32_t(model.interp.size());
+			model.interp.insert(model.interp.end(), program.begin(), program.end());
 			StreamGen tree(st.pool, model.tree, true);
 			tree.Gen(bn.evaluator);
 			tree.Finish();
-			fn.flags = interp.cullable ? kNodeCullable : 0u;
 			fn.flops = interp.flops;
 			if (tree.max_slots > max_slots) max_slots = tree.max_slots;
 			model.nodes[self] = fn;
@@ -554,7 +563,7 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 	}
 
 	out.stats.hash = 0xCBF29CE484222325ull;
-	Flattener flattener{ out };
+	Flattener flattener{ out, {}, {}, 0 };
 	{
 		const float lo[3] = { -INFINITY, -INFINITY, -INFINITY }, hi[3] = { INFINITY, INFINITY, INFINITY };
 		flattener.Walk(top, top.root, lo, hi);

@@ -147,5 +147,10 @@ struct FlatRegion
 static_assert(sizeof(FlatRegion) == 48, "FlatRegion layout");
 
 constexpr uint32_t kNodeCullable = 1u; // every primitive in the program is a true distance bound (no Ellipsoid)
+// Long programs (interior octree nodes keep hundreds of primitives) are flagged: one thread walking such a program
+// is bound by the latency of a dependent fetch + sqrt chain per primitive, and K0 schedules around that.
+constexpr uint32_t kNodeLong = 2u;       // FlatNode::flags: at least kLongProgram instructions
+constexpr uint32_t kNodeCountShift = 8;  // FlatNode::flags >> 8: instruction count of the kStreamInterp program (Stop excluded)
+constexpr uint32_t kLongProgram = 32;
 
 } // namespace tg

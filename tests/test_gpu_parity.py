@@ -137,6 +137,20 @@ def test_lattice_samples_bit_exact(name, models, oracles):
     assert np.array_equal(got >= 0, want >= 0)
 
 
+@pytest.mark.parametrize("name", ["seaside_town", "gear", "color-cube"])
+def test_far_field_point_queries(name, models, oracles):
+    """Points all over the bounding box and beyond the octree cube: most fall into empty octants of interior octree
+    nodes, where the reference evaluates the interior node's long program (sdf_evaluator.cpp:1828-1834)."""
+    tree, model = models(name)
+    om, oc = oracles(name)
+    lo, hi = tree.bounds()
+    rng = np.random.default_rng(7)
+    pts = (lo + (hi - lo) * rng.random((20000, 3))).astype(np.float32)
+    pts[:3000] = (lo - 0.3 + (hi - lo + 0.6) * rng.random((3000, 3))).astype(np.float32)  # outside the octree cube too
+    got = model.eval_points(pts, T.EVAL_OCTREE)
+    assert same_floats(got, oc.eval(pts))
+
+
 @pytest.mark.parametrize("name", ["basic_thing", "kitchen_sink", "gear"])
 def test_mesh_vertex_order_and_triangles_match_oracle(name, golden, models, oracles):
     tree, model = models(name)
