@@ -84,7 +84,7 @@ __device__ __forceinline__ float4 AsFloat4(const uint4& v)
 // Every fetch is a 128-bit load whose address does not depend on another fetch of the same instruction, and the
 // first quad of the next instruction is requested before this instruction's arithmetic starts.  The operator
 // switch sits outside the per-sample loops, so with a warp-uniform program there is one dispatch per brush.
-template <int S, bool PREFETCH = false>
+template <int S, bool PREFETCH = false, bool DEEP = false>
 __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const float (&px)[S], const float (&py)[S], const float (&pz)[S], float (&result)[S])
 {
 	float acc[S];
@@ -92,12 +92,11 @@ __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const f
 #pragma unroll
 	for (int s = 0; s < S; ++s) acc[s] = 0.0f;
 	uint4 q = __ldg(pc);
-	// PREFETCH (one thread, one point: culling, point queries, refinement) is latency bound -- nothing else hides the
-	// fetch of an instruction's operands behind the sqrt chain of the previous one -- so the four quads that can follow
-	// a header are requested a whole instruction ahead, whether or not the instruction turns out to use them (programs
-	// are contiguous and the stream ends in padding, so reading past an instruction is harmless).
+	// DEEP (K0: one thread walks a long program with next to nothing else resident to hide its latency): the four quads
+	// that can follow a header are requested a whole instruction ahead, whether or not the instruction turns out to
+	// use them (programs are contiguous and the stream ends in padding, so reading past an instruction is harmless).
 	uint4 m0 = q, m1 = q, m2 = q, m3 = q;
-	if (PREFETCH)
+	if (DEEP)
 	{
 		m0 = __ldg(pc + 1);
 		m1 = __ldg(pc + 2);
@@ -112,15 +111,15 @@ __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const f
 		const uint32_t slot = (header >> kHdrSlotShift) & 0xFFu;
 		const uint4* next = pc + (header >> kHdrLenShift);
 		uint4 nq = q, n0 = q, n1 = q, n2 = q, n3 = q;
-		if (PREFETCH)
+		if (DEEP)
 		{
 			nq = __ldg(next);
 			n0 = __ldg(next + 1);
 			n1 = __ldg(next + 2);
 			n2 = __ldg(next + 3);
 			n3 = __ldg(next + 4);
-			asm volatile("prefetch.global.L1 [%0];" ::"l"(pc + 32)); // 512 B ahead: long programs stream from L2 / HBM
 		}
+		if (PREFETCH) asm volatile("prefetch.global.L1 [%0];" ::"l"(pc + 32)); // 512 B ahead: long programs stream from L2 / HBM
 		if (brush != kBrushNone)
 		{
 			const float p0 = __uint_as_float(q.y), p1 = __uint_as_float(q.z), p2 = __uint_as_float(q.w);
@@ -129,16 +128,16 @@ __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const f
 			float scale = 1.0f, threshold = 0.0f;
 			if (xform == kXformMatrix)
 			{
-				const float4 a = PREFETCH ? AsFloat4(m0) : __ldg(reinterpret_cast<const float4*>(pc + 1));
-				const float4 b = PREFETCH ? AsFloat4(m1) : __ldg(reinterpret_cast<const float4*>(pc + 2));
-				const float4 c = PREFETCH ? AsFloat4(m2) : __ldg(reinterpret_cast<const float4*>(pc + 3));
+				const float4 a = DEEP ? AsFloat4(m0) : __ldg(reinterpret_cast<const float4*>(pc + 1));
+				const float4 b = DEEP ? AsFloat4(m1) : __ldg(reinterpret_cast<const float4*>(pc + 2));
+				const float4 c = DEEP ? AsFloat4(m2) : __ldg(reinterpret_cast<const float4*>(pc + 3));
 				if (header & kHdrTailBit)
 				{
-					const float4 t = PREFETCH ? AsFloat4(m3) : __ldg(reinterpret_cast<const float4*>(pc + 4));
+					const float4 t = DEEP ? AsFloat4(m3) : __ldg(reinterpret_cast<const float4*>(pc + 4));
 					scale = t.x;
 					threshold = t.y;
 				}
-				if (!PREFETCH) q = __ldg(next);
+				if (!DEEP) q = __ldg(next);
 				// glm mat4 * vec4(p, 1): (m0*x + m1*y) + (m2*z + m3*1)  (type_mat4x4.inl:561-572)
 				// columns: m0 = (a.x a.y a.z), m1 = (a.w b.x b.y), m2 = (b.z b.w c.x), m3 = (c.y c.z c.w)
 #pragma unroll
@@ -151,14 +150,14 @@ __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const f
 			}
 			else if (xform == kXformOffset)
 			{
-				const float4 o = PREFETCH ? AsFloat4(m0) : __ldg(reinterpret_cast<const float4*>(pc + 1));
+				const float4 o = DEEP ? AsFloat4(m0) : __ldg(reinterpret_cast<const float4*>(pc + 1));
 				if (header & kHdrTailBit)
 				{
-					const float4 t = PREFETCH ? AsFloat4(m1) : __ldg(reinterpret_cast<const float4*>(pc + 2));
+					const float4 t = DEEP ? AsFloat4(m1) : __ldg(reinterpret_cast<const float4*>(pc + 2));
 					scale = t.x;
 					threshold = t.y;
 				}
-				if (!PREFETCH) q = __ldg(next);
+				if (!DEEP) q = __ldg(next);
 #pragma unroll
 				for (int s = 0; s < S; ++s)
 				{
@@ -171,11 +170,11 @@ __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const f
 			{
 				if (header & kHdrTailBit)
 				{
-					const float4 t = PREFETCH ? AsFloat4(m0) : __ldg(reinterpret_cast<const float4*>(pc + 1));
+					const float4 t = DEEP ? AsFloat4(m0) : __ldg(reinterpret_cast<const float4*>(pc + 1));
 					scale = t.x;
 					threshold = t.y;
 				}
-				if (!PREFETCH) q = __ldg(next);
+				if (!DEEP) q = __ldg(next);
 #pragma unroll
 				for (int s = 0; s < S; ++s)
 				{
@@ -273,7 +272,7 @@ __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const f
 		else
 		{
 			const float param = __uint_as_float(q.y);
-			if (!PREFETCH) q = __ldg(next);
+			if (!DEEP) q = __ldg(next);
 			pc = next;
 			if (op == kOpFlate)
 			{
@@ -287,7 +286,7 @@ __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const f
 				for (int s = 0; s < S; ++s) acc[s] = sdf::SetOp(op, stack[slot][s], acc[s], param);
 			}
 		}
-		if (PREFETCH)
+		if (DEEP)
 		{
 			q = nq;
 			m0 = n0;
@@ -298,11 +297,12 @@ __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const f
 	}
 }
 
+template <bool DEEP = false>
 __device__ __forceinline__ float EvalInterp1(const DeviceModel& model, uint32_t word_offset, float x, float y, float z)
 {
 	const float px[1] = { x }, py[1] = { y }, pz[1] = { z };
 	float out[1];
-	EvalInterp<1, true>(model.interp + (word_offset >> 2), px, py, pz, out);
+	EvalInterp<1, true, DEEP>(model.interp + (word_offset >> 2), px, py, pz, out);
 	return out[0];
 }
 

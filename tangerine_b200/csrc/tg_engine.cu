@@ -50,12 +50,13 @@ constexpr int kTileSamples = kTile * kTile * kTile; // 729
 constexpr int kTilePadded = 736;
 constexpr int kBrickWarps = 4;            // warps per block of the brick kernels; every warp works alone
 constexpr int kBrickThreads = kBrickWarps * 32;
-constexpr int kMaxGroups = 32;            // distinct octree nodes per grouping round (one table slot per lane)
+constexpr int kMaxPending = 192;          // (node, box) pairs waiting in a warp's box resolution
+constexpr int kMaxFinal = 32;             // resolved (node, box) pairs per evaluation batch (one per lane)
+constexpr uint32_t kResolvedBit = 0x80000000u;
 #ifndef TG_LANE_SAMPLES
 #define TG_LANE_SAMPLES 2
 #endif
 constexpr int kLaneSamples = TG_LANE_SAMPLES; // samples interpreted per lane per dispatch
-constexpr uint32_t kEmptyGroup = 0xFFFFFFFFu;
 constexpr uint32_t kHaloFlag = 1u << 30;
 // The brick kernel is instruction-cache bound before it is anything else (ncu: stall_no_instruction): its bookkeeping
 // loops (per-round descent, sort, classification) are kept rolled so that the interpreter stays resident.
@@ -108,11 +109,14 @@ struct MeshParams
 
 struct WarpTile
 {
-	float tile[kTilePadded];       // sample values; while samples are being grouped: (group << 16) | rank
-	uint16_t order[kTilePadded];   // sample indices sorted by group; later the brick's active cell list
-	uint32_t group_node[kMaxGroups];
-	uint32_t group_count[kMaxGroups];
-	uint32_t group_start[kMaxGroups];
+	float tile[kTilePadded];          // sample values
+	uint16_t order[kTilePadded];      // sample indices grouped by octree node; later the brick's active cell list
+	uint32_t pend_node[kMaxPending];  // box resolution: (node to descend from, sample box) still to be resolved
+	uint32_t pend_box[kMaxPending];
+	uint32_t fin_node[kMaxFinal];     // resolved (octree node, sample box) pairs of the current evaluation batch
+	uint32_t fin_box[kMaxFinal];
+	uint32_t fin_start[kMaxFinal + 1]; // offset of each pair's samples in `order`
+	uint16_t rows[kTile * kTile + 1];  // sign bits of the tile, one word per row of 9 samples
 };
 
 __device__ __forceinline__ void TileCoords(const DeviceGrid& grid, uint32_t i0, uint32_t j0, uint32_t k0, int s, float& x, float& y, float& z)
@@ -125,170 +129,234 @@ __device__ __forceinline__ void TileCoords(const DeviceGrid& grid, uint32_t i0, 
 	z = LatticeCoord(grid.z, grid.dz, k0 + lk);
 }
 
+// A sample box of the tile: inclusive index ranges, four bits each.
+__device__ __forceinline__ uint32_t PackBox(int x0, int x1, int y0, int y1, int z0, int z1)
+{
+	return uint32_t(x0) | (uint32_t(x1) << 4) | (uint32_t(y0) << 8) | (uint32_t(y1) << 12) | (uint32_t(z0) << 16) | (uint32_t(z1) << 20);
+}
+__device__ __forceinline__ int BoxSamples(uint32_t b)
+{
+	return (int((b >> 4) & 15u) - int(b & 15u) + 1) * (int((b >> 12) & 15u) - int((b >> 8) & 15u) + 1) * (int((b >> 20) & 15u) - int((b >> 16) & 15u) + 1);
+}
+
+// First index in [a, b + 1] whose lattice coordinate is > pivot (SDFOctree::Descend's strict test, :1806-1817);
+// origin + float(i) * step is monotonic in i, so the samples below it take the lower octant and the rest the upper.
+__device__ __forceinline__ int SplitIndex(float origin, float step, uint32_t base, int a, int b, float pivot)
+{
+	int i = a;
+	while (i <= b && !(LatticeCoord(origin, step, base + uint32_t(i)) > pivot)) ++i;
+	return i;
+}
+
 // Evaluates the lattice samples (li < ni, lj < nj, kmin <= lk < nk) of a tile whose corner sample has lattice
-// index (i0, j0, k0) into w.tile.  Samples are first mapped to their octree node (SDFOctree::Descend), then
-// sorted by node so that every dispatch of the interpreter runs ONE program for the whole warp, kLaneSamples
-// samples per lane.  There is exactly one instantiation of the interpreter in the kernel (instruction-cache
-// footprint: every resident warp is in a different phase); a brick that straddles more than kMaxGroups nodes
-// repeats the group / evaluate round on the samples that did not get a table slot.
+// index (i0, j0, k0) into w.tile.
+//
+// Which program a sample runs is decided by SDFOctree::Descend (sdf_evaluator.cpp:1801-1835), and the points that
+// end at one node form a box.  So the tile is not descended sample by sample: the warp resolves BOXES.  A pending
+// (node, box) pair follows the octree while the whole box stays in one octant; where a pivot plane cuts it, it
+// splits into up to eight boxes (monotonic lattice coordinates: one split index per axis).  With leaves of >= 16
+// cells an 8-cell tile is cut at most once per axis, so a brick resolves in two or three lane-parallel rounds; coarse
+// grids (leaves smaller than a brick) just take more rounds.  Resolved pairs are sorted by node, their samples are
+// written to `order`, and every distinct node gets ONE run of interpreter dispatches over all its samples,
+// kLaneSamples per lane -- the only instantiation of the interpreter in the kernel (instruction-cache footprint).
 __device__ __forceinline__ void EvaluateTile(WarpTile& w, const DeviceModel& model, const DeviceGrid& grid,
 	uint32_t i0, uint32_t j0, uint32_t k0, int ni, int nj, int nk, int kmin, unsigned long long* counters)
 {
 	const int lane = threadIdx.x & 31;
-	constexpr int kRounds = (kTileSamples + 31) / 32;
-
-	// Brick-level descent: follow the octree while the whole tile lies in one octant.
-	uint32_t start = 0;
+	const unsigned lanes_below = (1u << lane) - 1u;
+	if (lane == 0)
 	{
-		const float lox = LatticeCoord(grid.x, grid.dx, i0), loy = LatticeCoord(grid.y, grid.dy, j0), loz = LatticeCoord(grid.z, grid.dz, k0 + kmin);
-		const float hix = LatticeCoord(grid.x, grid.dx, i0 + ni - 1), hiy = LatticeCoord(grid.y, grid.dy, j0 + nj - 1), hiz = LatticeCoord(grid.z, grid.dz, k0 + nk - 1);
-		for (;;)
-		{
-			const float4 head = __ldg(reinterpret_cast<const float4*>(&model.nodes[start]));
-			if (__float_as_uint(head.w) != 0u) break;
-			const int olo = (lox > head.x ? 1 : 0) | (loy > head.y ? 2 : 0) | (loz > head.z ? 4 : 0);
-			const int ohi = (hix > head.x ? 1 : 0) | (hiy > head.y ? 2 : 0) | (hiz > head.z ? 4 : 0);
-			if (olo != ohi) break;
-			const int32_t child = __ldg(&model.nodes[start].children[olo]);
-			if (child < 0) break;
-			start = uint32_t(child);
-		}
+		w.pend_node[0] = 0u; // the octree root
+		w.pend_box[0] = PackBox(0, ni - 1, 0, nj - 1, kmin, nk - 1);
 	}
-
-	// bit r of `pending`: sample 32 r + lane still has to be evaluated
-	uint32_t pending = 0;
-	for (int r = 0; r < kRounds; ++r)
+	__syncwarp();
+	int pend = 1, fin = 0;
+	for (;;)
 	{
-		const int s = r * 32 + lane;
-		if (s < kTileSamples)
+		// boxes resolved this round: as many as fit the lists (a split adds at most seven entries, a box at most one pair)
+		// A nearly full list is worked depth-first, one box at a time: a box then adds at most 7 entries per octree level
+		// below it, and 96 spare entries cover octrees 13 levels deep (the write below traps rather than overflow).
+		const int take = min(min(32, pend), max(1, (kMaxPending - 96 - pend) / 7));
+		if (fin > 0 && (pend == 0 || fin + take > kMaxFinal))
 		{
-			const int lk = s / (kTile * kTile);
-			const int rem = s - lk * (kTile * kTile);
-			const int lj = rem / kTile, li = rem - lj * kTile;
-			if (li < ni && lj < nj && lk < nk && lk >= kmin) pending |= 1u << r;
-		}
-	}
-
-	while (__any_sync(0xFFFFFFFFu, pending != 0u))
-	{
-		w.group_node[lane] = kEmptyGroup;
-		w.group_count[lane] = 0;
-		__syncwarp();
-
-		// Pass 1: per-sample descent, warp-aggregated insertion into the brick's node table (open addressing).
-		uint32_t assigned = 0;
-#pragma unroll kUnrollBookkeeping
-		for (int r = 0; r < kRounds; ++r)
-		{
-			const bool mine = (pending >> r) & 1u;
-			if (!__any_sync(0xFFFFFFFFu, mine)) continue;
-			const int s = r * 32 + lane;
-			uint32_t node = kEmptyGroup;
-			if (mine)
-			{
-				float x, y, z;
-				TileCoords(grid, i0, j0, k0, s, x, y, z);
-				node = Descend(model.nodes, start, x, y, z);
-			}
-			const unsigned peers = __match_any_sync(0xFFFFFFFFu, node);
-			if (mine)
-			{
-				const int leader = __ffs(peers) - 1;
-				uint32_t group = kEmptyGroup, rank0 = 0;
-				if (lane == leader)
-				{
-					uint32_t g = (node * 0x9E3779B1u) >> 27;
+			// ---- evaluation batch: sort the pairs by node, lay their samples out in `order`, run each node once ----
+			uint32_t node_e = lane < fin ? w.fin_node[lane] : 0xFFFFFFFFu;
+			uint32_t box_e = lane < fin ? w.fin_box[lane] : 0u;
+			int rank = 0;
 #pragma unroll 1
-					for (int probe = 0; probe < kMaxGroups; ++probe, g = (g + 1) & (kMaxGroups - 1))
+			for (int j = 0; j < fin; ++j)
+			{
+				const uint32_t other = __shfl_sync(0xFFFFFFFFu, node_e, j);
+				rank += (other < node_e || (other == node_e && j < lane)) ? 1 : 0;
+			}
+			__syncwarp();
+			if (lane < fin)
+			{
+				w.fin_node[rank] = node_e;
+				w.fin_box[rank] = box_e;
+			}
+			__syncwarp();
+			node_e = lane < fin ? w.fin_node[lane] : 0xFFFFFFFFu;
+			box_e = lane < fin ? w.fin_box[lane] : 0u;
+			const uint32_t size_e = lane < fin ? uint32_t(BoxSamples(box_e)) : 0u;
+			uint32_t incl = size_e;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+				if (lane >= o) incl += v;
+			}
+			const uint32_t start_e = incl - size_e;
+			if (lane < fin) w.fin_start[lane] = start_e;
+			if (lane == 31) w.fin_start[fin] = incl; // the batch total closes the last run
+			const uint32_t before = __shfl_up_sync(0xFFFFFFFFu, node_e, 1);
+			unsigned heads = __ballot_sync(0xFFFFFFFFu, lane < fin && (lane == 0 || before != node_e));
+			const uint32_t flops = size_e ? size_e * __ldg(&model.nodes[node_e].flops) : 0u;
+			const uint32_t flops_total = __reduce_add_sync(0xFFFFFFFFu, flops);
+			if (lane == 31)
+			{
+				atomicAdd(&counters[kCntSamples], (unsigned long long)incl);
+				atomicAdd(&counters[kCntFlops], (unsigned long long)flops_total);
+			}
+#pragma unroll 1
+			for (int e = 0; e < fin; ++e)
+			{
+				const uint32_t b = __shfl_sync(0xFFFFFFFFu, box_e, e);
+				const int first = int(__shfl_sync(0xFFFFFFFFu, start_e, e));
+				const int x0 = int(b & 15u), y0 = int((b >> 8) & 15u), z0 = int((b >> 16) & 15u);
+				const int dx = int((b >> 4) & 15u) - x0 + 1, dy = int((b >> 12) & 15u) - y0 + 1, dz = int((b >> 20) & 15u) - z0 + 1;
+				const int layer = dx * dy, n = layer * dz;
+				const float inv_layer = 1.0f / float(layer), inv_dx = 1.0f / float(dx);
+				for (int u = lane; u < n; u += 32)
+				{
+					// u < 729 and the divisors are <= 81: (u + 0.5) / d is at least 0.5 / 81 away from an integer, far more than the rounding
+					const int c = __float2int_rd((float(u) + 0.5f) * inv_layer);
+					const int r = u - c * layer;
+					const int q = __float2int_rd((float(r) + 0.5f) * inv_dx);
+					w.order[first + u] = uint16_t(((z0 + c) * kTile + (y0 + q)) * kTile + (x0 + r - q * dx));
+				}
+			}
+			__syncwarp();
+			while (heads)
+			{
+				const int g = __ffs(heads) - 1;
+				heads &= heads - 1u;
+				const int first = int(w.fin_start[g]);
+				const int total = int(w.fin_start[heads ? __ffs(heads) - 1 : fin]) - first;
+				const uint4* program = model.interp + (__ldg(&model.nodes[w.fin_node[g]].interp_offset) >> 2);
+				for (int done = 0; done < total; done += 32 * kLaneSamples)
+				{
+					const int count_here = min(total - done, 32 * kLaneSamples);
+					float px[kLaneSamples], py[kLaneSamples], pz[kLaneSamples], d[kLaneSamples];
+					int sample[kLaneSamples];
+#pragma unroll
+					for (int q = 0; q < kLaneSamples; ++q)
 					{
-						uint32_t seen = w.group_node[g];
-						if (seen == kEmptyGroup)
-						{
-							seen = atomicCAS(&w.group_node[g], kEmptyGroup, node); // other leaders of this warp race for the slot
-							if (seen == kEmptyGroup) seen = node;
-						}
-						if (seen == node)
-						{
-							group = g;
-							rank0 = atomicAdd(&w.group_count[g], uint32_t(__popc(peers)));
-							break;
-						}
+						const int idx = lane + 32 * q;
+						const int s = w.order[first + done + (idx < count_here ? idx : 0)];
+						sample[q] = idx < count_here ? s : -1;
+						TileCoords(grid, i0, j0, k0, s, px[q], py[q], pz[q]);
+					}
+					EvalInterp<kLaneSamples>(program, px, py, pz, d);
+#pragma unroll
+					for (int q = 0; q < kLaneSamples; ++q)
+					{
+						if (sample[q] >= 0) w.tile[sample[q]] = d[q];
 					}
 				}
-				group = __shfl_sync(peers, group, leader);
-				rank0 = __shfl_sync(peers, rank0, leader);
-				if (group != kEmptyGroup) // else the table is full: the sample waits for the next round
+			}
+			__syncwarp();
+			fin = 0;
+		}
+		if (pend == 0) break;
+
+		// ---- one round of box resolution: lane l takes the l-th pending pair from the top of the list ----
+		const bool mine = lane < take;
+		uint32_t node = 0u, box = 0u;
+		if (mine)
+		{
+			node = w.pend_node[pend - 1 - lane];
+			box = w.pend_box[pend - 1 - lane];
+		}
+		__syncwarp();
+		pend -= take;
+		bool resolved = false;
+		int x0 = 0, x1 = 0, y0 = 0, y1 = 0, z0 = 0, z1 = 0, xs = 0, ys = 0, zs = 0, parts = 0;
+		if (mine)
+		{
+			if (node & kResolvedBit)
+			{
+				node &= ~kResolvedBit; // an empty octant met by a split: Descend stops at the parent (:1828-1834)
+				resolved = true;
+			}
+			else
+			{
+				x0 = int(box & 15u), x1 = int((box >> 4) & 15u), y0 = int((box >> 8) & 15u), y1 = int((box >> 12) & 15u), z0 = int((box >> 16) & 15u), z1 = int((box >> 20) & 15u);
+				const float lox = LatticeCoord(grid.x, grid.dx, i0 + x0), loy = LatticeCoord(grid.y, grid.dy, j0 + y0), loz = LatticeCoord(grid.z, grid.dz, k0 + z0);
+				const float hix = LatticeCoord(grid.x, grid.dx, i0 + x1), hiy = LatticeCoord(grid.y, grid.dy, j0 + y1), hiz = LatticeCoord(grid.z, grid.dz, k0 + z1);
+				for (;;)
 				{
-					w.tile[s] = __uint_as_float((group << 16) | (rank0 + uint32_t(__popc(peers & ((1u << lane) - 1u)))));
-					assigned |= 1u << r;
+					const float4 head = __ldg(reinterpret_cast<const float4*>(&model.nodes[node]));
+					if (__float_as_uint(head.w) != 0u)
+					{
+						resolved = true;
+						break;
+					}
+					const int olo = (lox > head.x ? 1 : 0) | (loy > head.y ? 2 : 0) | (loz > head.z ? 4 : 0);
+					const int ohi = (hix > head.x ? 1 : 0) | (hiy > head.y ? 2 : 0) | (hiz > head.z ? 4 : 0);
+					if (olo != ohi)
+					{
+						// a pivot plane cuts the box: lower part [a, split - 1], upper part [split, b] on every axis (either may be empty)
+						xs = ((olo ^ ohi) & 1) ? SplitIndex(grid.x, grid.dx, i0, x0, x1, head.x) : ((olo & 1) ? x0 : x1 + 1);
+						ys = ((olo ^ ohi) & 2) ? SplitIndex(grid.y, grid.dy, j0, y0, y1, head.y) : ((olo & 2) ? y0 : y1 + 1);
+						zs = ((olo ^ ohi) & 4) ? SplitIndex(grid.z, grid.dz, k0, z0, z1, head.z) : ((olo & 4) ? z0 : z1 + 1);
+						parts = ((xs > x0 ? 1 : 0) + (xs <= x1 ? 1 : 0)) * ((ys > y0 ? 1 : 0) + (ys <= y1 ? 1 : 0)) * ((zs > z0 ? 1 : 0) + (zs <= z1 ? 1 : 0));
+						break;
+					}
+					const int32_t child = __ldg(&model.nodes[node].children[olo]);
+					if (child < 0)
+					{
+						resolved = true;
+						break;
+					}
+					node = uint32_t(child);
 				}
 			}
 		}
-		__syncwarp();
-
-		// Lane g owns group g: an exclusive scan gives each group its slice of `order`.
-		const uint32_t count = w.group_count[lane];
-		uint32_t incl = count;
+		const unsigned done_mask = __ballot_sync(0xFFFFFFFFu, resolved);
+		if (resolved)
+		{
+			const int slot = fin + __popc(done_mask & lanes_below);
+			w.fin_node[slot] = node;
+			w.fin_box[slot] = box;
+		}
+		fin += __popc(done_mask);
+		int incl = parts;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1)
 		{
-			const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-			if (lane >= o) incl += a;
+			const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+			if (lane >= o) incl += v;
 		}
-		w.group_start[lane] = incl - count;
-		const uint32_t flops = count ? count * __ldg(&model.nodes[w.group_node[lane]].flops) : 0u;
-		const uint32_t flops_total = __reduce_add_sync(0xFFFFFFFFu, flops);
-		if (lane == 31)
+		const int added = __shfl_sync(0xFFFFFFFFu, incl, 31);
+		if (parts)
 		{
-			atomicAdd(&counters[kCntSamples], (unsigned long long)incl);
-			atomicAdd(&counters[kCntFlops], (unsigned long long)flops_total);
-		}
-		unsigned live = __ballot_sync(0xFFFFFFFFu, count != 0u);
-		__syncwarp();
-
-		// Pass 2: sample indices sorted by group.
-#pragma unroll kUnrollBookkeeping
-		for (int r = 0; r < kRounds; ++r)
-		{
-			if ((assigned >> r) & 1u)
+			int at = pend + incl - parts;
+#pragma unroll 1
+			for (int o = 0; o < 8; ++o)
 			{
-				const int s = r * 32 + lane;
-				const uint32_t code = __float_as_uint(w.tile[s]);
-				w.order[w.group_start[code >> 16] + (code & 0xFFFFu)] = uint16_t(s);
+				const int ax = (o & 1) ? xs : x0, bx = (o & 1) ? x1 : xs - 1;
+				const int ay = (o & 2) ? ys : y0, by = (o & 2) ? y1 : ys - 1;
+				const int az = (o & 4) ? zs : z0, bz = (o & 4) ? z1 : zs - 1;
+				if (ax > bx || ay > by || az > bz) continue;
+				const int32_t child = __ldg(&model.nodes[node].children[o]);
+				if (at >= kMaxPending) __trap();
+				w.pend_node[at] = child < 0 ? (node | kResolvedBit) : uint32_t(child);
+				w.pend_box[at] = PackBox(ax, bx, ay, by, az, bz);
+				++at;
 			}
 		}
-		pending &= ~assigned;
-		__syncwarp();
-
-		// Evaluation: one program at a time, 32 * kLaneSamples samples per dispatch.
-		while (live)
-		{
-			const int g = __ffs(live) - 1;
-			live &= live - 1;
-			const int total = int(w.group_count[g]);
-			const int first = int(w.group_start[g]);
-			const uint4* program = model.interp + (__ldg(&model.nodes[w.group_node[g]].interp_offset) >> 2);
-			for (int done = 0; done < total; done += 32 * kLaneSamples)
-			{
-				const int count_here = min(total - done, 32 * kLaneSamples);
-				float px[kLaneSamples], py[kLaneSamples], pz[kLaneSamples], d[kLaneSamples];
-				int sample[kLaneSamples];
-#pragma unroll
-				for (int q = 0; q < kLaneSamples; ++q)
-				{
-					const int idx = lane + 32 * q;
-					const int s = w.order[first + done + (idx < count_here ? idx : 0)];
-					sample[q] = idx < count_here ? s : -1;
-					TileCoords(grid, i0, j0, k0, s, px[q], py[q], pz[q]);
-				}
-				EvalInterp<kLaneSamples>(program, px, py, pz, d);
-#pragma unroll
-				for (int q = 0; q < kLaneSamples; ++q)
-				{
-					if (sample[q] >= 0) w.tile[sample[q]] = d[q];
-				}
-			}
-		}
+		pend += added;
 		__syncwarp();
 	}
 }
@@ -348,38 +416,51 @@ __global__ void __launch_bounds__(kBrickThreads) MeshBricksKernel(const MeshPara
 
 		EvaluateTile(w, p.model, grid, i0, j0, k0, ni, nj, nk, kmin, p.counters);
 
-		// Classification: sign bits of FirstLoopInnerThunk (surface_nets.cpp:864-907); active cells go to the
-		// bitmap (one byte per 8-cell row) and, when this slab owns them, to the brick's cell list.
-		int emit_total = 0;
-#pragma unroll kUnrollBookkeeping
-		for (int base = 0; base < kBrick * kBrick * kBrick; base += 32)
+		// Classification: sign bits of FirstLoopInnerThunk (surface_nets.cpp:864-907).  is_scalar_positive is
+		// `scalar >= isovalue` (:733-735: -0.0 is positive, NaN is negative), and a cell is active when its eight corners
+		// do not agree (:903-907).  The signs of a sample row (9 samples along x) are packed into one word first; a lane
+		// then classifies a whole row of 8 cells with a dozen bit operations on the four sample rows around it, and the
+		// result IS the row's byte of the active-cell bitmap.
+		for (int r = lane; r < kTile * kTile; r += 32)
 		{
-			const int c = base + lane;
-			const int ci = c & 7, cj = (c >> 3) & 7, ck = c >> 6;
-			const uint32_t gi = i0 + ci, gj = j0 + cj, gk = k0 + ck;
-			const bool in_grid = gi < grid.sx && gj < grid.sy && gk < p.k_own_end && ck >= kmin;
-			bool active = false;
-			if (in_grid)
+			const float* t = w.tile + r * kTile;
+			uint32_t bits = 0;
+#pragma unroll
+			for (int i = 0; i < kTile; ++i) bits |= (t[i] >= 0.0f ? 1u : 0u) << i;
+			w.rows[r] = uint16_t(bits);
+		}
+		__syncwarp();
+		int emit_total = 0;
+		const uint32_t cells_x = min(uint32_t(kBrick), grid.sx - i0);
+#pragma unroll 1
+		for (int round = 0; round < 2; ++round)
+		{
+			const int cr = round * 32 + lane; // cell row: cj = cr & 7, ck = cr >> 3
+			const int cj = cr & 7, ck = cr >> 3;
+			const uint32_t gj = j0 + cj, gk = k0 + ck;
+			const uint32_t r00 = w.rows[ck * kTile + cj], r01 = w.rows[ck * kTile + cj + 1];
+			const uint32_t r10 = w.rows[(ck + 1) * kTile + cj], r11 = w.rows[(ck + 1) * kTile + cj + 1];
+			const uint32_t all = r00 & r01 & r10 & r11, any = r00 | r01 | r10 | r11;
+			uint32_t active = ~((all & (all >> 1)) | ~(any | (any >> 1))) & ((1u << cells_x) - 1u);
+			// the slab owns cell layers [k_own_begin, k_own_end) and classifies the halo layer k_base below it
+			if (!(gj < grid.sy && gk < p.k_own_end && ck >= kmin)) active = 0u;
+			if (active) bitmap_bytes[(size_t(gk - p.k_base) * grid.sy + gj) * (size_t(p.row_words) * 8u) + bx] = (unsigned char)active;
+			uint32_t emit = gk >= p.k_own_begin ? active : 0u; // the halo layer is classified but owned by the slab below
+			const int count = __popc(emit);
+			int incl = count;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
 			{
-				float v[8];
-				const unsigned signs = CellCorners(w, c, v);
-				active = signs != 0u && signs != 0xFFu;
+				const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+				if (lane >= o) incl += v;
 			}
-			const unsigned ballot = __ballot_sync(0xFFFFFFFFu, active);
-			// a warp pass covers 4 rows of 8 cells: lanes 0, 8, 16, 24 publish their row's byte
-			if ((lane & 7) == 0)
+			int at = emit_total + incl - count;
+			while (emit)
 			{
-				const unsigned byte = (ballot >> lane) & 0xFFu;
-				const bool layer_ok = gk >= p.k_base && gk < p.k_own_end && gj < grid.sy && ck >= kmin;
-				if (byte != 0u && layer_ok)
-				{
-					bitmap_bytes[(size_t(gk - p.k_base) * grid.sy + gj) * (size_t(p.row_words) * 8u) + bx] = (unsigned char)byte;
-				}
+				w.order[at++] = uint16_t(cr * kBrick + __ffs(emit) - 1);
+				emit &= emit - 1u;
 			}
-			const bool emit = active && gk >= p.k_own_begin; // the halo layer is classified but owned by the slab below
-			const unsigned emit_ballot = __ballot_sync(0xFFFFFFFFu, emit);
-			if (emit) w.order[emit_total + __popc(emit_ballot & ((1u << lane) - 1u))] = uint16_t(c);
-			emit_total += __popc(emit_ballot);
+			emit_total += __shfl_sync(0xFFFFFFFFu, incl, 31);
 		}
 		__syncwarp();
 		if (emit_total == 0) continue;
@@ -687,7 +768,7 @@ __global__ void __launch_bounds__(128) CullLevelKernel(const CullParams p)
 			const float ex = hix - lox, ey = hiy - loy, ez = hiz - loz;
 			const float radius = 0.5f * sqrtf(ex * ex + ey * ey + ez * ez);
 			const float threshold = radius * 1.001f + 1.0e-4f;
-			const float d = EvalInterp1(p.model, __ldg(&p.model.nodes[node].interp_offset), 0.5f * (lox + hix), 0.5f * (loy + hiy), 0.5f * (loz + hiz));
+			const float d = EvalInterp1<true>(p.model, __ldg(&p.model.nodes[node].interp_offset), 0.5f * (lox + hix), 0.5f * (loy + hiy), 0.5f * (loz + hiz));
 			if (fabsf(d) > threshold)
 			{
 				atomicOr(flag, d > 0.0f ? kFlagPositive : kFlagNegative);
@@ -796,12 +877,17 @@ __global__ void __launch_bounds__(256) BrickOrderKernel(const uint32_t* __restri
 	{
 		uint32_t before = 0;
 		for (int c = kCostClasses - 1; c > int(threadIdx.x); --c) before += class_counts[c];
-		class_base[threadIdx.x] = by_cost ? before : 0u;
+		class_base[threadIdx.x] = before;
 	}
 	__syncthreads();
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool valid = i < count;
-	const uint32_t cls = valid ? (by_cost ? uint32_t(classes[i]) : 0u) : 0xFFFFFFFFu;
+	if (!by_cost)
+	{
+		if (valid) ordered[i] = list[i];
+		return;
+	}
+	const uint32_t cls = valid ? uint32_t(classes[i]) : 0xFFFFFFFFu;
 	const unsigned peers = __match_any_sync(0xFFFFFFFFu, cls);
 	if (!valid) return;
 	const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
