@@ -425,9 +425,20 @@ def main():
     # SURVEY.md 8d "algorithmic bytes (mesh side)": cell->vertex map + neighbour ids + positions + indices + normals + colours
     mesh_bytes = slab_cells / 8.0 + 36.0 * r0_v + 12.0 * r0_v + 12.0 * r0_f + 12.0 * r0_v + 3.0 * r0_v
     mesh_ms = mean("compact_ms") + mean("faces_ms")
+    # DRAM traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed
+    # `ncu --set full` capture of this same workload (profiles/ncu_meshbricks.json names the capture); null otherwise
+    traffic, ncu_note = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_meshbricks.json")) as f:
+            cap = json.load(f)
+        if cap.get("workload") == args.workload and world == 1:
+            traffic = float(cap["dram_bytes_read"]) + float(cap["dram_bytes_write"])
+            ncu_note = {k: cap[k] for k in ("source", "issue_active_pct", "warp_instructions", "thread_instructions_per_sample") if k in cap}
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {
         "kernel": "MeshBricksKernel", "bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-        "frac": achieved_tflops / fp32_peak if fp32_peak else None, "traffic": None,
+        "frac": achieved_tflops / fp32_peak if fp32_peak else None, "traffic": traffic, "traffic_unit": "bytes per launch (ncu)", "ncu": ncu_note,
         "peak_source": "FP32 FMA-chain kernel measured in this run (MEASURED_PEAKS.json has no CUDA-core figure); theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5",
         "flops_convention": "SURVEY.md 8(d): FMA = 2, sqrt/div/abs/compare = 1, summed over the samples actually evaluated (culled bricks earn nothing)",
         "kernel_ms": eval_ms, "share_of_step": eval_ms / mean("total_device_ms") if mean("total_device_ms") else None,
