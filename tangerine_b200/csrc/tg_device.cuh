@@ -75,6 +75,13 @@ __device__ __forceinline__ uint32_t Descend(const FlatNode* __restrict__ nodes, 
 	}
 }
 
+// Returns v through an empty asm statement: the compiler can no longer tell that two comparisons test the same value.
+__device__ __forceinline__ uint32_t Opaque(uint32_t& v)
+{
+	asm volatile("" : "+r"(v));
+	return v;
+}
+
 __device__ __forceinline__ float4 AsFloat4(const uint4& v)
 {
 	return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
@@ -106,9 +113,9 @@ __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const f
 	for (;;)
 	{
 		const uint32_t header = q.x;
+		// fields are compared in place (mask, no shift): the decode runs once per primitive per 64 samples
 		const uint32_t brush = header & kHdrBrushMask;
-		const uint32_t op = (header >> kHdrOpShift) & 0xFu;
-		const uint32_t slot = (header >> kHdrSlotShift) & 0xFFu;
+		const uint32_t op = header & (0xFu << kHdrOpShift);
 		const uint4* next = pc + (header >> kHdrLenShift);
 		uint4 nq = q, n0 = q, n1 = q, n2 = q, n3 = q;
 		if (DEEP)
@@ -123,10 +130,10 @@ __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const f
 		if (brush != kBrushNone)
 		{
 			const float p0 = __uint_as_float(q.y), p1 = __uint_as_float(q.z), p2 = __uint_as_float(q.w);
-			const uint32_t xform = (header >> kHdrXformShift) & 3u;
+			const uint32_t xform = header & (3u << kHdrXformShift);
 			float lx[S], ly[S], lz[S];
 			float scale = 1.0f, threshold = 0.0f;
-			if (xform == kXformMatrix)
+			if (xform == (kXformMatrix << kHdrXformShift))
 			{
 				const float4 a = DEEP ? AsFloat4(m0) : __ldg(reinterpret_cast<const float4*>(pc + 1));
 				const float4 b = DEEP ? AsFloat4(m1) : __ldg(reinterpret_cast<const float4*>(pc + 2));
@@ -148,7 +155,7 @@ __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const f
 					lz[s] = (a.z * px[s] + b.y * py[s]) + (c.x * pz[s] + c.w);
 				}
 			}
-			else if (xform == kXformOffset)
+			else if (xform == (kXformOffset << kHdrXformShift))
 			{
 				const float4 o = DEEP ? AsFloat4(m0) : __ldg(reinterpret_cast<const float4*>(pc + 1));
 				if (header & kHdrTailBit)
@@ -185,85 +192,98 @@ __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const f
 			}
 			pc = next;
 
+			// Dispatch by comparison chains, commonest first: a jump table costs nine instructions per dispatch (clamp,
+			// scale, constant-bank load, BRX), a taken comparison two, and these run once per primitive per 64 samples.
 			float d[S];
-			switch (brush)
+			uint32_t kind = brush, oper = op; // laundered between comparisons: keeps the chain from being turned back into a table
+			if (kind == kBrushBox)
 			{
-			case kBrushSphere:
-#pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Sphere(lx[s], ly[s], lz[s], p0);
-				break;
-			case kBrushEllipsoid:
-#pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Ellipsoid(lx[s], ly[s], lz[s], p0, p1, p2);
-				break;
-			case kBrushBox:
 #pragma unroll
 				for (int s = 0; s < S; ++s) d[s] = sdf::Box(lx[s], ly[s], lz[s], p0, p1, p2);
-				break;
-			case kBrushTorus:
+			}
+			else if (Opaque(kind) == kBrushSphere)
+			{
 #pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Torus(lx[s], ly[s], lz[s], p0, p1);
-				break;
-			case kBrushCylinder:
+				for (int s = 0; s < S; ++s) d[s] = sdf::Sphere(lx[s], ly[s], lz[s], p0);
+			}
+			else if (Opaque(kind) == kBrushCylinder)
+			{
 #pragma unroll
 				for (int s = 0; s < S; ++s) d[s] = sdf::Cylinder(lx[s], ly[s], lz[s], p0, p1);
-				break;
-			case kBrushCone:
+			}
+			else if (Opaque(kind) == kBrushTorus)
+			{
 #pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Cone(lx[s], ly[s], lz[s], p0, p1);
-				break;
-			case kBrushConinder:
-#pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Coninder(lx[s], ly[s], lz[s], p0, p1, p2);
-				break;
-			default:
+				for (int s = 0; s < S; ++s) d[s] = sdf::Torus(lx[s], ly[s], lz[s], p0, p1);
+			}
+			else if (Opaque(kind) == kBrushPlane)
+			{
 #pragma unroll
 				for (int s = 0; s < S; ++s) d[s] = sdf::Plane(lx[s], ly[s], lz[s], p0, p1, p2);
-				break;
+			}
+			else if (Opaque(kind) == kBrushEllipsoid)
+			{
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Ellipsoid(lx[s], ly[s], lz[s], p0, p1, p2);
+			}
+			else if (Opaque(kind) == kBrushCone)
+			{
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Cone(lx[s], ly[s], lz[s], p0, p1);
+			}
+			else
+			{
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Coninder(lx[s], ly[s], lz[s], p0, p1, p2);
 			}
 			if (header & kHdrScaleBit)
 			{
 #pragma unroll
 				for (int s = 0; s < S; ++s) d[s] = d[s] * scale; // ScaleField (:1587-1591)
 			}
-			switch (op)
+			if (oper == (kOpPush << kHdrOpShift))
 			{
-			case kOpPush:
-				if (slot != kNoSlot)
+				if ((header & (0xFFu << kHdrSlotShift)) != (kNoSlot << kHdrSlotShift))
 				{
+					const uint32_t slot = (header >> kHdrSlotShift) & 0xFFu;
 #pragma unroll
 					for (int s = 0; s < S; ++s) stack[slot][s] = acc[s];
 				}
 #pragma unroll
 				for (int s = 0; s < S; ++s) acc[s] = d[s];
-				break;
-			case kOpUnion:
+			}
+			else if (Opaque(oper) == (kOpUnion << kHdrOpShift))
+			{
 #pragma unroll
 				for (int s = 0; s < S; ++s) acc[s] = sdf::Union(acc[s], d[s]);
-				break;
-			case kOpInter:
-#pragma unroll
-				for (int s = 0; s < S; ++s) acc[s] = sdf::Inter(acc[s], d[s]);
-				break;
-			case kOpDiff:
-#pragma unroll
-				for (int s = 0; s < S; ++s) acc[s] = sdf::Diff(acc[s], d[s]);
-				break;
-			case kOpBlendUnion:
+			}
+			else if (Opaque(oper) == (kOpBlendUnion << kHdrOpShift))
+			{
 #pragma unroll
 				for (int s = 0; s < S; ++s) acc[s] = sdf::BlendUnion(acc[s], d[s], threshold);
-				break;
-			case kOpBlendInter:
+			}
+			else if (Opaque(oper) == (kOpDiff << kHdrOpShift))
+			{
 #pragma unroll
-				for (int s = 0; s < S; ++s) acc[s] = sdf::BlendInter(acc[s], d[s], threshold);
-				break;
-			default:
+				for (int s = 0; s < S; ++s) acc[s] = sdf::Diff(acc[s], d[s]);
+			}
+			else if (Opaque(oper) == (kOpInter << kHdrOpShift))
+			{
+#pragma unroll
+				for (int s = 0; s < S; ++s) acc[s] = sdf::Inter(acc[s], d[s]);
+			}
+			else if (Opaque(oper) == (kOpBlendDiff << kHdrOpShift))
+			{
 #pragma unroll
 				for (int s = 0; s < S; ++s) acc[s] = sdf::BlendDiff(acc[s], d[s], threshold);
-				break;
+			}
+			else
+			{
+#pragma unroll
+				for (int s = 0; s < S; ++s) acc[s] = sdf::BlendInter(acc[s], d[s], threshold);
 			}
 		}
-		else if (op == kOpStop)
+		else if (op == (kOpStop << kHdrOpShift))
 		{
 #pragma unroll
 			for (int s = 0; s < S; ++s) result[s] = acc[s];
@@ -274,7 +294,7 @@ __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const f
 			const float param = __uint_as_float(q.y);
 			if (!DEEP) q = __ldg(next);
 			pc = next;
-			if (op == kOpFlate)
+			if (op == (kOpFlate << kHdrOpShift))
 			{
 #pragma unroll
 				for (int s = 0; s < S; ++s) acc[s] = acc[s] - param; // :1567-1571
@@ -282,8 +302,41 @@ __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const f
 			else
 			{
 				// stack-form set operator: lhs was spilled, rhs is the accumulator
+				const uint32_t slot = (header >> kHdrSlotShift) & 0xFFu;
+				float lhs[S];
 #pragma unroll
-				for (int s = 0; s < S; ++s) acc[s] = sdf::SetOp(op, stack[slot][s], acc[s], param);
+				for (int s = 0; s < S; ++s) lhs[s] = stack[slot][s];
+				uint32_t oper = op;
+				if (oper == (kOpUnion << kHdrOpShift))
+				{
+#pragma unroll
+					for (int s = 0; s < S; ++s) acc[s] = sdf::Union(lhs[s], acc[s]);
+				}
+				else if (Opaque(oper) == (kOpDiff << kHdrOpShift))
+				{
+#pragma unroll
+					for (int s = 0; s < S; ++s) acc[s] = sdf::Diff(lhs[s], acc[s]);
+				}
+				else if (Opaque(oper) == (kOpInter << kHdrOpShift))
+				{
+#pragma unroll
+					for (int s = 0; s < S; ++s) acc[s] = sdf::Inter(lhs[s], acc[s]);
+				}
+				else if (Opaque(oper) == (kOpBlendUnion << kHdrOpShift))
+				{
+#pragma unroll
+					for (int s = 0; s < S; ++s) acc[s] = sdf::BlendUnion(lhs[s], acc[s], param);
+				}
+				else if (Opaque(oper) == (kOpBlendInter << kHdrOpShift))
+				{
+#pragma unroll
+					for (int s = 0; s < S; ++s) acc[s] = sdf::BlendInter(lhs[s], acc[s], param);
+				}
+				else
+				{
+#pragma unroll
+					for (int s = 0; s < S; ++s) acc[s] = sdf::BlendDiff(lhs[s], acc[s], param);
+				}
 			}
 		}
 		if (DEEP)
@@ -398,72 +451,62 @@ __device__ __forceinline__ void RunProgram(const uint32_t* __restrict__ program,
 			}
 
 			float d[S];
-			switch (brush)
-			{
-			case kBrushSphere:
-			{
-				const float r = __ldg(arg);
-				arg += 1;
-#pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Sphere(lx[s], ly[s], lz[s], r);
-				break;
-			}
-			case kBrushEllipsoid:
-			{
-				const float a = __ldg(arg), b = __ldg(arg + 1), c = __ldg(arg + 2);
-				arg += 3;
-#pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Ellipsoid(lx[s], ly[s], lz[s], a, b, c);
-				break;
-			}
-			case kBrushBox:
+			uint32_t kind = brush; // comparison chains instead of jump tables, as in EvalInterp
+			if (kind == kBrushBox)
 			{
 				const float a = __ldg(arg), b = __ldg(arg + 1), c = __ldg(arg + 2);
 				arg += 3;
 #pragma unroll
 				for (int s = 0; s < S; ++s) d[s] = sdf::Box(lx[s], ly[s], lz[s], a, b, c);
-				break;
 			}
-			case kBrushTorus:
+			else if (Opaque(kind) == kBrushSphere)
 			{
-				const float a = __ldg(arg), b = __ldg(arg + 1);
-				arg += 2;
+				const float r = __ldg(arg);
+				arg += 1;
 #pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Torus(lx[s], ly[s], lz[s], a, b);
-				break;
+				for (int s = 0; s < S; ++s) d[s] = sdf::Sphere(lx[s], ly[s], lz[s], r);
 			}
-			case kBrushCylinder:
+			else if (Opaque(kind) == kBrushCylinder)
 			{
 				const float a = __ldg(arg), b = __ldg(arg + 1);
 				arg += 2;
 #pragma unroll
 				for (int s = 0; s < S; ++s) d[s] = sdf::Cylinder(lx[s], ly[s], lz[s], a, b);
-				break;
 			}
-			case kBrushCone:
+			else if (Opaque(kind) == kBrushTorus)
 			{
 				const float a = __ldg(arg), b = __ldg(arg + 1);
 				arg += 2;
 #pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Cone(lx[s], ly[s], lz[s], a, b);
-				break;
+				for (int s = 0; s < S; ++s) d[s] = sdf::Torus(lx[s], ly[s], lz[s], a, b);
 			}
-			case kBrushConinder:
-			{
-				const float a = __ldg(arg), b = __ldg(arg + 1), c = __ldg(arg + 2);
-				arg += 3;
-#pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Coninder(lx[s], ly[s], lz[s], a, b, c);
-				break;
-			}
-			default:
+			else if (Opaque(kind) == kBrushPlane)
 			{
 				const float a = __ldg(arg), b = __ldg(arg + 1), c = __ldg(arg + 2);
 				arg += 3;
 #pragma unroll
 				for (int s = 0; s < S; ++s) d[s] = sdf::Plane(lx[s], ly[s], lz[s], a, b, c);
-				break;
 			}
+			else if (Opaque(kind) == kBrushEllipsoid)
+			{
+				const float a = __ldg(arg), b = __ldg(arg + 1), c = __ldg(arg + 2);
+				arg += 3;
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Ellipsoid(lx[s], ly[s], lz[s], a, b, c);
+			}
+			else if (Opaque(kind) == kBrushCone)
+			{
+				const float a = __ldg(arg), b = __ldg(arg + 1);
+				arg += 2;
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Cone(lx[s], ly[s], lz[s], a, b);
+			}
+			else
+			{
+				const float a = __ldg(arg), b = __ldg(arg + 1), c = __ldg(arg + 2);
+				arg += 3;
+#pragma unroll
+				for (int s = 0; s < S; ++s) d[s] = sdf::Coninder(lx[s], ly[s], lz[s], a, b, c);
 			}
 			if (header & kHdrScaleBit)
 			{
@@ -501,32 +544,36 @@ __device__ __forceinline__ void RunProgram(const uint32_t* __restrict__ program,
 			{
 				const float threshold = (op >= kOpBlendUnion) ? __ldg(arg) : 0.0f;
 				float dist[S];
-				switch (op) // one dispatch per instruction, not per sample
+				uint32_t oper = op; // one dispatch per instruction, not per sample
+				if (oper == kOpUnion)
 				{
-				case kOpUnion:
 #pragma unroll
 					for (int s = 0; s < S; ++s) dist[s] = sdf::Union(acc[s], d[s]);
-					break;
-				case kOpInter:
-#pragma unroll
-					for (int s = 0; s < S; ++s) dist[s] = sdf::Inter(acc[s], d[s]);
-					break;
-				case kOpDiff:
-#pragma unroll
-					for (int s = 0; s < S; ++s) dist[s] = sdf::Diff(acc[s], d[s]);
-					break;
-				case kOpBlendUnion:
+				}
+				else if (Opaque(oper) == kOpBlendUnion)
+				{
 #pragma unroll
 					for (int s = 0; s < S; ++s) dist[s] = sdf::BlendUnion(acc[s], d[s], threshold);
-					break;
-				case kOpBlendInter:
+				}
+				else if (Opaque(oper) == kOpDiff)
+				{
 #pragma unroll
-					for (int s = 0; s < S; ++s) dist[s] = sdf::BlendInter(acc[s], d[s], threshold);
-					break;
-				default:
+					for (int s = 0; s < S; ++s) dist[s] = sdf::Diff(acc[s], d[s]);
+				}
+				else if (Opaque(oper) == kOpInter)
+				{
+#pragma unroll
+					for (int s = 0; s < S; ++s) dist[s] = sdf::Inter(acc[s], d[s]);
+				}
+				else if (Opaque(oper) == kOpBlendDiff)
+				{
 #pragma unroll
 					for (int s = 0; s < S; ++s) dist[s] = sdf::BlendDiff(acc[s], d[s], threshold);
-					break;
+				}
+				else
+				{
+#pragma unroll
+					for (int s = 0; s < S; ++s) dist[s] = sdf::BlendInter(acc[s], d[s], threshold);
 				}
 #pragma unroll
 				for (int s = 0; s < S; ++s)

@@ -382,7 +382,7 @@ __device__ __forceinline__ unsigned CellCorners(const WarpTile& w, int c, float 
 	return signs;
 }
 
-__global__ void __launch_bounds__(kBrickThreads) MeshBricksKernel(const MeshParams p)
+__global__ void __launch_bounds__(kBrickThreads, 8) MeshBricksKernel(const MeshParams p)
 {
 	__shared__ WarpTile tiles[kBrickWarps];
 	WarpTile& w = tiles[threadIdx.x >> 5];
