@@ -434,9 +434,19 @@ __device__ __forceinline__ void RunProgram(const uint32_t* __restrict__ program,
 					const float vx = px[s] - tx, vy = py[s] - ty, vz = pz[s] - tz;
 					const float uvx = qy * vz - vy * qz, uvy = qz * vx - vz * qx, uvz = qx * vy - vx * qy;
 					const float uuvx = qy * uvz - uvy * qz, uuvy = qz * uvx - uvz * qx, uuvz = qx * uvy - uvx * qy;
-					lx[s] = (vx + ((uvx * qw) + uuvx) * 2.0f) / sc;
-					ly[s] = (vy + ((uvy * qw) + uuvy) * 2.0f) / sc;
-					lz[s] = (vz + ((uvz * qw) + uuvz) * 2.0f) / sc;
+					lx[s] = vx + ((uvx * qw) + uuvx) * 2.0f;
+					ly[s] = vy + ((uvy * qw) + uuvy) * 2.0f;
+					lz[s] = vz + ((uvz * qw) + uuvz) * 2.0f;
+				}
+				if (sc != 1.0f) // x / 1.0f is x, bit for bit: unscaled brushes (most) skip three IEEE divisions per sample
+				{
+#pragma unroll
+					for (int s = 0; s < S; ++s)
+					{
+						lx[s] = lx[s] / sc;
+						ly[s] = ly[s] / sc;
+						lz[s] = lz[s] / sc;
+					}
 				}
 			}
 			else
