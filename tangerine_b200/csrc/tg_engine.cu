@@ -110,7 +110,7 @@ struct MeshParams
 struct WarpTile
 {
 	float tile[kTilePadded];          // sample values
-	uint16_t order[kTilePadded];      // sample indices grouped by octree node; later the brick's active cell list
+	uint16_t order[kTilePadded];      // samples (li | lj << 4 | lk << 8) grouped by octree node; later the brick's active cell list
 	uint32_t pend_node[kMaxPending];  // box resolution: (node to descend from, sample box) still to be resolved
 	uint32_t pend_box[kMaxPending];
 	uint32_t fin_node[kMaxFinal];     // resolved (octree node, sample box) pairs of the current evaluation batch
@@ -118,16 +118,6 @@ struct WarpTile
 	uint32_t fin_start[kMaxFinal + 1]; // offset of each pair's samples in `order`
 	uint16_t rows[kTile * kTile + 1];  // sign bits of the tile, one word per row of 9 samples
 };
-
-__device__ __forceinline__ void TileCoords(const DeviceGrid& grid, uint32_t i0, uint32_t j0, uint32_t k0, int s, float& x, float& y, float& z)
-{
-	const int lk = s / (kTile * kTile);
-	const int r = s - lk * (kTile * kTile);
-	const int lj = r / kTile, li = r - lj * kTile;
-	x = LatticeCoord(grid.x, grid.dx, i0 + li);
-	y = LatticeCoord(grid.y, grid.dy, j0 + lj);
-	z = LatticeCoord(grid.z, grid.dz, k0 + lk);
-}
 
 // A sample box of the tile: inclusive index ranges, four bits each.
 __device__ __forceinline__ uint32_t PackBox(int x0, int x1, int y0, int y1, int z0, int z1)
@@ -233,7 +223,7 @@ __device__ __forceinline__ void EvaluateTile(WarpTile& w, const DeviceModel& mod
 					const int c = __float2int_rd((float(u) + 0.5f) * inv_layer);
 					const int r = u - c * layer;
 					const int q = __float2int_rd((float(r) + 0.5f) * inv_dx);
-					w.order[first + u] = uint16_t(((z0 + c) * kTile + (y0 + q)) * kTile + (x0 + r - q * dx));
+					w.order[first + u] = uint16_t((x0 + r - q * dx) | ((y0 + q) << 4) | ((z0 + c) << 8)); // li | lj << 4 | lk << 8
 				}
 			}
 			__syncwarp();
@@ -253,9 +243,12 @@ __device__ __forceinline__ void EvaluateTile(WarpTile& w, const DeviceModel& mod
 					for (int q = 0; q < kLaneSamples; ++q)
 					{
 						const int idx = lane + 32 * q;
-						const int s = w.order[first + done + (idx < count_here ? idx : 0)];
-						sample[q] = idx < count_here ? s : -1;
-						TileCoords(grid, i0, j0, k0, s, px[q], py[q], pz[q]);
+						const uint32_t code = w.order[first + done + (idx < count_here ? idx : 0)];
+						const uint32_t li = code & 15u, lj = (code >> 4) & 15u, lk = code >> 8;
+						sample[q] = idx < count_here ? int((lk * kTile + lj) * kTile + li) : -1;
+						px[q] = LatticeCoord(grid.x, grid.dx, i0 + li);
+						py[q] = LatticeCoord(grid.y, grid.dy, j0 + lj);
+						pz[q] = LatticeCoord(grid.z, grid.dz, k0 + lk);
 					}
 					EvalInterp<kLaneSamples>(program, px, py, pz, d);
 #pragma unroll
@@ -1140,20 +1133,43 @@ __global__ void __launch_bounds__(kScanBlock) PairSumsKernel(LoadVertexQuadCount
 // Pass 2 (one block): exclusive scan of the tile totals in place; grand totals to totals_out[0] (vertices) and [1] (quads).
 __global__ void __launch_bounds__(1024) PairSumsScanKernel(unsigned long long* block_sums, uint32_t count, unsigned long long* totals_out)
 {
+	// 4096 block sums per pass (coalesced through shared memory, four consecutive entries per thread, one block scan)
+	constexpr uint32_t kPer = 4;
+	__shared__ unsigned long long tile[1024 * kPer];
 	__shared__ unsigned long long warp_sums[32];
-	__shared__ unsigned long long carry;
-	if (threadIdx.x == 0) carry = 0;
-	__syncthreads();
-	for (uint32_t base = 0; base < count; base += blockDim.x)
+	unsigned long long carry = 0;
+	for (uint32_t base = 0; base < count; base += 1024 * kPer)
 	{
-		const uint32_t i = base + threadIdx.x;
-		const unsigned long long v = i < count ? block_sums[i] : 0ull;
-		unsigned long long total;
-		const unsigned long long ex = BlockExclusiveScan64(v, warp_sums, total);
-		const unsigned long long c = carry;
-		if (i < count) block_sums[i] = c + ex;
+#pragma unroll
+		for (uint32_t i = 0; i < kPer; ++i)
+		{
+			const uint32_t at = base + i * 1024 + threadIdx.x;
+			tile[i * 1024 + threadIdx.x] = at < count ? block_sums[at] : 0ull;
+		}
 		__syncthreads();
-		if (threadIdx.x == 0) carry = c + total;
+		unsigned long long v[kPer], sum = 0;
+#pragma unroll
+		for (uint32_t i = 0; i < kPer; ++i)
+		{
+			v[i] = tile[threadIdx.x * kPer + i];
+			sum += v[i];
+		}
+		unsigned long long total;
+		unsigned long long running = carry + BlockExclusiveScan64(sum, warp_sums, total);
+#pragma unroll
+		for (uint32_t i = 0; i < kPer; ++i)
+		{
+			tile[threadIdx.x * kPer + i] = running;
+			running += v[i];
+		}
+		__syncthreads();
+#pragma unroll
+		for (uint32_t i = 0; i < kPer; ++i)
+		{
+			const uint32_t at = base + i * 1024 + threadIdx.x;
+			if (at < count) block_sums[at] = tile[i * 1024 + threadIdx.x];
+		}
+		carry += total;
 		__syncthreads();
 	}
 	if (threadIdx.x == 0)
@@ -1343,23 +1359,47 @@ __global__ void __launch_bounds__(256) VertexNodeKernel(const DeviceModel model,
 	}
 }
 
-// One block: exclusive scan of the per-node histogram (a few tens of thousands of entries).
+// One block: exclusive scan of the per-node histogram (a few tens of thousands of entries), 8192 entries per pass:
+// coalesced into shared memory, eight consecutive entries per thread, one block scan, coalesced out.  (A fixed cost of
+// every slab: 27 us when each pass covered 1024 entries.)
 __global__ void __launch_bounds__(1024) NodeOffsetsKernel(const uint32_t* __restrict__ histogram, uint32_t node_count, uint32_t* __restrict__ node_offset)
 {
+	constexpr uint32_t kPer = 8;
+	__shared__ uint32_t tile[1024 * kPer];
 	__shared__ uint32_t warp_sums[32];
-	__shared__ uint32_t carry;
-	if (threadIdx.x == 0) carry = 0;
-	__syncthreads();
-	for (uint32_t base = 0; base < node_count; base += blockDim.x)
+	uint32_t carry = 0;
+	for (uint32_t base = 0; base < node_count; base += 1024 * kPer)
 	{
-		const uint32_t i = base + threadIdx.x;
-		const uint32_t v = i < node_count ? histogram[i] : 0u;
-		uint32_t total;
-		const uint32_t ex = BlockExclusiveScan(v, warp_sums, total);
-		const uint32_t c = carry;
-		if (i < node_count) node_offset[i] = c + ex;
+#pragma unroll
+		for (uint32_t i = 0; i < kPer; ++i)
+		{
+			const uint32_t at = base + i * 1024 + threadIdx.x;
+			tile[i * 1024 + threadIdx.x] = at < node_count ? histogram[at] : 0u;
+		}
 		__syncthreads();
-		if (threadIdx.x == 0) carry = c + total;
+		uint32_t v[kPer], sum = 0;
+#pragma unroll
+		for (uint32_t i = 0; i < kPer; ++i)
+		{
+			v[i] = tile[threadIdx.x * kPer + i];
+			sum += v[i];
+		}
+		uint32_t total;
+		uint32_t running = carry + BlockExclusiveScan(sum, warp_sums, total);
+#pragma unroll
+		for (uint32_t i = 0; i < kPer; ++i)
+		{
+			tile[threadIdx.x * kPer + i] = running;
+			running += v[i];
+		}
+		__syncthreads();
+#pragma unroll
+		for (uint32_t i = 0; i < kPer; ++i)
+		{
+			const uint32_t at = base + i * 1024 + threadIdx.x;
+			if (at < node_count) node_offset[at] = tile[i * 1024 + threadIdx.x];
+		}
+		carry += total;
 		__syncthreads();
 	}
 }
@@ -3237,9 +3277,10 @@ static int PipelineChunks(const tg_grid& g, const tg_mesh_options& options)
 	// worth it once the result is tens of megabytes: below that the copies are short next to the launch overheads
 	const double cells = double(g.sx) * double(g.sy) * double(g.sz);
 	if (cells < double(1 << 24) || g.sz < 128) return 1;
-	// measured on seaside_town 1024^3 (profiles/): 1 slab 10.3 ms end to end, 2: 9.3, 4: 8.6, 8: 9.2 -- every slab adds
-	// the tail of a persistent kernel and a dozen small launches, so few slabs win
-	return 4;
+	// measured on seaside_town 1024^3 (profiles/r1j_e2e_pipeline_probe.txt), export call only: 2 slabs 7.7 ms, 3: 7.1,
+	// 4: 7.2, 5: 7.1, 6: 7.4, 8: 7.7 (one slab, no overlap: about 10) -- every slab adds the tail of three persistent kernels and a dozen small
+	// launches (about 0.35 ms), so few slabs win
+	return 3;
 }
 
 int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options& options, tg_mesh* out, std::string& error)
