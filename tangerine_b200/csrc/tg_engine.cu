@@ -1443,7 +1443,7 @@ __device__ __forceinline__ void VertexAttributes(const AttributeParams& p, uint3
 
 // Persistent warps over the device-side vertex count: a warp takes the next 32 entries of the node-sorted order from
 // a device-wide cursor (so it runs one tree program, and long and short programs balance themselves over the SMs).
-__global__ void __launch_bounds__(128) AttributesKernel(const AttributeParams p)
+__global__ void __launch_bounds__(128, 8) AttributesKernel(const AttributeParams p)
 {
 	const uint32_t count = BoundedCount(p.count_ptr, p.capacity);
 	const int lane = threadIdx.x & 31;

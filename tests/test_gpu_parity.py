@@ -137,6 +137,21 @@ def test_lattice_samples_bit_exact(name, models, oracles):
     assert np.array_equal(got >= 0, want >= 0)
 
 
+@pytest.mark.parametrize("name,step", [("seaside_town", 0.5), ("seaside_town", 1.0), ("color-cube", 0.7), ("gear", 0.4)])
+def test_lattice_on_grids_coarser_than_the_octree(name, step, models, oracles):
+    """Octree leaves (0.25 and smaller) far smaller than a brick: one 9^3 tile then straddles hundreds of octree regions,
+    so the brick kernel's box resolution runs many rounds, works its pending list depth-first and evaluates in
+    several batches."""
+    tree, model = models(name)
+    om, oc = oracles(name)
+    lo, hi = tree.bounds()
+    grid = T.export_grid(lo, hi, np.float32(step))
+    got, ms = model.eval_lattice(grid)
+    want = oc.lattice(O.export_grid(lo, hi, np.float32(step)))
+    assert got.shape == want.shape
+    assert same_floats(got, want)
+
+
 @pytest.mark.parametrize("name", ["seaside_town", "gear", "color-cube"])
 def test_far_field_point_queries(name, models, oracles):
     """Points all over the bounding box and beyond the octree cube: most fall into empty octants of interior octree
