@@ -26,6 +26,7 @@ struct DeviceModel
 	const uint4* interp;       // kStreamInterp, 16-byte quads; FlatNode::interp_offset / 4 indexes it
 	const uint32_t* tree;
 	const FlatRegion* regions;
+	const uint32_t* node_rank; // node -> position by descending program cost (key of the attribute pass's counting sort)
 	uint32_t region_count;
 	const float* material_rgb; // 3 floats per id
 	uint32_t material_count;   // index of the trailing default-white entry

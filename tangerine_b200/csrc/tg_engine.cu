@@ -1269,7 +1269,7 @@ __global__ void __launch_bounds__(256) FinalizeMeshKernel(const FaceParams p)
 			const uint32_t node = Descend(p.model.nodes, 0, pos.x, pos.y, pos.z);
 			p.vertex_node[id] = node;
 			const unsigned peers = __match_any_sync(__activemask(), node);
-			if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&p.node_histogram[node], uint32_t(__popc(peers)));
+			if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&p.node_histogram[__ldg(&p.model.node_rank[node])], uint32_t(__popc(peers)));
 		}
 		const QuadWords q = QuadMasks(p.bitmap, word_index, word, p.row_words, p.sy);
 		const uint32_t quads = uint32_t((q.z >> bit) & 1ull) | (uint32_t((q.y >> bit) & 1ull) << 1) | (uint32_t((q.x >> bit) & 1ull) << 2);
@@ -1355,7 +1355,7 @@ __global__ void __launch_bounds__(256) VertexNodeKernel(const DeviceModel model,
 		const uint32_t node = Descend(model.nodes, 0, positions[size_t(v) * 3 + 0], positions[size_t(v) * 3 + 1], positions[size_t(v) * 3 + 2]);
 		vertex_node[v] = node;
 		const unsigned peers = __match_any_sync(__activemask(), node);
-		if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&histogram[node], uint32_t(__popc(peers)));
+		if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&histogram[__ldg(&model.node_rank[node])], uint32_t(__popc(peers)));
 	}
 }
 
@@ -1404,14 +1404,14 @@ __global__ void __launch_bounds__(1024) NodeOffsetsKernel(const uint32_t* __rest
 	}
 }
 
-__global__ void __launch_bounds__(256) VertexPermutationKernel(const uint32_t* __restrict__ vertex_node, const unsigned long long* __restrict__ count_ptr, uint32_t capacity,
-	const uint32_t* __restrict__ node_offset, uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm)
+__global__ void __launch_bounds__(256) VertexPermutationKernel(const uint32_t* __restrict__ vertex_node, const uint32_t* __restrict__ node_rank,
+	const unsigned long long* __restrict__ count_ptr, uint32_t capacity, const uint32_t* __restrict__ node_offset, uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm)
 {
 	const uint32_t count = BoundedCount(count_ptr, capacity);
 	const uint32_t stride = gridDim.x * blockDim.x;
 	for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < count; v += stride)
 	{
-		const uint32_t node = vertex_node[v];
+		const uint32_t node = __ldg(&node_rank[vertex_node[v]]); // the sort key: costliest programs first
 		const unsigned peers = __match_any_sync(__activemask(), node);
 		const int leader = __ffs(peers) - 1;
 		uint32_t base = 0;
@@ -2006,7 +2006,7 @@ static int UploadVector(Context* c, const std::vector<T>& v, void** device, void
 
 static void FreeModelTables(Model* m)
 {
-	void** tables[] = { &m->d_nodes, &m->d_interp, &m->d_tree, &m->d_materials, &m->d_regions };
+	void** tables[] = { &m->d_nodes, &m->d_interp, &m->d_tree, &m->d_materials, &m->d_regions, &m->d_node_rank };
 	for (void** t : tables)
 	{
 		cudaFree(*t);
@@ -2031,6 +2031,7 @@ static int UploadModel(Model* m, std::string& error)
 	if ((rc = UploadVector(c, m->flat.tree, &m->d_tree, &m->staging[2], m->device_bytes, error)) != TG_OK) return rc;
 	if ((rc = UploadVector(c, m->flat.material_rgb, &m->d_materials, &m->staging[3], m->device_bytes, error)) != TG_OK) return rc;
 	if ((rc = UploadVector(c, m->flat.regions, &m->d_regions, &m->staging[4], m->device_bytes, error)) != TG_OK) return rc;
+	if ((rc = UploadVector(c, m->flat.node_rank, &m->d_node_rank, &m->staging[5], m->device_bytes, error)) != TG_OK) return rc;
 	TG_CUDA(cudaStreamSynchronize(StreamOf(c)));
 	return TG_OK;
 }
@@ -2084,6 +2085,7 @@ static DeviceModel MakeDeviceModel(const Model* m)
 	d.tree = static_cast<const uint32_t*>(m->d_tree);
 	d.material_rgb = static_cast<const float*>(m->d_materials);
 	d.regions = static_cast<const FlatRegion*>(m->d_regions);
+	d.node_rank = static_cast<const uint32_t*>(m->d_node_rank);
 	d.region_count = uint32_t(m->flat.regions.size());
 	d.material_count = uint32_t(m->flat.material_rgb.size() / 3 - 1);
 	d.root_interp_offset = m->flat.root_interp_offset;
@@ -2323,7 +2325,7 @@ static int EnqueueAttributes(Model* model, Scratch& scratch, MeshResultDevice* r
 		launches++;
 	}
 	NodeOffsetsKernel<<<1, 1024, 0, stream>>>(as.histogram, node_count, node_offset);
-	VertexPermutationKernel<<<wide_perm, 256, 0, stream>>>(as.vertex_node, count_ptr, capacity, node_offset, as.histogram + node_count, perm);
+	VertexPermutationKernel<<<wide_perm, 256, 0, stream>>>(as.vertex_node, ap.model.node_rank, count_ptr, capacity, node_offset, as.histogram + node_count, perm);
 	launches += 2;
 	ap.perm = perm;
 	ap.vertex_node = as.vertex_node;

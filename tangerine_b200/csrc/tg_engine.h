@@ -77,7 +77,8 @@ public:
 	void* d_tree = nullptr;
 	void* d_materials = nullptr;
 	void* d_regions = nullptr;
-	void* staging[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; // page-locked host copies of the five tables
+	void* d_node_rank = nullptr;
+	void* staging[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // page-locked host copies of the six tables
 	uint64_t device_bytes = 0;
 	double upload_seconds = 0.0;
 	int leaf_count = 0;

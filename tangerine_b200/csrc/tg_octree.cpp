@@ -2,6 +2,7 @@
 #include "tg_octree.h"
 
 #include <chrono>
+#include <algorithm>
 #include <cmath>
 #include <future>
 #include <memory>
@@ -574,6 +575,15 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 		return false;
 	}
 	out.has_paint = top.pool.nodes[top.nodes[top.root].evaluator].has_paint;
+	{
+		// The attribute pass works through the vertices grouped by octree node; with the costly programs first its
+		// persistent warps finish on short batches (the tail of a slab's attribute kernels is a fixed cost per slab).
+		std::vector<uint32_t> by_cost(out.nodes.size());
+		for (size_t i = 0; i < by_cost.size(); ++i) by_cost[i] = uint32_t(i);
+		std::stable_sort(by_cost.begin(), by_cost.end(), [&](uint32_t a, uint32_t b) { return out.nodes[a].flops > out.nodes[b].flops; });
+		out.node_rank.resize(by_cost.size());
+		for (size_t r = 0; r < by_cost.size(); ++r) out.node_rank[by_cost[r]] = uint32_t(r);
+	}
 
 	// Unpruned model programs (VoxExport and whole-tree point queries).
 	{

@@ -38,6 +38,7 @@ struct FlatModel
 	std::vector<uint32_t> interp;     // kStreamInterp programs, addressed by FlatNode::interp_offset
 	std::vector<uint32_t> tree;       // kStreamTree programs, addressed by FlatNode::tree_offset
 	std::vector<FlatRegion> regions;  // evaluation regions (tg_program.h), pre-order
+	std::vector<uint32_t> node_rank;  // position of every node when the nodes are sorted by program cost, costliest first
 	std::vector<float> material_rgb;  // 3 floats per material id; one extra trailing entry = default white
 	uint32_t root_tree_offset = 0;    // kStreamTree program of the *unpruned* model (VoxExport samples it, magica.cpp:61)
 	uint32_t root_interp_offset = 0;  // kStreamInterp program of the unpruned model
