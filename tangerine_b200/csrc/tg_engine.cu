@@ -578,7 +578,12 @@ struct CullParams
 	RegionRange* ranges;
 	CullItem* lists[kCullLevels];
 	uint32_t capacity[kCullLevels];
-	uint32_t* counts;                  // kCullLevels item counters
+	uint32_t* counts;                  // kCullLevels item counters, then kCullLevels counters of the long-program items
+	// Items whose region runs a long program (kNodeLong) are kept in a list of their own and handed to the first threads
+	// of a level: one of them keeps its thread busy for ~100 us, which hides behind the level's other items only if it
+	// starts with them instead of after them.
+	CullItem* long_lists[kCullLevels];
+	uint32_t long_capacity[kCullLevels];
 	uint32_t* flags[kCullLevels];
 	uint32_t dims[kCullLevels][3];     // bricks per axis at each level
 	int level;
@@ -688,8 +693,10 @@ __global__ void __launch_bounds__(128) CullRegionInitKernel(const CullParams p)
 					atomicOr(&p.flags[level][(size_t(z) * p.dims[level][1] + y) * p.dims[level][0] + x], kFlagPositive);
 		return;
 	}
-	const uint32_t base = atomicAdd(&p.counts[level], n);
-	if (base + n > p.capacity[level])
+	const bool is_long = (__ldg(&p.model.nodes[region.node].flags) & kNodeLong) != 0u;
+	CullItem* list = is_long ? p.long_lists[level] : p.lists[level];
+	const uint32_t base = atomicAdd(&p.counts[is_long ? kCullLevels + level : level], n);
+	if (base + n > (is_long ? p.long_capacity[level] : p.capacity[level]))
 	{
 		// cannot queue: ask for every brick under these cells to be evaluated
 		for (uint32_t z = z0; z <= z1; ++z)
@@ -704,7 +711,7 @@ __global__ void __launch_bounds__(128) CullRegionInitKernel(const CullParams p)
 			for (uint32_t x = x0; x <= x1; ++x)
 			{
 				CullItem item = { r, x | (y << 10) | (z << 20) };
-				p.lists[level][o++] = item;
+				list[o++] = item;
 			}
 }
 
@@ -712,8 +719,9 @@ __global__ void __launch_bounds__(128) CullLevelKernel(const CullParams p)
 {
 	const uint32_t index = blockIdx.x * blockDim.x + threadIdx.x;
 	const int level = p.level;
-	const uint32_t count = min(p.counts[level], p.capacity[level]);
-	if (blockIdx.x * blockDim.x >= count) return; // whole block beyond the list (warps stay intact below)
+	const uint32_t long_count = min(p.counts[kCullLevels + level], p.long_capacity[level]);
+	const uint32_t count = long_count + min(p.counts[level], p.capacity[level]);
+	if (blockIdx.x * blockDim.x >= count) return; // whole block beyond the lists (warps stay intact below)
 	const DeviceGrid& g = p.grid;
 	const uint32_t width = uint32_t(kBrick) << level;
 	bool live = index < count;
@@ -721,7 +729,7 @@ __global__ void __launch_bounds__(128) CullLevelKernel(const CullParams p)
 	uint32_t cx = 0, cy = 0, cz = 0, lo_i = 0, hi_i = 0, lo_j = 0, hi_j = 0, lo_k = 0, hi_k = 0;
 	if (live)
 	{
-		item = p.lists[level][index];
+		item = index < long_count ? p.long_lists[level][index] : p.lists[level][index - long_count];
 		const RegionRange range = p.ranges[item.region];
 		cx = item.cell & 1023u, cy = (item.cell >> 10) & 1023u, cz = (item.cell >> 20) & 1023u;
 		// sample box of this brick (clipped to grid and slab) intersected with the region's sample box
@@ -789,18 +797,22 @@ __global__ void __launch_bounds__(128) CullLevelKernel(const CullParams p)
 			if (hit) children[n++] = x | (y << 10) | (z << 20);
 		}
 	}
-	bool fits;
-	const uint32_t base = WarpAppend(&p.counts[level - 1], n, fits, p.capacity[level - 1]);
+	// children stay in their parent's class (same region, same program); every lane takes part in both appends
+	const bool to_long = index < long_count;
+	bool fits_short, fits_long;
+	const uint32_t base_short = WarpAppend(&p.counts[level - 1], to_long ? 0u : n, fits_short, p.capacity[level - 1]);
+	const uint32_t base_long = WarpAppend(&p.counts[kCullLevels + level - 1], to_long ? n : 0u, fits_long, p.long_capacity[level - 1]);
 	if (!live) return;
-	if (!fits)
+	if (!(to_long ? fits_long : fits_short))
 	{
 		atomicOr(flag, kFlagEvaluate); // inherited by every brick below this one
 		return;
 	}
+	CullItem* out = to_long ? p.long_lists[level - 1] + base_long : p.lists[level - 1] + base_short;
 	for (uint32_t c = 0; c < n; ++c)
 	{
 		CullItem child = { item.region, children[c] };
-		p.lists[level - 1][base + c] = child;
+		out[c] = child;
 	}
 }
 
@@ -2390,14 +2402,16 @@ static int BuildCullFlags(Model* model, cudaStream_t stream, Scratch& scratch, c
 		cp.flags[level] = no_cull ? nullptr : flags_storage + flag_words;
 		cp.lists[level] = nullptr;
 		cp.capacity[level] = 0;
+		cp.long_lists[level] = nullptr;
+		cp.long_capacity[level] = 0;
 		flag_words += size_t(cp.dims[level][0]) * cp.dims[level][1] * cp.dims[level][2];
 	}
 	if (no_cull) return TG_OK;
 	uint32_t* counts = nullptr;
-	TG_CUDA(scratch.Alloc(&counts, kCullLevels));
+	TG_CUDA(scratch.Alloc(&counts, 2 * kCullLevels));
 	cp.counts = counts;
 	TG_CUDA(cudaMemsetAsync(flags_storage, 0, flag_words * 4, stream));
-	TG_CUDA(cudaMemsetAsync(counts, 0, kCullLevels * 4, stream));
+	TG_CUDA(cudaMemsetAsync(counts, 0, 2 * kCullLevels * 4, stream));
 	TG_CUDA(scratch.Alloc(&cp.ranges, cp.model.region_count));
 	for (int level = 0; level < kCullLevels; ++level)
 	{
@@ -2405,6 +2419,8 @@ static int BuildCullFlags(Model* model, cudaStream_t stream, Scratch& scratch, c
 		const size_t cells = size_t(cp.dims[level][0]) * cp.dims[level][1] * ((bz_end - row_begin + (1u << level) - 1) >> level);
 		cp.capacity[level] = uint32_t(std::min<size_t>(size_t(cp.model.region_count) * 8 + cells * 4 + 65536, 0x7FFFFFFFu));
 		TG_CUDA(scratch.Alloc(&cp.lists[level], cp.capacity[level]));
+		cp.long_capacity[level] = cp.capacity[level] / 4 + 4096; // long programs belong to a minority of the regions
+		TG_CUDA(scratch.Alloc(&cp.long_lists[level], cp.long_capacity[level]));
 	}
 	CullRegionInitKernel<<<(cp.model.region_count + 127) / 128, 128, 0, stream>>>(cp);
 	launches++;
@@ -2413,8 +2429,9 @@ static int BuildCullFlags(Model* model, cudaStream_t stream, Scratch& scratch, c
 	uint64_t bound = 0;
 	for (int level = kCullLevels - 1; level >= 0; --level)
 	{
-		const uint64_t seeded = std::min<uint64_t>(uint64_t(cp.model.region_count) * kSeedSpan * kSeedSpan * kSeedSpan, cp.capacity[level]);
-		bound = std::min<uint64_t>(bound * 8u + seeded, cp.capacity[level]);
+		const uint64_t both = uint64_t(cp.capacity[level]) + cp.long_capacity[level];
+		const uint64_t seeded = std::min<uint64_t>(uint64_t(cp.model.region_count) * kSeedSpan * kSeedSpan * kSeedSpan, both);
+		bound = std::min<uint64_t>(bound * 8u + seeded, both);
 		cp.level = level;
 		CullLevelKernel<<<uint32_t((bound + 127) / 128), 128, 0, stream>>>(cp);
 		launches++;
