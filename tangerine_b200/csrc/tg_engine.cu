@@ -2419,7 +2419,7 @@ static int BuildCullFlags(Model* model, cudaStream_t stream, Scratch& scratch, c
 		const size_t cells = size_t(cp.dims[level][0]) * cp.dims[level][1] * ((bz_end - row_begin + (1u << level) - 1) >> level);
 		cp.capacity[level] = uint32_t(std::min<size_t>(size_t(cp.model.region_count) * 8 + cells * 4 + 65536, 0x7FFFFFFFu));
 		TG_CUDA(scratch.Alloc(&cp.lists[level], cp.capacity[level]));
-		cp.long_capacity[level] = cp.capacity[level] / 4 + 4096; // long programs belong to a minority of the regions
+		cp.long_capacity[level] = cp.capacity[level]; // dense scenes (10k primitives) have long programs in most regions
 		TG_CUDA(scratch.Alloc(&cp.long_lists[level], cp.long_capacity[level]));
 	}
 	CullRegionInitKernel<<<(cp.model.region_count + 127) / 128, 128, 0, stream>>>(cp);
@@ -2542,8 +2542,8 @@ struct MeshJob
 
 static void DefaultCapacities(uint64_t slab_cells, uint32_t& cap_v, uint32_t& cap_q)
 {
-	// surfaces occupy a few percent of the cells at most; quads come to about one per vertex (three at the very most)
-	const uint64_t v = std::min<uint64_t>(slab_cells, std::max<uint64_t>(slab_cells / 16, 1 << 22));
+	// surfaces occupy a few percent of the cells (9 % for the 10k-primitive scene at 512^3); quads come to about one per vertex (three at the very most)
+	const uint64_t v = std::min<uint64_t>(slab_cells, std::max<uint64_t>(slab_cells / 8, 1 << 22));
 	cap_v = uint32_t(std::min<uint64_t>(v, 0xFFFFFFF0ull));
 	cap_q = uint32_t(std::min<uint64_t>(std::min<uint64_t>(v * 3, std::max<uint64_t>(v + v / 2, 1 << 20)), 0x2AAAAAA0ull));
 	if (const char* env = std::getenv("TG_TEST_CAPACITY")) // tests: force the overflow-and-repeat path
@@ -3134,12 +3134,17 @@ static int ExportMeshPipelined(Model* model, const tg_grid& grid_in, const tg_me
 		return rc;
 	};
 
+	bool overflowed = false;
 	auto collect = [&](int c) -> int {
 		MeshJob& job = *jobs[size_t(c)];
 		MeshCounts counts;
 		int rc = WaitCounts(job, counts, error);
 		if (rc != TG_OK) return rc;
-		if (counts.overflow) return TG_RETRY_ONE_SHOT;
+		// A slab that outgrew its capacities spoils the export, but the remaining slabs are still collected (results
+		// dropped): WaitCounts records every slab's exact counts, so the NEXT export of this grid pipelines cleanly
+		// instead of tripping over the next slab.
+		if (counts.overflow) overflowed = true;
+		if (overflowed) return TG_OK;
 		const uint64_t v = counts.vertices, t = counts.quads * 2;
 		if (v_done + v > 0xFFFFFFF0ull || t_done + t > 0xFFFFFFF0ull)
 		{
@@ -3214,6 +3219,7 @@ static int ExportMeshPipelined(Model* model, const tg_grid& grid_in, const tg_me
 		const int rc = collect(chunks - 1);
 		if (rc != TG_OK) return abandon(rc);
 	}
+	if (overflowed) return abandon(TG_RETRY_ONE_SHOT);
 	TG_CUDA(cudaStreamSynchronize(copy_stream));
 	TG_CUDA(cudaStreamSynchronize(lane1));
 	TG_CUDA(cudaStreamSynchronize(stream));
