@@ -1,13 +1,16 @@
 // CUDA engine for the SDF meshing hot path (sm_100a).  See DESIGN.md for the pipeline and data layout.
 //
-//   K0  CullRegionInit/Level/Resolve  Lipschitz culling of empty space driven by the octree's evaluation regions
-//   K1  MeshBricksKernel       per active 8^3 brick: octree descent per lattice sample, node-coherent
-//       (+K2 fused)            re-binning, postfix interpreter (4 samples / lane), 9^3 tile in shared memory,
-//                              sign classification, surface-nets vertex, ballot-compacted writes
-//   --  BitmapCount/Scan/Prefix  device-wide exclusive scan over the active-cell bitmap (vertex numbering)
-//   K3  ScatterVerticesKernel  final (k, j, i)-lexicographic vertex order + per-cell quad mask
-//       EmitTrianglesKernel    quads from the three lower neighbours (reference's active-only rule)
-//   K4  AttributesKernel       fused gradient-descent refinement + normal + colour per vertex
+//   K0  CullRegionInit/Level/Resolve  Lipschitz culling of empty space driven by the octree's evaluation regions;
+//       BrickOrder                     the active brick list, costliest first when the list is short
+//   K1  MeshBricksKernel       per active 8^3 brick, one warp: box resolution (the 9^3 tile is split along the
+//       (+K2 fused)            octree's pivot planes instead of descending sample by sample), one interpreter run per
+//                              octree node (2 samples / lane), tile in shared memory, bit-parallel sign
+//                              classification, surface-nets vertex, scan-compacted writes
+//   --  PairSums/Scan/Prefix   one dual exclusive scan over the active-cell bitmap (vertex and quad numbering)
+//   K3  FinalizeMeshKernel     final (k, j, i)-lexicographic vertex order, quads from the three lower neighbours
+//                              (reference's active-only rule), node histogram for K4
+//   K4  AttributesKernel       gradient-descent refinement + normal per vertex, vertices sorted by program cost
+//       ColorsKernel           material walk -> colour bytes
 //   K5  VoxelKernel / PointCloudKernel   dense centre sampling (MagicaVoxel / point-cloud export)
 //
 // There is no CPU fallback: every entry point fails with TG_ERR_NO_DEVICE / TG_ERR_CUDA when the device or
@@ -57,17 +60,6 @@ constexpr uint32_t kResolvedBit = 0x80000000u;
 #define TG_LANE_SAMPLES 2
 #endif
 constexpr int kLaneSamples = TG_LANE_SAMPLES; // samples interpreted per lane per dispatch
-constexpr uint32_t kHaloFlag = 1u << 30;
-// The brick kernel is instruction-cache bound before it is anything else (ncu: stall_no_instruction): its bookkeeping
-// loops (per-round descent, sort, classification) are kept rolled so that the interpreter stays resident.
-#ifndef TG_UNROLL_BOOKKEEPING
-#define TG_UNROLL_BOOKKEEPING 1
-#endif
-constexpr int kUnrollBookkeeping = TG_UNROLL_BOOKKEEPING;
-#ifndef TG_TOP_LEVEL
-#define TG_TOP_LEVEL 3
-#endif
-constexpr int kTopLevel = TG_TOP_LEVEL;  // cull hierarchy starts at (8 << kTopLevel)-cell bricks
 
 enum Counter
 {
