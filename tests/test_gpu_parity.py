@@ -370,6 +370,23 @@ def test_exported_files_match_the_reference_writers(name, golden, tmp_path):
         assert files[key] == value, key
 
 
+def test_cli_export_matches_the_reference_writers(golden, tmp_path):
+    """python -m tangerine_b200 export: the headless front of tg_export_ply / _stl / _magica_voxel."""
+    from golden_util import ply_file_digests, stl_file_digests, vox_file_digests
+    from tangerine_b200.__main__ import main
+    name = "basic_thing"
+    files = golden[name]["files"]
+    model = O.model_path(name)
+    cpu = str(golden[name]["cells_per_unit"])
+    ply, stl, vox = (str(tmp_path / (name + ext)) for ext in (".ply", ".stl", ".vox"))
+    assert main(["export", model, ply, "--grid", cpu, "--refine", "0"]) == 0
+    assert main(["export", model, stl, "--grid", cpu, "--refine", "0"]) == 0
+    assert main(["export", model, vox, "--grid", str(files["vox_grid_size"]), "--color-index", str(files["vox_color_index"])]) == 0
+    got = dict(ply_file_digests(ply), **stl_file_digests(stl), **vox_file_digests(vox))
+    for key, value in got.items():
+        assert files[key] == value, key
+
+
 @pytest.mark.parametrize("name,cpu", [("kitchen_sink", 70), ("seaside_town", 26), ("color-cube", 27)])
 def test_pipelined_export_equals_one_shot(name, cpu, golden, models, monkeypatch):
     """tg_export_mesh with host results is software-pipelined over z-slabs once the grid is large (device -> host copies

@@ -254,3 +254,18 @@ def test_write_stl_layout(tmp_path):
     assert struct.unpack("<I", data[80:84])[0] == 2
     rec = struct.unpack("<12fH", data[84:134])
     assert rec[:3] == (0.0, 0.0, 1.0) and rec[3:12] == (0, 0, 0, 1, 0, 0, 0, 1, 0) and rec[12] == 0
+
+
+def test_cli_info_and_loud_failure_without_a_device(tmp_path, capsys):
+    """python -m tangerine_b200: `info` is host-only; `export` has no CPU path to fall back to (exit code 2)."""
+    import torch
+    from tangerine_b200.__main__ import main
+    model = O.model_path("basic_thing")
+    assert main(["info", model]) == 0
+    assert "primitives 5" in capsys.readouterr().out
+    assert main(["export", model, str(tmp_path / "x.obj"), "--grid", "8"]) == 2      # the reference has no OBJ writer either
+    if not torch.cuda.is_available():
+        assert main(["export", model, str(tmp_path / "x.ply"), "--grid", "8"]) == 2
+        assert "no CPU fallback" in capsys.readouterr().err
+        assert not (tmp_path / "x.ply").exists()
+
