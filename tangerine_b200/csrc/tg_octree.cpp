@@ -101,6 +101,7 @@ struct Builder
 				jobs[i] = std::async(std::launch::async, [this, &st, evaluator, cb, depth]()
 				{
 					std::unique_ptr<Subtree> child(new Subtree);
+					child->pool.nodes.reserve(st.pool.nodes.size() * 4 + 4096); // pruning appends set nodes: grow without re-copying
 					child->pool = st.pool;
 					child->root = Construct(*child, evaluator, cb, depth + 1);
 					return child;
@@ -180,16 +181,18 @@ struct StreamGen
 	uint32_t flops = 0;
 	bool cullable = true;
 	std::vector<uint32_t> starts; // kStreamInterp: quad offset of every instruction (Stop excluded), relative to the first
+	const Mat4* inverse = nullptr; // CompiledInverseMatrix per brush node (optional), see NodePool::CompileReference
+	uint32_t inverse_count = 0;
 
 	StreamGen(const NodePool& p, std::vector<uint32_t>& o, bool tree) : pool(p), out(o), tree_stream(tree) {}
 
 	void PushF(float f) { out.push_back(FloatBits(f)); }
 
-	void EmitBrush(const Node& n, uint32_t op, float threshold, uint32_t flags)
+	void EmitBrush(const Node& n, uint32_t node_index, uint32_t op, float threshold, uint32_t flags)
 	{
 		if (!tree_stream)
 		{
-			EmitBrushQuads(n, op, threshold, flags);
+			EmitBrushQuads(n, node_index, op, threshold, flags);
 			return;
 		}
 		const size_t start = out.size();
@@ -247,7 +250,7 @@ struct StreamGen
 	}
 
 	// kStreamInterp: 16-byte quads (tg_program.h).  [header p0 p1 p2] [3 quads matrix | 1 quad offset]? [scale threshold 0 0]?
-	void EmitBrushQuads(const Node& n, uint32_t op, float threshold, uint32_t flags)
+	void EmitBrushQuads(const Node& n, uint32_t node_index, uint32_t op, float threshold, uint32_t flags)
 	{
 		const size_t start = out.size();
 		starts.push_back(uint32_t(start / 4));
@@ -264,7 +267,7 @@ struct StreamGen
 		if (!identity || !unit)
 		{
 			xform = kXformMatrix;
-			Mat4 inv = CompiledInverseMatrix(n);
+			Mat4 inv = (inverse && node_index < inverse_count) ? inverse[node_index] : CompiledInverseMatrix(n);
 			for (int c = 0; c < 4; ++c)
 			{
 				for (int r = 0; r < 3; ++r)
@@ -341,7 +344,7 @@ struct StreamGen
 		const Node& n = pool.nodes[index];
 		if (IsBrush(n.kind))
 		{
-			EmitBrush(n, kOpPush, 0.0f, 0);
+			EmitBrush(n, index, kOpPush, 0.0f, 0);
 		}
 		else if (IsSet(n.kind))
 		{
@@ -351,7 +354,7 @@ struct StreamGen
 			const uint32_t op = n.kind - 8;
 			if (IsBrush(r.kind))
 			{
-				EmitBrush(r, op, n.params[0], flags); // fused: accumulator = op(accumulator, brush)
+				EmitBrush(r, n.b, op, n.params[0], flags); // fused: accumulator = op(accumulator, brush)
 			}
 			else
 			{
@@ -401,6 +404,7 @@ struct Flattener
 	FlatModel& model;
 	std::vector<uint32_t> ref_words;
 	std::vector<uint32_t> program; // kStreamInterp program of the node being emitted
+	std::vector<Mat4> inverse;     // CompiledInverseMatrix of every brush of the model, by node index
 	int max_slots = 0;
 
 	// Pre-order walk (same order as the octree hash in oracle/ref_tool.cpp) emitting one FlatNode per octree node.
@@ -419,6 +423,8 @@ struct Flattener
 			fn.tree_offset = uint32_t(model.tree.size());
 			program.clear();
 			StreamGen interp(st.pool, program, false);
+			interp.inverse = inverse.data();
+			interp.inverse_count = uint32_t(inverse.size());
 			interp.Gen(bn.evaluator);
 			interp.Finish();
 			fn.flags = interp.cullable ? kNodeCullable : 0u;
@@ -436,7 +442,7 @@ struct Flattener
 		}
 		// Reference-format words: statistics + hash only.
 		ref_words.clear();
-		st.pool.CompileReference(bn.evaluator, ref_words);
+		st.pool.CompileReference(bn.evaluator, ref_words, inverse.empty() ? nullptr : inverse.data());
 		ref_words.push_back(0); // OpcodeT::Stop (:1381)
 		uint32_t child_mask = 0;
 		for (int i = 0; i < 8; ++i)
@@ -552,7 +558,7 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 	}
 	Builder builder;
 	builder.target_size = target_size;
-	builder.parallel_depth = threads >= 16 ? 2 : threads >= 2 ? 1 : 0;
+	builder.parallel_depth = threads >= 4 ? 2 : threads >= 2 ? 1 : 0; // 64 tasks: the octants are very unequal (most of a scene sits in a few of them)
 
 	Subtree top;
 	top.pool = tree.pool;
@@ -564,7 +570,13 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 	}
 
 	out.stats.hash = 0xCBF29CE484222325ull;
-	Flattener flattener{ out, {}, {}, 0 };
+	Flattener flattener{ out, {}, {}, {}, 0 };
+	flattener.inverse.resize(tree.pool.nodes.size());
+	for (size_t i = 0; i < tree.pool.nodes.size(); ++i)
+	{
+		const Node& n = tree.pool.nodes[i];
+		if (IsBrush(n.kind) && (!n.rotation.IsIdentity() || n.scalation != 1.0f)) flattener.inverse[i] = CompiledInverseMatrix(n);
+	}
 	{
 		const float lo[3] = { -INFINITY, -INFINITY, -INFINITY }, hi[3] = { INFINITY, INFINITY, INFINITY };
 		flattener.Walk(top, top.root, lo, hi);
@@ -578,11 +590,11 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 	{
 		// The attribute pass works through the vertices grouped by octree node; with the costly programs first its
 		// persistent warps finish on short batches (the tail of a slab's attribute kernels is a fixed cost per slab).
-		std::vector<uint32_t> by_cost(out.nodes.size());
-		for (size_t i = 0; i < by_cost.size(); ++i) by_cost[i] = uint32_t(i);
-		std::stable_sort(by_cost.begin(), by_cost.end(), [&](uint32_t a, uint32_t b) { return out.nodes[a].flops > out.nodes[b].flops; });
+		std::vector<uint64_t> by_cost(out.nodes.size()); // (~flops, index): ascending = costliest first, ties in node order
+		for (size_t i = 0; i < by_cost.size(); ++i) by_cost[i] = (uint64_t(~out.nodes[i].flops) << 32) | uint64_t(i);
+		std::sort(by_cost.begin(), by_cost.end());
 		out.node_rank.resize(by_cost.size());
-		for (size_t r = 0; r < by_cost.size(); ++r) out.node_rank[by_cost[r]] = uint32_t(r);
+		for (size_t r = 0; r < by_cost.size(); ++r) out.node_rank[uint32_t(by_cost[r])] = uint32_t(r);
 	}
 
 	// Unpruned model programs (VoxExport and whole-tree point queries).

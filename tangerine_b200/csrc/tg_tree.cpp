@@ -178,16 +178,69 @@ float NodePool::Eval(uint32_t index, Vec3 point) const
 // the reference's Copy() of a surviving brush is the brush's own index here.
 uint32_t NodePool::Clip(uint32_t index, Vec3 point, float radius, float* top_value)
 {
+	// a new epoch invalidates the values kept by the previous clip (another point)
+	if (++memo_epoch == 0)
+	{
+		std::fill(memo_stamp.begin(), memo_stamp.end(), 0u);
+		memo_epoch = 1;
+	}
+	return ClipRec(index, point, radius, top_value);
+}
+
+// NodePool::Eval with the values of this clip's point kept per node: the same arithmetic in the same order, once.
+float NodePool::EvalMemo(uint32_t index, Vec3 point)
+{
+	if (index < memo_stamp.size() && memo_stamp[index] == memo_epoch)
+	{
+		return memo_value[index];
+	}
+	const Node& n = nodes[index];
+	float value;
+	if (IsBrush(n.kind))
+	{
+		Vec3 local = ApplyInv(n, point);
+		value = sdf::Brush(n.kind, n.params, local.x, local.y, local.z) * n.scalation;
+	}
+	else if (IsSet(n.kind))
+	{
+		const uint32_t a = n.a, b = n.b, op = n.kind - 8;
+		const float threshold = n.params[0];
+		float l = EvalMemo(a, point);
+		float r = EvalMemo(b, point);
+		value = sdf::SetOp(op, l, r, threshold);
+	}
+	else if (n.kind == kKindFlate)
+	{
+		const float radius = n.params[0];
+		value = EvalMemo(n.a, point) - radius;
+	}
+	else
+	{
+		value = EvalMemo(n.a, point);
+	}
+	if (index >= memo_stamp.size())
+	{
+		const size_t size = std::max<size_t>(nodes.size(), size_t(index) + 1);
+		memo_stamp.resize(size, 0u);
+		memo_value.resize(size, 0.0f);
+	}
+	memo_stamp[index] = memo_epoch;
+	memo_value[index] = value;
+	return value;
+}
+
+uint32_t NodePool::ClipRec(uint32_t index, Vec3 point, float radius, float* top_value)
+{
 	const uint32_t kind = nodes[index].kind;
 	if (IsBrush(kind))
 	{
-		const float value = Eval(index, point);
+		const float value = EvalMemo(index, point);
 		if (top_value) *top_value = value;
 		return value <= radius ? index : kNoNode;
 	}
 	if (IsSet(kind))
 	{
-		const float value = Eval(index, point);
+		const float value = EvalMemo(index, point);
 		if (top_value) *top_value = value;
 		if (!(value <= radius))
 		{
@@ -200,8 +253,8 @@ uint32_t NodePool::Clip(uint32_t index, Vec3 point, float radius, float* top_val
 		if (IsBlend(kind))
 		{
 			// Inside the blending region both operands must survive a clip widened by the threshold.
-			uint32_t nl = Clip(lhs, point, radius + threshold);
-			uint32_t nr = Clip(rhs, point, radius + threshold);
+			uint32_t nl = ClipRec(lhs, point, radius + threshold, nullptr);
+			uint32_t nr = ClipRec(rhs, point, radius + threshold, nullptr);
 			if (nl != kNoNode && nr != kNoNode)
 			{
 				return AddSet(kind, nl, nr, threshold);
@@ -211,8 +264,8 @@ uint32_t NodePool::Clip(uint32_t index, Vec3 point, float radius, float* top_val
 				return kNoNode;
 			}
 		}
-		uint32_t nl = Clip(lhs, point, radius);
-		uint32_t nr = Clip(rhs, point, radius);
+		uint32_t nl = ClipRec(lhs, point, radius, nullptr);
+		uint32_t nr = ClipRec(rhs, point, radius, nullptr);
 		if (nl != kNoNode && nr != kNoNode)
 		{
 			return AddSet(kind, nl, nr, threshold);
@@ -229,18 +282,18 @@ uint32_t NodePool::Clip(uint32_t index, Vec3 point, float radius, float* top_val
 	}
 	if (kind == kKindFlate)
 	{
-		const float value = Eval(index, point);
+		const float value = EvalMemo(index, point);
 		if (top_value) *top_value = value;
 		if (!(value <= radius))
 		{
 			return kNoNode;
 		}
 		const float flate = nodes[index].params[0];
-		uint32_t child = Clip(nodes[index].a, point, radius + flate);
+		uint32_t child = ClipRec(nodes[index].a, point, radius + flate, nullptr);
 		return child == kNoNode ? kNoNode : AddFlate(child, flate);
 	}
-	if (top_value) *top_value = Eval(index, point);
-	uint32_t child = Clip(nodes[index].a, point, radius);
+	if (top_value) *top_value = EvalMemo(index, point);
+	uint32_t child = ClipRec(nodes[index].a, point, radius, nullptr);
 	return child == kNoNode ? kNoNode : AddStencil(kind, child, nodes[index].b, nodes[index].material);
 }
 
@@ -456,7 +509,7 @@ Mat4 CompiledInverseMatrix(const Node& n)
 
 // Compile(ProgramBuffer&): brush :495-507, set :915-924, flate :1098-1103, stencil :632-635.
 // Produces the reference's own word stream (opcode or float per word); used for hashing / parity only.
-void NodePool::CompileReference(uint32_t index, std::vector<uint32_t>& words) const
+void NodePool::CompileReference(uint32_t index, std::vector<uint32_t>& words, const Mat4* inverse) const
 {
 	const Node& n = nodes[index];
 	if (IsBrush(n.kind))
@@ -466,7 +519,7 @@ void NodePool::CompileReference(uint32_t index, std::vector<uint32_t>& words) co
 		const bool has_translation = !(n.translation == Vec3(0.0f, 0.0f, 0.0f));
 		if (has_rotation || has_scalation)
 		{
-			Mat4 inv = CompiledInverseMatrix(n);
+			Mat4 inv = inverse ? inverse[index] : CompiledInverseMatrix(n);
 			words.push_back(17); // OpcodeT::Matrix
 			for (int c = 0; c < 4; ++c)
 			{
@@ -496,8 +549,8 @@ void NodePool::CompileReference(uint32_t index, std::vector<uint32_t>& words) co
 	}
 	else if (IsSet(n.kind))
 	{
-		CompileReference(n.a, words);
-		CompileReference(n.b, words);
+		CompileReference(n.a, words, inverse);
+		CompileReference(n.b, words, inverse);
 		words.push_back(n.kind);
 		if (IsBlend(n.kind))
 		{
@@ -506,13 +559,13 @@ void NodePool::CompileReference(uint32_t index, std::vector<uint32_t>& words) co
 	}
 	else if (n.kind == kKindFlate)
 	{
-		CompileReference(n.a, words);
+		CompileReference(n.a, words, inverse);
 		words.push_back(kKindFlate);
 		PushFloat(words, n.params[0]);
 	}
 	else
 	{
-		CompileReference(n.a, words);
+		CompileReference(n.a, words, inverse);
 	}
 }
 

@@ -99,10 +99,20 @@ struct NodePool
 	Box3 InnerBounds(uint32_t index) const;                       // InnerBounds()
 	uint32_t Material(uint32_t index, Vec3 point) const;          // GetMaterial -> material id
 	Vec3 Gradient(uint32_t index, Vec3 point) const;              // SDFNode::Gradient
-	void CompileReference(uint32_t index, std::vector<uint32_t>& words) const; // Compile(ProgramBuffer&)
+	// `inverse` (optional): CompiledInverseMatrix of every brush node, indexed like `nodes` (brushes are immutable and
+	// shared by all pruned programs, so the octree flattener inverts each of them once instead of once per occurrence)
+	void CompileReference(uint32_t index, std::vector<uint32_t>& words, const Mat4* inverse = nullptr) const; // Compile(ProgramBuffer&)
 
 private:
 	void Derive(uint32_t index);
+	// One Clip call evaluates the same point at every set node it visits, and the reference's recursion re-evaluates the
+	// whole subtree each time (quadratic in the length of a left-leaning chain: 500k brush evaluations for one clip of
+	// a 1000-primitive tree).  The values are the same numbers whichever call computes them, so a clip keeps them.
+	uint32_t ClipRec(uint32_t index, Vec3 point, float radius, float* top_value);
+	float EvalMemo(uint32_t index, Vec3 point);
+	std::vector<float> memo_value;
+	std::vector<uint32_t> memo_stamp;
+	uint32_t memo_epoch = 0;
 };
 
 class Tree
