@@ -121,6 +121,8 @@ typedef struct tg_context tg_context;
 typedef struct tg_model tg_model;
 
 TG_API tg_context* tg_context_create(int cuda_device);
+/* Destroy the models of a context before the context.  Meshes may outlive it: their arrays are blocks of the context's
+ * pinned cache, so a context with live meshes is torn down by the tg_mesh_free of the last one. */
 TG_API void tg_context_destroy(tg_context* context);
 TG_API int tg_context_device(const tg_context* context);
 
@@ -250,8 +252,9 @@ TG_API int tg_eval_lattice(tg_model* model, const tg_grid* grid, float* out, flo
 /* ------------------------------------------------------------------------------------------------
  * Point-cloud export.  Replaces PointCloudExportThread's two Pool() passes (export.cpp:393-469).
  * ---------------------------------------------------------------------------------------------- */
+/* `scale` multiplies the positions last, after normals and colours were sampled (WritePLY, export.cpp:313, 476); 0 means 1. */
 TG_API int tg_export_points(tg_model* model, const float model_min[3], const float model_max[3], const float step[3],
-	int refine_iterations, uint32_t flags, tg_mesh* out);
+	int refine_iterations, uint32_t flags, float scale, tg_mesh* out);
 
 /* ------------------------------------------------------------------------------------------------
  * Voxel occupancy.  Replaces the Pool() loop of VoxExport (tangerine/magica.cpp:27-69).

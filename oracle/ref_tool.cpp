@@ -23,6 +23,8 @@
 #include <atomic>
 #include <fstream>
 #include <surface_nets.h>
+#include <numeric>
+#include <algorithm>
 
 #include "lua_env.h"
 #include "export.h"
@@ -442,7 +444,8 @@ static int Usage()
 		"  export    <model> <cells_per_unit> <refine> <out.ply|.stl>   reference ExportCommon (as shipped)\n"
 		"  export-grid <model> <minx miny minz maxx maxy maxz> <step> <refine> <pointcloud 0|1> <out.ply|.stl>\n"
 		"  vox       <model> <grid_size> <color_index> <out.vox>\n"
-		"  bench     <model> <minx..maxz> <step> <threads> <slice_stride> reference thunks on std::threads (JSON)\n");
+		"  bench     <model> <minx..maxz> <step> <threads> <slice_stride> reference thunks on std::threads (JSON)\n"
+		"  slices    <model> <minx..maxz> <step> <threads> <k_begin> <k_end|0> <attributes 0|1> <out.json>   per-layer digests of the reference mesh\n");
 	return 1;
 }
 
@@ -689,6 +692,270 @@ static int CmdBench(SDFNodeShared Tree, GridArgs Args, int ThreadCount, int Slic
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// `slices`: the reference's loop 1 + loop 2 + attribute loop over a whole grid (or cell layers [k0, k1)) on
+// std::threads, reported as per-z-slice digests in the serial (k, j, i) order -- the fixture the GPU parity tests
+// compare the BENCHED grid sizes against (tests/golden/make_slices.py).  Vertex ids are renumbered to that order so
+// that triangle indices can be compared as they are.
+// ------------------------------------------------------------------------------------------------
+
+struct Sha256
+{
+	uint32_t H[8] = { 0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u };
+	uint8_t Block[64];
+	size_t Fill = 0;
+	uint64_t Total = 0;
+
+	static uint32_t Rotr(uint32_t X, int N) { return (X >> N) | (X << (32 - N)); }
+
+	void Compress()
+	{
+		static const uint32_t K[64] = {
+			0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+			0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+			0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+			0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2 };
+		uint32_t W[64];
+		for (int t = 0; t < 16; ++t) W[t] = (uint32_t(Block[t * 4]) << 24) | (uint32_t(Block[t * 4 + 1]) << 16) | (uint32_t(Block[t * 4 + 2]) << 8) | uint32_t(Block[t * 4 + 3]);
+		for (int t = 16; t < 64; ++t)
+		{
+			uint32_t S0 = Rotr(W[t - 15], 7) ^ Rotr(W[t - 15], 18) ^ (W[t - 15] >> 3);
+			uint32_t S1 = Rotr(W[t - 2], 17) ^ Rotr(W[t - 2], 19) ^ (W[t - 2] >> 10);
+			W[t] = W[t - 16] + S0 + W[t - 7] + S1;
+		}
+		uint32_t A = H[0], B = H[1], C = H[2], D = H[3], E = H[4], F = H[5], G = H[6], Hh = H[7];
+		for (int t = 0; t < 64; ++t)
+		{
+			uint32_t T1 = Hh + (Rotr(E, 6) ^ Rotr(E, 11) ^ Rotr(E, 25)) + ((E & F) ^ (~E & G)) + K[t] + W[t];
+			uint32_t T2 = (Rotr(A, 2) ^ Rotr(A, 13) ^ Rotr(A, 22)) + ((A & B) ^ (A & C) ^ (B & C));
+			Hh = G; G = F; F = E; E = D + T1; D = C; C = B; B = A; A = T1 + T2;
+		}
+		H[0] += A; H[1] += B; H[2] += C; H[3] += D; H[4] += E; H[5] += F; H[6] += G; H[7] += Hh;
+	}
+
+	void Update(const void* Data, size_t Bytes)
+	{
+		const uint8_t* P = static_cast<const uint8_t*>(Data);
+		Total += Bytes;
+		while (Bytes)
+		{
+			size_t N = std::min(Bytes, size_t(64) - Fill);
+			std::memcpy(Block + Fill, P, N);
+			Fill += N; P += N; Bytes -= N;
+			if (Fill == 64) { Compress(); Fill = 0; }
+		}
+	}
+
+	std::string Hex(int Chars = 64)
+	{
+		uint64_t Bits = Total * 8;
+		uint8_t Pad = 0x80;
+		Update(&Pad, 1);
+		uint8_t Zero = 0;
+		while (Fill != 56) Update(&Zero, 1);
+		uint8_t Len[8];
+		for (int i = 0; i < 8; ++i) Len[i] = uint8_t(Bits >> (56 - 8 * i));
+		Update(Len, 8);
+		char Out[65];
+		for (int i = 0; i < 8; ++i) std::snprintf(Out + i * 8, 9, "%08x", H[i]);
+		return std::string(Out).substr(0, size_t(Chars));
+	}
+};
+
+// Bit pattern of a float with the sign of zero and NaN payloads canonicalised (the tests compare "equal up to the sign
+// of zero and NaN payloads", tests/golden_util.py same_floats).
+static uint32_t CanonicalBits(float Value)
+{
+	if (Value != Value) return 0x7FC00000u;
+	if (Value == 0.0f) return 0u;
+	uint32_t Bits;
+	std::memcpy(&Bits, &Value, 4);
+	return Bits;
+}
+
+template <typename Fn>
+static void ParallelFor(size_t Count, int ThreadCount, size_t Chunk, Fn Body)
+{
+	std::atomic<size_t> Next(0);
+	std::vector<std::thread> Threads;
+	for (int t = 0; t < ThreadCount; ++t)
+	{
+		Threads.emplace_back([&]()
+		{
+			while (true)
+			{
+				size_t Begin = Next.fetch_add(Chunk);
+				if (Begin >= Count) break;
+				size_t End = std::min(Begin + Chunk, Count);
+				for (size_t i = Begin; i < End; ++i) Body(i);
+			}
+		});
+	}
+	for (auto& Thread : Threads) Thread.join();
+}
+
+static int CmdSlices(SDFNodeShared Tree, GridArgs Args, int ThreadCount, long K0, long K1, int Attributes, const char* OutPath)
+{
+	auto T0 = Clock::now();
+	SDFOctreeShared Octree = SDFOctree::Create(Tree, 0.25);
+	auto T1 = Clock::now();
+
+	vec3 ModelMin = Args.Min - Args.Step * vec3(2.0);
+	ivec3 Extent = ivec3(ceil((Args.Max - ModelMin) / Args.Step));
+
+	isosurface::AsyncParallelSurfaceNets Task;
+	Task.Grid.x = ModelMin.x;
+	Task.Grid.y = ModelMin.y;
+	Task.Grid.z = ModelMin.z;
+	Task.Grid.dx = Args.Step.x;
+	Task.Grid.dy = Args.Step.y;
+	Task.Grid.dz = Args.Step.z;
+	Task.Grid.sx = Extent.x;
+	Task.Grid.sy = Extent.y;
+	Task.Grid.sz = Extent.z;
+	Task.ImplicitFunction = [&](float X, float Y, float Z) -> float
+	{
+		return Octree->Eval(vec3(X, Y, Z));
+	};
+	Task.Setup();
+	const size_t SX = Task.Grid.sx, SY = Task.Grid.sy, SZ = Task.Grid.sz;
+	if (K1 <= 0 || size_t(K1) > SZ) K1 = long(SZ);
+	if (K0 < 0) K0 = 0;
+	// loop 2 of layer K0 needs the vertices of layer K0 - 1
+	const size_t First = K0 > 0 ? size_t(K0 - 1) : 0;
+	const size_t Layers = size_t(K1) - First;
+
+	// Loop 1: every cell of the layers, work items are (layer, row) pairs.
+	ParallelFor(Layers * SY, ThreadCount, 1, [&](size_t Index)
+	{
+		size_t k = First + Index / SY;
+		size_t j = Index % SY;
+		for (size_t i = 0; i < SX; ++i)
+		{
+			Task.FirstLoopInnerThunk(Task, { i, j, k });
+		}
+	});
+	auto T2 = Clock::now();
+
+	// Serial order: rank of every vertex among the active cells sorted by flat cell index (= k, j, i lexicographic).
+	std::vector<std::pair<size_t, uint64_t>> Cells(Task.SecondLoopDomain.begin(), Task.SecondLoopDomain.end());
+	std::sort(Cells.begin(), Cells.end());
+	const size_t VertexCount = Cells.size();
+	std::vector<uint32_t> Rank(VertexCount);
+	for (size_t r = 0; r < VertexCount; ++r) Rank[size_t(Cells[r].second)] = uint32_t(r);
+
+	// Loop 2 over the cells of layers [K0, K1).
+	std::vector<std::pair<size_t, uint64_t>> Domain;
+	for (auto& Cell : Cells)
+	{
+		if (Cell.first / (SX * SY) >= size_t(K0)) Domain.push_back(Cell);
+	}
+	ParallelFor(Domain.size(), ThreadCount, 256, [&](size_t c)
+	{
+		Task.SecondLoopThunk(Task, Domain[c]);
+	});
+	auto T3 = Clock::now();
+
+	// Quads (two consecutive faces appended under one lock) in owner-cell order; the emission order inside a cell
+	// (edge 0, 1, 2) survives the stable sort.
+	const auto& Faces = Task.OutputMesh.faces_;
+	const size_t QuadCount = Faces.size() / 2;
+	std::vector<uint32_t> QuadOrder(QuadCount);
+	std::iota(QuadOrder.begin(), QuadOrder.end(), 0u);
+	std::stable_sort(QuadOrder.begin(), QuadOrder.end(), [&](uint32_t A, uint32_t B)
+	{
+		return Rank[size_t(Faces[size_t(A) * 2].v0)] < Rank[size_t(Faces[size_t(B) * 2].v0)];
+	});
+
+	// Attribute loop of WritePLY (export.cpp:297-312), threaded; vertices in serial order.
+	const auto& Vertices = Task.OutputMesh.vertices_;
+	const bool ExportColor = Octree->Evaluator->HasPaint();
+	std::vector<vec3> Normals;
+	std::vector<uint8_t> Colors;
+	if (Attributes)
+	{
+		Normals.resize(VertexCount);
+		if (ExportColor) Colors.resize(VertexCount * 3);
+		ParallelFor(VertexCount, ThreadCount, 256, [&](size_t r)
+		{
+			const auto& P = Vertices[size_t(Cells[r].second)];
+			vec3 Point(P.x, P.y, P.z);
+			Normals[r] = Octree->Gradient(Point);
+			if (ExportColor)
+			{
+				vec3 Color = vec3(1.0f);
+				MaterialShared Material = Octree->GetMaterial(Point);
+				if (Material)
+				{
+					Color = SampleColor(Material->GuessColor());
+				}
+				Colors[r * 3 + 0] = 0xFF * Color.r;
+				Colors[r * 3 + 1] = 0xFF * Color.g;
+				Colors[r * 3 + 2] = 0xFF * Color.b;
+			}
+		});
+	}
+	auto T4 = Clock::now();
+
+	FILE* Out = std::fopen(OutPath, "w");
+	if (!Out) return 2;
+	std::fprintf(Out, "{\"grid\": [%zu, %zu, %zu], \"k_begin\": %ld, \"k_end\": %ld, \"threads\": %d, \"has_color\": %s, \"attributes\": %s,\n"
+		" \"octree_build_s\": %.3f, \"loop1_s\": %.3f, \"loop2_s\": %.3f, \"attributes_s\": %.3f,\n",
+		SX, SY, SZ, K0, K1, ThreadCount, ExportColor ? "true" : "false", Attributes ? "true" : "false",
+		Seconds(T0, T1), Seconds(T1, T2), Seconds(T2, T3), Seconds(T3, T4));
+	// per layer: [k, vertices, triangles, sha(positions), sha(normals), sha(colours), sha(triangle indices)]
+	std::fprintf(Out, " \"digest\": \"sha256 (first 16 hex digits) over the layer's records in (k, j, i) order: positions / normals as canonical float32 bits x3 "
+		"(-0 -> +0, NaN -> 7fc00000), colours u8 x3, triangles u32 x3 in the serial vertex numbering (rank among active cells), two per quad, by owner cell then edge\",\n");
+	std::fprintf(Out, " \"layers\": [\n");
+	size_t v = 0, q = 0, OwnedVertices = 0, HelperVertices = 0;
+	bool FirstRow = true;
+	Sha256 All;
+	for (size_t k = First; k < size_t(K1); ++k)
+	{
+		Sha256 HP, HN, HC, HT;
+		size_t nv = 0, nt = 0;
+		for (; v < VertexCount && Cells[v].first / (SX * SY) == k; ++v, ++nv)
+		{
+			const auto& P = Vertices[size_t(Cells[v].second)];
+			uint32_t Bits[3] = { CanonicalBits(P.x), CanonicalBits(P.y), CanonicalBits(P.z) };
+			HP.Update(Bits, 12);
+			if (Attributes)
+			{
+				uint32_t NBits[3] = { CanonicalBits(Normals[v].x), CanonicalBits(Normals[v].y), CanonicalBits(Normals[v].z) };
+				HN.Update(NBits, 12);
+				if (ExportColor) HC.Update(&Colors[v * 3], 3);
+			}
+		}
+		for (; q < QuadCount; ++q)
+		{
+			const auto& F0 = Faces[size_t(QuadOrder[q]) * 2];
+			const auto& F1 = Faces[size_t(QuadOrder[q]) * 2 + 1];
+			size_t Owner = Cells[Rank[size_t(F0.v0)]].first;
+			if (Owner / (SX * SY) != k) break;
+			// ranks are relative to the first layer walked; subtract nothing: with K0 = 0 they are global ids
+			uint32_t Tri[6] = { Rank[size_t(F0.v0)], Rank[size_t(F0.v1)], Rank[size_t(F0.v2)], Rank[size_t(F1.v0)], Rank[size_t(F1.v1)], Rank[size_t(F1.v2)] };
+			HT.Update(Tri, 24);
+			nt += 2;
+		}
+		if (k < size_t(K0))
+		{
+			HelperVertices = nv; // the helper layer below the range: its vertices hold the first ranks
+			continue;
+		}
+		OwnedVertices += nv;
+		if (nv == 0 && nt == 0) continue;
+		std::string SP = HP.Hex(16), SN = HN.Hex(16), SC = HC.Hex(16), ST = HT.Hex(16);
+		std::fprintf(Out, "%s  [%zu, %zu, %zu, \"%s\", \"%s\", \"%s\", \"%s\"]", FirstRow ? "" : ",\n", k, nv, nt, SP.c_str(), SN.c_str(), SC.c_str(), ST.c_str());
+		FirstRow = false;
+	}
+	std::fprintf(Out, "\n ],\n \"first_rank\": %zu, \"vertices\": %zu, \"triangles\": %zu}\n", HelperVertices, OwnedVertices, QuadCount * 2);
+	std::fclose(Out);
+	std::printf("{\"vertices\": %zu, \"triangles\": %zu, \"octree_build_s\": %.3f, \"loop1_s\": %.3f, \"loop2_s\": %.3f, \"attributes_s\": %.3f}\n",
+		OwnedVertices, QuadCount * 2, Seconds(T0, T1), Seconds(T1, T2), Seconds(T2, T3), Seconds(T3, T4));
+	return 0;
+}
+
+
 int main(int Argc, char** Argv)
 {
 	if (Argc < 3)
@@ -759,6 +1026,11 @@ int main(int Argc, char** Argv)
 		VoxExport(Tree, Path, float(std::atof(Argv[3])), std::atoi(Argv[4]));
 		std::printf("{\"vox_s\": %.6f}\n", Seconds(T0, Clock::now()));
 		return 0;
+	}
+	else if (Command == "slices" && Argc == 15)
+	{
+		GridArgs Grid = ParseGrid(Argv + 3);
+		return CmdSlices(Tree, Grid, std::atoi(Argv[10]), std::atol(Argv[11]), std::atol(Argv[12]), std::atoi(Argv[13]), Argv[14]);
 	}
 	else if (Command == "bench" && Argc == 12)
 	{

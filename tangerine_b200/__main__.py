@@ -4,7 +4,9 @@ The reference has no headless export flag (`--headless` only 
 reachable through the dialog and through the legacy C entry points ExportPLY / ExportSTL / ExportMagicaVoxel
 (tangerine/export.cpp:611-622, tangerine/magica.cpp:77-84).  This command is those three entry points on the CUDA
 path (tg_export_ply / tg_export_stl / tg_export_magica_voxel), with the output format taken from the file extension
-the way the dialog does it (tangerine/tangerine.cpp:895-918).  MODEL.tgm is a CSG tree dumped from the reference's Lua
+the way the dialog does it (tangerine/tangerine.cpp:895-918).  One deliberate difference: the reference's mesh export
+ignores RefineIterations (only its point-cloud export refines, export.cpp:433-469) while tg_export_ply / tg_export_stl
+honour it, so --refine defaults to 0 here (= the reference's files, byte for byte) and refinement is opt-in.  MODEL.tgm is a CSG tree dumped from the reference's Lua
 front-end (oracle/ref_tool.cpp dump-tgm).  No CPU fallback: without a B200 the command fails with exit code 2.
 """
 import argparse
@@ -21,7 +23,10 @@ def main(argv=None):
     ex.add_argument("model")
     ex.add_argument("output")
     ex.add_argument("--grid", type=float, required=True, help="cells per model unit (GridSize of ExportPLY / ExportMagicaVoxel)")
-    ex.add_argument("--refine", type=int, default=5, help="refinement iterations (the dialog's default, tangerine.cpp:1024)")
+    ex.add_argument("--refine", type=int, default=0,
+                    help="refinement iterations applied to the MESH vertices (export.cpp:446-461).  Default 0 = byte-compatible with the "
+                         "reference's ExportPLY / ExportSTL, whose MeshExportThread accepts RefineIterations and never uses it "
+                         "(export.cpp:320-381); > 0 is this library's opt-in extension (BASELINE.json north_star)")
     ex.add_argument("--color-index", type=int, default=1, help="MagicaVoxel palette index (magica.cpp:62-66)")
     ex.add_argument("--device", type=int, default=0, help="CUDA device")
     info = sub.add_parser("info", help="bounds, primitive count and octree statistics of a .tgm model (host only)")

@@ -149,7 +149,7 @@ def lib():
         "tg_mesh_free": (None, [C.POINTER(_Mesh)]),
         "tg_mesh_download": (i32, [C.POINTER(_Mesh), u32]),
         "tg_eval_lattice": (i32, [vp, C.POINTER(Grid), fp, fp]),
-        "tg_export_points": (i32, [vp, fp, fp, fp, i32, u32, C.POINTER(_Mesh)]),
+        "tg_export_points": (i32, [vp, fp, fp, fp, i32, u32, C.c_float, C.POINTER(_Mesh)]),
         "tg_export_voxels": (i32, [vp, C.c_float, C.POINTER(C.c_int32), fp, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(u64)]),
         "tg_free": (None, [vp]),
         "tg_progress": (i32, [vp, fp, C.POINTER(i32)]),
@@ -396,8 +396,10 @@ class Context:
 class Mesh:
     """Result of an export; owns the library-side buffers until closed."""
 
-    def __init__(self, raw):
+    def __init__(self, raw, model=None):
         self.raw = raw
+        # the arrays are blocks of the context's pinned cache: keep model and context alive for as long as the mesh is
+        self._model = model
         self.layer_vertices = (np.ctypeslib.as_array(raw.layer_vertices, shape=(int(raw.layer_count),)).copy()
                                if raw.layer_vertices and raw.layer_count else np.zeros(0, np.uint32))
         self.layer_vertex_cost = (np.ctypeslib.as_array(raw.layer_vertex_cost, shape=(int(raw.layer_count),)).copy()
@@ -499,13 +501,13 @@ class Model:
             opt.slab_begin, opt.slab_end = int(slab[0]), int(slab[1])
         raw = _Mesh()
         _check(lib().tg_export_mesh(self.h, C.byref(grid), C.byref(opt), C.byref(raw)))
-        return Mesh(raw)
+        return Mesh(raw, self)
 
-    def export_points(self, lo, hi, step, refine=0, flags=MESH_NORMALS | MESH_COLORS):
+    def export_points(self, lo, hi, step, refine=0, flags=MESH_NORMALS | MESH_COLORS, scale=1.0):
         lo, hi, step = _f3(lo), _f3(hi), _f3(step)
         raw = _Mesh()
-        _check(lib().tg_export_points(self.h, _fp(lo), _fp(hi), _fp(step), refine, flags, C.byref(raw)))
-        return Mesh(raw)
+        _check(lib().tg_export_points(self.h, _fp(lo), _fp(hi), _fp(step), refine, flags, scale, C.byref(raw)))
+        return Mesh(raw, self)
 
     def export_voxels(self, grid_size):
         size = (C.c_int32 * 3)()

@@ -58,6 +58,23 @@ tg_tree* MakeSet(uint32_t kind, const tg_tree* lhs, const tg_tree* rhs, float th
 }
 } // namespace
 
+// No C++ exception may cross the C ABI (a std::bad_alloc from a malformed size, a std::system_error from thread
+// creation ...): every entry point is a function-try-block that turns it into a status code.
+#define TG_CATCH_STATUS                                                                                         \
+	catch (const std::bad_alloc&) { return Fail(TG_ERR_MEMORY, "out of host memory"); }                         \
+	catch (const std::exception& e) { return Fail(TG_ERR_INVALID, std::string("internal error: ") + e.what()); } \
+	catch (...) { return Fail(TG_ERR_INVALID, "internal error: unknown exception"); }
+#define TG_CATCH_NULL                                                                                           \
+	catch (const std::bad_alloc&) { Fail(TG_ERR_MEMORY, "out of host memory"); return nullptr; }                \
+	catch (const std::exception& e) { Fail(TG_ERR_INVALID, std::string("internal error: ") + e.what()); return nullptr; } \
+	catch (...) { Fail(TG_ERR_INVALID, "internal error: unknown exception"); return nullptr; }
+#define TG_CATCH_VALUE(v)                                                                                       \
+	catch (const std::bad_alloc&) { Fail(TG_ERR_MEMORY, "out of host memory"); return v; }                      \
+	catch (const std::exception& e) { Fail(TG_ERR_INVALID, std::string("internal error: ") + e.what()); return v; } \
+	catch (...) { Fail(TG_ERR_INVALID, "internal error: unknown exception"); return v; }
+#define TG_CATCH_VOID catch (...) {}
+
+
 extern "C"
 {
 
@@ -73,23 +90,23 @@ const char* tg_version(void)
 
 // ---- trees ---------------------------------------------------------------------------------------
 
-tg_tree* tg_make_sphere(float radius) { return Wrap(Tree::Sphere(radius)); }
-tg_tree* tg_make_ellipsoid(float x, float y, float z) { return Wrap(Tree::Ellipsoid(x, y, z)); }
-tg_tree* tg_make_box(float x, float y, float z) { return Wrap(Tree::Box(x, y, z)); }
-tg_tree* tg_make_torus(float major_radius, float minor_radius) { return Wrap(Tree::Torus(major_radius, minor_radius)); }
-tg_tree* tg_make_cylinder(float radius, float extent) { return Wrap(Tree::Cylinder(radius, extent)); }
-tg_tree* tg_make_plane(float x, float y, float z) { return Wrap(Tree::Plane(x, y, z)); }
-tg_tree* tg_make_cone(float radius, float height) { return Wrap(Tree::Cone(radius, height)); }
-tg_tree* tg_make_coninder(float radius_l, float radius_h, float height) { return Wrap(Tree::Coninder(radius_l, radius_h, height)); }
+tg_tree* tg_make_sphere(float radius) try { return Wrap(Tree::Sphere(radius)); } TG_CATCH_NULL
+tg_tree* tg_make_ellipsoid(float x, float y, float z) try { return Wrap(Tree::Ellipsoid(x, y, z)); } TG_CATCH_NULL
+tg_tree* tg_make_box(float x, float y, float z) try { return Wrap(Tree::Box(x, y, z)); } TG_CATCH_NULL
+tg_tree* tg_make_torus(float major_radius, float minor_radius) try { return Wrap(Tree::Torus(major_radius, minor_radius)); } TG_CATCH_NULL
+tg_tree* tg_make_cylinder(float radius, float extent) try { return Wrap(Tree::Cylinder(radius, extent)); } TG_CATCH_NULL
+tg_tree* tg_make_plane(float x, float y, float z) try { return Wrap(Tree::Plane(x, y, z)); } TG_CATCH_NULL
+tg_tree* tg_make_cone(float radius, float height) try { return Wrap(Tree::Cone(radius, height)); } TG_CATCH_NULL
+tg_tree* tg_make_coninder(float radius_l, float radius_h, float height) try { return Wrap(Tree::Coninder(radius_l, radius_h, height)); } TG_CATCH_NULL
 
-tg_tree* tg_make_union(const tg_tree* l, const tg_tree* r) { return MakeSet(kKindUnion, l, r, 0.0f); }
-tg_tree* tg_make_diff(const tg_tree* l, const tg_tree* r) { return MakeSet(kKindDiff, l, r, 0.0f); }
-tg_tree* tg_make_inter(const tg_tree* l, const tg_tree* r) { return MakeSet(kKindInter, l, r, 0.0f); }
-tg_tree* tg_make_blend_union(float t, const tg_tree* l, const tg_tree* r) { return MakeSet(kKindBlendUnion, l, r, t); }
-tg_tree* tg_make_blend_diff(float t, const tg_tree* l, const tg_tree* r) { return MakeSet(kKindBlendDiff, l, r, t); }
-tg_tree* tg_make_blend_inter(float t, const tg_tree* l, const tg_tree* r) { return MakeSet(kKindBlendInter, l, r, t); }
+tg_tree* tg_make_union(const tg_tree* l, const tg_tree* r) try { return MakeSet(kKindUnion, l, r, 0.0f); } TG_CATCH_NULL
+tg_tree* tg_make_diff(const tg_tree* l, const tg_tree* r) try { return MakeSet(kKindDiff, l, r, 0.0f); } TG_CATCH_NULL
+tg_tree* tg_make_inter(const tg_tree* l, const tg_tree* r) try { return MakeSet(kKindInter, l, r, 0.0f); } TG_CATCH_NULL
+tg_tree* tg_make_blend_union(float t, const tg_tree* l, const tg_tree* r) try { return MakeSet(kKindBlendUnion, l, r, t); } TG_CATCH_NULL
+tg_tree* tg_make_blend_diff(float t, const tg_tree* l, const tg_tree* r) try { return MakeSet(kKindBlendDiff, l, r, t); } TG_CATCH_NULL
+tg_tree* tg_make_blend_inter(float t, const tg_tree* l, const tg_tree* r) try { return MakeSet(kKindBlendInter, l, r, t); } TG_CATCH_NULL
 
-tg_tree* tg_make_flate(const tg_tree* child, float radius)
+tg_tree* tg_make_flate(const tg_tree* child, float radius) try
 {
 	if (!child || !child->tree.Valid())
 	{
@@ -98,8 +115,9 @@ tg_tree* tg_make_flate(const tg_tree* child, float radius)
 	}
 	return Wrap(Tree::Flate(child->tree, radius));
 }
+TG_CATCH_NULL
 
-tg_tree* tg_make_stencil(const tg_tree* child, const tg_tree* mask, uint32_t material, int apply_to_negative)
+tg_tree* tg_make_stencil(const tg_tree* child, const tg_tree* mask, uint32_t material, int apply_to_negative) try
 {
 	if (!child || !mask || !child->tree.Valid() || !mask->tree.Valid())
 	{
@@ -108,8 +126,9 @@ tg_tree* tg_make_stencil(const tg_tree* child, const tg_tree* mask, uint32_t mat
 	}
 	return Wrap(Tree::Stencil(child->tree, mask->tree, material, apply_to_negative != 0));
 }
+TG_CATCH_NULL
 
-tg_tree* tg_tree_copy(const tg_tree* tree)
+tg_tree* tg_tree_copy(const tg_tree* tree) try
 {
 	if (!tree)
 	{
@@ -120,23 +139,26 @@ tg_tree* tg_tree_copy(const tg_tree* tree)
 	h->tree = tree->tree;
 	return h;
 }
+TG_CATCH_NULL
 
-void tg_tree_free(tg_tree* tree)
+void tg_tree_free(tg_tree* tree) try
 {
 	delete tree;
 }
+TG_CATCH_VOID
 
 #define TG_REQUIRE_TREE(t) \
 	if (!(t) || !(t)->tree.Valid()) return Fail(TG_ERR_INVALID, "null or empty tree")
 
-int tg_tree_move(tg_tree* t, float x, float y, float z)
+int tg_tree_move(tg_tree* t, float x, float y, float z) try
 {
 	TG_REQUIRE_TREE(t);
 	t->tree.Move(Vec3(x, y, z));
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
-int tg_tree_rotate(tg_tree* t, float qx, float qy, float qz, float qw)
+int tg_tree_rotate(tg_tree* t, float qx, float qy, float qz, float qw) try
 {
 	TG_REQUIRE_TREE(t);
 	Quat q;
@@ -147,56 +169,64 @@ int tg_tree_rotate(tg_tree* t, float qx, float qy, float qz, float qw)
 	t->tree.Rotate(q);
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
-int tg_tree_rotate_x(tg_tree* t, float degrees)
+int tg_tree_rotate_x(tg_tree* t, float degrees) try
 {
 	TG_REQUIRE_TREE(t);
 	t->tree.RotateX(degrees);
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
-int tg_tree_rotate_y(tg_tree* t, float degrees)
+int tg_tree_rotate_y(tg_tree* t, float degrees) try
 {
 	TG_REQUIRE_TREE(t);
 	t->tree.RotateY(degrees);
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
-int tg_tree_rotate_z(tg_tree* t, float degrees)
+int tg_tree_rotate_z(tg_tree* t, float degrees) try
 {
 	TG_REQUIRE_TREE(t);
 	t->tree.RotateZ(degrees);
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
-int tg_tree_scale(tg_tree* t, float scale)
+int tg_tree_scale(tg_tree* t, float scale) try
 {
 	TG_REQUIRE_TREE(t);
 	t->tree.Scale(scale);
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
-int tg_tree_align(tg_tree* t, float x, float y, float z)
+int tg_tree_align(tg_tree* t, float x, float y, float z) try
 {
 	TG_REQUIRE_TREE(t);
 	t->tree.Align(Vec3(x, y, z));
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
-int tg_tree_paint(tg_tree* t, uint32_t material, int force)
+int tg_tree_paint(tg_tree* t, uint32_t material, int force) try
 {
 	TG_REQUIRE_TREE(t);
 	if (material >= MaterialCount()) return Fail(TG_ERR_INVALID, "unknown material id");
 	t->tree.Paint(material, force != 0);
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
-uint32_t tg_material_create(float r, float g, float b)
+uint32_t tg_material_create(float r, float g, float b) try
 {
 	return RegisterMaterial(r, g, b);
 }
+TG_CATCH_VALUE(kNoMaterial)
 
-float tg_tree_eval(const tg_tree* t, float x, float y, float z)
+float tg_tree_eval(const tg_tree* t, float x, float y, float z) try
 {
 	if (!t || !t->tree.Valid())
 	{
@@ -205,8 +235,9 @@ float tg_tree_eval(const tg_tree* t, float x, float y, float z)
 	}
 	return t->tree.Eval(Vec3(x, y, z));
 }
+TG_CATCH_VALUE(NAN)
 
-int tg_tree_bounds(const tg_tree* t, float out_min[3], float out_max[3])
+int tg_tree_bounds(const tg_tree* t, float out_min[3], float out_max[3]) try
 {
 	TG_REQUIRE_TREE(t);
 	Box3 b = t->tree.Bounds();
@@ -217,12 +248,13 @@ int tg_tree_bounds(const tg_tree* t, float out_min[3], float out_max[3])
 	}
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
-int tg_tree_has_paint(const tg_tree* t) { return t && t->tree.Valid() && t->tree.HasPaint() ? 1 : 0; }
-int tg_tree_has_finite_bounds(const tg_tree* t) { return t && t->tree.Valid() && t->tree.HasFiniteBounds() ? 1 : 0; }
-int tg_tree_leaf_count(const tg_tree* t) { return t && t->tree.Valid() ? t->tree.LeafCount() : 0; }
+int tg_tree_has_paint(const tg_tree* t) try { return t && t->tree.Valid() && t->tree.HasPaint() ? 1 : 0; } TG_CATCH_VALUE(0)
+int tg_tree_has_finite_bounds(const tg_tree* t) try { return t && t->tree.Valid() && t->tree.HasFiniteBounds() ? 1 : 0; } TG_CATCH_VALUE(0)
+int tg_tree_leaf_count(const tg_tree* t) try { return t && t->tree.Valid() ? t->tree.LeafCount() : 0; } TG_CATCH_VALUE(0)
 
-tg_tree* tg_tree_load(const char* path)
+tg_tree* tg_tree_load(const char* path) try
 {
 	if (!path)
 	{
@@ -238,14 +270,16 @@ tg_tree* tg_tree_load(const char* path)
 	}
 	return Wrap(std::move(t));
 }
+TG_CATCH_NULL
 
-int tg_tree_save(const tg_tree* t, const char* path)
+int tg_tree_save(const tg_tree* t, const char* path) try
 {
 	TG_REQUIRE_TREE(t);
 	std::string error;
 	if (!path || !t->tree.SaveTgm(path, error)) return Fail(TG_ERR_IO, path ? error : "null path");
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
 // Config C4 (BASELINE.json configs[3]): a synthetic random CSG scene.  Uniforms are (rng() >> 8) * 2^-24 from
 // std::mt19937(seed), so the tree is the same on every toolchain.
@@ -260,7 +294,7 @@ int tg_tree_save(const tg_tree* t, const char* path)
 // Blend chains of 8 keep the build polynomial while every sample still runs smooth unions and differences.
 constexpr uint32_t kSyntheticCluster = 8;
 
-tg_tree* tg_make_synthetic(uint32_t primitives, uint32_t seed)
+tg_tree* tg_make_synthetic(uint32_t primitives, uint32_t seed) try
 {
 	if (primitives == 0)
 	{
@@ -328,10 +362,11 @@ tg_tree* tg_make_synthetic(uint32_t primitives, uint32_t seed)
 	model.Fold(kKindInter, Tree::Box(5.0f, 5.0f, 5.0f), 0.0f);
 	return Wrap(std::move(model));
 }
+TG_CATCH_NULL
 
 // ---- contexts and models -------------------------------------------------------------------------
 
-tg_context* tg_context_create(int cuda_device)
+tg_context* tg_context_create(int cuda_device) try
 {
 	std::string error;
 	Context* c = Context::Create(cuda_device, error);
@@ -344,18 +379,28 @@ tg_context* tg_context_create(int cuda_device)
 	h->impl.reset(c);
 	return h;
 }
+TG_CATCH_NULL
 
-void tg_context_destroy(tg_context* context)
+void tg_context_destroy(tg_context* context) try
 {
+	if (!context) return;
+	if (context->impl && context->impl->live_results.load() > 0)
+	{
+		// meshes of this context are still alive: tg_mesh_free of the last one tears the context down
+		context->impl->orphaned.store(true);
+		if (context->impl->live_results.load() > 0) context->impl.release();
+	}
 	delete context;
 }
+TG_CATCH_VOID
 
-int tg_context_device(const tg_context* context)
+int tg_context_device(const tg_context* context) try
 {
 	return context ? context->impl->device : -1;
 }
+TG_CATCH_STATUS
 
-tg_model* tg_model_create(tg_context* context, const tg_tree* tree, float target_size, int host_threads)
+tg_model* tg_model_create(tg_context* context, const tg_tree* tree, float target_size, int host_threads) try
 {
 	if (!context || !tree || !tree->tree.Valid())
 	{
@@ -375,11 +420,13 @@ tg_model* tg_model_create(tg_context* context, const tg_tree* tree, float target
 	h->context = context;
 	return h;
 }
+TG_CATCH_NULL
 
-void tg_model_destroy(tg_model* model)
+void tg_model_destroy(tg_model* model) try
 {
 	delete model;
 }
+TG_CATCH_VOID
 
 static void FillStats(const FlatModel& f, tg_model_stats* out)
 {
@@ -400,7 +447,7 @@ static void FillStats(const FlatModel& f, tg_model_stats* out)
 	out->has_paint = f.has_paint ? 1 : 0;
 }
 
-int tg_tree_octree_stats(const tg_tree* tree, float target_size, int host_threads, tg_model_stats* out)
+int tg_tree_octree_stats(const tg_tree* tree, float target_size, int host_threads, tg_model_stats* out) try
 {
 	TG_REQUIRE_TREE(tree);
 	if (!out) return Fail(TG_ERR_INVALID, "null argument");
@@ -415,8 +462,9 @@ int tg_tree_octree_stats(const tg_tree* tree, float target_size, int host_thread
 	out->leaf_count = tree->tree.LeafCount();
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
-int tg_model_get_stats(const tg_model* model, tg_model_stats* out)
+int tg_model_get_stats(const tg_model* model, tg_model_stats* out) try
 {
 	if (!model || !out) return Fail(TG_ERR_INVALID, "null argument");
 	FillStats(model->impl->flat, out);
@@ -425,18 +473,20 @@ int tg_model_get_stats(const tg_model* model, tg_model_stats* out)
 	out->leaf_count = model->impl->leaf_count;
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
 // ---- queries and exports -------------------------------------------------------------------------
 
-int tg_eval_points(tg_model* model, int mode, const float* points, uint64_t count, void* out)
+int tg_eval_points(tg_model* model, int mode, const float* points, uint64_t count, void* out) try
 {
 	if (!model || (count && (!points || !out))) return Fail(TG_ERR_INVALID, "null argument");
 	std::string error;
 	int rc = EngineEvalPoints(model->impl.get(), mode, points, count, out, error);
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
+TG_CATCH_STATUS
 
-int tg_export_grid(const float mn[3], const float mx[3], const float step[3], tg_grid* out)
+int tg_export_grid(const float mn[3], const float mx[3], const float step[3], tg_grid* out) try
 {
 	if (!mn || !mx || !step || !out) return Fail(TG_ERR_INVALID, "null argument");
 	// export.cpp:324-337
@@ -455,8 +505,9 @@ int tg_export_grid(const float mn[3], const float mx[3], const float step[3], tg
 	out->sx = size[0]; out->sy = size[1]; out->sz = size[2];
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
-int tg_export_mesh(tg_model* model, const tg_grid* grid, const tg_mesh_options* options, tg_mesh* out)
+int tg_export_mesh(tg_model* model, const tg_grid* grid, const tg_mesh_options* options, tg_mesh* out) try
 {
 	if (!model || !grid || !out) return Fail(TG_ERR_INVALID, "null argument");
 	tg_mesh_options defaults;
@@ -474,26 +525,29 @@ int tg_export_mesh(tg_model* model, const tg_grid* grid, const tg_mesh_options* 
 	}
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
-void tg_mesh_free(tg_mesh* mesh)
+void tg_mesh_free(tg_mesh* mesh) try
 {
 	EngineFreeMesh(mesh);
 }
+TG_CATCH_VOID
 
-int tg_eval_lattice(tg_model* model, const tg_grid* grid, float* out, float* out_ms)
+int tg_eval_lattice(tg_model* model, const tg_grid* grid, float* out, float* out_ms) try
 {
 	if (!model || !grid) return Fail(TG_ERR_INVALID, "null argument");
 	std::string error;
 	int rc = EngineEvalLattice(model->impl.get(), *grid, out, out_ms, error);
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
+TG_CATCH_STATUS
 
-int tg_export_points(tg_model* model, const float mn[3], const float mx[3], const float step[3], int refine, uint32_t flags, tg_mesh* out)
+int tg_export_points(tg_model* model, const float mn[3], const float mx[3], const float step[3], int refine, uint32_t flags, float scale, tg_mesh* out) try
 {
 	if (!model || !mn || !mx || !step || !out) return Fail(TG_ERR_INVALID, "null argument");
 	std::string error;
 	model->context->impl->active.store(true);
-	int rc = EngineExportPoints(model->impl.get(), mn, mx, step, refine, flags, out, error);
+	int rc = EngineExportPoints(model->impl.get(), mn, mx, step, refine, flags, scale, out, error);
 	if (rc != TG_OK)
 	{
 		EngineFreeMesh(out);
@@ -502,21 +556,24 @@ int tg_export_points(tg_model* model, const float mn[3], const float mx[3], cons
 	}
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
-int tg_export_voxels(tg_model* model, float grid_size, int32_t out_size[3], float* out_radius, int32_t** out_xyz, uint64_t* out_count)
+int tg_export_voxels(tg_model* model, float grid_size, int32_t out_size[3], float* out_radius, int32_t** out_xyz, uint64_t* out_count) try
 {
 	if (!model || !out_size || !out_radius || !out_xyz || !out_count) return Fail(TG_ERR_INVALID, "null argument");
 	std::string error;
 	int rc = EngineExportVoxels(model->impl.get(), grid_size, out_size, out_radius, out_xyz, out_count, error);
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
+TG_CATCH_STATUS
 
-void tg_free(void* pointer)
+void tg_free(void* pointer) try
 {
 	std::free(pointer);
 }
+TG_CATCH_VOID
 
-int tg_progress(const tg_context* context, float out_ratios[4], int* out_stage)
+int tg_progress(const tg_context* context, float out_ratios[4], int* out_stage) try
 {
 	if (!context) return Fail(TG_ERR_INVALID, "null context");
 	const Context* c = context->impl.get();
@@ -531,8 +588,9 @@ int tg_progress(const tg_context* context, float out_ratios[4], int* out_stage)
 	}
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
-int tg_cancel(tg_context* context, int halt)
+int tg_cancel(tg_context* context, int halt) try
 {
 	if (!context) return Fail(TG_ERR_INVALID, "null context");
 	// CancelExport (export.cpp:582-592): Halt stops the export; otherwise the current stage is skipped.
@@ -541,6 +599,7 @@ int tg_cancel(tg_context* context, int halt)
 	context->impl->active.store(false);
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
 // ---- file-level entry points ---------------------------------------------------------------------
 
@@ -586,17 +645,19 @@ static int ExportFile(const tg_tree* tree, float grid_size, int refine, const ch
 	return rc;
 }
 
-int tg_export_ply(const tg_tree* tree, float grid_size, int refine_iterations, const char* path, int cuda_device)
+int tg_export_ply(const tg_tree* tree, float grid_size, int refine_iterations, const char* path, int cuda_device) try
 {
 	return ExportFile(tree, grid_size, refine_iterations, path, cuda_device, false);
 }
+TG_CATCH_STATUS
 
-int tg_export_stl(const tg_tree* tree, float grid_size, int refine_iterations, const char* path, int cuda_device)
+int tg_export_stl(const tg_tree* tree, float grid_size, int refine_iterations, const char* path, int cuda_device) try
 {
 	return ExportFile(tree, grid_size, refine_iterations, path, cuda_device, true);
 }
+TG_CATCH_STATUS
 
-int tg_export_magica_voxel(const tg_tree* tree, float grid_size, int color_index, const char* path, int cuda_device)
+int tg_export_magica_voxel(const tg_tree* tree, float grid_size, int color_index, const char* path, int cuda_device) try
 {
 	TG_REQUIRE_TREE(tree);
 	if (!path) return Fail(TG_ERR_INVALID, "null path");
@@ -622,87 +683,98 @@ int tg_export_magica_voxel(const tg_tree* tree, float grid_size, int color_index
 	tg_context_destroy(context);
 	return rc;
 }
+TG_CATCH_STATUS
 
-int tg_write_ply(const char* path, const tg_mesh* mesh)
+int tg_write_ply(const char* path, const tg_mesh* mesh) try
 {
 	if (!path || !mesh) return Fail(TG_ERR_INVALID, "null argument");
 	std::string error;
 	if (!WritePly(path, mesh->positions, mesh->normals, mesh->colors, mesh->vertex_count, mesh->triangles, mesh->triangle_count, error)) return Fail(TG_ERR_IO, error);
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
-int tg_write_stl(const char* path, const tg_mesh* mesh)
+int tg_write_stl(const char* path, const tg_mesh* mesh) try
 {
 	if (!path || !mesh) return Fail(TG_ERR_INVALID, "null argument");
 	std::string error;
 	if (!WriteStl(path, mesh->positions, mesh->normals, mesh->face_normals, mesh->vertex_count, mesh->triangles, mesh->triangle_count, error)) return Fail(TG_ERR_IO, error);
 	return TG_OK;
 }
+TG_CATCH_STATUS
 
 // ---- measurement helpers -------------------------------------------------------------------------
 
-int tg_timer_begin(tg_context* context)
+int tg_timer_begin(tg_context* context) try
 {
 	if (!context) return Fail(TG_ERR_INVALID, "null context");
 	std::string error;
 	int rc = EngineTimerBegin(context->impl.get(), error);
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
+TG_CATCH_STATUS
 
-int tg_timer_end(tg_context* context, float* out_ms)
+int tg_timer_end(tg_context* context, float* out_ms) try
 {
 	if (!context || !out_ms) return Fail(TG_ERR_INVALID, "null argument");
 	std::string error;
 	int rc = EngineTimerEnd(context->impl.get(), out_ms, error);
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
+TG_CATCH_STATUS
 
-int tg_measure_fp32_peak(tg_context* context, double* out_tflops)
+int tg_measure_fp32_peak(tg_context* context, double* out_tflops) try
 {
 	if (!context || !out_tflops) return Fail(TG_ERR_INVALID, "null argument");
 	std::string error;
 	int rc = EngineMeasureFp32Peak(context->impl.get(), out_tflops, error);
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
+TG_CATCH_STATUS
 
-int tg_flush_l2(tg_context* context)
+int tg_flush_l2(tg_context* context) try
 {
 	if (!context) return Fail(TG_ERR_INVALID, "null context");
 	std::string error;
 	int rc = EngineFlushL2(context->impl.get(), error);
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
+TG_CATCH_STATUS
 
-int tg_mesh_download(tg_mesh* mesh, uint32_t index_base)
+int tg_mesh_download(tg_mesh* mesh, uint32_t index_base) try
 {
 	if (!mesh) return Fail(TG_ERR_INVALID, "null mesh");
 	std::string error;
 	int rc = EngineDownloadMesh(mesh, index_base, error);
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
+TG_CATCH_STATUS
 
-int tg_context_synchronize(tg_context* context)
+int tg_context_synchronize(tg_context* context) try
 {
 	if (!context) return Fail(TG_ERR_INVALID, "null context");
 	std::string error;
 	int rc = EngineSynchronize(context->impl.get(), error);
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
+TG_CATCH_STATUS
 
-int tg_model_upload(tg_model* model)
+int tg_model_upload(tg_model* model) try
 {
 	if (!model) return Fail(TG_ERR_INVALID, "null model");
 	std::string error;
 	int rc = EngineUploadModel(model->impl.get(), error);
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
+TG_CATCH_STATUS
 
-int tg_brick_profile(tg_model* model, const tg_grid* grid, uint32_t* out_layers, uint32_t layer_count)
+int tg_brick_profile(tg_model* model, const tg_grid* grid, uint32_t* out_layers, uint32_t layer_count) try
 {
 	if (!model || !grid || !out_layers) return Fail(TG_ERR_INVALID, "null argument");
 	std::string error;
 	int rc = EngineBrickProfile(model->impl.get(), *grid, out_layers, layer_count, error);
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
+TG_CATCH_STATUS
 
 } // extern "C"

@@ -2175,6 +2175,10 @@ struct Scratch
 struct MeshResultDevice
 {
 	Context* context = nullptr;
+	explicit MeshResultDevice(Context* c) : context(c) { c->live_results.fetch_add(1); }
+	~MeshResultDevice() { context->live_results.fetch_sub(1); }
+	MeshResultDevice(const MeshResultDevice&) = delete;
+	MeshResultDevice& operator=(const MeshResultDevice&) = delete;
 	float* d_positions = nullptr;
 	float* d_normals = nullptr;
 	unsigned char* d_colors = nullptr;
@@ -2198,7 +2202,9 @@ void EngineFreeMesh(tg_mesh* mesh)
 		r->context->ReleaseDevice(r->d_triangles);
 		r->context->ReleaseDevice(r->d_face_normals);
 		for (void* p : r->pinned) r->context->ReleasePinned(p);
+		Context* owner = r->context;
 		delete r;
+		if (owner->orphaned.load() && owner->live_results.load() == 0) delete owner; // tg_context_destroy came first
 	}
 	std::free(mesh->layer_vertices);
 	std::free(mesh->layer_vertex_cost);
@@ -2631,8 +2637,7 @@ static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const
 	static_assert(sizeof(Mailbox) <= kMailboxBytes, "mailbox block too small");
 	job.mailbox = static_cast<Mailbox*>(ctx->AcquireMailbox(error));
 	if (!job.mailbox) return TG_ERR_MEMORY;
-	job.result = new MeshResultDevice();
-	job.result->context = ctx;
+	job.result = new MeshResultDevice(ctx);
 	MeshResultDevice* result = job.result;
 
 	Scratch scratch(ctx, lane);
@@ -3247,8 +3252,7 @@ static int ExportMeshPipelined(Model* model, const tg_grid& grid_in, const tg_me
 		j->result = nullptr;
 	}
 
-	MeshResultDevice* result = new MeshResultDevice();
-	result->context = ctx;
+	MeshResultDevice* result = new MeshResultDevice(ctx);
 	result->pinned.push_back(host.positions);
 	if (host.normals) result->pinned.push_back(host.normals);
 	if (host.colors) result->pinned.push_back(host.colors);
@@ -3531,7 +3535,7 @@ int EngineExportVoxels(Model* model, float grid_size, int32_t out_size[3], float
 	return TG_OK;
 }
 
-int EngineExportPoints(Model* model, const float mn[3], const float mx[3], const float step[3], int refine, uint32_t flags, tg_mesh* out, std::string& error)
+int EngineExportPoints(Model* model, const float mn[3], const float mx[3], const float step[3], int refine, uint32_t flags, float scale, tg_mesh* out, std::string& error)
 {
 	std::memset(out, 0, sizeof(*out));
 	Context* ctx = model->context;
@@ -3578,8 +3582,7 @@ int EngineExportPoints(Model* model, const float mn[3], const float mx[3], const
 	TG_CUDA(cudaMemcpyAsync(&host_total, counters + kCntTotalVertices, 8, cudaMemcpyDeviceToHost, stream));
 	TG_CUDA(cudaStreamSynchronize(stream));
 	const uint32_t count = uint32_t(host_total);
-	MeshResultDevice* result = new MeshResultDevice();
-	result->context = ctx;
+	MeshResultDevice* result = new MeshResultDevice(ctx);
 	out->opaque = result;
 	out->vertex_count = count;
 	if (count > 0)
@@ -3592,7 +3595,7 @@ int EngineExportPoints(Model* model, const float mn[3], const float mx[3], const
 		std::memset(&options, 0, sizeof(options));
 		options.flags = flags;
 		options.refine_iterations = refine;
-		options.scale = 1.0f;
+		options.scale = scale == 0.0f ? 1.0f : scale; // WritePLY multiplies after sampling normal and colour (export.cpp:313, 476)
 		const float halfv[3] = { half.x, half.y, half.z };
 		AttributeScratch as;
 		if (WantsAttributePass(model, options))

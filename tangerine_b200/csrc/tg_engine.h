@@ -45,6 +45,10 @@ public:
 	// Export progress mirrors the reference's atomics (export.cpp:48-57).
 	std::atomic<int> stage{ 0 };
 	std::atomic<bool> active{ true };
+	// Results handed to the caller (tg_mesh) keep blocks of this context's pinned / device caches: the context is only
+	// torn down once the last of them was freed (tg_context_destroy on a context with live meshes defers to that moment).
+	std::atomic<int> live_results{ 0 };
+	std::atomic<bool> orphaned{ false };
 	std::atomic<uint64_t> progress_done[4];
 	std::atomic<uint64_t> progress_total[4];
 
@@ -92,7 +96,7 @@ struct MeshResultDevice; // opaque device-side result kept alive by tg_mesh.opaq
 int EngineEvalPoints(Model* model, int mode, const float* points, uint64_t count, void* out, std::string& error);
 int EngineEvalLattice(Model* model, const tg_grid& grid, float* out, float* out_ms, std::string& error);
 int EngineExportMesh(Model* model, const tg_grid& grid, const tg_mesh_options& options, tg_mesh* out, std::string& error);
-int EngineExportPoints(Model* model, const float mn[3], const float mx[3], const float step[3], int refine, uint32_t flags, tg_mesh* out, std::string& error);
+int EngineExportPoints(Model* model, const float mn[3], const float mx[3], const float step[3], int refine, uint32_t flags, float scale, tg_mesh* out, std::string& error);
 int EngineExportVoxels(Model* model, float grid_size, int32_t out_size[3], float* out_radius, int32_t** out_xyz, uint64_t* out_count, std::string& error);
 void EngineFreeMesh(tg_mesh* mesh);
 int EngineDownloadMesh(tg_mesh* mesh, uint32_t index_base, std::string& error);

@@ -44,7 +44,7 @@ int RunExport(const tg_tree* tree, const std::string& path, const float mn[3], c
 		if (point_cloud)
 		{
 			// PointCloudExportThread only writes PLY (export.cpp:473-477)
-			rc = format == ExportFormat::PLY ? tg_export_points(model, mn, mx, step, refine, TG_MESH_NORMALS | TG_MESH_COLORS, &mesh) : TG_ERR_INVALID;
+			rc = format == ExportFormat::PLY ? tg_export_points(model, mn, mx, step, refine, TG_MESH_NORMALS | TG_MESH_COLORS, scale, &mesh) : TG_ERR_INVALID;
 		}
 		else
 		{
@@ -93,7 +93,15 @@ void MeshExport(const tg_tree* Evaluator, std::string Path, const float ModelMin
 	const float st[3] = { Step[0], Step[1], Step[2] };
 	std::thread worker([=]()
 	{
-		int rc = copy ? RunExport(copy, Path, mn, mx, st, RefineIterations, Format, ExportPointCloud, Scale) : TG_ERR_INVALID;
+		int rc = TG_ERR_INVALID;
+		try
+		{
+			if (copy) rc = RunExport(copy, Path, mn, mx, st, RefineIterations, Format, ExportPointCloud, Scale);
+		}
+		catch (...)
+		{
+			rc = TG_ERR_MEMORY; // nothing may unwind out of a detached thread
+		}
 		tg_tree_free(copy);
 		Finish(rc);
 		g_stage.store(0);

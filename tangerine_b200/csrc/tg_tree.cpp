@@ -811,6 +811,13 @@ bool Tree::LoadTgm(const std::string& path, Tree& out, std::string& error)
 	}
 	uint32_t header[4];
 	bool ok = std::fread(header, 4, 4, f) == 4 && header[0] == 0x314D4754u;
+	if (ok)
+	{
+		// the counts come from the file: they must account for its size exactly before anything is sized by them
+		long size = -1;
+		if (std::fseek(f, 0, SEEK_END) == 0) size = std::ftell(f);
+		ok = size >= 16 && uint64_t(size) == 16ull + uint64_t(header[2]) * 12ull + uint64_t(header[1]) * sizeof(TgmRecord) && std::fseek(f, 16, SEEK_SET) == 0;
+	}
 	std::vector<float> colors;
 	std::vector<TgmRecord> records;
 	if (ok)
