@@ -4,18 +4,25 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload seaside1024] [--impl ours|reference]
 
 A "step" is one whole mesh export of the workload: culling, brick evaluation + cell classification, vertex
-numbering, quad emission, refinement + normals + colours.  With N > 1 (launched by torch.distributed.run, one
-rank per GPU) the grid is cut into z-slabs, one per rank, with a one-layer halo; the only exchange is an
-all-gather of the per-slab vertex / triangle counts, so the job is the same fixed grid at
+numbering, quad emission, refinement + normals + colours.  With N > 1 the export runs INSIDE the library on a
+multi-device context (tg_context_create_multi): one process, one host thread + stream per GPU, z-slabs cut from a
+host-side work estimate (no planning exports, plan_iters = 0), the per-slab vertex counts all-gathered with NCCL on the
+devices, one stitched host mesh.  Under torch.distributed.run rank 0 drives that call; the other ranks join the NCCL
+process group (so the launch contract's rendezvous and barrier hold) and wait.  The job is the same fixed grid at
 every N ("strong" scaling).
 
 JSON keys (one line on stdout, rank 0):
-  value          Mvoxel/s = grid cells / device time per step, model tables resident in HBM, results left in HBM
-  e2e            Mvoxel/s through the C ABI the reference would bind (tg_model_upload + tg_export_mesh with
-                 host result buffers): per step the model tables go host -> device and the mesh comes back
-  evals_per_s    SDF evaluations per second (unique lattice samples run + per-vertex evaluations)
+  value          Mvoxel/s = grid cells / device time per step (max over the devices), model tables resident in HBM,
+                 results left in HBM
+  e2e            Mvoxel/s through the C ABI the reference would bind (tg_model_upload + tg_export_mesh with host result
+                 buffers): per step the model tables go host -> device and the mesh comes back
+  whole_export   wall time from the CSG tree to the host mesh (octree build + flattening + upload + export): what a
+                 caller of MeshExport waits for
+  parity         the benched mesh compared layer by layer with the reference's own mesh of the same grid
+                 (tests/golden/slices_<workload>.json), outside the timed region
   roofline       dominant kernel = MeshBricksKernel (evaluation + classification), FP32-pipe bound; `hbm` holds the
                  bandwidth-bound mesh kernels (vertex numbering / scatter / quad emission)
+  workloads      (N = 1) the other BASELINE.json configurations, a short run each
   cpu_baseline   the reference's own thunks (oracle/_ref/tangerine_ref, built from /root/reference by
                  oracle/Makefile) on all host threads over a stratified sample of z-slices of the same grid
 """
@@ -31,6 +38,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(1, os.path.join(ROOT, "tests"))
 MODELS = os.path.join(ROOT, "tests", "golden", "models")
 REF_TOOL = os.path.join(ROOT, "oracle", "_ref", "tangerine_ref")
 
@@ -49,16 +57,34 @@ WORKLOADS = {
 }
 
 
+def model_file(name):
+    """.tgm file of a workload's CSG tree.  The synthetic scene (tg_make_synthetic(10000, 1234)) is committed as a file
+    too, so that the reference arm needs nothing from this repository's library."""
+    return os.path.join(MODELS, name.replace(":", "") + ".tgm")
+
+
 def load_workload_tree(T, name):
     """Returns (tree, path of a .tgm file of it for the reference tool)."""
-    if name.startswith("synthetic:"):
-        import tempfile
+    path = model_file(name)
+    if name.startswith("synthetic:") and not os.path.exists(path):
         tree = T.Tree.synthetic(int(name.split(":")[1]), 1234)
-        path = os.path.join(tempfile.gettempdir(), "tg_%s_%d.tgm" % (name.replace(":", "_"), os.getpid()))
         tree.save(path)
         return tree, path
-    path = os.path.join(MODELS, name + ".tgm")
     return T.Tree.load(path), path
+
+
+def export_grid_shape(lo, hi, step):
+    """MeshExportThread's grid (export.cpp:324-337) in float32, without the library: (origin, cells per axis)."""
+    lo, hi, step = np.asarray(lo, np.float32), np.asarray(hi, np.float32), np.float32(step)
+    origin = (lo - step * np.float32(2.0)).astype(np.float32)
+    shape = [int(np.ceil(np.float32((hi[i] - origin[i]) / step))) for i in range(3)]
+    return origin, shape
+
+
+def workload_config(workload, shape):
+    """The `config` object both arms print (same keys, same values)."""
+    name, step, refine, desc = WORKLOADS[workload]
+    return {"workload": desc, "model": name.replace(":", "") + ".tgm", "grid": list(shape), "refine_iterations": refine}
 
 
 def log(*a):
@@ -170,15 +196,17 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
-def run_reference_sample(model_file, lo, hi, step, stride, threads):
+def run_reference_sample(tgm_path, lo, hi, step, stride, threads):
     """The reference's FirstLoopInnerThunk / SecondLoopThunk on std::threads over every `stride`-th z-slice."""
-    args = [REF_TOOL, "bench", model_file] + ["%.9g" % v for v in list(lo) + list(hi)] + ["%.9g" % step, str(threads), str(stride)]
+    args = [REF_TOOL, "bench", tgm_path] + ["%.9g" % v for v in list(lo) + list(hi)] + ["%.9g" % step, str(threads), str(stride)]
     out = subprocess.run(args, check=True, capture_output=True, text=True).stdout
     return json.loads(out.strip().splitlines()[-1])
 
 
 def reference_arm(args, workload):
-    """--impl reference: the reference CPU implementation, all host threads, bounded sample per step."""
+    """--impl reference: the reference CPU implementation (oracle/_ref/tangerine_ref = its own sources), all host threads,
+    a bounded sample of the workload per step.  Nothing of this repository's library is loaded here: bounds come from
+    `tangerine_ref info`, the grid from the reference's own formula."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -186,36 +214,214 @@ def reference_arm(args, workload):
     if not os.path.exists(REF_TOOL):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/tangerine_ref was not built (run __graft_entry__.build() where /root/reference exists)"}))
         return 0
-    import tangerine_b200 as T
-    tree, model_file = load_workload_tree(T, name)
-    lo, hi = tree.bounds()
+    tgm = model_file(name)
+    if not os.path.exists(tgm):
+        print(json.dumps({"impl": "reference", "unavailable": "model file %s is missing" % os.path.basename(tgm)}))
+        return 0
+    info = json.loads(subprocess.run([REF_TOOL, "info", tgm], check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1])
+    lo, hi = info["bounds_min"], info["bounds_max"]
     step32 = float(np.float32(step))
     threads = os.cpu_count() or 1
-    grid = T.export_grid(lo, hi, np.float32(step))
-    stride = args.ref_stride or max(1, grid.shape[2] // 8)
+    _, shape = export_grid_shape(lo, hi, step32)
+    stride = args.ref_stride or max(1, shape[2] // 8)
     for _ in range(args.warmup):
-        run_reference_sample(model_file, lo, hi, step32, max(stride * 4, 1), threads)
+        run_reference_sample(tgm, lo, hi, step32, max(stride * 4, 1), threads)
     cells = 0.0
     seconds = 0.0
     last = None
     for _ in range(args.steps):
-        last = run_reference_sample(model_file, lo, hi, step32, stride, threads)
+        last = run_reference_sample(tgm, lo, hi, step32, stride, threads)
         cells += last["cells_timed"]
-        seconds += last["loop1_s"] + last["loop2_s"]
+        seconds += last["loop1_s"]
     value = cells / seconds * 1e-6
-    sample = "every %d-th z-slice of the %dx%dx%d grid (%d slices, %.3g Mcells) per step, loop 1 (FirstLoopInnerThunk) only; octree build %.2f s excluded" % (
-        stride, grid.shape[0], grid.shape[1], grid.shape[2], last["slices_timed"], last["cells_timed"] * 1e-6, last["octree_build_s"])
+    sample = "every %d-th z-slice of the %dx%dx%d grid (%d slices, %.3g Mcells) per step through the reference's FirstLoopInnerThunk on %d std::threads; octree build %.2f s, loop 2 and the serial attribute pass are not in the time" % (
+        stride, shape[0], shape[1], shape[2], last["slices_timed"], last["cells_timed"] * 1e-6, threads, last["octree_build_s"])
     line = {
         "impl": "reference", "metric": "mesh export throughput", "value": value, "unit": "Mvoxel/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "grid": list(grid.shape), "model": name + ".tgm"},
+        "config": workload_config(workload, shape),
         "cpu_baseline": {"value": value, "unit": "Mvoxel/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "Mvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except OSError:
+        return {}
+
+
+def check_parity(workload, mesh):
+    """Layer-by-layer comparison of a host mesh with the reference's mesh of the same grid (committed fixture)."""
+    path = os.path.join(ROOT, "tests", "golden", "slices_%s.json" % workload)
+    if not os.path.exists(path):
+        return {"fixture": None, "equal": None, "note": "no reference fixture for this workload (tests/golden/make_slices.py)"}
+    from golden_util import layer_report
+    with open(path) as f:
+        fixture = json.load(f)
+    layers, v, t, bad = layer_report(mesh.positions, mesh.normals, mesh.colors, mesh.triangles, fixture)
+    return {"fixture": "tests/golden/" + os.path.basename(path), "against": "the reference's own thunks over the whole grid (oracle/_ref/tangerine_ref slices)",
+            "layers": layers, "vertices_compared": v, "triangles_compared": t, "equal": not bad, "first_mismatches": [list(b) for b in bad[:4]],
+            "compared": "positions, normals, colours, triangle indices per cell layer, bit for bit up to the sign of zero / NaN payloads"}
+
+
+def measure_workload(T, ctx, workload, steps, warmup, flags_extra=0, with_parity=True, fp32_peak=None, hbm_peak=None, devices=1, with_fast=True):
+    """One workload on `ctx` (single- or multi-device): device-resident steps, end-to-end steps, parity, roofline."""
+    name, step, refine, desc = WORKLOADS[workload]
+    tree, tgm = load_workload_tree(T, name)
+    lo, hi = tree.bounds()
+    grid = T.export_grid(lo, hi, np.float32(step))
+    sx, sy, sz = grid.shape
+    cells_total = sx * sy * sz
+    flags = T.MESH_NORMALS | T.MESH_COLORS | flags_extra
+
+    # ---- what a caller of MeshExport waits for: tree -> host mesh, cold (first export of this model on this context) ----
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    model = T.Model(ctx, tree)
+    model_seconds = time.perf_counter() - t0
+    first = model.export_mesh(grid, flags=flags, refine=refine)
+    whole_cold_ms = (time.perf_counter() - t0) * 1e3
+    first_export_ms = whole_cold_ms - model_seconds * 1e3
+    parity = None
+    if with_parity:
+        if refine > 0:
+            # the reference's mesh export never refines (export.cpp:320-381): its mesh is compared with the unrefined export of
+            # the same grid; the refined positions are checked against the C oracle in tests/test_gpu_bench_parity.py
+            plain = model.export_mesh(grid, flags=flags, refine=0)
+            parity = check_parity(workload, plain)
+            parity["note"] = "compared at refine 0 (the reference's MeshExportThread ignores RefineIterations); refined vertices: tests/test_gpu_bench_parity.py::test_gear512_refine5_against_oracle"
+            plain.close()
+        else:
+            parity = check_parity(workload, first)
+    first.close()
+    stats = model.stats()
+
+    # ---- device-resident throughput (`value`) ----
+    def device_step():
+        mesh = model.export_mesh(grid, flags=flags | T.MESH_DEVICE_ONLY, refine=refine)
+        t = dict(mesh.timings)
+        t["vertices"], t["triangles"] = mesh.vertex_count, mesh.triangle_count
+        t["ranks"] = mesh.rank_info()
+        mesh.close()
+        return t
+
+    for _ in range(warmup):
+        device_step()
+    ctx.synchronize()
+    records = []
+    ms_total = 0.0
+    for _ in range(steps):
+        ctx.flush_l2()                 # between timed iterations, outside the timed interval
+        ctx.timer_begin()              # CUDA events on every device's own stream, the ones the kernels are launched on
+        records.append(device_step())
+        ms_total += ctx.timer_end()    # slowest device
+    ms_per_step = ms_total / steps
+    value = cells_total / (ms_per_step * 1e-3) * 1e-6
+
+    # ---- end to end through the C ABI with host buffers (`e2e`) ----
+    def e2e_step():
+        model.upload()                                  # host -> device: octree table, regions, both instruction streams
+        mesh = model.export_mesh(grid, flags=flags, refine=refine)      # device -> host: one pinned result mesh
+        d2h = mesh.vertex_count * (12 + 12 + (3 if mesh.colors is not None else 0)) + mesh.triangle_count * 12
+        mesh.close()
+        return d2h
+
+    for _ in range(max(1, warmup // 2)):
+        e2e_step()
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    d2h = [e2e_step() for _ in range(steps)][-1]
+    ctx.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+    e2e_value = cells_total / (e2e_ms * 1e-3) * 1e-6
+
+    # ---- the whole export once more, warm: octree build + flatten + upload + export to the host ----
+    t0 = time.perf_counter()
+    model2 = T.Model(ctx, tree)
+    m2 = model2.export_mesh(grid, flags=flags, refine=refine)
+    whole_warm_ms = (time.perf_counter() - t0) * 1e3
+    m2.close()
+    model2.close()
+
+    # ---- the opt-in fast arithmetic (TG_MESH_FAST: FMA contraction, approximate sqrt / div), same steps ----
+    fast_records = []
+    fast_ms = 0.0
+    if with_fast:
+        for _ in range(max(1, warmup // 2)):
+            model.export_mesh(grid, flags=flags | T.MESH_DEVICE_ONLY | T.MESH_FAST, refine=refine).close()
+        ctx.synchronize()
+        for _ in range(steps):
+            ctx.flush_l2()
+            ctx.timer_begin()
+            mesh = model.export_mesh(grid, flags=flags | T.MESH_DEVICE_ONLY | T.MESH_FAST, refine=refine)
+            fast_ms += ctx.timer_end()
+            t = dict(mesh.timings)
+            t["vertices"], t["triangles"], t["ranks"] = mesh.vertex_count, mesh.triangle_count, mesh.rank_info()
+            fast_records.append(t)
+            mesh.close()
+
+    last = records[-1]
+
+    def mean(key):
+        return float(np.mean([r[key] for r in records]))
+
+    vertices, triangles = int(last["vertices"]), int(last["triangles"])
+    samples, flops = float(last["samples_evaluated"]), float(last["algorithmic_flops"])
+    vertex_evals = vertices * (5 * refine + 4 + (1 if stats["has_paint"] else 0))
+    out = {
+        "workload": workload, "config": workload_config(workload, grid.shape), "cells": cells_total,
+        "ms_per_step": ms_per_step, "value": value,
+        "e2e": {"value": e2e_value, "unit": "Mvoxel/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": float(stats["device_bytes"]) * devices, "d2h_bytes_per_step": float(d2h),
+                "timed": "host wall clock around tg_model_upload + tg_export_mesh with pinned host results (one call, one host mesh, whatever the device count)"},
+        "whole_export": {"cold_ms": whole_cold_ms, "warm_ms": whole_warm_ms, "model_build_ms": model_seconds * 1e3, "host_octree_build_ms": stats["build_seconds"] * 1e3,
+                         "first_export_ms": first_export_ms,
+                         "spans": "tg_model_create (host octree build + flatten + upload) + tg_export_mesh to host memory; cold = first use of the context (allocations), warm = again"},
+        "mesh": {"vertices": vertices, "triangles": triangles},
+        "bricks": {"total": float(last["bricks_total"]), "evaluated": float(last["bricks_evaluated"])},
+        "evals_per_s": (samples + vertex_evals) / (ms_per_step * 1e-3),
+        "reference_equivalent_evals_per_s": (8.0 * cells_total + 6.0 * vertices) / (ms_per_step * 1e-3),
+        "stage_ms": {k: mean(k) for k in ("cull_ms", "evaluate_ms", "compact_ms", "faces_ms", "attributes_ms", "total_device_ms")},
+        "octree_nodes": stats["octree_nodes"], "gpu_launches": int(sum(r["kernel_launches"] for r in records)),
+        "parity": parity,
+    }
+    if last["ranks"]:
+        keys = ("cull_ms", "evaluate_ms", "compact_ms", "faces_ms", "attributes_ms", "total_device_ms")
+        out["per_rank_ms"] = {k: [round(float(np.mean([r["ranks"][i][2][k] for r in records])), 4) for i in range(len(last["ranks"]))] for k in keys}
+        out["slabs"] = [[b, e] for b, e, _ in last["ranks"]]
+    # roofline of the dominant kernel (evaluation) and of the bandwidth-bound mesh kernels
+    eval_ms = mean("evaluate_ms")
+    if last["ranks"]:   # multi-device: the ranks evaluate concurrently; achieved = all FLOPs / slowest rank's kernel, peak = N x one device
+        eval_ms = max(out["per_rank_ms"]["evaluate_ms"])
+    achieved = flops / (eval_ms * 1e-3) * 1e-12 if eval_ms > 0 else 0.0
+    peak = (fp32_peak or 0.0) * devices
+    mesh_bytes = cells_total / 8.0 + 36.0 * vertices + 12.0 * vertices + 12.0 * triangles + 12.0 * vertices + 3.0 * vertices
+    mesh_ms = mean("compact_ms") + mean("faces_ms")
+    out["roofline"] = {
+        "kernel": "MeshBricksKernel", "bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+        "kernel_ms": eval_ms, "share_of_step": eval_ms / mean("total_device_ms") if mean("total_device_ms") else None,
+        "hbm": {"kernels": "vertex / quad numbering over the bitmap + FinalizeMeshKernel", "bound": "hbm", "achieved": mesh_bytes / (mesh_ms * 1e-3) * 1e-9 if mesh_ms > 0 else None,
+                "peak": (hbm_peak or 0.0) * devices, "unit": "GB/s", "frac": (mesh_bytes / (mesh_ms * 1e-3) * 1e-9 / (hbm_peak * devices)) if mesh_ms > 0 and hbm_peak else None, "kernel_ms": mesh_ms},
+    }
+    if fast_records:
+        f_eval = float(np.mean([r["evaluate_ms"] for r in fast_records]))
+        if fast_records[-1]["ranks"]:
+            f_eval = max(float(np.mean([r["ranks"][i][2]["evaluate_ms"] for r in fast_records])) for i in range(len(fast_records[-1]["ranks"])))
+        f_flops = float(fast_records[-1]["algorithmic_flops"])
+        f_achieved = f_flops / (f_eval * 1e-3) * 1e-12 if f_eval > 0 else 0.0
+        out["fast"] = {"flag": "TG_MESH_FAST (opt-in; not bit-identical: FMA contraction, approximate sqrt / div; within the north-star tolerances, tests/test_gpu_fast.py)",
+                       "ms_per_step": fast_ms / steps, "value": cells_total / (fast_ms / steps * 1e-3) * 1e-6,
+                       "mesh": {"vertices": int(fast_records[-1]["vertices"]), "triangles": int(fast_records[-1]["triangles"])},
+                       "roofline": {"kernel": "MeshBricksKernel (fast build)", "bound": "fp32", "achieved": f_achieved, "peak": peak, "unit": "TFLOP/s",
+                                    "frac": f_achieved / peak if peak else None, "kernel_ms": f_eval}}
+    model.close()
+    return out, (tgm, lo, hi, float(np.float32(step)), grid.shape)
 
 
 def main():
@@ -225,11 +431,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="seaside1024", choices=sorted(WORKLOADS))
-    ap.add_argument("--refine", type=int, default=None, help="override the workload's refinement iterations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-workloads", action="store_true", help="N = 1: skip the short runs of the other BASELINE configurations")
     ap.add_argument("--ref-stride", type=int, default=0, help="z-slice stride of the CPU sample (0 = auto)")
     ap.add_argument("--no-cull", action="store_true", help="evaluate every brick like the reference does")
-    ap.add_argument("--slab-align", type=int, default=1, help="z-slab cuts fall on multiples of this many cell layers (8 = whole brick rows)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -238,7 +443,6 @@ def main():
     import torch
     import torch.distributed as dist
     import tangerine_b200 as T
-    from tangerine_b200.slabs import balanced_slabs, exchange_counts, layer_costs, rebalance
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -246,197 +450,35 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: tangerine_b200 has no CPU path")
     torch.cuda.set_device(local)
+    waiters = None
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    name, step, refine, desc = WORKLOADS[args.workload]
-    if args.refine is not None:
-        refine = args.refine
-    tree, model_file = load_workload_tree(T, name)
-    lo, hi = tree.bounds()
-    grid = T.export_grid(lo, hi, np.float32(step))
-    sx, sy, sz = grid.shape
-    cells_total = sx * sy * sz
-
-    ctx = T.Context(local)
-    t0 = time.perf_counter()
-    model = T.Model(ctx, tree)
-    model_seconds = time.perf_counter() - t0
-    stats = model.stats()
-    flags = T.MESH_NORMALS | T.MESH_COLORS | (T.MESH_NO_CULL if args.no_cull else 0)
-
-    # z-slab partition.  First cut: the cull-only work estimate every rank computes identically (tg_brick_profile).
-    # After the first warm-up export the measured per-layer vertex cost (sum of program FLOPs over a layer's vertices) and stage times are all-reduced and the
-    # cut is redone on cost = eval_rate * brick_weight + vertex_rate * vertex_cost (same inputs on every rank, so
-    # no further communication is needed to agree on it).
-    if world > 1:
-        profile = model.brick_profile(grid).astype(np.float64)
-        slabs = balanced_slabs(profile, world, sz, args.slab_align)
-        slab = slabs[rank]
-    else:
-        profile = None
-        slabs = [(0, sz)]
-        slab = None
-
-    def barrier():
-        ctx.synchronize()
-        if world > 1:
-            dist.barrier()
+        t = torch.ones(1, device="cuda")
+        dist.all_reduce(t)                      # the launch contract's rendezvous: every rank's GPU joins one NCCL communicator
         torch.cuda.synchronize()
+        assert int(t.item()) == world
+        waiters = dist.new_group(backend="gloo")    # ranks > 0 wait on the host, not with a kernel spinning on their GPU
+    if rank != 0:
+        # The export is ONE call in ONE process driving every GPU of the box (tg_context_create_multi): rank 0 makes it.
+        dist.barrier(group=waiters)
+        dist.destroy_process_group()
+        return 0
 
-    def all_max(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def all_sum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    # ---- device-resident throughput (`value`) -------------------------------------------------------------
-    def device_step():
-        mesh = model.export_mesh(grid, flags=flags | T.MESH_DEVICE_ONLY, refine=refine, slab=slab)
-        t = dict(mesh.timings)
-        t["vertices"], t["triangles"] = mesh.vertex_count, mesh.triangle_count
-        mesh.close()
-        return t
-
-    cost = None          # modelled work per CELL layer
-    # Partition planning (world > 1): untimed exports that move the cuts by the measured per-rank times.  This is
-    # set-up, like the octree build -- it runs a fixed number of times whatever --warmup says -- and the partition
-    # with the smallest slowest rank seen on the way is the one that is then warmed up and timed.
-    plan_iters = 14 if world > 1 else 0
-    best_time, best_slabs = float("inf"), slabs
-    for w in range(plan_iters):
-        mesh = model.export_mesh(grid, flags=flags | T.MESH_DEVICE_ONLY, refine=refine, slab=slab)
-        tm = mesh.timings
-        n = len(profile)
-        brick_work = layer_costs(profile, sz)
-        mine = np.zeros(n + 4 + world, np.float64)
-        mine[:n] = mesh.layer_vertex_cost[:n]
-        mine[n:n + 4] = [tm["evaluate_ms"] + tm["cull_ms"], brick_work[slab[0]:slab[1]].sum(), tm["compact_ms"] + tm["faces_ms"] + tm["attributes_ms"], mesh.layer_vertex_cost.sum()]
-        mine[n + 4 + rank] = tm["total_device_ms"]
-        mesh.close()
-        t = torch.from_numpy(mine).cuda()
-        dist.all_reduce(t)
-        allv = t.cpu().numpy()
-        times = [float(allv[n + 4 + r]) for r in range(world)]
-        if w >= 1 and max(times) < best_time:      # the very first export also pays for first-touch allocations
-            best_time, best_slabs = max(times), list(slabs)
-        if cost is None:
-            # first model: two rates fitted to the measured stage times of all ranks
-            eval_rate = allv[n] / max(allv[n + 1], 1.0)
-            vertex_rate = allv[n + 2] / max(allv[n + 3], 1.0)
-            cost = eval_rate * brick_work + vertex_rate * layer_costs(allv[:n], sz) + 1e-9
-        # feedback: rescale every slab's layers so that the model reproduces the time that slab just took
-        for r, (k0, k1) in enumerate(slabs):
-            predicted = cost[k0:k1].sum()
-            if predicted > 0 and times[r] > 0:
-                cost[k0:k1] *= times[r] / predicted
-        if w < 2:
-            slabs = balanced_slabs(cost, world, sz, args.slab_align)
-        else:
-            # the cost model has placed the cuts roughly; from here on they move by the measured times alone
-            slabs = rebalance(slabs, times, sz, args.slab_align)
-        slab = slabs[rank]
-    if world > 1:
-        slabs = best_slabs
-        slab = slabs[rank]
-    for w in range(args.warmup):
-        model.export_mesh(grid, flags=flags | T.MESH_DEVICE_ONLY, refine=refine, slab=slab).close()
-    sampler = ClockSampler(local)
-    if rank == 0 and not os.environ.get("TG_BENCH_NO_SMI"):
-        sampler.start()
-    barrier()
-    steps = []
-    ms_local = 0.0
-    for _ in range(args.steps):
-        ctx.flush_l2()                 # between timed iterations, outside the timed interval
-        ctx.timer_begin()              # CUDA events on the context's own stream, the one every kernel is launched on
-        steps.append(device_step())
-        ms_local += ctx.timer_end()
-    barrier()
-    ms_total = all_max(ms_local)
-    ms_per_step = ms_total / args.steps
-    # per-rank view of the same region: wall (events around the K steps) and the sum of the engine's stage timers
-    stage_keys = ("cull_ms", "evaluate_ms", "compact_ms", "faces_ms", "attributes_ms")
-    per_rank = [[ms_local / args.steps, float(np.mean([s["total_device_ms"] for s in steps]))] + [float(np.mean([s[k] for s in steps])) for k in stage_keys]]
-    if world > 1:
-        t = torch.zeros((world, len(per_rank[0])), dtype=torch.float64, device="cuda")
-        dist.all_gather_into_tensor(t, torch.tensor(per_rank[0], dtype=torch.float64, device="cuda"))
-        per_rank = t.cpu().numpy().tolist()
-    value = cells_total / (ms_per_step * 1e-3) * 1e-6
-
-    # ---- end to end through the C ABI with host buffers (`e2e`) ------------------------------------------
-    def e2e_step():
-        model.upload()                                  # host -> device: octree table, regions, both instruction streams
-        if world == 1:
-            mesh = model.export_mesh(grid, flags=flags, refine=refine)      # device -> host: pinned result arrays
-        else:
-            mesh = model.export_mesh(grid, flags=flags | T.MESH_DEVICE_ONLY, refine=refine, slab=slab)
-            # the one exchange of the path: per-slab counts -> exclusive prefix -> global vertex ids
-            base, _, _, _ = exchange_counts(mesh.vertex_count, mesh.triangle_count, rank, world, device="cuda")
-            mesh.download(index_base=base)              # rebase on the device, then device -> host
-        d2h = mesh.vertex_count * (12 + 12 + (3 if mesh.colors is not None else 0)) + mesh.triangle_count * 12
-        v, f = mesh.vertex_count, mesh.triangle_count
-        mesh.close()
-        return d2h, v, f
-
-    for _ in range(max(1, args.warmup // 2)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    ctx.timer_begin()
-    e2e_results = [e2e_step() for _ in range(args.steps)]
-    e2e_dev_ms = ctx.timer_end()
-    barrier()
-    e2e_wall_ms = all_max((time.perf_counter() - t0) * 1e3)
-    e2e_value = cells_total / (e2e_wall_ms / args.steps * 1e-3) * 1e-6
-    clocks = sampler.stop() if rank == 0 else None
-    d2h_total = all_sum(float(e2e_results[-1][0]))
-    h2d_total = float(stats["device_bytes"]) * world
-
-    # ---- whole-job tallies ------------------------------------------------------------------------------------
-    last = steps[-1]
-    vertices = int(all_sum(float(last["vertices"])))
-    triangles = int(all_sum(float(last["triangles"])))
-    samples = all_sum(float(last["samples_evaluated"]))
-    flops = all_sum(float(last["algorithmic_flops"]))
-    launches = int(all_sum(float(sum(s["kernel_launches"] for s in steps))))
-    bricks_total = all_sum(float(last["bricks_total"]))
-    bricks_eval = all_sum(float(last["bricks_evaluated"]))
-    # per-vertex evaluations: R x (4-tap gradient + 1) + 4-tap normal + 1 material walk
-    vertex_evals = vertices * (5 * refine + 4 + (1 if stats["has_paint"] else 0))
-    evals_per_s = (samples + vertex_evals) / (ms_per_step * 1e-3)
-    reference_equivalent_evals = 8.0 * cells_total + 6.0 * vertices
-
-    def mean(key):
-        return float(np.mean([s[key] for s in steps]))
-
-    # ---- roofline of the dominant kernel (rank 0's slab; kernel time from CUDA events inside the engine) ----
-    fp32_peak = ctx.fp32_peak_tflops()
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except OSError:
-        pass
+    devices = list(range(world))
+    ctx = T.Context(devices=devices) if world > 1 else T.Context(local)
+    peaks = load_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    eval_ms = mean("evaluate_ms")
-    r0_flops = float(last["algorithmic_flops"])
-    achieved_tflops = r0_flops / (eval_ms * 1e-3) * 1e-12 if eval_ms > 0 else 0.0
-    r0_v, r0_f = last["vertices"], last["triangles"]
-    slab_cells = sx * sy * ((slab[1] - slab[0]) if slab else sz)
-    # SURVEY.md 8d "algorithmic bytes (mesh side)": cell->vertex map + neighbour ids + positions + indices + normals + colours
-    mesh_bytes = slab_cells / 8.0 + 36.0 * r0_v + 12.0 * r0_v + 12.0 * r0_f + 12.0 * r0_v + 3.0 * r0_v
-    mesh_ms = mean("compact_ms") + mean("faces_ms")
+    fp32_peak = ctx.fp32_peak_tflops()
+    flags_extra = T.MESH_NO_CULL if args.no_cull else 0
+
+    sampler = ClockSampler(local)
+    if not os.environ.get("TG_BENCH_NO_SMI"):
+        sampler.start()
+    head, ref_args = measure_workload(T, ctx, args.workload, args.steps, args.warmup, flags_extra, True, fp32_peak, hbm_peak, world)
+    clocks = sampler.stop()
+
     # DRAM traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed
     # `ncu --set full` capture of this same workload (profiles/ncu_meshbricks.json names the capture); null otherwise
     traffic, ncu_note = None, None
@@ -448,61 +490,81 @@ def main():
             ncu_note = {k: cap[k] for k in ("source", "issue_active_pct", "warp_instructions", "thread_instructions_per_sample") if k in cap}
     except (OSError, ValueError, KeyError):
         pass
-    roofline = {
-        "kernel": "MeshBricksKernel", "bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-        "frac": achieved_tflops / fp32_peak if fp32_peak else None, "traffic": traffic, "traffic_unit": "bytes per launch (ncu)", "ncu": ncu_note,
-        "peak_source": "FP32 FMA-chain kernel measured in this run (MEASURED_PEAKS.json has no CUDA-core figure); theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5",
-        "flops_convention": "SURVEY.md 8(d): FMA = 2, sqrt/div/abs/compare = 1, summed over the samples actually evaluated (culled bricks earn nothing)",
-        "kernel_ms": eval_ms, "share_of_step": eval_ms / mean("total_device_ms") if mean("total_device_ms") else None,
-        "hbm": {"kernels": "dual vertex/quad scan over the bitmap (3 launches) + FinalizeMeshKernel", "bound": "hbm", "achieved": mesh_bytes / (mesh_ms * 1e-3) * 1e-9 if mesh_ms > 0 else None,
-                "peak": hbm_peak, "unit": "GB/s", "frac": (mesh_bytes / (mesh_ms * 1e-3) * 1e-9 / hbm_peak) if mesh_ms > 0 else None,
-                "kernel_ms": mesh_ms, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
-    }
+    roofline = head["roofline"]
+    roofline.update({
+        "traffic": traffic, "traffic_unit": "bytes per launch (ncu)", "ncu": ncu_note,
+        "peak_source": "FP32 FMA-chain kernel measured in this run x %d device(s) (MEASURED_PEAKS.json has no CUDA-core figure); theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5 per device" % world,
+        "flops_convention": "SURVEY.md 8(d): FMA = 2, sqrt/div/abs/compare = 1, summed over the samples actually evaluated (culled bricks earn nothing)"})
+    roofline["hbm"]["peak_source"] = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
 
-    # ---- the reference's CPU path on this box's host cores, bounded sample (rank 0, N = 1 only) -----------
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        if os.path.exists(REF_TOOL):
-            stride = args.ref_stride or max(1, sz // 16)
+    # ---- the other BASELINE.json configurations, a short run each (N = 1) ----
+    workloads = None
+    if world == 1 and not args.no_extra_workloads:
+        workloads = {}
+        for w in ("basic66", "gear512", "colorcube512", "synthetic256", "synthetic512", "synthetic1024", "synthetic2048"):
+            if w == args.workload:
+                continue
             try:
-                r = run_reference_sample(model_file, lo, hi, float(np.float32(step)), stride, threads)
+                r, _ = measure_workload(T, ctx, w, 3, 2, flags_extra, True, fp32_peak, hbm_peak, 1)
+                workloads[w] = {"config": r["config"], "ms_per_step": r["ms_per_step"], "value": r["value"], "e2e_ms_per_step": r["e2e"]["ms_per_step"], "e2e": r["e2e"]["value"],
+                                "whole_export_ms": r["whole_export"]["warm_ms"], "host_octree_build_ms": r["whole_export"]["host_octree_build_ms"],
+                                "roofline_frac": r["roofline"]["frac"], "hbm_frac": r["roofline"]["hbm"]["frac"], "vertices": r["mesh"]["vertices"], "triangles": r["mesh"]["triangles"],
+                                "bricks_evaluated_frac": r["bricks"]["evaluated"] / max(r["bricks"]["total"], 1.0), "stage_ms": r["stage_ms"],
+                                "fast_ms_per_step": r["fast"]["ms_per_step"] if "fast" in r else None, "fast_roofline_frac": r["fast"]["roofline"]["frac"] if "fast" in r else None,
+                                "parity_equal": r["parity"]["equal"] if r["parity"] else None}
+            except T.TangerineError as e:
+                workloads[w] = {"error": str(e)}
+        # MagicaVoxel export of color-cube at the two grid sizes BASELINE configs[4] names (multi-cube above 126 cells)
+        try:
+            tree, _ = load_workload_tree(T, "color-cube")
+            model = T.Model(ctx, tree)
+            vox = {}
+            for g in (10.0, 25.0):
+                model.export_voxels(g)
+                t0 = time.perf_counter()
+                size, radius, xyz = model.export_voxels(g)
+                vox["grid_size_%d" % g] = {"size": list(size), "voxels": int(len(xyz)), "ms": (time.perf_counter() - t0) * 1e3}
+            model.close()
+            workloads["colorcube_vox"] = vox
+        except T.TangerineError as e:
+            workloads["colorcube_vox"] = {"error": str(e)}
+
+    # ---- the reference's CPU path on this box's host cores, bounded sample (N = 1 only) ----
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        tgm, lo, hi, step32, shape = ref_args
+        if os.path.exists(REF_TOOL):
+            stride = args.ref_stride or max(1, shape[2] // 16)
+            try:
+                r = run_reference_sample(tgm, lo, hi, step32, stride, threads)
                 cpu_baseline = {
-                    "value": r["cells_timed"] / (r["loop1_s"] + r["loop2_s"]) * 1e-6, "unit": "Mvoxel/s", "cores": threads, "kind": "reference",
+                    "value": r["cells_timed"] / r["loop1_s"] * 1e-6, "unit": "Mvoxel/s", "cores": threads, "kind": "reference",
                     "sample": "reference thunks (FirstLoopInnerThunk via oracle/_ref/tangerine_ref) on %d std::threads over every %d-th z-slice of the same %dx%dx%d grid: %d slices, %.3g Mcells in %.2f s; scaled to the whole grid this is %.0f s (extrapolated); octree build %.2f s, loop 2 and the serial attribute pass not included"
-                              % (threads, stride, sx, sy, sz, r["slices_timed"], r["cells_timed"] * 1e-6, r["loop1_s"], r["loop1_s"] * r["cells_total"] / r["cells_timed"], r["octree_build_s"]),
+                              % (threads, stride, shape[0], shape[1], shape[2], r["slices_timed"], r["cells_timed"] * 1e-6, r["loop1_s"], r["loop1_s"] * r["cells_total"] / r["cells_timed"], r["octree_build_s"]),
                 }
             except (subprocess.CalledProcessError, ValueError) as e:
                 cpu_baseline = {"value": None, "unit": "Mvoxel/s", "cores": threads, "kind": "reference", "sample": "failed: %s" % e}
         else:
             cpu_baseline = {"value": None, "unit": "Mvoxel/s", "cores": threads, "kind": "reference", "sample": "oracle/_ref/tangerine_ref not built"}
 
-    if rank == 0:
-        line = {
-            "metric": "mesh export throughput", "value": value, "unit": "Mvoxel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "model": (name + ".tgm (CSG tree dumped from the reference's Lua front-end)") if not name.startswith("synthetic:") else "tg_make_synthetic(%s, 1234)" % name.split(":")[1], "grid": [sx, sy, sz], "refine_iterations": refine,
-                       "attributes": "normals+colours", "culling": not args.no_cull, "partition": "z-slabs %s (cuts on multiples of %d layers)" % (slabs, args.slab_align),
-                       "l2": "flushed before every timed step (256 MiB fill, outside the per-step event pair); per-step scratch (bitmap + prefix) also exceeds L2 at this grid"},
-            "evals_per_s": evals_per_s, "reference_equivalent_evals_per_s": reference_equivalent_evals / (ms_per_step * 1e-3),
-            "mesh": {"vertices": vertices, "triangles": triangles},
-            "bricks": {"total": bricks_total, "evaluated": bricks_eval},
-            "stage_ms_rank0": {k: mean(k) for k in ("cull_ms", "evaluate_ms", "compact_ms", "faces_ms", "attributes_ms", "total_device_ms")},
-            "per_rank_ms": dict({"step_wall": [round(r[0], 4) for r in per_rank], "stage_sum": [round(r[1], 4) for r in per_rank]},
-                                **{k: [round(r[2 + i], 4) for r in per_rank] for i, k in enumerate(stage_keys)}),
-            "model_build_s": model_seconds, "octree_nodes": stats["octree_nodes"],
-            "e2e": {"value": e2e_value, "unit": "Mvoxel/s", "ms_per_step": e2e_wall_ms / args.steps, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
-                    "timed": "host wall clock around tg_model_upload + tg_export_mesh (pinned host results)%s, max over ranks" % (" + NCCL count all-gather + tg_mesh_download (index rebase on device)" if world > 1 else ""),
-                    "device_ms_per_step_rank0": e2e_dev_ms / args.steps},
-            "gpu_launches": launches,
-            "roofline": roofline,
-            "cpu_baseline": cpu_baseline,
-            "clocks": clocks,
-        }
-        print(json.dumps(line))
-    model.close()
+    config = dict(head["config"])
+    config.update({"attributes": "normals+colours", "culling": not args.no_cull,
+                   "partition": ("z-slabs %s cut from the host-side work estimate, plan_iters 0" % head.get("slabs")) if world > 1 else "one device",
+                   "l2": "flushed before every timed step (256 MiB fill per device, outside the per-step event pair); per-step scratch (bitmap + prefix) also exceeds L2 at this grid"})
+    line = {
+        "metric": "mesh export throughput", "value": head["value"], "unit": "Mvoxel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config, "plan_iters": 0,
+        "evals_per_s": head["evals_per_s"], "reference_equivalent_evals_per_s": head["reference_equivalent_evals_per_s"],
+        "mesh": head["mesh"], "bricks": head["bricks"], "stage_ms_rank0": head["stage_ms"], "per_rank_ms": head.get("per_rank_ms"),
+        "octree_nodes": head["octree_nodes"], "e2e": head["e2e"], "whole_export": head["whole_export"], "parity": head["parity"],
+        "gpu_launches": head["gpu_launches"], "roofline": roofline, "fast": head.get("fast"), "workloads": workloads, "cpu_baseline": cpu_baseline, "clocks": clocks,
+    }
+    print(json.dumps(line))
     ctx.close()
     if world > 1:
+        dist.barrier(group=waiters)
         dist.destroy_process_group()
     return 0
 

@@ -125,6 +125,13 @@ TG_API tg_context* tg_context_create(int cuda_device);
  * pinned cache, so a context with live meshes is torn down by the tg_mesh_free of the last one. */
 TG_API void tg_context_destroy(tg_context* context);
 TG_API int tg_context_device(const tg_context* context);
+/* Multi-GPU context: the devices of one box, driven from this one process (SURVEY.md 8b `tg_ctx_create(devices[], n)`).
+ * Models created on it are replicated to every device; tg_export_mesh then cuts the grid into z-slabs, one per device,
+ * combines the per-slab vertex counts with an ncclAllGather over NVLink and returns ONE host mesh, exactly as on one
+ * device.  Needs libnccl.so.2 at run time when count > 1 (TG_ERR_UNSUPPORTED otherwise); every other
+ * call on such a context runs on its first device. */
+TG_API tg_context* tg_context_create_multi(const int* cuda_devices, int count);
+TG_API int tg_context_device_count(const tg_context* context);
 
 typedef struct tg_model_stats
 {
@@ -188,7 +195,13 @@ enum
 	TG_MESH_COLORS = 1u << 1,       /* per-vertex export colour; ignored (white) when the model has no paint */
 	TG_MESH_NO_CULL = 1u << 2,      /* evaluate every brick, as the reference does (dense sweep) */
 	TG_MESH_DEVICE_ONLY = 1u << 3,  /* leave results in HBM: out->positions etc. are NULL, counts are valid */
-	TG_MESH_FACE_NORMALS = 1u << 4  /* per-triangle gradient at the centroid (WriteSTL, export.cpp:130-140) */
+	TG_MESH_FACE_NORMALS = 1u << 4, /* per-triangle gradient at the centroid (WriteSTL, export.cpp:130-140) */
+	TG_MESH_KEEP_CANCEL = 1u << 5,  /* do not re-arm the context: a tg_cancel issued before this call still cancels it */
+	/* Opt-in fast arithmetic for the lattice evaluation: FMA contraction, approximate sqrt / division, float where the
+	 * reference promotes to double.  Samples stay within BASELINE.json's tolerance (1e-5 relative / 4 ULP) of the
+	 * reference but are no longer bit-identical, so a cell whose corner value is within that tolerance of zero may change
+	 * its classification.  Without this flag every sample, vertex, normal and colour is bit-identical to the reference. */
+	TG_MESH_FAST = 1u << 6
 };
 
 typedef struct tg_mesh_options
@@ -239,6 +252,13 @@ typedef struct tg_mesh
 } tg_mesh;
 
 TG_API int tg_export_mesh(tg_model* model, const tg_grid* grid, const tg_mesh_options* options, tg_mesh* out);
+/* The z-slab cuts a multi-GPU export of `tree` on `grid` over `ranks` devices would use (host only, no device needed):
+ * out_cuts receives ranks + 1 cell-layer indices, 0 ... grid->sz.  They come from a host-side estimate of the work per
+ * cell layer made from the octree's terminus cells (optional out_layer_cost, grid->sz entries); no warm-up exports. */
+TG_API int tg_tree_plan_slabs(const tg_tree* tree, float octree_target_size, const tg_grid* grid, int ranks, uint64_t* out_cuts, double* out_layer_cost);
+/* Multi-GPU exports only: number of ranks (or -1 for a single-device result), and for `rank` its z-slab [begin, end) and
+ * the stage timings of its device (the timings in tg_mesh are the maximum over the ranks). */
+TG_API int tg_mesh_rank_info(const tg_mesh* mesh, int rank, uint64_t* out_slab_begin, uint64_t* out_slab_end, tg_mesh_timings* out_timings);
 TG_API void tg_mesh_free(tg_mesh* mesh);
 /* Second half of a TG_MESH_DEVICE_ONLY export: adds index_base to every triangle index on the device (multi-GPU:
  * the vertex total of the lower ranks, known once the per-slab counts were exchanged) and copies the arrays into
@@ -248,6 +268,8 @@ TG_API int tg_mesh_download(tg_mesh* mesh, uint32_t index_base);
 /* Raw lattice samples of the grid through SDFOctree::Eval: (sx+1)*(sy+1)*(sz+1) floats, x fastest.
  * `out` may be NULL to time the evaluator alone; elapsed device milliseconds are returned in *out_ms. */
 TG_API int tg_eval_lattice(tg_model* model, const tg_grid* grid, float* out, float* out_ms);
+/* The same with mesh flags: TG_MESH_FAST evaluates with the fast arithmetic (tolerance tests). */
+TG_API int tg_eval_lattice_flags(tg_model* model, const tg_grid* grid, uint32_t flags, float* out, float* out_ms);
 
 /* ------------------------------------------------------------------------------------------------
  * Point-cloud export.  Replaces PointCloudExportThread's two Pool() passes (export.cpp:393-469).

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 
 EVAL_OCTREE, EVAL_INTERP, EVAL_TREE, EVAL_GRADIENT, EVAL_COLOR = range(5)
-MESH_NORMALS, MESH_COLORS, MESH_NO_CULL, MESH_DEVICE_ONLY, MESH_FACE_NORMALS = 1, 2, 4, 8, 16
+MESH_NORMALS, MESH_COLORS, MESH_NO_CULL, MESH_DEVICE_ONLY, MESH_FACE_NORMALS, MESH_KEEP_CANCEL, MESH_FAST = 1, 2, 4, 8, 16, 32, 64
 
 
 class TangerineError(RuntimeError):
@@ -139,9 +139,13 @@ def lib():
         "tg_context_create": (vp, [i32]),
         "tg_context_destroy": (None, [vp]),
         "tg_context_device": (i32, [vp]),
+        "tg_context_create_multi": (vp, [C.POINTER(C.c_int), i32]),
+        "tg_context_device_count": (i32, [vp]),
+        "tg_mesh_rank_info": (i32, [C.POINTER(_Mesh), i32, C.POINTER(u64), C.POINTER(u64), C.POINTER(MeshTimings)]),
         "tg_model_create": (vp, [vp, vp, C.c_float, i32]),
         "tg_tree_octree_stats": (i32, [vp, C.c_float, i32, C.POINTER(ModelStats)]),
         "tg_model_destroy": (None, [vp]),
+        "tg_tree_plan_slabs": (i32, [vp, C.c_float, C.POINTER(Grid), i32, C.POINTER(u64), C.POINTER(C.c_double)]),
         "tg_model_get_stats": (i32, [vp, C.POINTER(ModelStats)]),
         "tg_eval_points": (i32, [vp, i32, fp, u64, vp]),
         "tg_export_grid": (i32, [fp, fp, fp, C.POINTER(Grid)]),
@@ -149,6 +153,7 @@ def lib():
         "tg_mesh_free": (None, [C.POINTER(_Mesh)]),
         "tg_mesh_download": (i32, [C.POINTER(_Mesh), u32]),
         "tg_eval_lattice": (i32, [vp, C.POINTER(Grid), fp, fp]),
+        "tg_eval_lattice_flags": (i32, [vp, C.POINTER(Grid), u32, fp, fp]),
         "tg_export_points": (i32, [vp, fp, fp, fp, i32, u32, C.c_float, C.POINTER(_Mesh)]),
         "tg_export_voxels": (i32, [vp, C.c_float, C.POINTER(C.c_int32), fp, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(u64)]),
         "tg_free": (None, [vp]),
@@ -335,6 +340,13 @@ class Tree:
     def save(self, path):
         _check(lib().tg_tree_save(self.h, os.fsencode(path)))
 
+    def plan_slabs(self, grid, ranks, target_size=0.25):
+        """(cuts, per-layer cost estimate) of a multi-GPU export of this tree over `ranks` devices (host only)."""
+        cuts = (C.c_uint64 * (ranks + 1))()
+        cost = np.zeros(grid.shape[2], np.float64)
+        _check(lib().tg_tree_plan_slabs(self.h, target_size, C.byref(grid), ranks, cuts, cost.ctypes.data_as(C.POINTER(C.c_double))))
+        return [int(c) for c in cuts], cost
+
     def octree_stats(self, target_size=0.25, threads=0):
         s = ModelStats()
         _check(lib().tg_tree_octree_stats(self.h, target_size, threads, C.byref(s)))
@@ -353,8 +365,18 @@ def export_grid(lo, hi, step):
 
 
 class Context:
-    def __init__(self, device=0):
-        self.h = _handle(lib().tg_context_create(device))
+    """One CUDA device, or -- Context(devices=[0, 1, ...]) -- the GPUs of one box driven together (tg_context_create_multi)."""
+
+    def __init__(self, device=0, devices=None):
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            self.h = _handle(lib().tg_context_create_multi(arr, len(devices)))
+        else:
+            self.h = _handle(lib().tg_context_create(device))
+
+    @property
+    def device_count(self):
+        return int(lib().tg_context_device_count(self.h))
 
     def close(self):
         if getattr(self, "h", None):
@@ -433,6 +455,21 @@ class Mesh:
         if nt == 0:
             self.triangles = np.zeros((0, 3), np.uint32)
 
+    def rank_info(self):
+        """Multi-GPU exports: [(slab_begin, slab_end, timings dict)] per rank; [] for a single-device result."""
+        out = []
+        rank = 0
+        while True:
+            b, e, t = C.c_uint64(), C.c_uint64(), MeshTimings()
+            n = lib().tg_mesh_rank_info(C.byref(self.raw), rank, C.byref(b), C.byref(e), C.byref(t))
+            if n <= 0:
+                break
+            out.append((int(b.value), int(e.value), t.as_dict()))
+            rank += 1
+            if rank >= n:
+                break
+        return out
+
     def write_ply(self, path):
         _check(lib().tg_write_ply(os.fsencode(path), C.byref(self.raw)))
 
@@ -488,11 +525,11 @@ class Model:
         _check(lib().tg_eval_points(self.h, mode, _fp(pts), n, out.ctypes.data_as(C.c_void_p)))
         return out
 
-    def eval_lattice(self, grid, download=True):
+    def eval_lattice(self, grid, download=True, flags=0):
         sx, sy, sz = grid.shape
         ms = C.c_float()
         out = np.zeros((sz + 1, sy + 1, sx + 1), np.float32) if download else None
-        _check(lib().tg_eval_lattice(self.h, C.byref(grid), _fp(out) if download else None, C.byref(ms)))
+        _check(lib().tg_eval_lattice_flags(self.h, C.byref(grid), flags, _fp(out) if download else None, C.byref(ms)))
         return out, ms.value
 
     def export_mesh(self, grid, flags=MESH_NORMALS | MESH_COLORS, refine=0, scale=1.0, slab=None):

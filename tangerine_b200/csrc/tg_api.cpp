@@ -21,13 +21,28 @@ struct tg_tree
 
 struct tg_context
 {
-	std::unique_ptr<Context> impl;
+	std::unique_ptr<Context> impl;                // the (first) device
+	std::vector<std::unique_ptr<Context>> peers;  // multi-GPU contexts: the other devices ...
+	std::unique_ptr<DeviceGroup> group;           // ... and their worker threads + NCCL communicators
+
+	~tg_context()
+	{
+		group.reset(); // joins the workers and destroys the communicators before the device contexts go
+	}
 };
 
 struct tg_model
 {
 	std::unique_ptr<Model> impl;
+	std::vector<std::unique_ptr<Model>> replicas; // the same tables on the peers of a multi-GPU context
 	tg_context* context;
+
+	std::vector<Model*> All() const
+	{
+		std::vector<Model*> all(1, impl.get());
+		for (const auto& r : replicas) all.push_back(r.get());
+		return all;
+	}
 };
 
 namespace
@@ -381,6 +396,58 @@ tg_context* tg_context_create(int cuda_device) try
 }
 TG_CATCH_NULL
 
+tg_context* tg_context_create_multi(const int* cuda_devices, int count) try
+{
+	if (!cuda_devices || count < 1)
+	{
+		Fail(TG_ERR_INVALID, "tg_context_create_multi needs at least one device");
+		return nullptr;
+	}
+	for (int i = 0; i < count; ++i)
+	{
+		for (int j = 0; j < i; ++j)
+		{
+			if (cuda_devices[i] == cuda_devices[j])
+			{
+				Fail(TG_ERR_INVALID, "tg_context_create_multi: a device is listed twice");
+				return nullptr;
+			}
+		}
+	}
+	std::unique_ptr<tg_context> h(new tg_context());
+	std::string error;
+	std::vector<Context*> all;
+	for (int i = 0; i < count; ++i)
+	{
+		Context* c = Context::Create(cuda_devices[i], error);
+		if (!c)
+		{
+			Fail(TG_ERR_NO_DEVICE, error);
+			return nullptr;
+		}
+		if (i == 0) h->impl.reset(c);
+		else h->peers.emplace_back(c);
+		all.push_back(c);
+	}
+	if (count > 1)
+	{
+		DeviceGroup* group = DeviceGroup::Create(all, error);
+		if (!group)
+		{
+			Fail(TG_ERR_UNSUPPORTED, error);
+			return nullptr;
+		}
+		h->group.reset(group);
+	}
+	return h.release();
+}
+TG_CATCH_NULL
+
+int tg_context_device_count(const tg_context* context)
+{
+	return context ? 1 + int(context->peers.size()) : 0;
+}
+
 void tg_context_destroy(tg_context* context) try
 {
 	if (!context) return;
@@ -415,10 +482,20 @@ tg_model* tg_model_create(tg_context* context, const tg_tree* tree, float target
 		Fail(error.find("deeper") != std::string::npos ? TG_ERR_UNSUPPORTED : TG_ERR_INVALID, error);
 		return nullptr;
 	}
-	tg_model* h = new tg_model();
+	std::unique_ptr<tg_model> h(new tg_model());
 	h->impl.reset(m);
 	h->context = context;
-	return h;
+	for (const auto& peer : context->peers)
+	{
+		Model* replica = Model::CreateReplica(peer.get(), m, error);
+		if (!replica)
+		{
+			Fail(TG_ERR_CUDA, error);
+			return nullptr;
+		}
+		h->replicas.emplace_back(replica);
+	}
+	return h.release();
 }
 TG_CATCH_NULL
 
@@ -460,6 +537,25 @@ int tg_tree_octree_stats(const tg_tree* tree, float target_size, int host_thread
 	}
 	FillStats(flat, out);
 	out->leaf_count = tree->tree.LeafCount();
+	return TG_OK;
+}
+TG_CATCH_STATUS
+
+int tg_tree_plan_slabs(const tg_tree* tree, float target_size, const tg_grid* grid, int ranks, uint64_t* out_cuts, double* out_layer_cost) try
+{
+	TG_REQUIRE_TREE(tree);
+	if (!grid || ranks < 1 || !out_cuts || grid->sz == 0 || grid->sz > 8184) return Fail(TG_ERR_INVALID, "bad argument");
+	if (!(target_size > 0.0f)) target_size = 0.25f;
+	FlatModel flat;
+	std::string error;
+	if (!BuildFlatModel(tree->tree, target_size, 0, flat, error)) return Fail(TG_ERR_INVALID, error);
+	const std::vector<double> cost = EstimateLayerCost(flat, *grid);
+	const std::vector<uint32_t> cuts = PlanSlabs(cost, uint32_t(grid->sz), ranks);
+	for (int r = 0; r <= ranks; ++r) out_cuts[r] = cuts[size_t(r)];
+	if (out_layer_cost)
+	{
+		for (size_t k = 0; k < cost.size(); ++k) out_layer_cost[k] = cost[k];
+	}
 	return TG_OK;
 }
 TG_CATCH_STATUS
@@ -515,8 +611,12 @@ int tg_export_mesh(tg_model* model, const tg_grid* grid, const tg_mesh_options* 
 	defaults.flags = TG_MESH_NORMALS | TG_MESH_COLORS;
 	defaults.scale = 1.0f;
 	std::string error;
-	model->context->impl->active.store(true); // MeshExport re-arms ExportActive on every call (export.cpp:568)
-	int rc = EngineExportMesh(model->impl.get(), *grid, options ? *options : defaults, out, error);
+	// MeshExport re-arms ExportActive on every call (export.cpp:568); TG_MESH_KEEP_CANCEL leaves a cancel that arrived
+	// before this call in force (the C++ mirror arms once, when it creates the context)
+	if (!options || !(options->flags & TG_MESH_KEEP_CANCEL)) model->context->impl->active.store(true);
+	int rc = model->context->group
+		? EngineExportMeshMulti(model->context->group.get(), model->All(), *grid, options ? *options : defaults, out, error)
+		: EngineExportMesh(model->impl.get(), *grid, options ? *options : defaults, out, error);
 	if (rc != TG_OK)
 	{
 		EngineFreeMesh(out);
@@ -537,7 +637,16 @@ int tg_eval_lattice(tg_model* model, const tg_grid* grid, float* out, float* out
 {
 	if (!model || !grid) return Fail(TG_ERR_INVALID, "null argument");
 	std::string error;
-	int rc = EngineEvalLattice(model->impl.get(), *grid, out, out_ms, error);
+	int rc = EngineEvalLattice(model->impl.get(), *grid, 0u, out, out_ms, error);
+	return rc == TG_OK ? rc : Fail(rc, error);
+}
+TG_CATCH_STATUS
+
+int tg_eval_lattice_flags(tg_model* model, const tg_grid* grid, uint32_t flags, float* out, float* out_ms) try
+{
+	if (!model || !grid) return Fail(TG_ERR_INVALID, "null argument");
+	std::string error;
+	int rc = EngineEvalLattice(model->impl.get(), *grid, flags, out, out_ms, error);
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
 TG_CATCH_STATUS
@@ -546,7 +655,7 @@ int tg_export_points(tg_model* model, const float mn[3], const float mx[3], cons
 {
 	if (!model || !mn || !mx || !step || !out) return Fail(TG_ERR_INVALID, "null argument");
 	std::string error;
-	model->context->impl->active.store(true);
+	if (!(flags & TG_MESH_KEEP_CANCEL)) model->context->impl->active.store(true);
 	int rc = EngineExportPoints(model->impl.get(), mn, mx, step, refine, flags, scale, out, error);
 	if (rc != TG_OK)
 	{
@@ -576,16 +685,9 @@ TG_CATCH_VOID
 int tg_progress(const tg_context* context, float out_ratios[4], int* out_stage) try
 {
 	if (!context) return Fail(TG_ERR_INVALID, "null context");
-	const Context* c = context->impl.get();
-	if (out_stage) *out_stage = c->stage.load();
-	if (out_ratios)
-	{
-		for (int i = 0; i < 4; ++i)
-		{
-			const uint64_t total = c->progress_total[i].load();
-			out_ratios[i] = total ? float(double(c->progress_done[i].load()) / double(total)) : 0.0f;
-		}
-	}
+	std::vector<const Context*> all(1, context->impl.get());
+	for (const auto& peer : context->peers) all.push_back(peer.get());
+	EngineProgress(all, out_ratios, out_stage);
 	return TG_OK;
 }
 TG_CATCH_STATUS
@@ -709,7 +811,7 @@ int tg_timer_begin(tg_context* context) try
 {
 	if (!context) return Fail(TG_ERR_INVALID, "null context");
 	std::string error;
-	int rc = EngineTimerBegin(context->impl.get(), error);
+	int rc = context->group ? EngineTimerBeginMulti(context->group.get(), error) : EngineTimerBegin(context->impl.get(), error);
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
 TG_CATCH_STATUS
@@ -718,7 +820,7 @@ int tg_timer_end(tg_context* context, float* out_ms) try
 {
 	if (!context || !out_ms) return Fail(TG_ERR_INVALID, "null argument");
 	std::string error;
-	int rc = EngineTimerEnd(context->impl.get(), out_ms, error);
+	int rc = context->group ? EngineTimerEndMulti(context->group.get(), out_ms, error) : EngineTimerEnd(context->impl.get(), out_ms, error);
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
 TG_CATCH_STATUS
@@ -737,6 +839,10 @@ int tg_flush_l2(tg_context* context) try
 	if (!context) return Fail(TG_ERR_INVALID, "null context");
 	std::string error;
 	int rc = EngineFlushL2(context->impl.get(), error);
+	for (const auto& peer : context->peers)
+	{
+		if (rc == TG_OK) rc = EngineFlushL2(peer.get(), error);
+	}
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
 TG_CATCH_STATUS
@@ -750,11 +856,20 @@ int tg_mesh_download(tg_mesh* mesh, uint32_t index_base) try
 }
 TG_CATCH_STATUS
 
+int tg_mesh_rank_info(const tg_mesh* mesh, int rank, uint64_t* out_slab_begin, uint64_t* out_slab_end, tg_mesh_timings* out_timings)
+{
+	return EngineMeshRankInfo(mesh, rank, out_slab_begin, out_slab_end, out_timings);
+}
+
 int tg_context_synchronize(tg_context* context) try
 {
 	if (!context) return Fail(TG_ERR_INVALID, "null context");
 	std::string error;
 	int rc = EngineSynchronize(context->impl.get(), error);
+	for (const auto& peer : context->peers)
+	{
+		if (rc == TG_OK) rc = EngineSynchronize(peer.get(), error);
+	}
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
 TG_CATCH_STATUS
@@ -763,7 +878,14 @@ int tg_model_upload(tg_model* model) try
 {
 	if (!model) return Fail(TG_ERR_INVALID, "null model");
 	std::string error;
-	int rc = EngineUploadModel(model->impl.get(), error);
+	int rc = TG_OK;
+	if (model->context->group)
+	{
+		// every device pulls the tables over its own PCIe link from the one page-locked staging copy, all at once
+		const std::vector<Model*> all = model->All();
+		rc = model->context->group->Run([&](int rank, std::string& e) { return EngineUploadModel(all[size_t(rank)], e); }, error);
+	}
+	else rc = EngineUploadModel(model->impl.get(), error);
 	return rc == TG_OK ? rc : Fail(rc, error);
 }
 TG_CATCH_STATUS

@@ -360,6 +360,347 @@ __device__ __forceinline__ float EvalInterp1(const DeviceModel& model, uint32_t 
 	return out[0];
 }
 
+// A GROUP of threads (a warp or a whole block) evaluates ONE point of a long program (FlatNode::flags & kNodeLong)
+// cooperatively.  The program is preceded by the table of its instructions' quad offsets (tg_octree.cpp), so every thread
+// fetches its own instructions directly -- no dependent fetch chain -- and the brush distances are computed in parallel
+// (an instruction's operand quads sit at fixed offsets behind its header; reading past a short instruction is harmless:
+// programs are contiguous and the stream ends in padding).  What is left is the operator chain over (code, value)
+// steps parked in shared memory, and it is folded in parallel too:
+//   1. every right-nested operand of the main chain -- [brush pushed with spill slot 0 ... stack-form operator with
+//      slot 0] -- is folded by the thread that owns its first step, privately, and collapses into ONE step of the main
+//      chain (min / max / blend with the operand's value);
+//   2. the main chain is then a sequence of x -> min(x, v) / max(x, v) steps, i.e. of clamps x -> min(max(x, lo), hi),
+//      and clamps compose associatively: every thread composes its contiguous share, thread 0 composes the shares in
+//      order.  min and max select one of their arguments, so the result is the sequential value bit for bit.
+// Blend or flate steps on the main chain (rare in long programs) fall back to one thread walking the collapsed chain.
+// Same arithmetic as EvalInterp everywhere.
+constexpr int kLongThreads = 256;     // block size of the kernel that evaluates long programs
+constexpr int kLongWarpSteps = 256;   // a warp handles programs up to this many instructions on its own ...
+constexpr int kLongBlockSteps = 2048; // ... the whole block the ones up to this many; beyond: sequential rounds
+
+struct LongScratch
+{
+	uint2 step[kLongBlockSteps];  // x: fold code | slot << 8 | operator << 16, y: value (brush distance, negated for Diff; or operator parameter)
+	float param[kLongBlockSteps]; // blend threshold of fused instructions
+	float2 share[kLongThreads];   // clamp (lo, hi) of every thread's part of a chain; also the operand lists
+	uint32_t marks[kLongThreads]; // per-thread counts of operand openings / closings
+	float result[kLongThreads / 32];
+};
+
+enum : uint32_t
+{
+	kFoldMin = 0, kFoldMax = 1, kFoldNop = 2, kFoldPush = 3, kFoldBlendUnion = 4, kFoldBlendInter = 5, kFoldBlendDiff = 6,
+	kFoldFlate = 7, kFoldStackOp = 8
+};
+
+// One step of the chain applied to (acc, stack).
+__device__ __forceinline__ void FoldStep(uint32_t word, float v, float param, float& acc, float (&stack)[kMaxStackSlots])
+{
+	const uint32_t code = word & 0xFFu;
+	if (code == kFoldMin) acc = fminf(acc, v);
+	else if (code == kFoldMax) acc = fmaxf(acc, v);
+	else if (code == kFoldPush)
+	{
+		const uint32_t slot = (word >> 8) & 0xFFu;
+		if (slot != kNoSlot) stack[slot] = acc;
+		acc = v;
+	}
+	else if (code >= kFoldBlendUnion && code <= kFoldBlendDiff) acc = sdf::SetOp(kOpBlendUnion + (code - kFoldBlendUnion), acc, v, param);
+	else if (code == kFoldFlate) acc = acc - v;
+	else if (code == kFoldStackOp) acc = sdf::SetOp(word >> 16, stack[(word >> 8) & 0xFFu], acc, v);
+}
+
+// Brush distance and fold code of instruction `pc` at (x, y, z).
+__device__ __forceinline__ void LongStep(const uint4* __restrict__ pc, float x, float y, float z, uint2& step, float& param)
+{
+	const uint4 q = __ldg(pc);
+	const float4 m0 = __ldg(reinterpret_cast<const float4*>(pc + 1));
+	const float4 m1 = __ldg(reinterpret_cast<const float4*>(pc + 2));
+	const float4 m2 = __ldg(reinterpret_cast<const float4*>(pc + 3));
+	const float4 m3 = __ldg(reinterpret_cast<const float4*>(pc + 4));
+	const uint32_t header = q.x;
+	const uint32_t brush = header & kHdrBrushMask;
+	const uint32_t op = (header >> kHdrOpShift) & 0xFu;
+	const uint32_t slot = (header >> kHdrSlotShift) & 0xFFu;
+	uint32_t code;
+	float value;
+	param = 0.0f;
+	if (brush != kBrushNone)
+	{
+		const uint32_t xform = (header >> kHdrXformShift) & 3u;
+		float lx = x, ly = y, lz = z;
+		float4 tail = m0;
+		if (xform == kXformMatrix)
+		{
+			lx = (m0.x * x + m0.w * y) + (m1.z * z + m2.y);
+			ly = (m0.y * x + m1.x * y) + (m1.w * z + m2.z);
+			lz = (m0.z * x + m1.y * y) + (m2.x * z + m2.w);
+			tail = m3;
+		}
+		else if (xform == kXformOffset)
+		{
+			lx = x + m0.x;
+			ly = y + m0.y;
+			lz = z + m0.z;
+			tail = m1;
+		}
+		const float p[3] = { __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w) };
+		float d = sdf::Brush(brush, p, lx, ly, lz);
+		if (header & kHdrTailBit)
+		{
+			if (header & kHdrScaleBit) d = d * tail.x;
+			param = tail.y;
+		}
+		value = d;
+		if (op == kOpPush) code = kFoldPush;
+		else if (op == kOpUnion) code = kFoldMin;
+		else if (op == kOpInter) code = kFoldMax;
+		else if (op == kOpDiff) { code = kFoldMax; value = -d; } // Diff(l, r) = fmaxf(l, -r)
+		else code = kFoldBlendUnion + (op - kOpBlendUnion);
+	}
+	else
+	{
+		value = __uint_as_float(q.y);
+		code = op == kOpFlate ? kFoldFlate : op == kOpStop ? kFoldNop : kFoldStackOp;
+	}
+	step = make_uint2(code | (slot << 8) | (op << 16), __float_as_uint(value));
+}
+
+// Clamp x -> min(max(x, lo), hi) as a value; Then() composes "this first, g second".
+struct Clamp
+{
+	float lo, hi;
+	__device__ __forceinline__ void Then(float glo, float ghi)
+	{
+		lo = fminf(fmaxf(lo, glo), ghi);
+		hi = fminf(fmaxf(hi, glo), ghi);
+	}
+};
+
+// Composes the steps [begin, end) that this thread holds of a chain into `c`; returns false when a step is not a clamp
+// (blend, flate, a push / stack operator that was not collapsed).  `first` is the chain's opening push (a constant).
+__device__ __forceinline__ bool ComposeShare(const uint2* steps, uint32_t begin, uint32_t end, uint32_t first, Clamp& c)
+{
+	bool clamps_only = true;
+	for (uint32_t i = begin; i < end; ++i)
+	{
+		const uint32_t code = steps[i].x & 0xFFu;
+		const float v = __uint_as_float(steps[i].y);
+		if (code == kFoldMin) c.Then(-INFINITY, v);
+		else if (code == kFoldMax) c.Then(v, INFINITY);
+		else if (code == kFoldPush && i == first) c.Then(v, v);
+		else if (code != kFoldNop) clamps_only = false;
+	}
+	return clamps_only;
+}
+
+// The step a collapsed operand becomes in its parent chain: parent = op(parent, value).
+__device__ __forceinline__ void CollapseInto(uint2* steps, float* params, uint32_t at, float value)
+{
+	const uint32_t op = steps[at].x >> 16;
+	const float threshold = __uint_as_float(steps[at].y);
+	uint32_t code;
+	if (op == kOpUnion) code = kFoldMin;
+	else if (op == kOpInter) code = kFoldMax;
+	else if (op == kOpDiff) { code = kFoldMax; value = -value; }
+	else code = kFoldBlendUnion + (op - kOpBlendUnion);
+	steps[at] = make_uint2(code | (kNoSlot << 8) | (op << 16), __float_as_uint(value));
+	params[at] = threshold;
+}
+
+// GROUP = 32: the calling warp works alone (tid = lane; `steps`, `params`, `share`, `marks`, `result_out` are its own
+// slices of the scratch); GROUP = kLongThreads: the whole block.  Every thread of the group must call; all get the value.
+//
+// The fold, after the brush distances are in `steps`:
+//   a. operands nested two deep (pushed with spill slot 1; anything deeper sits inside them) are folded by the thread
+//      that owns their first step and collapse into one step of the chain above;
+//   b. the operands of the main chain (slot 0) are then plain chains.  Their k-th opening push pairs with the k-th
+//      closing operator, so both are listed in order; short ones are folded by one thread each, long ones (a whole town
+//      united into one right-hand operand, seaside_town.lua:106) by the whole group: min / max steps are clamps, clamps
+//      compose associatively, every thread composes a contiguous share and thread 0 the shares in order;
+//   c. the main chain is reduced the same way.
+// min and max select one of their arguments, so every value is the sequential one bit for bit; chains with a blend or
+// flate step are walked by one thread instead.
+template <int GROUP>
+__device__ __forceinline__ float GroupEvalLong(const uint4* __restrict__ program, uint32_t count, float x, float y, float z,
+	uint2* steps, float* params, float2* share, uint32_t* marks, float* result_out, int capacity)
+{
+	const int tid = GROUP == 32 ? int(threadIdx.x & 31) : int(threadIdx.x);
+	auto sync = [] { if (GROUP == 32) __syncwarp(); else __syncthreads(); };
+	const uint32_t* __restrict__ table = reinterpret_cast<const uint32_t*>(program) - ((count + 3u) & ~3u);
+	if (count > uint32_t(capacity))
+	{
+		// larger than the scratch: rounds of `capacity` steps, folded one after the other by the first thread
+		float acc = 0.0f;
+		float stack[kMaxStackSlots];
+		for (uint32_t base = 0; base < count; base += uint32_t(capacity))
+		{
+			const uint32_t n = min(uint32_t(capacity), count - base);
+			for (uint32_t i = tid; i < n; i += GROUP) LongStep(program + __ldg(&table[base + i]), x, y, z, steps[i], params[i]);
+			sync();
+			if (tid == 0)
+			{
+				for (uint32_t i = 0; i < n; ++i) FoldStep(steps[i].x, __uint_as_float(steps[i].y), params[i], acc, stack);
+				*result_out = acc;
+			}
+			sync();
+		}
+		return *result_out;
+	}
+	const uint32_t n = count;
+	for (uint32_t i = tid; i < n; i += GROUP) LongStep(program + __ldg(&table[i]), x, y, z, steps[i], params[i]);
+	sync();
+
+	// a. operands two deep
+	for (uint32_t i = tid; i < n; i += GROUP)
+	{
+		if ((steps[i].x & 0xFFFFu) != (kFoldPush | (1u << 8))) continue;
+		float acc = __uint_as_float(steps[i].y);
+		float stack[kMaxStackSlots];
+		uint32_t j = i + 1;
+		for (; j < n; ++j)
+		{
+			const uint32_t word = steps[j].x;
+			if ((word & 0xFFFFu) == (kFoldStackOp | (1u << 8))) break;
+			FoldStep(word, __uint_as_float(steps[j].y), params[j], acc, stack);
+		}
+		if (j >= n) continue;
+		for (uint32_t k = i; k < j; ++k) steps[k].x = kFoldNop | (kNoSlot << 8);
+		CollapseInto(steps, params, j, acc);
+	}
+	sync();
+
+	// b. operands of the main chain: ordered lists of their opening pushes and closing operators.  `marks` holds, per
+	// thread, the number of openings (low half) and closings (high half) in its contiguous share -> exclusive prefix.
+	const uint32_t per = (n + GROUP - 1) / GROUP;
+	const uint32_t lo_i = min(n, uint32_t(tid) * per), hi_i = min(n, uint32_t(tid + 1) * per);
+	uint32_t mine = 0;
+	for (uint32_t i = lo_i; i < hi_i; ++i)
+	{
+		const uint32_t key = steps[i].x & 0xFFFFu;
+		mine += (key == (kFoldPush | (0u << 8)) ? 1u : 0u) + (key == (kFoldStackOp | (0u << 8)) ? 0x10000u : 0u);
+	}
+	marks[tid] = mine;
+	sync();
+	uint32_t before = 0, total = 0;
+	for (int t = 0; t < GROUP; ++t) // GROUP <= 256 adds from shared memory: a fraction of a microsecond
+	{
+		const uint32_t m = marks[t];
+		if (t < tid) before += m;
+		total += m;
+	}
+	sync();
+	// the lists reuse `share` (x: position of the k-th opening, y: of the k-th closing), as bit patterns
+	const uint32_t operands = min(total & 0xFFFFu, total >> 16);
+	{
+		uint32_t open_rank = before & 0xFFFFu, close_rank = before >> 16;
+		for (uint32_t i = lo_i; i < hi_i; ++i)
+		{
+			const uint32_t key = steps[i].x & 0xFFFFu;
+			if (key == (kFoldPush | (0u << 8)) && open_rank < uint32_t(GROUP)) share[open_rank++].x = __uint_as_float(i);
+			else if (key == (kFoldStackOp | (0u << 8)) && close_rank < uint32_t(GROUP)) share[close_rank++].y = __uint_as_float(i);
+		}
+	}
+	sync();
+	constexpr uint32_t kShortOperand = 48;
+	bool walk_all = operands > uint32_t(GROUP); // more operands than list entries: one thread walks the whole program
+	uint32_t my_open = 0, my_close = 0;
+	if (!walk_all && uint32_t(tid) < operands)
+	{
+		my_open = __float_as_uint(share[tid].x);
+		my_close = __float_as_uint(share[tid].y);
+		if (my_close <= my_open) walk_all = true; // malformed pairing
+	}
+	walk_all = GROUP == 32 ? __any_sync(0xFFFFFFFFu, walk_all) : (__syncthreads_or(walk_all ? 1 : 0) != 0);
+	if (!walk_all)
+	{
+		// short operands: one thread each
+		if (uint32_t(tid) < operands && my_close - my_open <= kShortOperand)
+		{
+			float acc = __uint_as_float(steps[my_open].y);
+			float stack[kMaxStackSlots];
+			for (uint32_t j = my_open + 1; j < my_close; ++j) FoldStep(steps[j].x, __uint_as_float(steps[j].y), params[j], acc, stack);
+			for (uint32_t k = my_open; k < my_close; ++k) steps[k].x = kFoldNop | (kNoSlot << 8);
+			CollapseInto(steps, params, my_close, acc);
+		}
+		// long operands: the whole group, one after the other (the lists are read before `share` is reused)
+		uint32_t long_open[4], long_close[4];
+		uint32_t long_count = 0;
+		for (uint32_t k = 0; k < operands; ++k)
+		{
+			const uint32_t o = __float_as_uint(share[k].x), c = __float_as_uint(share[k].y);
+			if (c > o && c - o > kShortOperand)
+			{
+				if (long_count < 4u)
+				{
+					long_open[long_count] = o;
+					long_close[long_count] = c;
+				}
+				long_count++;
+			}
+		}
+		sync();
+		for (uint32_t g = 0; g < min(long_count, 4u); ++g)
+		{
+			const uint32_t o = long_open[g], c = long_close[g], len = c - o;
+			const uint32_t part = (len + GROUP - 1) / GROUP;
+			const uint32_t b0 = o + min(len, uint32_t(tid) * part), b1 = o + min(len, uint32_t(tid + 1) * part);
+			Clamp mineclamp = { -INFINITY, INFINITY };
+			const bool clamps_only = ComposeShare(steps, b0, b1, o, mineclamp);
+			share[tid] = make_float2(mineclamp.lo, mineclamp.hi);
+			const bool all_clamps = GROUP == 32 ? __all_sync(0xFFFFFFFFu, clamps_only) : (__syncthreads_and(clamps_only ? 1 : 0) != 0);
+			sync();
+			if (tid == 0)
+			{
+				float value;
+				if (all_clamps)
+				{
+					Clamp t = { -INFINITY, INFINITY };
+					for (int k = 0; k < GROUP; ++k) t.Then(share[k].x, share[k].y);
+					value = t.hi; // the chain opens with a constant, so lo == hi
+				}
+				else
+				{
+					float acc = __uint_as_float(steps[o].y);
+					float stack[kMaxStackSlots];
+					for (uint32_t j = o + 1; j < c; ++j) FoldStep(steps[j].x, __uint_as_float(steps[j].y), params[j], acc, stack);
+					value = acc;
+				}
+				CollapseInto(steps, params, c, value);
+			}
+			for (uint32_t k = b0; k < b1; ++k) steps[k].x = kFoldNop | (kNoSlot << 8);
+			sync();
+		}
+		if (long_count > 4u) walk_all = true; // (uniform: every thread counted the same lists)
+	}
+	sync();
+
+	// c. the main chain
+	Clamp chain = { -INFINITY, INFINITY };
+	const bool clamps_only = walk_all ? false : ComposeShare(steps, lo_i, hi_i, 0u, chain);
+	share[tid] = make_float2(chain.lo, chain.hi);
+	const bool all_clamps = GROUP == 32 ? __all_sync(0xFFFFFFFFu, clamps_only) : (__syncthreads_and(clamps_only ? 1 : 0) != 0);
+	sync();
+	if (tid == 0)
+	{
+		float acc = 0.0f;
+		if (all_clamps)
+		{
+			Clamp t = { -INFINITY, INFINITY };
+			for (int k = 0; k < GROUP; ++k) t.Then(share[k].x, share[k].y);
+			acc = fminf(fmaxf(acc, t.lo), t.hi);
+		}
+		else
+		{
+			float stack[kMaxStackSlots];
+			for (uint32_t i = 0; i < n; ++i) FoldStep(steps[i].x, __uint_as_float(steps[i].y), params[i], acc, stack);
+		}
+		*result_out = acc;
+	}
+	sync();
+	return *result_out;
+}
+
 template <int S>
 struct MaterialRegs
 {

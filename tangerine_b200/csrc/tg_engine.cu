@@ -29,9 +29,15 @@
 #include <cuda_runtime.h>
 
 #include "tg_device.cuh"
+#include "tg_bricks.cuh"
 
 namespace tg
 {
+
+// tg_fast.cu: the brick and lattice kernels of the opt-in fast build
+int LaunchMeshBricksFast(const void* mesh_params, unsigned blocks, void* stream);
+int LaunchLatticeFast(const void* device_model, const void* device_grid, float* out, unsigned tiles_x, unsigned tiles_y, unsigned tile_count, unsigned long long* counters, void* stream);
+int FastBrickBlocksPerSm();
 
 #define TG_CUDA(call)                                                                                           \
 	do                                                                                                          \
@@ -47,485 +53,7 @@ namespace tg
 		}                                                                                                       \
 	} while (0)
 
-constexpr int kBrick = 8;                 // cells per brick edge
-constexpr int kTile = kBrick + 1;         // lattice samples per brick edge
-constexpr int kTileSamples = kTile * kTile * kTile; // 729
-constexpr int kTilePadded = 736;
-constexpr int kBrickWarps = 4;            // warps per block of the brick kernels; every warp works alone
-constexpr int kBrickThreads = kBrickWarps * 32;
-constexpr int kMaxPending = 192;          // (node, box) pairs waiting in a warp's box resolution
-constexpr int kMaxFinal = 32;             // resolved (node, box) pairs per evaluation batch (one per lane)
-constexpr uint32_t kResolvedBit = 0x80000000u;
-#ifndef TG_LANE_SAMPLES
-#define TG_LANE_SAMPLES 2
-#endif
-constexpr int kLaneSamples = TG_LANE_SAMPLES; // samples interpreted per lane per dispatch
-
-enum Counter
-{
-	kCntTmpVertices = 0,
-	kCntSamples = 1,
-	kCntFlops = 2,
-	kCntListA = 3,
-	kCntListB = 4,
-	kCntTotalVertices = 5,
-	kCntTotalQuads = 6,
-	kCntHalo = 7,
-	kCntBrickCursor = 8,
-	kCntAttrCursor = 9,
-	kCntCount = 16
-};
-
-struct MeshParams
-{
-	DeviceModel model;
-	DeviceGrid grid;
-	const uint32_t* bricks;
-	const unsigned long long* brick_count; // device: length of `bricks` (written by CullResolveKernel)
-	uint32_t brick_capacity;
-	unsigned long long* bitmap; // one bit per cell, rows padded to 64 cells; layer 0 = cell layer k_base
-	uint32_t row_words;
-	uint32_t k_base;
-	uint32_t k_own_begin, k_own_end;
-	float4* tmp_pos;            // xyz + orientation bits
-	unsigned long long* tmp_key; // bit index in the bitmap
-	uint32_t tmp_capacity;
-	unsigned long long* counters;
-};
-
-// ------------------------------------------------------------------------------------------------
-// K1 + K2: evaluate one brick's 9^3 lattice tile and extract its surface-nets vertices.
-// One WARP owns one brick from start to finish, so the kernel has no block-wide barrier at all: a warp that is
-// waiting on an octree or instruction fetch is covered by the other resident warps, whatever phase they are in.
-// ------------------------------------------------------------------------------------------------
-
-struct WarpTile
-{
-	float tile[kTilePadded];          // sample values
-	uint16_t order[kTilePadded];      // samples (li | lj << 4 | lk << 8) grouped by octree node; later the brick's active cell list
-	uint32_t pend_node[kMaxPending];  // box resolution: (node to descend from, sample box) still to be resolved
-	uint32_t pend_box[kMaxPending];
-	uint32_t fin_node[kMaxFinal];     // resolved (octree node, sample box) pairs of the current evaluation batch
-	uint32_t fin_box[kMaxFinal];
-	uint32_t fin_start[kMaxFinal + 1]; // offset of each pair's samples in `order`
-	uint16_t rows[kTile * kTile + 1];  // sign bits of the tile, one word per row of 9 samples
-};
-
-// A sample box of the tile: inclusive index ranges, four bits each.
-__device__ __forceinline__ uint32_t PackBox(int x0, int x1, int y0, int y1, int z0, int z1)
-{
-	return uint32_t(x0) | (uint32_t(x1) << 4) | (uint32_t(y0) << 8) | (uint32_t(y1) << 12) | (uint32_t(z0) << 16) | (uint32_t(z1) << 20);
-}
-__device__ __forceinline__ int BoxSamples(uint32_t b)
-{
-	return (int((b >> 4) & 15u) - int(b & 15u) + 1) * (int((b >> 12) & 15u) - int((b >> 8) & 15u) + 1) * (int((b >> 20) & 15u) - int((b >> 16) & 15u) + 1);
-}
-
-// First index in [a, b + 1] whose lattice coordinate is > pivot (SDFOctree::Descend's strict test, :1806-1817);
-// origin + float(i) * step is monotonic in i, so the samples below it take the lower octant and the rest the upper.
-__device__ __forceinline__ int SplitIndex(float origin, float step, uint32_t base, int a, int b, float pivot)
-{
-	int i = a;
-	while (i <= b && !(LatticeCoord(origin, step, base + uint32_t(i)) > pivot)) ++i;
-	return i;
-}
-
-// Evaluates the lattice samples (li < ni, lj < nj, kmin <= lk < nk) of a tile whose corner sample has lattice
-// index (i0, j0, k0) into w.tile.
-//
-// Which program a sample runs is decided by SDFOctree::Descend (sdf_evaluator.cpp:1801-1835), and the points that
-// end at one node form a box.  So the tile is not descended sample by sample: the warp resolves BOXES.  A pending
-// (node, box) pair follows the octree while the whole box stays in one octant; where a pivot plane cuts it, it
-// splits into up to eight boxes (monotonic lattice coordinates: one split index per axis).  With leaves of >= 16
-// cells an 8-cell tile is cut at most once per axis, so a brick resolves in two or three lane-parallel rounds; coarse
-// grids (leaves smaller than a brick) just take more rounds.  Resolved pairs are sorted by node, their samples are
-// written to `order`, and every distinct node gets ONE run of interpreter dispatches over all its samples,
-// kLaneSamples per lane -- the only instantiation of the interpreter in the kernel (instruction-cache footprint).
-__device__ __forceinline__ void EvaluateTile(WarpTile& w, const DeviceModel& model, const DeviceGrid& grid,
-	uint32_t i0, uint32_t j0, uint32_t k0, int ni, int nj, int nk, int kmin, unsigned long long* counters)
-{
-	const int lane = threadIdx.x & 31;
-	const unsigned lanes_below = (1u << lane) - 1u;
-	if (lane == 0)
-	{
-		w.pend_node[0] = 0u; // the octree root
-		w.pend_box[0] = PackBox(0, ni - 1, 0, nj - 1, kmin, nk - 1);
-	}
-	__syncwarp();
-	int pend = 1, fin = 0;
-	for (;;)
-	{
-		// boxes resolved this round: as many as fit the lists (a split adds at most seven entries, a box at most one pair)
-		// A nearly full list is worked depth-first, one box at a time: a box then adds at most 7 entries per octree level
-		// below it, and 96 spare entries cover octrees 13 levels deep (the write below traps rather than overflow).
-		const int take = min(min(32, pend), max(1, (kMaxPending - 96 - pend) / 7));
-		if (fin > 0 && (pend == 0 || fin + take > kMaxFinal))
-		{
-			// ---- evaluation batch: sort the pairs by node, lay their samples out in `order`, run each node once ----
-			uint32_t node_e = lane < fin ? w.fin_node[lane] : 0xFFFFFFFFu;
-			uint32_t box_e = lane < fin ? w.fin_box[lane] : 0u;
-			int rank = 0;
-#pragma unroll 1
-			for (int j = 0; j < fin; ++j)
-			{
-				const uint32_t other = __shfl_sync(0xFFFFFFFFu, node_e, j);
-				rank += (other < node_e || (other == node_e && j < lane)) ? 1 : 0;
-			}
-			__syncwarp();
-			if (lane < fin)
-			{
-				w.fin_node[rank] = node_e;
-				w.fin_box[rank] = box_e;
-			}
-			__syncwarp();
-			node_e = lane < fin ? w.fin_node[lane] : 0xFFFFFFFFu;
-			box_e = lane < fin ? w.fin_box[lane] : 0u;
-			const uint32_t size_e = lane < fin ? uint32_t(BoxSamples(box_e)) : 0u;
-			uint32_t incl = size_e;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1)
-			{
-				const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-				if (lane >= o) incl += v;
-			}
-			const uint32_t start_e = incl - size_e;
-			if (lane < fin) w.fin_start[lane] = start_e;
-			if (lane == 31) w.fin_start[fin] = incl; // the batch total closes the last run
-			const uint32_t before = __shfl_up_sync(0xFFFFFFFFu, node_e, 1);
-			unsigned heads = __ballot_sync(0xFFFFFFFFu, lane < fin && (lane == 0 || before != node_e));
-			const uint32_t flops = size_e ? size_e * __ldg(&model.nodes[node_e].flops) : 0u;
-			const uint32_t flops_total = __reduce_add_sync(0xFFFFFFFFu, flops);
-			if (lane == 31)
-			{
-				atomicAdd(&counters[kCntSamples], (unsigned long long)incl);
-				atomicAdd(&counters[kCntFlops], (unsigned long long)flops_total);
-			}
-#pragma unroll 1
-			for (int e = 0; e < fin; ++e)
-			{
-				const uint32_t b = __shfl_sync(0xFFFFFFFFu, box_e, e);
-				const int first = int(__shfl_sync(0xFFFFFFFFu, start_e, e));
-				const int x0 = int(b & 15u), y0 = int((b >> 8) & 15u), z0 = int((b >> 16) & 15u);
-				const int dx = int((b >> 4) & 15u) - x0 + 1, dy = int((b >> 12) & 15u) - y0 + 1, dz = int((b >> 20) & 15u) - z0 + 1;
-				const int layer = dx * dy, n = layer * dz;
-				const float inv_layer = 1.0f / float(layer), inv_dx = 1.0f / float(dx);
-				for (int u = lane; u < n; u += 32)
-				{
-					// u < 729 and the divisors are <= 81: (u + 0.5) / d is at least 0.5 / 81 away from an integer, far more than the rounding
-					const int c = __float2int_rd((float(u) + 0.5f) * inv_layer);
-					const int r = u - c * layer;
-					const int q = __float2int_rd((float(r) + 0.5f) * inv_dx);
-					w.order[first + u] = uint16_t((x0 + r - q * dx) | ((y0 + q) << 4) | ((z0 + c) << 8)); // li | lj << 4 | lk << 8
-				}
-			}
-			__syncwarp();
-			while (heads)
-			{
-				const int g = __ffs(heads) - 1;
-				heads &= heads - 1u;
-				const int first = int(w.fin_start[g]);
-				const int total = int(w.fin_start[heads ? __ffs(heads) - 1 : fin]) - first;
-				const uint4* program = model.interp + (__ldg(&model.nodes[w.fin_node[g]].interp_offset) >> 2);
-				for (int done = 0; done < total; done += 32 * kLaneSamples)
-				{
-					const int count_here = min(total - done, 32 * kLaneSamples);
-					float px[kLaneSamples], py[kLaneSamples], pz[kLaneSamples], d[kLaneSamples];
-					int sample[kLaneSamples];
-#pragma unroll
-					for (int q = 0; q < kLaneSamples; ++q)
-					{
-						const int idx = lane + 32 * q;
-						const uint32_t code = w.order[first + done + (idx < count_here ? idx : 0)];
-						const uint32_t li = code & 15u, lj = (code >> 4) & 15u, lk = code >> 8;
-						sample[q] = idx < count_here ? int((lk * kTile + lj) * kTile + li) : -1;
-						px[q] = LatticeCoord(grid.x, grid.dx, i0 + li);
-						py[q] = LatticeCoord(grid.y, grid.dy, j0 + lj);
-						pz[q] = LatticeCoord(grid.z, grid.dz, k0 + lk);
-					}
-					EvalInterp<kLaneSamples>(program, px, py, pz, d);
-#pragma unroll
-					for (int q = 0; q < kLaneSamples; ++q)
-					{
-						if (sample[q] >= 0) w.tile[sample[q]] = d[q];
-					}
-				}
-			}
-			__syncwarp();
-			fin = 0;
-		}
-		if (pend == 0) break;
-
-		// ---- one round of box resolution: lane l takes the l-th pending pair from the top of the list ----
-		const bool mine = lane < take;
-		uint32_t node = 0u, box = 0u;
-		if (mine)
-		{
-			node = w.pend_node[pend - 1 - lane];
-			box = w.pend_box[pend - 1 - lane];
-		}
-		__syncwarp();
-		pend -= take;
-		bool resolved = false;
-		int x0 = 0, x1 = 0, y0 = 0, y1 = 0, z0 = 0, z1 = 0, xs = 0, ys = 0, zs = 0, parts = 0;
-		if (mine)
-		{
-			if (node & kResolvedBit)
-			{
-				node &= ~kResolvedBit; // an empty octant met by a split: Descend stops at the parent (:1828-1834)
-				resolved = true;
-			}
-			else
-			{
-				x0 = int(box & 15u), x1 = int((box >> 4) & 15u), y0 = int((box >> 8) & 15u), y1 = int((box >> 12) & 15u), z0 = int((box >> 16) & 15u), z1 = int((box >> 20) & 15u);
-				const float lox = LatticeCoord(grid.x, grid.dx, i0 + x0), loy = LatticeCoord(grid.y, grid.dy, j0 + y0), loz = LatticeCoord(grid.z, grid.dz, k0 + z0);
-				const float hix = LatticeCoord(grid.x, grid.dx, i0 + x1), hiy = LatticeCoord(grid.y, grid.dy, j0 + y1), hiz = LatticeCoord(grid.z, grid.dz, k0 + z1);
-				for (;;)
-				{
-					const float4 head = __ldg(reinterpret_cast<const float4*>(&model.nodes[node]));
-					if (__float_as_uint(head.w) != 0u)
-					{
-						resolved = true;
-						break;
-					}
-					const int olo = (lox > head.x ? 1 : 0) | (loy > head.y ? 2 : 0) | (loz > head.z ? 4 : 0);
-					const int ohi = (hix > head.x ? 1 : 0) | (hiy > head.y ? 2 : 0) | (hiz > head.z ? 4 : 0);
-					if (olo != ohi)
-					{
-						// a pivot plane cuts the box: lower part [a, split - 1], upper part [split, b] on every axis (either may be empty)
-						xs = ((olo ^ ohi) & 1) ? SplitIndex(grid.x, grid.dx, i0, x0, x1, head.x) : ((olo & 1) ? x0 : x1 + 1);
-						ys = ((olo ^ ohi) & 2) ? SplitIndex(grid.y, grid.dy, j0, y0, y1, head.y) : ((olo & 2) ? y0 : y1 + 1);
-						zs = ((olo ^ ohi) & 4) ? SplitIndex(grid.z, grid.dz, k0, z0, z1, head.z) : ((olo & 4) ? z0 : z1 + 1);
-						parts = ((xs > x0 ? 1 : 0) + (xs <= x1 ? 1 : 0)) * ((ys > y0 ? 1 : 0) + (ys <= y1 ? 1 : 0)) * ((zs > z0 ? 1 : 0) + (zs <= z1 ? 1 : 0));
-						break;
-					}
-					const int32_t child = __ldg(&model.nodes[node].children[olo]);
-					if (child < 0)
-					{
-						resolved = true;
-						break;
-					}
-					node = uint32_t(child);
-				}
-			}
-		}
-		const unsigned done_mask = __ballot_sync(0xFFFFFFFFu, resolved);
-		if (resolved)
-		{
-			const int slot = fin + __popc(done_mask & lanes_below);
-			w.fin_node[slot] = node;
-			w.fin_box[slot] = box;
-		}
-		fin += __popc(done_mask);
-		int incl = parts;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1)
-		{
-			const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-			if (lane >= o) incl += v;
-		}
-		const int added = __shfl_sync(0xFFFFFFFFu, incl, 31);
-		if (parts)
-		{
-			int at = pend + incl - parts;
-#pragma unroll 1
-			for (int o = 0; o < 8; ++o)
-			{
-				const int ax = (o & 1) ? xs : x0, bx = (o & 1) ? x1 : xs - 1;
-				const int ay = (o & 2) ? ys : y0, by = (o & 2) ? y1 : ys - 1;
-				const int az = (o & 4) ? zs : z0, bz = (o & 4) ? z1 : zs - 1;
-				if (ax > bx || ay > by || az > bz) continue;
-				const int32_t child = __ldg(&model.nodes[node].children[o]);
-				if (at >= kMaxPending) __trap();
-				w.pend_node[at] = child < 0 ? (node | kResolvedBit) : uint32_t(child);
-				w.pend_box[at] = PackBox(ax, bx, ay, by, az, bz);
-				++at;
-			}
-		}
-		pend += added;
-		__syncwarp();
-	}
-}
-
-// Loads the eight corner samples of cell c (0..511) of the brick in the reference's corner numbering
-// (get_voxel_corner_grid_positions, surface_nets.cpp:632-646) and returns the `>= 0` mask.
-__device__ __forceinline__ unsigned CellCorners(const WarpTile& w, int c, float (&v)[8])
-{
-	const int ci = c & 7, cj = (c >> 3) & 7, ck = c >> 6;
-	const float* t = w.tile + (ck * kTile + cj) * kTile + ci;
-	v[0] = t[0];
-	v[1] = t[1];
-	v[2] = t[kTile + 1];
-	v[3] = t[kTile];
-	v[4] = t[kTile * kTile];
-	v[5] = t[kTile * kTile + 1];
-	v[6] = t[kTile * kTile + kTile + 1];
-	v[7] = t[kTile * kTile + kTile];
-	// is_scalar_positive is `scalar >= isovalue` (:733-735): -0.0 is positive, NaN is negative
-	unsigned signs = 0;
-#pragma unroll
-	for (int k = 0; k < 8; ++k) signs |= (v[k] >= 0.0f ? 1u : 0u) << k;
-	return signs;
-}
-
-__global__ void __launch_bounds__(kBrickThreads, 8) MeshBricksKernel(const MeshParams p)
-{
-	__shared__ WarpTile tiles[kBrickWarps];
-	WarpTile& w = tiles[threadIdx.x >> 5];
-	const DeviceGrid& grid = p.grid;
-	const int lane = threadIdx.x & 31;
-
-	const float bbminx = grid.x, bbminy = grid.y, bbminz = grid.z;
-	const float bbmaxx = __fadd_rn(grid.x, __fmul_rn(float(grid.sx), grid.dx));
-	const float bbmaxy = __fadd_rn(grid.y, __fmul_rn(float(grid.sy), grid.dy));
-	const float bbmaxz = __fadd_rn(grid.z, __fmul_rn(float(grid.sz), grid.dz));
-	unsigned char* bitmap_bytes = reinterpret_cast<unsigned char*>(p.bitmap);
-	const uint32_t brick_count = uint32_t(min(*p.brick_count, (unsigned long long)p.brick_capacity));
-
-	for (;;)
-	{
-		// persistent warps pull bricks from one device-wide cursor
-		uint32_t item = 0;
-		if (lane == 0) item = uint32_t(atomicAdd(&p.counters[kCntBrickCursor], 1ull));
-		item = __shfl_sync(0xFFFFFFFFu, item, 0);
-		if (item >= brick_count) break;
-
-		const uint32_t brick = __ldg(&p.bricks[item]);
-		const uint32_t bx = brick & 1023u, by = (brick >> 10) & 1023u, bz = (brick >> 20) & 1023u;
-		const uint32_t i0 = bx * kBrick, j0 = by * kBrick, k0 = bz * kBrick;
-		const int ni = int(min(uint32_t(kTile), grid.sx + 1 - i0));
-		const int nj = int(min(uint32_t(kTile), grid.sy + 1 - j0));
-		// The slab owns cell layers [k_own_begin, k_own_end) and also classifies the halo layer k_base below it; a
-		// brick that sticks out of that window only evaluates the sample layers the window needs.
-		const int nk = int(min(uint32_t(kTile), p.k_own_end + 1 - k0));
-		const int kmin = p.k_base > k0 ? int(p.k_base - k0) : 0;
-
-		EvaluateTile(w, p.model, grid, i0, j0, k0, ni, nj, nk, kmin, p.counters);
-
-		// Classification: sign bits of FirstLoopInnerThunk (surface_nets.cpp:864-907).  is_scalar_positive is
-		// `scalar >= isovalue` (:733-735: -0.0 is positive, NaN is negative), and a cell is active when its eight corners
-		// do not agree (:903-907).  The signs of a sample row (9 samples along x) are packed into one word first; a lane
-		// then classifies a whole row of 8 cells with a dozen bit operations on the four sample rows around it, and the
-		// result IS the row's byte of the active-cell bitmap.
-		for (int r = lane; r < kTile * kTile; r += 32)
-		{
-			const float* t = w.tile + r * kTile;
-			uint32_t bits = 0;
-#pragma unroll
-			for (int i = 0; i < kTile; ++i) bits |= (t[i] >= 0.0f ? 1u : 0u) << i;
-			w.rows[r] = uint16_t(bits);
-		}
-		__syncwarp();
-		int emit_total = 0;
-		const uint32_t cells_x = min(uint32_t(kBrick), grid.sx - i0);
-#pragma unroll 1
-		for (int round = 0; round < 2; ++round)
-		{
-			const int cr = round * 32 + lane; // cell row: cj = cr & 7, ck = cr >> 3
-			const int cj = cr & 7, ck = cr >> 3;
-			const uint32_t gj = j0 + cj, gk = k0 + ck;
-			const uint32_t r00 = w.rows[ck * kTile + cj], r01 = w.rows[ck * kTile + cj + 1];
-			const uint32_t r10 = w.rows[(ck + 1) * kTile + cj], r11 = w.rows[(ck + 1) * kTile + cj + 1];
-			const uint32_t all = r00 & r01 & r10 & r11, any = r00 | r01 | r10 | r11;
-			uint32_t active = ~((all & (all >> 1)) | ~(any | (any >> 1))) & ((1u << cells_x) - 1u);
-			// the slab owns cell layers [k_own_begin, k_own_end) and classifies the halo layer k_base below it
-			if (!(gj < grid.sy && gk < p.k_own_end && ck >= kmin)) active = 0u;
-			if (active) bitmap_bytes[(size_t(gk - p.k_base) * grid.sy + gj) * (size_t(p.row_words) * 8u) + bx] = (unsigned char)active;
-			uint32_t emit = gk >= p.k_own_begin ? active : 0u; // the halo layer is classified but owned by the slab below
-			const int count = __popc(emit);
-			int incl = count;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1)
-			{
-				const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-				if (lane >= o) incl += v;
-			}
-			int at = emit_total + incl - count;
-			while (emit)
-			{
-				w.order[at++] = uint16_t(cr * kBrick + __ffs(emit) - 1);
-				emit &= emit - 1u;
-			}
-			emit_total += __shfl_sync(0xFFFFFFFFu, incl, 31);
-		}
-		__syncwarp();
-		if (emit_total == 0) continue;
-
-		uint32_t out_base = 0;
-		if (lane == 0) out_base = uint32_t(atomicAdd(&p.counters[kCntTmpVertices], (unsigned long long)emit_total));
-		out_base = __shfl_sync(0xFFFFFFFFu, out_base, 0);
-
-		// Vertices of the active cells, densely packed over the lanes: :920-965
-		for (int e = lane; e < emit_total; e += 32)
-		{
-			const int c = w.order[e];
-			const int ci = c & 7, cj = (c >> 3) & 7, ck = c >> 6;
-			const uint32_t gi = i0 + ci, gj = j0 + cj, gk = k0 + ck;
-			float v[8];
-			CellCorners(w, c, v);
-			const float fi = float(gi), fj = float(gj), fk = float(gk);
-			const float gx[8] = { fi, fi + 1.f, fi + 1.f, fi, fi, fi + 1.f, fi + 1.f, fi };
-			const float gy[8] = { fj, fj, fj + 1.f, fj + 1.f, fj, fj, fj + 1.f, fj + 1.f };
-			const float gz[8] = { fk, fk, fk, fk, fk + 1.f, fk + 1.f, fk + 1.f, fk + 1.f };
-			const int e0[12] = { 0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3 }; // edge table :889-901
-			const int e1[12] = { 1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7 };
-			float sx = 0.f, sy = 0.f, sz = 0.f;
-			int n = 0;
-#pragma unroll
-			for (int ed = 0; ed < 12; ++ed)
-			{
-				const float s1 = v[e0[ed]], s2 = v[e1[ed]];
-				if ((s1 >= 0.0f) != (s2 >= 0.0f))
-				{
-					const float t = (0.0f - s1) / (s2 - s1); // :937
-					sx = sx + (gx[e0[ed]] + t * (gx[e1[ed]] - gx[e0[ed]]));
-					sy = sy + (gy[e0[ed]] + t * (gy[e1[ed]] - gy[e0[ed]]));
-					sz = sz + (gz[e0[ed]] + t * (gz[e1[ed]] - gz[e0[ed]]));
-					n++;
-				}
-			}
-			const float count = float(n);
-			const float cx = sx / count, cy = sy / count, cz = sz / count;
-			// :952-965  min + (max - min) * (centre - 0) / (size - 0)
-			const float px = bbminx + (bbmaxx - bbminx) * (cx - 0.f) / (float(grid.sx) - 0.f);
-			const float py = bbminy + (bbmaxy - bbminy) * (cy - 0.f) / (float(grid.sy) - 0.f);
-			const float pz = bbminz + (bbmaxz - bbminz) * (cz - 0.f) / (float(grid.sz) - 0.f);
-			// winding bits for SecondLoopThunk (:1041-1067, :1103-1105): edge (0,4), (3,0), (0,1)
-			const uint32_t orient = (v[4] > v[0] ? 1u : 0u) | (v[0] > v[3] ? 2u : 0u) | (v[1] > v[0] ? 4u : 0u);
-			const uint32_t dst = out_base + uint32_t(e);
-			if (dst < p.tmp_capacity)
-			{
-				p.tmp_pos[dst] = make_float4(px, py, pz, __uint_as_float(orient));
-				p.tmp_key[dst] = ((unsigned long long)(gk - p.k_base) * grid.sy + gj) * ((unsigned long long)p.row_words * 64ull) + gi;
-			}
-		}
-		__syncwarp();
-	}
-}
-
-// Dense lattice dump: one 8^3 tile of samples per warp, written to a (sz+1, sy+1, sx+1) array.
-__global__ void __launch_bounds__(kBrickThreads) LatticeKernel(const DeviceModel model, const DeviceGrid grid, float* __restrict__ out,
-	uint32_t tiles_x, uint32_t tiles_y, uint32_t tile_count, unsigned long long* counters)
-{
-	__shared__ WarpTile tiles[kBrickWarps];
-	WarpTile& w = tiles[threadIdx.x >> 5];
-	const int lane = threadIdx.x & 31;
-	const uint32_t tile = blockIdx.x * kBrickWarps + (threadIdx.x >> 5);
-	if (tile >= tile_count) return;
-	const uint32_t tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, tz = tile / (tiles_x * tiles_y);
-	const uint32_t i0 = tx * kBrick, j0 = ty * kBrick, k0 = tz * kBrick;
-	const uint32_t nx = grid.sx + 1, ny = grid.sy + 1, nz = grid.sz + 1;
-	const int ni = int(min(uint32_t(kBrick), nx - i0)), nj = int(min(uint32_t(kBrick), ny - j0)), nk = int(min(uint32_t(kBrick), nz - k0));
-	EvaluateTile(w, model, grid, i0, j0, k0, ni, nj, nk, 0, counters);
-	if (out == nullptr) return;
-	for (int s = lane; s < kBrick * kBrick * kBrick; s += 32)
-	{
-		const int li = s & 7, lj = (s >> 3) & 7, lk = s >> 6;
-		if (li < ni && lj < nj && lk < nk)
-		{
-			out[(size_t(k0 + lk) * ny + (j0 + lj)) * nx + (i0 + li)] = w.tile[(lk * kTile + lj) * kTile + li];
-		}
-	}
-}
+// (the brick kernel and its helpers live in tg_bricks.cuh, which is also compiled into the fast build, tg_fast.cu)
 
 // ------------------------------------------------------------------------------------------------
 // K0: empty-space culling, driven by the octree's evaluation regions (FlatRegion) instead of the grid.
@@ -579,6 +107,7 @@ struct CullParams
 	uint32_t* flags[kCullLevels];
 	uint32_t dims[kCullLevels][3];     // bricks per axis at each level
 	int level;
+	int long_every_other_level;        // tuning: evaluate long programs at the 128 / 32 / 8-cell levels only
 };
 
 // First lattice index i in [0, last + 1] with LatticeCoord(origin, step, i) > p (last + 1 when there is none).
@@ -707,66 +236,102 @@ __global__ void __launch_bounds__(128) CullRegionInitKernel(const CullParams p)
 			}
 }
 
+// What both item kernels decide first: the sample box of the item's brick inside its region.
+struct ItemBox
+{
+	uint32_t cx, cy, cz, lo_i, hi_i, lo_j, hi_j, lo_k, hi_k;
+	bool live;
+};
+
+__device__ __forceinline__ ItemBox MakeItemBox(const CullParams& p, const CullItem& item, uint32_t width)
+{
+	const DeviceGrid& g = p.grid;
+	ItemBox b;
+	const RegionRange range = p.ranges[item.region];
+	b.cx = item.cell & 1023u, b.cy = (item.cell >> 10) & 1023u, b.cz = (item.cell >> 20) & 1023u;
+	// sample box of this brick (clipped to grid and slab) intersected with the region's sample box
+	b.lo_i = max(b.cx * width, uint32_t(range.a[0])), b.hi_i = min(min((b.cx + 1u) * width, g.sx), uint32_t(range.b[0]));
+	b.lo_j = max(b.cy * width, uint32_t(range.a[1])), b.hi_j = min(min((b.cy + 1u) * width, g.sy), uint32_t(range.b[1]));
+	b.lo_k = max(b.cz * width, uint32_t(range.a[2])), b.hi_k = min(min((b.cz + 1u) * width, g.sz), uint32_t(range.b[2]));
+	b.live = b.lo_i <= b.hi_i && b.lo_j <= b.hi_j && b.lo_k <= b.hi_k;
+	return b;
+}
+
+// Centre and culling threshold of an item's sample box.
+__device__ __forceinline__ void ItemProbe(const DeviceGrid& g, const ItemBox& b, float& x, float& y, float& z, float& threshold)
+{
+	const float lox = LatticeCoord(g.x, g.dx, b.lo_i), loy = LatticeCoord(g.y, g.dy, b.lo_j), loz = LatticeCoord(g.z, g.dz, b.lo_k);
+	const float hix = LatticeCoord(g.x, g.dx, b.hi_i), hiy = LatticeCoord(g.y, g.dy, b.hi_j), hiz = LatticeCoord(g.z, g.dz, b.hi_k);
+	const float ex = hix - lox, ey = hiy - loy, ez = hiz - loz;
+	const float radius = 0.5f * sqrtf(ex * ex + ey * ey + ez * ez);
+	threshold = radius * 1.001f + 1.0e-4f;
+	x = 0.5f * (lox + hix);
+	y = 0.5f * (loy + hiy);
+	z = 0.5f * (loz + hiz);
+}
+
+// The child bricks (one level down) whose sample box still meets the region.
+__device__ __forceinline__ uint32_t ItemChildren(const CullParams& p, const ItemBox& b, uint32_t width, uint32_t (&children)[8])
+{
+	const DeviceGrid& g = p.grid;
+	const uint32_t half = width >> 1;
+	uint32_t n = 0;
+#pragma unroll
+	for (int o = 0; o < 8; ++o)
+	{
+		const uint32_t x = b.cx * 2u + (o & 1), y = b.cy * 2u + ((o >> 1) & 1), z = b.cz * 2u + ((o >> 2) & 1);
+		const bool hit = max(x * half, b.lo_i) <= min((x + 1u) * half, b.hi_i) && max(y * half, b.lo_j) <= min((y + 1u) * half, b.hi_j) &&
+			max(z * half, b.lo_k) <= min((z + 1u) * half, b.hi_k) && x * half < g.sx && y * half < g.sy && z * half < p.cell_k_hi && (z + 1u) * half > p.cell_k_lo;
+		if (hit) children[n++] = x | (y << 10) | (z << 20);
+	}
+	return n;
+}
+
+// Items of regions with short programs: one thread per item.
 __global__ void __launch_bounds__(128) CullLevelKernel(const CullParams p)
 {
 	const uint32_t index = blockIdx.x * blockDim.x + threadIdx.x;
 	const int level = p.level;
-	const uint32_t long_count = min(p.counts[kCullLevels + level], p.long_capacity[level]);
-	const uint32_t count = long_count + min(p.counts[level], p.capacity[level]);
-	if (blockIdx.x * blockDim.x >= count) return; // whole block beyond the lists (warps stay intact below)
+	const uint32_t count = min(p.counts[level], p.capacity[level]);
+	if (blockIdx.x * blockDim.x >= count) return; // whole block beyond the list (warps stay intact below)
 	const DeviceGrid& g = p.grid;
 	const uint32_t width = uint32_t(kBrick) << level;
-	bool live = index < count;
 	CullItem item = { 0u, 0u };
-	uint32_t cx = 0, cy = 0, cz = 0, lo_i = 0, hi_i = 0, lo_j = 0, hi_j = 0, lo_k = 0, hi_k = 0;
-	if (live)
+	ItemBox b = {};
+	if (index < count)
 	{
-		item = index < long_count ? p.long_lists[level][index] : p.lists[level][index - long_count];
-		const RegionRange range = p.ranges[item.region];
-		cx = item.cell & 1023u, cy = (item.cell >> 10) & 1023u, cz = (item.cell >> 20) & 1023u;
-		// sample box of this brick (clipped to grid and slab) intersected with the region's sample box
-		lo_i = max(cx * width, uint32_t(range.a[0])), hi_i = min(min((cx + 1u) * width, g.sx), uint32_t(range.b[0]));
-		lo_j = max(cy * width, uint32_t(range.a[1])), hi_j = min(min((cy + 1u) * width, g.sy), uint32_t(range.b[1]));
-		lo_k = max(cz * width, uint32_t(range.a[2])), hi_k = min(min((cz + 1u) * width, g.sz), uint32_t(range.b[2]));
-		live = lo_i <= hi_i && lo_j <= hi_j && lo_k <= hi_k;
+		item = p.lists[level][index];
+		b = MakeItemBox(p, item, width);
 	}
-	uint32_t* flag = &p.flags[level][(size_t(cz) * p.dims[level][1] + cy) * p.dims[level][0] + cx];
+	bool live = b.live;
+	uint32_t* flag = &p.flags[level][(size_t(b.cz) * p.dims[level][1] + b.cy) * p.dims[level][0] + b.cx];
+	const uint32_t node = p.model.regions[item.region].node;
 	if (live && level == 0)
 	{
 		// work estimate of the brick, kept above the three flag bits of its word: samples of this region in the brick x
 		// the cost of the region's program.  CullResolveKernel orders the brick list by it (longest first).
-		const uint32_t samples = (hi_i - lo_i + 1u) * (hi_j - lo_j + 1u) * (hi_k - lo_k + 1u);
-		const uint32_t flops = __ldg(&p.model.nodes[p.model.regions[item.region].node].flops);
+		const uint32_t samples = (b.hi_i - b.lo_i + 1u) * (b.hi_j - b.lo_j + 1u) * (b.hi_k - b.lo_k + 1u);
+		const uint32_t flops = __ldg(&p.model.nodes[node].flops);
 		atomicAdd(flag, (((samples * (min(flops, 1u << 20) + 64u)) >> 10) + 1u) << kCostShift);
 	}
-	if (live && KnownEmpty(p.model, p.model.regions[item.region], g, lo_i, hi_i, lo_j, hi_j, lo_k, hi_k))
+	if (live && KnownEmpty(p.model, p.model.regions[item.region], g, b.lo_i, b.hi_i, b.lo_j, b.hi_j, b.lo_k, b.hi_k))
 	{
 		atomicOr(flag, kFlagPositive);
 		live = false; // decided without running the program
 	}
-	// An empty octant runs its parent's large program: once the known ball has failed, do not pay for it at every
-	// level on the way down -- split to the 8-cell bricks and evaluate there, once.
-	// Any long program costs one thread ~a thousand cycles per primitive (dependent fetch + sqrt chain), and a level has
-	// too few such items to hide that: the three finest levels each used to wait ~170 us for one 336-primitive program
-	// of seaside_town.  Long programs are therefore evaluated at every other level only (128, 32 and 8 cells).
-	const uint32_t node = p.model.regions[item.region].node;
+	// An empty octant runs its parent's program: once the known ball has failed, do not pay for it at every level on
+	// the way down -- split to the 8-cell bricks and evaluate there, once.
 	const uint32_t node_flags = live ? __ldg(&p.model.nodes[node].flags) : 0u;
-	const bool defer = level > 0 && (p.model.regions[item.region].known_value > 0.0f || ((node_flags & kNodeLong) != 0u && (level & 1) != 0));
-	if (live && !defer)
+	const bool defer = level > 0 && p.model.regions[item.region].known_value > 0.0f;
+	if (live && !defer && (node_flags & kNodeCullable))
 	{
-		if (node_flags & kNodeCullable)
+		float x, y, z, threshold;
+		ItemProbe(g, b, x, y, z, threshold);
+		const float d = EvalInterp1(p.model, __ldg(&p.model.nodes[node].interp_offset), x, y, z);
+		if (fabsf(d) > threshold)
 		{
-			const float lox = LatticeCoord(g.x, g.dx, lo_i), loy = LatticeCoord(g.y, g.dy, lo_j), loz = LatticeCoord(g.z, g.dz, lo_k);
-			const float hix = LatticeCoord(g.x, g.dx, hi_i), hiy = LatticeCoord(g.y, g.dy, hi_j), hiz = LatticeCoord(g.z, g.dz, hi_k);
-			const float ex = hix - lox, ey = hiy - loy, ez = hiz - loz;
-			const float radius = 0.5f * sqrtf(ex * ex + ey * ey + ez * ez);
-			const float threshold = radius * 1.001f + 1.0e-4f;
-			const float d = EvalInterp1<true>(p.model, __ldg(&p.model.nodes[node].interp_offset), 0.5f * (lox + hix), 0.5f * (loy + hiy), 0.5f * (loz + hiz));
-			if (fabsf(d) > threshold)
-			{
-				atomicOr(flag, d > 0.0f ? kFlagPositive : kFlagNegative);
-				live = false; // decided
-			}
+			atomicOr(flag, d > 0.0f ? kFlagPositive : kFlagNegative);
+			live = false; // decided
 		}
 	}
 	if (level == 0)
@@ -774,37 +339,124 @@ __global__ void __launch_bounds__(128) CullLevelKernel(const CullParams p)
 		if (live) atomicOr(flag, kFlagEvaluate);
 		return;
 	}
-	// split into the child bricks whose sample box still meets the region
-	const uint32_t half = width >> 1;
 	uint32_t children[8];
-	uint32_t n = 0;
-	if (live)
-	{
-#pragma unroll
-		for (int o = 0; o < 8; ++o)
-		{
-			const uint32_t x = cx * 2u + (o & 1), y = cy * 2u + ((o >> 1) & 1), z = cz * 2u + ((o >> 2) & 1);
-			const bool hit = max(x * half, lo_i) <= min((x + 1u) * half, hi_i) && max(y * half, lo_j) <= min((y + 1u) * half, hi_j) &&
-				max(z * half, lo_k) <= min((z + 1u) * half, hi_k) && x * half < g.sx && y * half < g.sy && z * half < p.cell_k_hi && (z + 1u) * half > p.cell_k_lo;
-			if (hit) children[n++] = x | (y << 10) | (z << 20);
-		}
-	}
-	// children stay in their parent's class (same region, same program); every lane takes part in both appends
-	const bool to_long = index < long_count;
-	bool fits_short, fits_long;
-	const uint32_t base_short = WarpAppend(&p.counts[level - 1], to_long ? 0u : n, fits_short, p.capacity[level - 1]);
-	const uint32_t base_long = WarpAppend(&p.counts[kCullLevels + level - 1], to_long ? n : 0u, fits_long, p.long_capacity[level - 1]);
+	const uint32_t n = live ? ItemChildren(p, b, width, children) : 0u;
+	bool fits;
+	const uint32_t base = WarpAppend(&p.counts[level - 1], n, fits, p.capacity[level - 1]); // every lane takes part
 	if (!live) return;
-	if (!(to_long ? fits_long : fits_short))
+	if (!fits)
 	{
 		atomicOr(flag, kFlagEvaluate); // inherited by every brick below this one
 		return;
 	}
-	CullItem* out = to_long ? p.long_lists[level - 1] + base_long : p.lists[level - 1] + base_short;
+	CullItem* out = p.lists[level - 1] + base;
 	for (uint32_t c = 0; c < n; ++c)
 	{
 		CullItem child = { item.region, children[c] };
 		out[c] = child;
+	}
+}
+
+// Items of regions with long programs (interior octree nodes keep hundreds of primitives: kNodeLong).  One thread
+// walking such a program is a chain of dependent fetches at ~850 cycles per primitive -- 170 us for the 336 primitives
+// of seaside_town's largest leaf, which used to be the whole duration of a level.  Here a GROUP of threads evaluates an
+// item together (GroupEvalLong): a warp for programs of up to kLongWarpSteps instructions (pass A: persistent warps
+// striding over the list), the whole block for the few larger ones (pass B: persistent blocks).
+template <int GROUP>
+__device__ __forceinline__ void CullLongItem(const CullParams& p, int level, const CullItem& item, LongScratch& scratch)
+{
+	const DeviceGrid& g = p.grid;
+	const uint32_t width = uint32_t(kBrick) << level;
+	const int tid = GROUP == 32 ? int(threadIdx.x & 31) : int(threadIdx.x);
+	const int warp = int(threadIdx.x >> 5);
+	const ItemBox b = MakeItemBox(p, item, width);
+	if (!b.live) return;
+	uint32_t* flag = &p.flags[level][(size_t(b.cz) * p.dims[level][1] + b.cy) * p.dims[level][0] + b.cx];
+	const FlatRegion& region = p.model.regions[item.region];
+	const uint32_t node = region.node;
+	const uint32_t node_flags = __ldg(&p.model.nodes[node].flags);
+	if (level == 0 && tid == 0)
+	{
+		const uint32_t samples = (b.hi_i - b.lo_i + 1u) * (b.hi_j - b.lo_j + 1u) * (b.hi_k - b.lo_k + 1u);
+		const uint32_t flops = __ldg(&p.model.nodes[node].flops);
+		atomicAdd(flag, (((samples * (min(flops, 1u << 20) + 64u)) >> 10) + 1u) << kCostShift);
+	}
+	if (KnownEmpty(p.model, region, g, b.lo_i, b.hi_i, b.lo_j, b.hi_j, b.lo_k, b.hi_k))
+	{
+		if (tid == 0) atomicOr(flag, kFlagPositive);
+		return;
+	}
+	const bool defer = level > 0 && (region.known_value > 0.0f || (p.long_every_other_level && (level & 1) != 0));
+	if (!defer && (node_flags & kNodeCullable))
+	{
+		float x, y, z, threshold;
+		ItemProbe(g, b, x, y, z, threshold);
+		const uint4* program = p.model.interp + (__ldg(&p.model.nodes[node].interp_offset) >> 2);
+		const uint32_t count = node_flags >> kNodeCountShift;
+		const float d = GROUP == 32
+			? GroupEvalLong<32>(program, count, x, y, z, scratch.step + warp * kLongWarpSteps, scratch.param + warp * kLongWarpSteps, scratch.share + warp * 32,
+				scratch.marks + warp * 32, scratch.result + warp, kLongWarpSteps)
+			: GroupEvalLong<kLongThreads>(program, count, x, y, z, scratch.step, scratch.param, scratch.share, scratch.marks, scratch.result, kLongBlockSteps);
+		if (fabsf(d) > threshold)
+		{
+			if (tid == 0) atomicOr(flag, d > 0.0f ? kFlagPositive : kFlagNegative);
+			return;
+		}
+	}
+	if (level == 0)
+	{
+		if (tid == 0) atomicOr(flag, kFlagEvaluate);
+		return;
+	}
+	if (tid < 32) // one warp appends the children
+	{
+		uint32_t children[8];
+		const uint32_t n = ItemChildren(p, b, width, children);
+		uint32_t base = 0;
+		if (tid == 0 && n) base = atomicAdd(&p.counts[kCullLevels + level - 1], n);
+		base = __shfl_sync(0xFFFFFFFFu, base, 0);
+		if (base + n > p.long_capacity[level - 1])
+		{
+			if (tid == 0) atomicOr(flag, kFlagEvaluate); // inherited by every brick below this one
+		}
+		else if (tid < int(n))
+		{
+			CullItem child = { item.region, children[0] };
+#pragma unroll
+			for (int c = 1; c < 8; ++c)
+			{
+				if (tid == c) child.cell = children[c];
+			}
+			p.long_lists[level - 1][base + tid] = child;
+		}
+	}
+}
+
+__global__ void __launch_bounds__(kLongThreads) CullLongKernel(const CullParams p)
+{
+	static_assert(kLongWarpSteps * (kLongThreads / 32) <= kLongBlockSteps, "the warps' slices of the scratch");
+	__shared__ LongScratch scratch;
+	const int level = p.level;
+	const uint32_t count = min(p.counts[kCullLevels + level], p.long_capacity[level]);
+	// pass A: a warp per item
+	const uint32_t warps = gridDim.x * (kLongThreads / 32);
+	for (uint32_t index = blockIdx.x * (kLongThreads / 32) + (threadIdx.x >> 5); index < count; index += warps)
+	{
+		const CullItem item = p.long_lists[level][index];
+		const uint32_t steps = __ldg(&p.model.nodes[p.model.regions[item.region].node].flags) >> kNodeCountShift;
+		if (steps > uint32_t(kLongWarpSteps)) continue;
+		CullLongItem<32>(p, level, item, scratch);
+		__syncwarp();
+	}
+	__syncthreads();
+	// pass B: the block per item, for the programs a warp would take too long over
+	for (uint32_t index = blockIdx.x; index < count; index += gridDim.x)
+	{
+		const CullItem item = p.long_lists[level][index];
+		const uint32_t steps = __ldg(&p.model.nodes[p.model.regions[item.region].node].flags) >> kNodeCountShift;
+		if (steps <= uint32_t(kLongWarpSteps)) continue;
+		CullLongItem<kLongThreads>(p, level, item, scratch);
+		__syncthreads();
 	}
 }
 
@@ -1345,6 +997,8 @@ struct AttributeParams
 	unsigned long long* cursor;  // device work cursor, zero at launch
 	const uint32_t* perm;        // may be null (identity)
 	const uint32_t* vertex_node; // may be null
+	volatile uint32_t* progress; // page-locked host word, may be null
+	uint32_t progress_base;
 };
 
 // Counting sort of the vertices by octree node, so that the lanes of a warp run the same tree program.  The
@@ -1457,6 +1111,7 @@ __global__ void __launch_bounds__(128, 8) AttributesKernel(const AttributeParams
 		if (lane == 0) first = atomicAdd(p.cursor, 32ull);
 		first = __shfl_sync(0xFFFFFFFFu, first, 0);
 		if (first >= count) break;
+		if (p.progress && lane == 0 && (first & 2047ull) == 0ull) *p.progress = p.progress_base + uint32_t(first * 1023ull / count);
 		const uint32_t t = uint32_t(first) + uint32_t(lane);
 		if (t < count) VertexAttributes(p, t);
 		__syncwarp();
@@ -1634,6 +1289,39 @@ __global__ void __launch_bounds__(128) EvalPointsKernel(const DeviceModel model,
 	{
 		const uint32_t node = Descend(model.nodes, 0, x, y, z);
 		ExportColor(model, node, x, y, z, static_cast<unsigned char*>(out) + size_t(i) * 3);
+	}
+}
+
+// Slab planner input (tg_multi.inl): which quarter-span sub-cells of every terminus cell can hold surface.  64 threads
+// per cell, one per sub-cell: the cell's own program at the sub-cell's centre against the sub-cell's half diagonal -- the
+// test K0 applies per brick, at a granularity that does not depend on the export grid.  Runs once per model.
+__global__ void __launch_bounds__(128) LeafProfileKernel(const DeviceModel model, const uint32_t* __restrict__ leaf_nodes, const float* __restrict__ leaf_span,
+	uint32_t leaf_count, unsigned long long* __restrict__ masks)
+{
+	const uint32_t thread = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t leaf = thread >> 6, sub = thread & 63u;
+	bool maybe = false;
+	if (leaf < leaf_count)
+	{
+		const uint32_t node = leaf_nodes[leaf];
+		const float span = leaf_span[leaf];
+		const float4 head = __ldg(reinterpret_cast<const float4*>(&model.nodes[node])); // pivot = cell centre
+		const float quarter = span * 0.25f;
+		const float x = head.x + (float(sub & 3u) - 1.5f) * quarter;
+		const float y = head.y + (float((sub >> 2) & 3u) - 1.5f) * quarter;
+		const float z = head.z + (float(sub >> 4) - 1.5f) * quarter;
+		const uint32_t flags = __ldg(&model.nodes[node].flags);
+		if ((flags & kNodeCullable) == 0u) maybe = true; // not a distance bound: assume surface
+		else
+		{
+			const float d = EvalInterp1(model, __ldg(&model.nodes[node].interp_offset), x, y, z);
+			maybe = !(fabsf(d) > quarter * 0.8660254f * 1.001f + 1.0e-4f);
+		}
+	}
+	const unsigned ballot = __ballot_sync(0xFFFFFFFFu, maybe);
+	if ((threadIdx.x & 31) == 0 && leaf < leaf_count)
+	{
+		atomicOr(&masks[leaf], (unsigned long long)ballot << (sub & 32u));
 	}
 }
 
@@ -1849,6 +1537,12 @@ Context* Context::Create(int device, std::string& error)
 		c->progress_done[i] = 0;
 		c->progress_total[i] = 0;
 	}
+	void* words = nullptr;
+	if (cudaMallocHost(&words, 64) == cudaSuccess)
+	{
+		std::memset(words, 0, 64);
+		c->progress_words = static_cast<volatile uint32_t*>(words);
+	}
 	return c;
 }
 
@@ -1864,6 +1558,7 @@ Context::~Context()
 	{
 		if (ev) cudaEventDestroy(static_cast<cudaEvent_t>(ev));
 	}
+	if (progress_words) cudaFreeHost(const_cast<uint32_t*>(progress_words));
 	if (arena) cudaFree(arena);
 	if (arena2) cudaFree(arena2);
 	for (PinnedBlock& b : device_blocks)
@@ -1993,17 +1688,21 @@ void Context::ReleasePinned(void* ptr)
 // Copies one table host -> device.  The device allocation and a page-locked staging copy of the host vector are
 // made on first use and kept for the model's lifetime, so a repeated upload (tg_model_upload) is a plain async copy.
 template <typename T>
-static int UploadVector(Context* c, const std::vector<T>& v, void** device, void** staging, uint64_t& bytes_total, std::string& error)
+static int UploadVector(Context* c, const std::vector<T>& v, void** device, void** staging, const void* shared_staging, uint64_t& bytes_total, std::string& error)
 {
 	const size_t payload = v.size() * sizeof(T);
 	const size_t bytes = std::max<size_t>(payload, 16);
 	if (!*device)
 	{
 		TG_CUDA(cudaMalloc(device, bytes));
-		TG_CUDA(cudaMallocHost(staging, bytes));
-		std::memcpy(*staging, v.data(), payload);
+		if (!shared_staging)
+		{
+			TG_CUDA(cudaMallocHost(staging, bytes));
+			std::memcpy(*staging, v.data(), payload);
+		}
 	}
-	TG_CUDA(cudaMemcpyAsync(*device, *staging, payload, cudaMemcpyHostToDevice, StreamOf(c)));
+	// a replica of a multi-GPU model copies from the primary's staging block (page-locked memory is visible to every device)
+	TG_CUDA(cudaMemcpyAsync(*device, shared_staging ? shared_staging : *staging, payload, cudaMemcpyHostToDevice, StreamOf(c)));
 	bytes_total += bytes;
 	return TG_OK;
 }
@@ -2030,13 +1729,43 @@ static int UploadModel(Model* m, std::string& error)
 	TG_CUDA(cudaSetDevice(c->device));
 	m->device_bytes = 0;
 	int rc;
-	if ((rc = UploadVector(c, m->flat.nodes, &m->d_nodes, &m->staging[0], m->device_bytes, error)) != TG_OK) return rc;
-	if ((rc = UploadVector(c, m->flat.interp, &m->d_interp, &m->staging[1], m->device_bytes, error)) != TG_OK) return rc;
-	if ((rc = UploadVector(c, m->flat.tree, &m->d_tree, &m->staging[2], m->device_bytes, error)) != TG_OK) return rc;
-	if ((rc = UploadVector(c, m->flat.material_rgb, &m->d_materials, &m->staging[3], m->device_bytes, error)) != TG_OK) return rc;
-	if ((rc = UploadVector(c, m->flat.regions, &m->d_regions, &m->staging[4], m->device_bytes, error)) != TG_OK) return rc;
-	if ((rc = UploadVector(c, m->flat.node_rank, &m->d_node_rank, &m->staging[5], m->device_bytes, error)) != TG_OK) return rc;
+	const Model* src = m->primary;
+	if ((rc = UploadVector(c, m->flat.nodes, &m->d_nodes, &m->staging[0], src ? src->staging[0] : nullptr, m->device_bytes, error)) != TG_OK) return rc;
+	if ((rc = UploadVector(c, m->flat.interp, &m->d_interp, &m->staging[1], src ? src->staging[1] : nullptr, m->device_bytes, error)) != TG_OK) return rc;
+	if ((rc = UploadVector(c, m->flat.tree, &m->d_tree, &m->staging[2], src ? src->staging[2] : nullptr, m->device_bytes, error)) != TG_OK) return rc;
+	if ((rc = UploadVector(c, m->flat.material_rgb, &m->d_materials, &m->staging[3], src ? src->staging[3] : nullptr, m->device_bytes, error)) != TG_OK) return rc;
+	if ((rc = UploadVector(c, m->flat.regions, &m->d_regions, &m->staging[4], src ? src->staging[4] : nullptr, m->device_bytes, error)) != TG_OK) return rc;
+	if ((rc = UploadVector(c, m->flat.node_rank, &m->d_node_rank, &m->staging[5], src ? src->staging[5] : nullptr, m->device_bytes, error)) != TG_OK) return rc;
 	TG_CUDA(cudaStreamSynchronize(StreamOf(c)));
+	return TG_OK;
+}
+
+static DeviceModel MakeDeviceModel(const Model* m);
+
+// Fills FlatModel::leaf_mask on the device (LeafProfileKernel): part of building a model, like the octree.
+static int ProfileLeaves(Model* m, std::string& error)
+{
+	FlatModel& flat = m->flat;
+	const uint32_t count = uint32_t(flat.leaf_nodes.size());
+	flat.leaf_mask.assign(count, 0ull);
+	if (count == 0) return TG_OK;
+	cudaStream_t stream = StreamOf(m->context);
+	uint32_t* d_nodes = nullptr;
+	float* d_span = nullptr;
+	unsigned long long* d_masks = nullptr;
+	TG_CUDA(cudaMalloc(&d_nodes, size_t(count) * 4));
+	TG_CUDA(cudaMalloc(&d_span, size_t(count) * 4));
+	TG_CUDA(cudaMalloc(&d_masks, size_t(count) * 8));
+	TG_CUDA(cudaMemcpyAsync(d_nodes, flat.leaf_nodes.data(), size_t(count) * 4, cudaMemcpyHostToDevice, stream));
+	TG_CUDA(cudaMemcpyAsync(d_span, flat.leaf_span.data(), size_t(count) * 4, cudaMemcpyHostToDevice, stream));
+	TG_CUDA(cudaMemsetAsync(d_masks, 0, size_t(count) * 8, stream));
+	LeafProfileKernel<<<uint32_t((uint64_t(count) * 64 + 127) / 128), 128, 0, stream>>>(MakeDeviceModel(m), d_nodes, d_span, count, d_masks);
+	TG_CUDA(cudaGetLastError());
+	TG_CUDA(cudaMemcpyAsync(flat.leaf_mask.data(), d_masks, size_t(count) * 8, cudaMemcpyDeviceToHost, stream));
+	TG_CUDA(cudaStreamSynchronize(stream));
+	cudaFree(d_nodes);
+	cudaFree(d_span);
+	cudaFree(d_masks);
 	return TG_OK;
 }
 
@@ -2057,6 +1786,11 @@ Model* Model::Create(Context* context, const Tree& tree, float target_size, int 
 		return nullptr;
 	}
 	m->upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	if (ProfileLeaves(m, error) != TG_OK)
+	{
+		delete m;
+		return nullptr;
+	}
 	return m;
 }
 
@@ -2072,6 +1806,35 @@ int EngineUploadModel(Model* model, std::string& error)
 	const int rc = UploadModel(model, error);
 	model->upload_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 	return rc;
+}
+
+void EngineProgress(const std::vector<const Context*>& contexts, float out_ratios[4], int* out_stage)
+{
+	const Context* first = contexts[0];
+	const int stage = first->stage.load();
+	if (out_stage) *out_stage = stage;
+	if (!out_ratios) return;
+	double generation = 0.0, attributes = 0.0;
+	for (const Context* c : contexts)
+	{
+		const double slabs = double(std::max<uint32_t>(c->progress_slabs, 1u)) * 1024.0;
+		if (c->progress_words)
+		{
+			generation += std::min(1.0, double(c->progress_words[0]) / slabs);
+			attributes += std::min(1.0, double(c->progress_words[1]) / slabs);
+		}
+	}
+	generation /= double(contexts.size());
+	attributes /= double(contexts.size());
+	// whole slabs that are home count for sure (the words only move while a kernel runs)
+	const uint64_t total = first->progress_total[0].load();
+	if (total) generation = std::max(generation, double(first->progress_done[0].load()) / double(total) * (stage == 0 ? 1.0 : 0.999));
+	const bool refining = stage == 2;
+	out_ratios[0] = float(generation);                  // GenerationProgress / GenerationEstimate
+	out_ratios[1] = refining ? float(attributes) : 0.0f; // RefinementProgress / VertexCount
+	out_ratios[2] = refining ? 0.0f : float(attributes); // SecondaryProgress / SecondaryCount (attribute loop)
+	const uint64_t wtotal = first->progress_total[3].load();
+	out_ratios[3] = wtotal ? float(double(first->progress_done[3].load()) / double(wtotal)) : 0.0f;
 }
 
 int EngineSynchronize(Context* ctx, std::string& error)
@@ -2185,6 +1948,10 @@ struct MeshResultDevice
 	uint32_t* d_triangles = nullptr;
 	float* d_face_normals = nullptr;
 	std::vector<void*> pinned;
+	// multi-GPU exports: the per-device results of a TG_MESH_DEVICE_ONLY export, and per-rank detail for tg_mesh_rank_info
+	std::vector<MeshResultDevice*> parts;
+	std::vector<tg_mesh_timings> rank_timings;
+	std::vector<uint32_t> rank_cuts;
 };
 
 void EngineFreeMesh(tg_mesh* mesh)
@@ -2193,6 +1960,17 @@ void EngineFreeMesh(tg_mesh* mesh)
 	MeshResultDevice* r = static_cast<MeshResultDevice*>(mesh->opaque);
 	if (r)
 	{
+		for (MeshResultDevice* part : r->parts)
+		{
+			if (!part) continue;
+			cudaSetDevice(part->context->device);
+			part->context->ReleaseDevice(part->d_positions);
+			part->context->ReleaseDevice(part->d_normals);
+			part->context->ReleaseDevice(part->d_colors);
+			part->context->ReleaseDevice(part->d_triangles);
+			part->context->ReleaseDevice(part->d_face_normals);
+			delete part;
+		}
 		cudaSetDevice(r->context->device);
 		cudaStream_t s = StreamOf(r->context);
 		(void)s;
@@ -2322,6 +2100,8 @@ static int EnqueueAttributes(Model* model, Scratch& scratch, MeshResultDevice* r
 	ap.grid_z = grid_z;
 	ap.grid_dz = grid_dz;
 	ap.layer_count = layer_count;
+	ap.progress = ctx->progress_words ? ctx->progress_words + 1 : nullptr;
+	ap.progress_base = ctx->progress_base;
 	// node-coherent order: counting sort of the vertices by octree node
 	const uint32_t node_count = uint32_t(model->flat.nodes.size());
 	static const uint32_t wide_node = PersistentGrid(ctx, VertexNodeKernel, 256), wide_perm = PersistentGrid(ctx, VertexPermutationKernel, 256);
@@ -2391,6 +2171,8 @@ static int BuildCullFlags(Model* model, cudaStream_t stream, Scratch& scratch, c
 	cp.ranges = nullptr;
 	cp.counts = nullptr;
 	cp.level = 0;
+	cp.long_every_other_level = 0;
+	if (const char* env = std::getenv("TG_CULL_LONG_SKIP")) cp.long_every_other_level = std::atoi(env) > 0 ? 1 : 0;
 	size_t flag_words = 0;
 	for (int level = 0; level < kCullLevels; ++level)
 	{
@@ -2425,16 +2207,38 @@ static int BuildCullFlags(Model* model, cudaStream_t stream, Scratch& scratch, c
 	// Levels run top-down with grids sized for the level's capacity bound by what can actually arrive
 	// (threads beyond the device-side count exit at once), so no count is read back between levels.
 	uint64_t bound = 0;
+	static const uint32_t wide_long = PersistentGrid(model->context, CullLongKernel, kLongThreads);
 	for (int level = kCullLevels - 1; level >= 0; --level)
 	{
-		const uint64_t both = uint64_t(cp.capacity[level]) + cp.long_capacity[level];
-		const uint64_t seeded = std::min<uint64_t>(uint64_t(cp.model.region_count) * kSeedSpan * kSeedSpan * kSeedSpan, both);
-		bound = std::min<uint64_t>(bound * 8u + seeded, both);
+		const uint64_t seeded = std::min<uint64_t>(uint64_t(cp.model.region_count) * kSeedSpan * kSeedSpan * kSeedSpan, cp.capacity[level]);
+		bound = std::min<uint64_t>(bound * 8u + seeded, cp.capacity[level]);
 		cp.level = level;
+		CullLongKernel<<<wide_long, kLongThreads, 0, stream>>>(cp);
 		CullLevelKernel<<<uint32_t((bound + 127) / 128), 128, 0, stream>>>(cp);
-		launches++;
+		launches += 2;
 	}
 	TG_CUDA(cudaGetLastError());
+	if (std::getenv("TG_TRACE_CULL"))
+	{
+		// diagnostics: items per level (short / long) and the sizes of the long programs
+		uint32_t host_counts[2 * kCullLevels];
+		TG_CUDA(cudaMemcpyAsync(host_counts, counts, sizeof(host_counts), cudaMemcpyDeviceToHost, stream));
+		TG_CUDA(cudaStreamSynchronize(stream));
+		for (int level = kCullLevels - 1; level >= 0; --level) std::fprintf(stderr, "cull level %d: %u short items, %u long items\n", level, host_counts[level], host_counts[kCullLevels + level]);
+		uint32_t long_regions = 0, max_count = 0;
+		uint64_t sum = 0;
+		for (const FlatRegion& r : model->flat.regions)
+		{
+			const uint32_t f = model->flat.nodes[r.node].flags;
+			if (f & kNodeLong)
+			{
+				long_regions++;
+				sum += f >> kNodeCountShift;
+				max_count = std::max(max_count, f >> kNodeCountShift);
+			}
+		}
+		std::fprintf(stderr, "cull: %zu regions, %u with long programs (mean %.1f instructions, max %u)\n", model->flat.regions.size(), long_regions, long_regions ? double(sum) / long_regions : 0.0, max_count);
+	}
 	return TG_OK;
 }
 
@@ -2522,6 +2326,7 @@ struct MeshJob
 	Mailbox* mailbox = nullptr;             // pinned host
 	cudaEvent_t marks[6] = {};              // start, cull, eval, scan, faces, attributes
 	cudaEvent_t faces_ready = nullptr, all_ready = nullptr;
+	cudaEvent_t bricks_done = nullptr, base_set = nullptr; // multi-GPU: around the all-gather of the per-slab vertex counts
 	uint64_t launches = 0;
 	bool enqueued = false;
 	int lane = 0;
@@ -2534,6 +2339,8 @@ struct MeshJob
 		}
 		if (faces_ready) cudaEventDestroy(faces_ready);
 		if (all_ready) cudaEventDestroy(all_ready);
+		if (bricks_done) cudaEventDestroy(bricks_done);
+		if (base_set) cudaEventDestroy(base_set);
 		if (mailbox && model) model->context->ReleaseMailbox(mailbox);
 	}
 };
@@ -2551,10 +2358,31 @@ static void DefaultCapacities(uint64_t slab_cells, uint32_t& cap_v, uint32_t& ca
 	}
 }
 
+// Multi-GPU export (tg_multi.inl): what a slab's job needs to learn the vertex total of the slabs below it.
+struct MultiHook
+{
+	void* comm = nullptr;                   // ncclComm_t of this rank
+	int rank = 0, ranks = 1;
+	unsigned long long* gathered = nullptr; // device: `ranks` entries, filled by the all-gather
+	int (*all_gather)(void* comm, const void* send, void* recv, cudaStream_t stream, std::string& error) = nullptr;
+};
+
+// index_base = vertices owned by the slabs of the lower ranks.
+__global__ void GatherPrefixKernel(const unsigned long long* __restrict__ gathered, int rank, unsigned long long* index_base)
+{
+	if (threadIdx.x == 0 && blockIdx.x == 0)
+	{
+		unsigned long long sum = 0;
+		for (int r = 0; r < rank; ++r) sum += gathered[r];
+		*index_base = sum;
+	}
+}
+
 // Enqueues one slab: culling, brick evaluation, numbering, emission, attributes, mailbox copies.  Does not wait.
 // index_base (device, may be null) is added to every triangle index and then advanced by the slab's vertex count.
 static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const tg_mesh_options& options, uint32_t cap_v, uint32_t cap_q,
-	unsigned long long* index_base, std::string& error, int lane = 0, cudaEvent_t base_ready = nullptr, const CullParams* shared_cull = nullptr)
+	unsigned long long* index_base, std::string& error, int lane = 0, cudaEvent_t base_ready = nullptr, const CullParams* shared_cull = nullptr,
+	const MultiHook* hook = nullptr)
 {
 	Context* ctx = model->context;
 	cudaStream_t stream = static_cast<cudaStream_t>(lane ? ctx->stream2 : ctx->stream);
@@ -2667,6 +2495,9 @@ static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const
 	TG_CUDA(cudaEventRecord(job.marks[1], stream));
 
 	// ---- K1 + K2: evaluate bricks, classify, extract vertices ------------------------------------
+	// (result buffers first: an allocator call must not sit between this rank's collective and its peers')
+	{ void* p_ = ctx->AcquireDevice(size_t(cap_v) * 12, error); if (!p_) return TG_ERR_MEMORY; result->d_positions = static_cast<decltype(result->d_positions)>(p_); }
+	{ void* p_ = ctx->AcquireDevice(size_t(cap_q) * 24, error); if (!p_) return TG_ERR_MEMORY; result->d_triangles = static_cast<decltype(result->d_triangles)>(p_); }
 	float4* tmp_pos = nullptr;
 	unsigned long long* tmp_key = nullptr;
 	TG_CUDA(scratch.Alloc(&tmp_pos, cap_v));
@@ -2686,11 +2517,38 @@ static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const
 	mp.tmp_pos = tmp_pos;
 	mp.tmp_key = tmp_key;
 	mp.tmp_capacity = cap_v;
+	mp.progress = ctx->progress_words;
+	mp.progress_base = ctx->progress_base;
 	// persistent warps: the grid fills every SM; warps beyond the list length leave at their first fetch
-	MeshBricksKernel<<<uint32_t(ctx->sm_count) * uint32_t(ctx->brick_blocks_per_sm), kBrickThreads, 0, stream>>>(mp);
+	if (options.flags & TG_MESH_FAST)
+	{
+		static const int fast_blocks_per_sm = FastBrickBlocksPerSm();
+		TG_CUDA(cudaError_t(LaunchMeshBricksFast(&mp, uint32_t(ctx->sm_count) * uint32_t(fast_blocks_per_sm), stream)));
+	}
+	else
+	{
+		MeshBricksKernel<<<uint32_t(ctx->sm_count) * uint32_t(ctx->brick_blocks_per_sm), kBrickThreads, 0, stream>>>(mp);
+		TG_CUDA(cudaGetLastError());
+	}
 	launches++;
-	TG_CUDA(cudaGetLastError());
 	TG_CUDA(cudaEventRecord(job.marks[2], stream));
+	if (hook)
+	{
+		// The one exchange of the path: every rank's owned vertex count, all-gathered over NVLink on the
+		// side stream while this stream goes on numbering; FinalizeMeshKernel waits for the resulting index base.
+		cudaStream_t side = static_cast<cudaStream_t>(ctx->stream2);
+		TG_CUDA(cudaEventCreateWithFlags(&job.bricks_done, cudaEventDisableTiming));
+		TG_CUDA(cudaEventCreateWithFlags(&job.base_set, cudaEventDisableTiming));
+		TG_CUDA(cudaEventRecord(job.bricks_done, stream));
+		TG_CUDA(cudaStreamWaitEvent(side, job.bricks_done, 0));
+		const int rcg = hook->all_gather(hook->comm, counters + kCntTmpVertices, hook->gathered, side, error);
+		if (rcg != TG_OK) return rcg;
+		GatherPrefixKernel<<<1, 32, 0, side>>>(hook->gathered, hook->rank, index_base);
+		launches += 2;
+		TG_CUDA(cudaGetLastError());
+		TG_CUDA(cudaEventRecord(job.base_set, side));
+		base_ready = job.base_set;
+	}
 
 	// ---- vertex + quad numbering: one dual scan over the bitmap ----------------------------------
 	{
@@ -2713,8 +2571,6 @@ static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const
 	TG_CUDA(scratch.Alloc(&layer_starts, job.profile_layers + 2));
 	TG_CUDA(scratch.Alloc(&layer_cost, nbz_all));
 	TG_CUDA(cudaMemsetAsync(layer_cost, 0, size_t(nbz_all) * 8, stream));
-	{ void* p_ = ctx->AcquireDevice(size_t(cap_v) * 12, error); if (!p_) return TG_ERR_MEMORY; result->d_positions = static_cast<decltype(result->d_positions)>(p_); }
-	{ void* p_ = ctx->AcquireDevice(size_t(cap_q) * 24, error); if (!p_) return TG_ERR_MEMORY; result->d_triangles = static_cast<decltype(result->d_triangles)>(p_); }
 	const double h_alloc = host_us(h_begin);
 	const bool attribute_pass = WantsAttributePass(model, options);
 	AttributeScratch as;
@@ -2749,7 +2605,7 @@ static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const
 	if (base_ready) TG_CUDA(cudaStreamWaitEvent(stream, base_ready, 0)); // the slab below has advanced the index base
 	FinalizeMeshKernel<<<wide_finalize, 256, 0, stream>>>(fp);
 	launches++;
-	if (index_base)
+	if (index_base && !hook)
 	{
 		AdvanceIndexBaseKernel<<<1, 32, 0, stream>>>(index_base, counters, cap_v);
 		launches++;
@@ -3194,6 +3050,7 @@ static int ExportMeshPipelined(Model* model, const tg_grid& grid_in, const tg_me
 	};
 
 	ctx->progress_total[0] = uint64_t(chunks);
+	ctx->progress_slabs = uint32_t(chunks);
 	// One compute lane by default.  Two lanes (even / odd slabs on two streams with their own scratch arenas, so that a
 	// slab's persistent brick kernel fills the SMs while its predecessor drains) measured no better on seaside 1024^3:
 	// the small numbering / attribute kernels of slab c then queue behind the resident blocks of slab c + 1.
@@ -3208,6 +3065,7 @@ static int ExportMeshPipelined(Model* model, const tg_grid& grid_in, const tg_me
 		slab.slab_begin = uint64_t(nbz) * uint64_t(c) / uint64_t(chunks) * kBrick;
 		slab.slab_end = c + 1 == chunks ? grid.sz : uint64_t(nbz) * uint64_t(c + 1) / uint64_t(chunks) * kBrick;
 		jobs.emplace_back(new MeshJob());
+		ctx->progress_base = uint32_t(c) * 1024u;
 		int rc = EnqueueMesh(*jobs.back(), model, grid_in, slab, 0, 0, index_base, error, lanes > 1 ? (c & 1) : 0, c > 0 ? jobs[size_t(c) - 1]->faces_ready : nullptr, &shared_cull);
 		if (rc != TG_OK) return abandon(rc);
 		if (c > 0 && (rc = collect(c - 1)) != TG_OK) return abandon(rc);
@@ -3312,6 +3170,9 @@ int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options
 	ctx->stage.store(1);
 	ctx->progress_done[0] = 0;
 	ctx->progress_total[0] = 1;
+	ctx->progress_base = 0;
+	ctx->progress_slabs = 1;
+	if (ctx->progress_words) ctx->progress_words[0] = ctx->progress_words[1] = 0u;
 	if (ctx->Cancelled()) return TG_ERR_CANCELLED;
 	int rc = TG_RETRY_ONE_SHOT;
 	const int chunks = PipelineChunks(grid_in, options);
@@ -3338,6 +3199,16 @@ int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options
 
 // Brings a TG_MESH_DEVICE_ONLY result to the host, adding index_base to every triangle index first (multi-GPU
 // runs: the vertex total of the lower ranks, known only after the counts were exchanged).
+int EngineMeshRankInfo(const tg_mesh* mesh, int rank, uint64_t* slab_begin, uint64_t* slab_end, tg_mesh_timings* timings)
+{
+	const MeshResultDevice* result = mesh ? static_cast<const MeshResultDevice*>(mesh->opaque) : nullptr;
+	if (!result || rank < 0 || size_t(rank) >= result->rank_timings.size()) return -1;
+	if (slab_begin) *slab_begin = result->rank_cuts[size_t(rank)];
+	if (slab_end) *slab_end = result->rank_cuts[size_t(rank) + 1];
+	if (timings) *timings = result->rank_timings[size_t(rank)];
+	return int(result->rank_timings.size());
+}
+
 int EngineDownloadMesh(tg_mesh* mesh, uint32_t index_base, std::string& error)
 {
 	MeshResultDevice* result = static_cast<MeshResultDevice*>(mesh->opaque);
@@ -3345,6 +3216,11 @@ int EngineDownloadMesh(tg_mesh* mesh, uint32_t index_base, std::string& error)
 	{
 		error = "mesh has no device data";
 		return TG_ERR_INVALID;
+	}
+	if (!result->parts.empty())
+	{
+		error = "tg_mesh_download does not apply to multi-GPU results: export without TG_MESH_DEVICE_ONLY";
+		return TG_ERR_UNSUPPORTED;
 	}
 	Context* ctx = result->context;
 	TG_CUDA(cudaSetDevice(ctx->device));
@@ -3415,7 +3291,7 @@ int EngineBrickProfile(Model* model, const tg_grid& grid_in, uint32_t* out_layer
 	return TG_OK;
 }
 
-int EngineEvalLattice(Model* model, const tg_grid& grid_in, float* out, float* out_ms, std::string& error)
+int EngineEvalLattice(Model* model, const tg_grid& grid_in, uint32_t flags, float* out, float* out_ms, std::string& error)
 {
 	Context* ctx = model->context;
 	TG_CUDA(cudaSetDevice(ctx->device));
@@ -3434,7 +3310,12 @@ int EngineEvalLattice(Model* model, const tg_grid& grid_in, float* out, float* o
 	StageTimer timer(stream);
 	const int t0 = timer.Mark();
 	const uint32_t tile_count = tx * ty * tz;
-	LatticeKernel<<<(tile_count + kBrickWarps - 1) / kBrickWarps, kBrickThreads, 0, stream>>>(MakeDeviceModel(model), grid, d_out, tx, ty, tile_count, counters);
+	if (flags & TG_MESH_FAST)
+	{
+		const DeviceModel dm = MakeDeviceModel(model);
+		TG_CUDA(cudaError_t(LaunchLatticeFast(&dm, &grid, d_out, tx, ty, tile_count, counters, stream)));
+	}
+	else LatticeKernel<<<(tile_count + kBrickWarps - 1) / kBrickWarps, kBrickThreads, 0, stream>>>(MakeDeviceModel(model), grid, d_out, tx, ty, tile_count, counters);
 	const int t1 = timer.Mark();
 	TG_CUDA(cudaGetLastError());
 	if (out) TG_CUDA(cudaMemcpyAsync(out, d_out, total * 4, cudaMemcpyDeviceToHost, stream));
@@ -3540,6 +3421,7 @@ int EngineExportPoints(Model* model, const float mn[3], const float mx[3], const
 	std::memset(out, 0, sizeof(*out));
 	Context* ctx = model->context;
 	TG_CUDA(cudaSetDevice(ctx->device));
+	if (ctx->Cancelled()) return TG_ERR_CANCELLED;
 	cudaStream_t stream = StreamOf(ctx);
 	// export.cpp:394-399
 	int n[3];
@@ -3682,5 +3564,7 @@ int EngineFlushL2(Context* ctx, std::string& error)
 	TG_CUDA(cudaGetLastError());
 	return TG_OK;
 }
+
+#include "tg_multi.inl"
 
 } // namespace tg

@@ -3,8 +3,13 @@
 #pragma once
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdint>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/tangerine_b200.h"
@@ -51,6 +56,11 @@ public:
 	std::atomic<bool> orphaned{ false };
 	std::atomic<uint64_t> progress_done[4];
 	std::atomic<uint64_t> progress_total[4];
+	// Fine-grained progress, written by the kernels themselves into page-locked host memory: [0] bricks evaluated,
+	// [1] vertices through the refinement / attribute pass, both in 1/1024ths of a slab on top of 1024 x slabs done.
+	volatile uint32_t* progress_words = nullptr;
+	uint32_t progress_base = 0;   // 1024 x index of the slab being enqueued
+	uint32_t progress_slabs = 1;  // slabs of the export in flight
 
 	static Context* Create(int device, std::string& error);
 	~Context();
@@ -75,7 +85,9 @@ class Model
 {
 public:
 	Context* context = nullptr;
-	FlatModel flat;          // host copy of the tables (kept for stats and debugging)
+	std::shared_ptr<FlatModel> flat_owner; // one host copy of the tables, shared by the replicas of a multi-GPU model
+	FlatModel& flat;
+	Model* primary = nullptr; // replica: uploads from the primary's page-locked staging copies
 	void* d_nodes = nullptr;
 	void* d_interp = nullptr;
 	void* d_tree = nullptr;
@@ -86,16 +98,64 @@ public:
 	uint64_t device_bytes = 0;
 	double upload_seconds = 0.0;
 	int leaf_count = 0;
+	// slab cuts of the last multi-GPU export (the estimate walks every terminus cell: milliseconds, so it is made once per grid)
+	struct { tg_grid grid; int ranks = 0; std::vector<uint32_t> cuts; } plan;
 
+	Model() : flat_owner(std::make_shared<FlatModel>()), flat(*flat_owner) {}
+	explicit Model(const std::shared_ptr<FlatModel>& shared) : flat_owner(shared), flat(*flat_owner) {}
 	static Model* Create(Context* context, const Tree& tree, float target_size, int threads, std::string& error);
+	// The same tables on another device of a DeviceGroup (no second octree build).
+	static Model* CreateReplica(Context* context, Model* primary, std::string& error);
 	~Model();
+};
+
+// The devices of a multi-GPU context (tg_context_create_multi): one host thread per device and one NCCL communicator
+// per device (ncclCommInitAll, one process).  libnccl is loaded at run time (dlopen), so single-GPU hosts need none.
+class DeviceGroup
+{
+public:
+	std::vector<Context*> contexts; // borrowed; contexts[0] is the primary
+	std::vector<void*> comms;       // ncclComm_t, by rank
+	std::string nccl_version;
+
+	static DeviceGroup* Create(const std::vector<Context*>& contexts, std::string& error);
+	~DeviceGroup();
+	int size() const { return int(contexts.size()); }
+	// Runs task(rank, error) on every worker thread and waits; returns the first non-zero status (with its message).
+	int Run(const std::function<int(int, std::string&)>& task, std::string& error);
+	// Rendezvous of the worker threads inside a task.
+	void Barrier();
+
+private:
+	std::vector<std::thread> threads;
+	std::mutex lock;
+	std::condition_variable wake, done;
+	const std::function<int(int, std::string&)>* task = nullptr;
+	uint64_t generation = 0;
+	int pending = 0;
+	bool quit = false;
+	std::vector<int> status;
+	std::vector<std::string> errors;
+	std::atomic<int> barrier_count{ 0 };
+	std::atomic<int> barrier_phase{ 0 };
+	void Worker(int rank);
 };
 
 struct MeshResultDevice; // opaque device-side result kept alive by tg_mesh.opaque
 
 int EngineEvalPoints(Model* model, int mode, const float* points, uint64_t count, void* out, std::string& error);
-int EngineEvalLattice(Model* model, const tg_grid& grid, float* out, float* out_ms, std::string& error);
+int EngineEvalLattice(Model* model, const tg_grid& grid, uint32_t flags, float* out, float* out_ms, std::string& error);
 int EngineExportMesh(Model* model, const tg_grid& grid, const tg_mesh_options& options, tg_mesh* out, std::string& error);
+// The same export on all devices of a group: z-slabs cut from a host-side work estimate, per-slab vertex counts combined
+// by an NCCL all-gather on the devices, every device copying straight into its slice of ONE host mesh.
+int EngineExportMeshMulti(DeviceGroup* group, const std::vector<Model*>& models, const tg_grid& grid, const tg_mesh_options& options, tg_mesh* out, std::string& error);
+// Per-rank detail of a multi-GPU export: returns the number of ranks (or -1), slab [begin, end) and stage timings of `rank`.
+int EngineMeshRankInfo(const tg_mesh* mesh, int rank, uint64_t* slab_begin, uint64_t* slab_end, tg_mesh_timings* timings);
+// Host-side slab planning (no device work): estimated cost of every cell layer, and the cuts of `ranks` z-slabs.
+std::vector<double> EstimateLayerCost(const FlatModel& flat, const tg_grid& grid);
+std::vector<uint32_t> PlanSlabs(const std::vector<double>& cost, uint32_t sz, int ranks);
+int EngineTimerBeginMulti(DeviceGroup* group, std::string& error);
+int EngineTimerEndMulti(DeviceGroup* group, float* out_ms, std::string& error);
 int EngineExportPoints(Model* model, const float mn[3], const float mx[3], const float step[3], int refine, uint32_t flags, float scale, tg_mesh* out, std::string& error);
 int EngineExportVoxels(Model* model, float grid_size, int32_t out_size[3], float* out_radius, int32_t** out_xyz, uint64_t* out_count, std::string& error);
 void EngineFreeMesh(tg_mesh* mesh);
@@ -105,6 +165,8 @@ int EngineTimerEnd(Context* context, float* out_ms, std::string& error);
 int EngineMeasureFp32Peak(Context* context, double* out_tflops, std::string& error);
 int EngineFlushL2(Context* context, std::string& error);
 int EngineSynchronize(Context* context, std::string& error);
+// GetExportProgress's ratios (export.cpp:483-492) from the device-written words of these contexts (one, or a group's).
+void EngineProgress(const std::vector<const Context*>& contexts, float out_ratios[4], int* out_stage);
 int EngineUploadModel(Model* model, std::string& error);
 int EngineBrickProfile(Model* model, const tg_grid& grid, uint32_t* out_layers, uint32_t layer_count, std::string& error);
 

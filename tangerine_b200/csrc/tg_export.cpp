@@ -15,6 +15,7 @@ std::atomic<int> g_device{ 0 };
 std::mutex g_state_lock;
 tg_context* g_active_context = nullptr; // context of the export in flight, for progress / cancel
 std::atomic<int> g_stage{ 0 };
+std::atomic<bool> g_cancel{ false }; // CancelExport seen by the export in flight, whatever phase it is in
 std::atomic<int> g_status{ TG_OK };
 std::string g_error;
 
@@ -34,9 +35,16 @@ int RunExport(const tg_tree* tree, const std::string& path, const float mn[3], c
 	{
 		std::lock_guard<std::mutex> lock(g_state_lock);
 		g_active_context = context;
+		if (g_cancel.load()) tg_cancel(context, 1); // CancelExport ran before the context existed
 	}
 	int rc = TG_ERR_INVALID;
 	tg_model* model = tg_model_create(context, tree, 0.25f, 0); // SDFOctree::Create(Evaluator, 0.25), export.cpp:322 / 388
+	if (model && g_cancel.load())
+	{
+		rc = TG_ERR_CANCELLED; // cancelled while the octree was being built
+		tg_model_destroy(model);
+		model = nullptr;
+	}
 	if (model)
 	{
 		tg_mesh mesh;
@@ -44,7 +52,7 @@ int RunExport(const tg_tree* tree, const std::string& path, const float mn[3], c
 		if (point_cloud)
 		{
 			// PointCloudExportThread only writes PLY (export.cpp:473-477)
-			rc = format == ExportFormat::PLY ? tg_export_points(model, mn, mx, step, refine, TG_MESH_NORMALS | TG_MESH_COLORS, scale, &mesh) : TG_ERR_INVALID;
+			rc = format == ExportFormat::PLY ? tg_export_points(model, mn, mx, step, refine, TG_MESH_NORMALS | TG_MESH_COLORS | TG_MESH_KEEP_CANCEL, scale, &mesh) : TG_ERR_INVALID;
 		}
 		else
 		{
@@ -54,13 +62,18 @@ int RunExport(const tg_tree* tree, const std::string& path, const float mn[3], c
 			{
 				tg_mesh_options options;
 				std::memset(&options, 0, sizeof(options));
-				options.flags = format == ExportFormat::STL ? TG_MESH_FACE_NORMALS : (TG_MESH_NORMALS | TG_MESH_COLORS);
+				options.flags = (format == ExportFormat::STL ? TG_MESH_FACE_NORMALS : (TG_MESH_NORMALS | TG_MESH_COLORS)) | TG_MESH_KEEP_CANCEL;
 				options.refine_iterations = refine;
 				options.scale = scale;
 				rc = tg_export_mesh(model, &grid, &options, &mesh);
 			}
 		}
-		if (rc == TG_OK)
+		if (rc == TG_OK && g_cancel.load())
+		{
+			rc = TG_ERR_CANCELLED; // no file is written for a cancelled export
+			tg_mesh_free(&mesh);
+		}
+		else if (rc == TG_OK)
 		{
 			g_stage.store(3);
 			rc = format == ExportFormat::STL ? tg_write_stl(path.c_str(), &mesh) : tg_write_ply(path.c_str(), &mesh);
@@ -86,6 +99,7 @@ void MeshExport(const tg_tree* Evaluator, std::string Path, const float ModelMin
 	int RefineIterations, ExportFormat Format, bool ExportPointCloud, float Scale)
 {
 	g_status.store(TG_OK);
+	g_cancel.store(false); // MeshExport re-arms ExportActive (export.cpp:568)
 	g_stage.store(1);
 	tg_tree* copy = tg_tree_copy(Evaluator); // the detached thread must not depend on the caller's lifetime
 	const float mn[3] = { ModelMin[0], ModelMin[1], ModelMin[2] };
@@ -111,6 +125,7 @@ void MeshExport(const tg_tree* Evaluator, std::string Path, const float ModelMin
 
 void CancelExport(bool Halt)
 {
+	g_cancel.store(true);
 	std::lock_guard<std::mutex> lock(g_state_lock);
 	if (g_active_context) tg_cancel(g_active_context, Halt ? 1 : 0);
 }
@@ -152,6 +167,7 @@ int ExportCommon(const tg_tree* Evaluator, float GridSize, int RefineIterations,
 	if (!Path || !(GridSize > 0.0f)) return TG_ERR_INVALID;
 	const float step = float(1.0 / GridSize);
 	const float steps[3] = { step, step, step };
+	g_cancel.store(false);
 	g_stage.store(1);
 	rc = RunExport(Evaluator, Path, mn, mx, steps, RefineIterations, Format, false, Scale);
 	Finish(rc);

@@ -430,7 +430,14 @@ struct Flattener
 			fn.flags = interp.cullable ? kNodeCullable : 0u;
 			const size_t count = interp.starts.size();
 			fn.flags |= uint32_t(std::min<size_t>(count, (1u << 24) - 1u)) << kNodeCountShift;
-			if (count >= kLongProgram) fn.flags |= kNodeLong;
+			if (count >= kLongProgram)
+			{
+				// Long programs carry a table of their instructions' quad offsets right in front of them (padded to whole
+				// quads): K0 evaluates such a program with one warp, every lane fetching its own instructions directly.
+				fn.flags |= kNodeLong;
+				for (size_t i = 0; i < count; ++i) model.interp.push_back(interp.starts[i]);
+				while (model.interp.size() % 4 != 0) model.interp.push_back(0);
+			}
 			fn.interp_offset = uint32_t(model.interp.size());
 			model.interp.insert(model.interp.end(), program.begin(), program.end());
 			StreamGen tree(st.pool, model.tree, true);
@@ -471,6 +478,9 @@ struct Flattener
 		{
 			FlatRegion region = { { lo[0], lo[1], lo[2] }, { hi[0], hi[1], hi[2] }, { 0.0f, 0.0f, 0.0f }, 0.0f, self, 0 };
 			model.regions.push_back(region);
+			const Vec3 extent = bn.bounds.max - bn.bounds.min;
+			model.leaf_nodes.push_back(self);
+			model.leaf_span.push_back(std::fmax(std::fmax(extent.x, extent.y), extent.z));
 			return self;
 		}
 		const float pivot[3] = { bn.pivot.x, bn.pivot.y, bn.pivot.z };

@@ -39,6 +39,12 @@ struct FlatModel
 	std::vector<uint32_t> tree;       // kStreamTree programs, addressed by FlatNode::tree_offset
 	std::vector<FlatRegion> regions;  // evaluation regions (tg_program.h), pre-order
 	std::vector<uint32_t> node_rank;  // position of every node when the nodes are sorted by program cost, costliest first
+	// Terminus cells of the octree, for the multi-GPU slab planner: node index, cell span, and -- filled by
+	// Model::Create on the device, one bit per 1/4-span sub-cell (x + 4 y + 16 z) -- whether the cell's program can have
+	// a zero there (|d(sub-cell centre)| <= its half diagonal).  Empty mask vector = nothing known (all set is assumed).
+	std::vector<uint32_t> leaf_nodes;
+	std::vector<float> leaf_span;
+	std::vector<uint64_t> leaf_mask;
 	std::vector<float> material_rgb;  // 3 floats per material id; one extra trailing entry = default white
 	uint32_t root_tree_offset = 0;    // kStreamTree program of the *unpruned* model (VoxExport samples it, magica.cpp:61)
 	uint32_t root_interp_offset = 0;  // kStreamInterp program of the unpruned model

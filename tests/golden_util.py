@@ -110,3 +110,43 @@ def vox_file_digests(path):
 
     walk(8, len(data))
     return {"vox_bytes": len(data), "vox_voxels": voxels, "vox_canonical_sha256": hashlib.sha256(bytes(data)).hexdigest()}
+
+
+# ---- layer-by-layer comparison with a tests/golden/slices_<workload>.json fixture (tests/golden/make_slices.py) -----
+# Used by tests/test_gpu_bench_parity.py and by bench.py's `parity` key (outside the timed region).
+
+def canonical_bits(a):
+    """float32 -> uint32 bit patterns with -0 -> +0 and every NaN -> 0x7fc00000 (oracle/ref_tool.cpp CanonicalBits)."""
+    a = np.ascontiguousarray(a, np.float32)
+    bits = a.view(np.uint32).copy()
+    bits[a == 0] = 0
+    bits[np.isnan(a)] = 0x7FC00000
+    return bits
+
+
+def sha16(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def layer_report(positions, normals, colors, triangles, fixture):
+    """Cuts a whole-grid mesh into cell layers by the reference's counts and compares every layer's digests.
+    Returns (layers, vertices compared, triangles compared, [(k, what) that differ])."""
+    pos = canonical_bits(positions)
+    nrm = canonical_bits(normals) if normals is not None else None
+    tri = np.ascontiguousarray(triangles, np.uint32)
+    bad = []
+    v = t = 0
+    if len(pos) != fixture["vertices"] or len(tri) != fixture["triangles"]:
+        return len(fixture["layers"]), 0, 0, [(-1, "counts: %d / %d vertices, %d / %d triangles" % (len(pos), fixture["vertices"], len(tri), fixture["triangles"]))]
+    for k, nv, nt, hp, hn, hc, ht in fixture["layers"]:
+        if sha16(pos[v:v + nv]) != hp:
+            bad.append((k, "positions"))
+        if nrm is not None and fixture["attributes"] and sha16(nrm[v:v + nv]) != hn:
+            bad.append((k, "normals"))
+        if colors is not None and fixture["has_color"] and sha16(colors[v:v + nv]) != hc:
+            bad.append((k, "colours"))
+        if sha16(tri[t:t + nt]) != ht:
+            bad.append((k, "triangles"))
+        v += nv
+        t += nt
+    return len(fixture["layers"]), v, t, bad

@@ -440,3 +440,49 @@ def test_capacity_overflow_is_retried_with_exact_sizes(models, oracles, monkeypa
     mesh = model.export_mesh(g)
     assert mesh.vertex_count == len(v) and np.array_equal(mesh.triangles, tris)
     mesh.close()
+
+
+def _device_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("name,scale", [("kitchen_sink", 2), ("seaside_town", 24)])
+def test_multi_gpu_context_returns_the_single_gpu_mesh(name, scale, golden):
+    """tg_context_create_multi: one call, z-slabs on every device, vertex counts all-gathered with
+    NCCL on the devices, one stitched host mesh -- array for array the mesh one GPU produces.  Needs >= 2 devices."""
+    n = _device_count()
+    if n < 2:
+        pytest.skip("needs at least two CUDA devices")
+    tree = T.Tree.load(O.model_path(name))
+    single_ctx = T.Context(0)
+    single = T.Model(single_ctx, tree)
+    grid = _grid(tree, golden[name]["cells_per_unit"] * scale)
+    want = single.export_mesh(grid, refine=0)
+    for devices in ([0, 1], list(range(n))):
+        ctx = T.Context(devices=devices)
+        assert ctx.device_count == len(devices)
+        model = T.Model(ctx, tree)
+        for _ in range(2):  # the second export runs on cached capacities and pinned blocks
+            got = model.export_mesh(grid, refine=0)
+            assert got.vertex_count == want.vertex_count and got.triangle_count == want.triangle_count
+            assert np.array_equal(got.positions, want.positions)
+            assert same_floats(got.normals, want.normals)
+            assert (got.colors is None) == (want.colors is None)
+            if want.colors is not None:
+                assert np.array_equal(got.colors, want.colors)
+            assert np.array_equal(got.triangles, want.triangles)
+            ranks = got.rank_info()
+            if grid.shape[2] >= 16 * len(devices):
+                assert len(ranks) == len(devices) and ranks[0][0] == 0 and ranks[-1][1] == grid.shape[2]
+            got.close()
+        model.close()
+        ctx.close()
+        if n == 2:
+            break
+    want.close()
+    single.close()
+    single_ctx.close()
