@@ -424,6 +424,40 @@ def measure_workload(T, ctx, workload, steps, warmup, flags_extra=0, with_parity
     return out, (tgm, lo, hi, float(np.float32(step)), grid.shape)
 
 
+def join_ranks(backend, device=None):
+    """The launch contract's rendezvous (one rank per GPU, launched by torch.distributed.run): every rank joins one
+    process group of `backend` and proves it with an all-reduce; then the ranks > 0 only have to wait for rank 0, which
+    they do in a gloo group -- on the host, not with a collective kernel spinning on their GPU.  Returns
+    (rank, world, waiting group or None)."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:
+        return rank, world, None
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    if device is not None:
+        dist.init_process_group(backend, device_id=device)
+    else:
+        dist.init_process_group(backend)
+    t = torch.ones(1, device=device if device is not None else "cpu")
+    dist.all_reduce(t)
+    if device is not None:
+        torch.cuda.synchronize()
+    assert int(t.item()) == world, "rendezvous: %d of %d ranks answered" % (int(t.item()), world)
+    waiters = dist.new_group(backend="gloo")
+    return rank, world, waiters
+
+
+def leave_ranks(waiters):
+    """Ranks > 0: wait for rank 0 to finish; rank 0: release them.  Then tear the group down."""
+    import torch.distributed as dist
+    if waiters is not None:
+        dist.barrier(group=waiters)
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -441,29 +475,16 @@ def main():
         return reference_arm(args, args.workload)
 
     import torch
-    import torch.distributed as dist
     import tangerine_b200 as T
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: tangerine_b200 has no CPU path")
     torch.cuda.set_device(local)
-    waiters = None
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        t = torch.ones(1, device="cuda")
-        dist.all_reduce(t)                      # the launch contract's rendezvous: every rank's GPU joins one NCCL communicator
-        torch.cuda.synchronize()
-        assert int(t.item()) == world
-        waiters = dist.new_group(backend="gloo")    # ranks > 0 wait on the host, not with a kernel spinning on their GPU
+    rank, world, waiters = join_ranks("nccl", torch.device("cuda", local))
     if rank != 0:
         # The export is ONE call in ONE process driving every GPU of the box (tg_context_create_multi): rank 0 makes it.
-        dist.barrier(group=waiters)
-        dist.destroy_process_group()
+        leave_ranks(waiters)
         return 0
 
     devices = list(range(world))
@@ -563,9 +584,7 @@ def main():
     }
     print(json.dumps(line))
     ctx.close()
-    if world > 1:
-        dist.barrier(group=waiters)
-        dist.destroy_process_group()
+    leave_ranks(waiters)
     return 0
 
 

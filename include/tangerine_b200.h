@@ -173,6 +173,11 @@ TG_API int tg_model_get_stats(const tg_model* model, tg_model_stats* out);
 enum { TG_EVAL_OCTREE = 0, TG_EVAL_INTERP = 1, TG_EVAL_TREE = 2, TG_EVAL_GRADIENT = 3, TG_EVAL_COLOR = 4 };
 TG_API int tg_eval_points(tg_model* model, int mode, const float* points, uint64_t count, void* out);
 
+/* Self-check used by the tests: the culling pass evaluates long programs cooperatively (a warp or a block per point,
+ * parallel fold); this runs every long program of the model at 9 points within `reach` of its octree node's pivot both
+ * ways and returns { probes, disagreements of the block form, disagreements of the warp form } -- the last two must be 0. */
+TG_API int tg_debug_check_long_programs(tg_model* model, float reach, uint64_t out_counts[3]);
+
 /* ------------------------------------------------------------------------------------------------
  * Mesh export.  Replaces the span export.cpp:324-365 (grid set-up, isosurface::par_surface_nets with
  * the octree as implicit function, mesh conversion) plus the per-vertex attribute loops

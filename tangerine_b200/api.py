@@ -149,6 +149,7 @@ def lib():
         "tg_model_get_stats": (i32, [vp, C.POINTER(ModelStats)]),
         "tg_eval_points": (i32, [vp, i32, fp, u64, vp]),
         "tg_export_grid": (i32, [fp, fp, fp, C.POINTER(Grid)]),
+        "tg_debug_check_long_programs": (i32, [vp, C.c_float, C.POINTER(u64)]),
         "tg_export_mesh": (i32, [vp, C.POINTER(Grid), C.POINTER(MeshOptions), C.POINTER(_Mesh)]),
         "tg_mesh_free": (None, [C.POINTER(_Mesh)]),
         "tg_mesh_download": (i32, [C.POINTER(_Mesh), u32]),
@@ -524,6 +525,11 @@ class Model:
             out = np.zeros(n, np.float32)
         _check(lib().tg_eval_points(self.h, mode, _fp(pts), n, out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def check_long_programs(self, reach=0.5):
+        out = (C.c_uint64 * 3)()
+        _check(lib().tg_debug_check_long_programs(self.h, reach, out))
+        return tuple(int(v) for v in out)
 
     def eval_lattice(self, grid, download=True, flags=0):
         sx, sy, sz = grid.shape

@@ -582,6 +582,15 @@ int tg_eval_points(tg_model* model, int mode, const float* points, uint64_t coun
 }
 TG_CATCH_STATUS
 
+int tg_debug_check_long_programs(tg_model* model, float reach, uint64_t out_counts[3]) try
+{
+	if (!model || !out_counts) return Fail(TG_ERR_INVALID, "null argument");
+	std::string error;
+	int rc = EngineCheckLongPrograms(model->impl.get(), reach, out_counts, error);
+	return rc == TG_OK ? rc : Fail(rc, error);
+}
+TG_CATCH_STATUS
+
 int tg_export_grid(const float mn[3], const float mx[3], const float step[3], tg_grid* out) try
 {
 	if (!mn || !mx || !step || !out) return Fail(TG_ERR_INVALID, "null argument");

@@ -410,14 +410,10 @@ __device__ __forceinline__ void FoldStep(uint32_t word, float v, float param, fl
 	else if (code == kFoldStackOp) acc = sdf::SetOp(word >> 16, stack[(word >> 8) & 0xFFu], acc, v);
 }
 
-// Brush distance and fold code of instruction `pc` at (x, y, z).
-__device__ __forceinline__ void LongStep(const uint4* __restrict__ pc, float x, float y, float z, uint2& step, float& param)
+// Brush distance and fold code of one instruction (header quad q, the four quads behind it) at (x, y, z).
+__device__ __forceinline__ void LongStepLoaded(const uint4& q, const float4& m0, const float4& m1, const float4& m2, const float4& m3,
+	float x, float y, float z, uint2& step, float& param)
 {
-	const uint4 q = __ldg(pc);
-	const float4 m0 = __ldg(reinterpret_cast<const float4*>(pc + 1));
-	const float4 m1 = __ldg(reinterpret_cast<const float4*>(pc + 2));
-	const float4 m2 = __ldg(reinterpret_cast<const float4*>(pc + 3));
-	const float4 m3 = __ldg(reinterpret_cast<const float4*>(pc + 4));
 	const uint32_t header = q.x;
 	const uint32_t brush = header & kHdrBrushMask;
 	const uint32_t op = (header >> kHdrOpShift) & 0xFu;
@@ -466,6 +462,16 @@ __device__ __forceinline__ void LongStep(const uint4* __restrict__ pc, float x, 
 	step = make_uint2(code | (slot << 8) | (op << 16), __float_as_uint(value));
 }
 
+__device__ __forceinline__ void LongStep(const uint4* __restrict__ pc, float x, float y, float z, uint2& step, float& param)
+{
+	LongStepLoaded(__ldg(pc), __ldg(reinterpret_cast<const float4*>(pc + 1)), __ldg(reinterpret_cast<const float4*>(pc + 2)),
+		__ldg(reinterpret_cast<const float4*>(pc + 3)), __ldg(reinterpret_cast<const float4*>(pc + 4)), x, y, z, step, param);
+}
+
+// Test hook (tg_debug_check_long_programs): bit 0 skips pass a, bit 1 pass b, bit 2 the batched loads of GroupEvalLong, so
+// that a disagreement with the plain interpreter can be pinned on one of them.  0 in normal operation.
+__device__ int g_long_debug = 0;
+
 // Clamp x -> min(max(x, lo), hi) as a value; Then() composes "this first, g second".
 struct Clamp
 {
@@ -508,6 +514,62 @@ __device__ __forceinline__ void CollapseInto(uint2* steps, float* params, uint32
 	params[at] = threshold;
 }
 
+// Ordered composition of every thread's clamp (thread 0's first); thread 0 of the group gets the total.  Warp level by
+// shuffles (compose mine, then the partner's -- the operator is associative, not commutative), across the warps of a
+// block through `share`.
+template <int GROUP>
+__device__ __forceinline__ Clamp ComposeGroup(Clamp c, float2* share)
+{
+	const int lane = threadIdx.x & 31;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		const float plo = __shfl_down_sync(0xFFFFFFFFu, c.lo, o), phi = __shfl_down_sync(0xFFFFFFFFu, c.hi, o);
+		if (lane + o < 32) c.Then(plo, phi);
+	}
+	if (GROUP == 32) return c;
+	if (lane == 0) share[threadIdx.x >> 5] = make_float2(c.lo, c.hi);
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		for (int w = 1; w < GROUP / 32; ++w) c.Then(share[w].x, share[w].y);
+	}
+	__syncthreads();
+	return c;
+}
+
+// Exclusive prefix of a per-thread count over the group, and the group total.
+template <int GROUP>
+__device__ __forceinline__ uint32_t PrefixGroup(uint32_t mine, uint32_t* marks, uint32_t& total)
+{
+	const int lane = threadIdx.x & 31;
+	uint32_t incl = mine;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+		if (lane >= o) incl += v;
+	}
+	if (GROUP == 32)
+	{
+		total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+		return incl - mine;
+	}
+	const int warp = threadIdx.x >> 5;
+	if (lane == 31) marks[warp] = incl;
+	__syncthreads();
+	uint32_t base = 0;
+	total = 0;
+	for (int w = 0; w < GROUP / 32; ++w)
+	{
+		const uint32_t m = marks[w];
+		if (w < warp) base += m;
+		total += m;
+	}
+	__syncthreads();
+	return base + incl - mine;
+}
+
 // GROUP = 32: the calling warp works alone (tid = lane; `steps`, `params`, `share`, `marks`, `result_out` are its own
 // slices of the scratch); GROUP = kLongThreads: the whole block.  Every thread of the group must call; all get the value.
 //
@@ -548,11 +610,37 @@ __device__ __forceinline__ float GroupEvalLong(const uint4* __restrict__ program
 		return *result_out;
 	}
 	const uint32_t n = count;
-	for (uint32_t i = tid; i < n; i += GROUP) LongStep(program + __ldg(&table[i]), x, y, z, steps[i], params[i]);
+	// brush distances, four instructions per thread at a time: the four table entries travel together, then the twenty
+	// operand quads (two memory round trips per batch instead of eight)
+	for (uint32_t first = tid; first < n; first += GROUP * 4)
+	{
+		uint32_t at[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) at[u] = __ldg(&table[min(first + uint32_t(u) * GROUP, n - 1u)]);
+		uint4 q[4];
+		float4 m0[4], m1[4], m2[4], m3[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+		{
+			const uint4* pc = program + at[u];
+			q[u] = __ldg(pc);
+			m0[u] = __ldg(reinterpret_cast<const float4*>(pc + 1));
+			m1[u] = __ldg(reinterpret_cast<const float4*>(pc + 2));
+			m2[u] = __ldg(reinterpret_cast<const float4*>(pc + 3));
+			m3[u] = __ldg(reinterpret_cast<const float4*>(pc + 4));
+		}
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+		{
+			const uint32_t i = first + uint32_t(u) * GROUP;
+			if (i < n) LongStepLoaded(q[u], m0[u], m1[u], m2[u], m3[u], x, y, z, steps[i], params[i]);
+		}
+	}
 	sync();
 
 	// a. operands two deep
-	for (uint32_t i = tid; i < n; i += GROUP)
+	const int debug = g_long_debug;
+	for (uint32_t i = tid; i < n && !(debug & 1); i += GROUP)
 	{
 		if ((steps[i].x & 0xFFFFu) != (kFoldPush | (1u << 8))) continue;
 		float acc = __uint_as_float(steps[i].y);
@@ -580,16 +668,8 @@ __device__ __forceinline__ float GroupEvalLong(const uint4* __restrict__ program
 		const uint32_t key = steps[i].x & 0xFFFFu;
 		mine += (key == (kFoldPush | (0u << 8)) ? 1u : 0u) + (key == (kFoldStackOp | (0u << 8)) ? 0x10000u : 0u);
 	}
-	marks[tid] = mine;
-	sync();
-	uint32_t before = 0, total = 0;
-	for (int t = 0; t < GROUP; ++t) // GROUP <= 256 adds from shared memory: a fraction of a microsecond
-	{
-		const uint32_t m = marks[t];
-		if (t < tid) before += m;
-		total += m;
-	}
-	sync();
+	uint32_t total = 0;
+	const uint32_t before = PrefixGroup<GROUP>(mine, marks, total);
 	// the lists reuse `share` (x: position of the k-th opening, y: of the k-th closing), as bit patterns
 	const uint32_t operands = min(total & 0xFFFFu, total >> 16);
 	{
@@ -603,7 +683,7 @@ __device__ __forceinline__ float GroupEvalLong(const uint4* __restrict__ program
 	}
 	sync();
 	constexpr uint32_t kShortOperand = 48;
-	bool walk_all = operands > uint32_t(GROUP); // more operands than list entries: one thread walks the whole program
+	bool walk_all = operands > uint32_t(GROUP) || (debug & 2) != 0; // more operands than list entries: one thread walks the whole program
 	uint32_t my_open = 0, my_close = 0;
 	if (!walk_all && uint32_t(tid) < operands)
 	{
@@ -647,17 +727,14 @@ __device__ __forceinline__ float GroupEvalLong(const uint4* __restrict__ program
 			const uint32_t b0 = o + min(len, uint32_t(tid) * part), b1 = o + min(len, uint32_t(tid + 1) * part);
 			Clamp mineclamp = { -INFINITY, INFINITY };
 			const bool clamps_only = ComposeShare(steps, b0, b1, o, mineclamp);
-			share[tid] = make_float2(mineclamp.lo, mineclamp.hi);
 			const bool all_clamps = GROUP == 32 ? __all_sync(0xFFFFFFFFu, clamps_only) : (__syncthreads_and(clamps_only ? 1 : 0) != 0);
-			sync();
+			const Clamp whole = ComposeGroup<GROUP>(mineclamp, share);
 			if (tid == 0)
 			{
 				float value;
 				if (all_clamps)
 				{
-					Clamp t = { -INFINITY, INFINITY };
-					for (int k = 0; k < GROUP; ++k) t.Then(share[k].x, share[k].y);
-					value = t.hi; // the chain opens with a constant, so lo == hi
+					value = whole.hi; // the chain opens with a constant, so lo == hi
 				}
 				else
 				{
@@ -666,8 +743,9 @@ __device__ __forceinline__ float GroupEvalLong(const uint4* __restrict__ program
 					for (uint32_t j = o + 1; j < c; ++j) FoldStep(steps[j].x, __uint_as_float(steps[j].y), params[j], acc, stack);
 					value = acc;
 				}
-				CollapseInto(steps, params, c, value);
+				CollapseInto(steps, params, c, value); // (c itself lies outside every share)
 			}
+			sync(); // thread 0 may have walked the steps: nobody erases them before it is done
 			for (uint32_t k = b0; k < b1; ++k) steps[k].x = kFoldNop | (kNoSlot << 8);
 			sync();
 		}
@@ -678,17 +756,14 @@ __device__ __forceinline__ float GroupEvalLong(const uint4* __restrict__ program
 	// c. the main chain
 	Clamp chain = { -INFINITY, INFINITY };
 	const bool clamps_only = walk_all ? false : ComposeShare(steps, lo_i, hi_i, 0u, chain);
-	share[tid] = make_float2(chain.lo, chain.hi);
 	const bool all_clamps = GROUP == 32 ? __all_sync(0xFFFFFFFFu, clamps_only) : (__syncthreads_and(clamps_only ? 1 : 0) != 0);
-	sync();
+	const Clamp whole = ComposeGroup<GROUP>(chain, share);
 	if (tid == 0)
 	{
 		float acc = 0.0f;
 		if (all_clamps)
 		{
-			Clamp t = { -INFINITY, INFINITY };
-			for (int k = 0; k < GROUP; ++k) t.Then(share[k].x, share[k].y);
-			acc = fminf(fmaxf(acc, t.lo), t.hi);
+			acc = fminf(fmaxf(acc, whole.lo), whole.hi);
 		}
 		else
 		{

@@ -155,9 +155,11 @@ __device__ __forceinline__ bool KnownEmpty(const DeviceModel& model, const FlatR
 	return region.known_value > reach * 1.001f + 1.0e-4f;
 }
 
+// One WARP per region: the lanes share the region's scalars and spread its seed items (up to kSeedSpan^3) between them.
 __global__ void __launch_bounds__(128) CullRegionInitKernel(const CullParams p)
 {
-	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t lane = threadIdx.x & 31u;
 	if (r >= p.model.region_count) return;
 	const FlatRegion region = p.model.regions[r];
 	const DeviceGrid& g = p.grid;
@@ -176,14 +178,17 @@ __global__ void __launch_bounds__(128) CullRegionInitKernel(const CullParams p)
 	a[2] = max(a[2], p.sample_k_lo);
 	b[2] = empty ? 0u : min(b[2], p.sample_k_hi);
 	empty = empty || a[0] > b[0] || a[1] > b[1] || a[2] > b[2];
-	RegionRange range;
-#pragma unroll
-	for (int ax = 0; ax < 3; ++ax)
+	if (lane == 0)
 	{
-		range.a[ax] = uint16_t(empty ? 1u : a[ax]);
-		range.b[ax] = uint16_t(empty ? 0u : b[ax]);
+		RegionRange range;
+#pragma unroll
+		for (int ax = 0; ax < 3; ++ax)
+		{
+			range.a[ax] = uint16_t(empty ? 1u : a[ax]);
+			range.b[ax] = uint16_t(empty ? 0u : b[ax]);
+		}
+		p.ranges[r] = range;
 	}
-	p.ranges[r] = range;
 	if (empty) return;
 	// cells that use these samples: [a - 1, b], clipped to the grid / slab
 	uint32_t clo[3], chi[3];
@@ -204,36 +209,40 @@ __global__ void __launch_bounds__(128) CullRegionInitKernel(const CullParams p)
 	}
 	const int sh = 3 + level;
 	const uint32_t x0 = clo[0] >> sh, x1 = chi[0] >> sh, y0 = clo[1] >> sh, y1 = chi[1] >> sh, z0 = clo[2] >> sh, z1 = chi[2] >> sh;
-	const uint32_t n = (x1 - x0 + 1u) * (y1 - y0 + 1u) * (z1 - z0 + 1u);
+	const uint32_t nx = x1 - x0 + 1u, ny = y1 - y0 + 1u;
+	const uint32_t n = nx * ny * (z1 - z0 + 1u);
+	auto cell_of = [&](uint32_t i, uint32_t& x, uint32_t& y, uint32_t& z)
+	{
+		x = x0 + i % nx;
+		y = y0 + (i / nx) % ny;
+		z = z0 + i / (nx * ny);
+	};
+	uint32_t flag_bits = 0u; // nonzero: nothing is queued, every brick under these cells gets these bits instead
+	uint32_t base = 0;
+	CullItem* list = nullptr;
 	if (KnownEmpty(p.model, region, g, a[0], b[0], a[1], b[1], a[2], b[2]))
 	{
-		// the octree build already proved this whole region empty (outside): flag its bricks, queue nothing
-		for (uint32_t z = z0; z <= z1; ++z)
-			for (uint32_t y = y0; y <= y1; ++y)
-				for (uint32_t x = x0; x <= x1; ++x)
-					atomicOr(&p.flags[level][(size_t(z) * p.dims[level][1] + y) * p.dims[level][0] + x], kFlagPositive);
-		return;
+		flag_bits = kFlagPositive; // the octree build already proved this whole region empty (outside)
 	}
-	const bool is_long = (__ldg(&p.model.nodes[region.node].flags) & kNodeLong) != 0u;
-	CullItem* list = is_long ? p.long_lists[level] : p.lists[level];
-	const uint32_t base = atomicAdd(&p.counts[is_long ? kCullLevels + level : level], n);
-	if (base + n > (is_long ? p.long_capacity[level] : p.capacity[level]))
+	else
 	{
-		// cannot queue: ask for every brick under these cells to be evaluated
-		for (uint32_t z = z0; z <= z1; ++z)
-			for (uint32_t y = y0; y <= y1; ++y)
-				for (uint32_t x = x0; x <= x1; ++x)
-					atomicOr(&p.flags[level][(size_t(z) * p.dims[level][1] + y) * p.dims[level][0] + x], kFlagEvaluate);
-		return;
+		const bool is_long = (__ldg(&p.model.nodes[region.node].flags) & kNodeLong) != 0u;
+		list = is_long ? p.long_lists[level] : p.lists[level];
+		if (lane == 0) base = atomicAdd(&p.counts[is_long ? kCullLevels + level : level], n);
+		base = __shfl_sync(0xFFFFFFFFu, base, 0);
+		if (base + n > (is_long ? p.long_capacity[level] : p.capacity[level])) flag_bits = kFlagEvaluate; // cannot queue
 	}
-	uint32_t o = base;
-	for (uint32_t z = z0; z <= z1; ++z)
-		for (uint32_t y = y0; y <= y1; ++y)
-			for (uint32_t x = x0; x <= x1; ++x)
-			{
-				CullItem item = { r, x | (y << 10) | (z << 20) };
-				list[o++] = item;
-			}
+	for (uint32_t i = lane; i < n; i += 32u)
+	{
+		uint32_t x, y, z;
+		cell_of(i, x, y, z);
+		if (flag_bits) atomicOr(&p.flags[level][(size_t(z) * p.dims[level][1] + y) * p.dims[level][0] + x], flag_bits);
+		else
+		{
+			CullItem item = { r, x | (y << 10) | (z << 20) };
+			list[base + i] = item;
+		}
+	}
 }
 
 // What both item kernels decide first: the sample box of the item's brick inside its region.
@@ -457,6 +466,47 @@ __global__ void __launch_bounds__(kLongThreads) CullLongKernel(const CullParams 
 		if (steps <= uint32_t(kLongWarpSteps)) continue;
 		CullLongItem<kLongThreads>(p, level, item, scratch);
 		__syncthreads();
+	}
+}
+
+// Self-check of the cooperative evaluation (tg_debug_check_long_programs): every long program at a few points around
+// its node's pivot, by the whole block, by one warp (when it fits) and by one thread walking it; counts disagreements.
+__global__ void __launch_bounds__(kLongThreads) LongEvalCheckKernel(const DeviceModel model, float reach, unsigned long long* __restrict__ out)
+{
+	__shared__ LongScratch scratch;
+	__shared__ float reference;
+	for (uint32_t node = blockIdx.x; node < model.node_count; node += gridDim.x)
+	{
+		const uint32_t flags = __ldg(&model.nodes[node].flags);
+		if ((flags & kNodeLong) == 0u) continue;
+		const uint32_t count = flags >> kNodeCountShift;
+		const uint4* program = model.interp + (__ldg(&model.nodes[node].interp_offset) >> 2);
+		const float4 head = __ldg(reinterpret_cast<const float4*>(&model.nodes[node]));
+		for (int probe = 0; probe < 9; ++probe)
+		{
+			const float x = head.x + (probe == 0 ? 0.0f : ((probe & 1) ? reach : -reach) * float(probe) * 0.25f);
+			const float y = head.y + (probe == 0 ? 0.0f : ((probe & 2) ? reach : -reach) * float(probe) * 0.25f);
+			const float z = head.z + (probe == 0 ? 0.0f : ((probe & 4) ? reach : -reach) * float(probe) * 0.25f);
+			if (threadIdx.x == 0) reference = EvalInterp1(model, __ldg(&model.nodes[node].interp_offset), x, y, z);
+			__syncthreads();
+			const float by_block = GroupEvalLong<kLongThreads>(program, count, x, y, z, scratch.step, scratch.param, scratch.share, scratch.marks, scratch.result, kLongBlockSteps);
+			__syncthreads();
+			float by_warp = by_block;
+			if (count <= uint32_t(kLongWarpSteps) && threadIdx.x < 32)
+			{
+				by_warp = GroupEvalLong<32>(program, count, x, y, z, scratch.step, scratch.param, scratch.share, scratch.marks, scratch.result, kLongWarpSteps);
+			}
+			__syncthreads();
+			if (threadIdx.x == 0)
+			{
+				atomicAdd(&out[0], 1ull);
+				const bool same_block = by_block == reference || (by_block != by_block && reference != reference);
+				const bool same_warp = by_warp == reference || (by_warp != by_warp && reference != reference);
+				if (!same_block) atomicAdd(&out[1], 1ull);
+				if (!same_warp) atomicAdd(&out[2], 1ull);
+			}
+			__syncthreads();
+		}
 	}
 }
 
@@ -2202,7 +2252,7 @@ static int BuildCullFlags(Model* model, cudaStream_t stream, Scratch& scratch, c
 		cp.long_capacity[level] = cp.capacity[level]; // dense scenes (10k primitives) have long programs in most regions
 		TG_CUDA(scratch.Alloc(&cp.long_lists[level], cp.long_capacity[level]));
 	}
-	CullRegionInitKernel<<<(cp.model.region_count + 127) / 128, 128, 0, stream>>>(cp);
+	CullRegionInitKernel<<<(cp.model.region_count + 3) / 4, 128, 0, stream>>>(cp); // a warp per region
 	launches++;
 	// Levels run top-down with grids sized for the level's capacity bound by what can actually arrive
 	// (threads beyond the device-side count exit at once), so no count is read back between levels.
@@ -3321,6 +3371,29 @@ int EngineEvalLattice(Model* model, const tg_grid& grid_in, uint32_t flags, floa
 	if (out) TG_CUDA(cudaMemcpyAsync(out, d_out, total * 4, cudaMemcpyDeviceToHost, stream));
 	TG_CUDA(cudaStreamSynchronize(stream));
 	if (out_ms) *out_ms = timer.Ms(t0, t1);
+	return TG_OK;
+}
+
+int EngineCheckLongPrograms(Model* model, float reach, uint64_t out[3], std::string& error)
+{
+	Context* ctx = model->context;
+	TG_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t stream = StreamOf(ctx);
+	int debug = 0;
+	if (const char* env = std::getenv("TG_LONG_DEBUG")) debug = std::atoi(env);
+	TG_CUDA(cudaMemcpyToSymbolAsync(g_long_debug, &debug, sizeof(int), 0, cudaMemcpyHostToDevice, stream));
+	Scratch scratch(ctx);
+	unsigned long long* d = nullptr;
+	TG_CUDA(scratch.Alloc(&d, 4));
+	TG_CUDA(cudaMemsetAsync(d, 0, 32, stream));
+	LongEvalCheckKernel<<<uint32_t(ctx->sm_count) * 4u, kLongThreads, 0, stream>>>(MakeDeviceModel(model), reach, d);
+	TG_CUDA(cudaGetLastError());
+	unsigned long long host[3] = { 0, 0, 0 };
+	TG_CUDA(cudaMemcpyAsync(host, d, 24, cudaMemcpyDeviceToHost, stream));
+	TG_CUDA(cudaStreamSynchronize(stream));
+	for (int i = 0; i < 3; ++i) out[i] = host[i];
+	debug = 0;
+	TG_CUDA(cudaMemcpyToSymbol(g_long_debug, &debug, sizeof(int)));
 	return TG_OK;
 }
 

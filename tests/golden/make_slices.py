@@ -34,6 +34,8 @@ WORKLOADS = {
     "seaside512": ("seaside_town", 10.0 / 510.0),
     "seaside1024": ("seaside_town", 10.0 / 1022.0),
     "synthetic256": ("synthetic:10000", 10.0 / 254.0),
+    "synthetic512": ("synthetic:10000", 10.0 / 510.0),
+    "synthetic1024": ("synthetic:10000", 10.0 / 1022.0),
 }
 
 

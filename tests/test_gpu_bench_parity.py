@@ -41,7 +41,7 @@ def context():
     ctx.close()
 
 
-@pytest.mark.parametrize("workload", ["basic66", "gear512", "colorcube512", "seaside512", "seaside1024", "synthetic256"])
+@pytest.mark.parametrize("workload", ["basic66", "gear512", "colorcube512", "seaside512", "seaside1024", "synthetic256", "synthetic512", "synthetic1024"])
 def test_benched_grid_matches_reference_layer_by_layer(workload, context):
     fx = load_fixture(workload)
     tree = workload_tree(fx["model"])

@@ -486,3 +486,14 @@ def test_multi_gpu_context_returns_the_single_gpu_mesh(name, scale, golden):
     want.close()
     single.close()
     single_ctx.close()
+
+
+@pytest.mark.parametrize("name", ["seaside_town", "gear", "color-cube", "kitchen_sink", "synthetic200", "stencil_test"])
+@pytest.mark.parametrize("reach", [0.05, 0.7, 4.0])
+def test_cooperative_long_program_evaluation_is_exact(name, reach, models):
+    """K0 evaluates long programs with a warp / a block per point and folds the operator chain in parallel (clamps
+    compose associatively, tg_device.cuh GroupEvalLong).  Every long program of the model, at points near and far from
+    its node, must give the bits the plain interpreter gives."""
+    tree, model = models(name)
+    probes, block_bad, warp_bad = model.check_long_programs(reach)
+    assert block_bad == 0 and warp_bad == 0, (probes, block_bad, warp_bad)
