@@ -173,10 +173,19 @@ TG_API int tg_model_get_stats(const tg_model* model, tg_model_stats* out);
 enum { TG_EVAL_OCTREE = 0, TG_EVAL_INTERP = 1, TG_EVAL_TREE = 2, TG_EVAL_GRADIENT = 3, TG_EVAL_COLOR = 4 };
 TG_API int tg_eval_points(tg_model* model, int mode, const float* points, uint64_t count, void* out);
 
+/* Batched ray casts: SDFNode::RayMarch (tangerine/sdf_evaluator.cpp:336-354) on the unpruned model, the call behind the
+ * Lua methods `ray_cast` and `magnet` (lua_sdf.cpp:410-444, 745-749; their defaults are max_iterations = 100,
+ * epsilon = 0.001).  rays: 6 floats each, origin then direction (magnet != 0: origin then TARGET, the direction being
+ * normalize(target - origin)).  out_hits: 5 floats per ray -- hit (1 or 0), travel (infinity on a miss), position. */
+TG_API int tg_ray_cast(tg_model* model, const float* rays, uint64_t count, int max_iterations, float epsilon, int magnet, float* out_hits);
+
 /* Self-check used by the tests: the culling pass evaluates long programs cooperatively (a warp or a block per point,
  * parallel fold); this runs every long program of the model at 9 points within `reach` of its octree node's pivot both
  * ways and returns { probes, disagreements of the block form, disagreements of the warp form } -- the last two must be 0. */
 TG_API int tg_debug_check_long_programs(tg_model* model, float reach, uint64_t out_counts[3]);
+/* Diagnostics: the device instruction stream (kStreamInterp words, tangerine_b200/csrc/tg_program.h) of one octree node,
+ * built on the host.  Returns the word count (0 = no such node). */
+TG_API uint64_t tg_debug_node_program(const tg_tree* tree, uint32_t node, uint32_t* out_words, uint64_t capacity, uint32_t* out_instruction_count);
 
 /* ------------------------------------------------------------------------------------------------
  * Mesh export.  Replaces the span export.cpp:324-365 (grid set-up, isosurface::par_surface_nets with

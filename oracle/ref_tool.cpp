@@ -440,7 +440,7 @@ static int Usage()
 		"  dump-tgm  <model.lua|.tgm> <out.tgm>\n"
 		"  info      <model>                                  bounds / tree / octree statistics + hash (JSON)\n"
 		"  octree    <model> <out.bin>                        dump every octree node's pruned program\n"
-		"  eval      <model> <mode> <points.f32> <out.bin>    mode: octree | tree | interp | gradient | color | clipnull\n"
+		"  eval      <model> <mode> <points.f32> <out.bin>    mode: octree | tree | interp | gradient | color | raycast | magnet (6 floats per ray)\n"
 		"  export    <model> <cells_per_unit> <refine> <out.ply|.stl>   reference ExportCommon (as shipped)\n"
 		"  export-grid <model> <minx miny minz maxx maxy maxz> <step> <refine> <pointcloud 0|1> <out.ply|.stl>\n"
 		"  vox       <model> <grid_size> <color_index> <out.vox>\n"
@@ -496,6 +496,27 @@ static int CmdEval(SDFNodeShared Tree, const std::string& Mode, const char* Poin
 	size_t Count = Points.size() / 3;
 	FILE* Out = std::fopen(OutPath, "wb");
 	if (!Out) return 2;
+	if (Mode == "raycast" || Mode == "magnet")
+	{
+		// SDFNode::RayMarch on the model, with the Lua binding's defaults (lua_sdf.cpp:410-444): 6 floats per ray in,
+		// { u32 hit, f32 travel, f32 position[3] } out
+		for (size_t i = 0; i + 1 < Count; i += 2)
+		{
+			vec3 Origin(Points[i * 3 + 0], Points[i * 3 + 1], Points[i * 3 + 2]);
+			vec3 Direction(Points[i * 3 + 3], Points[i * 3 + 4], Points[i * 3 + 5]);
+			if (Mode == "magnet")
+			{
+				Direction = glm::normalize(Direction - Origin);
+			}
+			RayHit Hit = Tree->RayMarch(Origin, Direction, 100, 0.001f);
+			uint32_t Flag = Hit.Hit ? 1 : 0;
+			std::fwrite(&Flag, 4, 1, Out);
+			std::fwrite(&Hit.Travel, 4, 1, Out);
+			std::fwrite(&Hit.Position, 4, 3, Out);
+		}
+		std::fclose(Out);
+		return 0;
+	}
 	SDFOctreeShared Octree = SDFOctree::Create(Tree, 0.25);
 	SDFInterpreter Root(Tree);
 	const bool ExportColor = Tree->HasPaint();

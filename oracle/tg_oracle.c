@@ -1226,6 +1226,43 @@ void tgo_eval_tree(const TgoModel* m, const float* points, uint64_t count, float
 	parallel_for(count, threads, eval_tree_range, &c);
 }
 
+/* SDFNode::RayMarch (sdf_evaluator.cpp:336-354) on the unpruned tree, as the Lua ray_cast / magnet calls run it
+ * (lua_sdf.cpp:410-444).  rays: 6 floats each (origin, direction); out5: hit (1.0 / 0.0), travel, position xyz. */
+void tgo_ray_march(const TgoModel* m, const float* rays, uint64_t count, int max_iterations, float epsilon, int magnet, float* out5)
+{
+	for (uint64_t i = 0; i < count; ++i)
+	{
+		v3 start = V3(rays[i * 6], rays[i * 6 + 1], rays[i * 6 + 2]);
+		v3 dir = V3(rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]);
+		if (magnet) /* Direction = normalize(Direction - Origin), lua_sdf.cpp:419-422 */
+		{
+			v3 d = sub3(dir, start);
+			dir = muls3(d, 1.0f / sqrtf(dot3(d, d)));
+		}
+		dir = muls3(dir, 1.0f / sqrtf(dot3(dir, dir))); /* glm::normalize = v * inversesqrt(dot(v, v)) */
+		v3 position = start;
+		float travel = 0.0f;
+		int hit = 0;
+		for (int it = 0; it < max_iterations; ++it)
+		{
+			float dist = tree_eval(&m->arena, m->root, position);
+			if (dist <= epsilon)
+			{
+				hit = 1;
+				break;
+			}
+			travel += dist;
+			position = add3(muls3(dir, travel), start);
+		}
+		if (!hit) travel = INFINITY;
+		out5[i * 5 + 0] = hit ? 1.0f : 0.0f;
+		out5[i * 5 + 1] = travel;
+		out5[i * 5 + 2] = position.x;
+		out5[i * 5 + 3] = position.y;
+		out5[i * 5 + 4] = position.z;
+	}
+}
+
 void tgo_eval_interp(const TgoModel* m, const float* points, uint64_t count, float* out)
 {
 	Program p = { 0 };

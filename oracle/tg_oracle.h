@@ -63,6 +63,8 @@ void tgo_octree_stats(const TgoOctree* octree, TgoOctreeStats* out);
 void tgo_eval_octree(const TgoOctree* octree, const float* points, uint64_t count, float* out, int threads);
 void tgo_eval_tree(const TgoModel* model, const float* points, uint64_t count, float* out, int threads);
 void tgo_eval_interp(const TgoModel* model, const float* points, uint64_t count, float* out);
+/* SDFNode::RayMarch (sdf_evaluator.cpp:336-354): rays = 6 floats (origin, direction), out5 = hit, travel, position */
+void tgo_ray_march(const TgoModel* model, const float* rays, uint64_t count, int max_iterations, float epsilon, int magnet, float* out5);
 void tgo_gradient(const TgoOctree* octree, const float* points, uint64_t count, float* out3);
 void tgo_color(const TgoOctree* octree, const float* points, uint64_t count, uint8_t* out3);
 

@@ -150,6 +150,8 @@ def lib():
         "tg_eval_points": (i32, [vp, i32, fp, u64, vp]),
         "tg_export_grid": (i32, [fp, fp, fp, C.POINTER(Grid)]),
         "tg_debug_check_long_programs": (i32, [vp, C.c_float, C.POINTER(u64)]),
+        "tg_ray_cast": (i32, [vp, fp, u64, i32, C.c_float, i32, fp]),
+        "tg_debug_node_program": (u64, [vp, u32, C.POINTER(u32), u64, C.POINTER(u32)]),
         "tg_export_mesh": (i32, [vp, C.POINTER(Grid), C.POINTER(MeshOptions), C.POINTER(_Mesh)]),
         "tg_mesh_free": (None, [C.POINTER(_Mesh)]),
         "tg_mesh_download": (i32, [C.POINTER(_Mesh), u32]),
@@ -525,6 +527,13 @@ class Model:
             out = np.zeros(n, np.float32)
         _check(lib().tg_eval_points(self.h, mode, _fp(pts), n, out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def ray_cast(self, rays, max_iterations=100, epsilon=0.001, magnet=False):
+        """rays: (n, 6) origin + direction (or + target with magnet).  Returns (hit bool[n], travel[n], position[n, 3])."""
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        out = np.zeros((len(rays), 5), np.float32)
+        _check(lib().tg_ray_cast(self.h, _fp(rays), len(rays), max_iterations, epsilon, 1 if magnet else 0, _fp(out)))
+        return out[:, 0] != 0, out[:, 1].copy(), out[:, 2:5].copy()
 
     def check_long_programs(self, reach=0.5):
         out = (C.c_uint64 * 3)()

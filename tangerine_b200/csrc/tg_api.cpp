@@ -582,6 +582,37 @@ int tg_eval_points(tg_model* model, int mode, const float* points, uint64_t coun
 }
 TG_CATCH_STATUS
 
+int tg_ray_cast(tg_model* model, const float* rays, uint64_t count, int max_iterations, float epsilon, int magnet, float* out_hits) try
+{
+	if (!model || (count && (!rays || !out_hits))) return Fail(TG_ERR_INVALID, "null argument");
+	if (max_iterations < 0) return Fail(TG_ERR_INVALID, "negative iteration count");
+	std::string error;
+	int rc = EngineRayMarch(model->impl.get(), rays, count, max_iterations, epsilon, magnet ? 1 : 0, out_hits, error);
+	return rc == TG_OK ? rc : Fail(rc, error);
+}
+TG_CATCH_STATUS
+
+// Test / diagnostics hook: the kStreamInterp program (32-bit words, tg_program.h) of octree node `node` of `tree`,
+// built on the host.  Returns the number of words (0 = no such node), copying at most `capacity` of them.
+uint64_t tg_debug_node_program(const tg_tree* tree, uint32_t node, uint32_t* out_words, uint64_t capacity, uint32_t* out_instruction_count) try
+{
+	if (!tree || !tree->tree.Valid()) return 0;
+	FlatModel flat;
+	std::string error;
+	if (!BuildFlatModel(tree->tree, 0.25f, 0, flat, error) || node >= flat.nodes.size()) return 0;
+	const uint32_t begin = flat.nodes[node].interp_offset;
+	uint32_t end = uint32_t(flat.interp.size());
+	for (const FlatNode& n : flat.nodes)
+	{
+		if (n.interp_offset > begin && n.interp_offset < end) end = n.interp_offset;
+	}
+	if (flat.root_interp_offset > begin && flat.root_interp_offset < end) end = flat.root_interp_offset;
+	if (out_instruction_count) *out_instruction_count = flat.nodes[node].flags >> kNodeCountShift;
+	for (uint64_t i = 0; i < capacity && begin + i < end; ++i) out_words[i] = flat.interp[begin + i];
+	return end - begin;
+}
+TG_CATCH_VALUE(0)
+
 int tg_debug_check_long_programs(tg_model* model, float reach, uint64_t out_counts[3]) try
 {
 	if (!model || !out_counts) return Fail(TG_ERR_INVALID, "null argument");

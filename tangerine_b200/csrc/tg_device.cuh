@@ -383,7 +383,7 @@ struct LongScratch
 	uint2 step[kLongBlockSteps];  // x: fold code | slot << 8 | operator << 16, y: value (brush distance, negated for Diff; or operator parameter)
 	float param[kLongBlockSteps]; // blend threshold of fused instructions
 	float2 share[kLongThreads];   // clamp (lo, hi) of every thread's part of a chain; also the operand lists
-	uint32_t marks[kLongThreads]; // per-thread counts of operand openings / closings
+	uint32_t marks[kLongThreads]; // scratch of the group-wide prefix and of FoldChain (3 words per warp)
 	float result[kLongThreads / 32];
 };
 
@@ -514,28 +514,74 @@ __device__ __forceinline__ void CollapseInto(uint2* steps, float* params, uint32
 	params[at] = threshold;
 }
 
-// Ordered composition of every thread's clamp (thread 0's first); thread 0 of the group gets the total.  Warp level by
-// shuffles (compose mine, then the partner's -- the operator is associative, not commutative), across the warps of a
-// block through `share`.
+// Folds the chain steps[begin, end) -- it opens with a constant at `first` (a push), or continues from acc = 0 -- with
+// the whole group.  Every thread composes its contiguous share into a clamp; a share that holds anything but min / max
+// steps (a blend, a flate, an operand that was not collapsed) is marked general.  A warp whose shares are all clamps
+// composes them by shuffles (compose mine, then the partner's: the operator is associative, not commutative).  Thread 0
+// then walks the chain in order: a whole warp's clamp at a time where it can, share by share where a general share sits
+// in the warp, step by step (FoldStep) inside a general share.  Long programs have a handful of general steps (the
+// blends of the first tree of seaside_town's town), so the walk is a few dozen operations instead of a thousand.
+// Returns the chain's value in thread 0 (other threads: unspecified).  `marks` needs 3 words per warp of the group.
 template <int GROUP>
-__device__ __forceinline__ Clamp ComposeGroup(Clamp c, float2* share)
+__device__ __forceinline__ float FoldChain(const uint2* steps, const float* params, uint32_t begin, uint32_t end, uint32_t first,
+	float2* share, uint32_t* marks)
 {
+	const int tid = GROUP == 32 ? int(threadIdx.x & 31) : int(threadIdx.x);
 	const int lane = threadIdx.x & 31;
+	const int warp = GROUP == 32 ? 0 : int(threadIdx.x >> 5);
+	const uint32_t len = end - begin;
+	const uint32_t part = (len + GROUP - 1) / GROUP;
+	const uint32_t b0 = begin + min(len, uint32_t(tid) * part), b1 = begin + min(len, uint32_t(tid + 1) * part);
+	Clamp mine = { -INFINITY, INFINITY };
+	const bool general = !ComposeShare(steps, b0, b1, first, mine);
+	share[tid] = make_float2(mine.lo, mine.hi);
+	const unsigned general_mask = __ballot_sync(0xFFFFFFFFu, general);
+	Clamp whole = mine;
 #pragma unroll
 	for (int o = 1; o < 32; o <<= 1)
 	{
-		const float plo = __shfl_down_sync(0xFFFFFFFFu, c.lo, o), phi = __shfl_down_sync(0xFFFFFFFFu, c.hi, o);
-		if (lane + o < 32) c.Then(plo, phi);
+		const float plo = __shfl_down_sync(0xFFFFFFFFu, whole.lo, o), phi = __shfl_down_sync(0xFFFFFFFFu, whole.hi, o);
+		if (lane + o < 32) whole.Then(plo, phi);
 	}
-	if (GROUP == 32) return c;
-	if (lane == 0) share[threadIdx.x >> 5] = make_float2(c.lo, c.hi);
-	__syncthreads();
-	if (threadIdx.x == 0)
+	if (lane == 0)
 	{
-		for (int w = 1; w < GROUP / 32; ++w) c.Then(share[w].x, share[w].y);
+		marks[warp * 3 + 0] = general_mask;
+		marks[warp * 3 + 1] = __float_as_uint(whole.lo);
+		marks[warp * 3 + 2] = __float_as_uint(whole.hi);
 	}
-	__syncthreads();
-	return c;
+	if (GROUP == 32) __syncwarp(); else __syncthreads();
+	float acc = 0.0f;
+	if (tid == 0)
+	{
+		float stack[kMaxStackSlots];
+		for (int w = 0; w < GROUP / 32; ++w)
+		{
+			const uint32_t mask = marks[w * 3 + 0];
+			if (mask == 0u)
+			{
+				acc = fminf(fmaxf(acc, __uint_as_float(marks[w * 3 + 1])), __uint_as_float(marks[w * 3 + 2]));
+				continue;
+			}
+			for (int l = 0; l < 32; ++l)
+			{
+				const uint32_t t = uint32_t(w * 32 + l);
+				if ((mask >> l) & 1u)
+				{
+					const uint32_t s0 = begin + min(len, t * part), s1 = begin + min(len, (t + 1u) * part);
+					for (uint32_t i = s0; i < s1; ++i)
+					{
+						uint32_t word = steps[i].x;
+						// the chain's opening push spills the accumulator of the chain ABOVE to a slot this walk does not own
+						if (i == first && (word & 0xFFu) == kFoldPush) word = kFoldPush | (kNoSlot << 8);
+						FoldStep(word, __uint_as_float(steps[i].y), params[i], acc, stack);
+					}
+				}
+				else acc = fminf(fmaxf(acc, share[t].x), share[t].y);
+			}
+		}
+	}
+	if (GROUP == 32) __syncwarp(); else __syncthreads();
+	return acc;
 }
 
 // Exclusive prefix of a per-thread count over the group, and the group total.
@@ -725,27 +771,8 @@ __device__ __forceinline__ float GroupEvalLong(const uint4* __restrict__ program
 			const uint32_t o = long_open[g], c = long_close[g], len = c - o;
 			const uint32_t part = (len + GROUP - 1) / GROUP;
 			const uint32_t b0 = o + min(len, uint32_t(tid) * part), b1 = o + min(len, uint32_t(tid + 1) * part);
-			Clamp mineclamp = { -INFINITY, INFINITY };
-			const bool clamps_only = ComposeShare(steps, b0, b1, o, mineclamp);
-			const bool all_clamps = GROUP == 32 ? __all_sync(0xFFFFFFFFu, clamps_only) : (__syncthreads_and(clamps_only ? 1 : 0) != 0);
-			const Clamp whole = ComposeGroup<GROUP>(mineclamp, share);
-			if (tid == 0)
-			{
-				float value;
-				if (all_clamps)
-				{
-					value = whole.hi; // the chain opens with a constant, so lo == hi
-				}
-				else
-				{
-					float acc = __uint_as_float(steps[o].y);
-					float stack[kMaxStackSlots];
-					for (uint32_t j = o + 1; j < c; ++j) FoldStep(steps[j].x, __uint_as_float(steps[j].y), params[j], acc, stack);
-					value = acc;
-				}
-				CollapseInto(steps, params, c, value); // (c itself lies outside every share)
-			}
-			sync(); // thread 0 may have walked the steps: nobody erases them before it is done
+			const float value = FoldChain<GROUP>(steps, params, o, c, o, share, marks);
+			if (tid == 0) CollapseInto(steps, params, c, value); // (c itself lies outside every share)
 			for (uint32_t k = b0; k < b1; ++k) steps[k].x = kFoldNop | (kNoSlot << 8);
 			sync();
 		}
@@ -753,25 +780,10 @@ __device__ __forceinline__ float GroupEvalLong(const uint4* __restrict__ program
 	}
 	sync();
 
-	// c. the main chain
-	Clamp chain = { -INFINITY, INFINITY };
-	const bool clamps_only = walk_all ? false : ComposeShare(steps, lo_i, hi_i, 0u, chain);
-	const bool all_clamps = GROUP == 32 ? __all_sync(0xFFFFFFFFu, clamps_only) : (__syncthreads_and(clamps_only ? 1 : 0) != 0);
-	const Clamp whole = ComposeGroup<GROUP>(chain, share);
-	if (tid == 0)
-	{
-		float acc = 0.0f;
-		if (all_clamps)
-		{
-			acc = fminf(fmaxf(acc, whole.lo), whole.hi);
-		}
-		else
-		{
-			float stack[kMaxStackSlots];
-			for (uint32_t i = 0; i < n; ++i) FoldStep(steps[i].x, __uint_as_float(steps[i].y), params[i], acc, stack);
-		}
-		*result_out = acc;
-	}
+	// c. the main chain (after a walk_all its operands are still in place: the walk handles them step by step, every
+	// share that holds one being general)
+	const float value = FoldChain<GROUP>(steps, params, 0u, n, 0u, share, marks);
+	if (tid == 0) *result_out = value;
 	sync();
 	return *result_out;
 }

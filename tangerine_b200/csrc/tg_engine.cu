@@ -441,7 +441,7 @@ __device__ __forceinline__ void CullLongItem(const CullParams& p, int level, con
 	}
 }
 
-__global__ void __launch_bounds__(kLongThreads) CullLongKernel(const CullParams p)
+__global__ void __launch_bounds__(kLongThreads, 4) CullLongKernel(const CullParams p)
 {
 	static_assert(kLongWarpSteps * (kLongThreads / 32) <= kLongBlockSteps, "the warps' slices of the scratch");
 	__shared__ LongScratch scratch;
@@ -1373,6 +1373,53 @@ __global__ void __launch_bounds__(128) LeafProfileKernel(const DeviceModel model
 	{
 		atomicOr(&masks[leaf], (unsigned long long)ballot << (sub & 32u));
 	}
+}
+
+// SDFNode::RayMarch (sdf_evaluator.cpp:336-354), one ray per thread, on the unpruned model's tree program -- what the
+// Lua calls ray_cast / magnet run (lua_sdf.cpp:410-444; seaside_town.lua casts 1,764 of them while it builds itself).
+__global__ void __launch_bounds__(128) RayMarchKernel(const DeviceModel model, const float* __restrict__ rays, uint32_t count, int max_iterations, float epsilon, int magnet,
+	float* __restrict__ out5)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count) return;
+	const float sx = rays[size_t(i) * 6 + 0], sy = rays[size_t(i) * 6 + 1], sz = rays[size_t(i) * 6 + 2];
+	float dx = rays[size_t(i) * 6 + 3], dy = rays[size_t(i) * 6 + 4], dz = rays[size_t(i) * 6 + 5];
+	if (magnet) // Direction = normalize(Direction - Origin)
+	{
+		dx = dx - sx; dy = dy - sy; dz = dz - sz;
+		const float inv = 1.0f / sqrtf((dx * dx + dy * dy) + dz * dz);
+		dx = dx * inv; dy = dy * inv; dz = dz * inv;
+	}
+	{
+		const float inv = 1.0f / sqrtf((dx * dx + dy * dy) + dz * dz); // glm::normalize = v * inversesqrt(dot(v, v))
+		dx = dx * inv; dy = dy * inv; dz = dz * inv;
+	}
+	float px = sx, py = sy, pz = sz, travel = 0.0f;
+	bool hit = false;
+	const uint32_t* program = model.tree + model.root_tree_offset;
+	for (int it = 0; it < max_iterations; ++it)
+	{
+		const float dist = EvalTreeCentre(program, px, py, pz);
+		if (dist <= epsilon)
+		{
+			hit = true;
+			break;
+		}
+		travel = travel + dist;
+		// A ray that has left for infinity is a miss.  (The reference keeps evaluating the field at +-inf / NaN coordinates
+		// until the iterations run out; whether a NaN survives its min / max there is a property of x86 glm, not of the model.)
+		if (!(fabsf(travel) < INFINITY)) break;
+		px = dx * travel + sx;
+		py = dy * travel + sy;
+		pz = dz * travel + sz;
+	}
+	if (!hit) travel = INFINITY;
+	float* o = out5 + size_t(i) * 5;
+	o[0] = hit ? 1.0f : 0.0f;
+	o[1] = travel;
+	o[2] = px;
+	o[3] = py;
+	o[4] = pz;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -3371,6 +3418,29 @@ int EngineEvalLattice(Model* model, const tg_grid& grid_in, uint32_t flags, floa
 	if (out) TG_CUDA(cudaMemcpyAsync(out, d_out, total * 4, cudaMemcpyDeviceToHost, stream));
 	TG_CUDA(cudaStreamSynchronize(stream));
 	if (out_ms) *out_ms = timer.Ms(t0, t1);
+	return TG_OK;
+}
+
+int EngineRayMarch(Model* model, const float* rays, uint64_t count, int max_iterations, float epsilon, int magnet, float* out5, std::string& error)
+{
+	if (count == 0) return TG_OK;
+	if (count > 0x7FFFFFF0ull)
+	{
+		error = "too many rays for one call";
+		return TG_ERR_INVALID;
+	}
+	Context* ctx = model->context;
+	TG_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t stream = StreamOf(ctx);
+	Scratch scratch(ctx);
+	float *d_rays = nullptr, *d_out = nullptr;
+	TG_CUDA(scratch.Alloc(&d_rays, size_t(count) * 6));
+	TG_CUDA(scratch.Alloc(&d_out, size_t(count) * 5));
+	TG_CUDA(cudaMemcpyAsync(d_rays, rays, size_t(count) * 24, cudaMemcpyHostToDevice, stream));
+	RayMarchKernel<<<uint32_t((count + 127) / 128), 128, 0, stream>>>(MakeDeviceModel(model), d_rays, uint32_t(count), max_iterations, epsilon, magnet, d_out);
+	TG_CUDA(cudaGetLastError());
+	TG_CUDA(cudaMemcpyAsync(out5, d_out, size_t(count) * 20, cudaMemcpyDeviceToHost, stream));
+	TG_CUDA(cudaStreamSynchronize(stream));
 	return TG_OK;
 }
 

@@ -146,6 +146,7 @@ struct MeshResultDevice; // opaque device-side result kept alive by tg_mesh.opaq
 int EngineEvalPoints(Model* model, int mode, const float* points, uint64_t count, void* out, std::string& error);
 // K0's cooperative evaluation of long programs against the plain interpreter: out = { probes, block mismatches, warp mismatches }.
 int EngineCheckLongPrograms(Model* model, float reach, uint64_t out[3], std::string& error);
+int EngineRayMarch(Model* model, const float* rays, uint64_t count, int max_iterations, float epsilon, int magnet, float* out5, std::string& error);
 int EngineEvalLattice(Model* model, const tg_grid& grid, uint32_t flags, float* out, float* out_ms, std::string& error);
 int EngineExportMesh(Model* model, const tg_grid& grid, const tg_mesh_options& options, tg_mesh* out, std::string& error);
 // The same export on all devices of a group: z-slabs cut from a host-side work estimate, per-slab vertex counts combined

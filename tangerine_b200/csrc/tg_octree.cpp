@@ -2,6 +2,8 @@
 #include "tg_octree.h"
 
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <future>
@@ -579,6 +581,8 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 		return false;
 	}
 
+	const double construct_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	if (std::getenv("TG_TRACE_HOST")) std::fprintf(stderr, "octree build: construct %.1f ms (threads %d)\n", construct_seconds * 1e3, threads);
 	out.stats.hash = 0xCBF29CE484222325ull;
 	Flattener flattener{ out, {}, {}, {}, 0 };
 	flattener.inverse.resize(tree.pool.nodes.size());
@@ -632,6 +636,7 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 	out.stats.interp_words = out.interp.size();
 	out.stats.tree_words = out.tree.size();
 	out.stats.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	if (std::getenv("TG_TRACE_HOST")) std::fprintf(stderr, "octree build: total %.1f ms\n", out.stats.build_seconds * 1e3);
 	return true;
 }
 

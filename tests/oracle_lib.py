@@ -69,6 +69,8 @@ def lib():
         L.tgo_octree_stats.argtypes = [vp, C.POINTER(_Stats)]
         L.tgo_eval_octree.argtypes = [vp, fp, C.c_uint64, fp, C.c_int]
         L.tgo_eval_tree.argtypes = [vp, fp, C.c_uint64, fp, C.c_int]
+        L.tgo_ray_march.argtypes = [vp, fp, C.c_uint64, C.c_int, C.c_float, C.c_int, fp]
+        L.tgo_ray_march.restype = None
         L.tgo_eval_interp.argtypes = [vp, fp, C.c_uint64, fp]
         L.tgo_gradient.argtypes = [vp, fp, C.c_uint64, fp]
         L.tgo_color.argtypes = [vp, fp, C.c_uint64, C.POINTER(C.c_uint8)]
@@ -134,6 +136,12 @@ class Model:
         out = np.zeros(len(pts), np.float32)
         lib().tgo_eval_tree(self.h, _fp(pts), len(pts), _fp(out), THREADS)
         return out
+
+    def ray_march(self, rays, max_iterations=100, epsilon=0.001, magnet=False):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
+        out = np.zeros((len(rays), 5), np.float32)
+        lib().tgo_ray_march(self.h, _fp(rays), len(rays), max_iterations, epsilon, 1 if magnet else 0, _fp(out))
+        return out[:, 0] != 0, out[:, 1].copy(), out[:, 2:5].copy()
 
     def eval_interp(self, pts):
         pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
