@@ -212,7 +212,10 @@ __device__ __forceinline__ void EvaluateTile(WarpTile& w, const DeviceModel& mod
 						py[q] = LatticeCoord(grid.y, grid.dy, j0 + lj);
 						pz[q] = LatticeCoord(grid.z, grid.dz, k0 + lk);
 					}
-					EvalInterp<kLaneSamples>(program, px, py, pz, d);
+					// square roots on the branch-free fast path; the (practically never taken) repeat keeps the result exact
+					uint32_t suspect = 0u;
+					EvalInterp<kLaneSamples, false, false, true>(program, px, py, pz, d, &suspect);
+					if (__any_sync(0xFFFFFFFFu, suspect != 0u)) EvalInterp<kLaneSamples>(program, px, py, pz, d);
 #pragma unroll
 					for (int q = 0; q < kLaneSamples; ++q)
 					{

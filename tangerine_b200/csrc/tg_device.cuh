@@ -92,9 +92,24 @@ __device__ __forceinline__ float4 AsFloat4(const uint4& v)
 // Every fetch is a 128-bit load whose address does not depend on another fetch of the same instruction, and the
 // first quad of the next instruction is requested before this instruction's arithmetic starts.  The operator
 // switch sits outside the per-sample loops, so with a warp-uniform program there is one dispatch per brush.
-template <int S, bool PREFETCH = false, bool DEEP = false>
-__device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const float (&px)[S], const float (&py)[S], const float (&pz)[S], float (&result)[S])
+// DEFER: square roots take the branch-free fast path (sdf::SqrtDeferred) and *suspect is raised when an argument fell
+// outside its range -- the caller then evaluates again without DEFER.
+template <bool DEFER> struct SqrtPolicy
 {
+	using type = sdf::SqrtExact;
+	static __device__ __forceinline__ type Make(uint32_t*) { return type(); }
+};
+template <> struct SqrtPolicy<true>
+{
+	using type = sdf::SqrtDeferred;
+	static __device__ __forceinline__ type Make(uint32_t* suspect) { return type{ suspect }; }
+};
+
+template <int S, bool PREFETCH = false, bool DEEP = false, bool DEFER = false>
+__device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const float (&px)[S], const float (&py)[S], const float (&pz)[S], float (&result)[S],
+	uint32_t* suspect = nullptr)
+{
+	const typename SqrtPolicy<DEFER>::type sq = SqrtPolicy<DEFER>::Make(suspect);
 	float acc[S];
 	float stack[kMaxStackSlots][S];
 #pragma unroll
@@ -200,22 +215,22 @@ __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const f
 			if (kind == kBrushBox)
 			{
 #pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Box(lx[s], ly[s], lz[s], p0, p1, p2);
+				for (int s = 0; s < S; ++s) d[s] = sdf::Box(lx[s], ly[s], lz[s], p0, p1, p2, sq);
 			}
 			else if (Opaque(kind) == kBrushSphere)
 			{
 #pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Sphere(lx[s], ly[s], lz[s], p0);
+				for (int s = 0; s < S; ++s) d[s] = sdf::Sphere(lx[s], ly[s], lz[s], p0, sq);
 			}
 			else if (Opaque(kind) == kBrushCylinder)
 			{
 #pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Cylinder(lx[s], ly[s], lz[s], p0, p1);
+				for (int s = 0; s < S; ++s) d[s] = sdf::Cylinder(lx[s], ly[s], lz[s], p0, p1, sq);
 			}
 			else if (Opaque(kind) == kBrushTorus)
 			{
 #pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Torus(lx[s], ly[s], lz[s], p0, p1);
+				for (int s = 0; s < S; ++s) d[s] = sdf::Torus(lx[s], ly[s], lz[s], p0, p1, sq);
 			}
 			else if (Opaque(kind) == kBrushPlane)
 			{
@@ -225,17 +240,17 @@ __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const f
 			else if (Opaque(kind) == kBrushEllipsoid)
 			{
 #pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Ellipsoid(lx[s], ly[s], lz[s], p0, p1, p2);
+				for (int s = 0; s < S; ++s) d[s] = sdf::Ellipsoid(lx[s], ly[s], lz[s], p0, p1, p2, sq);
 			}
 			else if (Opaque(kind) == kBrushCone)
 			{
 #pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Cone(lx[s], ly[s], lz[s], p0, p1);
+				for (int s = 0; s < S; ++s) d[s] = sdf::Cone(lx[s], ly[s], lz[s], p0, p1, sq);
 			}
 			else
 			{
 #pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Coninder(lx[s], ly[s], lz[s], p0, p1, p2);
+				for (int s = 0; s < S; ++s) d[s] = sdf::Coninder(lx[s], ly[s], lz[s], p0, p1, p2, sq);
 			}
 			if (header & kHdrScaleBit)
 			{

@@ -1612,6 +1612,12 @@ Context* Context::Create(int device, std::string& error)
 	cudaEvent_t ce0;
 	cudaEventCreateWithFlags(&ce0, cudaEventDisableTiming);
 	c->copy_events[0] = ce0;
+	for (void*& e : c->cull_events)
+	{
+		cudaEvent_t ce;
+		cudaEventCreateWithFlags(&ce, cudaEventDisableTiming);
+		e = ce;
+	}
 	cudaEvent_t ev0, ev1;
 	cudaEventCreate(&ev0);
 	cudaEventCreate(&ev1);
@@ -1666,6 +1672,10 @@ Context::~Context()
 	if (index_base) cudaFree(index_base);
 	for (void* m : mailboxes) cudaFreeHost(m);
 	if (copy_events[0]) cudaEventDestroy(static_cast<cudaEvent_t>(copy_events[0]));
+	for (void* e : cull_events)
+	{
+		if (e) cudaEventDestroy(static_cast<cudaEvent_t>(e));
+	}
 	if (copy_stream) cudaStreamDestroy(static_cast<cudaStream_t>(copy_stream));
 	if (stream) cudaStreamDestroy(StreamOf(this));
 }
@@ -2310,8 +2320,23 @@ static int BuildCullFlags(Model* model, cudaStream_t stream, Scratch& scratch, c
 		const uint64_t seeded = std::min<uint64_t>(uint64_t(cp.model.region_count) * kSeedSpan * kSeedSpan * kSeedSpan, cp.capacity[level]);
 		bound = std::min<uint64_t>(bound * 8u + seeded, cp.capacity[level]);
 		cp.level = level;
-		CullLongKernel<<<wide_long, kLongThreads, 0, stream>>>(cp);
+		// the two kernels of a level are independent (both only append to the next level's lists and OR flags): the
+		// long-program items run beside the short ones on the context's second stream
+		Context* ctx = model->context;
+		cudaStream_t side = static_cast<cudaStream_t>(ctx->stream2);
+		const bool fork = side != stream && ctx->cull_events[0] && ctx->cull_events[1];
+		if (fork)
+		{
+			TG_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ctx->cull_events[0]), stream));
+			TG_CUDA(cudaStreamWaitEvent(side, static_cast<cudaEvent_t>(ctx->cull_events[0]), 0));
+		}
+		CullLongKernel<<<wide_long, kLongThreads, 0, fork ? side : stream>>>(cp);
 		CullLevelKernel<<<uint32_t((bound + 127) / 128), 128, 0, stream>>>(cp);
+		if (fork)
+		{
+			TG_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ctx->cull_events[1]), side));
+			TG_CUDA(cudaStreamWaitEvent(stream, static_cast<cudaEvent_t>(ctx->cull_events[1]), 0));
+		}
 		launches += 2;
 	}
 	TG_CUDA(cudaGetLastError());

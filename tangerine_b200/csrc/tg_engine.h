@@ -33,6 +33,7 @@ public:
 	void* stream2 = nullptr;     // cudaStream_t: second compute lane of the slab pipeline (odd slabs)
 	void* copy_stream = nullptr; // cudaStream_t: device -> host copies that overlap compute
 	void* copy_events[1] = { nullptr };
+	void* cull_events[2] = { nullptr, nullptr }; // fork / join of the two kernels of a culling level
 	void* timer_events[2] = { nullptr, nullptr };
 	std::vector<PinnedBlock> pinned; // grow-only pool of page-locked host buffers for results
 	std::vector<PinnedBlock> device_blocks; // grow-only cache of device buffers for results (no allocator call in steady state)
@@ -131,9 +132,9 @@ private:
 	std::mutex lock;
 	std::condition_variable wake, done;
 	const std::function<int(int, std::string&)>* task = nullptr;
-	uint64_t generation = 0;
-	int pending = 0;
-	bool quit = false;
+	std::atomic<uint64_t> generation{ 0 };
+	std::atomic<int> pending{ 0 };
+	std::atomic<bool> quit{ false };
 	std::vector<int> status;
 	std::vector<std::string> errors;
 	std::atomic<int> barrier_count{ 0 };

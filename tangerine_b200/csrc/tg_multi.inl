@@ -114,8 +114,8 @@ DeviceGroup::~DeviceGroup()
 {
 	{
 		std::lock_guard<std::mutex> guard(lock);
-		quit = true;
-		generation++;
+		quit.store(true);
+		generation.fetch_add(1);
 	}
 	wake.notify_all();
 	for (std::thread& t : threads)
@@ -132,20 +132,28 @@ DeviceGroup::~DeviceGroup()
 	}
 }
 
+// A worker first spins on the generation counter for a while (an export is a few hundred microseconds, and a caller that
+// exports repeatedly should not pay a futex wake-up per device each time), then sleeps on the condition variable.
 void DeviceGroup::Worker(int rank)
 {
 	cudaSetDevice(contexts[size_t(rank)]->device);
 	uint64_t seen = 0;
 	for (;;)
 	{
-		const std::function<int(int, std::string&)>* job = nullptr;
+		for (int spin = 0; spin < 40000 && generation.load(std::memory_order_acquire) == seen; ++spin)
+		{
+#if defined(__x86_64__)
+			__builtin_ia32_pause();
+#endif
+		}
+		if (generation.load(std::memory_order_acquire) == seen)
 		{
 			std::unique_lock<std::mutex> guard(lock);
-			wake.wait(guard, [&] { return generation != seen; });
-			seen = generation;
-			if (quit) return;
-			job = task;
+			wake.wait(guard, [&] { return generation.load(std::memory_order_acquire) != seen; });
 		}
+		seen = generation.load(std::memory_order_acquire);
+		if (quit.load()) return;
+		const std::function<int(int, std::string&)>* job = task;
 		int rc = TG_ERR_INVALID;
 		std::string message;
 		try
@@ -162,11 +170,12 @@ void DeviceGroup::Worker(int rank)
 			rc = TG_ERR_INVALID;
 			message = std::string("internal error: ") + e.what();
 		}
+		status[size_t(rank)] = rc;
+		errors[size_t(rank)] = message;
+		if (pending.fetch_sub(1, std::memory_order_acq_rel) == 1)
 		{
 			std::lock_guard<std::mutex> guard(lock);
-			status[size_t(rank)] = rc;
-			errors[size_t(rank)] = message;
-			if (--pending == 0) done.notify_all();
+			done.notify_all();
 		}
 	}
 }
@@ -176,12 +185,21 @@ int DeviceGroup::Run(const std::function<int(int, std::string&)>& fn, std::strin
 	{
 		std::lock_guard<std::mutex> guard(lock);
 		task = &fn;
-		pending = size();
-		generation++;
+		pending.store(size(), std::memory_order_release);
+		generation.fetch_add(1, std::memory_order_acq_rel);
 	}
 	wake.notify_all();
-	std::unique_lock<std::mutex> guard(lock);
-	done.wait(guard, [&] { return pending == 0; });
+	for (int spin = 0; spin < 2000000 && pending.load(std::memory_order_acquire) != 0; ++spin)
+	{
+#if defined(__x86_64__)
+		__builtin_ia32_pause();
+#endif
+	}
+	if (pending.load(std::memory_order_acquire) != 0)
+	{
+		std::unique_lock<std::mutex> guard(lock);
+		done.wait(guard, [&] { return pending.load(std::memory_order_acquire) == 0; });
+	}
 	task = nullptr;
 	for (int r = 0; r < size(); ++r)
 	{
@@ -445,6 +463,10 @@ int EngineExportMeshMulti(DeviceGroup* group, const std::vector<Model*>& models,
 		Model* model = models[size_t(rank)];
 		cudaStream_t stream = StreamOf(ctx);
 		cudaStream_t copy_stream = static_cast<cudaStream_t>(ctx->copy_stream);
+		const bool trace = std::getenv("TG_TRACE_MULTI") != nullptr;
+		double t_enqueued = 0.0, t_counts = 0.0, t_finish = 0.0;
+		auto since = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - h0).count(); };
+		const double t_start = since();
 #define TG_RANK_CUDA(call)                                                                  \
 		do                                                                                  \
 		{                                                                                   \
@@ -497,7 +519,9 @@ int EngineExportMeshMulti(DeviceGroup* group, const std::vector<Model*>& models,
 			}
 			MeshCounts& counts = ex.counts[size_t(rank)];
 			counts = MeshCounts();
+			t_enqueued = since();
 			if (rc == TG_OK) rc = WaitCounts(job, counts, err);
+			t_counts = since();
 			if (rc != TG_OK) ex.failed.store(1);
 			if (rc == TG_OK && counts.overflow) ex.overflowed.store(1);
 			group->Barrier();
@@ -573,6 +597,7 @@ int EngineExportMeshMulti(DeviceGroup* group, const std::vector<Model*>& models,
 		tg_mesh part;
 		std::memset(&part, 0, sizeof(part));
 		if (rc == TG_OK) rc = FinishJob(job, counts, &part, err);
+		t_finish = since();
 		ex.timings[size_t(rank)] = part.timings;
 		std::free(part.layer_vertices);
 		std::free(part.layer_vertex_cost);
@@ -592,11 +617,13 @@ int EngineExportMeshMulti(DeviceGroup* group, const std::vector<Model*>& models,
 			job.result = nullptr;
 		}
 		primary->progress_done[0].fetch_add(1);
+		if (trace) std::fprintf(stderr, "rank %d host us: start %.0f  enqueued %.0f  counts %.0f  finished %.0f  done %.0f  (device total %.0f)\n", rank, t_start, t_enqueued, t_counts, t_finish, since(), double(part.timings.total_device_ms) * 1e3);
 #undef TG_RANK_CUDA
 		return rc;
 	};
 
 	int rc = group->Run(rank_task, error);
+	if (std::getenv("TG_TRACE_MULTI")) std::fprintf(stderr, "multi export host us: all ranks done %.0f\n", std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - h0).count());
 	for (int r = 0; r < n; ++r)
 	{
 		Context* ctx = group->contexts[size_t(r)];

@@ -13,7 +13,7 @@ model = T.Model(ctx, tree)
 lo, hi = tree.bounds()
 grid = T.export_grid(lo, hi, np.float32(step))
 flags = T.MESH_NORMALS | T.MESH_COLORS
-for mode in ("device", "host"):
+for mode in (("device", "host") if not os.environ.get("TG_PROBE_DEVICE_ONLY") else ("device",)):
     for i in range(4):
         ctx.synchronize()
         t0 = time.perf_counter()
@@ -27,8 +27,9 @@ for mode in ("device", "host"):
         if i == 3:
             print("%s: V=%d F=%d  device %.3f ms  wall %.3f ms" % (mode, m.vertex_count, m.triangle_count, ms, wall))
             for r, (b, e, t) in enumerate(ranks):
-                print("  rank %d  slab [%4d, %4d)  cull %.3f eval %.3f scan %.3f faces %.3f attr %.3f  total %.3f  bricks %d" % (
-                    r, b, e, t["cull_ms"], t["evaluate_ms"], t["compact_ms"], t["faces_ms"], t["attributes_ms"], t["total_device_ms"], t["bricks_evaluated"]))
+                print("  rank %d  slab [%4d, %4d)  cull %.3f eval %.3f scan %.3f faces %.3f attr %.3f  total %.3f  bricks %d  flops/sample %.0f  ns/brick %.1f" % (
+                    r, b, e, t["cull_ms"], t["evaluate_ms"], t["compact_ms"], t["faces_ms"], t["attributes_ms"], t["total_device_ms"], t["bricks_evaluated"],
+                    t["algorithmic_flops"] / max(t["samples_evaluated"], 1), t["evaluate_ms"] * 1e6 / max(t["bricks_evaluated"], 1)))
         m.close()
 model.close()
 ctx.close()
