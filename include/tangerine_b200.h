@@ -215,7 +215,10 @@ enum
 	 * reference promotes to double.  Samples stay within BASELINE.json's tolerance (1e-5 relative / 4 ULP) of the
 	 * reference but are no longer bit-identical, so a cell whose corner value is within that tolerance of zero may change
 	 * its classification.  Without this flag every sample, vertex, normal and colour is bit-identical to the reference. */
-	TG_MESH_FAST = 1u << 6
+	TG_MESH_FAST = 1u << 6,
+	/* Multi-GPU contexts: after this export, move the slab cuts of the next export of the same model and grid by the
+	 * per-device times just measured.  Without it every export runs on the cuts of the host-side estimate alone. */
+	TG_MESH_REBALANCE = 1u << 7
 };
 
 typedef struct tg_mesh_options

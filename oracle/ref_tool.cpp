@@ -410,10 +410,14 @@ static void WalkOctree(SDFOctree* Node, OctreeStats& Stats)
 	}
 	Stats.MaxWords = std::max<uint64_t>(Stats.MaxWords, WordCount);
 	Stats.MaxStack = std::max<uint64_t>(Stats.MaxStack, Node->Interpreter->StackSize);
-	Stats.Hash = Fnv(Stats.Hash, &Node->Pivot, 12);
-	Stats.Hash = Fnv(Stats.Hash, &Terminus, 4);
-	Stats.Hash = Fnv(Stats.Hash, &ChildMask, 4);
-	Stats.Hash = Fnv(Stats.Hash, Words.data(), WordCount * 4);
+	// per node FNV-1a over (pivot, terminus, child mask, words); the octree hash is FNV-1a over those in pre-order
+	// (two levels so that the product can hash its nodes on several threads)
+	uint64_t NodeHash = 0xCBF29CE484222325ull;
+	NodeHash = Fnv(NodeHash, &Node->Pivot, 12);
+	NodeHash = Fnv(NodeHash, &Terminus, 4);
+	NodeHash = Fnv(NodeHash, &ChildMask, 4);
+	NodeHash = Fnv(NodeHash, Words.data(), WordCount * 4);
+	Stats.Hash = Fnv(Stats.Hash, &NodeHash, 8);
 	if (Stats.Dump)
 	{
 		std::fwrite(&Node->Pivot, 4, 3, Stats.Dump);

@@ -1076,10 +1076,13 @@ static void oct_walk(const TgoOctree* o, int32_t index, TgoOctreeStats* s)
 	}
 	if (words > s->max_words) s->max_words = words;
 	if (n->stack_size > s->max_stack) s->max_stack = n->stack_size;
-	s->hash = fnv(s->hash, &n->pivot, 12);
-	s->hash = fnv(s->hash, &terminus, 4);
-	s->hash = fnv(s->hash, &mask, 4);
-	s->hash = fnv(s->hash, o->programs.words + n->prog_offset, words * 4);
+	/* per node FNV-1a over (pivot, terminus, child mask, words); the octree hash is FNV-1a over those in pre-order */
+	uint64_t node_hash = 0xCBF29CE484222325ull;
+	node_hash = fnv(node_hash, &n->pivot, 12);
+	node_hash = fnv(node_hash, &terminus, 4);
+	node_hash = fnv(node_hash, &mask, 4);
+	node_hash = fnv(node_hash, o->programs.words + n->prog_offset, words * 4);
+	s->hash = fnv(s->hash, &node_hash, 8);
 	for (int i = 0; i < 8; ++i) if (n->children[i] >= 0) oct_walk(o, n->children[i], s);
 }
 

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 
 EVAL_OCTREE, EVAL_INTERP, EVAL_TREE, EVAL_GRADIENT, EVAL_COLOR = range(5)
-MESH_NORMALS, MESH_COLORS, MESH_NO_CULL, MESH_DEVICE_ONLY, MESH_FACE_NORMALS, MESH_KEEP_CANCEL, MESH_FAST = 1, 2, 4, 8, 16, 32, 64
+MESH_NORMALS, MESH_COLORS, MESH_NO_CULL, MESH_DEVICE_ONLY, MESH_FACE_NORMALS, MESH_KEEP_CANCEL, MESH_FAST, MESH_REBALANCE = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 class TangerineError(RuntimeError):

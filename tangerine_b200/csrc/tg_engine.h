@@ -100,7 +100,7 @@ public:
 	double upload_seconds = 0.0;
 	int leaf_count = 0;
 	// slab cuts of the last multi-GPU export (the estimate walks every terminus cell: milliseconds, so it is made once per grid)
-	struct { tg_grid grid; int ranks = 0; std::vector<uint32_t> cuts; } plan;
+	struct { tg_grid grid; int ranks = 0; std::vector<uint32_t> cuts; std::vector<double> layer_cost; int feedback_rounds = 0; } plan;
 
 	Model() : flat_owner(std::make_shared<FlatModel>()), flat(*flat_owner) {}
 	explicit Model(const std::shared_ptr<FlatModel>& shared) : flat_owner(shared), flat(*flat_owner) {}

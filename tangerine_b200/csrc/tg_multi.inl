@@ -429,9 +429,11 @@ int EngineExportMeshMulti(DeviceGroup* group, const std::vector<Model*>& models,
 		auto& plan = models[0]->plan;
 		if (plan.ranks != n || std::memcmp(&plan.grid, &grid_in, sizeof(tg_grid)) != 0 || std::getenv("TG_PLAN_CONSTANT"))
 		{
-			plan.cuts = PlanSlabs(EstimateLayerCost(models[0]->flat, grid_in), grid.sz, n);
+			plan.layer_cost = EstimateLayerCost(models[0]->flat, grid_in);
+			plan.cuts = PlanSlabs(plan.layer_cost, grid.sz, n);
 			plan.grid = grid_in;
 			plan.ranks = n;
+			plan.feedback_rounds = 0;
 		}
 		ex.cuts = plan.cuts;
 	}
@@ -695,6 +697,34 @@ int EngineExportMeshMulti(DeviceGroup* group, const std::vector<Model*>& models,
 		tm.kernel_launches += p.kernel_launches;
 	}
 	tm.download_ms = ex.want_host ? float(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count()) : 0.0f;
+	if ((options.flags & TG_MESH_REBALANCE) && models[0]->plan.layer_cost.size() == grid.sz)
+	{
+		// Opt-in feedback: the estimate of every slab's layers is scaled towards the share of the work its device just
+		// measured (culling + evaluation + numbering + attributes; the wait for the all-gather is not work), and the cuts
+		// of the next export of this model and grid are planned on the corrected estimate.
+		auto& plan = models[0]->plan;
+		std::vector<double> measured(size_t(n), 0.0), predicted(size_t(n), 0.0);
+		double measured_sum = 0.0, predicted_sum = 0.0;
+		for (int r = 0; r < n; ++r)
+		{
+			const tg_mesh_timings& p = ex.timings[size_t(r)];
+			measured[size_t(r)] = double(p.cull_ms) + p.evaluate_ms + p.compact_ms + p.attributes_ms;
+			for (uint32_t k = ex.cuts[size_t(r)]; k < ex.cuts[size_t(r) + 1]; ++k) predicted[size_t(r)] += plan.layer_cost[k];
+			measured_sum += measured[size_t(r)];
+			predicted_sum += predicted[size_t(r)];
+		}
+		if (measured_sum > 0.0 && predicted_sum > 0.0)
+		{
+			for (int r = 0; r < n; ++r)
+			{
+				if (!(predicted[size_t(r)] > 0.0) || !(measured[size_t(r)] > 0.0)) continue;
+				const double scale = (measured[size_t(r)] / measured_sum) / (predicted[size_t(r)] / predicted_sum);
+				for (uint32_t k = ex.cuts[size_t(r)]; k < ex.cuts[size_t(r) + 1]; ++k) plan.layer_cost[k] *= scale;
+			}
+			plan.cuts = PlanSlabs(plan.layer_cost, grid.sz, n);
+			plan.feedback_rounds++;
+		}
+	}
 	// per-rank detail for tg_mesh_rank_timings (bench.py reports the balance)
 	result->rank_timings = ex.timings;
 	result->rank_cuts = ex.cuts;

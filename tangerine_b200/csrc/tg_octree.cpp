@@ -6,8 +6,12 @@
 #include <cstdlib>
 #include <algorithm>
 #include <cmath>
-#include <future>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <memory>
+#include <mutex>
 #include <thread>
 
 namespace tg
@@ -42,10 +46,83 @@ struct Subtree
 	int32_t root = -1;
 };
 
+// A fixed set of worker threads and one queue of tasks.  A thread that waits for tasks it submitted runs queued tasks
+// itself meanwhile (HelpUntil), so the recursion of the octree build can fan out at any depth without ever holding a
+// thread idle or creating one per task.
+class TaskPool
+{
+public:
+	explicit TaskPool(int threads)
+	{
+		for (int t = 1; t < threads; ++t) workers.emplace_back([this] { Work(); }); // the caller is the first thread
+	}
+	~TaskPool()
+	{
+		{
+			std::lock_guard<std::mutex> guard(lock);
+			stop = true;
+		}
+		wake.notify_all();
+		for (std::thread& t : workers) t.join();
+	}
+	void Submit(std::function<void()> task)
+	{
+		{
+			std::lock_guard<std::mutex> guard(lock);
+			queue.push_back(std::move(task));
+		}
+		wake.notify_one();
+	}
+	void HelpUntil(const std::atomic<int>& pending)
+	{
+		while (pending.load(std::memory_order_acquire) != 0)
+		{
+			std::function<void()> task;
+			{
+				std::lock_guard<std::mutex> guard(lock);
+				if (!queue.empty())
+				{
+					task = std::move(queue.back()); // newest first: the deepest, smallest work stays with its creator
+					queue.pop_back();
+				}
+			}
+			if (task) task();
+			else std::this_thread::yield();
+		}
+	}
+
+private:
+	void Work()
+	{
+		for (;;)
+		{
+			std::function<void()> task;
+			{
+				std::unique_lock<std::mutex> guard(lock);
+				wake.wait(guard, [this] { return stop || !queue.empty(); });
+				if (queue.empty()) return; // stop
+				task = std::move(queue.front()); // oldest first: the largest subtrees spread over the workers
+				queue.pop_front();
+			}
+			task();
+		}
+	}
+	std::vector<std::thread> workers;
+	std::mutex lock;
+	std::condition_variable wake;
+	std::deque<std::function<void()>> queue;
+	bool stop = false;
+};
+
 struct Builder
 {
 	float target_size;
-	int parallel_depth; // nodes at depth <= parallel_depth build their octants on worker threads
+	TaskPool* tasks = nullptr; // null: build serially
+	std::atomic<bool> failed{ false };
+	// A node hands its eight octants to the task pool when its pruned tree still has this many brushes (below that a
+	// task's bookkeeping costs more than the octant) and it is not too deep.
+	static constexpr int kSpawnLeaves = 12;
+	static constexpr int kSpawnDepth = 7;
 
 	// SDFOctree::SDFOctree :1641-1700 with Coalesce = true, MaxDepth = -1 (what MeshExportThread asks for)
 	int32_t Construct(Subtree& st, uint32_t in_evaluator, Box3 bounds, int depth)
@@ -93,25 +170,36 @@ struct Builder
 		bool penultimate = true;
 		int live = 0;
 
-		if (depth <= parallel_depth)
+		if (tasks && depth <= kSpawnDepth && st.nodes[self].evaluator_leaves >= kSpawnLeaves)
 		{
-			// Each octant prunes against a private copy of the pool, so the eight can run concurrently.
-			std::future<std::unique_ptr<Subtree>> jobs[8];
+			// Each octant prunes in a pool of its own laid over this one (NodePool::Overlay: nothing is copied).  This pool
+			// does not grow while they run: its owner -- this thread -- only helps with other tasks until they are done.
+			std::unique_ptr<Subtree> results[8];
+			std::atomic<int> pending{ 8 };
 			for (int i = 0; i < 8; ++i)
 			{
-				Box3 cb = Octant(bounds, pivot, i);
-				jobs[i] = std::async(std::launch::async, [this, &st, evaluator, cb, depth]()
+				const Box3 cb = Octant(bounds, pivot, i);
+				tasks->Submit([this, &st, &results, &pending, evaluator, cb, depth, i]()
 				{
-					std::unique_ptr<Subtree> child(new Subtree);
-					child->pool.nodes.reserve(st.pool.nodes.size() * 4 + 4096); // pruning appends set nodes: grow without re-copying
-					child->pool = st.pool;
-					child->root = Construct(*child, evaluator, cb, depth + 1);
-					return child;
+					try
+					{
+						std::unique_ptr<Subtree> child(new Subtree);
+						child->pool.Overlay(st.pool);
+						child->root = Construct(*child, evaluator, cb, depth + 1);
+						results[i] = std::move(child);
+					}
+					catch (...)
+					{
+						failed.store(true);
+					}
+					pending.fetch_sub(1, std::memory_order_acq_rel);
 				});
 			}
+			tasks->HelpUntil(pending);
 			for (int i = 0; i < 8; ++i)
 			{
-				std::unique_ptr<Subtree> child = jobs[i].get();
+				std::unique_ptr<Subtree> child = std::move(results[i]);
+				if (!child) continue; // (failed: reported by the caller)
 				const BuildNode& cn = child->nodes[child->root];
 				if (cn.evaluator != kNoNode)
 				{
@@ -401,15 +489,31 @@ inline uint64_t Fnv(uint64_t hash, const void* data, size_t bytes)
 	return hash;
 }
 
+// Flattening in three passes.  (1) A serial pre-order walk over the octree -- the order of the reference's own walks,
+// oracle/ref_tool.cpp -- lays out the node table, the evaluation regions and the list of programs to generate; it does
+// no heavy work.  (2) Every node's two device programs and the statistics / hash of its program in the reference's word
+// encoding are generated independently, on the task pool.  (3) A serial pass gives the programs their offsets and
+// concatenates them.
 struct Flattener
 {
+	struct Job
+	{
+		const Subtree* st;
+		int32_t index;
+		std::vector<uint32_t> interp; // starts table (long programs) + program, whole quads
+		uint32_t interp_program_at = 0; // word offset of the program inside `interp`
+		std::vector<uint32_t> tree;
+		uint32_t flags = 0, flops = 0;
+		int max_slots = 0;
+		uint64_t ref_words = 0, stack = 0, node_hash = 0;
+	};
+
 	FlatModel& model;
-	std::vector<uint32_t> ref_words;
-	std::vector<uint32_t> program; // kStreamInterp program of the node being emitted
 	std::vector<Mat4> inverse;     // CompiledInverseMatrix of every brush of the model, by node index
+	std::vector<Job> jobs;         // one per octree node, pre-order
 	int max_slots = 0;
 
-	// Pre-order walk (same order as the octree hash in oracle/ref_tool.cpp) emitting one FlatNode per octree node.
+	// Pass 1: pre-order walk emitting one FlatNode (pivot, terminus, children) per octree node and the regions.
 	uint32_t Walk(const Subtree& st, int32_t index, const float (&lo)[3], const float (&hi)[3])
 	{
 		const BuildNode& bn = st.nodes[index];
@@ -422,60 +526,12 @@ struct Flattener
 			fn.pivot[2] = bn.pivot.z;
 			fn.terminus = bn.terminus ? 1u : 0u;
 			for (int i = 0; i < 8; ++i) fn.children[i] = -1;
-			fn.tree_offset = uint32_t(model.tree.size());
-			program.clear();
-			StreamGen interp(st.pool, program, false);
-			interp.inverse = inverse.data();
-			interp.inverse_count = uint32_t(inverse.size());
-			interp.Gen(bn.evaluator);
-			interp.Finish();
-			fn.flags = interp.cullable ? kNodeCullable : 0u;
-			const size_t count = interp.starts.size();
-			fn.flags |= uint32_t(std::min<size_t>(count, (1u << 24) - 1u)) << kNodeCountShift;
-			if (count >= kLongProgram)
-			{
-				// Long programs carry a table of their instructions' quad offsets right in front of them (padded to whole
-				// quads): K0 evaluates such a program with one warp, every lane fetching its own instructions directly.
-				fn.flags |= kNodeLong;
-				for (size_t i = 0; i < count; ++i) model.interp.push_back(interp.starts[i]);
-				while (model.interp.size() % 4 != 0) model.interp.push_back(0);
-			}
-			fn.interp_offset = uint32_t(model.interp.size());
-			model.interp.insert(model.interp.end(), program.begin(), program.end());
-			StreamGen tree(st.pool, model.tree, true);
-			tree.Gen(bn.evaluator);
-			tree.Finish();
-			fn.flops = interp.flops;
-			if (tree.max_slots > max_slots) max_slots = tree.max_slots;
+			fn.interp_offset = fn.tree_offset = fn.flags = fn.flops = 0u;
 			model.nodes[self] = fn;
 		}
-		// Reference-format words: statistics + hash only.
-		ref_words.clear();
-		st.pool.CompileReference(bn.evaluator, ref_words, inverse.empty() ? nullptr : inverse.data());
-		ref_words.push_back(0); // OpcodeT::Stop (:1381)
-		uint32_t child_mask = 0;
-		for (int i = 0; i < 8; ++i)
-		{
-			if (bn.children[i] != -1) child_mask |= 1u << i;
-		}
-		FlatModelStats& s = model.stats;
-		const uint32_t terminus = bn.terminus ? 1u : 0u;
-		const uint64_t words = ref_words.size();
-		s.nodes++;
-		s.ref_words += words;
-		if (terminus)
-		{
-			s.leaves++;
-			s.ref_leaf_words += words;
-		}
-		if (words > s.ref_max_words) s.ref_max_words = words;
-		const uint64_t stack = st.pool.nodes[bn.evaluator].stack_size;
-		if (stack > s.max_stack) s.max_stack = stack;
-		s.hash = Fnv(s.hash, &bn.pivot, 12);
-		s.hash = Fnv(s.hash, &terminus, 4);
-		s.hash = Fnv(s.hash, &child_mask, 4);
-		s.hash = Fnv(s.hash, ref_words.data(), words * 4);
-
+		jobs.emplace_back();
+		jobs.back().st = &st;
+		jobs.back().index = index;
 		if (bn.terminus)
 		{
 			FlatRegion region = { { lo[0], lo[1], lo[2] }, { hi[0], hi[1], hi[2] }, { 0.0f, 0.0f, 0.0f }, 0.0f, self, 0 };
@@ -517,6 +573,94 @@ struct Flattener
 			model.nodes[self].children[i] = int32_t(child_index);
 		}
 		return self;
+	}
+
+	// Pass 2: one node's programs and reference-format statistics (thread-safe: touches only its job).
+	void Generate(Job& job) const
+	{
+		const Subtree& st = *job.st;
+		const BuildNode& bn = st.nodes[job.index];
+		std::vector<uint32_t> program;
+		StreamGen interp(st.pool, program, false);
+		interp.inverse = inverse.data();
+		interp.inverse_count = uint32_t(inverse.size());
+		interp.Gen(bn.evaluator);
+		interp.Finish();
+		job.flags = interp.cullable ? kNodeCullable : 0u;
+		const size_t count = interp.starts.size();
+		job.flags |= uint32_t(std::min<size_t>(count, (1u << 24) - 1u)) << kNodeCountShift;
+		if (count >= kLongProgram)
+		{
+			// Long programs carry a table of their instructions' quad offsets right in front of them (padded to whole
+			// quads): K0 evaluates such a program with a group of threads, each fetching its own instructions directly.
+			job.flags |= kNodeLong;
+			job.interp.reserve(count + 4 + program.size());
+			for (size_t i = 0; i < count; ++i) job.interp.push_back(interp.starts[i]);
+			while (job.interp.size() % 4 != 0) job.interp.push_back(0);
+		}
+		job.interp_program_at = uint32_t(job.interp.size());
+		job.interp.insert(job.interp.end(), program.begin(), program.end());
+		StreamGen tree(st.pool, job.tree, true);
+		tree.Gen(bn.evaluator);
+		tree.Finish();
+		job.flops = interp.flops;
+		job.max_slots = tree.max_slots;
+		// Reference-format words: statistics + hash only.
+		std::vector<uint32_t> ref_words;
+		st.pool.CompileReference(bn.evaluator, ref_words, inverse.empty() ? nullptr : inverse.data());
+		ref_words.push_back(0); // OpcodeT::Stop (:1381)
+		uint32_t child_mask = 0;
+		for (int i = 0; i < 8; ++i)
+		{
+			if (bn.children[i] != -1) child_mask |= 1u << i;
+		}
+		const uint32_t terminus = bn.terminus ? 1u : 0u;
+		job.ref_words = ref_words.size();
+		job.stack = st.pool.nodes[bn.evaluator].stack_size;
+		uint64_t h = 0xCBF29CE484222325ull;
+		h = Fnv(h, &bn.pivot, 12);
+		h = Fnv(h, &terminus, 4);
+		h = Fnv(h, &child_mask, 4);
+		h = Fnv(h, ref_words.data(), ref_words.size() * 4);
+		job.node_hash = h;
+	}
+
+	// Pass 3: offsets, concatenation, statistics.  The octree hash is FNV-1a over the nodes' own hashes in pre-order.
+	void Assemble()
+	{
+		size_t interp_words = 0, tree_words = 0;
+		for (const Job& job : jobs)
+		{
+			interp_words += job.interp.size();
+			tree_words += job.tree.size();
+		}
+		model.interp.reserve(model.interp.size() + interp_words + 4096);
+		model.tree.reserve(model.tree.size() + tree_words + 4096);
+		FlatModelStats& s = model.stats;
+		for (size_t i = 0; i < jobs.size(); ++i)
+		{
+			Job& job = jobs[i];
+			FlatNode& fn = model.nodes[i];
+			fn.interp_offset = uint32_t(model.interp.size()) + job.interp_program_at;
+			model.interp.insert(model.interp.end(), job.interp.begin(), job.interp.end());
+			fn.tree_offset = uint32_t(model.tree.size());
+			model.tree.insert(model.tree.end(), job.tree.begin(), job.tree.end());
+			fn.flags = job.flags;
+			fn.flops = job.flops;
+			if (job.max_slots > max_slots) max_slots = job.max_slots;
+			s.nodes++;
+			s.ref_words += job.ref_words;
+			if (fn.terminus)
+			{
+				s.leaves++;
+				s.ref_leaf_words += job.ref_words;
+			}
+			if (job.ref_words > s.ref_max_words) s.ref_max_words = job.ref_words;
+			if (job.stack > s.max_stack) s.max_stack = job.stack;
+			s.hash = Fnv(s.hash, &job.node_hash, 8);
+			std::vector<uint32_t>().swap(job.interp);
+			std::vector<uint32_t>().swap(job.tree);
+		}
 	}
 };
 
@@ -570,11 +714,34 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 	}
 	Builder builder;
 	builder.target_size = target_size;
-	builder.parallel_depth = threads >= 4 ? 2 : threads >= 2 ? 1 : 0; // 64 tasks: the octants are very unequal (most of a scene sits in a few of them)
+	// One pool of workers per process, kept between builds: fresh threads start with cold allocator arenas and
+	// unmapped stacks, which cost a first build more than the build itself.
+	TaskPool* tasks = nullptr;
+	if (threads > 1)
+	{
+		static std::mutex pools_lock;
+		static std::vector<std::pair<int, std::unique_ptr<TaskPool>>> pools;
+		std::lock_guard<std::mutex> guard(pools_lock);
+		for (auto& p : pools)
+		{
+			if (p.first == threads) tasks = p.second.get();
+		}
+		if (!tasks)
+		{
+			pools.emplace_back(threads, std::unique_ptr<TaskPool>(new TaskPool(threads)));
+			tasks = pools.back().second.get();
+		}
+		builder.tasks = tasks;
+	}
 
 	Subtree top;
-	top.pool = tree.pool;
+	top.pool.Overlay(tree.pool); // prunes against the caller's tree without copying it
 	top.root = builder.Construct(top, tree.root, cube, 1);
+	if (builder.failed.load())
+	{
+		error = "out of memory while building the octree";
+		return false;
+	}
 	if (top.nodes[top.root].evaluator == kNoNode)
 	{
 		error = "octree pruned the whole model away";
@@ -584,7 +751,7 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 	const double construct_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 	if (std::getenv("TG_TRACE_HOST")) std::fprintf(stderr, "octree build: construct %.1f ms (threads %d)\n", construct_seconds * 1e3, threads);
 	out.stats.hash = 0xCBF29CE484222325ull;
-	Flattener flattener{ out, {}, {}, {}, 0 };
+	Flattener flattener{ out, {}, {}, 0 };
 	flattener.inverse.resize(tree.pool.nodes.size());
 	for (size_t i = 0; i < tree.pool.nodes.size(); ++i)
 	{
@@ -594,6 +761,43 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 	{
 		const float lo[3] = { -INFINITY, -INFINITY, -INFINITY }, hi[3] = { INFINITY, INFINITY, INFINITY };
 		flattener.Walk(top, top.root, lo, hi);
+	}
+	{
+		// programs of all nodes, in batches on the task pool (or here, serially)
+		std::vector<Flattener::Job>& jobs = flattener.jobs;
+		const size_t batch = 64;
+		const size_t batches = (jobs.size() + batch - 1) / batch;
+		if (tasks)
+		{
+			std::atomic<int> pending{ int(batches) };
+			std::atomic<bool> generate_failed{ false };
+			for (size_t b = 0; b < batches; ++b)
+			{
+				tasks->Submit([&flattener, &jobs, &pending, &generate_failed, b, batch]()
+				{
+					try
+					{
+						for (size_t i = b * batch; i < std::min(jobs.size(), (b + 1) * batch); ++i) flattener.Generate(jobs[i]);
+					}
+					catch (...)
+					{
+						generate_failed.store(true);
+					}
+					pending.fetch_sub(1, std::memory_order_acq_rel);
+				});
+			}
+			tasks->HelpUntil(pending);
+			if (generate_failed.load())
+			{
+				error = "out of memory while flattening the octree";
+				return false;
+			}
+		}
+		else
+		{
+			for (Flattener::Job& job : jobs) flattener.Generate(job);
+		}
+		flattener.Assemble();
 	}
 	if (flattener.max_slots > kMaxStackSlots)
 	{

@@ -176,9 +176,19 @@ float NodePool::Eval(uint32_t index, Vec3 point) const
 
 // Clip: brush :468-478, set :782-850, flate :1064-1075, stencil :603-615.  Brushes are immutable, so
 // the reference's Copy() of a surviving brush is the brush's own index here.
+// The values a clip keeps live in per-THREAD arrays indexed by node: one clip runs on one thread from start to end, and
+// the octree build makes hundreds of thousands of short-lived pools (one per task), which must not each allocate and
+// zero arrays as long as the whole tree.
+namespace
+{
+thread_local std::vector<float> memo_value;
+thread_local std::vector<uint32_t> memo_stamp;
+thread_local uint32_t memo_epoch = 0;
+} // namespace
+
 uint32_t NodePool::Clip(uint32_t index, Vec3 point, float radius, float* top_value)
 {
-	// a new epoch invalidates the values kept by the previous clip (another point)
+	// a new epoch invalidates the values kept by the previous clip (another point, possibly another pool)
 	if (++memo_epoch == 0)
 	{
 		std::fill(memo_stamp.begin(), memo_stamp.end(), 0u);
@@ -220,7 +230,7 @@ float NodePool::EvalMemo(uint32_t index, Vec3 point)
 	}
 	if (index >= memo_stamp.size())
 	{
-		const size_t size = std::max<size_t>(nodes.size(), size_t(index) + 1);
+		const size_t size = std::max<size_t>(nodes.size() + nodes.size() / 2, size_t(index) + 1);
 		memo_stamp.resize(size, 0u);
 		memo_value.resize(size, 0.0f);
 	}

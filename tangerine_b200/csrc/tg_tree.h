@@ -80,10 +80,46 @@ void SnapshotMaterials(std::vector<float>& out_rgb);
 // Transform::ToMatrix followed by glm::inverse: the matrix EvaluatorTransform::Compile emits (sdf_evaluator.cpp:409-429).
 Mat4 CompiledInverseMatrix(const struct Node& n);
 
-// Growable node pool.  Trees own one; octree workers own private copies that grow as they prune.
+// Node storage of a pool: its own nodes, optionally BEHIND the first base_count nodes of another pool's storage, which
+// must outlive this one and not grow while this one is in use.  Octree workers prune against their parent's nodes
+// this way without copying them (node indices mean the same thing in the parent and in every pool laid over it).
+class NodeStore
+{
+public:
+	const NodeStore* base = nullptr;
+	uint32_t base_count = 0;
+	std::vector<Node> own;
+
+	size_t size() const { return size_t(base_count) + own.size(); }
+	const Node& operator[](size_t i) const
+	{
+		const NodeStore* s = this;
+		while (i < s->base_count) s = s->base;
+		return s->own[i - s->base_count];
+	}
+	// (nodes of the base are never modified through an overlay; the reference is mutable for the pool's own nodes)
+	Node& operator[](size_t i) { return const_cast<Node&>(static_cast<const NodeStore&>(*this)[i]); }
+	// iteration covers the pool's own nodes: whole trees (no base) are the only things iterated
+	std::vector<Node>::iterator begin() { return own.begin(); }
+	std::vector<Node>::iterator end() { return own.end(); }
+	std::vector<Node>::const_iterator begin() const { return own.begin(); }
+	std::vector<Node>::const_iterator end() const { return own.end(); }
+	void push_back(const Node& n) { own.push_back(n); }
+	void reserve(size_t n) { own.reserve(n > base_count ? n - base_count : 0); }
+};
+
+// Growable node pool.  Trees own one; octree workers lay theirs over their parent's (Overlay) and grow as they prune.
 struct NodePool
 {
-	std::vector<Node> nodes;
+	NodeStore nodes;
+
+	// Makes this (empty) pool a view of `parent`'s nodes plus whatever gets added here.
+	void Overlay(const NodePool& parent)
+	{
+		nodes.base = &parent.nodes;
+		nodes.base_count = uint32_t(parent.nodes.size());
+		nodes.own.clear();
+	}
 
 	uint32_t Add(const Node& n);
 	// SetNode constructor (sdf_evaluator.cpp:737-772) with its left-leaning operand swap.
@@ -110,9 +146,6 @@ private:
 	// a 1000-primitive tree).  The values are the same numbers whichever call computes them, so a clip keeps them.
 	uint32_t ClipRec(uint32_t index, Vec3 point, float radius, float* top_value);
 	float EvalMemo(uint32_t index, Vec3 point);
-	std::vector<float> memo_value;
-	std::vector<uint32_t> memo_stamp;
-	uint32_t memo_epoch = 0;
 };
 
 class Tree
