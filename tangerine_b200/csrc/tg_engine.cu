@@ -1628,6 +1628,11 @@ Context* Context::Create(int device, std::string& error)
 	{
 		c->brick_blocks_per_sm = 1;
 	}
+	if (const char* env = std::getenv("TG_BRICK_BLOCKS")) // tuning: resident brick-kernel blocks per SM
+	{
+		const int n = std::atoi(env);
+		if (n >= 1 && n < c->brick_blocks_per_sm) c->brick_blocks_per_sm = n;
+	}
 	// Keep freed scratch in the pool so steady-state exports do not hit the allocator.
 	cudaMemPool_t pool;
 	if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)

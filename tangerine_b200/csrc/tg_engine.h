@@ -101,6 +101,8 @@ public:
 	int leaf_count = 0;
 	// slab cuts of the last multi-GPU export (the estimate walks every terminus cell: milliseconds, so it is made once per grid)
 	struct { tg_grid grid; int ranks = 0; std::vector<uint32_t> cuts; std::vector<double> layer_cost; int feedback_rounds = 0; } plan;
+	// vertex / quad counts of this device's last slab of a multi-GPU export: capacities of the next one when the cuts moved
+	uint64_t last_slab_vertices = 0, last_slab_quads = 0;
 
 	Model() : flat_owner(std::make_shared<FlatModel>()), flat(*flat_owner) {}
 	explicit Model(const std::shared_ptr<FlatModel>& shared) : flat_owner(shared), flat(*flat_owner) {}

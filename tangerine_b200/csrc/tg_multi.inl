@@ -273,7 +273,13 @@ std::vector<double> EstimateLayerCost(const FlatModel& flat, const tg_grid& grid
 		const uint64_t mask = have_masks ? flat.leaf_mask[leaf] : ~0ull;
 		if (mask == 0ull) continue;
 		const double quarter = double(flat.leaf_span[leaf]) * 0.25;
-		const double per_brick = double(node.flops) + constant;
+		// A brick that straddles octree cells runs one batch per cell (fewer samples per interpreter dispatch, more box
+		// resolution): measured on seaside_town, bricks among 16-cell leaves cost about a third more per FLOP than bricks
+		// inside large coalesced cells.  (1 + 8 / cells per leaf side) is the mean number of cells a brick meets per axis.
+		const double leaf_cells = std::max(1.0, double(flat.leaf_span[leaf]) / step[0]);
+		double straddle = 1.0 + 1.5 * double(kBrick) / leaf_cells;
+		if (const char* env = std::getenv("TG_PLAN_STRADDLE")) straddle = 1.0 + std::atof(env) * double(kBrick) / leaf_cells;
+		const double per_brick = (double(node.flops) + constant) * straddle;
 		for (int sz = 0; sz < 4; ++sz)
 		{
 			const uint32_t layer_mask = uint32_t(mask >> (16 * sz)) & 0xFFFFu;
@@ -386,17 +392,26 @@ int EngineTimerBeginMulti(DeviceGroup* group, std::string& error)
 	return TG_OK;
 }
 
-// Elapsed device time of the slowest rank (every rank's events sit on its own stream).
+// Elapsed device time of the slowest rank (every rank's events sit on its own stream).  All end events are recorded
+// before the first is waited for: a record-and-wait per device in turn would date the later devices' ends later.
 int EngineTimerEndMulti(DeviceGroup* group, float* out_ms, std::string& error)
 {
+	for (Context* c : group->contexts)
+	{
+		TG_CUDA(cudaSetDevice(c->device));
+		TG_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(c->timer_events[1]), StreamOf(c)));
+	}
 	float worst = 0.0f;
 	for (Context* c : group->contexts)
 	{
+		TG_CUDA(cudaSetDevice(c->device));
+		cudaEvent_t e1 = static_cast<cudaEvent_t>(c->timer_events[1]);
+		TG_CUDA(cudaEventSynchronize(e1));
 		float ms = 0.0f;
-		const int rc = EngineTimerEnd(c, &ms, error);
-		if (rc != TG_OK) return rc;
+		TG_CUDA(cudaEventElapsedTime(&ms, static_cast<cudaEvent_t>(c->timer_events[0]), e1));
 		worst = std::max(worst, ms);
 	}
+	TG_CUDA(cudaSetDevice(group->contexts[0]->device));
 	*out_ms = worst;
 	return TG_OK;
 }
@@ -503,6 +518,13 @@ int EngineExportMeshMulti(DeviceGroup* group, const std::vector<Model*>& models,
 		hook.all_gather = &NcclAllGatherCount;
 		// Every rank makes the same sequence of collective calls whatever happens to it: a rank that failed before the
 		// all-gather still has to enter it, or its peers would wait forever.  So errors are remembered, not returned early.
+		if (ex.cap_v[size_t(rank)] == 0 && (ex.options.flags & TG_MESH_REBALANCE) && model->last_slab_vertices > 0)
+		{
+			// the cuts move from export to export: size the arrays by this device's last slab (plus half) instead of by
+			// the cautious default for an unknown slab, so that the result buffers of the last export fit again
+			ex.cap_v[size_t(rank)] = uint32_t(std::min<uint64_t>(model->last_slab_vertices + model->last_slab_vertices / 2 + 4096, 0xFFFFFFF0ull));
+			ex.cap_q[size_t(rank)] = uint32_t(std::min<uint64_t>(model->last_slab_quads + model->last_slab_quads / 2 + 4096, 0x2AAAAAA0ull));
+		}
 		for (int attempt = 0; attempt < 2; ++attempt)
 		{
 			ex.jobs[size_t(rank)].reset(new MeshJob());
@@ -587,6 +609,8 @@ int EngineExportMeshMulti(DeviceGroup* group, const std::vector<Model*>& models,
 		group->Barrier();
 		const MeshCounts& counts = ex.counts[size_t(rank)];
 		const uint64_t v = counts.vertices, t = counts.quads * 2;
+		model->last_slab_vertices = counts.vertices;
+		model->last_slab_quads = counts.quads;
 		MeshResultDevice* r = job.result;
 		if (ex.want_host && ex.host_ok)
 		{
@@ -718,7 +742,8 @@ int EngineExportMeshMulti(DeviceGroup* group, const std::vector<Model*>& models,
 			for (int r = 0; r < n; ++r)
 			{
 				if (!(predicted[size_t(r)] > 0.0) || !(measured[size_t(r)] > 0.0)) continue;
-				const double scale = (measured[size_t(r)] / measured_sum) / (predicted[size_t(r)] / predicted_sum);
+				// (square root: half the correction per export, so that one noisy measurement cannot throw the cuts)
+				const double scale = std::sqrt((measured[size_t(r)] / measured_sum) / (predicted[size_t(r)] / predicted_sum));
 				for (uint32_t k = ex.cuts[size_t(r)]; k < ex.cuts[size_t(r) + 1]; ++k) plan.layer_cost[k] *= scale;
 			}
 			plan.cuts = PlanSlabs(plan.layer_cost, grid.sz, n);

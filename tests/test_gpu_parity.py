@@ -497,3 +497,30 @@ def test_cooperative_long_program_evaluation_is_exact(name, reach, models):
     tree, model = models(name)
     probes, block_bad, warp_bad = model.check_long_programs(reach)
     assert block_bad == 0 and warp_bad == 0, (probes, block_bad, warp_bad)
+
+
+def test_exported_ply_with_refinement_differs_from_the_reference_on_purpose(golden, tmp_path):
+    """tg_export_ply(tree, GridSize, RefineIterations = 5, ...): the reference's ExportPLY takes the same argument and
+    never uses it -- MeshExportThread ignores RefineIterations, only the point-cloud export refines (export.cpp:320-381
+    against :433-469) -- while this library applies the refinement loop to the mesh vertices (BASELINE.json north_star).
+    So with refine = 0 the file is the reference's byte for byte (test above), and with refine = 5 it has the same
+    header, the same faces and refined vertices: positions / normals equal to the C oracle's refinement of the
+    reference's vertices, each within half a cell of where it started."""
+    import os
+    name = "basic_thing"
+    tree = T.Tree.load(O.model_path(name))
+    cpu = float(golden[name]["cells_per_unit"])
+    plain, refined = str(tmp_path / "plain.ply"), str(tmp_path / "refined.ply")
+    L = T.lib()
+    assert L.tg_export_ply(tree.h, cpu, 0, os.fsencode(plain), 0) == 0, L.tg_last_error()
+    assert L.tg_export_ply(tree.h, cpu, 5, os.fsencode(refined), 0) == 0, L.tg_last_error()
+    a, b = O.read_ply(plain), O.read_ply(refined)
+    assert len(a["pos"]) == len(b["pos"]) and np.array_equal(a["tris"], b["tris"])
+    assert not np.array_equal(a["pos"], b["pos"])                       # the documented difference from the reference
+    step = np.float32(1.0 / cpu)
+    assert np.abs(a["pos"] - b["pos"]).max() <= step / 2 + 1e-6        # clamped to half a cell (export.cpp:453)
+    om = O.Model(name)
+    oc = O.Octree(om)
+    want = oc.refine(a["pos"].copy(), [step / 2] * 3, 5)
+    assert same_floats(b["pos"], want)
+    assert same_floats(b["normal"], oc.gradient(want))
