@@ -563,6 +563,19 @@ TG_CATCH_STATUS
 int tg_model_get_stats(const tg_model* model, tg_model_stats* out) try
 {
 	if (!model || !out) return Fail(TG_ERR_INVALID, "null argument");
+	FlatModelStats& stats = model->impl->flat.stats;
+	if (!stats.reference_done && model->impl->source)
+	{
+		// tg_model_create skips the reference-format diagnostics (word counts, octree hash); they are computed here, once
+		FlatModel again;
+		std::string error;
+		if (!BuildFlatModel(*model->impl->source, model->impl->source_target_size, 0, again, error)) return Fail(TG_ERR_INVALID, error);
+		stats.ref_words = again.stats.ref_words;
+		stats.ref_leaf_words = again.stats.ref_leaf_words;
+		stats.ref_max_words = again.stats.ref_max_words;
+		stats.hash = again.stats.hash;
+		stats.reference_done = true;
+	}
 	FillStats(model->impl->flat, out);
 	out->device_bytes = model->impl->device_bytes;
 	out->upload_seconds = model->impl->upload_seconds;

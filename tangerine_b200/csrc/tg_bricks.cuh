@@ -52,6 +52,7 @@ struct MeshParams
 	const unsigned long long* brick_count; // device: length of `bricks` (written by CullResolveKernel)
 	uint32_t brick_capacity;
 	unsigned long long* bitmap; // one bit per cell, rows padded to 64 cells; layer 0 = cell layer k_base
+	uint32_t* word_flags;       // one bit per bitmap word: the word holds active cells (the numbering scans skip the rest unread)
 	uint32_t row_words;
 	uint32_t k_base;
 	uint32_t k_own_begin, k_own_end;
@@ -213,9 +214,9 @@ __device__ __forceinline__ void EvaluateTile(WarpTile& w, const DeviceModel& mod
 						pz[q] = LatticeCoord(grid.z, grid.dz, k0 + lk);
 					}
 					// square roots on the branch-free fast path; the (practically never taken) repeat keeps the result exact
-					uint32_t suspect = 0u;
-					EvalInterp<kLaneSamples, false, false, true>(program, px, py, pz, d, &suspect);
-					if (__any_sync(0xFFFFFFFFu, suspect != 0u)) EvalInterp<kLaneSamples>(program, px, py, pz, d);
+					sdf::SqrtRange seen;
+					EvalInterp<kLaneSamples, false, false, true>(program, px, py, pz, d, &seen);
+					if (__any_sync(0xFFFFFFFFu, seen.Suspect())) EvalInterp<kLaneSamples>(program, px, py, pz, d);
 #pragma unroll
 					for (int q = 0; q < kLaneSamples; ++q)
 					{
@@ -340,7 +341,10 @@ __device__ __forceinline__ unsigned CellCorners(const WarpTile& w, int c, float 
 	return signs;
 }
 
-__global__ void __launch_bounds__(kBrickThreads, 8) MeshBricksKernel(const MeshParams p)
+#ifndef TG_BRICK_MIN_BLOCKS
+#define TG_BRICK_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(kBrickThreads, TG_BRICK_MIN_BLOCKS) MeshBricksKernel(const MeshParams p)
 {
 	__shared__ WarpTile tiles[kBrickWarps];
 	WarpTile& w = tiles[threadIdx.x >> 5];
@@ -403,7 +407,12 @@ __global__ void __launch_bounds__(kBrickThreads, 8) MeshBricksKernel(const MeshP
 			uint32_t active = ~((all & (all >> 1)) | ~(any | (any >> 1))) & ((1u << cells_x) - 1u);
 			// the slab owns cell layers [k_own_begin, k_own_end) and classifies the halo layer k_base below it
 			if (!(gj < grid.sy && gk < p.k_own_end && ck >= kmin)) active = 0u;
-			if (active) bitmap_bytes[(size_t(gk - p.k_base) * grid.sy + gj) * (size_t(p.row_words) * 8u) + bx] = (unsigned char)active;
+			if (active)
+			{
+				const size_t word = (size_t(gk - p.k_base) * grid.sy + gj) * size_t(p.row_words) + (bx >> 3);
+				bitmap_bytes[word * 8u + (bx & 7u)] = (unsigned char)active;
+				atomicOr(&p.word_flags[word >> 5], 1u << (word & 31u));
+			}
 			uint32_t emit = gk >= p.k_own_begin ? active : 0u; // the halo layer is classified but owned by the slab below
 			const int count = __popc(emit);
 			int incl = count;

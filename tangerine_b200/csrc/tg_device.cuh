@@ -92,24 +92,24 @@ __device__ __forceinline__ float4 AsFloat4(const uint4& v)
 // Every fetch is a 128-bit load whose address does not depend on another fetch of the same instruction, and the
 // first quad of the next instruction is requested before this instruction's arithmetic starts.  The operator
 // switch sits outside the per-sample loops, so with a warp-uniform program there is one dispatch per brush.
-// DEFER: square roots take the branch-free fast path (sdf::SqrtDeferred) and *suspect is raised when an argument fell
+// DEFER: square roots take the branch-free fast path (sdf::SqrtDeferred) and *seen (sdf::SqrtRange) records whether an argument fell
 // outside its range -- the caller then evaluates again without DEFER.
 template <bool DEFER> struct SqrtPolicy
 {
 	using type = sdf::SqrtExact;
-	static __device__ __forceinline__ type Make(uint32_t*) { return type(); }
+	static __device__ __forceinline__ type Make(sdf::SqrtRange*) { return type(); }
 };
 template <> struct SqrtPolicy<true>
 {
 	using type = sdf::SqrtDeferred;
-	static __device__ __forceinline__ type Make(uint32_t* suspect) { return type{ suspect }; }
+	static __device__ __forceinline__ type Make(sdf::SqrtRange* seen) { return type{ seen }; }
 };
 
 template <int S, bool PREFETCH = false, bool DEEP = false, bool DEFER = false>
 __device__ __forceinline__ void EvalInterp(const uint4* __restrict__ pc, const float (&px)[S], const float (&py)[S], const float (&pz)[S], float (&result)[S],
-	uint32_t* suspect = nullptr)
+	sdf::SqrtRange* seen = nullptr)
 {
-	const typename SqrtPolicy<DEFER>::type sq = SqrtPolicy<DEFER>::Make(suspect);
+	const typename SqrtPolicy<DEFER>::type sq = SqrtPolicy<DEFER>::Make(seen);
 	float acc[S];
 	float stack[kMaxStackSlots][S];
 #pragma unroll
@@ -810,10 +810,11 @@ struct MaterialRegs
 };
 
 // Executes `program` for S points.  MATERIAL selects the GetMaterial walk (tree stream only).
-template <int S, bool MATERIAL>
+template <int S, bool MATERIAL, bool DEFER = false>
 __device__ __forceinline__ void RunProgram(const uint32_t* __restrict__ program, const float (&px)[S], const float (&py)[S], const float (&pz)[S],
-	float (&result)[S], uint32_t (&result_material)[S])
+	float (&result)[S], uint32_t (&result_material)[S], sdf::SqrtRange* seen = nullptr)
 {
+	const typename SqrtPolicy<DEFER>::type sq = SqrtPolicy<DEFER>::Make(seen);
 	float acc[S];
 	uint32_t accm[S];
 	float stack[kMaxStackSlots][S];
@@ -911,28 +912,28 @@ __device__ __forceinline__ void RunProgram(const uint32_t* __restrict__ program,
 				const float a = __ldg(arg), b = __ldg(arg + 1), c = __ldg(arg + 2);
 				arg += 3;
 #pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Box(lx[s], ly[s], lz[s], a, b, c);
+				for (int s = 0; s < S; ++s) d[s] = sdf::Box(lx[s], ly[s], lz[s], a, b, c, sq);
 			}
 			else if (Opaque(kind) == kBrushSphere)
 			{
 				const float r = __ldg(arg);
 				arg += 1;
 #pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Sphere(lx[s], ly[s], lz[s], r);
+				for (int s = 0; s < S; ++s) d[s] = sdf::Sphere(lx[s], ly[s], lz[s], r, sq);
 			}
 			else if (Opaque(kind) == kBrushCylinder)
 			{
 				const float a = __ldg(arg), b = __ldg(arg + 1);
 				arg += 2;
 #pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Cylinder(lx[s], ly[s], lz[s], a, b);
+				for (int s = 0; s < S; ++s) d[s] = sdf::Cylinder(lx[s], ly[s], lz[s], a, b, sq);
 			}
 			else if (Opaque(kind) == kBrushTorus)
 			{
 				const float a = __ldg(arg), b = __ldg(arg + 1);
 				arg += 2;
 #pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Torus(lx[s], ly[s], lz[s], a, b);
+				for (int s = 0; s < S; ++s) d[s] = sdf::Torus(lx[s], ly[s], lz[s], a, b, sq);
 			}
 			else if (Opaque(kind) == kBrushPlane)
 			{
@@ -946,21 +947,21 @@ __device__ __forceinline__ void RunProgram(const uint32_t* __restrict__ program,
 				const float a = __ldg(arg), b = __ldg(arg + 1), c = __ldg(arg + 2);
 				arg += 3;
 #pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Ellipsoid(lx[s], ly[s], lz[s], a, b, c);
+				for (int s = 0; s < S; ++s) d[s] = sdf::Ellipsoid(lx[s], ly[s], lz[s], a, b, c, sq);
 			}
 			else if (Opaque(kind) == kBrushCone)
 			{
 				const float a = __ldg(arg), b = __ldg(arg + 1);
 				arg += 2;
 #pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Cone(lx[s], ly[s], lz[s], a, b);
+				for (int s = 0; s < S; ++s) d[s] = sdf::Cone(lx[s], ly[s], lz[s], a, b, sq);
 			}
 			else
 			{
 				const float a = __ldg(arg), b = __ldg(arg + 1), c = __ldg(arg + 2);
 				arg += 3;
 #pragma unroll
-				for (int s = 0; s < S; ++s) d[s] = sdf::Coninder(lx[s], ly[s], lz[s], a, b, c);
+				for (int s = 0; s < S; ++s) d[s] = sdf::Coninder(lx[s], ly[s], lz[s], a, b, c, sq);
 			}
 			if (header & kHdrScaleBit)
 			{
@@ -1142,6 +1143,11 @@ __device__ __noinline__ float EvalTreeCentre(const uint32_t* __restrict__ tree_p
 	return d[0];
 }
 
+__device__ __noinline__ void EvalDistance4Exact(const uint32_t* __restrict__ program, const float (&px)[4], const float (&py)[4], const float (&pz)[4], float (&out)[4])
+{
+	EvalDistance<4>(program, px, py, pz, out);
+}
+
 // SDFNode::Gradient (sdf_evaluator.cpp:298-333) on a tree-stream program: the four tetrahedral taps are
 // the four samples of one RunProgram<4> call.
 __device__ __forceinline__ void EvalGradient(const uint32_t* __restrict__ tree_program, float x, float y, float z, float& gx, float& gy, float& gz)
@@ -1153,7 +1159,13 @@ __device__ __forceinline__ void EvalGradient(const uint32_t* __restrict__ tree_p
 	const float py[4] = { y + oy, y + oy, y + ox, y + ox };
 	const float pz[4] = { z + oy, z + ox, z + oy, z + ox };
 	float d[4];
-	EvalDistance<4>(tree_program, px, py, pz, d);
+	{
+		// branch-free square roots (sdf::SqrtDeferred); the exact repeat is practically never taken and lives out of line
+		uint32_t unused[4];
+		sdf::SqrtRange seen;
+		RunProgram<4, false, true>(tree_program, px, py, pz, d, unused, &seen);
+		if (seen.Suspect()) EvalDistance4Exact(tree_program, px, py, pz, d);
+	}
 	// Offset.xyy * d0 + Offset.yyx * d1 + Offset.yxy * d2 + Offset.xxx * d3, summed left to right
 	float sx = ((ox * d[0] + oy * d[1]) + oy * d[2]) + ox * d[3];
 	float sy = ((oy * d[0] + oy * d[1]) + ox * d[2]) + ox * d[3];

@@ -790,6 +790,31 @@ struct LoadVertexQuadCounts
 	}
 };
 
+// The same count for a word KNOWN to hold cells (its flag is set) whose row position the caller already has: all seven
+// bitmap loads are issued together instead of behind the test of the word itself -- one memory round trip, not two.
+__device__ __forceinline__ unsigned long long CountFlaggedWord(const unsigned long long* __restrict__ bitmap, size_t index, uint32_t wi, bool inner,
+	uint32_t row_words, uint32_t sy)
+{
+	// inner: layer != 0 && j != 0.  Outside of it (and for i - 1 at wi == 0) the loads fall back on the word itself.
+	const size_t back = inner ? index - row_words : index;
+	const size_t below = inner ? index - size_t(sy) * row_words : index;
+	const size_t below_back = inner ? below - row_words : index;
+	const size_t prev = (inner && wi != 0u) ? 1u : 0u;
+	const unsigned long long self = bitmap[index], b = bitmap[back], c = bitmap[below], d = bitmap[below_back];
+	unsigned long long wp = bitmap[index - prev], bp = bitmap[back - prev], cp = bitmap[below - prev];
+	uint32_t quads = 0;
+	if (inner)
+	{
+		if (wi == 0u) wp = bp = cp = 0ull;
+		const unsigned long long n0 = (self << 1) | (wp >> 63); // (i-1, j,   k)
+		const unsigned long long n1 = (b << 1) | (bp >> 63);    // (i-1, j-1, k)
+		const unsigned long long n5 = (c << 1) | (cp >> 63);    // (i-1, j,   k-1)
+		const unsigned long long not_first = wi == 0u ? ~1ull : ~0ull; // i != 0
+		quads = uint32_t(__popcll(self & n0 & n1 & b) + __popcll(self & n0 & n5 & c) + __popcll(self & b & d & c & not_first));
+	}
+	return (unsigned long long)__popcll(self) | ((unsigned long long)quads << 32);
+}
+
 __device__ __forceinline__ unsigned long long BlockExclusiveScan64(unsigned long long value, unsigned long long* warp_sums, unsigned long long& block_total)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -820,20 +845,63 @@ __device__ __forceinline__ unsigned long long BlockExclusiveScan64(unsigned long
 	return warp_base + inclusive - value;
 }
 
-// Dual scan, pass 1: per-tile totals of (vertices, quads), packed low / high.
-__global__ void __launch_bounds__(kScanBlock) PairSumsKernel(LoadVertexQuadCounts load, size_t count, unsigned long long* block_sums)
+// The dual (vertex, quad) scan is sparse: MeshBricksKernel raises one flag bit per bitmap word that holds active cells
+// and words without a flag are neither read nor given a prefix (at seaside 1024^3 a few words in a hundred are flagged:
+// 2 MB of flags stand in for 128 MB of bitmap and 128 MB of prefix).  A warp owns 32 flag words = 1024 consecutive bitmap
+// words and walks the non-empty flag words one at a time, lane l on bitmap word l of the 32 -- coalesced like a dense pass.
+constexpr int kPairWarpWords = 1024;
+constexpr int kPairWarps = kScanBlock / 32;
+
+// Dual scan, pass 1: (vertices, quads) of every flagged word, stashed packed (v | q << 16) in the word's prefix slot, and
+// the totals of every warp's 1024 words, packed low / high.  The warp first lists its flagged words in shared memory and
+// then counts them one per lane: the seven bitmap loads behind a count (QuadMasks) are independent across lanes.
+__global__ void __launch_bounds__(kScanBlock) PairSumsKernel(LoadVertexQuadCounts load, const uint32_t* __restrict__ word_flags, size_t count, uint2* stash,
+	unsigned long long* warp_sums)
 {
-	__shared__ unsigned long long warp_sums[32];
-	const size_t base = size_t(blockIdx.x) * kScanTile + size_t(threadIdx.x) * kScanItems;
-	unsigned long long sum = 0;
+	__shared__ uint16_t listed[kPairWarps][kPairWarpWords];
+	const int lane = threadIdx.x & 31;
+	uint16_t* list = listed[threadIdx.x >> 5];
+	const size_t warp = size_t(blockIdx.x) * kPairWarps + (threadIdx.x >> 5);
+	const size_t base = warp * kPairWarpWords;
+	if (base >= count) return;
+	uint32_t mine = base + size_t(lane) * 32 < count ? word_flags[(base >> 5) + lane] : 0u;
+	const int own = __popc(mine);
+	int inclusive = own;
 #pragma unroll
-	for (int i = 0; i < kScanItems; ++i)
+	for (int o = 1; o < 32; o <<= 1)
 	{
-		if (base + i < count) sum += load(base + i);
+		const int n = __shfl_up_sync(0xFFFFFFFFu, inclusive, o);
+		if (lane >= o) inclusive += n;
 	}
-	unsigned long long total;
-	BlockExclusiveScan64(sum, warp_sums, total);
-	if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+	const int total = __shfl_sync(0xFFFFFFFFu, inclusive, 31);
+	int at = inclusive - own;
+	while (mine)
+	{
+		list[at++] = uint16_t(lane * 32 + __ffs(mine) - 1);
+		mine &= mine - 1u;
+	}
+	__syncwarp();
+	// row position of the warp's first word (64-bit divisions, once); the items then get by with 32-bit arithmetic
+	const size_t row0 = base / load.row_words;
+	const uint32_t wi0 = uint32_t(base - row0 * load.row_words), j0 = uint32_t(row0 % load.sy);
+	const bool layer0 = row0 / load.sy == 0;
+	uint32_t vertices = 0, quads = 0;
+	for (int t = lane; t < total; t += 32)
+	{
+		const uint32_t along = wi0 + list[t], rows = along / load.row_words; // rows past row0
+		const size_t word = base + list[t];
+		const uint32_t wi = along - rows * load.row_words;
+		const uint32_t j_long = j0 + rows; // j, or sy or more past it in the layers above
+		const bool inner = !(layer0 && j_long < load.sy) && j_long % load.sy != 0u;
+		const unsigned long long c = CountFlaggedWord(load.bitmap, word, wi, inner, load.row_words, load.sy);
+		const uint32_t v = uint32_t(c), q = uint32_t(c >> 32);
+		stash[word].x = v | (q << 16); // v <= 64, q <= 192
+		vertices += v;
+		quads += q;
+	}
+	vertices = __reduce_add_sync(0xFFFFFFFFu, vertices);
+	quads = __reduce_add_sync(0xFFFFFFFFu, quads);
+	if (lane == 0) warp_sums[warp] = (unsigned long long)vertices | ((unsigned long long)quads << 32);
 }
 
 // Pass 2 (one block): exclusive scan of the tile totals in place; grand totals to totals_out[0] (vertices) and [1] (quads).
@@ -885,26 +953,64 @@ __global__ void __launch_bounds__(1024) PairSumsScanKernel(unsigned long long* b
 	}
 }
 
-// Pass 3: exclusive (vertex, quad) prefix of every bitmap word.
-__global__ void __launch_bounds__(kScanBlock) PairPrefixKernel(LoadVertexQuadCounts load, size_t count, const unsigned long long* block_sums, uint2* out)
+// Pass 3: exclusive (vertex, quad) prefix of every flagged bitmap word, and of the first word of every cell layer
+// (the layer profile and the halo count read those whether or not they hold cells).  Warps work alone: the scanned
+// warp totals give each its start.
+__global__ void __launch_bounds__(kScanBlock) PairPrefixKernel(const uint32_t* __restrict__ word_flags, size_t count, const unsigned long long* warp_sums, uint2* out,
+	size_t layer_words)
 {
-	__shared__ unsigned long long warp_sums[32];
-	const size_t base = size_t(blockIdx.x) * kScanTile + size_t(threadIdx.x) * kScanItems;
-	unsigned long long v[kScanItems];
-	unsigned long long sum = 0;
-#pragma unroll
-	for (int i = 0; i < kScanItems; ++i)
+	const int lane = threadIdx.x & 31;
+	const size_t warp = size_t(blockIdx.x) * kPairWarps + (threadIdx.x >> 5);
+	const size_t base = warp * kPairWarpWords;
+	if (base >= count) return;
+	const uint32_t mine = base + size_t(lane) * 32 < count ? word_flags[(base >> 5) + lane] : 0u;
+	unsigned rounds = __ballot_sync(0xFFFFFFFFu, mine != 0u);
+	// rounds that hold the first word of a layer run even when nothing in them is flagged
+	size_t next_layer = (base + layer_words - 1) / layer_words * layer_words;
+	const size_t end = base + kPairWarpWords < count ? base + kPairWarpWords : count;
+	for (size_t at = next_layer; at < end; at += layer_words) rounds |= 1u << uint32_t((at - base) >> 5);
+	const unsigned long long start = warp_sums[warp];
+	uint32_t run_v = uint32_t(start), run_q = uint32_t(start >> 32);
+	// eight flag words at a time: all their stash loads are in flight before the first in-warp scan needs one
+#pragma unroll 1
+	for (int batch = 0; batch < 4; ++batch)
 	{
-		v[i] = base + i < count ? load(base + i) : 0ull;
-		sum += v[i];
-	}
-	unsigned long long total;
-	unsigned long long running = BlockExclusiveScan64(sum, warp_sums, total) + block_sums[blockIdx.x];
+		const unsigned batch_rounds = (rounds >> (batch * 8)) & 0xFFu;
+		if (batch_rounds == 0u) continue;
+		uint32_t packed[8];
 #pragma unroll
-	for (int i = 0; i < kScanItems; ++i)
-	{
-		if (base + i < count) out[base + i] = make_uint2(uint32_t(running), uint32_t(running >> 32));
-		running += v[i];
+		for (int i = 0; i < 8; ++i)
+		{
+			const int r = batch * 8 + i;
+			const uint32_t flags = __shfl_sync(0xFFFFFFFFu, mine, r);
+			packed[i] = ((flags >> lane) & 1u) ? out[base + size_t(r) * 32 + lane].x : 0u;
+		}
+#pragma unroll
+		for (int i = 0; i < 8; ++i)
+		{
+			if (!((batch_rounds >> i) & 1u)) continue;
+			const int r = batch * 8 + i;
+			const uint32_t flags = __shfl_sync(0xFFFFFFFFu, mine, r);
+			const size_t round_base = base + size_t(r) * 32;
+			uint32_t inclusive = packed[i]; // sums of a round stay below 2^16 in both halves (32 * 64, 32 * 192)
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inclusive, o);
+				if (lane >= o) inclusive += n;
+			}
+			const uint32_t exclusive = inclusive - packed[i];
+			const uint2 prefix = make_uint2(run_v + (exclusive & 0xFFFFu), run_q + (exclusive >> 16));
+			if ((flags >> lane) & 1u) out[round_base + lane] = prefix;
+			while (next_layer < round_base + 32 && next_layer < end)
+			{
+				if (next_layer >= round_base && size_t(lane) == next_layer - round_base) out[next_layer] = prefix;
+				next_layer += layer_words;
+			}
+			const uint32_t total = __shfl_sync(0xFFFFFFFFu, inclusive, 31);
+			run_v += total & 0xFFFFu;
+			run_q += total >> 16;
+		}
 	}
 }
 
@@ -1885,12 +1991,14 @@ Model* Model::Create(Context* context, const Tree& tree, float target_size, int 
 {
 	Model* m = new Model();
 	m->context = context;
-	if (!BuildFlatModel(tree, target_size, threads, m->flat, error))
+	if (!BuildFlatModel(tree, target_size, threads, m->flat, error, false)) // reference statistics on demand (tg_model_get_stats)
 	{
 		delete m;
 		return nullptr;
 	}
 	m->leaf_count = tree.LeafCount();
+	m->source = std::make_shared<const Tree>(tree);
+	m->source_target_size = target_size;
 	const auto t0 = std::chrono::steady_clock::now();
 	if (UploadModel(m, error) != TG_OK)
 	{
@@ -2606,6 +2714,9 @@ static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const
 	TG_CUDA(scratch.Alloc(&prefix, bitmap_words));
 	TG_CUDA(cudaMemsetAsync(counters, 0, kCntCount * 8, stream));
 	TG_CUDA(cudaMemsetAsync(bitmap, 0, bitmap_words * 8, stream));
+	uint32_t* word_flags = nullptr;
+	TG_CUDA(scratch.Alloc(&word_flags, (bitmap_words + 31) / 32));
+	TG_CUDA(cudaMemsetAsync(word_flags, 0, (bitmap_words + 31) / 32 * 4, stream));
 	job.counters = counters;
 	TG_CUDA(cudaEventRecord(job.marks[0], stream));
 	const double h_setup = host_us(h_begin);
@@ -2636,6 +2747,7 @@ static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const
 	mp.brick_count = counters + kCntListA;
 	mp.brick_capacity = uint32_t(job.list_capacity);
 	mp.bitmap = bitmap;
+	mp.word_flags = word_flags;
 	mp.row_words = row_words;
 	mp.k_base = k_base;
 	mp.k_own_begin = k_begin;
@@ -2680,12 +2792,13 @@ static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const
 	// ---- vertex + quad numbering: one dual scan over the bitmap ----------------------------------
 	{
 		const LoadVertexQuadCounts load{ bitmap, row_words, grid.sy };
-		const uint32_t blocks = uint32_t((bitmap_words + kScanTile - 1) / kScanTile);
+		const uint32_t warps = uint32_t((bitmap_words + kPairWarpWords - 1) / kPairWarpWords);
+		const uint32_t blocks = (warps + kPairWarps - 1) / kPairWarps;
 		unsigned long long* sums = nullptr;
-		TG_CUDA(scratch.Alloc(&sums, std::max<uint32_t>(blocks, 1)));
-		PairSumsKernel<<<blocks, kScanBlock, 0, stream>>>(load, bitmap_words, sums);
-		PairSumsScanKernel<<<1, 1024, 0, stream>>>(sums, blocks, counters + kCntTotalVertices);
-		PairPrefixKernel<<<blocks, kScanBlock, 0, stream>>>(load, bitmap_words, sums, prefix);
+		TG_CUDA(scratch.Alloc(&sums, std::max<uint32_t>(warps, 1)));
+		PairSumsKernel<<<blocks, kScanBlock, 0, stream>>>(load, word_flags, bitmap_words, prefix, sums);
+		PairSumsScanKernel<<<1, 1024, 0, stream>>>(sums, warps, counters + kCntTotalVertices);
+		PairPrefixKernel<<<blocks, kScanBlock, 0, stream>>>(word_flags, bitmap_words, sums, prefix, size_t(grid.sy) * row_words);
 		launches += 3;
 		TG_CUDA(cudaGetLastError());
 	}

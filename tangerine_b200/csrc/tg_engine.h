@@ -87,6 +87,8 @@ class Model
 public:
 	Context* context = nullptr;
 	std::shared_ptr<FlatModel> flat_owner; // one host copy of the tables, shared by the replicas of a multi-GPU model
+	std::shared_ptr<const Tree> source;    // the CSG tree the tables were built from: reference statistics on demand
+	float source_target_size = 0.25f;
 	FlatModel& flat;
 	Model* primary = nullptr; // replica: uploads from the primary's page-locked staging copies
 	void* d_nodes = nullptr;

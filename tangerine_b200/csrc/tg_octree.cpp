@@ -46,6 +46,13 @@ struct Subtree
 	int32_t root = -1;
 };
 
+static size_t CountBuildNodes(const Subtree& st)
+{
+	size_t n = st.nodes.size();
+	for (const auto& sub : st.spawned) n += CountBuildNodes(*sub);
+	return n;
+}
+
 // A fixed set of worker threads and one queue of tasks.  A thread that waits for tasks it submitted runs queued tasks
 // itself meanwhile (HelpUntil), so the recursion of the octree build can fan out at any depth without ever holding a
 // thread idle or creating one per task.
@@ -512,6 +519,7 @@ struct Flattener
 	std::vector<Mat4> inverse;     // CompiledInverseMatrix of every brush of the model, by node index
 	std::vector<Job> jobs;         // one per octree node, pre-order
 	int max_slots = 0;
+	bool reference_stats = true;
 
 	// Pass 1: pre-order walk emitting one FlatNode (pivot, terminus, children) per octree node and the regions.
 	uint32_t Walk(const Subtree& st, int32_t index, const float (&lo)[3], const float (&hi)[3])
@@ -605,6 +613,8 @@ struct Flattener
 		tree.Finish();
 		job.flops = interp.flops;
 		job.max_slots = tree.max_slots;
+		job.stack = st.pool.nodes[bn.evaluator].stack_size;
+		if (!reference_stats) return;
 		// Reference-format words: statistics + hash only.
 		std::vector<uint32_t> ref_words;
 		st.pool.CompileReference(bn.evaluator, ref_words, inverse.empty() ? nullptr : inverse.data());
@@ -616,7 +626,6 @@ struct Flattener
 		}
 		const uint32_t terminus = bn.terminus ? 1u : 0u;
 		job.ref_words = ref_words.size();
-		job.stack = st.pool.nodes[bn.evaluator].stack_size;
 		uint64_t h = 0xCBF29CE484222325ull;
 		h = Fnv(h, &bn.pivot, 12);
 		h = Fnv(h, &terminus, 4);
@@ -625,48 +634,77 @@ struct Flattener
 		job.node_hash = h;
 	}
 
-	// Pass 3: offsets, concatenation, statistics.  The octree hash is FNV-1a over the nodes' own hashes in pre-order.
-	void Assemble()
+	// Pass 3: offsets, statistics, concatenation (the copies in batches on the task pool when there is one).  The octree
+	// hash is FNV-1a over the nodes' own hashes in pre-order.
+	template <class Pool> void Assemble(Pool* tasks)
 	{
-		size_t interp_words = 0, tree_words = 0;
-		for (const Job& job : jobs)
-		{
-			interp_words += job.interp.size();
-			tree_words += job.tree.size();
-		}
-		model.interp.reserve(model.interp.size() + interp_words + 4096);
-		model.tree.reserve(model.tree.size() + tree_words + 4096);
+		std::vector<size_t> interp_at(jobs.size()), tree_at(jobs.size());
+		size_t interp_words = model.interp.size(), tree_words = model.tree.size();
 		FlatModelStats& s = model.stats;
 		for (size_t i = 0; i < jobs.size(); ++i)
 		{
-			Job& job = jobs[i];
+			const Job& job = jobs[i];
 			FlatNode& fn = model.nodes[i];
-			fn.interp_offset = uint32_t(model.interp.size()) + job.interp_program_at;
-			model.interp.insert(model.interp.end(), job.interp.begin(), job.interp.end());
-			fn.tree_offset = uint32_t(model.tree.size());
-			model.tree.insert(model.tree.end(), job.tree.begin(), job.tree.end());
+			interp_at[i] = interp_words;
+			tree_at[i] = tree_words;
+			fn.interp_offset = uint32_t(interp_words) + job.interp_program_at;
+			fn.tree_offset = uint32_t(tree_words);
+			interp_words += job.interp.size();
+			tree_words += job.tree.size();
 			fn.flags = job.flags;
 			fn.flops = job.flops;
 			if (job.max_slots > max_slots) max_slots = job.max_slots;
 			s.nodes++;
-			s.ref_words += job.ref_words;
-			if (fn.terminus)
-			{
-				s.leaves++;
-				s.ref_leaf_words += job.ref_words;
-			}
-			if (job.ref_words > s.ref_max_words) s.ref_max_words = job.ref_words;
+			if (fn.terminus) s.leaves++;
 			if (job.stack > s.max_stack) s.max_stack = job.stack;
+			if (!reference_stats) continue;
+			s.ref_words += job.ref_words;
+			if (fn.terminus) s.ref_leaf_words += job.ref_words;
+			if (job.ref_words > s.ref_max_words) s.ref_max_words = job.ref_words;
 			s.hash = Fnv(s.hash, &job.node_hash, 8);
-			std::vector<uint32_t>().swap(job.interp);
-			std::vector<uint32_t>().swap(job.tree);
+		}
+		// room for what BuildFlatModel appends afterwards (the unpruned programs are about the root node's size)
+		const size_t spare = jobs.empty() ? 0 : 2 * (jobs[0].interp.size() + jobs[0].tree.size()) + 4096;
+		model.interp.reserve(interp_words + spare);
+		model.tree.reserve(tree_words + spare);
+		model.interp.resize(interp_words);
+		model.tree.resize(tree_words);
+		auto copy = [&](size_t begin, size_t end)
+		{
+			for (size_t i = begin; i < end; ++i)
+			{
+				Job& job = jobs[i];
+				if (!job.interp.empty()) std::memcpy(model.interp.data() + interp_at[i], job.interp.data(), job.interp.size() * 4);
+				if (!job.tree.empty()) std::memcpy(model.tree.data() + tree_at[i], job.tree.data(), job.tree.size() * 4);
+				std::vector<uint32_t>().swap(job.interp);
+				std::vector<uint32_t>().swap(job.tree);
+			}
+		};
+		const size_t batch = 256;
+		const size_t batches = (jobs.size() + batch - 1) / batch;
+		if (tasks && batches > 1)
+		{
+			std::atomic<int> pending{ int(batches) };
+			for (size_t b = 0; b < batches; ++b)
+			{
+				tasks->Submit([&copy, &pending, b, batch, this]()
+				{
+					copy(b * batch, std::min(jobs.size(), (b + 1) * batch));
+					pending.fetch_sub(1, std::memory_order_acq_rel);
+				});
+			}
+			tasks->HelpUntil(pending);
+		}
+		else
+		{
+			copy(0, jobs.size());
 		}
 	}
 };
 
 } // namespace
 
-bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel& out, std::string& error)
+bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel& out, std::string& error, bool reference_stats)
 {
 	const auto t0 = std::chrono::steady_clock::now();
 	out = FlatModel();
@@ -750,8 +788,14 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 
 	const double construct_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 	if (std::getenv("TG_TRACE_HOST")) std::fprintf(stderr, "octree build: construct %.1f ms (threads %d)\n", construct_seconds * 1e3, threads);
+	const bool trace_host = std::getenv("TG_TRACE_HOST") != nullptr;
+	auto lap = [&](const char* what)
+	{
+		if (trace_host) std::fprintf(stderr, "octree build: %s at %.1f ms\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e3);
+	};
 	out.stats.hash = 0xCBF29CE484222325ull;
-	Flattener flattener{ out, {}, {}, 0 };
+	Flattener flattener{ out, {}, {}, 0, reference_stats };
+	out.stats.reference_done = reference_stats;
 	flattener.inverse.resize(tree.pool.nodes.size());
 	for (size_t i = 0; i < tree.pool.nodes.size(); ++i)
 	{
@@ -760,7 +804,15 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 	}
 	{
 		const float lo[3] = { -INFINITY, -INFINITY, -INFINITY }, hi[3] = { INFINITY, INFINITY, INFINITY };
+		lap("inverse matrices");
+		const size_t build_nodes = CountBuildNodes(top);
+		out.nodes.reserve(build_nodes);
+		flattener.jobs.reserve(build_nodes);
+		out.regions.reserve(build_nodes * 3);
+		out.leaf_nodes.reserve(build_nodes);
+		out.leaf_span.reserve(build_nodes);
 		flattener.Walk(top, top.root, lo, hi);
+		lap("walk");
 	}
 	{
 		// programs of all nodes, in batches on the task pool (or here, serially)
@@ -797,7 +849,9 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 		{
 			for (Flattener::Job& job : jobs) flattener.Generate(job);
 		}
-		flattener.Assemble();
+		lap("generate");
+		flattener.Assemble(tasks);
+		lap("assemble");
 	}
 	if (flattener.max_slots > kMaxStackSlots)
 	{
@@ -815,6 +869,7 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 		for (size_t r = 0; r < by_cost.size(); ++r) out.node_rank[uint32_t(by_cost[r])] = uint32_t(r);
 	}
 
+	lap("node ranks");
 	// Unpruned model programs (VoxExport and whole-tree point queries).
 	{
 		out.root_interp_offset = uint32_t(out.interp.size());
@@ -832,6 +887,7 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 			return false;
 		}
 	}
+	lap("unpruned programs");
 	for (int i = 0; i < 4 * 40; ++i) out.interp.push_back(0); // the interpreter fetches one quad and prefetches 512 B past an instruction
 	SnapshotMaterials(out.material_rgb);
 	out.material_rgb.push_back(1.0f); // default material (GetDefaultMaterial :34-38), addressed by kNoMaterial

@@ -27,6 +27,7 @@ struct FlatModelStats
 	uint64_t ref_max_words = 0;
 	uint64_t max_stack = 0;    // largest SDFNode::StackSize of any node program
 	uint64_t hash = 0;         // FNV-1a over (pivot, terminus, child mask, reference words) in pre-order
+	bool reference_done = false; // ref_* and hash were computed (BuildFlatModel's reference_stats)
 	uint64_t interp_words = 0; // device stream sizes
 	uint64_t tree_words = 0;
 	double build_seconds = 0.0;
@@ -56,6 +57,8 @@ struct FlatModel
 
 // Returns false (and sets error) when the tree has no finite bounds, prunes away entirely, or nests
 // deeper than the device stack supports.  threads <= 0 picks std::thread::hardware_concurrency().
-bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel& out, std::string& error);
+// reference_stats: also compile every node program into the reference's word encoding for FlatModelStats::ref_* and
+// ::hash (diagnostics that pin the octree against the reference's; the device tables do not depend on them).
+bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel& out, std::string& error, bool reference_stats = true);
 
 } // namespace tg
