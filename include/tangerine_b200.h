@@ -152,6 +152,10 @@ typedef struct tg_model_stats
 } tg_model_stats;
 
 TG_API tg_model* tg_model_create(tg_context* context, const tg_tree* tree, float octree_target_size, int host_threads);
+/* The live mesher's model (Sodapop, tangerine/sodapop.cpp:227-247 and 562-600): the octree of
+ * SDFOctree::Create(Evaluator, .25, false, 3, 0.0) with every incomplete node populated -- nothing is coalesced.  Use it
+ * with tg_live_grid, TG_MESH_LIVE_FIELD and TG_EVAL_LIVE; every other call works on it as on any model. */
+TG_API tg_model* tg_model_create_live(tg_context* context, const tg_tree* tree, float octree_target_size, int host_threads);
 /* Host half of tg_model_create only (octree build + flattening, no device needed): fills the octree_*,
  * reference_*, max_stack, bounds, has_paint, leaf_count and build_seconds fields. */
 TG_API int tg_tree_octree_stats(const tg_tree* tree, float octree_target_size, int host_threads, tg_model_stats* out);
@@ -168,9 +172,11 @@ TG_API int tg_model_get_stats(const tg_model* model, tg_model_stats* out);
  *   TG_EVAL_TREE      SDFNode::Eval on the unpruned model        (magica.cpp:61 samples this)
  *   TG_EVAL_GRADIENT  SDFOctree::Gradient   (sdf_evaluator.h:327-331)      3 floats per point
  *   TG_EVAL_COLOR     export colour bytes   (export.cpp:297-312)           3 bytes per point
+ *   TG_EVAL_LIVE      the live mesher's implicit function (sodapop.cpp:583-587): clamp(SDFOctree::Eval(p, Exact = false),
+ *                     -100, 100) -- an empty octant yields +infinity, i.e. 100, instead of the parent's program
  * `points` and `out` are host pointers; count points of 3 floats.
  * ---------------------------------------------------------------------------------------------- */
-enum { TG_EVAL_OCTREE = 0, TG_EVAL_INTERP = 1, TG_EVAL_TREE = 2, TG_EVAL_GRADIENT = 3, TG_EVAL_COLOR = 4 };
+enum { TG_EVAL_OCTREE = 0, TG_EVAL_INTERP = 1, TG_EVAL_TREE = 2, TG_EVAL_GRADIENT = 3, TG_EVAL_COLOR = 4, TG_EVAL_LIVE = 5 };
 TG_API int tg_eval_points(tg_model* model, int mode, const float* points, uint64_t count, void* out);
 
 /* Batched ray casts: SDFNode::RayMarch (tangerine/sdf_evaluator.cpp:336-354) on the unpruned model, the call behind the
@@ -200,6 +206,11 @@ typedef struct tg_grid
 	uint64_t sx, sy, sz; /* cells per axis */
 } tg_grid;
 
+/* The live mesher's grid (NaiveSurfaceNetsScratch, sodapop.cpp:153-179) for a meshing density (Sodapop's default is 20,
+ * sodapop.cpp:43, 221): floor(density) samples per unit of the octree's bounds, at least 8 per axis, two cells of margin
+ * below and one above.  `model` must come from tg_model_create_live. */
+TG_API int tg_live_grid(const tg_model* model, float density, tg_grid* out);
+
 /* MeshExportThread's grid: ModelMin -= 2 * Step; Extent = ceil((ModelMax - ModelMin) / Step) (export.cpp:324-337). */
 TG_API int tg_export_grid(const float model_min[3], const float model_max[3], const float step[3], tg_grid* out);
 
@@ -218,7 +229,12 @@ enum
 	TG_MESH_FAST = 1u << 6,
 	/* Multi-GPU contexts: after this export, move the slab cuts of the next export of the same model and grid by the
 	 * per-device times just measured.  Without it every export runs on the cuts of the host-side estimate alone. */
-	TG_MESH_REBALANCE = 1u << 7
+	TG_MESH_REBALANCE = 1u << 7,
+	/* Mesh (or sample, tg_eval_lattice_flags) the live mesher's field instead of the export's: TG_EVAL_LIVE at every
+	 * lattice point.  On a tg_model_create_live model over tg_live_grid this is Sodapop's NaiveSurfaceNets mesh
+	 * (sodapop.cpp:562-760): its first loop only visits the cells of the octree leaves' boxes ("point cache", :624-652), and
+	 * outside of them the clamped field is +100 everywhere, so the meshes are the same (tests/test_gpu_live.py). */
+	TG_MESH_LIVE_FIELD = 1u << 8
 };
 
 typedef struct tg_mesh_options

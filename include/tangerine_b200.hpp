@@ -4,7 +4,9 @@
 // not the call sites.
 #pragma once
 
+#include <cstdint>
 #include <string>
+#include <vector>
 
 #include "tangerine_b200.h"
 
@@ -50,5 +52,22 @@ TG_API int ExportCommon(const tg_tree* Evaluator, float GridSize, int RefineIter
 
 // tangerine/magica.h:20 / magica.cpp:27-72: synchronous MagicaVoxel export.
 TG_API int VoxExport(const tg_tree* Evaluator, const std::string& Path, float GridSize, int ColorIndex);
+
+// The arrays the live mesher fills on a Drawable (tangerine/sdf_model.h:59-62), four floats per vertex as there:
+// Positions (x, y, z, 1), Normals (SDFOctree::Gradient, 1) and Colors; Indices three per triangle.
+struct LiveDrawable
+{
+	std::vector<float> Positions;
+	std::vector<float> Normals;
+	std::vector<float> Colors;
+	std::vector<uint32_t> Indices;
+};
+
+// Sodapop::Populate (tangerine/sodapop.cpp:214-225) with the NaiveSurfaceNets algorithm (:562-897), synchronous: the
+// octree of MeshingJob::Run (:240), the grid of NaiveSurfaceNetsScratch at density 20 + MeshingDensityPush (:43, 153-179,
+// 221), the clamped inexact field (:583-587), vertex and face loops, gradient normals (:816).  Vertices come in (k, j, i)
+// cell order (the reference's order depends on its thread schedule).  Colors are (0, 0, 0, 1) as the reference leaves
+// them for materials without a Chthonic evaluator (:862-870); evaluating those materials is not part of this path.
+TG_API int PopulateDrawable(const tg_tree* Evaluator, float MeshingDensityPush, LiveDrawable& Painter);
 
 } // namespace tangerine_b200

@@ -19,6 +19,7 @@
 #include <cstdint>
 #include <chrono>
 #include <map>
+#include <set>
 #include <thread>
 #include <atomic>
 #include <fstream>
@@ -437,6 +438,31 @@ static void WalkOctree(SDFOctree* Node, OctreeStats& Stats)
 // Commands
 // ------------------------------------------------------------------------------------------------
 
+
+// The octree the live mesher works on (sodapop.cpp:227-247, 562-600): SDFOctree::Create(Evaluator, .25, false, 3, 0.0),
+// then every node the depth limit left Incomplete is populated (MeshingScratch's IncompleteSearch walk :108-120 and
+// MeshingOctreeTask's `Incomplete->Populate(false, 3, -1)` :568-571).
+static SDFOctreeShared CreateLiveOctree(SDFNodeShared Tree)
+{
+	SDFOctreeShared Octree = SDFOctree::Create(Tree, .25, false, 3, 0.0);
+	if (!Octree) return Octree;
+	std::vector<SDFOctree*> Incompletes;
+	SDFOctree::CallbackType IncompleteSearch = [&](SDFOctree& Leaf)
+	{
+		if (Leaf.Incomplete) Incompletes.push_back(&Leaf);
+	};
+	Octree->Walk(IncompleteSearch);
+	for (SDFOctree* Incomplete : Incompletes) Incomplete->Populate(false, 3, -1);
+	Octree->LinkLeaves();
+	return Octree;
+}
+
+// The live mesher's implicit function (sodapop.cpp:583-587).
+static float LiveField(SDFOctree* Octree, vec3 Point)
+{
+	return glm::clamp(Octree->Eval(Point, false), -100.0f, 100.0f);
+}
+
 static int Usage()
 {
 	std::fprintf(stderr,
@@ -444,12 +470,13 @@ static int Usage()
 		"  dump-tgm  <model.lua|.tgm> <out.tgm>\n"
 		"  info      <model>                                  bounds / tree / octree statistics + hash (JSON)\n"
 		"  octree    <model> <out.bin>                        dump every octree node's pruned program\n"
-		"  eval      <model> <mode> <points.f32> <out.bin>    mode: octree | tree | interp | gradient | color | raycast | magnet (6 floats per ray)\n"
+		"  eval      <model> <mode> <points.f32> <out.bin>    mode: octree | tree | interp | gradient | color | live | live-gradient | raycast | magnet (6 floats per ray)\n"
 		"  export    <model> <cells_per_unit> <refine> <out.ply|.stl>   reference ExportCommon (as shipped)\n"
 		"  export-grid <model> <minx miny minz maxx maxy maxz> <step> <refine> <pointcloud 0|1> <out.ply|.stl>\n"
 		"  vox       <model> <grid_size> <color_index> <out.vox>\n"
 		"  bench     <model> <minx..maxz> <step> <threads> <slice_stride> reference thunks on std::threads (JSON)\n"
-		"  slices    <model> <minx..maxz> <step> <threads> <k_begin> <k_end|0> <attributes 0|1> <out.json>   per-layer digests of the reference mesh\n");
+		"  slices    <model> <minx..maxz> <step> <threads> <k_begin> <k_end|0> <attributes 0|1> <out.json>   per-layer digests of the reference mesh\n"
+		"  slices-live <model> <density> <threads> <attributes 0|1> <out.json>   the same for the live mesher (sodapop.cpp) at a meshing density\n");
 	return 1;
 }
 
@@ -517,6 +544,28 @@ static int CmdEval(SDFNodeShared Tree, const std::string& Mode, const char* Poin
 			std::fwrite(&Flag, 4, 1, Out);
 			std::fwrite(&Hit.Travel, 4, 1, Out);
 			std::fwrite(&Hit.Position, 4, 3, Out);
+		}
+		std::fclose(Out);
+		return 0;
+	}
+	if (Mode == "live" || Mode == "live-gradient")
+	{
+		SDFOctreeShared Live = CreateLiveOctree(Tree);
+		if (!Live) return 2;
+		for (size_t i = 0; i < Count; ++i)
+		{
+			vec3 Point(Points[i * 3 + 0], Points[i * 3 + 1], Points[i * 3 + 2]);
+			if (Mode == "live")
+			{
+				float Dist = LiveField(Live.get(), Point);
+				std::fwrite(&Dist, 4, 1, Out);
+			}
+			else
+			{
+				// the live mesher's normals (sodapop.cpp:816, USE_GRADIENT_NORMALS)
+				vec3 Normal = Live->Gradient(Point);
+				std::fwrite(&Normal, 4, 3, Out);
+			}
 		}
 		std::fclose(Out);
 		return 0;
@@ -819,10 +868,14 @@ static void ParallelFor(size_t Count, int ThreadCount, size_t Chunk, Fn Body)
 	for (auto& Thread : Threads) Thread.join();
 }
 
-static int CmdSlices(SDFNodeShared Tree, GridArgs Args, int ThreadCount, long K0, long K1, int Attributes, const char* OutPath)
+// LiveDensity > 0: the live mesher instead of the export (sodapop.cpp:153-179 grid from the octree bounds and the
+// meshing density, :583-587 clamped inexact field, :624-652 loop 1 over the point cache of the octree leaves).
+static int CmdSlices(SDFNodeShared Tree, GridArgs Args, int ThreadCount, long K0, long K1, int Attributes, const char* OutPath, float LiveDensity = 0.0f)
 {
+	const bool Live = LiveDensity > 0.0f;
 	auto T0 = Clock::now();
-	SDFOctreeShared Octree = SDFOctree::Create(Tree, 0.25);
+	SDFOctreeShared Octree = Live ? CreateLiveOctree(Tree) : SDFOctree::Create(Tree, 0.25);
+	if (!Octree) return 2;
 	auto T1 = Clock::now();
 
 	vec3 ModelMin = Args.Min - Args.Step * vec3(2.0);
@@ -842,8 +895,62 @@ static int CmdSlices(SDFNodeShared Tree, GridArgs Args, int ThreadCount, long K0
 	{
 		return Octree->Eval(vec3(X, Y, Z));
 	};
+	if (Live)
+	{
+		isosurface::regular_grid_t& Grid = Task.Grid;
+		const float Density = glm::floor(LiveDensity);
+		const glm::vec3 SamplesPerUnit = glm::max(Octree->Bounds.Extent() * glm::vec3(Density), glm::vec3(8.0));
+		Grid.x = Octree->Bounds.Min.x;
+		Grid.y = Octree->Bounds.Min.y;
+		Grid.z = Octree->Bounds.Min.z;
+		Grid.sx = size_t(glm::ceil(SamplesPerUnit.x));
+		Grid.sy = size_t(glm::ceil(SamplesPerUnit.y));
+		Grid.sz = size_t(glm::ceil(SamplesPerUnit.z));
+		Grid.dx = Octree->Bounds.Extent().x / static_cast<float>(Grid.sx);
+		Grid.dy = Octree->Bounds.Extent().y / static_cast<float>(Grid.sy);
+		Grid.dz = Octree->Bounds.Extent().z / static_cast<float>(Grid.sz);
+		Grid.x -= Grid.dx * 2;
+		Grid.y -= Grid.dy * 2;
+		Grid.z -= Grid.dz * 2;
+		Grid.sx += 3;
+		Grid.sy += 3;
+		Grid.sz += 3;
+		SDFOctree* Raw = Octree.get();
+		Task.ImplicitFunction = [Raw](float X, float Y, float Z) -> float
+		{
+			return LiveField(Raw, vec3(X, Y, Z));
+		};
+	}
 	Task.Setup();
 	const size_t SX = Task.Grid.sx, SY = Task.Grid.sy, SZ = Task.Grid.sz;
+	// live: the cells of the point cache (:624-652), every octree leaf's box rounded outwards, as a sorted set
+	std::vector<size_t> LiveCells;
+	if (Live)
+	{
+		std::set<size_t> Cache;
+		const size_t IndexRange = SX * SY * SZ;
+		SDFOctree::CallbackType Gather = [&](SDFOctree& LeafNode)
+		{
+			if (!LeafNode.Evaluator) return;
+			glm::vec3 Origin(Task.Grid.x, Task.Grid.y, Task.Grid.z);
+			glm::vec3 Step(Task.Grid.dx, Task.Grid.dy, Task.Grid.dz);
+			glm::vec3 AlignedMin = glm::floor(glm::max(glm::vec3(0.0), LeafNode.Bounds.Min - Origin) / Step);
+			glm::vec3 AlignedMax = glm::ceil((LeafNode.Bounds.Max - Origin) / Step);
+			for (float z = AlignedMin.z; z <= AlignedMax.z; ++z)
+			{
+				for (float y = AlignedMin.y; y <= AlignedMax.y; ++y)
+				{
+					for (float x = AlignedMin.x; x <= AlignedMax.x; ++x)
+					{
+						const size_t Index = size_t(x) + size_t(y) * SX + size_t(z) * SX * SY;
+						if (Index < IndexRange) Cache.insert(Index); // `Bin < PointCache.size()` (:645)
+					}
+				}
+			}
+		};
+		Octree->Walk(Gather);
+		LiveCells.assign(Cache.begin(), Cache.end());
+	}
 	if (K1 <= 0 || size_t(K1) > SZ) K1 = long(SZ);
 	if (K0 < 0) K0 = 0;
 	// loop 2 of layer K0 needs the vertices of layer K0 - 1
@@ -851,7 +958,16 @@ static int CmdSlices(SDFNodeShared Tree, GridArgs Args, int ThreadCount, long K0
 	const size_t Layers = size_t(K1) - First;
 
 	// Loop 1: every cell of the layers, work items are (layer, row) pairs.
-	ParallelFor(Layers * SY, ThreadCount, 1, [&](size_t Index)
+	// TG_LIVE_FULL_GRID=1 walks every cell instead (checks that nothing outside the point cache would yield a vertex)
+	if (Live && !std::getenv("TG_LIVE_FULL_GRID"))
+	{
+		ParallelFor(LiveCells.size(), ThreadCount, 64, [&](size_t c)
+		{
+			const size_t GridIndex = LiveCells[c];
+			Task.FirstLoopInnerThunk(Task, { GridIndex % SX, (GridIndex / SX) % SY, GridIndex / (SX * SY) });
+		});
+	}
+	else ParallelFor(Layers * SY, ThreadCount, 1, [&](size_t Index)
 	{
 		size_t k = First + Index / SY;
 		size_t j = Index % SY;
@@ -894,7 +1010,7 @@ static int CmdSlices(SDFNodeShared Tree, GridArgs Args, int ThreadCount, long K0
 
 	// Attribute loop of WritePLY (export.cpp:297-312), threaded; vertices in serial order.
 	const auto& Vertices = Task.OutputMesh.vertices_;
-	const bool ExportColor = Octree->Evaluator->HasPaint();
+	const bool ExportColor = !Live && Octree->Evaluator->HasPaint(); // the live mesher colours by material evaluation, not GuessColor
 	std::vector<vec3> Normals;
 	std::vector<uint8_t> Colors;
 	if (Attributes)
@@ -924,9 +1040,15 @@ static int CmdSlices(SDFNodeShared Tree, GridArgs Args, int ThreadCount, long K0
 
 	FILE* Out = std::fopen(OutPath, "w");
 	if (!Out) return 2;
-	std::fprintf(Out, "{\"grid\": [%zu, %zu, %zu], \"k_begin\": %ld, \"k_end\": %ld, \"threads\": %d, \"has_color\": %s, \"attributes\": %s,\n"
+	if (Live)
+	{
+		std::fprintf(Out, "{\"live_grid\": {\"origin_bits\": [%u, %u, %u], \"step_bits\": [%u, %u, %u], \"cache_cells\": %zu},\n",
+			CanonicalBits(Task.Grid.x), CanonicalBits(Task.Grid.y), CanonicalBits(Task.Grid.z), CanonicalBits(Task.Grid.dx), CanonicalBits(Task.Grid.dy), CanonicalBits(Task.Grid.dz),
+			LiveCells.size());
+	}
+	std::fprintf(Out, "%s\"grid\": [%zu, %zu, %zu], \"k_begin\": %ld, \"k_end\": %ld, \"threads\": %d, \"has_color\": %s, \"attributes\": %s,\n"
 		" \"octree_build_s\": %.3f, \"loop1_s\": %.3f, \"loop2_s\": %.3f, \"attributes_s\": %.3f,\n",
-		SX, SY, SZ, K0, K1, ThreadCount, ExportColor ? "true" : "false", Attributes ? "true" : "false",
+		Live ? " " : "{", SX, SY, SZ, K0, K1, ThreadCount, ExportColor ? "true" : "false", Attributes ? "true" : "false",
 		Seconds(T0, T1), Seconds(T1, T2), Seconds(T2, T3), Seconds(T3, T4));
 	// per layer: [k, vertices, triangles, sha(positions), sha(normals), sha(colours), sha(triangle indices)]
 	std::fprintf(Out, " \"digest\": \"sha256 (first 16 hex digits) over the layer's records in (k, j, i) order: positions / normals as canonical float32 bits x3 "
@@ -1056,6 +1178,13 @@ int main(int Argc, char** Argv)
 	{
 		GridArgs Grid = ParseGrid(Argv + 3);
 		return CmdSlices(Tree, Grid, std::atoi(Argv[10]), std::atol(Argv[11]), std::atol(Argv[12]), std::atoi(Argv[13]), Argv[14]);
+	}
+	else if (Command == "slices-live" && Argc == 7)
+	{
+		GridArgs Unused;
+		Unused.Min = Unused.Max = vec3(0.0f);
+		Unused.Step = vec3(1.0f);
+		return CmdSlices(Tree, Unused, std::atoi(Argv[4]), 0, 0, std::atoi(Argv[5]), Argv[6], float(std::atof(Argv[3])));
 	}
 	else if (Command == "bench" && Argc == 12)
 	{

@@ -875,6 +875,9 @@ struct TgoOctree
 	Program programs; /* all node programs, concatenated */
 	float target_size;
 	int32_t root;
+	int coalesce;   /* SDFOctree::Create's Coalesce argument (1 for the export path) */
+	int max_depth;  /* ... and MaxDepth (-1 = no limit) */
+	int live_field; /* oct_eval is the live mesher's implicit function (sodapop.cpp:583-587) */
 };
 
 static int32_t oct_alloc(TgoOctree* o)
@@ -891,7 +894,8 @@ static int32_t oct_alloc(TgoOctree* o)
 
 static void oct_populate(TgoOctree* o, int32_t self, int depth);
 
-/* SDFOctree::SDFOctree :1641-1700 (Coalesce = true, MaxDepth = -1 as used by the export path) */
+/* SDFOctree::SDFOctree :1641-1700 (the export path asks for Coalesce = true, MaxDepth = -1; the live mesher for
+ * Coalesce = false, MaxDepth = 3 and populates the incomplete nodes afterwards, see tgo_octree_create_live) */
 static int32_t oct_construct(TgoOctree* o, uint32_t in_evaluator, AABB bounds, int depth)
 {
 	int32_t self = oct_alloc(o);
@@ -909,7 +913,10 @@ static int32_t oct_construct(TgoOctree* o, uint32_t in_evaluator, AABB bounds, i
 	if (!o->nodes[self].terminus)
 	{
 		o->nodes[self].incomplete = 1;
-		oct_populate(o, self, depth);
+		if (o->coalesce || o->max_depth == -1 || depth < o->max_depth) /* :1672-1682 */
+		{
+			oct_populate(o, self, depth);
+		}
 	}
 	if (o->nodes[self].evaluator != NONE)
 	{
@@ -961,8 +968,24 @@ static void oct_populate(TgoOctree* o, int32_t self, int depth)
 	}
 	else
 	{
+		/* :1761-1767 Bounds = union of the live children's Bounds (as they are at this moment) */
+		int first = 1;
+		for (int i = 0; i < 8; ++i)
+		{
+			int32_t c = o->nodes[self].children[i];
+			if (c < 0) continue;
+			AABB cb = o->nodes[c].bounds;
+			if (first) o->nodes[self].bounds = cb;
+			else
+			{
+				AABB* b = &o->nodes[self].bounds;
+				b->min = V3(fminf(b->min.x, cb.min.x), fminf(b->min.y, cb.min.y), fminf(b->min.z, cb.min.z));
+				b->max = V3(fmaxf(b->max.x, cb.max.x), fmaxf(b->max.y, cb.max.y), fmaxf(b->max.z, cb.max.z));
+			}
+			first = 0;
+		}
 		int limit = depth > 3 ? depth : 3;
-		if ((penultimate && uniform) || o->nodes[self].evaluator_leaves <= limit)
+		if (o->coalesce && ((penultimate && uniform) || o->nodes[self].evaluator_leaves <= limit))
 		{
 			for (int i = 0; i < 8; ++i) o->nodes[self].children[i] = -1;
 			o->nodes[self].terminus = 1;
@@ -990,8 +1013,71 @@ static void arena_copy(Arena* dst, const Arena* src)
 	memcpy(dst->nodes, src->nodes, src->count * sizeof(Node));
 }
 
-/* SDFOctree::Create :1609-1638 */
+static TgoOctree* octree_create(const TgoModel* model, float target_size, int coalesce, int max_depth);
+
+/* SDFOctree::Create :1609-1638 with the export path's arguments (export.cpp:322) */
 TgoOctree* tgo_octree_create(const TgoModel* model, float target_size)
+{
+	return octree_create(model, target_size, 1, -1);
+}
+
+/* SDFOctree::Walk :1950-1966: terminus or incomplete nodes */
+static void oct_collect_incomplete(const TgoOctree* o, int32_t index, int32_t* list, size_t* count)
+{
+	const OctNode* n = &o->nodes[index];
+	if (n->terminus || n->incomplete)
+	{
+		if (n->incomplete) list[(*count)++] = index;
+		return;
+	}
+	for (int i = 0; i < 8; ++i)
+	{
+		if (n->children[i] >= 0) oct_collect_incomplete(o, n->children[i], list, count);
+	}
+}
+
+/* The live mesher's octree: MeshingJob::Run (sodapop.cpp:240) creates it with Coalesce = false, MaxDepth = 3, Margin = 0;
+ * MeshingScratch's constructor (:108-120) collects the incomplete nodes and MeshingOctreeTask (:568-571) calls
+ * Populate(false, 3, -1) on each.  oct_eval on the result is the implicit function of :583-587. */
+TgoOctree* tgo_octree_create_live(const TgoModel* model, float target_size)
+{
+	TgoOctree* o = octree_create(model, target_size, 0, 3);
+	if (!o) return NULL;
+	int32_t* list = (int32_t*)malloc(sizeof(int32_t) * (o->count + 1));
+	size_t count = 0;
+	oct_collect_incomplete(o, o->root, list, &count);
+	o->max_depth = -1;
+	for (size_t i = 0; i < count; ++i) oct_populate(o, list[i], 3);
+	free(list);
+	o->live_field = 1;
+	return o;
+}
+
+/* NaiveSurfaceNetsScratch's constructor, sodapop.cpp:153-179 */
+void tgo_live_grid(const TgoOctree* o, float meshing_density, TgoGrid* g)
+{
+	const AABB b = o->nodes[o->root].bounds;
+	const float density = floorf(meshing_density);
+	const v3 extent = sub3(b.max, b.min);
+	const v3 samples = V3(fmaxf(extent.x * density, 8.0f), fmaxf(extent.y * density, 8.0f), fmaxf(extent.z * density, 8.0f));
+	g->x = b.min.x;
+	g->y = b.min.y;
+	g->z = b.min.z;
+	g->sx = (uint64_t)ceilf(samples.x);
+	g->sy = (uint64_t)ceilf(samples.y);
+	g->sz = (uint64_t)ceilf(samples.z);
+	g->dx = extent.x / (float)g->sx;
+	g->dy = extent.y / (float)g->sy;
+	g->dz = extent.z / (float)g->sz;
+	g->x -= g->dx * 2;
+	g->y -= g->dy * 2;
+	g->z -= g->dz * 2;
+	g->sx += 3;
+	g->sy += 3;
+	g->sz += 3;
+}
+
+static TgoOctree* octree_create(const TgoModel* model, float target_size, int coalesce, int max_depth)
 {
 	if (!model->arena.nodes[model->root].finite) return NULL;
 	AABB bounds = tree_bounds(&model->arena, model->root);
@@ -1012,6 +1098,8 @@ TgoOctree* tgo_octree_create(const TgoModel* model, float target_size)
 	o->materials = (float(*)[3])malloc(sizeof(float[3]) * (model->material_count + 1));
 	memcpy(o->materials, model->materials, sizeof(float[3]) * model->material_count);
 	o->target_size = target_size;
+	o->coalesce = coalesce;
+	o->max_depth = max_depth;
 	o->root = oct_construct(o, model->root, cube, 1);
 	if (o->nodes[o->root].evaluator == NONE)
 	{
@@ -1031,21 +1119,34 @@ void tgo_octree_free(TgoOctree* o)
 	free(o);
 }
 
-/* SDFOctree::Descend(Point, Exact = true) :1801-1835 */
-static const OctNode* oct_descend(const TgoOctree* o, v3 point)
+/* SDFOctree::Descend(Point, Exact) :1801-1835, as written: a child that finds nothing (possible only in a live
+ * octree, where a node populated after its parent may have lost its evaluator) hands the search back to its parent
+ * when Exact, and ends it when not. */
+static const OctNode* oct_descend_from(const TgoOctree* o, const OctNode* node, v3 point, int exact)
 {
-	const OctNode* node = &o->nodes[o->root];
-	while (!node->terminus)
+	if (!node->terminus)
 	{
 		int i = 0;
 		if (point.x > node->pivot.x) i |= 1;
 		if (point.y > node->pivot.y) i |= 2;
 		if (point.z > node->pivot.z) i |= 4;
 		int32_t child = node->children[i];
-		if (child < 0) break; /* empty octant: this node's larger program is used */
-		node = &o->nodes[child];
+		if (child >= 0)
+		{
+			const OctNode* found = oct_descend_from(o, &o->nodes[child], point, exact);
+			if (found || !exact) return found;
+		}
+		else if (!exact)
+		{
+			return NULL; /* empty octant, and empty regions need no evaluation */
+		}
 	}
-	return node;
+	return node->evaluator != NONE ? node : NULL;
+}
+
+static const OctNode* oct_descend(const TgoOctree* o, v3 point)
+{
+	return oct_descend_from(o, &o->nodes[o->root], point, 1);
 }
 
 static uint64_t fnv(uint64_t hash, const void* data, size_t bytes)
@@ -1198,9 +1299,28 @@ static void parallel_for(uint64_t count, int threads, RangeFn fn, void* ctx)
 /* Point queries                                                                                */
 /* ------------------------------------------------------------------------------------------- */
 
-/* SDFOctree::Eval(Point, Exact = true) :1969-1989 */
+static const OctNode* oct_descend_inexact(const TgoOctree* o, v3 point)
+{
+	return oct_descend_from(o, &o->nodes[o->root], point, 0);
+}
+
+/* glm::clamp = min(max(x, lo), hi) with glm's comparisons (detail/func_common.inl) */
+static float glm_clamp(float x, float lo, float hi)
+{
+	float t = (x < lo) ? lo : x;
+	return (hi < t) ? hi : t;
+}
+
+/* SDFOctree::Eval(Point, Exact = true) :1969-1989; on a live octree the live mesher's implicit function
+ * clamp(Eval(Point, false), -100, 100) (sodapop.cpp:583-587; nothing found = +infinity, :1978-1981) */
 static float oct_eval(const TgoOctree* o, v3 p)
 {
+	if (o->live_field)
+	{
+		const OctNode* found = oct_descend_inexact(o, p);
+		float d = found ? interp_eval(o->programs.words + found->prog_offset, found->prog_count, p) : INFINITY;
+		return glm_clamp(d, -100.0f, 100.0f);
+	}
 	const OctNode* n = oct_descend(o, p);
 	return interp_eval(o->programs.words + n->prog_offset, n->prog_count, p);
 }

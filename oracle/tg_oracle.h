@@ -55,6 +55,9 @@ int tgo_model_leaf_count(const TgoModel* model);
 uint64_t tgo_model_root_program(const TgoModel* model, uint32_t* out_words, uint64_t capacity);
 
 TgoOctree* tgo_octree_create(const TgoModel* model, float target_size);
+/* The live mesher's octree (sodapop.cpp:240, 568-571: no coalescing, populated in two steps).  tgo_eval_octree,
+ * tgo_lattice_samples and tgo_surface_nets on it sample the live mesher's implicit function (sodapop.cpp:583-587). */
+TgoOctree* tgo_octree_create_live(const TgoModel* model, float target_size);
 void tgo_octree_free(TgoOctree* octree);
 void tgo_octree_stats(const TgoOctree* octree, TgoOctreeStats* out);
 
@@ -70,6 +73,9 @@ void tgo_color(const TgoOctree* octree, const float* points, uint64_t count, uin
 
 /* MeshExportThread's grid (export.cpp:324-337) from model bounds and a step. */
 void tgo_export_grid(const float model_min[3], const float model_max[3], const float step[3], TgoGrid* out);
+
+/* NaiveSurfaceNetsScratch's grid (sodapop.cpp:153-179) from a live octree's bounds and the meshing density. */
+void tgo_live_grid(const TgoOctree* octree, float meshing_density, TgoGrid* out);
 
 /* par_surface_nets restated; lattice samples are computed once and shared between cells. */
 int tgo_surface_nets(const TgoOctree* octree, const TgoGrid* grid, TgoMesh* out, int threads);

@@ -8,8 +8,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 
-EVAL_OCTREE, EVAL_INTERP, EVAL_TREE, EVAL_GRADIENT, EVAL_COLOR = range(5)
+EVAL_OCTREE, EVAL_INTERP, EVAL_TREE, EVAL_GRADIENT, EVAL_COLOR, EVAL_LIVE = range(6)
 MESH_NORMALS, MESH_COLORS, MESH_NO_CULL, MESH_DEVICE_ONLY, MESH_FACE_NORMALS, MESH_KEEP_CANCEL, MESH_FAST, MESH_REBALANCE = 1, 2, 4, 8, 16, 32, 64, 128
+MESH_LIVE_FIELD = 256
 
 
 class TangerineError(RuntimeError):
@@ -143,6 +144,8 @@ def lib():
         "tg_context_device_count": (i32, [vp]),
         "tg_mesh_rank_info": (i32, [C.POINTER(_Mesh), i32, C.POINTER(u64), C.POINTER(u64), C.POINTER(MeshTimings)]),
         "tg_model_create": (vp, [vp, vp, C.c_float, i32]),
+        "tg_model_create_live": (vp, [vp, vp, C.c_float, i32]),
+        "tg_live_grid": (i32, [vp, C.c_float, C.POINTER(Grid)]),
         "tg_tree_octree_stats": (i32, [vp, C.c_float, i32, C.POINTER(ModelStats)]),
         "tg_model_destroy": (None, [vp]),
         "tg_tree_plan_slabs": (i32, [vp, C.c_float, C.POINTER(Grid), i32, C.POINTER(u64), C.POINTER(C.c_double)]),
@@ -490,9 +493,17 @@ class Mesh:
 
 
 class Model:
-    def __init__(self, context, tree, target_size=0.25, threads=0):
+    def __init__(self, context, tree, target_size=0.25, threads=0, live=False):
+        """live=True: the live mesher's octree (tg_model_create_live) instead of the export's."""
         self.context = context
-        self.h = _handle(lib().tg_model_create(context.h, tree.h, target_size, threads))
+        create = lib().tg_model_create_live if live else lib().tg_model_create
+        self.h = _handle(create(context.h, tree.h, target_size, threads))
+
+    def live_grid(self, density=20.0):
+        """The live mesher's grid for a meshing density (sodapop.cpp:153-179); needs live=True."""
+        grid = Grid()
+        _check(lib().tg_live_grid(self.h, density, C.byref(grid)))
+        return grid
 
     def close(self):
         if getattr(self, "h", None):

@@ -467,7 +467,49 @@ int tg_context_device(const tg_context* context) try
 }
 TG_CATCH_STATUS
 
+static tg_model* CreateModel(tg_context* context, const tg_tree* tree, float target_size, int host_threads, bool live_octree);
+
 tg_model* tg_model_create(tg_context* context, const tg_tree* tree, float target_size, int host_threads) try
+{
+	return CreateModel(context, tree, target_size, host_threads, false);
+}
+TG_CATCH_NULL
+
+tg_model* tg_model_create_live(tg_context* context, const tg_tree* tree, float target_size, int host_threads) try
+{
+	return CreateModel(context, tree, target_size, host_threads, true);
+}
+TG_CATCH_NULL
+
+// NaiveSurfaceNetsScratch's constructor (sodapop.cpp:153-179), float for float.
+int tg_live_grid(const tg_model* model, float density, tg_grid* out) try
+{
+	if (!model || !out) return Fail(TG_ERR_INVALID, "null argument");
+	const FlatModel& flat = model->impl->flat;
+	if (!flat.live_octree) return Fail(TG_ERR_INVALID, "tg_live_grid needs a model made by tg_model_create_live");
+	const float floor_density = std::floor(density);
+	const Vec3 extent = flat.live_bounds.max - flat.live_bounds.min;
+	const float samples[3] = { std::fmax(extent.x * floor_density, 8.0f), std::fmax(extent.y * floor_density, 8.0f), std::fmax(extent.z * floor_density, 8.0f) };
+	out->x = flat.live_bounds.min.x;
+	out->y = flat.live_bounds.min.y;
+	out->z = flat.live_bounds.min.z;
+	out->sx = uint64_t(std::ceil(samples[0]));
+	out->sy = uint64_t(std::ceil(samples[1]));
+	out->sz = uint64_t(std::ceil(samples[2]));
+	out->dx = extent.x / float(out->sx);
+	out->dy = extent.y / float(out->sy);
+	out->dz = extent.z / float(out->sz);
+	out->x -= out->dx * 2;
+	out->y -= out->dy * 2;
+	out->z -= out->dz * 2;
+	out->sx += 3;
+	out->sy += 3;
+	out->sz += 3;
+	return TG_OK;
+}
+TG_CATCH_STATUS
+
+static tg_model* CreateModel(tg_context* context, const tg_tree* tree, float target_size, int host_threads, bool live_octree)
 {
 	if (!context || !tree || !tree->tree.Valid())
 	{
@@ -476,7 +518,7 @@ tg_model* tg_model_create(tg_context* context, const tg_tree* tree, float target
 	}
 	if (!(target_size > 0.0f)) target_size = 0.25f; // the export path's constant (export.cpp:322)
 	std::string error;
-	Model* m = Model::Create(context->impl.get(), tree->tree, target_size, host_threads, error);
+	Model* m = Model::Create(context->impl.get(), tree->tree, target_size, host_threads, error, live_octree);
 	if (!m)
 	{
 		Fail(error.find("deeper") != std::string::npos ? TG_ERR_UNSUPPORTED : TG_ERR_INVALID, error);
@@ -497,7 +539,6 @@ tg_model* tg_model_create(tg_context* context, const tg_tree* tree, float target
 	}
 	return h.release();
 }
-TG_CATCH_NULL
 
 void tg_model_destroy(tg_model* model) try
 {
@@ -569,7 +610,7 @@ int tg_model_get_stats(const tg_model* model, tg_model_stats* out) try
 		// tg_model_create skips the reference-format diagnostics (word counts, octree hash); they are computed here, once
 		FlatModel again;
 		std::string error;
-		if (!BuildFlatModel(*model->impl->source, model->impl->source_target_size, 0, again, error)) return Fail(TG_ERR_INVALID, error);
+		if (!BuildFlatModel(*model->impl->source, model->impl->source_target_size, 0, again, error, true, !model->impl->flat.live_octree)) return Fail(TG_ERR_INVALID, error);
 		stats.ref_words = again.stats.ref_words;
 		stats.ref_leaf_words = again.stats.ref_leaf_words;
 		stats.ref_max_words = again.stats.ref_max_words;

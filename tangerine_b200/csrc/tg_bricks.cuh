@@ -62,6 +62,7 @@ struct MeshParams
 	unsigned long long* counters;
 	volatile uint32_t* progress; // page-locked host word, may be null
 	uint32_t progress_base;
+	uint32_t live;               // TG_MESH_LIVE_FIELD: the live mesher's field (inexact descent, clamp +-100)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -112,8 +113,11 @@ __device__ __forceinline__ int SplitIndex(float origin, float step, uint32_t bas
 // grids (leaves smaller than a brick) just take more rounds.  Resolved pairs are sorted by node, their samples are
 // written to `order`, and every distinct node gets ONE run of interpreter dispatches over all its samples,
 // kLaneSamples per lane -- the only instantiation of the interpreter in the kernel (instruction-cache footprint).
+// live: the field of the live mesher (sodapop.cpp:583-587) -- a box that ends in an empty octant is not evaluated with
+// the parent's program (Exact = false, sdf_evaluator.cpp:1828-1834) but holds +infinity, and every value is clamped
+// to +-100.
 __device__ __forceinline__ void EvaluateTile(WarpTile& w, const DeviceModel& model, const DeviceGrid& grid,
-	uint32_t i0, uint32_t j0, uint32_t k0, int ni, int nj, int nk, int kmin, unsigned long long* counters)
+	uint32_t i0, uint32_t j0, uint32_t k0, int ni, int nj, int nk, int kmin, unsigned long long* counters, bool live = false)
 {
 	const int lane = threadIdx.x & 31;
 	const unsigned lanes_below = (1u << lane) - 1u;
@@ -164,7 +168,7 @@ __device__ __forceinline__ void EvaluateTile(WarpTile& w, const DeviceModel& mod
 			if (lane == 31) w.fin_start[fin] = incl; // the batch total closes the last run
 			const uint32_t before = __shfl_up_sync(0xFFFFFFFFu, node_e, 1);
 			unsigned heads = __ballot_sync(0xFFFFFFFFu, lane < fin && (lane == 0 || before != node_e));
-			const uint32_t flops = size_e ? size_e * __ldg(&model.nodes[node_e].flops) : 0u;
+			const uint32_t flops = (size_e && node_e != kLiveEmpty) ? size_e * __ldg(&model.nodes[node_e].flops) : 0u;
 			const uint32_t flops_total = __reduce_add_sync(0xFFFFFFFFu, flops);
 			if (lane == 31)
 			{
@@ -196,6 +200,15 @@ __device__ __forceinline__ void EvaluateTile(WarpTile& w, const DeviceModel& mod
 				heads &= heads - 1u;
 				const int first = int(w.fin_start[g]);
 				const int total = int(w.fin_start[heads ? __ffs(heads) - 1 : fin]) - first;
+				if (w.fin_node[g] == kLiveEmpty)
+				{
+					for (int u = lane; u < total; u += 32)
+					{
+						const uint32_t code = w.order[first + u];
+						w.tile[((code >> 8) * kTile + ((code >> 4) & 15u)) * kTile + (code & 15u)] = 100.0f;
+					}
+					continue;
+				}
 				const uint4* program = model.interp + (__ldg(&model.nodes[w.fin_node[g]].interp_offset) >> 2);
 				for (int done = 0; done < total; done += 32 * kLaneSamples)
 				{
@@ -220,7 +233,7 @@ __device__ __forceinline__ void EvaluateTile(WarpTile& w, const DeviceModel& mod
 #pragma unroll
 					for (int q = 0; q < kLaneSamples; ++q)
 					{
-						if (sample[q] >= 0) w.tile[sample[q]] = d[q];
+						if (sample[q] >= 0) w.tile[sample[q]] = live ? LiveClamp(d[q]) : d[q];
 					}
 				}
 			}
@@ -245,7 +258,7 @@ __device__ __forceinline__ void EvaluateTile(WarpTile& w, const DeviceModel& mod
 		{
 			if (node & kResolvedBit)
 			{
-				node &= ~kResolvedBit; // an empty octant met by a split: Descend stops at the parent (:1828-1834)
+				node = live ? kLiveEmpty : node & ~kResolvedBit; // an empty octant met by a split: Descend stops at the parent (:1828-1834)
 				resolved = true;
 			}
 			else
@@ -275,6 +288,7 @@ __device__ __forceinline__ void EvaluateTile(WarpTile& w, const DeviceModel& mod
 					const int32_t child = __ldg(&model.nodes[node].children[olo]);
 					if (child < 0)
 					{
+						if (live) node = kLiveEmpty;
 						resolved = true;
 						break;
 					}
@@ -377,7 +391,7 @@ __global__ void __launch_bounds__(kBrickThreads, TG_BRICK_MIN_BLOCKS) MeshBricks
 		const int nk = int(min(uint32_t(kTile), p.k_own_end + 1 - k0));
 		const int kmin = p.k_base > k0 ? int(p.k_base - k0) : 0;
 
-		EvaluateTile(w, p.model, grid, i0, j0, k0, ni, nj, nk, kmin, p.counters);
+		EvaluateTile(w, p.model, grid, i0, j0, k0, ni, nj, nk, kmin, p.counters, p.live != 0u);
 
 		// Classification: sign bits of FirstLoopInnerThunk (surface_nets.cpp:864-907).  is_scalar_positive is
 		// `scalar >= isovalue` (:733-735: -0.0 is positive, NaN is negative), and a cell is active when its eight corners
@@ -487,7 +501,7 @@ __global__ void __launch_bounds__(kBrickThreads, TG_BRICK_MIN_BLOCKS) MeshBricks
 
 // Dense lattice dump: one 8^3 tile of samples per warp, written to a (sz+1, sy+1, sx+1) array.
 __global__ void __launch_bounds__(kBrickThreads) LatticeKernel(const DeviceModel model, const DeviceGrid grid, float* __restrict__ out,
-	uint32_t tiles_x, uint32_t tiles_y, uint32_t tile_count, unsigned long long* counters)
+	uint32_t tiles_x, uint32_t tiles_y, uint32_t tile_count, unsigned long long* counters, uint32_t live)
 {
 	__shared__ WarpTile tiles[kBrickWarps];
 	WarpTile& w = tiles[threadIdx.x >> 5];
@@ -498,7 +512,7 @@ __global__ void __launch_bounds__(kBrickThreads) LatticeKernel(const DeviceModel
 	const uint32_t i0 = tx * kBrick, j0 = ty * kBrick, k0 = tz * kBrick;
 	const uint32_t nx = grid.sx + 1, ny = grid.sy + 1, nz = grid.sz + 1;
 	const int ni = int(min(uint32_t(kBrick), nx - i0)), nj = int(min(uint32_t(kBrick), ny - j0)), nk = int(min(uint32_t(kBrick), nz - k0));
-	EvaluateTile(w, model, grid, i0, j0, k0, ni, nj, nk, 0, counters);
+	EvaluateTile(w, model, grid, i0, j0, k0, ni, nj, nk, 0, counters, live != 0u);
 	if (out == nullptr) return;
 	for (int s = lane; s < kBrick * kBrick * kBrick; s += 32)
 	{

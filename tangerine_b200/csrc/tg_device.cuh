@@ -94,6 +94,37 @@ __device__ __forceinline__ float4 AsFloat4(const uint4& v)
 // switch sits outside the per-sample loops, so with a warp-uniform program there is one dispatch per brush.
 // DEFER: square roots take the branch-free fast path (sdf::SqrtDeferred) and *seen (sdf::SqrtRange) records whether an argument fell
 // outside its range -- the caller then evaluates again without DEFER.
+// SDFOctree::Descend(Point, Exact = false) (sdf_evaluator.cpp:1801-1835): an empty octant ends the search with nothing
+// found -- kLiveEmpty -- instead of falling back on the parent's program.
+constexpr uint32_t kLiveEmpty = 0x7FFFFFFEu;
+__device__ __forceinline__ uint32_t DescendLive(const FlatNode* __restrict__ nodes, float px, float py, float pz)
+{
+	uint32_t n = 0;
+	for (;;)
+	{
+		const float4* q = reinterpret_cast<const float4*>(&nodes[n]);
+		const float4 head = __ldg(q);
+		const int4 lo = __ldg(reinterpret_cast<const int4*>(q + 1));
+		const int4 hi = __ldg(reinterpret_cast<const int4*>(q + 2));
+		if (__float_as_uint(head.w) != 0u) return n;
+		const int4 zsel = pz > head.z ? hi : lo;
+		const int c0 = py > head.y ? zsel.z : zsel.x;
+		const int c1 = py > head.y ? zsel.w : zsel.y;
+		const int32_t child = px > head.x ? c1 : c0;
+		if (child < 0) return kLiveEmpty;
+		n = uint32_t(child);
+	}
+}
+
+// glm::clamp(x, -100.0f, 100.0f) = min(max(x, lo), hi) with glm's comparisons (func_common.inl): NaN passes through.
+// The live mesher's implicit function wraps SDFOctree::Eval(Point, false) in it (sodapop.cpp:583-587); nothing found is
+// +infinity there (sdf_evaluator.cpp:1978-1981), i.e. 100 after the clamp.
+__device__ __forceinline__ float LiveClamp(float x)
+{
+	const float t = (x < -100.0f) ? -100.0f : x;
+	return (100.0f < t) ? 100.0f : t;
+}
+
 template <bool DEFER> struct SqrtPolicy
 {
 	using type = sdf::SqrtExact;

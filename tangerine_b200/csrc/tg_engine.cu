@@ -36,7 +36,7 @@ namespace tg
 
 // tg_fast.cu: the brick and lattice kernels of the opt-in fast build
 int LaunchMeshBricksFast(const void* mesh_params, unsigned blocks, void* stream);
-int LaunchLatticeFast(const void* device_model, const void* device_grid, float* out, unsigned tiles_x, unsigned tiles_y, unsigned tile_count, unsigned long long* counters, void* stream);
+int LaunchLatticeFast(const void* device_model, const void* device_grid, float* out, unsigned tiles_x, unsigned tiles_y, unsigned tile_count, unsigned long long* counters, unsigned live, void* stream);
 int FastBrickBlocksPerSm();
 
 #define TG_CUDA(call)                                                                                           \
@@ -1423,6 +1423,11 @@ __global__ void __launch_bounds__(128) EvalPointsKernel(const DeviceModel model,
 		const uint32_t node = Descend(model.nodes, 0, x, y, z);
 		static_cast<float*>(out)[i] = EvalInterp1(model, __ldg(&model.nodes[node].interp_offset), x, y, z);
 	}
+	else if (mode == TG_EVAL_LIVE)
+	{
+		const uint32_t node = DescendLive(model.nodes, x, y, z);
+		static_cast<float*>(out)[i] = node == kLiveEmpty ? 100.0f : LiveClamp(EvalInterp1(model, __ldg(&model.nodes[node].interp_offset), x, y, z));
+	}
 	else if (mode == TG_EVAL_INTERP)
 	{
 		static_cast<float*>(out)[i] = EvalInterp1(model, model.root_interp_offset, x, y, z);
@@ -1987,11 +1992,11 @@ static int ProfileLeaves(Model* m, std::string& error)
 	return TG_OK;
 }
 
-Model* Model::Create(Context* context, const Tree& tree, float target_size, int threads, std::string& error)
+Model* Model::Create(Context* context, const Tree& tree, float target_size, int threads, std::string& error, bool live_octree)
 {
 	Model* m = new Model();
 	m->context = context;
-	if (!BuildFlatModel(tree, target_size, threads, m->flat, error, false)) // reference statistics on demand (tg_model_get_stats)
+	if (!BuildFlatModel(tree, target_size, threads, m->flat, error, false, !live_octree)) // reference statistics on demand (tg_model_get_stats)
 	{
 		delete m;
 		return nullptr;
@@ -2758,6 +2763,7 @@ static int EnqueueMesh(MeshJob& job, Model* model, const tg_grid& grid_in, const
 	mp.tmp_capacity = cap_v;
 	mp.progress = ctx->progress_words;
 	mp.progress_base = ctx->progress_base;
+	mp.live = (options.flags & TG_MESH_LIVE_FIELD) ? 1u : 0u;
 	// persistent warps: the grid fills every SM; warps beyond the list length leave at their first fetch
 	if (options.flags & TG_MESH_FAST)
 	{
@@ -3550,12 +3556,13 @@ int EngineEvalLattice(Model* model, const tg_grid& grid_in, uint32_t flags, floa
 	StageTimer timer(stream);
 	const int t0 = timer.Mark();
 	const uint32_t tile_count = tx * ty * tz;
+	const uint32_t live = (flags & TG_MESH_LIVE_FIELD) ? 1u : 0u;
 	if (flags & TG_MESH_FAST)
 	{
 		const DeviceModel dm = MakeDeviceModel(model);
-		TG_CUDA(cudaError_t(LaunchLatticeFast(&dm, &grid, d_out, tx, ty, tile_count, counters, stream)));
+		TG_CUDA(cudaError_t(LaunchLatticeFast(&dm, &grid, d_out, tx, ty, tile_count, counters, live, stream)));
 	}
-	else LatticeKernel<<<(tile_count + kBrickWarps - 1) / kBrickWarps, kBrickThreads, 0, stream>>>(MakeDeviceModel(model), grid, d_out, tx, ty, tile_count, counters);
+	else LatticeKernel<<<(tile_count + kBrickWarps - 1) / kBrickWarps, kBrickThreads, 0, stream>>>(MakeDeviceModel(model), grid, d_out, tx, ty, tile_count, counters, live);
 	const int t1 = timer.Mark();
 	TG_CUDA(cudaGetLastError());
 	if (out) TG_CUDA(cudaMemcpyAsync(out, d_out, total * 4, cudaMemcpyDeviceToHost, stream));
@@ -3612,7 +3619,7 @@ int EngineCheckLongPrograms(Model* model, float reach, uint64_t out[3], std::str
 
 int EngineEvalPoints(Model* model, int mode, const float* points, uint64_t count, void* out, std::string& error)
 {
-	if (mode < TG_EVAL_OCTREE || mode > TG_EVAL_COLOR)
+	if (mode < TG_EVAL_OCTREE || mode > TG_EVAL_LIVE)
 	{
 		error = "unknown evaluation mode";
 		return TG_ERR_INVALID;

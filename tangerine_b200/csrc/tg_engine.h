@@ -108,7 +108,7 @@ public:
 
 	Model() : flat_owner(std::make_shared<FlatModel>()), flat(*flat_owner) {}
 	explicit Model(const std::shared_ptr<FlatModel>& shared) : flat_owner(shared), flat(*flat_owner) {}
-	static Model* Create(Context* context, const Tree& tree, float target_size, int threads, std::string& error);
+	static Model* Create(Context* context, const Tree& tree, float target_size, int threads, std::string& error, bool live_octree = false);
 	// The same tables on another device of a DeviceGroup (no second octree build).
 	static Model* CreateReplica(Context* context, Model* primary, std::string& error);
 	~Model();

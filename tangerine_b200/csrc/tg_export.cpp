@@ -175,6 +175,59 @@ int ExportCommon(const tg_tree* Evaluator, float GridSize, int RefineIterations,
 	return rc;
 }
 
+int PopulateDrawable(const tg_tree* Evaluator, float MeshingDensityPush, LiveDrawable& Painter)
+{
+	Painter = LiveDrawable();
+	tg_context* context = tg_context_create(g_device.load());
+	if (!context) return TG_ERR_NO_DEVICE;
+	int rc = TG_ERR_INVALID;
+	tg_model* model = tg_model_create_live(context, Evaluator, 0.25f, 0); // SDFOctree::Create(Evaluator, .25, false, 3, Margin = 0), sodapop.cpp:240
+	if (model)
+	{
+		tg_grid grid;
+		rc = tg_live_grid(model, 20.0f + MeshingDensityPush, &grid); // DefaultMeshingDensity + MeshingDensityPush, sodapop.cpp:43, 221
+		tg_mesh mesh;
+		std::memset(&mesh, 0, sizeof(mesh));
+		if (rc == TG_OK)
+		{
+			tg_mesh_options options;
+			std::memset(&options, 0, sizeof(options));
+			options.flags = TG_MESH_NORMALS | TG_MESH_LIVE_FIELD;
+			rc = tg_export_mesh(model, &grid, &options, &mesh);
+		}
+		if (rc == TG_OK)
+		{
+			try
+			{
+				const size_t vertices = size_t(mesh.vertex_count);
+				Painter.Positions.resize(vertices * 4);
+				Painter.Normals.resize(vertices * 4);
+				Painter.Colors.assign(vertices * 4, 0.0f);
+				for (size_t v = 0; v < vertices; ++v)
+				{
+					for (int a = 0; a < 3; ++a)
+					{
+						Painter.Positions[v * 4 + a] = mesh.positions[v * 3 + a];
+						Painter.Normals[v * 4 + a] = mesh.normals[v * 3 + a];
+					}
+					Painter.Positions[v * 4 + 3] = 1.0f;
+					Painter.Normals[v * 4 + 3] = 1.0f;
+					Painter.Colors[v * 4 + 3] = 1.0f;
+				}
+				Painter.Indices.assign(mesh.triangles, mesh.triangles + size_t(mesh.triangle_count) * 3);
+			}
+			catch (...)
+			{
+				rc = TG_ERR_MEMORY;
+			}
+		}
+		tg_mesh_free(&mesh);
+		tg_model_destroy(model);
+	}
+	tg_context_destroy(context);
+	return rc;
+}
+
 int VoxExport(const tg_tree* Evaluator, const std::string& Path, float GridSize, int ColorIndex)
 {
 	return tg_export_magica_voxel(Evaluator, GridSize, ColorIndex, Path.c_str(), g_device.load());

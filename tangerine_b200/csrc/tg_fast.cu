@@ -20,10 +20,10 @@ int LaunchMeshBricksFast(const void* mesh_params, unsigned blocks, void* stream)
 	return int(cudaGetLastError());
 }
 
-int LaunchLatticeFast(const void* device_model, const void* device_grid, float* out, unsigned tiles_x, unsigned tiles_y, unsigned tile_count, unsigned long long* counters, void* stream)
+int LaunchLatticeFast(const void* device_model, const void* device_grid, float* out, unsigned tiles_x, unsigned tiles_y, unsigned tile_count, unsigned long long* counters, unsigned live, void* stream)
 {
 	tg_fast::LatticeKernel<<<(tile_count + tg_fast::kBrickWarps - 1) / tg_fast::kBrickWarps, tg_fast::kBrickThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-		*static_cast<const tg_fast::DeviceModel*>(device_model), *static_cast<const tg_fast::DeviceGrid*>(device_grid), out, tiles_x, tiles_y, tile_count, counters);
+		*static_cast<const tg_fast::DeviceModel*>(device_model), *static_cast<const tg_fast::DeviceGrid*>(device_grid), out, tiles_x, tiles_y, tile_count, counters, live);
 	return int(cudaGetLastError());
 }
 

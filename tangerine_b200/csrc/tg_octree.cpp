@@ -126,6 +126,13 @@ struct Builder
 	float target_size;
 	TaskPool* tasks = nullptr; // null: build serially
 	std::atomic<bool> failed{ false };
+	// false: the live mesher's octree (no coalescing).  Its root Bounds are the union of the boxes of the nodes that were
+	// live when SDFOctree::Create stopped at MaxDepth = 3 (:1669-1684, :1763-1768: a parent sums up its children's Bounds
+	// when IT is populated; the nodes of depth 3 are populated later and no longer reach their parents).
+	bool coalesce = true;
+	std::mutex live_lock;
+	Box3 live_box;
+	bool live_any = false;
 	// A node hands its eight octants to the task pool when its pruned tree still has this many brushes (below that a
 	// task's bookkeeping costs more than the octant) and it is not too deep.
 	static constexpr int kSpawnLeaves = 12;
@@ -150,6 +157,17 @@ struct Builder
 			n.evaluator = evaluator;
 			n.evaluator_leaves = evaluator != kNoNode ? st.pool.nodes[evaluator].leaf_count : 0;
 			n.terminus = span <= target_size || evaluator == kNoNode;
+			if (!coalesce && evaluator != kNoNode && (depth == 3 || (depth < 3 && n.terminus)))
+			{
+				std::lock_guard<std::mutex> guard(live_lock);
+				if (!live_any) live_box = bounds;
+				else
+				{
+					live_box.min = Vec3(std::fmin(live_box.min.x, bounds.min.x), std::fmin(live_box.min.y, bounds.min.y), std::fmin(live_box.min.z, bounds.min.z));
+					live_box.max = Vec3(std::fmax(live_box.max.x, bounds.max.x), std::fmax(live_box.max.y, bounds.max.y), std::fmax(live_box.max.z, bounds.max.z));
+				}
+				live_any = true;
+			}
 		}
 		if (!st.nodes[self].terminus)
 		{
@@ -253,7 +271,7 @@ struct Builder
 			n.evaluator = kNoNode; // :1753-1759
 			n.terminus = true;
 		}
-		else if ((penultimate && uniform) || n.evaluator_leaves <= (depth > 3 ? depth : 3)) // :1769
+		else if (coalesce && ((penultimate && uniform) || n.evaluator_leaves <= (depth > 3 ? depth : 3))) // :1769
 		{
 			for (int i = 0; i < 8; ++i)
 			{
@@ -704,7 +722,7 @@ struct Flattener
 
 } // namespace
 
-bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel& out, std::string& error, bool reference_stats)
+bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel& out, std::string& error, bool reference_stats, bool coalesce)
 {
 	const auto t0 = std::chrono::steady_clock::now();
 	out = FlatModel();
@@ -752,6 +770,7 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 	}
 	Builder builder;
 	builder.target_size = target_size;
+	builder.coalesce = coalesce;
 	// One pool of workers per process, kept between builds: fresh threads start with cold allocator arenas and
 	// unmapped stacks, which cost a first build more than the build itself.
 	TaskPool* tasks = nullptr;
@@ -785,6 +804,9 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 		error = "octree pruned the whole model away";
 		return false;
 	}
+
+	out.live_octree = !coalesce;
+	out.live_bounds = builder.live_any ? builder.live_box : cube;
 
 	const double construct_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 	if (std::getenv("TG_TRACE_HOST")) std::fprintf(stderr, "octree build: construct %.1f ms (threads %d)\n", construct_seconds * 1e3, threads);

@@ -51,6 +51,8 @@ struct FlatModel
 	uint32_t root_interp_offset = 0;  // kStreamInterp program of the unpruned model
 	uint32_t root_flops = 0;
 	Box3 bounds;                      // Evaluator->Bounds()
+	bool live_octree = false;         // built with coalesce = false
+	Box3 live_bounds;                 // live_octree: SDFOctree::Bounds of the root (the live mesher's grid comes from it, sodapop.cpp:153-179)
 	bool has_paint = false;           // Octree->Evaluator->HasPaint() (export.cpp:285)
 	FlatModelStats stats;
 };
@@ -59,6 +61,9 @@ struct FlatModel
 // deeper than the device stack supports.  threads <= 0 picks std::thread::hardware_concurrency().
 // reference_stats: also compile every node program into the reference's word encoding for FlatModelStats::ref_* and
 // ::hash (diagnostics that pin the octree against the reference's; the device tables do not depend on them).
-bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel& out, std::string& error, bool reference_stats = true);
+// coalesce = false builds the live mesher's octree instead of the export's (SDFOctree::Create(Evaluator, .25, false, 3, 0.0)
+// followed by Populate(false, 3, -1) of every node the depth limit left incomplete, sodapop.cpp:240, 568-571): no node is
+// coalesced, and FlatModel::live_bounds is the root's Bounds as that two-step construction leaves them.
+bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel& out, std::string& error, bool reference_stats = true, bool coalesce = true);
 
 } // namespace tg

@@ -105,6 +105,23 @@ int main(int argc, char** argv)
 		if (!FileExists(out)) return Fail("no output file after the second export");
 		std::printf("OK cancel\n");
 	}
+	else if (mode == "live")
+	{
+		// Sodapop::Populate's result on a Drawable (sodapop.cpp:214-225, sdf_model.h:59-62) at the default density
+		LiveDrawable painter;
+		const int rc = PopulateDrawable(tree, 0.0f, painter);
+		if (rc != TG_OK) return Fail("PopulateDrawable failed");
+		if (painter.Positions.size() != painter.Normals.size() || painter.Positions.size() != painter.Colors.size()) return Fail("attribute arrays differ in length");
+		uint64_t hash = 0xCBF29CE484222325ull; // FNV-1a over the xyz bits of every position, in order
+		for (size_t v = 0; v < painter.Positions.size() / 4; ++v)
+		{
+			if (painter.Positions[v * 4 + 3] != 1.0f || painter.Normals[v * 4 + 3] != 1.0f || painter.Colors[v * 4 + 3] != 1.0f) return Fail("w components");
+			const unsigned char* bytes = reinterpret_cast<const unsigned char*>(&painter.Positions[v * 4]);
+			for (int b = 0; b < 12; ++b) hash = (hash ^ bytes[b]) * 0x100000001B3ull;
+		}
+		std::printf("live vertices %zu triangles %zu fnv %016llx\n", painter.Positions.size() / 4, painter.Indices.size() / 3, (unsigned long long)hash);
+		std::printf("OK live\n");
+	}
 	tg_tree_free(tree);
 	return 0;
 }

@@ -65,6 +65,10 @@ def lib():
         L.tgo_model_root_program.argtypes = [vp, C.POINTER(C.c_uint32), C.c_uint64]
         L.tgo_octree_create.restype = vp
         L.tgo_octree_create.argtypes = [vp, C.c_float]
+        L.tgo_octree_create_live.restype = vp
+        L.tgo_octree_create_live.argtypes = [vp, C.c_float]
+        L.tgo_live_grid.argtypes = [vp, C.c_float, C.POINTER(Grid)]
+        L.tgo_live_grid.restype = None
         L.tgo_octree_free.argtypes = [vp]
         L.tgo_octree_stats.argtypes = [vp, C.POINTER(_Stats)]
         L.tgo_eval_octree.argtypes = [vp, fp, C.c_uint64, fp, C.c_int]
@@ -160,11 +164,18 @@ class Model:
 
 
 class Octree:
-    def __init__(self, model, target_size=0.25):
+    def __init__(self, model, target_size=0.25, live=False):
+        """live=True: the live mesher's octree (sodapop.cpp:240, 568-571); eval / lattice / surface_nets then sample its
+        clamped inexact field (sodapop.cpp:583-587)."""
         self.model = model
-        self.h = lib().tgo_octree_create(model.h, target_size)
+        self.h = (lib().tgo_octree_create_live if live else lib().tgo_octree_create)(model.h, target_size)
         if not self.h:
             raise ValueError("octree could not be built")
+
+    def live_grid(self, density=20.0):
+        g = Grid()
+        lib().tgo_live_grid(self.h, density, C.byref(g))
+        return g
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -255,7 +266,7 @@ def ref_eval(model, mode, pts, tmpdir):
     pout = os.path.join(str(tmpdir), "out.bin")
     pts.tofile(pin)
     ref_run("eval", model, mode, pin, pout)
-    if mode == "gradient":
+    if mode in ("gradient", "live-gradient"):
         return np.fromfile(pout, np.float32).reshape(-1, 3)
     if mode == "color":
         return np.fromfile(pout, np.uint8).reshape(-1, 3)

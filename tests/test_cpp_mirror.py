@@ -47,3 +47,29 @@ def test_cancel_mid_flight(mirror, tmp_path, delay_ms):
         pytest.skip("the export finished before the cancel arrived (%d ms)" % delay_ms)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "OK cancel" in r.stdout
+
+
+@pytest.mark.gpu
+def test_populate_drawable_is_the_live_mesh(mirror, tmp_path):
+    """PopulateDrawable (the mirror of Sodapop::Populate) returns the mesh tests/test_gpu_live.py pins to the reference."""
+    import json
+    import re
+
+    import numpy as np
+    import tangerine_b200 as T
+    r = run(mirror, "live", O.model_path("basic_thing"), tmp_path / "unused.ply")
+    assert r.returncode == 0 and "OK live" in r.stdout, r.stdout + r.stderr
+    vertices, triangles, fnv = re.search(r"live vertices (\d+) triangles (\d+) fnv ([0-9a-f]+)", r.stdout).groups()
+    with open(os.path.join(ROOT, "tests", "golden", "slices_live_basic20.json")) as f:
+        fx = json.load(f)
+    assert (int(vertices), int(triangles)) == (fx["vertices"], fx["triangles"])
+    ctx = T.Context(0)
+    model = T.Model(ctx, T.Tree.load(O.model_path("basic_thing")), live=True)
+    mesh = model.export_mesh(model.live_grid(20.0), flags=T.MESH_NORMALS | T.MESH_LIVE_FIELD)
+    h = 0xCBF29CE484222325
+    for byte in np.ascontiguousarray(mesh.positions, np.float32).tobytes():
+        h = ((h ^ byte) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    assert "%016x" % h == fnv
+    mesh.close()
+    model.close()
+    ctx.close()
