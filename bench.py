@@ -509,8 +509,8 @@ def main():
         leave_ranks(waiters)
         return 0
 
-    devices = list(range(world))
-    ctx = T.Context(devices=devices) if world > 1 else T.Context(local)
+    devices = list(range(int(os.environ.get("TG_BENCH_DEVICES", world))))   # (tools: a single process driving several GPUs without torchrun)
+    ctx = T.Context(devices=devices) if len(devices) > 1 else T.Context(local)
     peaks = load_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     fp32_peak = ctx.fp32_peak_tflops()
@@ -519,7 +519,7 @@ def main():
     sampler = ClockSampler(local)
     if not os.environ.get("TG_BENCH_NO_SMI"):
         sampler.start()
-    head, ref_args = measure_workload(T, ctx, args.workload, args.steps, args.warmup, flags_extra, True, fp32_peak, hbm_peak, world)
+    head, ref_args = measure_workload(T, ctx, args.workload, args.steps, args.warmup, flags_extra, True, fp32_peak, hbm_peak, len(devices))
     clocks = sampler.stop()
 
     # DRAM traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed

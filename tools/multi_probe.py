@@ -14,7 +14,9 @@ lo, hi = tree.bounds()
 grid = T.export_grid(lo, hi, np.float32(step))
 flags = T.MESH_NORMALS | T.MESH_COLORS
 for mode in (("device", "host") if not os.environ.get("TG_PROBE_DEVICE_ONLY") else ("device",)):
-    for i in range(4):
+    iters = int(os.environ.get("TG_PROBE_ITERS", "4"))
+    walls = []
+    for i in range(iters):
         ctx.synchronize()
         t0 = time.perf_counter()
         ctx.timer_begin()
@@ -24,7 +26,10 @@ for mode in (("device", "host") if not os.environ.get("TG_PROBE_DEVICE_ONLY") el
         ms = ctx.timer_end()
         wall = (time.perf_counter() - t0) * 1e3
         ranks = m.rank_info()
-        if i == 3:
+        if i >= 3:
+            walls.append(wall)
+        if i == iters - 1:
+            print("%s: wall ms over %d exports: min %.3f median %.3f max %.3f" % (mode, len(walls), min(walls), sorted(walls)[len(walls) // 2], max(walls)))
             print("%s: V=%d F=%d  device %.3f ms  wall %.3f ms" % (mode, m.vertex_count, m.triangle_count, ms, wall))
             for r, (b, e, t) in enumerate(ranks):
                 print("  rank %d  slab [%4d, %4d)  cull %.3f eval %.3f scan %.3f faces %.3f attr %.3f  total %.3f  bricks %d  flops/sample %.0f  ns/brick %.1f" % (
