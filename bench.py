@@ -572,6 +572,33 @@ def main():
         except T.TangerineError as e:
             workloads["colorcube_vox"] = {"error": str(e)}
 
+        # the live viewport mesher (Sodapop): tree -> Drawable arrays at the default meshing density 20 and at 50
+        try:
+            tree, _ = load_workload_tree(T, "seaside_town")
+            live = {}
+            for density in (20.0, 50.0):
+                t0 = time.perf_counter()
+                model = T.Model(ctx, tree, live=True)      # the uncoalesced octree of sodapop.cpp:240, 568-571
+                build_ms = (time.perf_counter() - t0) * 1e3
+                grid = model.live_grid(density)            # NaiveSurfaceNetsScratch, sodapop.cpp:153-179
+                mesh = model.export_mesh(grid, flags=T.MESH_NORMALS | T.MESH_LIVE_FIELD)
+                parity = check_parity("live_seaside%d" % density, mesh)
+                mesh.close()
+                ms = 0.0
+                for _ in range(3):
+                    ctx.flush_l2()
+                    ctx.timer_begin()
+                    mesh = model.export_mesh(grid, flags=T.MESH_NORMALS | T.MESH_LIVE_FIELD | T.MESH_DEVICE_ONLY)
+                    ms += ctx.timer_end() / 3
+                    v, t = mesh.vertex_count, mesh.triangle_count
+                    mesh.close()
+                live["density_%d" % density] = {"grid": list(grid.shape), "vertices": v, "triangles": t, "ms_per_step": ms, "octree_build_ms": build_ms,
+                                                "parity_equal": parity["equal"], "fixture": parity["fixture"]}
+                model.close()
+            workloads["live_seaside"] = live
+        except T.TangerineError as e:
+            workloads["live_seaside"] = {"error": str(e)}
+
     # ---- the reference's CPU path on this box's host cores, bounded sample (N = 1 only) ----
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:

@@ -2587,8 +2587,12 @@ struct MeshJob
 
 static void DefaultCapacities(uint64_t slab_cells, uint32_t& cap_v, uint32_t& cap_q)
 {
-	// surfaces occupy a few percent of the cells (9 % for the 10k-primitive scene at 512^3); quads come to about one per vertex (three at the very most)
-	const uint64_t v = std::min<uint64_t>(slab_cells, std::max<uint64_t>(slab_cells / 8, 1 << 22));
+	// A surface grows with the square of the resolution: the 10k-primitive scene has 46-50 vertices per cells^(2/3) from
+	// 256^3 to 2048^3 (seaside_town 5.6), so 64 per cells^(2/3) bounds the first guess on large grids where an eighth of
+	// the cells would be tens of GB (an overflow repeats the export with exact sizes).  Quads: about one per vertex.
+	const double side = std::cbrt(double(slab_cells));
+	const uint64_t by_area = uint64_t(64.0 * side * side);
+	const uint64_t v = std::min<uint64_t>(slab_cells, std::max<uint64_t>(std::min<uint64_t>(slab_cells / 8, by_area), 1 << 22));
 	cap_v = uint32_t(std::min<uint64_t>(v, 0xFFFFFFF0ull));
 	cap_q = uint32_t(std::min<uint64_t>(std::min<uint64_t>(v * 3, std::max<uint64_t>(v + v / 2, 1 << 20)), 0x2AAAAAA0ull));
 	if (const char* env = std::getenv("TG_TEST_CAPACITY")) // tests: force the overflow-and-repeat path
