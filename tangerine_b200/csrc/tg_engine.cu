@@ -2045,8 +2045,16 @@ void EngineProgress(const std::vector<const Context*>& contexts, float out_ratio
 		const double slabs = double(std::max<uint32_t>(c->progress_slabs, 1u)) * 1024.0;
 		if (c->progress_words)
 		{
-			generation += std::min(1.0, double(c->progress_words[0]) / slabs);
-			attributes += std::min(1.0, double(c->progress_words[1]) / slabs);
+			uint32_t seen[2];
+			for (int w = 0; w < 2; ++w)
+			{
+				const uint32_t now = c->progress_words[w];
+				uint32_t before = c->progress_seen[w].load();
+				while (now > before && !c->progress_seen[w].compare_exchange_weak(before, now)) {}
+				seen[w] = std::max(now, before);
+			}
+			generation += std::min(1.0, double(seen[0]) / slabs);
+			attributes += std::min(1.0, double(seen[1]) / slabs);
 		}
 	}
 	generation /= double(contexts.size());
@@ -3140,6 +3148,11 @@ constexpr int TG_RETRY_ONE_SHOT = 1000; // internal: the pipelined export gave u
 // predecessor's arrays travel device -> host on the copy stream, straight to their final place in the host arrays
 // (vertex numbering is (k, j, i)-lexicographic, so slabs concatenate; triangle indices are made global on the device
 // by the running index base).  Same kernels and the same halo rule as the multi-GPU partition.
+// relative slab costs of the pipelined export, by slab count (see ExportMeshPipelined)
+static const double kPipelineShares3[3] = { 1.0, 1.0, 1.0 };
+static const double kPipelineShares4[4] = { 0.7, 1.3, 1.3, 0.7 };
+static const double kPipelineShares5[5] = { 1.0, 1.0, 1.0, 1.0, 1.0 };
+
 static int ExportMeshPipelined(Model* model, const tg_grid& grid_in, const tg_mesh_options& options, int chunks, tg_mesh* out, std::string& error)
 {
 	Context* ctx = model->context;
@@ -3299,6 +3312,56 @@ static int ExportMeshPipelined(Model* model, const tg_grid& grid_in, const tg_me
 		return TG_OK;
 	};
 
+	// Slab cuts, in brick layers.  The copy of slab c runs while slab c + 1 is evaluated, and nothing can be copied before
+	// the first slab is done, and the export ends one copy after the last slab: the slabs are cut by estimated COST (the
+	// multi-GPU planner's host-side estimate, tg_multi.inl), the first and the last smaller than the middle ones.
+	std::vector<uint32_t> cut(size_t(chunks) + 1, 0u);
+	{
+		for (int c = 0; c <= chunks; ++c) cut[size_t(c)] = uint32_t(uint64_t(nbz) * uint64_t(c) / uint64_t(chunks));
+		std::vector<double> shares;
+		if (const char* env = std::getenv("TG_PIPELINE_SHARES")) // tuning: comma-separated relative slab costs
+		{
+			for (const char* p = env; *p;)
+			{
+				char* end = nullptr;
+				const double v = std::strtod(p, &end);
+				if (end == p) break;
+				shares.push_back(v);
+				p = *end == ',' ? end + 1 : end;
+			}
+		}
+		else if (chunks == 3) shares = { kPipelineShares3[0], kPipelineShares3[1], kPipelineShares3[2] };
+		else if (chunks == 4) shares = { kPipelineShares4[0], kPipelineShares4[1], kPipelineShares4[2], kPipelineShares4[3] };
+		else if (chunks == 5) shares = { kPipelineShares5[0], kPipelineShares5[1], kPipelineShares5[2], kPipelineShares5[3], kPipelineShares5[4] };
+		if (shares.size() != size_t(chunks)) shares.assign(size_t(chunks), 1.0);
+		auto& plan = model->pipeline_plan;
+		if (!plan.valid || std::memcmp(&plan.grid, &grid_in, sizeof(tg_grid)) != 0)
+		{
+			plan.layer_cost = EstimateLayerCost(model->flat, grid_in);
+			plan.grid = grid_in;
+			plan.valid = true;
+		}
+		std::vector<double> cumulative(size_t(nbz) + 1, 0.0);
+		for (uint32_t b = 0; b < nbz; ++b)
+		{
+			double sum = 0.0;
+			for (uint32_t k = b * kBrick; k < std::min<uint32_t>((b + 1) * kBrick, grid.sz) && k < plan.layer_cost.size(); ++k) sum += plan.layer_cost[k];
+			cumulative[size_t(b) + 1] = cumulative[b] + sum;
+		}
+		double share_total = 0.0;
+		for (double v : shares) share_total += v;
+		if (cumulative[nbz] > 0.0 && share_total > 0.0)
+		{
+			double wanted = 0.0;
+			for (int c = 1; c < chunks; ++c)
+			{
+				wanted += shares[size_t(c) - 1] / share_total * cumulative[nbz];
+				uint32_t b = cut[size_t(c) - 1] + 1;
+				while (b < nbz && cumulative[b] < wanted) ++b;
+				cut[size_t(c)] = std::min<uint32_t>(b, nbz - uint32_t(chunks - c)); // every later slab keeps at least one brick layer
+			}
+		}
+	}
 	ctx->progress_total[0] = uint64_t(chunks);
 	ctx->progress_slabs = uint32_t(chunks);
 	// One compute lane by default.  Two lanes (even / odd slabs on two streams with their own scratch arenas, so that a
@@ -3312,8 +3375,8 @@ static int ExportMeshPipelined(Model* model, const tg_grid& grid_in, const tg_me
 		if (ctx->Cancelled()) return abandon(TG_ERR_CANCELLED);
 		tg_mesh_options slab = options;
 		slab.flags |= TG_MESH_DEVICE_ONLY;
-		slab.slab_begin = uint64_t(nbz) * uint64_t(c) / uint64_t(chunks) * kBrick;
-		slab.slab_end = c + 1 == chunks ? grid.sz : uint64_t(nbz) * uint64_t(c + 1) / uint64_t(chunks) * kBrick;
+		slab.slab_begin = uint64_t(cut[size_t(c)]) * kBrick;
+		slab.slab_end = c + 1 == chunks ? grid.sz : uint64_t(cut[size_t(c) + 1]) * kBrick;
 		jobs.emplace_back(new MeshJob());
 		ctx->progress_base = uint32_t(c) * 1024u;
 		int rc = EnqueueMesh(*jobs.back(), model, grid_in, slab, 0, 0, index_base, error, lanes > 1 ? (c & 1) : 0, c > 0 ? jobs[size_t(c) - 1]->faces_ready : nullptr, &shared_cull);
@@ -3406,10 +3469,11 @@ static int PipelineChunks(const tg_grid& g, const tg_mesh_options& options)
 	// worth it once the result is tens of megabytes: below that the copies are short next to the launch overheads
 	const double cells = double(g.sx) * double(g.sy) * double(g.sz);
 	if (cells < double(1 << 24) || g.sz < 128) return 1;
-	// measured on seaside_town 1024^3 (profiles/r1j_e2e_pipeline_probe.txt), export call only: 2 slabs 7.7 ms, 3: 7.1,
-	// 4: 7.2, 5: 7.1, 6: 7.4, 8: 7.7 (one slab, no overlap: about 10) -- every slab adds the tail of three persistent kernels and a dozen small
-	// launches (about 0.35 ms), so few slabs win
-	return 3;
+	// measured on seaside_town 1024^3 (profiles/r2_pipeline_probe.txt), upload + export: one slab 9.3 ms, 2 equal-cost slabs
+	// 8.1, 3: 7.7, 4: 7.5, 5: 7.7 -- every slab adds the tail of three persistent kernels and a dozen small launches, and
+	// the kernels run slower while a copy is in flight, so the chain of kernels (3.9 ms alone) grows to 5.6 ms at four slabs
+	// and the export ends one last-slab copy after it: few slabs, the first and the last smaller (kPipelineShares4)
+	return 4;
 }
 
 int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options& options, tg_mesh* out, std::string& error)
@@ -3423,6 +3487,7 @@ int EngineExportMesh(Model* model, const tg_grid& grid_in, const tg_mesh_options
 	ctx->progress_base = 0;
 	ctx->progress_slabs = 1;
 	if (ctx->progress_words) ctx->progress_words[0] = ctx->progress_words[1] = 0u;
+	ctx->progress_seen[0] = ctx->progress_seen[1] = 0u;
 	if (ctx->Cancelled()) return TG_ERR_CANCELLED;
 	int rc = TG_RETRY_ONE_SHOT;
 	const int chunks = PipelineChunks(grid_in, options);

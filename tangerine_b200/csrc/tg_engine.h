@@ -62,6 +62,8 @@ public:
 	volatile uint32_t* progress_words = nullptr;
 	uint32_t progress_base = 0;   // 1024 x index of the slab being enqueued
 	uint32_t progress_slabs = 1;  // slabs of the export in flight
+	// largest word values a poll has seen: persistent warps finish their items out of order, so the words themselves can step back
+	mutable std::atomic<uint32_t> progress_seen[2] = { { 0u }, { 0u } };
 
 	static Context* Create(int device, std::string& error);
 	~Context();
@@ -103,6 +105,8 @@ public:
 	int leaf_count = 0;
 	// slab cuts of the last multi-GPU export (the estimate walks every terminus cell: milliseconds, so it is made once per grid)
 	struct { tg_grid grid; int ranks = 0; std::vector<uint32_t> cuts; std::vector<double> layer_cost; int feedback_rounds = 0; } plan;
+	// the same estimate for the slab pipeline of a single-GPU export with host results (cuts by cost, not by thickness)
+	struct { tg_grid grid; std::vector<double> layer_cost; bool valid = false; } pipeline_plan;
 	// vertex / quad counts of this device's last slab of a multi-GPU export: capacities of the next one when the cuts moved
 	uint64_t last_slab_vertices = 0, last_slab_quads = 0;
 

@@ -499,6 +499,7 @@ int EngineExportMeshMulti(DeviceGroup* group, const std::vector<Model*>& models,
 		ctx->progress_base = 0;
 		ctx->progress_slabs = 1;
 		if (ctx->progress_words) ctx->progress_words[0] = ctx->progress_words[1] = 0u;
+		ctx->progress_seen[0] = ctx->progress_seen[1] = 0u;
 		if (!ctx->index_base) TG_RANK_CUDA(cudaMalloc(&ctx->index_base, 8));
 		if (!ex.gathered[size_t(rank)])
 		{

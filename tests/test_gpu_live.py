@@ -86,3 +86,19 @@ def test_live_grid_needs_a_live_model(context):
     with pytest.raises(T.TangerineError):
         model.live_grid(20.0)
     model.close()
+
+
+def test_live_mesh_on_two_gpus():
+    """The live field goes through the same multi-device export (z-slabs, one stitched host mesh)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two devices")
+    fx = live_fixture("seaside50")
+    ctx = T.Context(devices=[0, 1])
+    model = T.Model(ctx, T.Tree.load(O.model_path(fx["model"])), live=True)
+    mesh = model.export_mesh(model.live_grid(fx["density"]), flags=T.MESH_NORMALS | T.MESH_LIVE_FIELD, refine=0)
+    layers, v, t, bad = layer_report(mesh.positions, mesh.normals, None, mesh.triangles, fx)
+    assert (v, t) == (fx["vertices"], fx["triangles"]) and not bad, bad[:10]
+    mesh.close()
+    model.close()
+    ctx.close()
