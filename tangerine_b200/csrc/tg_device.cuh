@@ -730,25 +730,34 @@ __device__ __forceinline__ float GroupEvalLong(const uint4* __restrict__ program
 	}
 	sync();
 
-	// a. operands two deep
+	// a. operands two deep.  An owner first folds its operand reading only, the group meets, then the owners write: a
+	// thread that tests a step inside somebody else's operand must not see it half rewritten.
 	const int debug = g_long_debug;
-	for (uint32_t i = tid; i < n && !(debug & 1); i += GROUP)
+	for (uint32_t base = 0; base < n && !(debug & 1); base += GROUP)
 	{
-		if ((steps[i].x & 0xFFFFu) != (kFoldPush | (1u << 8))) continue;
-		float acc = __uint_as_float(steps[i].y);
-		float stack[kMaxStackSlots];
-		uint32_t j = i + 1;
-		for (; j < n; ++j)
+		const uint32_t i = base + uint32_t(tid);
+		const bool owner = i < n && (steps[i].x & 0xFFFFu) == (kFoldPush | (1u << 8));
+		float acc = 0.0f;
+		uint32_t j = n;
+		if (owner)
 		{
-			const uint32_t word = steps[j].x;
-			if ((word & 0xFFFFu) == (kFoldStackOp | (1u << 8))) break;
-			FoldStep(word, __uint_as_float(steps[j].y), params[j], acc, stack);
+			acc = __uint_as_float(steps[i].y);
+			float stack[kMaxStackSlots];
+			for (j = i + 1; j < n; ++j)
+			{
+				const uint32_t word = steps[j].x;
+				if ((word & 0xFFFFu) == (kFoldStackOp | (1u << 8))) break;
+				FoldStep(word, __uint_as_float(steps[j].y), params[j], acc, stack);
+			}
 		}
-		if (j >= n) continue;
-		for (uint32_t k = i; k < j; ++k) steps[k].x = kFoldNop | (kNoSlot << 8);
-		CollapseInto(steps, params, j, acc);
+		sync();
+		if (owner && j < n)
+		{
+			for (uint32_t k = i; k < j; ++k) steps[k].x = kFoldNop | (kNoSlot << 8);
+			CollapseInto(steps, params, j, acc);
+		}
+		sync();
 	}
-	sync();
 
 	// b. operands of the main chain: ordered lists of their opening pushes and closing operators.  `marks` holds, per
 	// thread, the number of openings (low half) and closings (high half) in its contiguous share -> exclusive prefix.

@@ -10,7 +10,7 @@ python bench.py --steps 5 --warmup 4 > $out/${tag}_bench_n1.json 2> $out/${tag}_
 cat $out/${tag}_bench_n1.json
 tail -3 $out/${tag}_bench_n1.err
 if [ "$2" != "quick" ]; then
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra-workloads > $out/${tag}_ncu_b.log 2>&1
 python tools/launch_list.py $out/${tag}_launches.csv 3 > $out/${tag}_launch_list.txt 2>&1
 cat $out/${tag}_launch_list.txt

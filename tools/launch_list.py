@@ -18,9 +18,14 @@ for r in rows:
     u = d['Metric Unit']
     v = v / 1e3 if u == 'ns' else v * 1e3 if u == 'ms' else v
     out.append((d['Kernel Name'][:56], v, d.get('Grid Size', '')))
-idx = [i for i, o in enumerate(out) if o[0].startswith('CullRegionInit') or o[0].startswith('CullResolve') and (i == 0 or not out[i - 1][0].startswith('Cull'))]
-idx.append(len(out))
-s, e = idx[which], idx[which + 1]
+# exports start at CullRegionInitKernel; a pipelined export (host results) runs several slabs -- several brick kernels --
+# behind one cull, a device-resident step exactly one: the n-th of those is listed
+starts = [i for i, o in enumerate(out) if o[0].startswith('CullRegionInit')] + [len(out)]
+steps = [(s, e) for s, e in zip(starts, starts[1:]) if sum(1 for o in out[s:e] if o[0].startswith('MeshBricksKernel')) == 1]
+s, e = steps[min(which, len(steps) - 1)]
+# drop what follows the export's last kernel (the L2 flush and the cull of nothing else belong to the next step)
+while e > s and out[e - 1][0].startswith(('FillKernel', 'FmaChain')):
+    e -= 1
 total = sum(o[1] for o in out[s:e])
 for o in out[s:e]:
     print("%-58s %9.1f us  %5.1f%%  grid %s" % (o[0], o[1], 100 * o[1] / total, o[2]))
