@@ -325,6 +325,9 @@ TG_API void tg_free(void* pointer);
  * ---------------------------------------------------------------------------------------------- */
 TG_API int tg_progress(const tg_context* context, float out_ratios[4], int* out_stage);
 TG_API int tg_cancel(tg_context* context, int halt);
+/* Clears a tg_cancel so that a long-lived context can run its next export (MeshExport sets ExportActive again, export.cpp:568).
+ * Exports started without TG_MESH_KEEP_CANCEL do this themselves. */
+TG_API int tg_rearm(tg_context* context);
 
 /* ------------------------------------------------------------------------------------------------
  * File-level entry points with the signatures of the reference's legacy FFI:

@@ -146,6 +146,7 @@ def lib():
         "tg_model_create": (vp, [vp, vp, C.c_float, i32]),
         "tg_model_create_live": (vp, [vp, vp, C.c_float, i32]),
         "tg_live_grid": (i32, [vp, C.c_float, C.POINTER(Grid)]),
+        "tg_rearm": (i32, [vp]),
         "tg_tree_octree_stats": (i32, [vp, C.c_float, i32, C.POINTER(ModelStats)]),
         "tg_model_destroy": (None, [vp]),
         "tg_tree_plan_slabs": (i32, [vp, C.c_float, C.POINTER(Grid), i32, C.POINTER(u64), C.POINTER(C.c_double)]),
@@ -419,6 +420,9 @@ class Context:
 
     def cancel(self, halt=True):
         _check(lib().tg_cancel(self.h, 1 if halt else 0))
+
+    def rearm(self):
+        _check(lib().tg_rearm(self.h))
 
 
 class Mesh:

@@ -451,12 +451,16 @@ int tg_context_device_count(const tg_context* context)
 void tg_context_destroy(tg_context* context) try
 {
 	if (!context) return;
-	if (context->impl && context->impl->live_results.load() > 0)
+	// meshes or models of this context are still alive: freeing the last one tears the device context down
+	context->group.reset(); // (the device threads go first: they only serve exports)
+	auto orphan = [](std::unique_ptr<Context>& c)
 	{
-		// meshes of this context are still alive: tg_mesh_free of the last one tears the context down
-		context->impl->orphaned.store(true);
-		if (context->impl->live_results.load() > 0) context->impl.release();
-	}
+		if (!c || c->live_results.load() <= 0) return;
+		c->orphaned.store(true);
+		if (c->live_results.load() > 0) c.release();
+	};
+	orphan(context->impl);
+	for (auto& peer : context->peers) orphan(peer);
 	delete context;
 }
 TG_CATCH_VOID
@@ -793,6 +797,15 @@ int tg_cancel(tg_context* context, int halt) try
 	// Stages here are whole kernels, so both requests stop at the next stage boundary.
 	(void)halt;
 	context->impl->active.store(false);
+	return TG_OK;
+}
+TG_CATCH_STATUS
+
+int tg_rearm(tg_context* context) try
+{
+	if (!context) return Fail(TG_ERR_INVALID, "null context");
+	context->impl->active.store(true);
+	for (auto& peer : context->peers) peer->active.store(true);
 	return TG_OK;
 }
 TG_CATCH_STATUS

@@ -1803,7 +1803,9 @@ void* Context::AcquirePinned(size_t bytes, std::string& error)
 	int best = -1;
 	for (size_t i = 0; i < pinned.size(); ++i)
 	{
-		if (!pinned[i].in_use && pinned[i].bytes >= bytes && (best < 0 || pinned[i].bytes < pinned[size_t(best)].bytes)) best = int(i);
+		// (a block more than twice the request stays free for what it was made for: a model's small tables must not sit in
+		// the blocks of a 300 MB mesh)
+		if (!pinned[i].in_use && pinned[i].bytes >= bytes && pinned[i].bytes <= 2 * bytes + (size_t(1) << 20) && (best < 0 || pinned[i].bytes < pinned[size_t(best)].bytes)) best = int(i);
 	}
 	if (best >= 0)
 	{
@@ -1831,7 +1833,7 @@ void* Context::AcquireDevice(size_t bytes, std::string& error)
 	for (size_t i = 0; i < device_blocks.size(); ++i)
 	{
 		const PinnedBlock& b = device_blocks[i];
-		if (!b.in_use && b.bytes >= bytes && (best < 0 || b.bytes < device_blocks[size_t(best)].bytes)) best = int(i);
+		if (!b.in_use && b.bytes >= bytes && b.bytes <= 2 * bytes + (size_t(1) << 20) && (best < 0 || b.bytes < device_blocks[size_t(best)].bytes)) best = int(i);
 	}
 	if (best >= 0)
 	{
@@ -1917,10 +1919,14 @@ static int UploadVector(Context* c, const std::vector<T>& v, void** device, void
 	const size_t bytes = std::max<size_t>(payload, 16);
 	if (!*device)
 	{
-		TG_CUDA(cudaMalloc(device, bytes));
+		// blocks of the context's caches: the next model made on this context pays for no allocation (cudaMalloc and above all
+		// cudaMallocHost of some 20 MB were a third of tg_model_create)
+		*device = c->AcquireDevice(bytes, error);
+		if (!*device) return TG_ERR_MEMORY;
 		if (!shared_staging)
 		{
-			TG_CUDA(cudaMallocHost(staging, bytes));
+			*staging = c->AcquirePinned(bytes, error);
+			if (!*staging) return TG_ERR_MEMORY;
 			std::memcpy(*staging, v.data(), payload);
 		}
 	}
@@ -1933,14 +1939,20 @@ static int UploadVector(Context* c, const std::vector<T>& v, void** device, void
 static void FreeModelTables(Model* m)
 {
 	void** tables[] = { &m->d_nodes, &m->d_interp, &m->d_tree, &m->d_materials, &m->d_regions, &m->d_node_rank };
+	if (m->context)
+	{
+		// the tables may still be read by kernels in flight: the blocks go back to the caches behind them
+		cudaStreamSynchronize(StreamOf(m->context));
+		cudaStreamSynchronize(static_cast<cudaStream_t>(m->context->stream2));
+	}
 	for (void** t : tables)
 	{
-		cudaFree(*t);
+		if (m->context) m->context->ReleaseDevice(*t);
 		*t = nullptr;
 	}
 	for (void*& h : m->staging)
 	{
-		cudaFreeHost(h);
+		if (m->context && h) m->context->ReleasePinned(h);
 		h = nullptr;
 	}
 	m->device_bytes = 0;
@@ -1976,9 +1988,17 @@ static int ProfileLeaves(Model* m, std::string& error)
 	uint32_t* d_nodes = nullptr;
 	float* d_span = nullptr;
 	unsigned long long* d_masks = nullptr;
-	TG_CUDA(cudaMalloc(&d_nodes, size_t(count) * 4));
-	TG_CUDA(cudaMalloc(&d_span, size_t(count) * 4));
-	TG_CUDA(cudaMalloc(&d_masks, size_t(count) * 8));
+	Context* ctx = m->context;
+	d_nodes = static_cast<uint32_t*>(ctx->AcquireDevice(size_t(count) * 4, error));
+	d_span = static_cast<float*>(ctx->AcquireDevice(size_t(count) * 4, error));
+	d_masks = static_cast<unsigned long long*>(ctx->AcquireDevice(size_t(count) * 8, error));
+	struct Return
+	{
+		Context* c;
+		void* p[3];
+		~Return() { for (void* q : p) c->ReleaseDevice(q); }
+	} give_back{ ctx, { d_nodes, d_span, d_masks } };
+	if (!d_nodes || !d_span || !d_masks) return TG_ERR_MEMORY;
 	TG_CUDA(cudaMemcpyAsync(d_nodes, flat.leaf_nodes.data(), size_t(count) * 4, cudaMemcpyHostToDevice, stream));
 	TG_CUDA(cudaMemcpyAsync(d_span, flat.leaf_span.data(), size_t(count) * 4, cudaMemcpyHostToDevice, stream));
 	TG_CUDA(cudaMemsetAsync(d_masks, 0, size_t(count) * 8, stream));
@@ -1986,9 +2006,6 @@ static int ProfileLeaves(Model* m, std::string& error)
 	TG_CUDA(cudaGetLastError());
 	TG_CUDA(cudaMemcpyAsync(flat.leaf_mask.data(), d_masks, size_t(count) * 8, cudaMemcpyDeviceToHost, stream));
 	TG_CUDA(cudaStreamSynchronize(stream));
-	cudaFree(d_nodes);
-	cudaFree(d_span);
-	cudaFree(d_masks);
 	return TG_OK;
 }
 
@@ -1996,6 +2013,7 @@ Model* Model::Create(Context* context, const Tree& tree, float target_size, int 
 {
 	Model* m = new Model();
 	m->context = context;
+	context->live_results.fetch_add(1); // a model keeps its context alive like a mesh does (its tables sit in the context's caches)
 	if (!BuildFlatModel(tree, target_size, threads, m->flat, error, false, !live_octree)) // reference statistics on demand (tg_model_get_stats)
 	{
 		delete m;
@@ -2021,8 +2039,12 @@ Model* Model::Create(Context* context, const Tree& tree, float target_size, int 
 
 Model::~Model()
 {
-	if (context) cudaSetDevice(context->device);
+	if (!context) return;
+	cudaSetDevice(context->device);
 	FreeModelTables(this);
+	Context* owner = context;
+	context = nullptr;
+	if (owner->live_results.fetch_sub(1) == 1 && owner->orphaned.load()) delete owner; // tg_context_destroy came first
 }
 
 int EngineUploadModel(Model* model, std::string& error)

@@ -237,6 +237,7 @@ Model* Model::CreateReplica(Context* context, Model* primary, std::string& error
 {
 	Model* m = new Model(primary->flat_owner);
 	m->context = context;
+	context->live_results.fetch_add(1);
 	m->primary = primary;
 	m->leaf_count = primary->leaf_count;
 	if (UploadModel(m, error) != TG_OK)
