@@ -27,6 +27,7 @@ struct DeviceModel
 	const uint32_t* tree;
 	const FlatRegion* regions;
 	const uint32_t* node_rank; // node -> position by descending program cost (key of the attribute pass's counting sort)
+	const uint32_t* node_material; // node -> the one material its program can return, or kMixedMaterial (FlatModel::node_material)
 	uint32_t region_count;
 	const float* material_rgb; // 3 floats per id
 	uint32_t material_count;   // index of the trailing default-white entry

@@ -1241,8 +1241,9 @@ __device__ __forceinline__ void ExportColor(const DeviceModel& model, uint32_t n
 	float r = 1.0f, g = 1.0f, b = 1.0f;
 	if (model.has_paint)
 	{
-		uint32_t m[1];
-		EvalTreeCentre(model.tree + __ldg(&model.nodes[node].tree_offset), x, y, z, &m[0]);
+		// a node whose program can only return one material needs no walk (warps are node-coherent: no divergence here)
+		uint32_t m[1] = { __ldg(&model.node_material[node]) };
+		if (m[0] == kMixedMaterial) EvalTreeCentre(model.tree + __ldg(&model.nodes[node].tree_offset), x, y, z, &m[0]);
 		const uint32_t id = m[0] == kNoMaterial || m[0] >= model.material_count ? model.material_count : m[0];
 		r = __ldg(&model.material_rgb[id * 3 + 0]);
 		g = __ldg(&model.material_rgb[id * 3 + 1]);
@@ -1938,7 +1939,7 @@ static int UploadVector(Context* c, const std::vector<T>& v, void** device, void
 
 static void FreeModelTables(Model* m)
 {
-	void** tables[] = { &m->d_nodes, &m->d_interp, &m->d_tree, &m->d_materials, &m->d_regions, &m->d_node_rank };
+	void** tables[] = { &m->d_nodes, &m->d_interp, &m->d_tree, &m->d_materials, &m->d_regions, &m->d_node_rank, &m->d_node_material };
 	if (m->context)
 	{
 		// the tables may still be read by kernels in flight: the blocks go back to the caches behind them
@@ -1971,6 +1972,7 @@ static int UploadModel(Model* m, std::string& error)
 	if ((rc = UploadVector(c, m->flat.material_rgb, &m->d_materials, &m->staging[3], src ? src->staging[3] : nullptr, m->device_bytes, error)) != TG_OK) return rc;
 	if ((rc = UploadVector(c, m->flat.regions, &m->d_regions, &m->staging[4], src ? src->staging[4] : nullptr, m->device_bytes, error)) != TG_OK) return rc;
 	if ((rc = UploadVector(c, m->flat.node_rank, &m->d_node_rank, &m->staging[5], src ? src->staging[5] : nullptr, m->device_bytes, error)) != TG_OK) return rc;
+	if ((rc = UploadVector(c, m->flat.node_material, &m->d_node_material, &m->staging[6], src ? src->staging[6] : nullptr, m->device_bytes, error)) != TG_OK) return rc;
 	TG_CUDA(cudaStreamSynchronize(StreamOf(c)));
 	return TG_OK;
 }
@@ -2108,6 +2110,7 @@ static DeviceModel MakeDeviceModel(const Model* m)
 	d.material_rgb = static_cast<const float*>(m->d_materials);
 	d.regions = static_cast<const FlatRegion*>(m->d_regions);
 	d.node_rank = static_cast<const uint32_t*>(m->d_node_rank);
+	d.node_material = static_cast<const uint32_t*>(m->d_node_material);
 	d.region_count = uint32_t(m->flat.regions.size());
 	d.material_count = uint32_t(m->flat.material_rgb.size() / 3 - 1);
 	d.root_interp_offset = m->flat.root_interp_offset;

@@ -99,7 +99,8 @@ public:
 	void* d_materials = nullptr;
 	void* d_regions = nullptr;
 	void* d_node_rank = nullptr;
-	void* staging[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // page-locked host copies of the six tables
+	void* d_node_material = nullptr;
+	void* staging[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // page-locked host copies of the seven tables
 	uint64_t device_bytes = 0;
 	double upload_seconds = 0.0;
 	int leaf_count = 0;

@@ -519,6 +519,26 @@ inline uint64_t Fnv(uint64_t hash, const void* data, size_t bytes)
 // no heavy work.  (2) Every node's two device programs and the statistics / hash of its program in the reference's word
 // encoding are generated independently, on the task pool.  (3) A serial pass gives the programs their offsets and
 // concatenates them.
+// The material SDFNode::GetMaterial returns at every point, when it does not depend on the point (sdf_evaluator.cpp:
+// 537-540 brush, 957-1012 set operators: a difference asks its left operand only, a union the operand that wins, an
+// intersection the winner among the operands that have paint, :1130-1133 the wrappers their child).  A stencil
+// (:666-679) decides by the sign of its mask: mixed.
+static uint32_t UniformMaterial(const NodePool& pool, uint32_t index)
+{
+	const Node& n = pool.nodes[index];
+	if (IsBrush(n.kind)) return n.material;
+	if (n.kind == kKindFlate) return UniformMaterial(pool, n.a);
+	if (!IsSet(n.kind)) return kMixedMaterial;
+	const Family family = SetFamily(n.kind);
+	const uint32_t l = UniformMaterial(pool, n.a);
+	if (family == Family::Diff) return l;
+	const uint32_t r = UniformMaterial(pool, n.b);
+	if (family == Family::Union) return l == r ? l : kMixedMaterial;
+	const bool l_valid = pool.nodes[n.a].has_paint, r_valid = pool.nodes[n.b].has_paint;
+	if (l_valid && r_valid) return l == r ? l : kMixedMaterial;
+	return l_valid ? l : r;
+}
+
 struct Flattener
 {
 	struct Job
@@ -531,6 +551,7 @@ struct Flattener
 		uint32_t flags = 0, flops = 0;
 		int max_slots = 0;
 		uint64_t ref_words = 0, stack = 0, node_hash = 0;
+		uint32_t material = kMixedMaterial;
 	};
 
 	FlatModel& model;
@@ -632,6 +653,7 @@ struct Flattener
 		job.flops = interp.flops;
 		job.max_slots = tree.max_slots;
 		job.stack = st.pool.nodes[bn.evaluator].stack_size;
+		job.material = UniformMaterial(st.pool, bn.evaluator);
 		if (!reference_stats) return;
 		// Reference-format words: statistics + hash only.
 		std::vector<uint32_t> ref_words;
@@ -657,6 +679,7 @@ struct Flattener
 	template <class Pool> void Assemble(Pool* tasks)
 	{
 		std::vector<size_t> interp_at(jobs.size()), tree_at(jobs.size());
+		model.node_material.assign(jobs.size(), kMixedMaterial);
 		size_t interp_words = model.interp.size(), tree_words = model.tree.size();
 		FlatModelStats& s = model.stats;
 		for (size_t i = 0; i < jobs.size(); ++i)
@@ -671,6 +694,7 @@ struct Flattener
 			tree_words += job.tree.size();
 			fn.flags = job.flags;
 			fn.flops = job.flops;
+			model.node_material[i] = job.material;
 			if (job.max_slots > max_slots) max_slots = job.max_slots;
 			s.nodes++;
 			if (fn.terminus) s.leaves++;
@@ -892,6 +916,17 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 	}
 
 	lap("node ranks");
+	if (trace_host)
+	{
+		size_t leaves = 0, uniform = 0;
+		for (size_t i = 0; i < out.nodes.size(); ++i)
+		{
+			if (!out.nodes[i].terminus) continue;
+			leaves++;
+			if (out.node_material[i] != kMixedMaterial) uniform++;
+		}
+		std::fprintf(stderr, "octree build: %zu of %zu terminus nodes have one material\n", uniform, leaves);
+	}
 	// Unpruned model programs (VoxExport and whole-tree point queries).
 	{
 		out.root_interp_offset = uint32_t(out.interp.size());

@@ -18,6 +18,8 @@
 namespace tg
 {
 
+constexpr uint32_t kMixedMaterial = 0xFFFFFFFEu;
+
 struct FlatModelStats
 {
 	uint64_t nodes = 0;        // octree nodes
@@ -40,6 +42,9 @@ struct FlatModel
 	std::vector<uint32_t> tree;       // kStreamTree programs, addressed by FlatNode::tree_offset
 	std::vector<FlatRegion> regions;  // evaluation regions (tg_program.h), pre-order
 	std::vector<uint32_t> node_rank;  // position of every node when the nodes are sorted by program cost, costliest first
+	// per node: the material GetMaterial returns WHEREVER its program is evaluated (every brush that can win carries the same
+	// one; kNoMaterial counts as one), or kMixedMaterial when it depends on the point and the walk has to run
+	std::vector<uint32_t> node_material;
 	// Terminus cells of the octree, for the multi-GPU slab planner: node index, cell span, and -- filled by
 	// Model::Create on the device, one bit per 1/4-span sub-cell (x + 4 y + 16 z) -- whether the cell's program can have
 	// a zero there (|d(sub-cell centre)| <= its half diagonal).  Empty mask vector = nothing known (all set is assumed).

@@ -17,7 +17,11 @@ for r in rows:
     v = float(d['Metric Value'].replace(',', ''))
     u = d['Metric Unit']
     v = v / 1e3 if u == 'ns' else v * 1e3 if u == 'ms' else v
-    out.append((d['Kernel Name'][:56], v, d.get('Grid Size', '')))
+    name = d['Kernel Name']
+    for prefix in ('tg::', 'tg_fast::'):
+        if name.startswith(prefix):
+            name = name[len(prefix):]
+    out.append((name[:56].replace('tg::', ''), v, d.get('Grid Size', '')))
 # exports start at CullRegionInitKernel; a pipelined export (host results) runs several slabs -- several brick kernels --
 # behind one cull, a device-resident step exactly one: the n-th of those is listed
 starts = [i for i, o in enumerate(out) if o[0].startswith('CullRegionInit')] + [len(out)]
