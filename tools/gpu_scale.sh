@@ -8,7 +8,7 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127
 python - $out/${tag}_bench_n$n.json <<'PY'
 import json, sys
 d = json.loads([l for l in open(sys.argv[1]) if l.startswith('{')][-1])
-print(sys.argv[1], "ms/step %.3f  value %.0f  e2e %.3f ms" % (d["ms_per_step"], d["value"], d["e2e"]["ms_per_step"]), d["config"]["partition"][:100])
+print(sys.argv[1], "ms/step %.3f  value %.0f  e2e %.3f ms" % (d["ms_per_step"], d["value"], d["e2e"]["ms_per_step"]), d["run"]["partition"][:100])
 for k, v in d["per_rank_ms"].items(): print("   ", k, [round(x, 3) for x in v])
 PY
 tail -2 $out/${tag}_bench_n$n.err
