@@ -121,8 +121,10 @@ typedef struct tg_context tg_context;
 typedef struct tg_model tg_model;
 
 TG_API tg_context* tg_context_create(int cuda_device);
-/* Destroy the models of a context before the context.  Meshes may outlive it: their arrays are blocks of the context's
- * pinned cache, so a context with live meshes is torn down by the tg_mesh_free of the last one. */
+/* Meshes and models may outlive their context: their arrays are blocks of the context's caches, so a context that still
+ * has live meshes or models is torn down when the last of them is freed (it can start no new export meanwhile).  A
+ * context is worth keeping for the life of the application: it owns the scratch arena, the result caches and the
+ * page-locked staging memory, which cost more to make than an export. */
 TG_API void tg_context_destroy(tg_context* context);
 TG_API int tg_context_device(const tg_context* context);
 /* Multi-GPU context: the devices of one box, driven from this one process (SURVEY.md 8b `tg_ctx_create(devices[], n)`).
