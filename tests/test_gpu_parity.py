@@ -524,3 +524,31 @@ def test_exported_ply_with_refinement_differs_from_the_reference_on_purpose(gold
     want = oc.refine(a["pos"].copy(), [step / 2] * 3, 5)
     assert same_floats(b["pos"], want)
     assert same_floats(b["normal"], oc.gradient(want))
+
+
+def test_models_and_meshes_may_outlive_their_context():
+    """tg_context_destroy with live models / meshes: the device context is torn down by whichever of them is freed last
+    (their arrays are blocks of the context's caches), in any order; a second context is unaffected."""
+    tree = T.Tree.load(O.model_path("basic_thing"))
+    lo, hi = tree.bounds()
+    grid = T.export_grid(lo, hi, np.float32(1.0 / 8.0))
+    for order in ("model first", "mesh first"):
+        ctx = T.Context(0)
+        model = T.Model(ctx, tree)
+        mesh = model.export_mesh(grid)
+        positions = mesh.positions.copy()
+        ctx.close()
+        assert np.array_equal(mesh.positions, positions)   # the pinned arrays are still there
+        if order == "model first":
+            model.close()
+            mesh.close()
+        else:
+            mesh.close()
+            model.close()
+    ctx = T.Context(0)
+    model = T.Model(ctx, tree)
+    again = model.export_mesh(grid)
+    assert np.array_equal(again.positions, positions)
+    again.close()
+    model.close()
+    ctx.close()
