@@ -187,6 +187,13 @@ TG_API int tg_eval_points(tg_model* model, int mode, const float* points, uint64
  * normalize(target - origin)).  out_hits: 5 floats per ray -- hit (1 or 0), travel (infinity on a miss), position. */
 TG_API int tg_ray_cast(tg_model* model, const float* rays, uint64_t count, int max_iterations, float epsilon, int magnet, float* out_hits);
 
+/* Vertex welding: MeshGenerator::Accumulate (tangerine/mesh_generators.cpp:20-80, used by the lattice mesher's "combined
+ * vertices" mode, sodapop.cpp:1287, 1508) over a stream of `count` vertices (3 floats each; a triangle soup is three per
+ * triangle).  out_indices[i] is the index of vertex i among the distinct vertices in order of first occurrence -- equal
+ * means numerically equal per component, so -0 welds with +0 -- and out_vertices4 receives those as (x, y, z, 1) with
+ * the bits of their first occurrence; both have room for `count` entries, *out_unique tells how many vertices there are. */
+TG_API int tg_weld(tg_context* context, const float* vertices, uint64_t count, float* out_vertices4, uint32_t* out_indices, uint64_t* out_unique);
+
 /* Self-check used by the tests: the culling pass evaluates long programs cooperatively (a warp or a block per point,
  * parallel fold); this runs every long program of the model at 9 points within `reach` of its octree node's pivot both
  * ways and returns { probes, disagreements of the block form, disagreements of the warp form } -- the last two must be 0. */

@@ -30,6 +30,7 @@
 #include "lua_env.h"
 #include "export.h"
 #include "magica.h"
+#include "mesh_generators.h"
 
 extern SDFNodeShared g_CapturedTree;
 extern std::atomic_bool ExportActive;
@@ -476,6 +477,7 @@ static int Usage()
 		"  vox       <model> <grid_size> <color_index> <out.vox>\n"
 		"  bench     <model> <minx..maxz> <step> <threads> <slice_stride> reference thunks on std::threads (JSON)\n"
 		"  slices    <model> <minx..maxz> <step> <threads> <k_begin> <k_end|0> <attributes 0|1> <out.json>   per-layer digests of the reference mesh\n"
+		"  weld      <vertices.f32> <out.bin>                 MeshGenerator::Accumulate over float3 vertices (mesh_generators.cpp)\n"
 		"  slices-live <model> <density> <threads> <attributes 0|1> <out.json>   the same for the live mesher (sodapop.cpp) at a meshing density\n");
 	return 1;
 }
@@ -1110,6 +1112,28 @@ int main(int Argc, char** Argv)
 		return Usage();
 	}
 	std::string Command = Argv[1];
+	if (Command == "weld" && Argc == 4)
+	{
+		// MeshGenerator::Accumulate(vertex) over a stream of float3 (mesh_generators.cpp:42-50): out = u32 distinct count,
+		// the distinct vertices as vec4, one u32 index per input vertex
+		std::ifstream In(Argv[2], std::ios::binary);
+		std::vector<char> Raw((std::istreambuf_iterator<char>(In)), std::istreambuf_iterator<char>());
+		const size_t Count = Raw.size() / 12;
+		const float* Values = reinterpret_cast<const float*>(Raw.data());
+		MeshGenerator Generator;
+		for (size_t i = 0; i < Count; ++i)
+		{
+			Generator.Accumulate(glm::vec3(Values[i * 3 + 0], Values[i * 3 + 1], Values[i * 3 + 2]));
+		}
+		FILE* Out = std::fopen(Argv[3], "wb");
+		if (!Out) return 2;
+		uint32_t Distinct = uint32_t(Generator.Vertices.size());
+		std::fwrite(&Distinct, 4, 1, Out);
+		std::fwrite(Generator.Vertices.data(), 16, Generator.Vertices.size(), Out);
+		std::fwrite(Generator.Indices.data(), 4, Generator.Indices.size(), Out);
+		std::fclose(Out);
+		return 0;
+	}
 	SDFNodeShared Tree = LoadModel(Argv[2]);
 	if (!Tree)
 	{

@@ -1799,3 +1799,70 @@ uint64_t tgo_voxels(const TgoModel* m, float grid_size, int32_t out_size[3], flo
 	*out_xyz = xyz;
 	return count;
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* MeshGenerator (tangerine/mesh_generators.cpp)                                                */
+/* ------------------------------------------------------------------------------------------- */
+
+/* LessVec3 :20-39: z, then y, then x */
+static int weld_less(const float* l, const float* r)
+{
+	if (l[2] < r[2]) return 1;
+	if (l[2] == r[2])
+	{
+		if (l[1] < r[1]) return 1;
+		if (l[1] == r[1]) return l[0] < r[0];
+	}
+	return 0;
+}
+
+typedef struct { const float* v; uint32_t index; } WeldEntry;
+static int weld_compare(const void* a, const void* b)
+{
+	const WeldEntry* x = (const WeldEntry*)a;
+	const WeldEntry* y = (const WeldEntry*)b;
+	if (weld_less(x->v, y->v)) return -1;
+	if (weld_less(y->v, x->v)) return 1;
+	return x->index < y->index ? -1 : (x->index > y->index ? 1 : 0); /* equivalent keys: earliest first */
+}
+
+/* Accumulate :42-50 for every vertex in order.  std::map::insert keeps the first key of an equivalence class and its
+ * value (the index the vertex got then); sorting by (key, position) and walking the classes gives the same answer. */
+uint64_t tgo_weld(const float* vertices, uint64_t count, float* out_vertices4, uint32_t* out_indices)
+{
+	if (count == 0) return 0;
+	WeldEntry* entries = (WeldEntry*)malloc(sizeof(WeldEntry) * count);
+	uint32_t* first_of = (uint32_t*)malloc(sizeof(uint32_t) * count); /* per vertex: position of its class's first vertex */
+	for (uint64_t i = 0; i < count; ++i)
+	{
+		entries[i].v = vertices + i * 3;
+		entries[i].index = (uint32_t)i;
+	}
+	qsort(entries, count, sizeof(WeldEntry), weld_compare);
+	for (uint64_t i = 0; i < count;)
+	{
+		uint64_t j = i + 1;
+		while (j < count && !weld_less(entries[i].v, entries[j].v) && !weld_less(entries[j].v, entries[i].v)) ++j;
+		for (uint64_t k = i; k < j; ++k) first_of[entries[k].index] = entries[i].index;
+		i = j;
+	}
+	uint64_t distinct = 0;
+	uint32_t* number = (uint32_t*)malloc(sizeof(uint32_t) * count);
+	for (uint64_t i = 0; i < count; ++i)
+	{
+		if (first_of[i] == i)
+		{
+			number[i] = (uint32_t)distinct;
+			out_vertices4[distinct * 4 + 0] = vertices[i * 3 + 0];
+			out_vertices4[distinct * 4 + 1] = vertices[i * 3 + 1];
+			out_vertices4[distinct * 4 + 2] = vertices[i * 3 + 2];
+			out_vertices4[distinct * 4 + 3] = 1.0f;
+			distinct++;
+		}
+		out_indices[i] = number[first_of[i]];
+	}
+	free(number);
+	free(first_of);
+	free(entries);
+	return distinct;
+}

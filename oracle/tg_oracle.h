@@ -74,6 +74,11 @@ void tgo_color(const TgoOctree* octree, const float* points, uint64_t count, uin
 /* MeshExportThread's grid (export.cpp:324-337) from model bounds and a step. */
 void tgo_export_grid(const float model_min[3], const float model_max[3], const float step[3], TgoGrid* out);
 
+/* MeshGenerator::Accumulate(vertex) for every vertex of a stream, in order (tangerine/mesh_generators.cpp:20-50): the
+ * distinct vertices as (x, y, z, 1) in order of first occurrence and one index per input vertex.  Equal = LessVec3's
+ * equivalence (numeric equality per component: -0 is +0).  Returns the number of distinct vertices. */
+uint64_t tgo_weld(const float* vertices, uint64_t count, float* out_vertices4, uint32_t* out_indices);
+
 /* NaiveSurfaceNetsScratch's grid (sodapop.cpp:153-179) from a live octree's bounds and the meshing density. */
 void tgo_live_grid(const TgoOctree* octree, float meshing_density, TgoGrid* out);
 

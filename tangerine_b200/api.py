@@ -147,6 +147,7 @@ def lib():
         "tg_model_create_live": (vp, [vp, vp, C.c_float, i32]),
         "tg_live_grid": (i32, [vp, C.c_float, C.POINTER(Grid)]),
         "tg_rearm": (i32, [vp]),
+        "tg_weld": (i32, [vp, C.POINTER(C.c_float), u64, C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(u64)]),
         "tg_tree_octree_stats": (i32, [vp, C.c_float, i32, C.POINTER(ModelStats)]),
         "tg_model_destroy": (None, [vp]),
         "tg_tree_plan_slabs": (i32, [vp, C.c_float, C.POINTER(Grid), i32, C.POINTER(u64), C.POINTER(C.c_double)]),
@@ -423,6 +424,15 @@ class Context:
 
     def rearm(self):
         _check(lib().tg_rearm(self.h))
+
+    def weld(self, vertices):
+        """MeshGenerator::Accumulate over a vertex stream: (distinct vertices as (n, 4) with w = 1, index per input vertex)."""
+        v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+        out = np.zeros((max(len(v), 1), 4), np.float32)
+        idx = np.zeros(max(len(v), 1), np.uint32)
+        unique = C.c_uint64(0)
+        _check(lib().tg_weld(self.h, _fp(v), len(v), _fp(out), idx.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(unique)))
+        return out[:unique.value].copy(), idx[:len(v)].copy()
 
 
 class Mesh:

@@ -801,6 +801,15 @@ int tg_cancel(tg_context* context, int halt) try
 }
 TG_CATCH_STATUS
 
+int tg_weld(tg_context* context, const float* vertices, uint64_t count, float* out_vertices4, uint32_t* out_indices, uint64_t* out_unique) try
+{
+	if (!context || !out_unique || (count && (!vertices || !out_vertices4 || !out_indices))) return Fail(TG_ERR_INVALID, "null argument");
+	std::string error;
+	const int rc = EngineWeld(context->impl.get(), vertices, count, out_vertices4, out_indices, out_unique, error);
+	return rc == TG_OK ? TG_OK : Fail(rc, error);
+}
+TG_CATCH_STATUS
+
 int tg_rearm(tg_context* context) try
 {
 	if (!context) return Fail(TG_ERR_INVALID, "null context");

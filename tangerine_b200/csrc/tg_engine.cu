@@ -1131,6 +1131,63 @@ __global__ void __launch_bounds__(256) FinalizeMeshKernel(const FaceParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
+// MeshGenerator (tangerine/mesh_generators.cpp:20-80): welds a vertex stream -- Accumulate(vertex) for every entry in
+// order.  A vertex equal to an earlier one (LessVec3's equivalence: numeric equality per component, so -0 is +0) gets
+// that one's index; a new one gets the next index and is stored as (x, y, z, 1) with the bits of its FIRST occurrence.
+// std::map there, here an open-addressing table keyed by the canonical bits: the first thread to claim a slot only
+// fixes WHICH key the slot holds; the smallest index among the slot's vertices is the representative (atomicMin), and
+// a prefix scan over "is its own representative" numbers the unique vertices in first-occurrence order.
+// ------------------------------------------------------------------------------------------------
+
+constexpr uint32_t kWeldEmpty = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t WeldBits(float v)
+{
+	return v == 0.0f ? 0u : __float_as_uint(v);
+}
+
+__global__ void __launch_bounds__(256) WeldInsertKernel(const float* __restrict__ vertices, uint32_t count, uint32_t* owner, uint32_t* smallest, uint32_t mask,
+	uint32_t* __restrict__ slot_of)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count) return;
+	const uint32_t kx = WeldBits(vertices[size_t(i) * 3 + 0]), ky = WeldBits(vertices[size_t(i) * 3 + 1]), kz = WeldBits(vertices[size_t(i) * 3 + 2]);
+	uint32_t h = kx * 0x9E3779B1u;
+	h = (h ^ (h >> 15) ^ ky) * 0x85EBCA77u;
+	h = (h ^ (h >> 13) ^ kz) * 0xC2B2AE3Du;
+	h ^= h >> 16;
+	for (uint32_t slot = h & mask;; slot = (slot + 1u) & mask)
+	{
+		uint32_t holder = atomicCAS(&owner[slot], kWeldEmpty, i);
+		if (holder == kWeldEmpty) holder = i;
+		if (holder == i || (WeldBits(vertices[size_t(holder) * 3 + 0]) == kx && WeldBits(vertices[size_t(holder) * 3 + 1]) == ky && WeldBits(vertices[size_t(holder) * 3 + 2]) == kz))
+		{
+			atomicMin(&smallest[slot], i);
+			slot_of[i] = slot;
+			return;
+		}
+	}
+}
+
+struct LoadWeldFirst
+{
+	const uint32_t* slot_of;
+	const uint32_t* smallest;
+	__device__ uint32_t operator()(size_t i) const { return smallest[slot_of[i]] == uint32_t(i) ? 1u : 0u; }
+};
+
+__global__ void __launch_bounds__(256) WeldEmitKernel(const float* __restrict__ vertices, uint32_t count, const uint32_t* __restrict__ slot_of, const uint32_t* __restrict__ smallest,
+	const uint32_t* __restrict__ prefix, float4* __restrict__ out_vertices, uint32_t* __restrict__ out_indices)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count) return;
+	const uint32_t representative = smallest[slot_of[i]];
+	const uint32_t index = prefix[representative];
+	out_indices[i] = index;
+	if (representative == i) out_vertices[index] = make_float4(vertices[size_t(i) * 3 + 0], vertices[size_t(i) * 3 + 1], vertices[size_t(i) * 3 + 2], 1.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4: refinement + normal + colour
 // ------------------------------------------------------------------------------------------------
 
@@ -3685,6 +3742,53 @@ int EngineRayMarch(Model* model, const float* rays, uint64_t count, int max_iter
 	TG_CUDA(cudaGetLastError());
 	TG_CUDA(cudaMemcpyAsync(out5, d_out, size_t(count) * 20, cudaMemcpyDeviceToHost, stream));
 	TG_CUDA(cudaStreamSynchronize(stream));
+	return TG_OK;
+}
+
+int EngineWeld(Context* ctx, const float* vertices, uint64_t count, float* out_vertices4, uint32_t* out_indices, uint64_t* out_unique, std::string& error)
+{
+	*out_unique = 0;
+	if (count == 0) return TG_OK;
+	if (count > 0x3FFFFFF0ull)
+	{
+		error = "too many vertices for one weld";
+		return TG_ERR_INVALID;
+	}
+	TG_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t stream = StreamOf(ctx);
+	Scratch scratch(ctx);
+	uint32_t table = 1024;
+	while (table < 2 * count) table <<= 1;
+	float* d_vertices = nullptr;
+	float4* d_out = nullptr;
+	uint32_t *d_owner = nullptr, *d_smallest = nullptr, *d_slot = nullptr, *d_prefix = nullptr, *d_indices = nullptr;
+	unsigned long long* d_total = nullptr;
+	TG_CUDA(scratch.Alloc(&d_vertices, size_t(count) * 3));
+	TG_CUDA(scratch.Alloc(&d_out, size_t(count)));
+	TG_CUDA(scratch.Alloc(&d_owner, size_t(table)));
+	TG_CUDA(scratch.Alloc(&d_smallest, size_t(table)));
+	TG_CUDA(scratch.Alloc(&d_slot, size_t(count)));
+	TG_CUDA(scratch.Alloc(&d_prefix, size_t(count)));
+	TG_CUDA(scratch.Alloc(&d_indices, size_t(count)));
+	TG_CUDA(scratch.Alloc(&d_total, 1));
+	TG_CUDA(cudaMemcpyAsync(d_vertices, vertices, size_t(count) * 12, cudaMemcpyHostToDevice, stream));
+	TG_CUDA(cudaMemsetAsync(d_owner, 0xFF, size_t(table) * 4, stream));
+	TG_CUDA(cudaMemsetAsync(d_smallest, 0xFF, size_t(table) * 4, stream));
+	const uint32_t n = uint32_t(count), blocks = (n + 255u) / 256u;
+	WeldInsertKernel<<<blocks, 256, 0, stream>>>(d_vertices, n, d_owner, d_smallest, table - 1u, d_slot);
+	TG_CUDA(cudaGetLastError());
+	uint64_t launches = 0;
+	const LoadWeldFirst first{ d_slot, d_smallest };
+	const int rc = DeviceExclusiveScan(stream, scratch, first, size_t(count), d_prefix, d_total, launches, error);
+	if (rc != TG_OK) return rc;
+	WeldEmitKernel<<<blocks, 256, 0, stream>>>(d_vertices, n, d_slot, d_smallest, d_prefix, d_out, d_indices);
+	TG_CUDA(cudaGetLastError());
+	unsigned long long unique = 0;
+	TG_CUDA(cudaMemcpyAsync(&unique, d_total, 8, cudaMemcpyDeviceToHost, stream));
+	TG_CUDA(cudaMemcpyAsync(out_indices, d_indices, size_t(count) * 4, cudaMemcpyDeviceToHost, stream));
+	TG_CUDA(cudaStreamSynchronize(stream));
+	if (unique) TG_CUDA(cudaMemcpy(out_vertices4, d_out, size_t(unique) * 16, cudaMemcpyDeviceToHost));
+	*out_unique = unique;
 	return TG_OK;
 }
 

@@ -156,6 +156,7 @@ struct MeshResultDevice; // opaque device-side result kept alive by tg_mesh.opaq
 int EngineEvalPoints(Model* model, int mode, const float* points, uint64_t count, void* out, std::string& error);
 // K0's cooperative evaluation of long programs against the plain interpreter: out = { probes, block mismatches, warp mismatches }.
 int EngineCheckLongPrograms(Model* model, float reach, uint64_t out[3], std::string& error);
+int EngineWeld(Context* ctx, const float* vertices, uint64_t count, float* out_vertices4, uint32_t* out_indices, uint64_t* out_unique, std::string& error);
 int EngineRayMarch(Model* model, const float* rays, uint64_t count, int max_iterations, float epsilon, int magnet, float* out5, std::string& error);
 int EngineEvalLattice(Model* model, const tg_grid& grid, uint32_t flags, float* out, float* out_ms, std::string& error);
 int EngineExportMesh(Model* model, const tg_grid& grid, const tg_mesh_options& options, tg_mesh* out, std::string& error);

@@ -69,6 +69,8 @@ def lib():
         L.tgo_octree_create_live.argtypes = [vp, C.c_float]
         L.tgo_live_grid.argtypes = [vp, C.c_float, C.POINTER(Grid)]
         L.tgo_live_grid.restype = None
+        L.tgo_weld.restype = C.c_uint64
+        L.tgo_weld.argtypes = [fp, C.c_uint64, fp, C.POINTER(C.c_uint32)]
         L.tgo_octree_free.argtypes = [vp]
         L.tgo_octree_stats.argtypes = [vp, C.POINTER(_Stats)]
         L.tgo_eval_octree.argtypes = [vp, fp, C.c_uint64, fp, C.c_int]
@@ -258,6 +260,26 @@ def have_ref():
 
 def ref_run(*args):
     return subprocess.run([REF_TOOL] + [str(a) for a in args], check=True, capture_output=True, text=True).stdout
+
+
+def weld(vertices):
+    """MeshGenerator::Accumulate over a vertex stream (oracle): (distinct vertices (n, 4), index per input vertex)."""
+    v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+    out = np.zeros((max(len(v), 1), 4), np.float32)
+    idx = np.zeros(max(len(v), 1), np.uint32)
+    n = lib().tgo_weld(_fp(v), len(v), _fp(out), idx.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return out[:n].copy(), idx[:len(v)].copy()
+
+
+def ref_weld(vertices, tmpdir):
+    """The reference's own MeshGenerator (oracle/_ref/tangerine_ref weld)."""
+    v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+    pin, pout = os.path.join(str(tmpdir), "weld_in.f32"), os.path.join(str(tmpdir), "weld_out.bin")
+    v.tofile(pin)
+    subprocess.run([REF_TOOL, "weld", pin, pout], check=True)
+    raw = open(pout, "rb").read()
+    n = int(np.frombuffer(raw[:4], np.uint32)[0])
+    return np.frombuffer(raw[4:4 + 16 * n], np.float32).reshape(-1, 4).copy(), np.frombuffer(raw[4 + 16 * n:], np.uint32).copy()
 
 
 def ref_eval(model, mode, pts, tmpdir):
