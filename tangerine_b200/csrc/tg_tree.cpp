@@ -267,7 +267,8 @@ uint32_t NodePool::ClipRec(uint32_t index, Vec3 point, float radius, float* top_
 			uint32_t nr = ClipRec(rhs, point, radius + threshold, nullptr);
 			if (nl != kNoNode && nr != kNoNode)
 			{
-				return AddSet(kind, nl, nr, threshold);
+				// (both operands came through whole: the node the reference would build anew is this very node)
+				return (nl == lhs && nr == rhs) ? index : AddSet(kind, nl, nr, threshold);
 			}
 			if (family == Family::Inter)
 			{
@@ -278,7 +279,7 @@ uint32_t NodePool::ClipRec(uint32_t index, Vec3 point, float radius, float* top_
 		uint32_t nr = ClipRec(rhs, point, radius, nullptr);
 		if (nl != kNoNode && nr != kNoNode)
 		{
-			return AddSet(kind, nl, nr, threshold);
+			return (nl == lhs && nr == rhs) ? index : AddSet(kind, nl, nr, threshold);
 		}
 		if (family == Family::Union)
 		{
@@ -300,11 +301,11 @@ uint32_t NodePool::ClipRec(uint32_t index, Vec3 point, float radius, float* top_
 		}
 		const float flate = nodes[index].params[0];
 		uint32_t child = ClipRec(nodes[index].a, point, radius + flate, nullptr);
-		return child == kNoNode ? kNoNode : AddFlate(child, flate);
+		return child == kNoNode ? kNoNode : (child == nodes[index].a ? index : AddFlate(child, flate));
 	}
 	if (top_value) *top_value = EvalMemo(index, point);
 	uint32_t child = ClipRec(nodes[index].a, point, radius, nullptr);
-	return child == kNoNode ? kNoNode : AddStencil(kind, child, nodes[index].b, nodes[index].material);
+	return child == kNoNode ? kNoNode : (child == nodes[index].a ? index : AddStencil(kind, child, nodes[index].b, nodes[index].material));
 }
 
 // operator== of the node classes (:564-579, :696-709, :1029-1037, :1150-1154)
