@@ -41,6 +41,8 @@ enum Counter
 	kCntHalo = 7,
 	kCntBrickCursor = 8,
 	kCntAttrCursor = 9,
+	kCntSlots = 10,    // -DTG_COUNT_SLOTS: sample slots the interpreter dispatches covered (64 per dispatch)
+	kCntTailSlots = 11, // ... of which in dispatches that held 32 samples or fewer
 	kCntCount = 16
 };
 
@@ -213,6 +215,13 @@ __device__ __forceinline__ void EvaluateTile(WarpTile& w, const DeviceModel& mod
 				for (int done = 0; done < total; done += 32 * kLaneSamples)
 				{
 					const int count_here = min(total - done, 32 * kLaneSamples);
+#ifdef TG_COUNT_SLOTS
+					if (lane == 0)
+					{
+						atomicAdd(&counters[kCntSlots], (unsigned long long)(32 * kLaneSamples));
+						if (count_here <= 32) atomicAdd(&counters[kCntTailSlots], (unsigned long long)(32 * kLaneSamples));
+					}
+#endif
 					float px[kLaneSamples], py[kLaneSamples], pz[kLaneSamples], d[kLaneSamples];
 					int sample[kLaneSamples];
 #pragma unroll

@@ -3040,6 +3040,10 @@ static int FinishJob(MeshJob& job, const MeshCounts& counts, tg_mesh* out, std::
 	tm.bricks_evaluated = std::min<unsigned long long>(mb.counters[kCntListA], job.list_capacity);
 	tm.samples_evaluated = tm.bricks_evaluated ? mb.counters[kCntSamples] : 0;
 	tm.algorithmic_flops = tm.bricks_evaluated ? mb.counters[kCntFlops] : 0;
+#ifdef TG_COUNT_SLOTS
+	std::fprintf(stderr, "interpreter dispatches: %llu samples in %llu slots (%.1f %% used), %llu slots in dispatches of <= 32 samples\n", (unsigned long long)mb.counters[kCntSamples],
+		(unsigned long long)mb.counters[kCntSlots], 100.0 * double(mb.counters[kCntSamples]) / double(std::max<unsigned long long>(mb.counters[kCntSlots], 1)), (unsigned long long)mb.counters[kCntTailSlots]);
+#endif
 	tm.kernel_launches = job.launches;
 	out->vertex_count = counts.vertices;
 	out->triangle_count = counts.quads * 2;
