@@ -265,7 +265,7 @@ std::vector<double> EstimateLayerCost(const FlatModel& flat, const tg_grid& grid
 	const double gmin[3] = { grid.x, grid.y, grid.z };
 	const double step[3] = { grid.dx, grid.dy, grid.dz };
 	const double size[3] = { double(grid.sx), double(grid.sy), double(grid.sz) };
-	double constant = 400.0;
+	double constant = 1600.0; // (with the straddle weight below: swept at 4 and 8 GPUs on seaside_town 1024^3, profiles/r2_plan_sweep.txt)
 	if (const char* env = std::getenv("TG_PLAN_CONSTANT")) constant = std::atof(env);
 	const bool have_masks = flat.leaf_mask.size() == flat.leaf_nodes.size();
 	for (size_t leaf = 0; leaf < flat.leaf_nodes.size(); ++leaf)
@@ -275,10 +275,11 @@ std::vector<double> EstimateLayerCost(const FlatModel& flat, const tg_grid& grid
 		if (mask == 0ull) continue;
 		const double quarter = double(flat.leaf_span[leaf]) * 0.25;
 		// A brick that straddles octree cells runs one batch per cell (fewer samples per interpreter dispatch, more box
-		// resolution): measured on seaside_town, bricks among 16-cell leaves cost about a third more per FLOP than bricks
-		// inside large coalesced cells.  (1 + 8 / cells per leaf side) is the mean number of cells a brick meets per axis.
+		// resolution), and small cells mean many primitives: longer programs for K0 and the attribute pass, which the FLOPs of
+		// the evaluated program do not show.  (1 + 8 / cells per leaf side) is the mean number of cells a brick meets per
+		// axis; the weight is fitted.
 		const double leaf_cells = std::max(1.0, double(flat.leaf_span[leaf]) / step[0]);
-		double straddle = 1.0 + 1.5 * double(kBrick) / leaf_cells;
+		double straddle = 1.0 + 3.0 * double(kBrick) / leaf_cells;
 		if (const char* env = std::getenv("TG_PLAN_STRADDLE")) straddle = 1.0 + std::atof(env) * double(kBrick) / leaf_cells;
 		const double per_brick = (double(node.flops) + constant) * straddle;
 		for (int sz = 0; sz < 4; ++sz)
