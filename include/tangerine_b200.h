@@ -161,6 +161,9 @@ TG_API tg_model* tg_model_create_live(tg_context* context, const tg_tree* tree, 
 /* Host half of tg_model_create only (octree build + flattening, no device needed): fills the octree_*,
  * reference_*, max_stack, bounds, has_paint, leaf_count and build_seconds fields. */
 TG_API int tg_tree_octree_stats(const tg_tree* tree, float octree_target_size, int host_threads, tg_model_stats* out);
+/* The same for the live mesher's octree (tg_model_create_live); bounds_min / bounds_max are then the octree's own Bounds,
+ * from which tg_live_grid makes its grid. */
+TG_API int tg_tree_octree_stats_live(const tg_tree* tree, float octree_target_size, int host_threads, tg_model_stats* out);
 TG_API void tg_model_destroy(tg_model* model);
 /* Copies the model's tables (octree nodes, both instruction streams, material colours) host -> device again.
  * tg_model_create already did this once; bench.py calls it inside its end-to-end timed region. */

@@ -393,12 +393,14 @@ struct OctreeStats
 
 // Pre-order walk; per node hashes (pivot, terminus, child mask, program words).  With Dump set,
 // writes the same fields as: f32 pivot[3], u32 terminus, u32 childmask, u32 nwords, u32 words[].
+// A child without evaluator (a node of the live octree that was populated after its parent and lost everything,
+// sdf_evaluator.cpp:1751-1757) is as good as absent -- Descend finds nothing in it either way (:1801-1835) -- and is skipped.
 static void WalkOctree(SDFOctree* Node, OctreeStats& Stats)
 {
 	uint32_t ChildMask = 0;
 	for (int i = 0; i < 8; ++i)
 	{
-		if (Node->Children[i]) ChildMask |= (1u << i);
+		if (Node->Children[i] && Node->Children[i]->Evaluator) ChildMask |= (1u << i);
 	}
 	uint32_t Terminus = Node->Terminus ? 1 : 0;
 	const std::vector<ProgramBuffer::Word>& Words = Node->Interpreter->Program.Words;
@@ -430,7 +432,7 @@ static void WalkOctree(SDFOctree* Node, OctreeStats& Stats)
 	}
 	for (int i = 0; i < 8; ++i)
 	{
-		if (Node->Children[i]) WalkOctree(Node->Children[i], Stats);
+		if (Node->Children[i] && Node->Children[i]->Evaluator) WalkOctree(Node->Children[i], Stats);
 	}
 }
 
@@ -470,6 +472,7 @@ static int Usage()
 		"usage: tangerine_ref <command> ...\n"
 		"  dump-tgm  <model.lua|.tgm> <out.tgm>\n"
 		"  info      <model>                                  bounds / tree / octree statistics + hash (JSON)\n"
+		"  info-live <model>                                  the same for the live mesher's octree (bounds = the octree's Bounds)\n"
 		"  octree    <model> <out.bin>                        dump every octree node's pruned program\n"
 		"  eval      <model> <mode> <points.f32> <out.bin>    mode: octree | tree | interp | gradient | color | live | live-gradient | raycast | magnet (6 floats per ray)\n"
 		"  export    <model> <cells_per_unit> <refine> <out.ply|.stl>   reference ExportCommon (as shipped)\n"
@@ -483,13 +486,17 @@ static int Usage()
 }
 
 
-static int CmdInfo(SDFNodeShared Tree)
+static SDFOctreeShared CreateLiveOctree(SDFNodeShared Tree);
+
+// Live: the live mesher's octree (CreateLiveOctree); bounds are then the octree's own Bounds, which its grid comes from.
+static int CmdInfo(SDFNodeShared Tree, bool Live = false)
 {
 	AABB Bounds = Tree->Bounds();
 	SDFInterpreter Root(Tree);
 	auto T0 = Clock::now();
-	SDFOctreeShared Octree = SDFOctree::Create(Tree, 0.25);
+	SDFOctreeShared Octree = Live ? CreateLiveOctree(Tree) : SDFOctree::Create(Tree, 0.25);
 	auto T1 = Clock::now();
+	if (Live && Octree) Bounds = Octree->Bounds;
 	OctreeStats Stats;
 	if (Octree)
 	{
@@ -1149,6 +1156,10 @@ int main(int Argc, char** Argv)
 	else if (Command == "info")
 	{
 		return CmdInfo(Tree);
+	}
+	else if (Command == "info-live")
+	{
+		return CmdInfo(Tree, true);
 	}
 	else if (Command == "octree" && Argc == 4)
 	{

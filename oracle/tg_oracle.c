@@ -1165,7 +1165,8 @@ static void oct_walk(const TgoOctree* o, int32_t index, TgoOctreeStats* s)
 {
 	const OctNode* n = &o->nodes[index];
 	uint32_t mask = 0;
-	for (int i = 0; i < 8; ++i) if (n->children[i] >= 0) mask |= 1u << i;
+	/* (a child without evaluator -- possible only in a live octree -- is as good as absent, as in ref_tool.cpp WalkOctree) */
+	for (int i = 0; i < 8; ++i) if (n->children[i] >= 0 && o->nodes[n->children[i]].evaluator != NONE) mask |= 1u << i;
 	uint32_t terminus = n->terminus ? 1 : 0;
 	uint32_t words = (uint32_t)n->prog_count;
 	s->nodes++;
@@ -1184,7 +1185,15 @@ static void oct_walk(const TgoOctree* o, int32_t index, TgoOctreeStats* s)
 	node_hash = fnv(node_hash, &mask, 4);
 	node_hash = fnv(node_hash, o->programs.words + n->prog_offset, words * 4);
 	s->hash = fnv(s->hash, &node_hash, 8);
-	for (int i = 0; i < 8; ++i) if (n->children[i] >= 0) oct_walk(o, n->children[i], s);
+	for (int i = 0; i < 8; ++i) if (n->children[i] >= 0 && o->nodes[n->children[i]].evaluator != NONE) oct_walk(o, n->children[i], s);
+}
+
+/* SDFOctree::Bounds of the root (what the live mesher's grid is made from) */
+void tgo_octree_bounds(const TgoOctree* o, float out_min[3], float out_max[3])
+{
+	const AABB b = o->nodes[o->root].bounds;
+	out_min[0] = b.min.x; out_min[1] = b.min.y; out_min[2] = b.min.z;
+	out_max[0] = b.max.x; out_max[1] = b.max.y; out_max[2] = b.max.z;
 }
 
 void tgo_octree_stats(const TgoOctree* o, TgoOctreeStats* out)

@@ -60,6 +60,7 @@ TgoOctree* tgo_octree_create(const TgoModel* model, float target_size);
 TgoOctree* tgo_octree_create_live(const TgoModel* model, float target_size);
 void tgo_octree_free(TgoOctree* octree);
 void tgo_octree_stats(const TgoOctree* octree, TgoOctreeStats* out);
+void tgo_octree_bounds(const TgoOctree* octree, float out_min[3], float out_max[3]);
 
 /* SDFOctree::Eval (interpreter of the node picked by Descend), SDFNode::Eval on the root tree,
  * SDFInterpreter::Eval on the root program, SDFOctree::Gradient, export colour bytes. */

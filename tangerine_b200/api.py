@@ -149,6 +149,7 @@ def lib():
         "tg_rearm": (i32, [vp]),
         "tg_weld": (i32, [vp, C.POINTER(C.c_float), u64, C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(u64)]),
         "tg_tree_octree_stats": (i32, [vp, C.c_float, i32, C.POINTER(ModelStats)]),
+        "tg_tree_octree_stats_live": (i32, [vp, C.c_float, i32, C.POINTER(ModelStats)]),
         "tg_model_destroy": (None, [vp]),
         "tg_tree_plan_slabs": (i32, [vp, C.c_float, C.POINTER(Grid), i32, C.POINTER(u64), C.POINTER(C.c_double)]),
         "tg_model_get_stats": (i32, [vp, C.POINTER(ModelStats)]),
@@ -355,9 +356,10 @@ class Tree:
         _check(lib().tg_tree_plan_slabs(self.h, target_size, C.byref(grid), ranks, cuts, cost.ctypes.data_as(C.POINTER(C.c_double))))
         return [int(c) for c in cuts], cost
 
-    def octree_stats(self, target_size=0.25, threads=0):
+    def octree_stats(self, target_size=0.25, threads=0, live=False):
+        """live=True: the live mesher's octree; bounds_min / bounds_max are then the octree's own Bounds."""
         s = ModelStats()
-        _check(lib().tg_tree_octree_stats(self.h, target_size, threads, C.byref(s)))
+        _check((lib().tg_tree_octree_stats_live if live else lib().tg_tree_octree_stats)(self.h, target_size, threads, C.byref(s)))
         return s.as_dict()
 
 

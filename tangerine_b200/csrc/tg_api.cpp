@@ -569,20 +569,36 @@ static void FillStats(const FlatModel& f, tg_model_stats* out)
 	out->has_paint = f.has_paint ? 1 : 0;
 }
 
-int tg_tree_octree_stats(const tg_tree* tree, float target_size, int host_threads, tg_model_stats* out) try
+static int TreeOctreeStats(const tg_tree* tree, float target_size, int host_threads, bool live, tg_model_stats* out)
 {
 	TG_REQUIRE_TREE(tree);
 	if (!out) return Fail(TG_ERR_INVALID, "null argument");
 	if (!(target_size > 0.0f)) target_size = 0.25f;
 	FlatModel flat;
 	std::string error;
-	if (!BuildFlatModel(tree->tree, target_size, host_threads, flat, error))
+	if (!BuildFlatModel(tree->tree, target_size, host_threads, flat, error, true, !live))
 	{
 		return Fail(error.find("deeper") != std::string::npos ? TG_ERR_UNSUPPORTED : TG_ERR_INVALID, error);
 	}
 	FillStats(flat, out);
+	if (live)
+	{
+		out->bounds_min[0] = flat.live_bounds.min.x; out->bounds_min[1] = flat.live_bounds.min.y; out->bounds_min[2] = flat.live_bounds.min.z;
+		out->bounds_max[0] = flat.live_bounds.max.x; out->bounds_max[1] = flat.live_bounds.max.y; out->bounds_max[2] = flat.live_bounds.max.z;
+	}
 	out->leaf_count = tree->tree.LeafCount();
 	return TG_OK;
+}
+
+int tg_tree_octree_stats(const tg_tree* tree, float target_size, int host_threads, tg_model_stats* out) try
+{
+	return TreeOctreeStats(tree, target_size, host_threads, false, out);
+}
+TG_CATCH_STATUS
+
+int tg_tree_octree_stats_live(const tg_tree* tree, float target_size, int host_threads, tg_model_stats* out) try
+{
+	return TreeOctreeStats(tree, target_size, host_threads, true, out);
 }
 TG_CATCH_STATUS
 

@@ -5,6 +5,7 @@
                              false), -100, 100) on the octree of SDFOctree::Create(Evaluator, .25, false, 3, 0.0) with its
                              incomplete nodes populated -- at the seeded points of <model>.npz (`tangerine_ref eval live`),
                              and SDFOctree::Gradient on that octree (`live-gradient`, the live mesher's normals, :816)
+  live_octree.json           per model: the live octree's statistics, hash (pre-order, as in manifest.json) and Bounds
   slices_live_<case>.json    per cell layer digests of the mesh of NaiveSurfaceNets' vertex and face loops over the point
                              cache of the octree leaves (:609-760) at a meshing density (`tangerine_ref slices-live`), with
                              the grid of NaiveSurfaceNetsScratch (:153-179)
@@ -40,6 +41,14 @@ def main():
         arrays[name + "/live_gradient"] = O.ref_eval(O.model_path(name), "live-gradient", pts, tmp)
         print(name, len(pts), int((arrays[name + "/live"] == 100.0).sum()), "samples at +100", flush=True)
     np.savez_compressed(os.path.join(HERE, "live.npz"), **arrays)
+    # the live octree itself (`tangerine_ref info-live`): node / leaf counts, program words, hash, and the octree's Bounds
+    octrees = {}
+    for name in MODELS + ["synthetic200"]:
+        info = json.loads(O.ref_run("info-live", O.model_path(name)))
+        info.pop("octree_build_s")
+        octrees[name] = info
+    with open(os.path.join(HERE, "live_octree.json"), "w") as f:
+        json.dump(octrees, f, indent=1, sort_keys=True)
     threads = os.cpu_count() or 1
     for case, (name, density) in CASES.items():
         out = os.path.join(HERE, "slices_live_%s.json" % case)

@@ -73,6 +73,8 @@ def lib():
         L.tgo_weld.argtypes = [fp, C.c_uint64, fp, C.POINTER(C.c_uint32)]
         L.tgo_octree_free.argtypes = [vp]
         L.tgo_octree_stats.argtypes = [vp, C.POINTER(_Stats)]
+        L.tgo_octree_bounds.argtypes = [vp, fp, fp]
+        L.tgo_octree_bounds.restype = None
         L.tgo_eval_octree.argtypes = [vp, fp, C.c_uint64, fp, C.c_int]
         L.tgo_eval_tree.argtypes = [vp, fp, C.c_uint64, fp, C.c_int]
         L.tgo_ray_march.argtypes = [vp, fp, C.c_uint64, C.c_int, C.c_float, C.c_int, fp]
@@ -173,6 +175,11 @@ class Octree:
         self.h = (lib().tgo_octree_create_live if live else lib().tgo_octree_create)(model.h, target_size)
         if not self.h:
             raise ValueError("octree could not be built")
+
+    def bounds(self):
+        lo, hi = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        lib().tgo_octree_bounds(self.h, _fp(lo), _fp(hi))
+        return lo, hi
 
     def live_grid(self, density=20.0):
         g = Grid()

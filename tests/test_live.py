@@ -55,3 +55,28 @@ def test_oracle_live_mesh_matches_the_reference_layer_by_layer(case):
     verts, cells, tris = oc.surface_nets(grid)
     layers, v, t, bad = layer_report(verts, oc.gradient(verts), None, tris, fx)
     assert (v, t) == (fx["vertices"], fx["triangles"]) and not bad, bad[:10]
+
+
+@pytest.fixture(scope="module")
+def live_octrees():
+    with open(os.path.join(HERE, "golden", "live_octree.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", MODELS + ["synthetic200"])
+def test_live_octree_of_library_and_oracle_match_the_reference(name, live_octrees):
+    """The host octree builder with coalesce = false (tg_model_create_live's octree, no device needed) and the oracle's
+    two-step construction against `tangerine_ref info-live`: nodes, leaves, program words, hash and the octree's Bounds."""
+    import tangerine_b200 as T
+    info = live_octrees[name]
+    for threads in (1, 4):
+        s = T.Tree.load(O.model_path(name)).octree_stats(0.25, threads, live=True)
+        assert s["octree_hash"] == info["octree_hash"]
+        assert (s["octree_nodes"], s["octree_leaves"], s["reference_words"]) == (info["octree_nodes"], info["octree_leaves"], info["octree_words"])
+        assert [np.float32(v) for v in s["bounds_min"]] == [np.float32(v) for v in info["bounds_min"]]
+        assert [np.float32(v) for v in s["bounds_max"]] == [np.float32(v) for v in info["bounds_max"]]
+    oc = O.Octree(O.Model(name), live=True)
+    stats = oc.stats()
+    assert stats["hash"] == info["octree_hash"] and stats["nodes"] == info["octree_nodes"]
+    lo, hi = oc.bounds()
+    assert [np.float32(v) for v in lo] == [np.float32(v) for v in info["bounds_min"]] and [np.float32(v) for v in hi] == [np.float32(v) for v in info["bounds_max"]]
