@@ -1,6 +1,10 @@
 // See tg_octree.h.  Line references are to the reference's tangerine/sdf_evaluator.cpp.
 #include "tg_octree.h"
 
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
+
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -45,6 +49,20 @@ struct Subtree
 	std::vector<std::unique_ptr<Subtree>> spawned;
 	int32_t root = -1;
 };
+
+// madvise(MADV_HUGEPAGE) on the 2 MB-aligned part of a freshly reserved buffer (no-op where the kernel offers none).
+static void AdviseHugePages(const void* data, size_t bytes)
+{
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+	const uintptr_t huge = uintptr_t(2) << 20;
+	const uintptr_t begin = (reinterpret_cast<uintptr_t>(data) + huge - 1) & ~(huge - 1);
+	const uintptr_t end = (reinterpret_cast<uintptr_t>(data) + bytes) & ~(huge - 1);
+	if (end > begin) madvise(reinterpret_cast<void*>(begin), size_t(end - begin), MADV_HUGEPAGE);
+#else
+	(void)data;
+	(void)bytes;
+#endif
+}
 
 static size_t CountBuildNodes(const Subtree& st)
 {
@@ -135,8 +153,11 @@ struct Builder
 	bool live_any = false;
 	// A node hands its eight octants to the task pool when its pruned tree still has this many brushes (below that a
 	// task's bookkeeping costs more than the octant) and it is not too deep.
-	static constexpr int kSpawnLeaves = 12;
-	static constexpr int kSpawnDepth = 7;
+	static constexpr int kSpawnLeaves = 100;
+	static constexpr int kSpawnDepth = 5;
+	// ... and near the root whenever there is anything to split: models of few brushes have deep octrees too
+	static constexpr int kSpawnAlwaysLeaves = 4;
+	static constexpr int kSpawnAlwaysDepth = 3;
 
 	// SDFOctree::SDFOctree :1641-1700 with Coalesce = true, MaxDepth = -1 (what MeshExportThread asks for)
 	int32_t Construct(Subtree& st, uint32_t in_evaluator, Box3 bounds, int depth)
@@ -185,17 +206,60 @@ struct Builder
 		return cb;
 	}
 
+	// Whether the node of `bounds` -- already clipped to `evaluator` -- would keep its evaluator: a node lives when its
+	// span is at most the target size, or when any of its octants clips to something that lives (:1649-1661, :1740-1757).
+	bool AnyLive(NodePool& pool, uint32_t evaluator, const Box3& bounds) const
+	{
+		const Vec3 extent = bounds.max - bounds.min;
+		const float span = std::fmax(std::fmax(extent.x, extent.y), extent.z);
+		if (span <= target_size) return true;
+		const Vec3 pivot = Vec3(float(span * 0.5)) + bounds.min;
+		for (int i = 0; i < 8; ++i)
+		{
+			const Box3 cb = Octant(bounds, pivot, i);
+			const Vec3 ce = cb.max - cb.min;
+			const float cs = std::fmax(std::fmax(ce.x, ce.y), ce.z);
+			const Vec3 cp = Vec3(float(cs * 0.5)) + cb.min;
+			const float cr = float(Length(Vec3(cs)) * 0.5);
+			const uint32_t child = pool.Clip(evaluator, cp, cr, nullptr);
+			if (child != kNoNode && AnyLive(pool, child, cb)) return true;
+		}
+		return false;
+	}
+
 	// SDFOctree::Populate :1703-1783
 	void Populate(Subtree& st, int32_t self, int depth)
 	{
 		const Box3 bounds = st.nodes[self].bounds;
 		const Vec3 pivot = st.nodes[self].pivot;
 		const uint32_t evaluator = st.nodes[self].evaluator;
+		if (coalesce && st.nodes[self].evaluator_leaves <= (depth > 3 ? depth : 3))
+		{
+			// This node coalesces whatever its children turn out to be (:1769: EvaluatorLeaves <= max(Depth, 3)) -- unless
+			// none of them lives, in which case it dies (:1751-1757).  Only that question is answered here: the reference
+			// builds the whole subtree below such a node and then deletes it (six nodes in seven of seaside_town's).
+			BuildNode& n = st.nodes[self];
+			bool any = false;
+			for (int i = 0; i < 8 && !any; ++i)
+			{
+				const Box3 cb = Octant(bounds, pivot, i);
+				const Vec3 ce = cb.max - cb.min;
+				const float cs = std::fmax(std::fmax(ce.x, ce.y), ce.z);
+				const Vec3 cp = Vec3(float(cs * 0.5)) + cb.min;
+				const float cr = float(Length(Vec3(cs)) * 0.5);
+				const uint32_t child = st.pool.Clip(evaluator, cp, cr, nullptr);
+				any = child != kNoNode && AnyLive(st.pool, child, cb);
+			}
+			if (!any) n.evaluator = kNoNode;
+			n.terminus = true;
+			return;
+		}
 		bool uniform = true;
 		bool penultimate = true;
 		int live = 0;
 
-		if (tasks && depth <= kSpawnDepth && st.nodes[self].evaluator_leaves >= kSpawnLeaves)
+		const int leaves_here = st.nodes[self].evaluator_leaves;
+		if (tasks && ((depth <= kSpawnDepth && leaves_here >= kSpawnLeaves) || (depth <= kSpawnAlwaysDepth && leaves_here >= kSpawnAlwaysLeaves)))
 		{
 			// Each octant prunes in a pool of its own laid over this one (NodePool::Overlay: nothing is copied).  This pool
 			// does not grow while they run: its owner -- this thread -- only helps with other tasks until they are done.
@@ -295,11 +359,14 @@ struct StreamGen
 	int max_slots = 0;  // deepest spill slot used + 1
 	uint32_t flops = 0;
 	bool cullable = true;
-	std::vector<uint32_t> starts; // kStreamInterp: quad offset of every instruction (Stop excluded), relative to the first
+	std::vector<uint32_t> own_starts;
+	std::vector<uint32_t>& starts; // kStreamInterp: quad offset of every instruction (Stop excluded), relative to the first
 	const Mat4* inverse = nullptr; // CompiledInverseMatrix per brush node (optional), see NodePool::CompileReference
 	uint32_t inverse_count = 0;
 
-	StreamGen(const NodePool& p, std::vector<uint32_t>& o, bool tree) : pool(p), out(o), tree_stream(tree) {}
+	StreamGen(const NodePool& p, std::vector<uint32_t>& o, bool tree) : pool(p), out(o), tree_stream(tree), starts(own_starts) {}
+	// (with a caller's vector for the offsets: a generator per octree node must not allocate one each)
+	StreamGen(const NodePool& p, std::vector<uint32_t>& o, bool tree, std::vector<uint32_t>& offsets) : pool(p), out(o), tree_stream(tree), starts(offsets) { starts.clear(); }
 
 	void PushF(float f) { out.push_back(FloatBits(f)); }
 
@@ -627,8 +694,10 @@ struct Flattener
 	{
 		const Subtree& st = *job.st;
 		const BuildNode& bn = st.nodes[job.index];
-		std::vector<uint32_t> program;
-		StreamGen interp(st.pool, program, false);
+		// (scratch vectors live per thread: six allocations per node were a fifth of a large octree's flattening)
+		static thread_local std::vector<uint32_t> program, offsets, ref_words;
+		program.clear();
+		StreamGen interp(st.pool, program, false, offsets);
 		interp.inverse = inverse.data();
 		interp.inverse_count = uint32_t(inverse.size());
 		interp.Gen(bn.evaluator);
@@ -646,7 +715,9 @@ struct Flattener
 			while (job.interp.size() % 4 != 0) job.interp.push_back(0);
 		}
 		job.interp_program_at = uint32_t(job.interp.size());
+		job.interp.reserve(job.interp.size() + program.size());
 		job.interp.insert(job.interp.end(), program.begin(), program.end());
+		job.tree.reserve(program.size());
 		StreamGen tree(st.pool, job.tree, true);
 		tree.Gen(bn.evaluator);
 		tree.Finish();
@@ -656,7 +727,7 @@ struct Flattener
 		job.material = UniformMaterial(st.pool, bn.evaluator);
 		if (!reference_stats) return;
 		// Reference-format words: statistics + hash only.
-		std::vector<uint32_t> ref_words;
+		ref_words.clear();
 		st.pool.CompileReference(bn.evaluator, ref_words, inverse.empty() ? nullptr : inverse.data());
 		ref_words.push_back(0); // OpcodeT::Stop (:1381)
 		uint32_t child_mask = 0;
@@ -709,6 +780,9 @@ struct Flattener
 		const size_t spare = jobs.empty() ? 0 : 2 * (jobs[0].interp.size() + jobs[0].tree.size()) + 4096;
 		model.interp.reserve(interp_words + spare);
 		model.tree.reserve(tree_words + spare);
+		// tens of MB of fresh memory: huge pages take a dozen faults where small ones take thousands (a third of this pass)
+		AdviseHugePages(model.interp.data(), model.interp.capacity() * 4);
+		AdviseHugePages(model.tree.data(), model.tree.capacity() * 4);
 		model.interp.resize(interp_words);
 		model.tree.resize(tree_words);
 		auto copy = [&](size_t begin, size_t end)
