@@ -23,7 +23,7 @@ std::string g_error;
 
 // One context per device for the life of the process: a context owns the scratch arena, the result caches and the
 // page-locked staging memory, and making them costs more than an export (first export on a fresh context 220 ms, on a
-// kept one 80 ms for seaside_town 1024^3).  `busy` serialises the callers (a context is used by one thread at a time).
+// kept one under 30 ms for seaside_town 1024^3).  `busy` serialises the callers (a context is used by one thread at a time).
 struct KeptContext
 {
 	tg_context* context = nullptr;
