@@ -612,18 +612,27 @@ struct Flattener
 	{
 		const Subtree* st;
 		int32_t index;
-		std::vector<uint32_t> interp; // starts table (long programs) + program, whole quads
-		uint32_t interp_program_at = 0; // word offset of the program inside `interp`
-		std::vector<uint32_t> tree;
+		// where the node's streams sit in its batch's buffers (kGenerateBatch consecutive nodes share a pair of buffers: one
+		// allocation and one copy per batch instead of two per node)
+		uint32_t interp_at = 0, interp_size = 0; // starts table (long programs) + program, whole quads
+		uint32_t interp_program_at = 0;          // word offset of the program inside that
+		uint32_t tree_at = 0, tree_size = 0;
 		uint32_t flags = 0, flops = 0;
 		int max_slots = 0;
 		uint64_t ref_words = 0, stack = 0, node_hash = 0;
 		uint32_t material = kMixedMaterial;
 	};
 
+	struct Batch
+	{
+		std::vector<uint32_t> interp, tree;
+	};
+	static constexpr size_t kGenerateBatch = 64;
+
 	FlatModel& model;
 	std::vector<Mat4> inverse;     // CompiledInverseMatrix of every brush of the model, by node index
 	std::vector<Job> jobs;         // one per octree node, pre-order
+	std::vector<Batch> batches;    // streams of jobs [b * kGenerateBatch, (b + 1) * kGenerateBatch), in job order
 	int max_slots = 0;
 	bool reference_stats = true;
 
@@ -689,8 +698,9 @@ struct Flattener
 		return self;
 	}
 
-	// Pass 2: one node's programs and reference-format statistics (thread-safe: touches only its job).
-	void Generate(Job& job) const
+	// Pass 2: one node's programs and reference-format statistics (thread-safe: touches only its job and -- in job order,
+	// from the one thread that works through the batch -- its batch).
+	void Generate(Job& job, Batch& batch) const
 	{
 		const Subtree& st = *job.st;
 		const BuildNode& bn = st.nodes[job.index];
@@ -705,22 +715,23 @@ struct Flattener
 		job.flags = interp.cullable ? kNodeCullable : 0u;
 		const size_t count = interp.starts.size();
 		job.flags |= uint32_t(std::min<size_t>(count, (1u << 24) - 1u)) << kNodeCountShift;
+		job.interp_at = uint32_t(batch.interp.size());
 		if (count >= kLongProgram)
 		{
 			// Long programs carry a table of their instructions' quad offsets right in front of them (padded to whole
 			// quads): K0 evaluates such a program with a group of threads, each fetching its own instructions directly.
 			job.flags |= kNodeLong;
-			job.interp.reserve(count + 4 + program.size());
-			for (size_t i = 0; i < count; ++i) job.interp.push_back(interp.starts[i]);
-			while (job.interp.size() % 4 != 0) job.interp.push_back(0);
+			for (size_t i = 0; i < count; ++i) batch.interp.push_back(interp.starts[i]);
+			while ((batch.interp.size() - job.interp_at) % 4 != 0) batch.interp.push_back(0);
 		}
-		job.interp_program_at = uint32_t(job.interp.size());
-		job.interp.reserve(job.interp.size() + program.size());
-		job.interp.insert(job.interp.end(), program.begin(), program.end());
-		job.tree.reserve(program.size());
-		StreamGen tree(st.pool, job.tree, true);
+		job.interp_program_at = uint32_t(batch.interp.size()) - job.interp_at;
+		batch.interp.insert(batch.interp.end(), program.begin(), program.end());
+		job.interp_size = uint32_t(batch.interp.size()) - job.interp_at;
+		job.tree_at = uint32_t(batch.tree.size());
+		StreamGen tree(st.pool, batch.tree, true);
 		tree.Gen(bn.evaluator);
 		tree.Finish();
+		job.tree_size = uint32_t(batch.tree.size()) - job.tree_at;
 		job.flops = interp.flops;
 		job.max_slots = tree.max_slots;
 		job.stack = st.pool.nodes[bn.evaluator].stack_size;
@@ -749,20 +760,24 @@ struct Flattener
 	// hash is FNV-1a over the nodes' own hashes in pre-order.
 	template <class Pool> void Assemble(Pool* tasks)
 	{
-		std::vector<size_t> interp_at(jobs.size()), tree_at(jobs.size());
 		model.node_material.assign(jobs.size(), kMixedMaterial);
+		std::vector<size_t> interp_base(batches.size()), tree_base(batches.size());
 		size_t interp_words = model.interp.size(), tree_words = model.tree.size();
+		for (size_t b = 0; b < batches.size(); ++b)
+		{
+			interp_base[b] = interp_words;
+			tree_base[b] = tree_words;
+			interp_words += batches[b].interp.size();
+			tree_words += batches[b].tree.size();
+		}
 		FlatModelStats& s = model.stats;
 		for (size_t i = 0; i < jobs.size(); ++i)
 		{
 			const Job& job = jobs[i];
 			FlatNode& fn = model.nodes[i];
-			interp_at[i] = interp_words;
-			tree_at[i] = tree_words;
-			fn.interp_offset = uint32_t(interp_words) + job.interp_program_at;
-			fn.tree_offset = uint32_t(tree_words);
-			interp_words += job.interp.size();
-			tree_words += job.tree.size();
+			const size_t b = i / kGenerateBatch;
+			fn.interp_offset = uint32_t(interp_base[b]) + job.interp_at + job.interp_program_at;
+			fn.tree_offset = uint32_t(tree_base[b]) + job.tree_at;
 			fn.flags = job.flags;
 			fn.flops = job.flops;
 			model.node_material[i] = job.material;
@@ -777,7 +792,7 @@ struct Flattener
 			s.hash = Fnv(s.hash, &job.node_hash, 8);
 		}
 		// room for what BuildFlatModel appends afterwards (the unpruned programs are about the root node's size)
-		const size_t spare = jobs.empty() ? 0 : 2 * (jobs[0].interp.size() + jobs[0].tree.size()) + 4096;
+		const size_t spare = jobs.empty() ? 0 : 2 * size_t(jobs[0].interp_size + jobs[0].tree_size) + 4096;
 		model.interp.reserve(interp_words + spare);
 		model.tree.reserve(tree_words + spare);
 		// tens of MB of fresh memory: huge pages take a dozen faults where small ones take thousands (a third of this pass)
@@ -787,25 +802,25 @@ struct Flattener
 		model.tree.resize(tree_words);
 		auto copy = [&](size_t begin, size_t end)
 		{
-			for (size_t i = begin; i < end; ++i)
+			for (size_t b = begin; b < end; ++b)
 			{
-				Job& job = jobs[i];
-				if (!job.interp.empty()) std::memcpy(model.interp.data() + interp_at[i], job.interp.data(), job.interp.size() * 4);
-				if (!job.tree.empty()) std::memcpy(model.tree.data() + tree_at[i], job.tree.data(), job.tree.size() * 4);
-				std::vector<uint32_t>().swap(job.interp);
-				std::vector<uint32_t>().swap(job.tree);
+				Batch& batch = batches[b];
+				if (!batch.interp.empty()) std::memcpy(model.interp.data() + interp_base[b], batch.interp.data(), batch.interp.size() * 4);
+				if (!batch.tree.empty()) std::memcpy(model.tree.data() + tree_base[b], batch.tree.data(), batch.tree.size() * 4);
+				std::vector<uint32_t>().swap(batch.interp);
+				std::vector<uint32_t>().swap(batch.tree);
 			}
 		};
-		const size_t batch = 256;
-		const size_t batches = (jobs.size() + batch - 1) / batch;
-		if (tasks && batches > 1)
+		const size_t group = 8; // batches per task
+		const size_t groups = (batches.size() + group - 1) / group;
+		if (tasks && groups > 1)
 		{
-			std::atomic<int> pending{ int(batches) };
-			for (size_t b = 0; b < batches; ++b)
+			std::atomic<int> pending{ int(groups) };
+			for (size_t g = 0; g < groups; ++g)
 			{
-				tasks->Submit([&copy, &pending, b, batch, this]()
+				tasks->Submit([&copy, &pending, g, group, this]()
 				{
-					copy(b * batch, std::min(jobs.size(), (b + 1) * batch));
+					copy(g * group, std::min(batches.size(), (g + 1) * group));
 					pending.fetch_sub(1, std::memory_order_acq_rel);
 				});
 			}
@@ -813,7 +828,7 @@ struct Flattener
 		}
 		else
 		{
-			copy(0, jobs.size());
+			copy(0, batches.size());
 		}
 	}
 };
@@ -914,7 +929,7 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 		if (trace_host) std::fprintf(stderr, "octree build: %s at %.1f ms\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e3);
 	};
 	out.stats.hash = 0xCBF29CE484222325ull;
-	Flattener flattener{ out, {}, {}, 0, reference_stats };
+	Flattener flattener{ out, {}, {}, {}, 0, reference_stats };
 	out.stats.reference_done = reference_stats;
 	flattener.inverse.resize(tree.pool.nodes.size());
 	for (size_t i = 0; i < tree.pool.nodes.size(); ++i)
@@ -937,8 +952,9 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 	{
 		// programs of all nodes, in batches on the task pool (or here, serially)
 		std::vector<Flattener::Job>& jobs = flattener.jobs;
-		const size_t batch = 64;
+		const size_t batch = Flattener::kGenerateBatch;
 		const size_t batches = (jobs.size() + batch - 1) / batch;
+		flattener.batches.resize(batches);
 		if (tasks)
 		{
 			std::atomic<int> pending{ int(batches) };
@@ -949,7 +965,7 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 				{
 					try
 					{
-						for (size_t i = b * batch; i < std::min(jobs.size(), (b + 1) * batch); ++i) flattener.Generate(jobs[i]);
+						for (size_t i = b * batch; i < std::min(jobs.size(), (b + 1) * batch); ++i) flattener.Generate(jobs[i], flattener.batches[b]);
 					}
 					catch (...)
 					{
@@ -967,7 +983,7 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 		}
 		else
 		{
-			for (Flattener::Job& job : jobs) flattener.Generate(job);
+			for (size_t i = 0; i < jobs.size(); ++i) flattener.Generate(jobs[i], flattener.batches[i / batch]);
 		}
 		lap("generate");
 		flattener.Assemble(tasks);
