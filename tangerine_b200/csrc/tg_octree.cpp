@@ -998,11 +998,22 @@ bool BuildFlatModel(const Tree& tree, float target_size, int threads, FlatModel&
 	{
 		// The attribute pass works through the vertices grouped by octree node; with the costly programs first its
 		// persistent warps finish on short batches (the tail of a slab's attribute kernels is a fixed cost per slab).
-		std::vector<uint64_t> by_cost(out.nodes.size()); // (~flops, index): ascending = costliest first, ties in node order
-		for (size_t i = 0; i < by_cost.size(); ++i) by_cost[i] = (uint64_t(~out.nodes[i].flops) << 32) | uint64_t(i);
-		std::sort(by_cost.begin(), by_cost.end());
-		out.node_rank.resize(by_cost.size());
-		for (size_t r = 0; r < by_cost.size(); ++r) out.node_rank[uint32_t(by_cost[r])] = uint32_t(r);
+		// order by (~flops, index) ascending = costliest first, ties in node order: a stable radix sort of the indices by
+		// ~flops, three passes of 11 bits (std::sort of the pairs was a tenth of a large octree's flattening)
+		const size_t count = out.nodes.size();
+		std::vector<uint32_t> order(count), other(count);
+		for (size_t i = 0; i < count; ++i) order[i] = uint32_t(i);
+		for (int pass = 0; pass < 3; ++pass)
+		{
+			const int shift = pass * 11;
+			size_t buckets[2049] = { 0 };
+			for (size_t i = 0; i < count; ++i) buckets[((~out.nodes[order[i]].flops >> shift) & 2047u) + 1]++;
+			for (int b = 0; b < 2048; ++b) buckets[b + 1] += buckets[b];
+			for (size_t i = 0; i < count; ++i) other[buckets[(~out.nodes[order[i]].flops >> shift) & 2047u]++] = order[i];
+			order.swap(other);
+		}
+		out.node_rank.resize(count);
+		for (size_t r = 0; r < count; ++r) out.node_rank[order[r]] = uint32_t(r);
 	}
 
 	lap("node ranks");
