@@ -197,6 +197,11 @@ TG_API int tg_ray_cast(tg_model* model, const float* rays, uint64_t count, int m
  * the bits of their first occurrence; both have room for `count` entries, *out_unique tells how many vertices there are. */
 TG_API int tg_weld(tg_context* context, const float* vertices, uint64_t count, float* out_vertices4, uint32_t* out_indices, uint64_t* out_unique);
 
+/* Diagnostics for the tests: FNV-1a hashes of the five device tables tg_model_create would upload for this tree (octree
+ * nodes, interpreter stream, tree stream, regions, node cost ranks), built on `host_threads` threads (live != 0: the live
+ * mesher's octree).  The tables must not depend on the thread count, and host-side refactors must not change them. */
+TG_API int tg_debug_tables_hash(const tg_tree* tree, float octree_target_size, int host_threads, int live, uint64_t out_hashes[5]);
+
 /* Self-check used by the tests: the culling pass evaluates long programs cooperatively (a warp or a block per point,
  * parallel fold); this runs every long program of the model at 9 points within `reach` of its octree node's pivot both
  * ways and returns { probes, disagreements of the block form, disagreements of the warp form } -- the last two must be 0. */

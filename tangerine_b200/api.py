@@ -147,6 +147,7 @@ def lib():
         "tg_model_create_live": (vp, [vp, vp, C.c_float, i32]),
         "tg_live_grid": (i32, [vp, C.c_float, C.POINTER(Grid)]),
         "tg_rearm": (i32, [vp]),
+        "tg_debug_tables_hash": (i32, [vp, C.c_float, i32, i32, C.POINTER(u64)]),
         "tg_weld": (i32, [vp, C.POINTER(C.c_float), u64, C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(u64)]),
         "tg_tree_octree_stats": (i32, [vp, C.c_float, i32, C.POINTER(ModelStats)]),
         "tg_tree_octree_stats_live": (i32, [vp, C.c_float, i32, C.POINTER(ModelStats)]),
@@ -348,6 +349,12 @@ class Tree:
 
     def save(self, path):
         _check(lib().tg_tree_save(self.h, os.fsencode(path)))
+
+    def tables_hash(self, threads=0, live=False, target_size=0.25):
+        """FNV-1a of the five device tables (nodes, interpreter stream, tree stream, regions, node ranks) as hex strings."""
+        out = (C.c_uint64 * 5)()
+        _check(lib().tg_debug_tables_hash(self.h, target_size, threads, 1 if live else 0, out))
+        return ["%016x" % v for v in out]
 
     def plan_slabs(self, grid, ranks, target_size=0.25):
         """(cuts, per-layer cost estimate) of a multi-GPU export of this tree over `ranks` devices (host only)."""

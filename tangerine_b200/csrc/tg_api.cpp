@@ -826,6 +826,30 @@ int tg_weld(tg_context* context, const float* vertices, uint64_t count, float* o
 }
 TG_CATCH_STATUS
 
+int tg_debug_tables_hash(const tg_tree* tree, float target_size, int host_threads, int live, uint64_t out_hashes[5]) try
+{
+	TG_REQUIRE_TREE(tree);
+	if (!out_hashes) return Fail(TG_ERR_INVALID, "null argument");
+	if (!(target_size > 0.0f)) target_size = 0.25f;
+	FlatModel flat;
+	std::string error;
+	if (!BuildFlatModel(tree->tree, target_size, host_threads, flat, error, false, live == 0)) return Fail(TG_ERR_INVALID, error);
+	auto fnv = [](const void* data, size_t bytes)
+	{
+		uint64_t h = 0xCBF29CE484222325ull;
+		const unsigned char* c = static_cast<const unsigned char*>(data);
+		for (size_t i = 0; i < bytes; ++i) h = (h ^ c[i]) * 0x100000001B3ull;
+		return h;
+	};
+	out_hashes[0] = fnv(flat.nodes.data(), flat.nodes.size() * sizeof(FlatNode));
+	out_hashes[1] = fnv(flat.interp.data(), flat.interp.size() * 4);
+	out_hashes[2] = fnv(flat.tree.data(), flat.tree.size() * 4);
+	out_hashes[3] = fnv(flat.regions.data(), flat.regions.size() * sizeof(FlatRegion));
+	out_hashes[4] = fnv(flat.node_rank.data(), flat.node_rank.size() * 4);
+	return TG_OK;
+}
+TG_CATCH_STATUS
+
 int tg_rearm(tg_context* context) try
 {
 	if (!context) return Fail(TG_ERR_INVALID, "null context");

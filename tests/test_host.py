@@ -269,3 +269,18 @@ def test_cli_info_and_loud_failure_without_a_device(tmp_path, capsys):
         assert "no CPU fallback" in capsys.readouterr().err
         assert not (tmp_path / "x.ply").exists()
 
+
+
+@pytest.mark.parametrize("name", ["basic_thing", "seaside_town", "gear", "kitchen_sink", "stencil_test", "cones", "scale", "flower", "color-cube", "synthetic200"])
+def test_device_tables_do_not_depend_on_threads_or_refactors(name):
+    """The five tables tg_model_create uploads (octree nodes, both instruction streams, regions, node ranks), hashed on
+    the host: the same on 1, 3 and 8 threads, for the export's octree and the live mesher's, and equal to
+    tests/golden/tables.json -- the tables every GPU parity test of this round ran on, so a host-side change of the
+    builder or the flattener that alters them shows up without a device."""
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tables.json")) as f:
+        want = json.load(f)[name]
+    tree = T.Tree.load(O.model_path(name))
+    for threads in (1, 3, 8):
+        assert tree.tables_hash(threads, live=False) == want["export"]
+        assert tree.tables_hash(threads, live=True) == want["live"]
